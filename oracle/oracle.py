@@ -1,0 +1,231 @@
+"""ctypes front-end for the two CPU checkers (oracle_api.h).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, ``__graft_entry__.smoke()`` and the
+``cpu_baseline`` / ``--impl reference`` legs of bench.py -- never by appleseed_b200/.
+
+``Oracle("orc")``   -> oracle/liboracle.so      (self-contained restatement, "port")
+``Oracle("asref")`` -> oracle/_ref/libasref.so  (the reference's own headers, "reference")
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from appleseed_b200.scene import HIT_DTYPE, CRays, CSceneDesc, RayBatch, SceneDesc
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_PATHS = {
+    "orc": os.path.join(_HERE, "liboracle.so"),
+    "asref": os.path.join(_HERE, "_ref", "libasref.so"),
+}
+
+
+class TriangleTreeView(C.Structure):
+    _fields_ = [
+        ("nodes", C.c_void_p),
+        ("node_bboxes", C.c_void_p),
+        ("leaf_data", C.c_void_p),
+        ("triangle_keys", C.c_void_p),
+        ("node_count", C.c_uint64),
+        ("node_bbox_count", C.c_uint64),
+        ("leaf_data_size", C.c_uint64),
+        ("triangle_key_count", C.c_uint64),
+        ("static_triangle_count", C.c_uint64),
+        ("moving_triangle_count", C.c_uint64),
+    ]
+
+
+class AssemblyTreeView(C.Structure):
+    _fields_ = [
+        ("nodes", C.c_void_p),
+        ("item_assembly_instance", C.c_void_p),
+        ("item_tree", C.c_void_p),
+        ("node_count", C.c_uint64),
+        ("item_count", C.c_uint64),
+    ]
+
+
+class Counters(C.Structure):
+    _fields_ = [
+        ("rays", C.c_uint64),
+        ("assembly_nodes_visited", C.c_uint64),
+        ("instances_visited", C.c_uint64),
+        ("triangle_nodes_visited", C.c_uint64),
+        ("triangles_tested", C.c_uint64),
+        ("hits", C.c_uint64),
+    ]
+
+    def as_dict(self):
+        return {k: int(getattr(self, k)) for k, _ in self._fields_}
+
+
+def build(which: str = "all") -> None:
+    """Compile the checkers (``make -C oracle``).  ``_ref`` is only rebuilt where the
+    reference tree exists; elsewhere the prebuilt library that travelled is used."""
+    target = {"all": "all", "orc": "liboracle.so", "asref": "ref"}[which]
+    subprocess.run(["make", "-s", "-C", _HERE, target], check=True)
+
+
+def available(prefix: str) -> bool:
+    return os.path.exists(_PATHS[prefix])
+
+
+def _view_bytes(ptr, nbytes):
+    if not ptr or nbytes == 0:
+        return np.zeros(0, dtype=np.uint8)
+    buf = (C.c_uint8 * nbytes).from_address(ptr)
+    return np.frombuffer(buf, dtype=np.uint8).copy()
+
+
+class Oracle:
+    def __init__(self, prefix: str = "orc"):
+        if prefix not in _PATHS:
+            raise ValueError(prefix)
+        path = _PATHS[prefix]
+        if not os.path.exists(path):
+            if prefix == "orc":
+                build("orc")
+            else:
+                raise FileNotFoundError(path)
+        self.prefix = prefix
+        self.lib = C.CDLL(path)
+        L, p = self.lib, prefix
+        self._create = getattr(L, p + "_scene_create")
+        self._create.restype = C.c_void_p
+        self._create.argtypes = [C.POINTER(CSceneDesc)]
+        self._destroy = getattr(L, p + "_scene_destroy")
+        self._destroy.argtypes = [C.c_void_p]
+        self._tree_count = getattr(L, p + "_tree_count")
+        self._tree_count.argtypes = [C.c_void_p]
+        self._tree_count.restype = C.c_int
+        self._get_tt = getattr(L, p + "_get_triangle_tree")
+        self._get_tt.argtypes = [C.c_void_p, C.c_int, C.POINTER(TriangleTreeView)]
+        self._get_at = getattr(L, p + "_get_assembly_tree")
+        self._get_at.argtypes = [C.c_void_p, C.POINTER(AssemblyTreeView)]
+        self._trace = getattr(L, p + "_trace")
+        self._trace.argtypes = [C.c_void_p, C.POINTER(CRays), C.c_size_t, C.c_void_p, C.c_int, C.POINTER(Counters)]
+        self._probe = getattr(L, p + "_trace_probe")
+        self._probe.argtypes = [C.c_void_p, C.POINTER(CRays), C.c_size_t, C.c_void_p, C.c_int, C.POINTER(Counters)]
+        if prefix == "orc":
+            self._two = L.orc_two_nearest
+            self._two.argtypes = [C.c_void_p, C.POINTER(CRays), C.c_size_t, C.c_void_p, C.c_void_p, C.c_int]
+        for name, argt, rest in (
+            ("_kat_ray_triangle", [C.c_void_p] * 5 + [C.c_double, C.c_double, C.c_void_p], C.c_int),
+            ("_kat_ray_triangle_bool", [C.c_void_p] * 5 + [C.c_double, C.c_double], C.c_int),
+            ("_kat_ray_aabb", [C.c_void_p] * 4 + [C.c_double, C.c_double, C.c_void_p], C.c_int),
+            ("_kat_ray_info", [C.c_void_p] * 3, None),
+        ):
+            f = getattr(L, p + name)
+            f.argtypes = argt
+            f.restype = rest
+
+    # -- scenes -------------------------------------------------------------------------------
+
+    def scene(self, desc: SceneDesc) -> "OracleScene":
+        return OracleScene(self, desc)
+
+    # -- known-answer entry points ------------------------------------------------------------
+
+    @staticmethod
+    def _v(a):
+        return np.ascontiguousarray(a, dtype=np.float64)
+
+    def kat_ray_triangle(self, v0, v1, v2, org, dir, tmin=0.0, tmax=np.finfo(np.float64).max):
+        a = [self._v(x) for x in (v0, v1, v2, org, dir)]
+        tuv = np.zeros(3)
+        hit = getattr(self.lib, self.prefix + "_kat_ray_triangle")(
+            *[x.ctypes.data for x in a], tmin, tmax, tuv.ctypes.data)
+        return bool(hit), tuv
+
+    def kat_ray_triangle_bool(self, v0, v1, v2, org, dir, tmin=0.0, tmax=np.finfo(np.float64).max):
+        a = [self._v(x) for x in (v0, v1, v2, org, dir)]
+        return bool(getattr(self.lib, self.prefix + "_kat_ray_triangle_bool")(
+            *[x.ctypes.data for x in a], tmin, tmax))
+
+    def kat_ray_aabb(self, bmin, bmax, org, dir, tmin=0.0, tmax=np.finfo(np.float64).max):
+        a = [self._v(x) for x in (bmin, bmax, org, dir)]
+        t = np.zeros(1)
+        hit = getattr(self.lib, self.prefix + "_kat_ray_aabb")(*[x.ctypes.data for x in a], tmin, tmax, t.ctypes.data)
+        return bool(hit), float(t[0])
+
+    def kat_ray_info(self, dir):
+        d = self._v(dir)
+        rcp = np.zeros(3)
+        sgn = np.zeros(3, dtype=np.uint32)
+        getattr(self.lib, self.prefix + "_kat_ray_info")(d.ctypes.data, rcp.ctypes.data, sgn.ctypes.data)
+        return rcp, sgn
+
+
+class OracleScene:
+    def __init__(self, oracle: Oracle, desc: SceneDesc):
+        self.oracle = oracle
+        self.desc = desc
+        self._cdesc, self._keep = desc.to_c()
+        self.handle = oracle._create(C.byref(self._cdesc))
+        if not self.handle:
+            raise RuntimeError("oracle scene_create failed")
+
+    def close(self):
+        if self.handle:
+            self.oracle._destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def tree_count(self) -> int:
+        return self.oracle._tree_count(self.handle)
+
+    def triangle_tree(self, index: int) -> dict:
+        """Copy of one reference-format triangle tree (the bytes an in-tree flattener sees)."""
+        v = TriangleTreeView()
+        self.oracle._get_tt(self.handle, index, C.byref(v))
+        return {
+            "nodes": _view_bytes(v.nodes, v.node_count * 128),
+            "node_bboxes": _view_bytes(v.node_bboxes, v.node_bbox_count * 48).view(np.float64),
+            "leaf_data": _view_bytes(v.leaf_data, v.leaf_data_size),
+            "triangle_keys": _view_bytes(v.triangle_keys, v.triangle_key_count * 12),
+            "static_triangle_count": int(v.static_triangle_count),
+            "moving_triangle_count": int(v.moving_triangle_count),
+        }
+
+    def assembly_tree(self) -> dict:
+        v = AssemblyTreeView()
+        self.oracle._get_at(self.handle, C.byref(v))
+        return {
+            "nodes": _view_bytes(v.nodes, v.node_count * 128),
+            "item_assembly_instance": _view_bytes(v.item_assembly_instance, v.item_count * 4).view(np.uint32),
+            "item_tree": _view_bytes(v.item_tree, v.item_count * 4).view(np.uint32),
+        }
+
+    def trace(self, rays: RayBatch, threads: int = 1, counters: bool = False):
+        n = len(rays)
+        out = np.zeros(n, dtype=HIT_DTYPE)
+        cr = rays.to_c()
+        cnt = Counters()
+        self.oracle._trace(self.handle, C.byref(cr), n, out.ctypes.data, threads, C.byref(cnt))
+        return (out, cnt.as_dict()) if counters else out
+
+    def trace_probe(self, rays: RayBatch, threads: int = 1, counters: bool = False):
+        n = len(rays)
+        out = np.zeros(n, dtype=np.uint8)
+        cr = rays.to_c()
+        cnt = Counters()
+        self.oracle._probe(self.handle, C.byref(cr), n, out.ctypes.data, threads, C.byref(cnt))
+        return (out, cnt.as_dict()) if counters else out
+
+    def two_nearest(self, rays: RayBatch, threads: int = 1):
+        n = len(rays)
+        t1 = np.zeros(n)
+        t2 = np.zeros(n)
+        cr = rays.to_c()
+        self.oracle._two(self.handle, C.byref(cr), n, t1.ctypes.data, t2.ctypes.data, threads)
+        return t1, t2
