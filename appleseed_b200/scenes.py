@@ -328,3 +328,60 @@ def hit_points_and_normals(desc: SceneDesc, rays: RayBatch, hits: np.ndarray) ->
     flip = np.sum(nrm * rays.dir[idx], axis=1) > 0.0
     nrm[flip] *= -1.0
     return mask, pts, nrm
+
+
+# ---------------------------------------------------------------------------------------------
+# C1: Cornell box
+# ---------------------------------------------------------------------------------------------
+
+def _golden_dir() -> str:
+    import os
+    return os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def load_cornell() -> dict:
+    import os
+    return dict(np.load(os.path.join(_golden_dir(), "cornell_box.npz")))
+
+
+def scene_c1() -> SceneDesc:
+    """The 8 meshes (32 triangles) of the reference's Cornell box, one assembly, one identity
+    assembly instance; object-instance transforms are the scene file's diag(0.00100000004749700)."""
+    fx = load_cornell()
+    n = len(fx["names"])
+    meshes = [Mesh(fx["vertices_%d" % i], fx["triangles_%d" % i]) for i in range(n)]
+    ois = [ObjectInstance(i, fx["transform_%d" % i]) for i in range(n)]
+    return SceneDesc(meshes, [Assembly(ois)], [AssemblyInstance(0)])
+
+
+def camera_rays(width: int, height: int, camera_matrix: np.ndarray, film=(0.025, 0.025), focal: float = 0.035,
+                flags: int = VIS_CAMERA) -> RayBatch:
+    """``PinholeCamera::spawn_ray`` (pinholecamera.cpp:159-195) through pixel centres:
+    org = translation of the camera matrix; dir = normalize(M3x3 . -ndc_to_camera(ndc)) with
+    ``ndc_to_camera`` = ((0.5 - x) * film_w, (y - 0.5) * film_h, focal) (perspectivecamera.cpp:204-211)."""
+    m = np.asarray(camera_matrix, dtype=np.float64).reshape(4, 4)
+    px, py = np.meshgrid(np.arange(width), np.arange(height), indexing="xy")
+    ndx = (px.reshape(-1) + 0.5) / width
+    ndy = (py.reshape(-1) + 0.5) / height
+    cam = -np.stack([(0.5 - ndx) * film[0], (ndy - 0.5) * film[1], np.full_like(ndx, focal)], axis=1)
+    d = _normalize(cam @ m[:3, :3].T)
+    n = d.shape[0]
+    org = np.broadcast_to(m[:3, 3], (n, 3)).copy()
+    return RayBatch(org, d, np.zeros(n), np.full(n, DBL_MAX), flags=np.full(n, flags, dtype=np.uint32))
+
+
+def rays_c1_primary() -> RayBatch:
+    fx = load_cornell()
+    w, h = (int(x) for x in fx["resolution"])
+    return camera_rays(w, h, fx["camera_matrix"], tuple(fx["film_dimensions"]), float(fx["focal_length"]))
+
+
+def rays_c1_ao(desc: SceneDesc, primary: RayBatch, hits: np.ndarray, seed: int = 0xA55EED) -> Tuple[np.ndarray, RayBatch]:
+    """One cosine-weighted ambient-occlusion probe per primary hit
+    (renderer/kernel/shading/ambientocclusion.h:56-113): tmin = 0, tmax = 1.0 (ao_surface_shader
+    default max_distance), flags ProbeRay, origin offset 1e-6 * scene diagonal along the normal."""
+    mask, pts, nrm = hit_points_and_normals(desc, primary, hits)
+    lo, hi = scene_bbox(desc)
+    diag = float(np.linalg.norm(hi - lo))
+    rays = bounce_rays(pts, nrm, seed, flags=VIS_PROBE, tmax=1.0, offset=1.0e-6 * diag)
+    return mask, rays

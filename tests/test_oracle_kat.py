@@ -1,0 +1,106 @@
+"""Pins the CPU oracle(s) to the reference's own known-answer tests (CPU only)."""
+import numpy as np
+import pytest
+
+import kat
+
+
+@pytest.fixture(params=["orc", "asref"])
+def oracle(request):
+    return request.getfixturevalue(request.param)
+
+
+@pytest.mark.parametrize("case", kat.RAY_TRIANGLE, ids=[c[0] for c in kat.RAY_TRIANGLE])
+def test_ray_triangle(oracle, case):
+    _, org, d, tmin, tmax, expect_hit, tuv = case
+    hit, got = oracle.kat_ray_triangle(*kat.TRI, org, d, tmin, tmax)
+    assert hit == expect_hit
+    assert oracle.kat_ray_triangle_bool(*kat.TRI, org, d, tmin, tmax) == expect_hit
+    if tuv is not None:
+        for g, e in zip(got, tuv):
+            if e is not None:
+                assert abs(g - e) <= 1e-14
+
+
+@pytest.mark.parametrize("case", kat.RAY_AABB, ids=[c[0] for c in kat.RAY_AABB])
+def test_ray_aabb(oracle, case):
+    _, bmin, bmax, org, d, tmin, tmax, expect_hit, dist = case
+    hit, t = oracle.kat_ray_aabb(bmin, bmax, org, d, tmin, tmax)
+    assert hit == expect_hit
+    if dist is not None:
+        assert abs(t - dist) <= 1e-14
+
+
+def test_ray_info(oracle):
+    d, rcp, sgn = kat.RAY_INFO
+    got_rcp, got_sgn = oracle.kat_ray_info(d)
+    assert got_rcp[0] == rcp[0] and np.isposinf(got_rcp[1]) and got_rcp[2] == rcp[2]
+    assert list(got_sgn) == sgn
+
+
+def test_negative_zero_direction_has_sign_zero(oracle):
+    # ray.h:313-321: sgn = (1 / dir >= 0); 1 / -0.0 = -inf -> 0.
+    rcp, sgn = oracle.kat_ray_info([-0.0, 1.0, 1.0])
+    assert np.isneginf(rcp[0]) and sgn[0] == 0
+
+
+def test_tracer_quad_hit_at_two(oracle):
+    # test_tracer.cpp:421-439: quad instanced at x = 2, ray (0,0,0) -> +x hits at distance 2.
+    s = oracle.scene(kat.tracer_scene([2.0]))
+    h = s.trace(kat.x_ray())
+    assert h["prim_type"][0] == 2 and h["t"][0] == 2.0 and h["assembly_instance"][0] == 0
+    # :441-456 opaque occluder => probe reports a hit.
+    assert s.trace_probe(kat.x_ray())[0] == 1
+
+
+def test_tracer_two_quads_nearest_then_unoccluded(oracle):
+    # test_tracer.cpp:954-981: planes at x = 2 and x = 4: nearest is 2.0; a probe from beyond the
+    # first plane to the second with tmax = dist * (1 - 1e-6) (tracer.h:249-259) is unoccluded.
+    s = oracle.scene(kat.tracer_scene([2.0, 4.0]))
+    h = s.trace(kat.x_ray())
+    assert h["t"][0] == 2.0 and h["assembly_instance"][0] == 0
+    from appleseed_b200.scene import RayBatch
+    probe = RayBatch(np.array([[2.0 + 1e-9, 0.0, 0.0]]), np.array([[1.0, 0.0, 0.0]]), 0.0, 2.0 * (1.0 - 1.0e-6))
+    assert s.trace_probe(probe)[0] == 0
+
+
+def test_tracer_scaled_assembly_instance(oracle):
+    # test_tracer.cpp:1016-1059: the assembly instance scaled by 0.5 => distance 1.0; t is shared
+    # between world and instance space because the local direction is not renormalised.
+    s = oracle.scene(kat.tracer_scene([2.0], scale=0.5))
+    h = s.trace(kat.x_ray())
+    assert h["prim_type"][0] == 2 and abs(h["t"][0] - 1.0) <= 1e-15
+
+
+def test_intersector_empty_bbox(oracle):
+    # test_intersector.cpp:116-147.
+    s = oracle.scene(kat.empty_bbox_scene())
+    h = s.trace(kat.empty_bbox_ray())
+    assert h["prim_type"][0] == 0 and h["assembly_instance"][0] == 0xFFFFFFFF and h["t"][0] == 2.0
+    assert s.trace_probe(kat.empty_bbox_ray())[0] == 0
+
+
+def test_interval_is_tmin_inclusive_tmax_exclusive(oracle):
+    # ray.h:49-53 through the whole two-level path.
+    s = oracle.scene(kat.tracer_scene([2.0]))
+    from appleseed_b200.scene import RayBatch
+    r = RayBatch(np.zeros((2, 3)), np.array([[1.0, 0, 0], [1.0, 0, 0]]), np.array([2.0, 0.0]), np.array([10.0, 2.0]))
+    h = s.trace(r)
+    assert h["prim_type"][0] == 2 and h["prim_type"][1] == 0
+    p = s.trace_probe(r)
+    assert list(p) == [1, 0]
+
+
+def test_visibility_flags(oracle):
+    # assemblytree.cpp:629 (instance flags) and triangletree.cpp:1389 (object-instance flags).
+    from appleseed_b200.scene import (VIS_CAMERA, VIS_SHADOW, Assembly, AssemblyInstance, ObjectInstance, SceneDesc)
+    from appleseed_b200 import scenes
+    desc = SceneDesc(
+        [kat.unit_quad()],
+        [Assembly([ObjectInstance(0, vis_flags=VIS_CAMERA)]), Assembly([ObjectInstance(0)])],
+        [AssemblyInstance(0, scenes.translation(2, 0, 0)), AssemblyInstance(1, scenes.translation(3, 0, 0), vis_flags=VIS_SHADOW)])
+    s = oracle.scene(desc)
+    assert s.trace(kat.x_ray(flags=VIS_CAMERA))["t"][0] == 2.0          # quad 0 visible to camera rays
+    h = s.trace(kat.x_ray(flags=VIS_SHADOW))                              # only instance 1 visible
+    assert h["t"][0] == 3.0 and h["assembly_instance"][0] == 1
+    assert s.trace(kat.x_ray(flags=1 << 5))["prim_type"][0] == 0          # diffuse rays see nothing
