@@ -1,0 +1,442 @@
+//
+// api.cu -- the extern "C" layer of include/asgpu.h.
+//
+// Host side of the drop-in boundary: owns the device blob, validates arguments, launches the
+// kernels of kernels.cu, and implements the host-buffer entry points as a chunked three-stream
+// pipeline (H2D copy / kernel / D2H copy of consecutive chunks overlap).  No torch types, no
+// exceptions across the ABI.
+//
+
+#include "../../include/asgpu.h"
+#include "flatten.h"
+#include "kernels.h"
+#include "tree_builder.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace asgpu;
+
+namespace
+{
+
+thread_local std::string g_last_error;
+
+int fail(const int code, const std::string& message)
+{
+    g_last_error = message;
+    return code;
+}
+
+int fail_cuda(const cudaError_t err, const char* what)
+{
+    g_last_error = std::string(what) + ": " + cudaGetErrorString(err);
+    return ASGPU_E_CUDA;
+}
+
+#define ASGPU_CUDA(call, what) do { const cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail_cuda(e_, what); } while (0)
+
+const size_t HostChunkRays = size_t(1) << 20;
+const int HostStreams = 3;
+const uint64_t QueueRing = 256;
+
+struct Staging
+{
+    cudaStream_t    stream = nullptr;
+    double*         org = nullptr;
+    double*         dir = nullptr;
+    double*         tmin = nullptr;
+    double*         tmax = nullptr;
+    float*          time_absolute = nullptr;
+    float*          time_normalized = nullptr;
+    uint32_t*       flags = nullptr;
+    asgpu_hit*      hits = nullptr;
+    uint8_t*        occluded = nullptr;
+    unsigned long long* queue = nullptr;
+};
+
+}   // anonymous namespace
+
+struct asgpu_trees
+{
+    HostTrees trees;
+};
+
+struct asgpu_scene
+{
+    int                 device = 0;
+    int                 sm_count = 0;
+    uint8_t*            blob = nullptr;         // device
+    bool                owns_blob = true;
+    size_t              blob_bytes = 0;
+    BlobHeader          header;
+    SceneView           view;
+    unsigned long long* queue = nullptr;        // device, ring of QueueRing cursors (one per launch)
+    uint64_t            queue_next = 0;
+    unsigned long long* counters = nullptr;     // device, asgpu_counters layout (first 6 words)
+    uint64_t            launches = 0;
+    std::mutex          mutex;
+    Staging             staging[HostStreams];
+    bool                staging_ready = false;
+};
+
+namespace
+{
+
+void make_view(asgpu_scene* s)
+{
+    s->view.blob = s->blob;
+    s->view.trees = s->header.trees;
+    s->view.items = s->header.items;
+    s->view.top_nodes = s->header.top_nodes;
+    s->view.top_wnodes = s->header.top_wnodes;
+    s->view.top_witems = s->header.top_witems;
+    s->view.tree_count = s->header.tree_count;
+    s->view.item_count = s->header.item_count;
+    s->view.top_node_count = s->header.top_node_count;
+    s->view.top_wnode_count = s->header.top_wnode_count;
+}
+
+int init_device_side(asgpu_scene* s)
+{
+    ASGPU_CUDA(cudaSetDevice(s->device), "cudaSetDevice");
+    cudaDeviceProp prop;
+    ASGPU_CUDA(cudaGetDeviceProperties(&prop, s->device), "cudaGetDeviceProperties");
+    s->sm_count = prop.multiProcessorCount;
+    ASGPU_CUDA(cudaMalloc(&s->queue, QueueRing * sizeof(unsigned long long)), "cudaMalloc(queue)");
+    ASGPU_CUDA(cudaMalloc(&s->counters, sizeof(asgpu_counters)), "cudaMalloc(counters)");
+    ASGPU_CUDA(cudaMemset(s->counters, 0, sizeof(asgpu_counters)), "cudaMemset(counters)");
+    return ASGPU_OK;
+}
+
+void free_staging(asgpu_scene* s)
+{
+    for (Staging& st : s->staging)
+    {
+        cudaFree(st.org); cudaFree(st.dir); cudaFree(st.tmin); cudaFree(st.tmax);
+        cudaFree(st.time_absolute); cudaFree(st.time_normalized); cudaFree(st.flags);
+        cudaFree(st.hits); cudaFree(st.occluded); cudaFree(st.queue);
+        if (st.stream) cudaStreamDestroy(st.stream);
+        st = Staging();
+    }
+    s->staging_ready = false;
+}
+
+int ensure_staging(asgpu_scene* s)
+{
+    if (s->staging_ready) return ASGPU_OK;
+    for (Staging& st : s->staging)
+    {
+        ASGPU_CUDA(cudaStreamCreateWithFlags(&st.stream, cudaStreamNonBlocking), "cudaStreamCreate");
+        ASGPU_CUDA(cudaMalloc(&st.org, HostChunkRays * 24), "cudaMalloc(staging)");
+        ASGPU_CUDA(cudaMalloc(&st.dir, HostChunkRays * 24), "cudaMalloc(staging)");
+        ASGPU_CUDA(cudaMalloc(&st.tmin, HostChunkRays * 8), "cudaMalloc(staging)");
+        ASGPU_CUDA(cudaMalloc(&st.tmax, HostChunkRays * 8), "cudaMalloc(staging)");
+        ASGPU_CUDA(cudaMalloc(&st.time_absolute, HostChunkRays * 4), "cudaMalloc(staging)");
+        ASGPU_CUDA(cudaMalloc(&st.time_normalized, HostChunkRays * 4), "cudaMalloc(staging)");
+        ASGPU_CUDA(cudaMalloc(&st.flags, HostChunkRays * 4), "cudaMalloc(staging)");
+        ASGPU_CUDA(cudaMalloc(&st.hits, HostChunkRays * sizeof(asgpu_hit)), "cudaMalloc(staging)");
+        ASGPU_CUDA(cudaMalloc(&st.occluded, HostChunkRays), "cudaMalloc(staging)");
+        ASGPU_CUDA(cudaMalloc(&st.queue, 64), "cudaMalloc(staging)");
+    }
+    s->staging_ready = true;
+    return ASGPU_OK;
+}
+
+int check_trace_args(asgpu_scene* scene, const asgpu_rays* rays, const size_t n, const void* out, const uint32_t flags, bool& wide)
+{
+    if (!scene) return fail(ASGPU_E_INVALID, "null scene");
+    if (n == 0) return ASGPU_OK;
+    if (!rays || !rays->org || !rays->dir || !rays->tmin || !rays->tmax) return fail(ASGPU_E_INVALID, "ray batch misses a mandatory array");
+    if (!out) return fail(ASGPU_E_INVALID, "null output array");
+    wide = (flags & ASGPU_TRACE_EXACT) == 0;
+    if (wide && !(scene->header.flags & ASGPU_SCENE_WIDE)) return fail(ASGPU_E_INVALID, "scene was created without the wide layout");
+    if (!wide && !(scene->header.flags & ASGPU_SCENE_EXACT)) return fail(ASGPU_E_INVALID, "scene was created without the exact layout");
+    return ASGPU_OK;
+}
+
+int trace_device(asgpu_scene* scene, const asgpu_rays* rays, const size_t n, asgpu_hit* hits, uint8_t* occluded,
+                 const bool any_hit, const uint32_t flags, unsigned long long* queue, void* stream)
+{
+    bool wide = true;
+    const int rc = check_trace_args(scene, rays, n, any_hit ? static_cast<const void*>(occluded) : static_cast<const void*>(hits), flags, wide);
+    if (rc != ASGPU_OK || n == 0) return rc;
+    ASGPU_CUDA(cudaSetDevice(scene->device), "cudaSetDevice");
+    const int err = launch_trace(scene->view, *rays, n, hits, occluded, any_hit, wide, queue,
+                                 (flags & ASGPU_TRACE_COUNTERS) ? scene->counters : nullptr, nullptr, scene->sm_count, stream);
+    if (err != 0) return fail_cuda(static_cast<cudaError_t>(err), "kernel launch");
+    ++scene->launches;
+    return ASGPU_OK;
+}
+
+int trace_host(asgpu_scene* scene, const asgpu_rays* rays, const size_t n, asgpu_hit* hits, uint8_t* occluded,
+               const bool any_hit, const uint32_t flags)
+{
+    bool wide = true;
+    int rc = check_trace_args(scene, rays, n, any_hit ? static_cast<const void*>(occluded) : static_cast<const void*>(hits), flags, wide);
+    if (rc != ASGPU_OK || n == 0) return rc;
+    std::lock_guard<std::mutex> lock(scene->mutex);
+    ASGPU_CUDA(cudaSetDevice(scene->device), "cudaSetDevice");
+    rc = ensure_staging(scene);
+    if (rc != ASGPU_OK) return rc;
+
+    size_t chunk_index = 0;
+    for (size_t begin = 0; begin < n; begin += HostChunkRays, ++chunk_index)
+    {
+        const size_t count = std::min(HostChunkRays, n - begin);
+        Staging& st = scene->staging[chunk_index % HostStreams];
+        // Stream order guarantees the previous use of this staging slot has drained.
+        ASGPU_CUDA(cudaMemcpyAsync(st.org, rays->org + begin * 3, count * 24, cudaMemcpyHostToDevice, st.stream), "H2D org");
+        ASGPU_CUDA(cudaMemcpyAsync(st.dir, rays->dir + begin * 3, count * 24, cudaMemcpyHostToDevice, st.stream), "H2D dir");
+        ASGPU_CUDA(cudaMemcpyAsync(st.tmin, rays->tmin + begin, count * 8, cudaMemcpyHostToDevice, st.stream), "H2D tmin");
+        ASGPU_CUDA(cudaMemcpyAsync(st.tmax, rays->tmax + begin, count * 8, cudaMemcpyHostToDevice, st.stream), "H2D tmax");
+        asgpu_rays dev;
+        dev.org = st.org; dev.dir = st.dir; dev.tmin = st.tmin; dev.tmax = st.tmax;
+        dev.time_absolute = nullptr; dev.time_normalized = nullptr; dev.flags = nullptr;
+        if (rays->time_absolute)
+        {
+            ASGPU_CUDA(cudaMemcpyAsync(st.time_absolute, rays->time_absolute + begin, count * 4, cudaMemcpyHostToDevice, st.stream), "H2D time");
+            dev.time_absolute = st.time_absolute;
+        }
+        if (rays->time_normalized)
+        {
+            ASGPU_CUDA(cudaMemcpyAsync(st.time_normalized, rays->time_normalized + begin, count * 4, cudaMemcpyHostToDevice, st.stream), "H2D time");
+            dev.time_normalized = st.time_normalized;
+        }
+        if (rays->flags)
+        {
+            ASGPU_CUDA(cudaMemcpyAsync(st.flags, rays->flags + begin, count * 4, cudaMemcpyHostToDevice, st.stream), "H2D flags");
+            dev.flags = st.flags;
+        }
+        const int err = launch_trace(scene->view, dev, count, st.hits, st.occluded, any_hit, wide, st.queue,
+                                     (flags & ASGPU_TRACE_COUNTERS) ? scene->counters : nullptr, nullptr, scene->sm_count, st.stream);
+        if (err != 0) return fail_cuda(static_cast<cudaError_t>(err), "kernel launch");
+        ++scene->launches;
+        if (any_hit)
+            ASGPU_CUDA(cudaMemcpyAsync(occluded + begin, st.occluded, count, cudaMemcpyDeviceToHost, st.stream), "D2H occluded");
+        else
+            ASGPU_CUDA(cudaMemcpyAsync(hits + begin, st.hits, count * sizeof(asgpu_hit), cudaMemcpyDeviceToHost, st.stream), "D2H hits");
+    }
+    for (Staging& st : scene->staging)
+        ASGPU_CUDA(cudaStreamSynchronize(st.stream), "cudaStreamSynchronize");
+    return ASGPU_OK;
+}
+
+asgpu_scene* adopt_blob_image(const std::vector<uint8_t>& image, const int device)
+{
+    asgpu_scene* s = new (std::nothrow) asgpu_scene();
+    if (!s) { fail(ASGPU_E_NOMEM, "out of host memory"); return nullptr; }
+    s->device = device;
+    std::memcpy(&s->header, image.data(), sizeof(BlobHeader));
+    s->blob_bytes = image.size();
+    if (init_device_side(s) != ASGPU_OK) { asgpu_scene_destroy(s); return nullptr; }
+    cudaError_t e = cudaMalloc(&s->blob, s->blob_bytes);
+    if (e != cudaSuccess) { fail_cuda(e, "cudaMalloc(blob)"); asgpu_scene_destroy(s); return nullptr; }
+    e = cudaMemcpy(s->blob, image.data(), s->blob_bytes, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { fail_cuda(e, "cudaMemcpy(blob)"); asgpu_scene_destroy(s); return nullptr; }
+    make_view(s);
+    return s;
+}
+
+}   // anonymous namespace
+
+extern "C" {
+
+const char* asgpu_last_error(void) { return g_last_error.c_str(); }
+
+int asgpu_version(void) { return ASGPU_VERSION; }
+
+// ---- host builder -------------------------------------------------------------------------
+
+asgpu_trees* asgpu_trees_build(const asgpu_scene_desc* desc, int threads)
+{
+    if (!desc) { fail(ASGPU_E_INVALID, "null scene description"); return nullptr; }
+    asgpu_trees* t = new (std::nothrow) asgpu_trees();
+    if (!t) { fail(ASGPU_E_NOMEM, "out of host memory"); return nullptr; }
+    std::string error;
+    bool ok = false;
+    try { ok = build_host_trees(*desc, threads, t->trees, error); }
+    catch (const std::exception& e) { error = e.what(); }
+    if (!ok) { fail(ASGPU_E_INVALID, error); delete t; return nullptr; }
+    return t;
+}
+
+void asgpu_trees_destroy(asgpu_trees* trees) { delete trees; }
+
+int asgpu_trees_triangle_tree_count(const asgpu_trees* trees)
+{
+    return trees ? static_cast<int>(trees->trees.triangle_trees.size()) : fail(ASGPU_E_INVALID, "null trees");
+}
+
+int asgpu_trees_get_triangle_tree(const asgpu_trees* trees, int index, asgpu_triangle_tree_view* out)
+{
+    if (!trees || !out) return fail(ASGPU_E_INVALID, "null argument");
+    if (index < 0 || index >= static_cast<int>(trees->trees.triangle_trees.size())) return fail(ASGPU_E_INVALID, "triangle tree index out of range");
+    const HostTriangleTree& t = *trees->trees.triangle_trees[index];
+    out->nodes = t.nodes.data();
+    out->node_bboxes = t.node_bboxes.empty() ? nullptr : t.node_bboxes.data();
+    out->leaf_data = t.leaf_data.empty() ? nullptr : t.leaf_data.data();
+    out->triangle_keys = t.keys.empty() ? nullptr : t.keys.data();
+    out->node_count = t.nodes.size();
+    out->node_bbox_count = t.node_bboxes.size() / 6;
+    out->leaf_data_size = t.leaf_data.size();
+    out->triangle_key_count = t.keys.size();
+    out->static_triangle_count = t.static_triangle_count;
+    out->moving_triangle_count = t.moving_triangle_count;
+    return ASGPU_OK;
+}
+
+int asgpu_trees_get_assembly_tree(const asgpu_trees* trees, asgpu_assembly_tree_view* out)
+{
+    if (!trees || !out) return fail(ASGPU_E_INVALID, "null argument");
+    const HostAssemblyTree& t = trees->trees.assembly_tree;
+    out->nodes = t.nodes.data();
+    out->items = t.items.empty() ? nullptr : t.items.data();
+    out->node_count = t.nodes.size();
+    out->item_count = t.items.size();
+    return ASGPU_OK;
+}
+
+double asgpu_trees_build_seconds(const asgpu_trees* trees) { return trees ? trees->trees.build_seconds : 0.0; }
+
+// ---- GPU scene ----------------------------------------------------------------------------
+
+asgpu_scene* asgpu_scene_create(
+    const asgpu_triangle_tree_view* triangle_trees,
+    uint32_t                        triangle_tree_count,
+    const asgpu_assembly_tree_view* assembly_tree,
+    uint32_t                        flags,
+    int                             device)
+{
+    if (!assembly_tree) { fail(ASGPU_E_INVALID, "null assembly tree"); return nullptr; }
+    std::vector<uint8_t> image;
+    std::string error;
+    int rc;
+    try { rc = flatten_scene(triangle_trees, triangle_tree_count, *assembly_tree, flags ? flags : ASGPU_SCENE_DEFAULT, image, error); }
+    catch (const std::exception& e) { rc = ASGPU_E_NOMEM; error = e.what(); }
+    if (rc != ASGPU_OK) { fail(rc, error); return nullptr; }
+    return adopt_blob_image(image, device);
+}
+
+asgpu_scene* asgpu_scene_create_from_desc(const asgpu_scene_desc* desc, uint32_t flags, int device, int threads)
+{
+    asgpu_trees* trees = asgpu_trees_build(desc, threads);
+    if (!trees) return nullptr;
+    std::vector<asgpu_triangle_tree_view> views(trees->trees.triangle_trees.size());
+    for (size_t i = 0; i < views.size(); ++i) asgpu_trees_get_triangle_tree(trees, static_cast<int>(i), &views[i]);
+    asgpu_assembly_tree_view top;
+    asgpu_trees_get_assembly_tree(trees, &top);
+    asgpu_scene* scene = asgpu_scene_create(views.empty() ? nullptr : views.data(), static_cast<uint32_t>(views.size()), &top, flags, device);
+    asgpu_trees_destroy(trees);
+    return scene;
+}
+
+void asgpu_scene_destroy(asgpu_scene* scene)
+{
+    if (!scene) return;
+    cudaSetDevice(scene->device);
+    free_staging(scene);
+    if (scene->owns_blob) cudaFree(scene->blob);
+    cudaFree(scene->queue);
+    cudaFree(scene->counters);
+    delete scene;
+}
+
+size_t asgpu_scene_blob_size(const asgpu_scene* scene) { return scene ? scene->blob_bytes : 0; }
+
+const void* asgpu_scene_blob_device_ptr(const asgpu_scene* scene) { return scene ? scene->blob : nullptr; }
+
+asgpu_scene* asgpu_scene_import_blob(const void* device_blob, size_t size, int device, int adopt)
+{
+    if (!device_blob || size < sizeof(BlobHeader)) { fail(ASGPU_E_INVALID, "blob too small"); return nullptr; }
+    asgpu_scene* s = new (std::nothrow) asgpu_scene();
+    if (!s) { fail(ASGPU_E_NOMEM, "out of host memory"); return nullptr; }
+    s->device = device;
+    s->blob_bytes = size;
+    if (init_device_side(s) != ASGPU_OK) { asgpu_scene_destroy(s); return nullptr; }
+    // Only the header and the small tables are inspected on the host.
+    cudaError_t e = cudaMemcpy(&s->header, device_blob, sizeof(BlobHeader), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { fail_cuda(e, "cudaMemcpy(blob header)"); asgpu_scene_destroy(s); return nullptr; }
+    if (s->header.magic != BlobMagic || s->header.version != BlobVersion || s->header.total_bytes != size)
+    { fail(ASGPU_E_INVALID, "blob header mismatch"); asgpu_scene_destroy(s); return nullptr; }
+    if (adopt)
+    {
+        s->blob = const_cast<uint8_t*>(static_cast<const uint8_t*>(device_blob));
+        s->owns_blob = false;
+    }
+    else
+    {
+        e = cudaMalloc(&s->blob, size);
+        if (e != cudaSuccess) { fail_cuda(e, "cudaMalloc(blob)"); asgpu_scene_destroy(s); return nullptr; }
+        e = cudaMemcpy(s->blob, device_blob, size, cudaMemcpyDeviceToDevice);
+        if (e != cudaSuccess) { fail_cuda(e, "cudaMemcpy(blob)"); asgpu_scene_destroy(s); return nullptr; }
+    }
+    make_view(s);
+    return s;
+}
+
+int asgpu_scene_get_info(const asgpu_scene* scene, asgpu_scene_info* out)
+{
+    if (!scene || !out) return fail(ASGPU_E_INVALID, "null argument");
+    const BlobHeader& h = scene->header;
+    out->blob_bytes = scene->blob_bytes;
+    out->triangle_tree_count = h.tree_count;
+    out->instance_count = h.item_count;
+    out->triangle_count = h.triangle_count;
+    out->moving_triangle_count = h.moving_triangle_count;
+    out->binary_node_count = h.binary_node_count;
+    out->wide_node_count = h.wide_node_count;
+    out->binary_node_bytes = h.binary_node_bytes;
+    out->wide_node_bytes = h.wide_node_bytes;
+    out->triangle_bytes = h.triangle_bytes;
+    out->flags = h.flags;
+    out->reserved = 0;
+    return ASGPU_OK;
+}
+
+// ---- tracing ------------------------------------------------------------------------------
+
+int asgpu_trace(asgpu_scene* scene, const asgpu_rays* rays, size_t n, asgpu_hit* hits, uint32_t flags, void* stream)
+{
+    return trace_device(scene, rays, n, hits, nullptr, false, flags, scene ? scene->queue + (scene->queue_next++ % QueueRing) : nullptr, stream);
+}
+
+int asgpu_trace_probe(asgpu_scene* scene, const asgpu_rays* rays, size_t n, uint8_t* occluded, uint32_t flags, void* stream)
+{
+    return trace_device(scene, rays, n, nullptr, occluded, true, flags, scene ? scene->queue + (scene->queue_next++ % QueueRing) : nullptr, stream);
+}
+
+int asgpu_trace_host(asgpu_scene* scene, const asgpu_rays* rays, size_t n, asgpu_hit* hits, uint32_t flags)
+{
+    return trace_host(scene, rays, n, hits, nullptr, false, flags);
+}
+
+int asgpu_trace_probe_host(asgpu_scene* scene, const asgpu_rays* rays, size_t n, uint8_t* occluded, uint32_t flags)
+{
+    return trace_host(scene, rays, n, nullptr, occluded, true, flags);
+}
+
+int asgpu_get_counters(asgpu_scene* scene, asgpu_counters* out, int reset)
+{
+    if (!scene || !out) return fail(ASGPU_E_INVALID, "null argument");
+    ASGPU_CUDA(cudaSetDevice(scene->device), "cudaSetDevice");
+    ASGPU_CUDA(cudaDeviceSynchronize(), "cudaDeviceSynchronize");
+    std::memset(out, 0, sizeof(*out));
+    ASGPU_CUDA(cudaMemcpy(out, scene->counters, 6 * sizeof(uint64_t), cudaMemcpyDeviceToHost), "cudaMemcpy(counters)");
+    out->kernel_launches = scene->launches;
+    if (reset)
+    {
+        ASGPU_CUDA(cudaMemset(scene->counters, 0, sizeof(asgpu_counters)), "cudaMemset(counters)");
+        scene->launches = 0;
+    }
+    return ASGPU_OK;
+}
+
+}   // extern "C"

@@ -1,0 +1,744 @@
+//
+// flatten.cpp -- host flattener: the reference's bvh::Tree arrays -> GPU blob.
+//
+// Input is exactly what appleseed's own classes hold (include/asgpu.h, *_view structs):
+//   bvh::Tree::m_nodes / m_node_bboxes           foundation/math/bvh/bvh_tree.h:77-78
+//   TriangleTree::m_triangle_keys / m_leaf_data  renderer/kernel/intersection/triangletree.h:116-125
+//   AssemblyTree nodes + items                   renderer/kernel/intersection/assemblytree.h:98-134
+// Leaf payloads are decoded as TriangleLeafVisitor reads them (triangletree.cpp:1363-1383,
+// layout written by triangleencoder.cpp:72-103).
+//
+// Output: see gpu_layout.h.  The EXACT layout is a lossless re-packing.  The WIDE layout
+// collapses each binary tree into 8-wide nodes (greedy largest-area expansion), orders children
+// into octant slots, stores child boxes quantised to 8 bits per plane ROUNDED OUTWARD, and
+// re-orders triangle records so that one node's leaves are contiguous.  Because every wide box
+// contains the binary boxes it replaces, a traversal that tests wide boxes conservatively can only
+// reach MORE leaves than the reference traversal, never fewer.
+//
+
+#include "flatten.h"
+#include "as_format.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <limits>
+
+namespace asgpu
+{
+
+namespace
+{
+
+struct FBox
+{
+    float lo[3], hi[3];
+    void reset() { for (int a = 0; a < 3; ++a) { lo[a] = std::numeric_limits<float>::max(); hi[a] = -std::numeric_limits<float>::max(); } }
+    void grow(const FBox& b) { for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], b.lo[a]); hi[a] = std::max(hi[a], b.hi[a]); } }
+    void grow(const float p[3]) { for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], p[a]); hi[a] = std::max(hi[a], p[a]); } }
+    bool valid() const { return lo[0] <= hi[0] && lo[1] <= hi[1] && lo[2] <= hi[2]; }
+    float half_area() const
+    {
+        if (!valid()) return 0.0f;
+        const float x = hi[0] - lo[0], y = hi[1] - lo[1], z = hi[2] - lo[2];
+        return x * y + x * z + y * z;
+    }
+};
+
+inline float float_below(const double v)    // largest float <= v
+{
+    float f = static_cast<float>(v);
+    if (static_cast<double>(f) > v) f = std::nextafterf(f, -std::numeric_limits<float>::infinity());
+    return f;
+}
+
+inline float float_above(const double v)    // smallest float >= v
+{
+    float f = static_cast<float>(v);
+    if (static_cast<double>(f) < v) f = std::nextafterf(f, std::numeric_limits<float>::infinity());
+    return f;
+}
+
+class BlobWriter
+{
+  public:
+    explicit BlobWriter(std::vector<uint8_t>& bytes) : m_bytes(bytes) { m_bytes.clear(); }
+
+    // Appends `size` bytes at the next SectionAlign boundary; returns the offset.
+    uint64_t append(const void* data, const size_t size)
+    {
+        const uint64_t offset = (m_bytes.size() + SectionAlign - 1) / SectionAlign * SectionAlign;
+        m_bytes.resize(offset + size, 0);
+        if (size) std::memcpy(m_bytes.data() + offset, data, size);
+        return offset;
+    }
+
+    template <typename T> uint64_t append(const std::vector<T>& v)
+    {
+        return append(v.empty() ? nullptr : v.data(), v.size() * sizeof(T));
+    }
+
+    void finish()
+    {
+        m_bytes.resize((m_bytes.size() + SectionAlign - 1) / SectionAlign * SectionAlign, 0);
+    }
+
+  private:
+    std::vector<uint8_t>& m_bytes;
+};
+
+//
+// EXACT layout of one triangle tree.
+//
+
+struct ExactTree
+{
+    std::vector<BNodeF>     bnodes;
+    std::vector<MNode>      mnodes;
+    std::vector<MBox>       mboxes;
+    std::vector<TriRecord>  tris;
+    std::vector<float>      poses;
+    std::vector<HitKey>     keys;
+    uint64_t                moving = 0;
+};
+
+int decode_tree(const asgpu_triangle_tree_view& v, ExactTree& out, std::string& error)
+{
+    if (v.node_count == 0 || !v.nodes) { error = "triangle tree without nodes"; return ASGPU_E_INVALID; }
+    if (v.node_count >= 0xFFFFFFFFull || v.triangle_key_count >= 0xFFFFFFFFull) { error = "triangle tree too large"; return ASGPU_E_UNSUPPORTED; }
+    const AsNode* nodes = static_cast<const AsNode*>(v.nodes);
+    const AsTriangleKey* keys = static_cast<const AsTriangleKey*>(v.triangle_keys);
+    const bool motion = v.moving_triangle_count > 0;
+
+    out.bnodes.resize(v.node_count);
+    if (motion) out.mnodes.resize(v.node_count);
+    out.tris.resize(v.triangle_key_count);
+    out.keys.resize(v.triangle_key_count);
+    for (uint64_t i = 0; i < v.triangle_key_count; ++i)
+    {
+        out.keys[i].object_instance_index = keys[i].object_instance_index;
+        out.keys[i].triangle_index = keys[i].triangle_index;
+    }
+
+    if (motion)
+    {
+        out.mboxes.resize(v.node_bbox_count);
+        for (uint64_t i = 0; i < v.node_bbox_count; ++i)
+            for (int k = 0; k < 6; ++k)
+            {
+                const double d = v.node_bboxes[i * 6 + k];
+                const float f = static_cast<float>(d);
+                if (static_cast<double>(f) != d) { error = "motion box is not float-representable"; return ASGPU_E_UNSUPPORTED; }
+                out.mboxes[i].v[k] = f;
+            }
+    }
+
+    std::vector<uint8_t> seen(v.triangle_key_count, 0);
+    for (uint64_t n = 0; n < v.node_count; ++n)
+    {
+        const AsNode& src = nodes[n];
+        BNodeF& dst = out.bnodes[n];
+        std::memset(&dst, 0, sizeof(dst));
+        dst.index = src.index;
+        dst.item_count = src.item_count;
+
+        if (src.interior())
+        {
+            if (uint64_t(src.index) + 1 >= v.node_count) { error = "child node index out of range"; return ASGPU_E_INVALID; }
+            for (int k = 0; k < 12; ++k)
+            {
+                const float f = static_cast<float>(src.bbox[k]);
+                // The reference builds triangle-tree boxes in float and widens them
+                // (triangletree.cpp:543, bvh_builder.h:193-204).
+                if (static_cast<double>(f) != src.bbox[k]) { error = "triangle tree box is not float-representable"; return ASGPU_E_UNSUPPORTED; }
+                dst.box[k] = f;
+            }
+            if (motion)
+            {
+                MNode& m = out.mnodes[n];
+                m.left_index = src.left_bbox_index; m.left_count = src.left_bbox_count;
+                m.right_index = src.right_bbox_index; m.right_count = src.right_bbox_count;
+                if ((m.left_count > 1 && uint64_t(m.left_index) + m.left_count > v.node_bbox_count) ||
+                    (m.right_count > 1 && uint64_t(m.right_index) + m.right_count > v.node_bbox_count) ||
+                    m.left_count == 0 || m.right_count == 0)
+                { error = "motion box range out of range"; return ASGPU_E_INVALID; }
+            }
+            continue;
+        }
+
+        if (uint64_t(src.index) + src.item_count > v.triangle_key_count) { error = "leaf item range out of range"; return ASGPU_E_INVALID; }
+
+        // Leaf payload: in the node when its first u32 is ~0, else at m_leaf_data[offset].
+        const uint8_t* user = src.user_data();
+        uint32_t offset;
+        std::memcpy(&offset, user, 4);
+        const uint8_t* p;
+        const uint8_t* limit;
+        if (src.item_count == 0) { p = limit = user; }
+        else if (offset == 0xFFFFFFFFu) { p = user + 4; limit = user + AsNodeUserDataSize; }
+        else
+        {
+            if (offset >= v.leaf_data_size) { error = "leaf data offset out of range"; return ASGPU_E_INVALID; }
+            p = v.leaf_data + offset; limit = v.leaf_data + v.leaf_data_size;
+        }
+
+        for (uint32_t j = 0; j < src.item_count; ++j)
+        {
+            const uint32_t slot = src.index + j;
+            if (seen[slot]) { error = "triangle slot referenced twice"; return ASGPU_E_INVALID; }
+            seen[slot] = 1;
+            if (p + 8 > limit) { error = "truncated leaf payload"; return ASGPU_E_INVALID; }
+            uint32_t vis, msc;
+            std::memcpy(&vis, p, 4); std::memcpy(&msc, p + 4, 4); p += 8;
+            TriRecord& tri = out.tris[slot];
+            std::memset(&tri, 0, sizeof(tri));
+            tri.vis_flags = vis;
+            tri.ref_slot = slot;
+            if (msc == 0)
+            {
+                if (p + AsTriangleBytes > limit) { error = "truncated leaf payload"; return ASGPU_E_INVALID; }
+                std::memcpy(tri.v0, p, AsTriangleBytes); p += AsTriangleBytes;
+                tri.motion = 0;
+            }
+            else
+            {
+                const size_t bytes = (size_t(msc) + 1) * AsPoseBytes;
+                if (p + bytes > limit) { error = "truncated leaf payload"; return ASGPU_E_INVALID; }
+                if (out.poses.size() + bytes / 4 >= 0xFFFFFFFEull) { error = "pose pool too large"; return ASGPU_E_UNSUPPORTED; }
+                tri.motion = static_cast<uint32_t>(out.poses.size()) + 1;
+                std::memcpy(&tri.v0[0], &msc, 4);
+                const size_t base = out.poses.size();
+                out.poses.resize(base + bytes / 4);
+                std::memcpy(out.poses.data() + base, p, bytes); p += bytes;
+                ++out.moving;
+            }
+        }
+    }
+    for (uint64_t i = 0; i < v.triangle_key_count; ++i)
+        if (!seen[i]) { error = "triangle slot not referenced by any leaf"; return ASGPU_E_INVALID; }
+    if ((out.moving > 0) != motion) { error = "moving_triangle_count does not match the leaf payloads"; return ASGPU_E_INVALID; }
+    return ASGPU_OK;
+}
+
+// Conservative all-time float box of a moving triangle: union of its poses.
+FBox triangle_box(const ExactTree& t, const uint32_t slot)
+{
+    FBox b; b.reset();
+    const TriRecord& tri = t.tris[slot];
+    if (tri.motion == 0)
+    {
+        const float v1[3] = { tri.v0[0] + tri.e0[0], tri.v0[1] + tri.e0[1], tri.v0[2] + tri.e0[2] };
+        const float v2[3] = { tri.v0[0] + tri.e1[0], tri.v0[1] + tri.e1[1], tri.v0[2] + tri.e1[2] };
+        b.grow(tri.v0); b.grow(v1); b.grow(v2);
+        // v0 + e is rounded; pad by an ulp-scale margin so the box is a true bound.
+        for (int a = 0; a < 3; ++a)
+        {
+            b.lo[a] = std::nextafterf(b.lo[a], -std::numeric_limits<float>::infinity());
+            b.hi[a] = std::nextafterf(b.hi[a], std::numeric_limits<float>::infinity());
+        }
+    }
+    else
+    {
+        uint32_t msc; std::memcpy(&msc, &tri.v0[0], 4);
+        const float* p = t.poses.data() + (tri.motion - 1);
+        for (uint32_t k = 0; k < (msc + 1) * 3; ++k) b.grow(p + k * 3);
+        // Interpolated vertices are computed in float with two roundings (triangletree.cpp:1438-1445).
+        for (int a = 0; a < 3; ++a)
+        {
+            const float m = std::max(std::fabs(b.lo[a]), std::fabs(b.hi[a])) * 4.0e-7f + std::numeric_limits<float>::min();
+            b.lo[a] -= m; b.hi[a] += m;
+        }
+    }
+    return b;
+}
+
+//
+// WIDE layout: generic collapse of a binary tree whose leaves hold item ranges.
+//
+
+struct BinaryView
+{
+    uint64_t                    node_count;
+    std::vector<uint32_t>       child;          // first child or InteriorMark^... (leaf: InteriorMark)
+    std::vector<uint32_t>       first, count;   // leaf item range
+    std::vector<FBox>           box;            // conservative all-time box of each node
+};
+
+struct WideOut
+{
+    std::vector<WNode>      nodes;
+    std::vector<uint32_t>   leaf_order;     // wide item order -> original item (slot) index
+};
+
+struct Element
+{
+    bool        is_node;        // binary interior node, else an item range
+    uint32_t    node;           // binary node index (is_node)
+    uint32_t    first, count;   // item range (!is_node)
+    FBox        box;
+};
+
+void make_element(const BinaryView& bv, const uint32_t node, Element& e)
+{
+    e.box = bv.box[node];
+    if (bv.child[node] != InteriorMark) { e.is_node = true; e.node = node; e.first = e.count = 0; }
+    else { e.is_node = false; e.node = 0; e.first = bv.first[node]; e.count = bv.count[node]; }
+}
+
+bool splittable(const Element& e, const uint32_t leaf_cap) { return e.is_node || e.count > leaf_cap; }
+
+void split_element(const BinaryView& bv, const Element& e, Element& a, Element& b)
+{
+    if (e.is_node)
+    {
+        make_element(bv, bv.child[e.node], a);
+        make_element(bv, bv.child[e.node] + 1, b);
+    }
+    else
+    {
+        // An over-full leaf (max_leaf_size > cap, or a range the SAH refused to split) is halved;
+        // both halves keep the leaf's box.
+        a = e; b = e;
+        a.count = e.count / 2;
+        b.first = e.first + a.count;
+        b.count = e.count - a.count;
+    }
+}
+
+int quantise_node(WNode& w, const Element* kids, const int n, const int* slot_of, std::string& error)
+{
+    FBox nb; nb.reset();
+    for (int i = 0; i < n; ++i) nb.grow(kids[i].box);
+    if (!nb.valid()) { for (int a = 0; a < 3; ++a) nb.lo[a] = nb.hi[a] = 0.0f; }
+
+    for (int a = 0; a < 3; ++a)
+    {
+        w.origin[a] = nb.lo[a];
+        const double extent = double(nb.hi[a]) - double(nb.lo[a]);
+        int e = -126;
+        if (extent > 0.0)
+        {
+            e = static_cast<int>(std::ceil(std::log2(extent / 255.0)));
+            while (std::ceil(extent / std::ldexp(1.0, e)) > 255.0) ++e;
+            while (e > -126 && std::ceil(extent / std::ldexp(1.0, e - 1)) <= 255.0) --e;
+        }
+        if (e < -126) e = -126;
+        if (e > 127) { error = "scene extent too large to quantise"; return ASGPU_E_UNSUPPORTED; }
+        w.exp[a] = static_cast<uint8_t>(e + 127);
+        const double scale = std::ldexp(1.0, e);
+        for (int i = 0; i < n; ++i)
+        {
+            const int s = slot_of[i];
+            if (!kids[i].box.valid()) { w.qlo[a][s] = 255; w.qhi[a][s] = 0; continue; }
+            double lo = std::floor((double(kids[i].box.lo[a]) - double(nb.lo[a])) / scale);
+            double hi = std::ceil((double(kids[i].box.hi[a]) - double(nb.lo[a])) / scale);
+            lo = std::min(255.0, std::max(0.0, lo));
+            hi = std::min(255.0, std::max(lo, hi));
+            w.qlo[a][s] = static_cast<uint8_t>(lo);
+            w.qhi[a][s] = static_cast<uint8_t>(hi);
+            // Outward-rounding invariants.
+            if (double(nb.lo[a]) + lo * scale > double(kids[i].box.lo[a]) || double(nb.lo[a]) + hi * scale < double(kids[i].box.hi[a]))
+            { error = "internal error: quantised box does not contain its child"; return ASGPU_E_INVALID; }
+        }
+    }
+    return ASGPU_OK;
+}
+
+int collapse(const BinaryView& bv, const uint32_t leaf_cap, WideOut& out, std::string& error)
+{
+    out.nodes.clear();
+    out.leaf_order.clear();
+
+    struct Pending { uint32_t wide_index; Element root; };
+    std::vector<Pending> queue;
+    {
+        WNode blank; std::memset(&blank, 0, sizeof(blank));
+        out.nodes.push_back(blank);
+        Pending p; p.wide_index = 0; make_element(bv, 0, p.root);
+        queue.push_back(p);
+    }
+
+    for (size_t qi = 0; qi < queue.size(); ++qi)
+    {
+        const Pending cur = queue[qi];
+        Element kids[8];
+        int n = 0;
+
+        if (splittable(cur.root, leaf_cap))
+        {
+            split_element(bv, cur.root, kids[0], kids[1]);
+            n = 2;
+            while (n < 8)
+            {
+                int best = -1; float best_area = -1.0f;
+                for (int i = 0; i < n; ++i)
+                    if (splittable(kids[i], leaf_cap))
+                    {
+                        const float area = kids[i].box.half_area();
+                        if (area > best_area) { best_area = area; best = i; }
+                    }
+                if (best < 0) break;
+                Element a, b;
+                split_element(bv, kids[best], a, b);
+                kids[best] = a;
+                kids[n++] = b;
+            }
+        }
+        else if (cur.root.count > 0) { kids[0] = cur.root; n = 1; }     // the whole tree is one small leaf
+
+        // Octant slot assignment: slot s should hold the child that comes first for rays whose
+        // direction signs are those of octant s (bit a set = negative along axis a).
+        FBox nb; nb.reset();
+        for (int i = 0; i < n; ++i) nb.grow(kids[i].box);
+        int slot_of[8];
+        bool slot_used[8] = { false, false, false, false, false, false, false, false };
+        bool kid_done[8] = { false, false, false, false, false, false, false, false };
+        float cost[8][8];
+        for (int i = 0; i < n; ++i)
+            for (int s = 0; s < 8; ++s)
+            {
+                float c = 0.0f;
+                for (int a = 0; a < 3; ++a)
+                {
+                    const float centre = kids[i].box.valid() ? 0.5f * (kids[i].box.lo[a] + kids[i].box.hi[a]) - 0.5f * (nb.lo[a] + nb.hi[a]) : 0.0f;
+                    c += ((s >> a) & 1) ? -centre : centre;
+                }
+                cost[i][s] = c;
+            }
+        for (int round = 0; round < n; ++round)
+        {
+            int bi = -1, bs = -1; float bc = std::numeric_limits<float>::max();
+            for (int i = 0; i < n; ++i)
+            {
+                if (kid_done[i]) continue;
+                for (int s = 0; s < 8; ++s)
+                    if (!slot_used[s] && cost[i][s] < bc) { bc = cost[i][s]; bi = i; bs = s; }
+            }
+            if (bi < 0)         // all remaining costs are +max/NaN: take any free pair
+            {
+                for (int i = 0; i < n && bi < 0; ++i) if (!kid_done[i]) bi = i;
+                for (int s = 0; s < 8 && bs < 0; ++s) if (!slot_used[s]) bs = s;
+            }
+            slot_of[bi] = bs; slot_used[bs] = true; kid_done[bi] = true;
+        }
+
+        WNode w; std::memset(&w, 0, sizeof(w));
+        for (int a = 0; a < 3; ++a) for (int s = 0; s < 8; ++s) { w.qlo[a][s] = 255; w.qhi[a][s] = 0; }
+        const int rc = quantise_node(w, kids, n, slot_of, error);
+        if (rc != ASGPU_OK) return rc;
+
+        // Internal children are allocated contiguously in slot order; leaves append their items
+        // to the wide item order in slot order.
+        int kid_in_slot[8];
+        for (int s = 0; s < 8; ++s) kid_in_slot[s] = -1;
+        for (int i = 0; i < n; ++i) kid_in_slot[slot_of[i]] = i;
+
+        w.child_base = static_cast<uint32_t>(out.nodes.size());
+        w.tri_base = static_cast<uint32_t>(out.leaf_order.size());
+        uint32_t leaf_offset = 0;
+        for (int s = 0; s < 8; ++s)
+        {
+            const int i = kid_in_slot[s];
+            if (i < 0) continue;
+            if (splittable(kids[i], leaf_cap))
+            {
+                w.imask |= uint8_t(1u << s);
+                w.meta[s] = uint8_t(0x20 | (24 + s));
+                WNode blank; std::memset(&blank, 0, sizeof(blank));
+                Pending p; p.wide_index = static_cast<uint32_t>(out.nodes.size()); p.root = kids[i];
+                out.nodes.push_back(blank);
+                queue.push_back(p);
+            }
+            else
+            {
+                if (kids[i].count == 0) { w.meta[s] = 0; continue; }
+                const uint32_t unary = (1u << kids[i].count) - 1;       // 1 -> 001, 2 -> 011, 3 -> 111
+                w.meta[s] = uint8_t((unary << 5) | leaf_offset);
+                for (uint32_t k = 0; k < kids[i].count; ++k) out.leaf_order.push_back(kids[i].first + k);
+                leaf_offset += kids[i].count;
+            }
+        }
+        if (out.nodes.size() >= 0xFFFFFFFFull) { error = "wide tree too large"; return ASGPU_E_UNSUPPORTED; }
+        out.nodes[cur.wide_index] = w;
+    }
+    return ASGPU_OK;
+}
+
+// Conservative all-time boxes of every binary node of a triangle tree.
+void triangle_tree_boxes(const asgpu_triangle_tree_view& v, const ExactTree& t, BinaryView& bv)
+{
+    const AsNode* nodes = static_cast<const AsNode*>(v.nodes);
+    const uint64_t n = v.node_count;
+    bv.node_count = n;
+    bv.child.assign(n, InteriorMark);
+    bv.first.assign(n, 0);
+    bv.count.assign(n, 0);
+    bv.box.resize(n);
+    const bool motion = t.moving > 0;
+
+    auto child_box = [&](const AsNode& node, const int side) -> FBox
+    {
+        FBox b;
+        const uint32_t count = side == 0 ? node.left_bbox_count : node.right_bbox_count;
+        const uint32_t index = side == 0 ? node.left_bbox_index : node.right_bbox_index;
+        if (motion && count > 1)
+        {
+            // The traversal interpolates between consecutive entries (bvh_intersector.h:680-722);
+            // their union bounds every interpolant.  a*w1 + b*w2 is rounded twice: pad slightly.
+            b.reset();
+            for (uint32_t k = 0; k < count; ++k)
+            {
+                const MBox& mb = t.mboxes[index + k];
+                for (int a = 0; a < 3; ++a) { b.lo[a] = std::min(b.lo[a], mb.v[a * 2]); b.hi[a] = std::max(b.hi[a], mb.v[a * 2 + 1]); }
+            }
+            for (int a = 0; a < 3; ++a)
+            {
+                const float m = std::max(std::fabs(b.lo[a]), std::fabs(b.hi[a])) * 2.0e-7f + std::numeric_limits<float>::min();
+                b.lo[a] -= m; b.hi[a] += m;
+            }
+        }
+        else
+        {
+            for (int a = 0; a < 3; ++a)
+            {
+                b.lo[a] = static_cast<float>(node.bbox[a * 4 + side]);
+                b.hi[a] = static_cast<float>(node.bbox[a * 4 + 2 + side]);
+            }
+        }
+        return b;
+    };
+
+    // Children always have larger indices than their parent (bvh_builder.h:197-205), so one
+    // forward pass assigns every box before it is needed.
+    if (nodes[0].interior())
+    {
+        bv.box[0] = child_box(nodes[0], 0);
+        bv.box[0].grow(child_box(nodes[0], 1));
+    }
+    else
+    {
+        bv.box[0].reset();
+        for (uint32_t j = 0; j < nodes[0].item_count; ++j) bv.box[0].grow(triangle_box(t, nodes[0].index + j));
+    }
+    for (uint64_t i = 0; i < n; ++i)
+    {
+        const AsNode& node = nodes[i];
+        if (node.interior())
+        {
+            bv.child[i] = node.index;
+            bv.box[node.index] = child_box(node, 0);
+            bv.box[node.index + 1] = child_box(node, 1);
+        }
+        else
+        {
+            bv.first[i] = node.index;
+            bv.count[i] = node.item_count;
+        }
+    }
+}
+
+int assembly_tree_boxes(const asgpu_assembly_tree_view& top, BinaryView& bv, std::string& error)
+{
+    const AsNode* nodes = static_cast<const AsNode*>(top.nodes);
+    const uint64_t n = top.node_count;
+    bv.node_count = n;
+    bv.child.assign(n, InteriorMark);
+    bv.first.assign(n, 0);
+    bv.count.assign(n, 0);
+    bv.box.resize(n);
+    auto child_box = [&](const AsNode& node, const int side) -> FBox
+    {
+        FBox b;
+        for (int a = 0; a < 3; ++a)
+        {
+            b.lo[a] = float_below(node.bbox[a * 4 + side]);
+            b.hi[a] = float_above(node.bbox[a * 4 + 2 + side]);
+        }
+        return b;
+    };
+    if (nodes[0].interior())
+    {
+        bv.box[0] = child_box(nodes[0], 0);
+        bv.box[0].grow(child_box(nodes[0], 1));
+    }
+    else
+    {
+        // A single-leaf assembly tree carries no box at all: use an unbounded one.
+        for (int a = 0; a < 3; ++a) { bv.box[0].lo[a] = -std::numeric_limits<float>::max(); bv.box[0].hi[a] = std::numeric_limits<float>::max(); }
+    }
+    for (uint64_t i = 0; i < n; ++i)
+    {
+        const AsNode& node = nodes[i];
+        if (node.interior())
+        {
+            if (uint64_t(node.index) + 1 >= n) { error = "assembly tree child index out of range"; return ASGPU_E_INVALID; }
+            bv.child[i] = node.index;
+            bv.box[node.index] = child_box(node, 0);
+            bv.box[node.index + 1] = child_box(node, 1);
+        }
+        else
+        {
+            if (uint64_t(node.index) + node.item_count > top.item_count) { error = "assembly tree item range out of range"; return ASGPU_E_INVALID; }
+            bv.first[i] = node.index;
+            bv.count[i] = node.item_count;
+        }
+    }
+    return ASGPU_OK;
+}
+
+}   // anonymous namespace
+
+int flatten_scene(
+    const asgpu_triangle_tree_view* trees,
+    uint32_t                        tree_count,
+    const asgpu_assembly_tree_view& top,
+    uint32_t                        flags,
+    std::vector<uint8_t>&           blob,
+    std::string&                    error)
+{
+    if ((flags & (ASGPU_SCENE_EXACT | ASGPU_SCENE_WIDE)) == 0) { error = "scene flags select no layout"; return ASGPU_E_INVALID; }
+    if (tree_count && !trees) { error = "null triangle tree array"; return ASGPU_E_INVALID; }
+    if (!top.nodes || top.node_count == 0) { error = "assembly tree without nodes"; return ASGPU_E_INVALID; }
+    if (top.item_count && !top.items) { error = "null assembly item array"; return ASGPU_E_INVALID; }
+    if (top.node_count >= 0xFFFFFFFFull || top.item_count >= 0xFFFFFFFFull) { error = "assembly tree too large"; return ASGPU_E_UNSUPPORTED; }
+
+    const bool want_exact = (flags & ASGPU_SCENE_EXACT) != 0;
+    const bool want_wide = (flags & ASGPU_SCENE_WIDE) != 0;
+
+    BlobHeader header; std::memset(&header, 0, sizeof(header));
+    header.magic = BlobMagic;
+    header.version = BlobVersion;
+    header.flags = flags & (ASGPU_SCENE_EXACT | ASGPU_SCENE_WIDE);
+    header.tree_count = tree_count;
+    header.item_count = static_cast<uint32_t>(top.item_count);
+
+    BlobWriter writer(blob);
+    writer.append(&header, sizeof(header));     // rewritten at the end
+
+    std::vector<TreeDesc> descs(tree_count);
+    for (uint32_t ti = 0; ti < tree_count; ++ti)
+    {
+        ExactTree et;
+        int rc = decode_tree(trees[ti], et, error);
+        if (rc != ASGPU_OK) return rc;
+
+        TreeDesc& d = descs[ti];
+        std::memset(&d, 0, sizeof(d));
+        d.slot_count = static_cast<uint32_t>(et.tris.size());
+        d.moving = static_cast<uint32_t>(et.moving);
+        d.keys = writer.append(et.keys);
+        if (!et.poses.empty()) d.poses = writer.append(et.poses);
+        header.triangle_count += et.tris.size();
+        header.moving_triangle_count += et.moving;
+        header.triangle_bytes += et.poses.size() * 4;
+
+        if (want_exact)
+        {
+            d.bnodes = writer.append(et.bnodes);
+            d.bnode_count = static_cast<uint32_t>(et.bnodes.size());
+            if (et.moving > 0)
+            {
+                d.mnodes = writer.append(et.mnodes);
+                d.mboxes = writer.append(et.mboxes);
+                d.mbox_count = static_cast<uint32_t>(et.mboxes.size());
+            }
+            d.tris = writer.append(et.tris);
+            header.binary_node_count += et.bnodes.size();
+            header.binary_node_bytes += et.bnodes.size() * sizeof(BNodeF) + et.mnodes.size() * sizeof(MNode) + et.mboxes.size() * sizeof(MBox);
+            header.triangle_bytes += et.tris.size() * sizeof(TriRecord);
+        }
+
+        if (want_wide)
+        {
+            BinaryView bv;
+            triangle_tree_boxes(trees[ti], et, bv);
+            WideOut wo;
+            rc = collapse(bv, 3, wo, error);
+            if (rc != ASGPU_OK) return rc;
+            if (wo.leaf_order.size() != et.tris.size()) { error = "internal error: wide collapse lost triangles"; return ASGPU_E_INVALID; }
+            std::vector<TriRecord> wtris(wo.leaf_order.size());
+            for (size_t i = 0; i < wtris.size(); ++i) wtris[i] = et.tris[wo.leaf_order[i]];
+            d.wnodes = writer.append(wo.nodes);
+            d.wnode_count = static_cast<uint32_t>(wo.nodes.size());
+            d.wtris = writer.append(wtris);
+            header.wide_node_count += wo.nodes.size();
+            header.wide_node_bytes += wo.nodes.size() * sizeof(WNode);
+            if (!want_exact) header.triangle_bytes += wtris.size() * sizeof(TriRecord);
+        }
+    }
+    header.trees = writer.append(descs);
+
+    // Items.
+    std::vector<ItemRecord> items(top.item_count);
+    for (uint64_t i = 0; i < top.item_count; ++i)
+    {
+        const asgpu_assembly_item& src = top.items[i];
+        // Transform::point_to_local divides by w only when w != 1 (transform.h:311-344); with an
+        // affine last row w is exactly 1 for finite points, so only affine instances are accepted.
+        if (src.parent_to_local[12] != 0.0 || src.parent_to_local[13] != 0.0 || src.parent_to_local[14] != 0.0 || src.parent_to_local[15] != 1.0)
+        { error = "projective assembly-instance transforms are not supported"; return ASGPU_E_UNSUPPORTED; }
+        if (src.triangle_tree != ASGPU_MISS && src.triangle_tree >= tree_count) { error = "assembly item references a missing triangle tree"; return ASGPU_E_INVALID; }
+        ItemRecord& dst = items[i];
+        std::memset(&dst, 0, sizeof(dst));
+        std::memcpy(dst.m, src.parent_to_local, 12 * sizeof(double));
+        dst.tree = src.triangle_tree;
+        dst.vis_flags = src.vis_flags;
+        dst.assembly_instance = src.assembly_instance;
+    }
+    header.items = writer.append(items);
+
+    if (want_exact)
+    {
+        static_assert(sizeof(BNodeD) == sizeof(AsNode), "top-level nodes are uploaded as they are");
+        header.top_nodes = writer.append(top.nodes, top.node_count * sizeof(AsNode));
+        header.top_node_count = static_cast<uint32_t>(top.node_count);
+        header.binary_node_count += top.node_count;
+        header.binary_node_bytes += top.node_count * sizeof(AsNode);
+    }
+
+    if (want_wide)
+    {
+        BinaryView bv;
+        int rc = assembly_tree_boxes(top, bv, error);
+        if (rc != ASGPU_OK) return rc;
+        WideOut wo;
+        rc = collapse(bv, 1, wo, error);
+        if (rc != ASGPU_OK) return rc;
+        if (wo.leaf_order.size() != top.item_count) { error = "internal error: wide collapse lost instances"; return ASGPU_E_INVALID; }
+        header.top_wnodes = writer.append(wo.nodes);
+        header.top_wnode_count = static_cast<uint32_t>(wo.nodes.size());
+        header.top_witems = writer.append(wo.leaf_order);
+        header.wide_node_count += wo.nodes.size();
+        header.wide_node_bytes += wo.nodes.size() * sizeof(WNode);
+    }
+
+    writer.finish();
+    header.total_bytes = blob.size();
+    std::memcpy(blob.data(), &header, sizeof(header));
+    return ASGPU_OK;
+}
+
+int validate_blob(const uint8_t* blob, size_t size, std::string& error)
+{
+    if (!blob || size < sizeof(BlobHeader)) { error = "blob too small"; return ASGPU_E_INVALID; }
+    BlobHeader h;
+    std::memcpy(&h, blob, sizeof(h));
+    if (h.magic != BlobMagic || h.version != BlobVersion) { error = "blob magic/version mismatch"; return ASGPU_E_INVALID; }
+    if (h.total_bytes != size) { error = "blob size mismatch"; return ASGPU_E_INVALID; }
+    auto inside = [&](uint64_t off, uint64_t bytes) { return off <= size && bytes <= size - off; };
+    if (!inside(h.trees, uint64_t(h.tree_count) * sizeof(TreeDesc)) || !inside(h.items, uint64_t(h.item_count) * sizeof(ItemRecord)) ||
+        !inside(h.top_nodes, uint64_t(h.top_node_count) * sizeof(BNodeD)) || !inside(h.top_wnodes, uint64_t(h.top_wnode_count) * sizeof(WNode)))
+    { error = "blob section out of range"; return ASGPU_E_INVALID; }
+    for (uint32_t i = 0; i < h.tree_count; ++i)
+    {
+        TreeDesc d;
+        std::memcpy(&d, blob + h.trees + uint64_t(i) * sizeof(TreeDesc), sizeof(d));
+        if (!inside(d.bnodes, uint64_t(d.bnode_count) * sizeof(BNodeF)) || !inside(d.wnodes, uint64_t(d.wnode_count) * sizeof(WNode)) ||
+            !inside(d.keys, uint64_t(d.slot_count) * sizeof(HitKey)) || !inside(d.tris, d.tris ? uint64_t(d.slot_count) * sizeof(TriRecord) : 0) ||
+            !inside(d.wtris, d.wtris ? uint64_t(d.slot_count) * sizeof(TriRecord) : 0))
+        { error = "blob tree section out of range"; return ASGPU_E_INVALID; }
+    }
+    return ASGPU_OK;
+}
+
+}   // namespace asgpu

@@ -1,0 +1,28 @@
+//
+// flatten.h -- host flattener: reference-format trees -> GPU blob (gpu_layout.h).
+//
+#pragma once
+
+#include "../../include/asgpu.h"
+#include "gpu_layout.h"
+
+#include <string>
+#include <vector>
+
+namespace asgpu
+{
+
+// Builds the blob image in host memory.  Returns ASGPU_OK or a negative error code with `error`
+// filled.  `flags` is a combination of ASGPU_SCENE_EXACT / ASGPU_SCENE_WIDE.
+int flatten_scene(
+    const asgpu_triangle_tree_view* trees,
+    uint32_t                        tree_count,
+    const asgpu_assembly_tree_view& top,
+    uint32_t                        flags,
+    std::vector<uint8_t>&           blob,
+    std::string&                    error);
+
+// Structural validation of a blob received from elsewhere (import path).
+int validate_blob(const uint8_t* blob, size_t size, std::string& error);
+
+}   // namespace asgpu

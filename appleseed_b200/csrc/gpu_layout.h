@@ -1,0 +1,158 @@
+//
+// gpu_layout.h -- the flattened scene as it lives in HBM.  Shared by the host flattener and the
+// CUDA kernels.
+//
+// The whole scene is ONE contiguous allocation (the "blob"): a BlobHeader at offset 0, then
+// 256-byte aligned sections addressed by byte offsets, so that a scene is position independent
+// and can be replicated to other GPUs with a single broadcast (asgpu_scene_export/import_blob).
+//
+// Two layouts of the same trees coexist in the blob:
+//
+//  * EXACT  -- a 1:1 image of the reference's binary BVHs.  Triangle-tree child boxes are stored
+//              as the floats they were built from (the reference widens float boxes to double,
+//              bvh_builder.h:193-204, so this is lossless) in 64-byte nodes; the assembly tree
+//              keeps the reference's own 128-byte double nodes.  Kernels on this layout repeat the
+//              reference's arithmetic and visit order operation for operation.
+//  * WIDE   -- 8-wide nodes with 8-bit quantised child boxes (80 bytes) over the same leaves,
+//              for the throughput kernels.
+//
+// Both share the per-slot triangle records (48 bytes: the 36-byte float Moeller-Trumbore triangle
+// the reference stores in its leaves + visibility flags + motion info), the pose pool of moving
+// triangles, and the 8-byte hit keys.
+//
+#pragma once
+
+#include <cstdint>
+
+namespace asgpu
+{
+
+const uint32_t BlobMagic = 0x42534131u;     // "1ASB"
+const uint32_t BlobVersion = 3;
+const uint64_t SectionAlign = 256;
+
+const uint32_t InteriorMark = 0xFFFFFFFFu;
+
+// EXACT: binary node of a triangle tree, 64 bytes.  box[] = [minL minR maxL maxR] x (x, y, z),
+// the order of bvh::Node::m_bbox_data (bvh_node.h:141-162).
+struct BNodeF
+{
+    uint32_t    index;          // interior: first child node; leaf: first triangle slot
+    uint32_t    item_count;     // InteriorMark for interior nodes
+    float       box[12];
+    uint32_t    pad[2];
+};
+static_assert(sizeof(BNodeF) == 64, "BNodeF");
+
+// EXACT: motion information of an interior node (only for trees with moving triangles).
+struct MNode
+{
+    uint32_t    left_index, left_count, right_index, right_count;   // into the motion box pool
+};
+static_assert(sizeof(MNode) == 16, "MNode");
+
+// One entry of Tree::m_node_bboxes, kept in the reference's swizzled order
+// minx maxx miny maxy minz maxz (triangletree.cpp:725-738) as floats (lossless, see above).
+struct MBox { float v[6]; };
+
+// Triangle record, 48 bytes = three 16-byte loads.  The EXACT layout keeps one per slot in the
+// reference's leaf order (ref_slot == its own index); the WIDE layout keeps a second array
+// ordered so that the leaves of one wide node are contiguous, ref_slot pointing back.
+// Static triangle (motion == 0): v0/e0/e1 = TriangleMT<float> exactly as TriangleEncoder stores it.
+// Moving triangle (motion != 0): motion - 1 = index of the first float of pose 0 in the pose pool
+// ((msc + 1) poses of 9 floats, pose-major) and the bits of v0[0] hold msc.
+struct TriRecord
+{
+    float       v0[3], e0[3], e1[3];
+    uint32_t    vis_flags;
+    uint32_t    ref_slot;
+    uint32_t    motion;
+};
+static_assert(sizeof(TriRecord) == 48, "TriRecord");
+
+// Hit key (TriangleKey without the primitive-attribute index, which stays on the host).
+struct HitKey { uint32_t object_instance_index, triangle_index; };
+
+// WIDE: 8-wide node, 80 bytes.  Child k's box is
+//   lo = origin + qlo[axis][k] * 2^exp[axis],  hi = origin + qhi[axis][k] * 2^exp[axis]
+// rounded outward.  meta[k]: 0 = empty; internal child: 0x20 | (24 + slot);  leaf child:
+// (triangle count as a unary mask << 5) | first-slot offset from tri_base (compressed-wide-BVH
+// encoding of Ylitie et al. 2017).
+struct WNode
+{
+    float       origin[3];
+    uint8_t     exp[3];
+    uint8_t     imask;          // bit k set: child k is an internal node
+    uint32_t    child_base;     // index of the first internal child node
+    uint32_t    tri_base;       // first triangle slot referenced by this node's leaves
+    uint8_t     meta[8];
+    uint8_t     qlo[3][8];
+    uint8_t     qhi[3][8];
+};
+static_assert(sizeof(WNode) == 80, "WNode");
+
+// Per triangle tree.
+struct TreeDesc
+{
+    uint64_t    bnodes;         // BNodeF[]        (EXACT)
+    uint64_t    mnodes;         // MNode[] or 0    (EXACT, trees with motion)
+    uint64_t    mboxes;         // MBox[] or 0
+    uint64_t    tris;           // TriRecord[slot_count], leaf order       (EXACT)
+    uint64_t    poses;          // float[] or 0
+    uint64_t    keys;           // HitKey[slot_count], leaf order
+    uint64_t    wnodes;         // WNode[] or 0                            (WIDE)
+    uint64_t    wtris;          // TriRecord[slot_count], wide-node order  (WIDE)
+    uint32_t    bnode_count;
+    uint32_t    wnode_count;
+    uint32_t    slot_count;
+    uint32_t    moving;         // number of moving triangles
+    uint32_t    mbox_count;
+    uint32_t    pad;
+};
+static_assert(sizeof(TreeDesc) == 88, "TreeDesc");
+
+// One assembly-tree item (tree order): world -> instance rows of parent_to_local.
+struct ItemRecord
+{
+    double      m[12];          // 3 x 4, row-major
+    uint32_t    tree;           // TreeDesc index or 0xFFFFFFFF
+    uint32_t    vis_flags;
+    uint32_t    assembly_instance;
+    uint32_t    pad[5];
+};
+static_assert(sizeof(ItemRecord) == 128, "ItemRecord");
+
+// EXACT top level: the reference's own node (bvh_node.h:100-107), double boxes.
+struct BNodeD
+{
+    uint32_t    item_count;
+    uint32_t    index;
+    uint32_t    unused[6];
+    double      box[12];
+};
+static_assert(sizeof(BNodeD) == 128, "BNodeD");
+
+struct BlobHeader
+{
+    uint32_t    magic, version;
+    uint32_t    flags;              // ASGPU_SCENE_*
+    uint32_t    tree_count;
+    uint32_t    item_count;
+    uint32_t    top_node_count;
+    uint32_t    top_wnode_count;
+    uint32_t    pad0;
+    uint64_t    total_bytes;
+    uint64_t    trees;              // TreeDesc[tree_count]
+    uint64_t    items;              // ItemRecord[item_count]
+    uint64_t    top_nodes;          // BNodeD[top_node_count]
+    uint64_t    top_wnodes;         // WNode[] over the items or 0
+    uint64_t    top_witems;         // uint32_t[item_count]: wide leaf order -> ItemRecord index
+    // statistics
+    uint64_t    triangle_count, moving_triangle_count;
+    uint64_t    binary_node_count, wide_node_count;
+    uint64_t    binary_node_bytes, wide_node_bytes, triangle_bytes;
+    uint64_t    pad1[1];
+};
+static_assert(sizeof(BlobHeader) % 16 == 0, "BlobHeader alignment");
+
+}   // namespace asgpu

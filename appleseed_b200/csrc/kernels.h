@@ -1,0 +1,28 @@
+//
+// kernels.h -- launch interface between the C ABI (api.cu) and the kernels (kernels.cu).
+//
+#pragma once
+
+#include "../../include/asgpu.h"
+#include "traverse_core.h"
+
+namespace asgpu
+{
+
+// Enqueues one trace over `n` rays on `stream`.  Exactly one kernel of this library is launched
+// (plus a memset of the queue cursor).  Returns a cudaError_t value (0 = success).
+int launch_trace(
+    const SceneView&    scene,
+    const asgpu_rays&   rays,       // device pointers
+    size_t              n,
+    asgpu_hit*          hits,       // closest hit output (device) or nullptr
+    uint8_t*            occluded,   // any hit output (device) or nullptr
+    bool                any_hit,
+    bool                wide,
+    unsigned long long* queue,      // device: ray queue cursor (8 bytes)
+    unsigned long long* counters,   // device: asgpu_counters or nullptr
+    const uint32_t*     order,      // device: optional ray permutation
+    int                 sm_count,
+    void*               stream);
+
+}   // namespace asgpu

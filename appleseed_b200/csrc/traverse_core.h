@@ -1,0 +1,803 @@
+//
+// traverse_core.h -- per-ray traversal and intersection, shared by the CUDA kernels (kernels.cu)
+// and by a TEST-ONLY host build (tests/hostsim) that runs the very same code on the CPU so the
+// logic can be checked against the oracle without a GPU.  The shipped library only contains the
+// CUDA instantiation; there is no CPU execution path in the product.
+//
+// Two traversals over the two layouts of gpu_layout.h:
+//
+//   exact_trace<ANY>  1:1 restatement of the reference's two-level traversal in fp64 on the EXACT
+//                     layout: generic scalar top-level loop (bvh_intersector.h:139-258) with
+//                     AssemblyLeaf[Probe]Visitor (assemblytree.cpp:604-838, 845-1054), SSE2-order
+//                     bottom-level loops (bvh_intersector.h:472-616, 623-890) with
+//                     TriangleLeaf[Probe]Visitor (triangletree.cpp:1352-1603).  Same visit order,
+//                     same operations, no FMA: results are bit-identical to the reference's.
+//
+//   wide_trace<ANY>   throughput traversal on the WIDE layout: 8-wide nodes, quantised child
+//                     boxes tested in fp32 INTERVAL arithmetic (directed rounding) so that a box is
+//                     never missed when the reference's fp64 slab test on the tighter binary box
+//                     would pass; candidate triangles then go through the same exact fp64
+//                     Moeller-Trumbore test as above.  The accepted set of triangles is therefore a
+//                     superset of the reference's and the nearest accepted one is reported.
+//
+// All fp64 arithmetic that must match the reference uses explicit round-to-nearest intrinsics
+// (never contracted into FMAs).
+//
+#pragma once
+
+#include "../../include/asgpu.h"
+#include "gpu_layout.h"
+
+#include <cstdint>
+
+#if defined(__CUDA_ARCH__)
+    #define ASGPU_DEVICE_CODE 1
+#else
+    #define ASGPU_DEVICE_CODE 0
+#endif
+
+#if defined(__CUDACC__)
+    #define ASGPU_HD __host__ __device__ __forceinline__
+#else
+    #define ASGPU_HD inline
+#endif
+
+#if !ASGPU_DEVICE_CODE
+    #include <cfenv>
+    #include <cmath>
+    #include <cstring>
+#endif
+
+namespace asgpu
+{
+
+// ------------------------------------------------------------------------------------------
+// Arithmetic primitives.
+// ------------------------------------------------------------------------------------------
+
+#if ASGPU_DEVICE_CODE
+
+ASGPU_HD double dmul(double a, double b) { return __dmul_rn(a, b); }
+ASGPU_HD double dadd(double a, double b) { return __dadd_rn(a, b); }
+ASGPU_HD double dsub(double a, double b) { return __dsub_rn(a, b); }
+ASGPU_HD double ddiv(double a, double b) { return __ddiv_rn(a, b); }
+ASGPU_HD float  fmul(float a, float b)   { return __fmul_rn(a, b); }
+ASGPU_HD float  fadd(float a, float b)   { return __fadd_rn(a, b); }
+ASGPU_HD float  fsub(float a, float b)   { return __fsub_rn(a, b); }
+ASGPU_HD float  fsub_dn(float a, float b) { return __fsub_rd(a, b); }
+ASGPU_HD float  fsub_up(float a, float b) { return __fsub_ru(a, b); }
+ASGPU_HD float  fmul_dn(float a, float b) { return __fmul_rd(a, b); }
+ASGPU_HD float  fmul_up(float a, float b) { return __fmul_ru(a, b); }
+ASGPU_HD float  fma_dn(float a, float b, float c) { return __fmaf_rd(a, b, c); }
+ASGPU_HD float  fma_up(float a, float b, float c) { return __fmaf_ru(a, b, c); }
+ASGPU_HD float  d2f_dn(double a) { return __double2float_rd(a); }
+ASGPU_HD float  d2f_up(double a) { return __double2float_ru(a); }
+ASGPU_HD float  fmin_nan(float a, float b) { return fminf(a, b); }     // returns the non-NaN operand
+ASGPU_HD float  fmax_nan(float a, float b) { return fmaxf(a, b); }
+ASGPU_HD float  bits_to_float(uint32_t u) { return __uint_as_float(u); }
+ASGPU_HD uint32_t float_to_bits(float f) { return __float_as_uint(f); }
+ASGPU_HD int    popc(uint32_t x) { return __popc(x); }
+ASGPU_HD int    high_bit(uint32_t x) { return 31 - __clz(x); }
+ASGPU_HD uint4  load16(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+ASGPU_HD uint2  load8(const void* p) { return __ldg(reinterpret_cast<const uint2*>(p)); }
+ASGPU_HD uint32_t load4(const void* p) { return __ldg(reinterpret_cast<const uint32_t*>(p)); }
+ASGPU_HD double load_f64(const void* p) { return __ldg(reinterpret_cast<const double*>(p)); }
+
+#else
+
+struct uint4_h { uint32_t x, y, z, w; };
+struct uint2_h { uint32_t x, y; };
+#if !defined(__CUDACC__)
+typedef uint4_h uint4;
+typedef uint2_h uint2;
+#endif
+
+// Host stand-ins (tests/hostsim is compiled with -ffp-contract=off -frounding-math).
+struct RoundScope
+{
+    int saved;
+    explicit RoundScope(int mode) : saved(fegetround()) { fesetround(mode); }
+    ~RoundScope() { fesetround(saved); }
+};
+inline double dmul(double a, double b) { volatile double r = a * b; return r; }
+inline double dadd(double a, double b) { volatile double r = a + b; return r; }
+inline double dsub(double a, double b) { volatile double r = a - b; return r; }
+inline double ddiv(double a, double b) { volatile double r = a / b; return r; }
+inline float  fmul(float a, float b)   { volatile float r = a * b; return r; }
+inline float  fadd(float a, float b)   { volatile float r = a + b; return r; }
+inline float  fsub(float a, float b)   { volatile float r = a - b; return r; }
+inline float  fsub_dn(float a, float b) { RoundScope s(FE_DOWNWARD); volatile float x = a, y = b; volatile float r = x - y; return r; }
+inline float  fsub_up(float a, float b) { RoundScope s(FE_UPWARD);   volatile float x = a, y = b; volatile float r = x - y; return r; }
+inline float  fmul_dn(float a, float b) { RoundScope s(FE_DOWNWARD); volatile float x = a, y = b; volatile float r = x * y; return r; }
+inline float  fmul_up(float a, float b) { RoundScope s(FE_UPWARD);   volatile float x = a, y = b; volatile float r = x * y; return r; }
+inline float  fma_dn(float a, float b, float c) { RoundScope s(FE_DOWNWARD); volatile float x = a, y = b, z = c; volatile float r = std::fmaf(x, y, z); return r; }
+inline float  fma_up(float a, float b, float c) { RoundScope s(FE_UPWARD);   volatile float x = a, y = b, z = c; volatile float r = std::fmaf(x, y, z); return r; }
+inline float  d2f_dn(double a) { RoundScope s(FE_DOWNWARD); volatile double x = a; volatile float r = static_cast<float>(x); return r; }
+inline float  d2f_up(double a) { RoundScope s(FE_UPWARD);   volatile double x = a; volatile float r = static_cast<float>(x); return r; }
+inline float  fmin_nan(float a, float b) { return std::fmin(a, b); }
+inline float  fmax_nan(float a, float b) { return std::fmax(a, b); }
+inline float  bits_to_float(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
+inline uint32_t float_to_bits(float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }
+inline int    popc(uint32_t x) { return __builtin_popcount(x); }
+inline int    high_bit(uint32_t x) { return 31 - __builtin_clz(x); }
+inline uint4  load16(const void* p) { uint4 r; std::memcpy(&r, p, 16); return r; }
+inline uint2  load8(const void* p) { uint2 r; std::memcpy(&r, p, 8); return r; }
+inline uint32_t load4(const void* p) { uint32_t r; std::memcpy(&r, p, 4); return r; }
+inline double load_f64(const void* p) { double r; std::memcpy(&r, p, 8); return r; }
+
+#endif
+
+ASGPU_HD float u2f(uint32_t u) { return bits_to_float(u); }
+
+// ------------------------------------------------------------------------------------------
+// Scene view, ray, hit.
+// ------------------------------------------------------------------------------------------
+
+struct SceneView
+{
+    const uint8_t*  blob;
+    uint64_t        trees, items, top_nodes, top_wnodes, top_witems;
+    uint32_t        tree_count, item_count, top_node_count, top_wnode_count;
+};
+
+struct Ray
+{
+    double      org[3], dir[3];
+    double      tmin, tmax;
+    float       time_absolute, time_normalized;
+    uint32_t    flags;
+};
+
+struct Hit
+{
+    float       u, v;
+    uint32_t    item;           // ItemRecord index, 0xFFFFFFFF = none
+    uint32_t    slot;           // reference leaf-order slot
+    uint32_t    segment;
+};
+
+struct Stats
+{
+    uint32_t    top_nodes, instances, nodes, triangles;
+};
+
+ASGPU_HD void load_ray(const asgpu_rays& rays, const size_t i, Ray& r)
+{
+#if ASGPU_DEVICE_CODE
+    r.org[0] = __ldg(rays.org + i * 3); r.org[1] = __ldg(rays.org + i * 3 + 1); r.org[2] = __ldg(rays.org + i * 3 + 2);
+    r.dir[0] = __ldg(rays.dir + i * 3); r.dir[1] = __ldg(rays.dir + i * 3 + 1); r.dir[2] = __ldg(rays.dir + i * 3 + 2);
+    r.tmin = __ldg(rays.tmin + i);
+    r.tmax = __ldg(rays.tmax + i);
+    r.time_absolute = rays.time_absolute ? __ldg(rays.time_absolute + i) : 0.0f;
+    r.time_normalized = rays.time_normalized ? __ldg(rays.time_normalized + i) : 0.0f;
+    r.flags = rays.flags ? __ldg(rays.flags + i) : 0xFFFFFFFFu;
+#else
+    for (int a = 0; a < 3; ++a) { r.org[a] = rays.org[i * 3 + a]; r.dir[a] = rays.dir[i * 3 + a]; }
+    r.tmin = rays.tmin[i];
+    r.tmax = rays.tmax[i];
+    r.time_absolute = rays.time_absolute ? rays.time_absolute[i] : 0.0f;
+    r.time_normalized = rays.time_normalized ? rays.time_normalized[i] : 0.0f;
+    r.flags = rays.flags ? rays.flags[i] : 0xFFFFFFFFu;
+#endif
+}
+
+// compute_assembly_instance_ray (assemblytree.cpp:556-596) with Transform::vector_to_local /
+// point_to_local (transform.h:311-344, 381-400): products accumulated left to right; the
+// instance matrix is affine so w == 1 and no division happens.
+ASGPU_HD void to_instance_space(const uint8_t* item, const Ray& world, Ray& local)
+{
+    double m[12];
+#if ASGPU_DEVICE_CODE
+    #pragma unroll
+#endif
+    for (int k = 0; k < 12; ++k) m[k] = load_f64(item + k * 8);
+#if ASGPU_DEVICE_CODE
+    #pragma unroll
+#endif
+    for (int r = 0; r < 3; ++r)
+    {
+        const double* row = m + r * 4;
+        local.dir[r] = dadd(dadd(dmul(row[0], world.dir[0]), dmul(row[1], world.dir[1])), dmul(row[2], world.dir[2]));
+        local.org[r] = dadd(dadd(dadd(dmul(row[0], world.org[0]), dmul(row[1], world.org[1])), dmul(row[2], world.org[2])), row[3]);
+    }
+    local.tmin = world.tmin;
+    local.tmax = world.tmax;
+    local.time_absolute = world.time_absolute;
+    local.time_normalized = world.time_normalized;
+    local.flags = world.flags;
+}
+
+// ------------------------------------------------------------------------------------------
+// Exact Moeller-Trumbore (raytrianglemt.h:148-268) on a float triangle widened to double
+// (raytrianglemt.h:139-146).  cross: vector.h:1239-1246; dot accumulates from 0: vector.h:745-753.
+// ------------------------------------------------------------------------------------------
+
+struct TriD { double v0[3], e0[3], e1[3]; };
+
+ASGPU_HD void cross_d(const double a[3], const double b[3], double r[3])
+{
+    r[0] = dsub(dmul(a[1], b[2]), dmul(b[1], a[2]));
+    r[1] = dsub(dmul(a[2], b[0]), dmul(b[2], a[0]));
+    r[2] = dsub(dmul(a[0], b[1]), dmul(b[0], a[1]));
+}
+
+ASGPU_HD double dot_d(const double a[3], const double b[3])
+{
+    double r = dadd(0.0, dmul(a[0], b[0]));
+    r = dadd(r, dmul(a[1], b[1]));
+    r = dadd(r, dmul(a[2], b[2]));
+    return r;
+}
+
+// Returns true when the ray hits within [tmin, tmax); WITH_TUV also produces the scaled t, u, v.
+template <bool WITH_TUV>
+ASGPU_HD bool mt_test(const TriD& tri, const Ray& ray, double& t, double& u, double& v)
+{
+    double pvec[3]; cross_d(ray.dir, tri.e1, pvec);
+    const double det = dot_d(tri.e0, pvec);
+    const double tvec[3] = { dsub(ray.org[0], tri.v0[0]), dsub(ray.org[1], tri.v0[1]), dsub(ray.org[2], tri.v0[2]) };
+    double qvec[3];
+    double tt, uu, vv;
+    if (det > 0.0)
+    {
+        uu = dot_d(tvec, pvec);
+        if (uu < 0.0 || uu > det) return false;
+        cross_d(tvec, tri.e0, qvec);
+        vv = dot_d(ray.dir, qvec);
+        if (vv < 0.0 || dadd(uu, vv) > det) return false;
+        tt = dot_d(tri.e1, qvec);
+        if (tt >= dmul(ray.tmax, det) || tt < dmul(ray.tmin, det)) return false;
+    }
+    else
+    {
+        uu = dot_d(tvec, pvec);
+        if (uu > 0.0 || uu < det) return false;
+        cross_d(tvec, tri.e0, qvec);
+        vv = dot_d(ray.dir, qvec);
+        if (vv > 0.0 || dadd(uu, vv) < det) return false;
+        tt = dot_d(tri.e1, qvec);
+        if (tt <= dmul(ray.tmax, det) || tt > dmul(ray.tmin, det)) return false;
+    }
+    if (WITH_TUV)
+    {
+        const double rcp_det = ddiv(1.0, det);
+        t = dmul(tt, rcp_det);
+        u = dmul(uu, rcp_det);
+        v = dmul(vv, rcp_det);
+    }
+    return true;
+}
+
+// Loads the triangle of one record for this ray's time.  Returns false when the triangle is
+// invisible to the ray (triangletree.cpp:1389-1393, 1426-1430).  Moving triangles follow
+// triangletree.cpp:1432-1451 (closest hit: float product) / :1570-1585 (probe: double product).
+template <bool ANY>
+ASGPU_HD bool fetch_triangle(const uint8_t* record, const uint8_t* poses, const Ray& ray, TriD& tri, uint32_t& slot, uint32_t& segment)
+{
+    const uint4 a = load16(record);
+    const uint4 b = load16(record + 16);
+    const uint4 c = load16(record + 32);
+    const uint32_t vis = c.y;
+    slot = c.z;
+    segment = 0;
+    if (!(vis & ray.flags)) return false;
+    float f[9];
+    if (c.w == 0)
+    {
+        f[0] = u2f(a.x); f[1] = u2f(a.y); f[2] = u2f(a.z); f[3] = u2f(a.w);
+        f[4] = u2f(b.x); f[5] = u2f(b.y); f[6] = u2f(b.z); f[7] = u2f(b.w);
+        f[8] = u2f(c.x);
+    }
+    else
+    {
+        const uint32_t msc = a.x;
+        double base_time;
+        if (ANY) base_time = dmul(static_cast<double>(ray.time_normalized), static_cast<double>(msc));
+        else base_time = static_cast<double>(fmul(ray.time_normalized, static_cast<float>(msc)));
+        const uint32_t base_index = static_cast<uint32_t>(base_time);
+        const float frac = static_cast<float>(dsub(base_time, static_cast<double>(base_index)));
+        const float omf = fsub(1.0f, frac);
+        const uint8_t* p = poses + (static_cast<uint64_t>(c.w - 1) + static_cast<uint64_t>(base_index) * 9) * 4;
+        float v[9];
+#if ASGPU_DEVICE_CODE
+        #pragma unroll
+#endif
+        for (int k = 0; k < 9; ++k)
+        {
+            const float p0 = u2f(load4(p + k * 4));
+            const float p1 = u2f(load4(p + 36 + k * 4));
+            v[k] = fadd(fmul(p0, omf), fmul(p1, frac));
+        }
+        // TriangleMT<float>(v0, v1, v2): edges in float (raytrianglemt.h:128-137).
+        f[0] = v[0]; f[1] = v[1]; f[2] = v[2];
+        f[3] = fsub(v[3], v[0]); f[4] = fsub(v[4], v[1]); f[5] = fsub(v[5], v[2]);
+        f[6] = fsub(v[6], v[0]); f[7] = fsub(v[7], v[1]); f[8] = fsub(v[8], v[2]);
+        segment = base_index;
+    }
+#if ASGPU_DEVICE_CODE
+    #pragma unroll
+#endif
+    for (int k = 0; k < 3; ++k)
+    {
+        tri.v0[k] = static_cast<double>(f[k]);
+        tri.e0[k] = static_cast<double>(f[3 + k]);
+        tri.e1[k] = static_cast<double>(f[6 + k]);
+    }
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------
+// EXACT traversal.
+// ------------------------------------------------------------------------------------------
+
+// minmax.h:171-180 -- identical selection to _mm_max_pd / _mm_min_pd (second operand on NaN).
+ASGPU_HD double ssemax(double a, double b) { return a > b ? a : b; }
+ASGPU_HD double ssemin(double a, double b) { return a < b ? a : b; }
+
+struct RayInfoD { double rcp[3]; int sgn[3]; };
+
+// RayInfo (ray.h:313-321).
+ASGPU_HD void make_ray_info(const Ray& r, RayInfoD& info)
+{
+#if ASGPU_DEVICE_CODE
+    #pragma unroll
+#endif
+    for (int a = 0; a < 3; ++a)
+    {
+        info.rcp[a] = ddiv(1.0, r.dir[a]);
+        info.sgn[a] = info.rcp[a] >= 0.0 ? 1 : 0;
+    }
+}
+
+// One child of an interior node; box[] = [minL minR maxL maxR] x axis (bvh_intersector.h:519-536).
+ASGPU_HD bool slab_child(const double box[12], const int side, const Ray& ray, const RayInfoD& info,
+                         const double ray_tmin, const double ray_tmax, double& tmin_out)
+{
+    double l1[3], l2[3];
+#if ASGPU_DEVICE_CODE
+    #pragma unroll
+#endif
+    for (int a = 0; a < 3; ++a)
+    {
+        const double near_plane = info.sgn[a] ? box[a * 4 + side] : box[a * 4 + 2 + side];
+        const double far_plane  = info.sgn[a] ? box[a * 4 + 2 + side] : box[a * 4 + side];
+        l1[a] = dmul(info.rcp[a], dsub(near_plane, ray.org[a]));
+        l2[a] = dmul(info.rcp[a], dsub(far_plane, ray.org[a]));
+    }
+    const double tmin = ssemax(l1[2], ssemax(l1[1], ssemax(l1[0], ray_tmin)));
+    const double tmax = ssemin(l2[2], ssemin(l2[1], ssemin(l2[0], ray_tmax)));
+    tmin_out = tmin;
+    return !(tmin > tmax || tmax < ray_tmin || tmin >= ray_tmax);
+}
+
+// Bottom level on one triangle tree.  `ray` is the instance-space ray; its tmax shrinks on hits
+// (closest hit).  Returns true on the first hit for ANY.
+template <bool ANY, bool COUNT>
+ASGPU_HD bool exact_triangle_tree(const uint8_t* blob, const TreeDesc& td, Ray& ray, Hit& hit, const uint32_t item, Stats& stats)
+{
+    RayInfoD info; make_ray_info(ray, info);
+    const bool motion = td.moving > 0;
+    const double ray_time = static_cast<double>(ray.time_normalized);
+    const uint8_t* bnodes = blob + td.bnodes;
+    const uint8_t* poses = blob + td.poses;
+
+    uint32_t stack[64];
+    int sp = 0;
+    uint32_t node = 0;
+    double rtmax = ray.tmax;
+
+    while (true)
+    {
+        if (COUNT) ++stats.nodes;
+        const uint8_t* np = bnodes + static_cast<uint64_t>(node) * sizeof(BNodeF);
+        const uint4 w0 = load16(np);
+        const uint32_t index = w0.x, item_count = w0.y;
+        if (item_count == InteriorMark)
+        {
+            const uint4 w1 = load16(np + 16), w2 = load16(np + 32), w3 = load16(np + 48);
+            double box[12];
+            box[0] = u2f(w0.z); box[1] = u2f(w0.w);
+            box[2] = u2f(w1.x); box[3] = u2f(w1.y); box[4] = u2f(w1.z); box[5] = u2f(w1.w);
+            box[6] = u2f(w2.x); box[7] = u2f(w2.y); box[8] = u2f(w2.z); box[9] = u2f(w2.w);
+            box[10] = u2f(w3.x); box[11] = u2f(w3.y);
+
+            if (motion)
+            {
+                // Children with several motion boxes are interpolated at the ray time
+                // (bvh_intersector.h:675-836): a * w1 + b * w2, w2 = t - trunc(t), w1 = 1 - w2.
+                const uint4 mn = load16(blob + td.mnodes + static_cast<uint64_t>(node) * sizeof(MNode));
+                const uint32_t idx[2] = { mn.x, mn.z }, cnt[2] = { mn.y, mn.w };
+                for (int side = 0; side < 2; ++side)
+                {
+                    const uint32_t segments = cnt[side] - 1;
+                    if (segments == 0) continue;
+                    const double t = dmul(ray_time, static_cast<double>(segments));
+                    const int prev = static_cast<int>(t);
+                    const double w2 = dsub(t, static_cast<double>(prev));
+                    const double w1 = dsub(1.0, w2);
+                    const uint8_t* mb = blob + td.mboxes + (static_cast<uint64_t>(idx[side]) + prev) * sizeof(MBox);
+                    for (int a = 0; a < 3; ++a)
+                    {
+                        const double lo0 = u2f(load4(mb + (a * 2) * 4)), hi0 = u2f(load4(mb + (a * 2 + 1) * 4));
+                        const double lo1 = u2f(load4(mb + 24 + (a * 2) * 4)), hi1 = u2f(load4(mb + 24 + (a * 2 + 1) * 4));
+                        box[a * 4 + side] = dadd(dmul(lo0, w1), dmul(lo1, w2));
+                        box[a * 4 + 2 + side] = dadd(dmul(hi0, w1), dmul(hi1, w2));
+                    }
+                }
+            }
+
+            double tmin0, tmin1;
+            const bool hit_left = slab_child(box, 0, ray, info, ray.tmin, rtmax, tmin0);
+            const bool hit_right = slab_child(box, 1, ray, info, ray.tmin, rtmax, tmin1);
+            if (hit_left != hit_right) { node = index + (hit_right ? 1 : 0); continue; }
+            if (hit_left)
+            {
+                // Near child first; ties go right first (bvh_intersector.h:551-562).
+                const int far_index = tmin0 < tmin1 ? 1 : 0;
+                stack[sp++] = index + far_index;
+                node = index + 1 - far_index;
+                continue;
+            }
+            if (sp == 0) break;
+            node = stack[--sp];
+            continue;
+        }
+
+        // Leaf: TriangleLeafVisitor::visit / TriangleLeafProbeVisitor::visit.
+        for (uint32_t j = 0; j < item_count; ++j)
+        {
+            if (COUNT) ++stats.triangles;
+            TriD tri; uint32_t slot, segment;
+            if (!fetch_triangle<ANY>(blob + td.tris + static_cast<uint64_t>(index + j) * sizeof(TriRecord), poses, ray, tri, slot, segment))
+                continue;
+            double t, u, v;
+            if (mt_test<!ANY>(tri, ray, t, u, v))
+            {
+                if (ANY) return true;
+                ray.tmax = t;
+                hit.u = static_cast<float>(u);
+                hit.v = static_cast<float>(v);
+                hit.item = item;
+                hit.slot = slot;
+                hit.segment = segment;
+            }
+        }
+        if (rtmax > ray.tmax) rtmax = ray.tmax;
+        if (sp == 0) break;
+        node = stack[--sp];
+    }
+    return false;
+}
+
+ASGPU_HD void load_tree_desc(const SceneView& s, const uint32_t tree, TreeDesc& td)
+{
+    const uint8_t* p = s.blob + s.trees + static_cast<uint64_t>(tree) * sizeof(TreeDesc);
+    uint64_t* dst = reinterpret_cast<uint64_t*>(&td);
+#if ASGPU_DEVICE_CODE
+    #pragma unroll
+#endif
+    for (int k = 0; k < static_cast<int>(sizeof(TreeDesc) / 8); ++k)
+    {
+        const uint2 w = load8(p + k * 8);
+        dst[k] = static_cast<uint64_t>(w.x) | (static_cast<uint64_t>(w.y) << 32);
+    }
+}
+
+// Top level: generic scalar intersector + assembly leaf visitors.  On return ray.tmax is the hit
+// distance (closest hit).  Returns true when something was hit.
+template <bool ANY, bool COUNT>
+ASGPU_HD bool exact_trace(const SceneView& s, Ray& ray, Hit& hit, Stats& stats)
+{
+    hit.item = 0xFFFFFFFFu; hit.slot = 0; hit.segment = 0; hit.u = hit.v = 0.0f;
+    RayInfoD info; make_ray_info(ray, info);
+    const uint8_t* top = s.blob + s.top_nodes;
+
+    uint32_t stack[64];
+    int sp = 0;
+    uint32_t node = 0;
+    double ray_tmax = ray.tmax;
+
+    while (true)
+    {
+        if (COUNT) ++stats.top_nodes;
+        const uint8_t* np = top + static_cast<uint64_t>(node) * sizeof(BNodeD);
+        const uint2 head = load8(np);
+        const uint32_t item_count = head.x, index = head.y;
+        if (item_count == InteriorMark)
+        {
+            double box[12];
+#if ASGPU_DEVICE_CODE
+            #pragma unroll
+#endif
+            for (int k = 0; k < 12; ++k) box[k] = load_f64(np + 32 + k * 8);
+            // rayaabb.h:228-252 reads the LIVE ray.tmax; the loop also requires tmin < ray_tmax
+            // (bvh_intersector.h:177-186).  tmin_out = ssemax(ray.tmin, tmin) == tmin.
+            double tmin0, tmin1;
+            const bool hit_left = slab_child(box, 0, ray, info, ray.tmin, ray.tmax, tmin0) && tmin0 < ray_tmax;
+            const bool hit_right = slab_child(box, 1, ray, info, ray.tmin, ray.tmax, tmin1) && tmin1 < ray_tmax;
+            if (hit_left != hit_right) { node = index + (hit_right ? 1 : 0); continue; }
+            if (hit_left)
+            {
+                const int far_index = tmin0 < tmin1 ? 1 : 0;
+                stack[sp++] = index + far_index;
+                node = index + 1 - far_index;
+                continue;
+            }
+            if (sp == 0) break;
+            node = stack[--sp];
+            continue;
+        }
+
+        for (uint32_t i = 0; i < item_count; ++i)
+        {
+            const uint32_t item = index + i;
+            const uint8_t* ip = s.blob + s.items + static_cast<uint64_t>(item) * sizeof(ItemRecord);
+            const uint4 meta = load16(ip + 96);     // tree, vis_flags, assembly_instance, pad
+            if (!(meta.y & ray.flags)) continue;
+            if (COUNT) ++stats.instances;
+            Ray local;
+            to_instance_space(ip, ray, local);
+            if (meta.x == 0xFFFFFFFFu) continue;
+            TreeDesc td; load_tree_desc(s, meta.x, td);
+            const bool found = exact_triangle_tree<ANY, COUNT>(s.blob, td, local, hit, item, stats);
+            if (ANY) { if (found) return true; }
+            else if (local.tmax < ray.tmax) ray.tmax = local.tmax;      // only a hit shrinks local.tmax
+        }
+        if (ray_tmax > ray.tmax) ray_tmax = ray.tmax;
+        if (sp == 0) break;
+        node = stack[--sp];
+    }
+    return !ANY && hit.item != 0xFFFFFFFFu;
+}
+
+// ------------------------------------------------------------------------------------------
+// WIDE traversal.
+// ------------------------------------------------------------------------------------------
+
+// Interval data for conservative fp32 box tests of one ray in one space.  The ray parameter is
+// shifted by `shift` = min(tmin, 0) so that the tested interval starts at a non-negative value;
+// with that, products of negative plane distances never matter and one multiply per plane is
+// enough.  Per axis the frame is mirrored when the direction is negative, so the near plane is
+// always the "lo" one in that frame:
+//   d_near >= A_lo + q_near * s   (rounded down),   tau_near = d_near * rn   (rounded down)
+//   d_far  <= A_hi + q_far  * s   (rounded up),     tau_far  = d_far  * rf   (rounded up)
+// with [rn, rf] enclosing |1 / dir|.
+struct WideRay
+{
+    float       o_lo[3], o_hi[3];   // origin interval (already mirrored per axis)
+    float       rn[3], rf[3];       // |1 / dir| interval
+    float       tmin_f, tmax_f;     // shifted parameter interval, rounded outward
+    uint32_t    oct;                // bit a set: direction negative along axis a
+    double      shift;
+};
+
+ASGPU_HD void make_wide_ray(const Ray& r, WideRay& w)
+{
+    w.shift = r.tmin < 0.0 ? r.tmin : 0.0;
+    w.oct = 0;
+#if ASGPU_DEVICE_CODE
+    #pragma unroll
+#endif
+    for (int a = 0; a < 3; ++a)
+    {
+        const double rcp = ddiv(1.0, r.dir[a]);
+        // Same sign convention as RayInfo (ray.h:313-321): negative when rcp < 0 (incl. -inf for -0.0).
+        const bool neg = !(rcp >= 0.0);
+        if (neg) w.oct |= 1u << a;
+        const double mag = neg ? -rcp : rcp;
+        w.rn[a] = d2f_dn(mag);
+        w.rf[a] = d2f_up(mag);
+        double o = r.org[a];
+        float lo, hi;
+        if (w.shift != 0.0)
+        {
+            // Shifted origin o + shift * dir, widened by a bound on its fp64 rounding error.
+            const double step = dmul(w.shift, r.dir[a]);
+            const double moved = dadd(o, step);
+            const double mag = dadd(o < 0.0 ? -o : o, step < 0.0 ? -step : step);
+            const double err = dmul(mag, 4.5e-16);
+            lo = d2f_dn(dsub(moved, err));
+            hi = d2f_up(dadd(moved, err));
+        }
+        else { lo = d2f_dn(o); hi = d2f_up(o); }
+        // Mirrored frame: x' = -x, so the interval becomes [-hi, -lo].
+        w.o_lo[a] = neg ? -hi : lo;
+        w.o_hi[a] = neg ? -lo : hi;
+    }
+    w.tmin_f = d2f_dn(dsub(r.tmin, w.shift));
+    w.tmax_f = d2f_up(dsub(r.tmax, w.shift));
+}
+
+ASGPU_HD void shrink_wide_ray(const Ray& r, WideRay& w)
+{
+    w.tmax_f = d2f_up(dsub(r.tmax, w.shift));
+}
+
+ASGPU_HD float byte_to_float(const uint32_t word, const int k)
+{
+#if ASGPU_DEVICE_CODE
+    // 0x4B0000bb - 2^23 == bb exactly.
+    return __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7650 + k)) - 8388608.0f;
+#else
+    return static_cast<float>((word >> (8 * k)) & 0xFF);
+#endif
+}
+
+// Tests the 8 children of a wide node.  Returns (internal-hit bits << 24 | imask) in `nmask` and
+// the triangle-hit bits in `tmask`; fills child_base / tri_base.
+ASGPU_HD void wide_node_test(const uint8_t* np, const WideRay& w, uint32_t& child_base, uint32_t& tri_base, uint32_t& nmask, uint32_t& tmask)
+{
+    const uint4 n0 = load16(np), n1 = load16(np + 16), n2 = load16(np + 32), n3 = load16(np + 48), n4 = load16(np + 64);
+    child_base = n1.x;
+    tri_base = n1.y;
+    const uint32_t imask = n0.w >> 24;
+    const uint32_t meta_lo = n1.z, meta_hi = n1.w;
+    // Quantised planes: qlo x (n2.x, n2.y) y (n2.z, n2.w) z (n3.x, n3.y); qhi x (n3.z, n3.w) y (n4.x, n4.y) z (n4.z, n4.w).
+    const uint32_t qlo[3][2] = { { n2.x, n2.y }, { n2.z, n2.w }, { n3.x, n3.y } };
+    const uint32_t qhi[3][2] = { { n3.z, n3.w }, { n4.x, n4.y }, { n4.z, n4.w } };
+    const float origin[3] = { u2f(n0.x), u2f(n0.y), u2f(n0.z) };
+
+    float s[3], a_lo[3], a_hi[3];
+    uint32_t qn[3][2], qf[3][2];
+#if ASGPU_DEVICE_CODE
+    #pragma unroll
+#endif
+    for (int a = 0; a < 3; ++a)
+    {
+        const bool neg = (w.oct >> a) & 1;
+        const float scale = u2f(((n0.w >> (8 * a)) & 0xFF) << 23);
+        const float p = neg ? -origin[a] : origin[a];       // node origin in the mirrored frame
+        s[a] = neg ? -scale : scale;
+        a_lo[a] = fsub_dn(p, w.o_hi[a]);
+        a_hi[a] = fsub_up(p, w.o_lo[a]);
+        qn[a][0] = neg ? qhi[a][0] : qlo[a][0]; qn[a][1] = neg ? qhi[a][1] : qlo[a][1];
+        qf[a][0] = neg ? qlo[a][0] : qhi[a][0]; qf[a][1] = neg ? qlo[a][1] : qhi[a][1];
+    }
+
+    const uint32_t oct_inv = 7 - w.oct;
+    nmask = 0; tmask = 0;
+#if ASGPU_DEVICE_CODE
+    #pragma unroll
+#endif
+    for (int k = 0; k < 8; ++k)
+    {
+        const uint32_t meta = ((k < 4 ? meta_lo : meta_hi) >> (8 * (k & 3))) & 0xFF;
+        float tn = w.tmin_f, tf = w.tmax_f;
+#if ASGPU_DEVICE_CODE
+        #pragma unroll
+#endif
+        for (int a = 0; a < 3; ++a)
+        {
+            const float dn = fma_dn(byte_to_float(qn[a][k >> 2], k & 3), s[a], a_lo[a]);
+            const float df = fma_up(byte_to_float(qf[a][k >> 2], k & 3), s[a], a_hi[a]);
+            tn = fmax_nan(tn, fmul_dn(dn, w.rn[a]));
+            tf = fmin_nan(tf, fmul_up(df, w.rf[a]));
+        }
+        if (meta != 0 && tn <= tf)
+        {
+            if ((imask >> k) & 1) nmask |= 1u << (24 + (k ^ oct_inv));
+            else tmask |= (meta >> 5) << (meta & 31);
+        }
+    }
+    nmask |= imask;
+}
+
+const uint32_t WideStackSize = 32;
+
+// `stack` must hold WideStackSize entries per thread, element i of this thread at stack[i * stride].
+template <bool ANY, bool COUNT>
+ASGPU_HD bool wide_trace(const SceneView& s, Ray& world, Hit& hit, Stats& stats, uint2* stack, const uint32_t stride)
+{
+    hit.item = 0xFFFFFFFFu; hit.slot = 0; hit.segment = 0; hit.u = hit.v = 0.0f;
+
+    Ray ray = world;                // current-space ray (world space first)
+    WideRay wr; make_wide_ray(ray, wr);
+
+    const uint8_t* wnodes = s.blob + s.top_wnodes;
+    const uint8_t* wtris = nullptr;
+    const uint8_t* poses = nullptr;
+    bool in_instance = false;
+    uint32_t cur_item = 0xFFFFFFFFu;
+
+    uint32_t sp = 0;
+    uint2 ngroup; ngroup.x = 0; ngroup.y = 0;
+    uint2 tgroup; tgroup.x = 0; tgroup.y = 0;
+    uint32_t fetch = 0;                             // node to fetch next, 0xFFFFFFFF = none
+    if (s.top_wnode_count == 0) return false;
+
+    while (true)
+    {
+        if (fetch != 0xFFFFFFFFu)
+        {
+            if (COUNT) { if (in_instance) ++stats.nodes; else ++stats.top_nodes; }
+            if (ngroup.y & 0xFF000000u) { stack[sp * stride] = ngroup; ++sp; }
+            uint32_t child_base, tri_base, nmask, tmask;
+            wide_node_test(wnodes + static_cast<uint64_t>(fetch) * sizeof(WNode), wr, child_base, tri_base, nmask, tmask);
+            ngroup.x = child_base; ngroup.y = nmask;
+            tgroup.x = tri_base; tgroup.y = tmask;
+            fetch = 0xFFFFFFFFu;
+        }
+
+        // Leaf items of the current node.
+        while (tgroup.y)
+        {
+            const int bit = high_bit(tgroup.y);
+            tgroup.y &= ~(1u << bit);
+            if (in_instance)
+            {
+                if (COUNT) ++stats.triangles;
+                TriD tri; uint32_t slot, segment;
+                if (!fetch_triangle<ANY>(wtris + static_cast<uint64_t>(tgroup.x + bit) * sizeof(TriRecord), poses, ray, tri, slot, segment))
+                    continue;
+                double t, u, v;
+                if (mt_test<!ANY>(tri, ray, t, u, v))
+                {
+                    if (ANY) return true;
+                    ray.tmax = t;
+                    world.tmax = t;
+                    shrink_wide_ray(ray, wr);
+                    hit.u = static_cast<float>(u);
+                    hit.v = static_cast<float>(v);
+                    hit.item = cur_item;
+                    hit.slot = slot;
+                    hit.segment = segment;
+                }
+            }
+            else
+            {
+                // Assembly instance: AssemblyLeafVisitor::visit (assemblytree.cpp:604-744).
+                const uint32_t item = load4(s.blob + s.top_witems + static_cast<uint64_t>(tgroup.x + bit) * 4);
+                const uint8_t* ip = s.blob + s.items + static_cast<uint64_t>(item) * sizeof(ItemRecord);
+                const uint4 meta = load16(ip + 96);
+                if (!(meta.y & world.flags) || meta.x == 0xFFFFFFFFu) continue;
+                if (COUNT) ++stats.instances;
+                // Save the world-space traversal state, then descend.
+                if (ngroup.y & 0xFF000000u) { stack[sp * stride] = ngroup; ++sp; }
+                if (tgroup.y) { stack[sp * stride] = tgroup; ++sp; }
+                uint2 sentinel; sentinel.x = 0xFFFFFFFFu; sentinel.y = 0;
+                stack[sp * stride] = sentinel; ++sp;
+                to_instance_space(ip, world, ray);
+                make_wide_ray(ray, wr);
+                TreeDesc td; load_tree_desc(s, meta.x, td);
+                wnodes = s.blob + td.wnodes;
+                wtris = s.blob + td.wtris;
+                poses = s.blob + td.poses;
+                in_instance = true;
+                cur_item = item;
+                ngroup.y = 0; tgroup.y = 0;
+                if (td.wnode_count != 0) fetch = 0;
+                break;
+            }
+        }
+        if (fetch != 0xFFFFFFFFu) continue;
+
+        // Next internal child of the current group, nearest octant slot first.
+        if (ngroup.y & 0xFF000000u)
+        {
+            const int bit = high_bit(ngroup.y);
+            ngroup.y &= ~(1u << bit);
+            const uint32_t k = static_cast<uint32_t>(bit - 24) ^ (7 - wr.oct);
+            fetch = ngroup.x + popc(ngroup.y & 0xFFu & ((1u << k) - 1u));
+            continue;
+        }
+
+        if (sp == 0) break;
+        --sp;
+        const uint2 top = stack[sp * stride];
+        if (top.x == 0xFFFFFFFFu && top.y == 0)
+        {
+            // Back to world space.
+            ray = world;
+            make_wide_ray(ray, wr);
+            wnodes = s.blob + s.top_wnodes;
+            in_instance = false;
+            ngroup.y = 0; tgroup.y = 0;
+            continue;
+        }
+        if (top.y & 0xFF000000u) { ngroup = top; tgroup.y = 0; }
+        else { tgroup = top; ngroup.y = 0; }
+    }
+    return !ANY && hit.item != 0xFFFFFFFFu;
+}
+
+}   // namespace asgpu

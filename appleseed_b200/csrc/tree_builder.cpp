@@ -1,0 +1,969 @@
+//
+// tree_builder.cpp -- host builder for reference-format trees.
+//
+// Produces, for the same input, the same binary BVHs the reference builds, so that the GPU
+// layouts derived from them (flatten.cpp) inherit the reference's leaf contents and visit order:
+//
+//   triangle trees   TriangleTree::build_bvh          renderer/kernel/intersection/triangletree.cpp:497-597
+//                    collect_*_triangles              :105-383
+//                    compute_motion_bboxes            :755-876
+//                    store_triangles + TriangleEncoder :878-978, triangleencoder.cpp:48-103
+//   assembly tree    AssemblyTree::rebuild_assembly_tree  assemblytree.cpp:111-245
+//   split search     bvh::SAHPartitioner::partition   foundation/math/bvh/bvh_sahpartitioner.h:99-170
+//   index upkeep     PartitionerBase::sort_indices    foundation/math/bvh/bvh_partitionerbase.h:135-198
+//   node order       bvh::Builder::subdivide_recurse  foundation/math/bvh/bvh_builder.h:163-229
+//
+// Unlike the reference's single-threaded recursion, the work is organised as independent range
+// tasks: the three initial centroid sorts run concurrently, the three per-axis sweeps of large
+// nodes run concurrently, and subtrees below a grain size are built in parallel into private
+// node arrays that are stitched into the reference's depth-first node order afterwards.  The
+// arithmetic (float boxes and costs for triangle trees, double for the assembly tree, no FMA
+// contraction -- this file is compiled with -ffp-contract=off) and every tie-break are the
+// reference's, so the resulting arrays are identical.
+//
+
+#include "tree_builder.h"
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cstring>
+#include <future>
+#include <limits>
+#include <thread>
+
+namespace asgpu
+{
+
+namespace
+{
+
+template <typename T>
+struct Bounds
+{
+    T lo[3], hi[3];
+
+    void reset()
+    {
+        for (int a = 0; a < 3; ++a)
+        {
+            lo[a] = std::numeric_limits<T>::max();
+            hi[a] = -std::numeric_limits<T>::max();
+        }
+    }
+
+    void grow(const T x, const T y, const T z)
+    {
+        const T p[3] = { x, y, z };
+        for (int a = 0; a < 3; ++a)
+        {
+            if (lo[a] > p[a]) lo[a] = p[a];
+            if (hi[a] < p[a]) hi[a] = p[a];
+        }
+    }
+
+    void grow(const Bounds& b)
+    {
+        for (int a = 0; a < 3; ++a)
+        {
+            if (lo[a] > b.lo[a]) lo[a] = b.lo[a];
+            if (hi[a] < b.hi[a]) hi[a] = b.hi[a];
+        }
+    }
+
+    // Number of axes with non-zero extent (AABBBase::rank, aabb.h:422-433).
+    int rank() const
+    {
+        return (lo[0] < hi[0] ? 1 : 0) + (lo[1] < hi[1] ? 1 : 0) + (lo[2] < hi[2] ? 1 : 0);
+    }
+
+    bool valid() const { return lo[0] <= hi[0] && lo[1] <= hi[1] && lo[2] <= hi[2]; }
+
+    // half_surface_area (aabb.h:723-730).
+    T half_area() const
+    {
+        const T ex = hi[0] - lo[0], ey = hi[1] - lo[1], ez = hi[2] - lo[2];
+        return ex * ey + ex * ez + ey * ez;
+    }
+};
+
+typedef Bounds<float> BoundsF;
+typedef Bounds<double> BoundsD;
+
+struct P3 { float x, y, z; };
+
+// Transform<double>::point_to_parent<float> (foundation/math/transform.h:346-375).
+inline P3 to_parent(const double* m, const P3& p)
+{
+    P3 r;
+    r.x = static_cast<float>(m[0] * double(p.x) + m[1] * double(p.y) + m[ 2] * double(p.z) + m[ 3]);
+    r.y = static_cast<float>(m[4] * double(p.x) + m[5] * double(p.y) + m[ 6] * double(p.z) + m[ 7]);
+    r.z = static_cast<float>(m[8] * double(p.x) + m[9] * double(p.y) + m[10] * double(p.z) + m[11]);
+    const float w = static_cast<float>(m[12] * double(p.x) + m[13] * double(p.y) + m[14] * double(p.z) + m[15]);
+    if (w != 1.0f) { r.x /= w; r.y /= w; r.z /= w; }
+    return r;
+}
+
+// Transform::to_parent(AABB) (transform.h:528-546): corner order matters only through min/max,
+// which is order-independent, but the point transform must be the float-returning one.
+inline BoundsF box_to_parent(const double* m, const BoundsF& b)
+{
+    if (!b.valid()) return b;
+    BoundsF r; r.reset();
+    for (int k = 0; k < 8; ++k)
+    {
+        const P3 c = { (k & 4) ? b.hi[0] : b.lo[0], (k & 2) ? b.hi[1] : b.lo[1], (k & 1) ? b.hi[2] : b.lo[2] };
+        const P3 q = to_parent(m, c);
+        r.grow(q.x, q.y, q.z);
+    }
+    return r;
+}
+
+// square_area(v0, v1, v2) == 0 (foundation/math/area.h:57-66), evaluated in float.
+inline bool degenerate(const P3& a, const P3& b, const P3& c)
+{
+    const float ux = b.x - a.x, uy = b.y - a.y, uz = b.z - a.z;
+    const float vx = c.x - a.x, vy = c.y - a.y, vz = c.z - a.z;
+    const float nx = uy * vz - vy * uz;
+    const float ny = uz * vx - vz * ux;
+    const float nz = ux * vy - vx * uy;
+    float s = 0.0f;
+    s += nx * nx; s += ny * ny; s += nz * nz;
+    return 0.25f * s == 0.0f;
+}
+
+//
+// Sweep-SAH range builder.
+//
+
+template <typename T>
+class SweepBuilder
+{
+  public:
+    typedef Bounds<T> Box;
+
+    SweepBuilder(const std::vector<Box>& boxes, size_t max_leaf_size, T traversal_cost, T item_cost, int threads)
+      : m_boxes(boxes)
+      , m_max_leaf(max_leaf_size)
+      , m_ct(traversal_cost)
+      , m_ci(item_cost)
+      , m_threads(threads < 1 ? 1 : threads)
+    {
+    }
+
+    // Final item ordering (PartitionerBase::get_item_ordering(0)).
+    const std::vector<uint32_t>& ordering() const { return m_order[0]; }
+
+    void build(AsNodeVector& nodes)
+    {
+        const size_t n = m_boxes.size();
+        sort_centroids(n);
+        m_scratch.resize(n);
+        m_side.resize(n);
+        for (int a = 0; a < 3; ++a) m_prefix[a].resize(n);
+
+        m_grain = std::max<size_t>(2048, n / (static_cast<size_t>(m_threads) * 16));
+
+        // Phase 1: expand the top of the tree serially (per-axis sweeps of each node run
+        // concurrently) down to ranges of at most m_grain items.
+        Box root; root.reset();
+        for (size_t i = 0; i < n; ++i) root.grow(m_boxes[m_order[0][i]]);
+        m_top.clear();
+        m_jobs.clear();
+        m_top.reserve(1024);
+        expand_top(0, n, widen(root));
+
+        // Phase 2: build the deferred subtrees in parallel, largest first.
+        std::vector<size_t> by_size(m_jobs.size());
+        for (size_t i = 0; i < by_size.size(); ++i) by_size[i] = i;
+        std::sort(by_size.begin(), by_size.end(), [this](size_t a, size_t b)
+        {
+            return (m_jobs[a].end - m_jobs[a].begin) > (m_jobs[b].end - m_jobs[b].begin);
+        });
+        std::atomic<size_t> next(0);
+        auto worker = [&]()
+        {
+            for (;;)
+            {
+                const size_t k = next.fetch_add(1);
+                if (k >= by_size.size()) break;
+                Job& job = m_jobs[by_size[k]];
+                build_range(job);
+            }
+        };
+        if (m_threads == 1 || m_jobs.size() < 2) worker();
+        else
+        {
+            std::vector<std::thread> pool;
+            for (int t = 0; t < m_threads; ++t) pool.emplace_back(worker);
+            for (std::thread& th : pool) th.join();
+        }
+
+        // Phase 3: lay everything out in the reference's depth-first order: a node's two
+        // children are adjacent and are followed by the whole left subtree, then the right one
+        // (bvh_builder.h:197-228).
+        size_t total = 1;
+        for (const TopNode& t : m_top) if (t.kind == Interior) total += 2;
+        for (const Job& j : m_jobs) total += j.nodes.size();
+        AsNode blank; std::memset(&blank, 0, sizeof(blank));
+        nodes.assign(total, blank);
+        size_t cursor = 1;
+        place(0, 0, cursor, nodes);
+    }
+
+  private:
+    enum Kind { Interior, Deferred };
+
+    struct TopNode
+    {
+        Kind    kind;
+        size_t  left, right;        // TopNode indices (Interior)
+        size_t  job;                // Job index (Deferred)
+        BoundsD left_box, right_box;
+    };
+
+    struct Job
+    {
+        size_t              begin, end;
+        BoundsD             box;
+        AsNode              root;       // the subtree's own root (lives in its parent's child pair)
+        std::vector<AsNode> nodes;      // descendants, child indices relative to nodes[0]
+    };
+
+    const std::vector<Box>&     m_boxes;
+    const size_t                m_max_leaf;
+    const T                     m_ct, m_ci;
+    const int                   m_threads;
+    size_t                      m_grain;
+    std::vector<uint32_t>       m_order[3];
+    std::vector<uint32_t>       m_scratch;
+    std::vector<uint8_t>        m_side;
+    std::vector<T>              m_prefix[3];
+    std::vector<TopNode>        m_top;
+    std::vector<Job>            m_jobs;
+
+    static BoundsD widen(const Box& b)
+    {
+        BoundsD r;
+        for (int a = 0; a < 3; ++a) { r.lo[a] = static_cast<double>(b.lo[a]); r.hi[a] = static_cast<double>(b.hi[a]); }
+        return r;
+    }
+
+    static Box narrow(const BoundsD& b)
+    {
+        Box r;
+        for (int a = 0; a < 3; ++a) { r.lo[a] = static_cast<T>(b.lo[a]); r.hi[a] = static_cast<T>(b.hi[a]); }
+        return r;
+    }
+
+    // PartitionerBase constructor (bvh_partitionerbase.h:95-120): identity order, then an
+    // unstable std::sort by (min + max) with a strict '<' (bvh_bboxsortpredicate.h:113-126).
+    // Ties fall where libstdc++'s introsort puts them, as they do in the reference; the key
+    // type must therefore also be the reference's (size_t), sorted here and narrowed after.
+    void sort_centroids(const size_t n)
+    {
+        auto sort_axis = [this, n](const int a)
+        {
+            std::vector<size_t> idx(n);
+            for (size_t i = 0; i < n; ++i) idx[i] = i;
+            const std::vector<Box>& bb = m_boxes;
+            std::sort(idx.begin(), idx.end(), [&bb, a](const size_t l, const size_t r)
+            {
+                return bb[l].lo[a] + bb[l].hi[a] < bb[r].lo[a] + bb[r].hi[a];
+            });
+            m_order[a].resize(n);
+            for (size_t i = 0; i < n; ++i) m_order[a][i] = static_cast<uint32_t>(idx[i]);
+        };
+        if (m_threads >= 3 && n > 50000)
+        {
+            std::thread t1(sort_axis, 1), t2(sort_axis, 2);
+            sort_axis(0);
+            t1.join(); t2.join();
+        }
+        else for (int a = 0; a < 3; ++a) sort_axis(a);
+    }
+
+    Box range_bounds(const size_t begin, const size_t end) const
+    {
+        Box b; b.reset();
+        for (size_t i = begin; i < end; ++i) b.grow(m_boxes[m_order[0][i]]);
+        return b;
+    }
+
+    struct Candidate { T cost; size_t pivot; };
+
+    // One axis of SAHPartitioner::partition (bvh_sahpartitioner.h:118-151): prefix areas left to
+    // right, then a right-to-left sweep keeping the strictly cheapest split.
+    Candidate sweep_axis(const int a, const size_t begin, const size_t end)
+    {
+        const size_t count = end - begin;
+        const uint32_t* order = m_order[a].data() + begin;
+        T* prefix = m_prefix[a].data() + begin;
+        Box acc;
+
+        acc.reset();
+        for (size_t i = 0; i + 1 < count; ++i)
+        {
+            acc.grow(m_boxes[order[i]]);
+            prefix[i] = acc.half_area();
+        }
+
+        Candidate best = { std::numeric_limits<T>::max(), 0 };
+        acc.reset();
+        for (size_t i = count - 1; i > 0; --i)
+        {
+            acc.grow(m_boxes[order[i]]);
+            const T left_cost = prefix[i - 1] * i;
+            const T right_cost = acc.half_area() * (count - i);
+            const T cost = left_cost + right_cost;
+            if (best.cost > cost) { best.cost = cost; best.pivot = i; }
+        }
+        return best;
+    }
+
+    // Returns the pivot (absolute position) or `end` when the range becomes a leaf.
+    size_t split(const size_t begin, const size_t end, const Box& box, const bool concurrent_axes)
+    {
+        if (box.rank() < 2) return end;                 // only degenerate items
+        const size_t count = end - begin;
+        if (count <= m_max_leaf) return end;
+
+        Candidate cand[3];
+        if (concurrent_axes)
+        {
+            std::future<Candidate> f1 = std::async(std::launch::async, [=]() { return sweep_axis(1, begin, end); });
+            std::future<Candidate> f2 = std::async(std::launch::async, [=]() { return sweep_axis(2, begin, end); });
+            cand[0] = sweep_axis(0, begin, end);
+            cand[1] = f1.get();
+            cand[2] = f2.get();
+        }
+        else for (int a = 0; a < 3; ++a) cand[a] = sweep_axis(a, begin, end);
+
+        // First axis / first pivot wins ties: strict '>' in axis order (bvh_sahpartitioner.h:144).
+        T best_cost = std::numeric_limits<T>::max();
+        int best_axis = 0;
+        size_t best_pivot = 0;
+        for (int a = 0; a < 3; ++a)
+            if (best_cost > cand[a].cost) { best_cost = cand[a].cost; best_axis = a; best_pivot = cand[a].pivot; }
+
+        const T split_cost = m_ct + best_cost / box.half_area() * m_ci;
+        const T leaf_cost = count * m_ci;
+        if (leaf_cost <= split_cost) return end;
+
+        const size_t pivot = begin + best_pivot;
+        repartition(best_axis, begin, end, pivot);
+        return pivot;
+    }
+
+    // PartitionerBase::sort_indices (bvh_partitionerbase.h:135-198): stable partition of the two
+    // other axes' orders by membership in the left set of the split axis.
+    void repartition(const int axis, const size_t begin, const size_t end, const size_t pivot)
+    {
+        const uint32_t* split_order = m_order[axis].data();
+        for (size_t i = begin; i < pivot; ++i) m_side[split_order[i]] = 0;
+        for (size_t i = pivot; i < end; ++i) m_side[split_order[i]] = 1;
+        for (int a = 0; a < 3; ++a)
+        {
+            if (a == axis) continue;
+            uint32_t* order = m_order[a].data();
+            size_t l = begin, r = pivot;
+            for (size_t i = begin; i < end; ++i)
+            {
+                const uint32_t item = order[i];
+                if (m_side[item] == 0) m_scratch[l++] = item;
+                else m_scratch[r++] = item;
+            }
+            std::memcpy(order + begin, m_scratch.data() + begin, (end - begin) * sizeof(uint32_t));
+        }
+    }
+
+    static void set_child_box(AsNode& node, const int side, const BoundsD& b)
+    {
+        for (int a = 0; a < 3; ++a)
+        {
+            node.bbox[a * 4 + side] = b.lo[a];
+            node.bbox[a * 4 + 2 + side] = b.hi[a];
+        }
+    }
+
+    size_t expand_top(const size_t begin, const size_t end, const BoundsD& box)
+    {
+        const size_t self = m_top.size();
+        m_top.push_back(TopNode());
+        if (end - begin <= m_grain)
+        {
+            m_top[self].kind = Deferred;
+            m_top[self].job = m_jobs.size();
+            Job job;
+            job.begin = begin; job.end = end; job.box = box;
+            m_jobs.push_back(std::move(job));
+            return self;
+        }
+        const size_t pivot = split(begin, end, narrow(box), m_threads >= 3);
+        if (pivot == end)
+        {
+            // A large range that refuses to split (all-degenerate boxes): a single-leaf job.
+            m_top[self].kind = Deferred;
+            m_top[self].job = m_jobs.size();
+            Job job;
+            job.begin = begin; job.end = end; job.box = box;
+            m_jobs.push_back(std::move(job));
+            m_jobs.back().nodes.clear();
+            return self;
+        }
+        const BoundsD lb = widen(range_bounds(begin, pivot));
+        const BoundsD rb = widen(range_bounds(pivot, end));
+        const size_t l = expand_top(begin, pivot, lb);
+        const size_t r = expand_top(pivot, end, rb);
+        TopNode& t = m_top[self];
+        t.kind = Interior;
+        t.left = l; t.right = r;
+        t.left_box = lb; t.right_box = rb;
+        return self;
+    }
+
+    // Builds one deferred range with an explicit stack; child indices are relative to job.nodes[0].
+    void build_range(Job& job)
+    {
+        struct Task { size_t slot; size_t begin, end; BoundsD box; };   // slot: index in job.nodes, or ~0 for job.root
+        AsNode blank; std::memset(&blank, 0, sizeof(blank));
+        job.root = blank;
+        job.nodes.clear();
+        job.nodes.reserve(2 * (job.end - job.begin) / (m_max_leaf ? m_max_leaf : 1) + 2);
+
+        std::vector<Task> stack;
+        stack.push_back(Task{ ~size_t(0), job.begin, job.end, job.box });
+        while (!stack.empty())
+        {
+            const Task t = stack.back();
+            stack.pop_back();
+
+            size_t pivot = t.end;
+            if (t.end - t.begin > 1)
+                pivot = split(t.begin, t.end, narrow(t.box), false);
+
+            if (pivot == t.end)
+            {
+                AsNode& node = t.slot == ~size_t(0) ? job.root : job.nodes[t.slot];
+                node.item_count = static_cast<uint32_t>(t.end - t.begin);
+                node.index = static_cast<uint32_t>(t.begin);
+                continue;
+            }
+
+            const BoundsD lb = widen(range_bounds(t.begin, pivot));
+            const BoundsD rb = widen(range_bounds(pivot, t.end));
+            const size_t pair = job.nodes.size();
+            job.nodes.push_back(blank);
+            job.nodes.push_back(blank);
+            AsNode& node = t.slot == ~size_t(0) ? job.root : job.nodes[t.slot];
+            node.item_count = 0xFFFFFFFFu;
+            node.index = static_cast<uint32_t>(pair);
+            set_child_box(node, 0, lb);
+            set_child_box(node, 1, rb);
+            // Left subtree first: push right, then left.
+            stack.push_back(Task{ pair + 1, pivot, t.end, rb });
+            stack.push_back(Task{ pair, t.begin, pivot, lb });
+        }
+    }
+
+    void place(const size_t top_index, const size_t slot, size_t& cursor, AsNodeVector& nodes)
+    {
+        const TopNode& t = m_top[top_index];
+        if (t.kind == Interior)
+        {
+            const size_t pair = cursor;
+            cursor += 2;
+            AsNode& node = nodes[slot];
+            node.item_count = 0xFFFFFFFFu;
+            node.index = static_cast<uint32_t>(pair);
+            set_child_box(node, 0, t.left_box);
+            set_child_box(node, 1, t.right_box);
+            place(t.left, pair, cursor, nodes);
+            place(t.right, pair + 1, cursor, nodes);
+        }
+        else
+        {
+            const Job& job = m_jobs[t.job];
+            const size_t base = cursor;
+            cursor += job.nodes.size();
+            nodes[slot] = job.root;
+            if (nodes[slot].interior()) nodes[slot].index += static_cast<uint32_t>(base);
+            for (size_t i = 0; i < job.nodes.size(); ++i)
+            {
+                AsNode& dst = nodes[base + i];
+                dst = job.nodes[i];
+                if (dst.interior()) dst.index += static_cast<uint32_t>(base);
+            }
+        }
+    }
+};
+
+//
+// Triangle collection (triangletree.cpp:105-383).
+//
+
+struct TriInfo { uint64_t first_vertex; uint32_t msc; uint32_t vis; };
+
+struct Collected
+{
+    std::vector<AsTriangleKey>  keys;
+    std::vector<TriInfo>        infos;
+    std::vector<P3>             vertices;       // assembly space, float; (msc + 1) * 3 per triangle, pose-major
+    std::vector<BoundsF>        boxes;          // build boxes (mid-time box for moving triangles)
+};
+
+inline P3 vertex_at(const asgpu_mesh& m, const size_t i)
+{
+    const P3 p = { m.vertices[i * 3], m.vertices[i * 3 + 1], m.vertices[i * 3 + 2] };
+    return p;
+}
+
+inline P3 pose_at(const asgpu_mesh& m, const size_t v, const size_t seg)
+{
+    const float* q = m.vertex_poses + (v * m.motion_segment_count + seg) * 3;
+    const P3 p = { q[0], q[1], q[2] };
+    return p;
+}
+
+// First two stages of foundation::intersect(bbox, v0, v1, v2) (intersection/aabbtriangle.h):
+// a vertex inside the box accepts, all vertices beyond one face rejects.  The tree box is the
+// union of the object instances' boxes (assemblytree.cpp:401-405), so triangles of this assembly
+// always take the first exit; anything else is kept (conservative).
+inline bool touches(const BoundsF& b, const P3& v0, const P3& v1, const P3& v2)
+{
+    const P3* vs[3] = { &v0, &v1, &v2 };
+    unsigned all = 0;
+    for (int k = 0; k < 3; ++k)
+    {
+        const float p[3] = { vs[k]->x, vs[k]->y, vs[k]->z };
+        unsigned m = 0;
+        for (int a = 0; a < 3; ++a)
+        {
+            if (p[a] >= b.lo[a]) m |= 1u << a;
+            if (p[a] <= b.hi[a]) m |= 8u << a;
+        }
+        if (m == 0x3F) return true;
+        all |= m;
+    }
+    return all == 0x3F;
+}
+
+void collect(const asgpu_scene_desc& desc, const asgpu_assembly& assembly, const BoundsF& tree_box, Collected& out)
+{
+    const double time = assembly.time;
+    uint64_t vertex_cursor = 0;
+    std::vector<BoundsF> pose_box;
+
+    for (uint32_t oi = 0; oi < assembly.object_instance_count; ++oi)
+    {
+        const asgpu_object_instance& inst = assembly.object_instances[oi];
+        const asgpu_mesh& mesh = desc.meshes[inst.mesh_index];
+        const double* m = inst.local_to_parent;
+        const uint32_t msc = mesh.motion_segment_count;
+        pose_box.resize(msc + 1);
+
+        for (uint32_t ti = 0; ti < mesh.triangle_count; ++ti)
+        {
+            const uint32_t* tv = mesh.triangles + size_t(ti) * 3;
+            BoundsF build_box;
+            const size_t vertex_mark = out.vertices.size();
+
+            if (msc == 0)
+            {
+                const P3 a_os = vertex_at(mesh, tv[0]), b_os = vertex_at(mesh, tv[1]), c_os = vertex_at(mesh, tv[2]);
+                if (degenerate(a_os, b_os, c_os)) continue;
+                const P3 a = to_parent(m, a_os), b = to_parent(m, b_os), c = to_parent(m, c_os);
+                if (degenerate(a, b, c)) continue;
+                if (!touches(tree_box, a, b, c)) continue;
+                build_box.reset();
+                build_box.grow(a.x, a.y, a.z); build_box.grow(b.x, b.y, b.z); build_box.grow(c.x, c.y, c.z);
+                out.vertices.push_back(a); out.vertices.push_back(b); out.vertices.push_back(c);
+            }
+            else
+            {
+                // Pose 0 is the base mesh, poses 1..msc the vertex poses (triangletree.cpp:238-256).
+                for (uint32_t s = 0; s <= msc; ++s)
+                {
+                    pose_box[s].reset();
+                    for (int k = 0; k < 3; ++k)
+                    {
+                        const P3 p = to_parent(m, s == 0 ? vertex_at(mesh, tv[k]) : pose_at(mesh, tv[k], s - 1));
+                        pose_box[s].grow(p.x, p.y, p.z);
+                        out.vertices.push_back(p);
+                    }
+                }
+                BoundsF motion_box = pose_box[0];
+                for (uint32_t s = 1; s <= msc; ++s) motion_box.grow(pose_box[s]);
+                bool keep = motion_box.rank() >= 2;
+                for (int a = 0; keep && a < 3; ++a)
+                    if (tree_box.lo[a] > motion_box.hi[a] || tree_box.hi[a] < motion_box.lo[a]) keep = false;
+                if (keep)
+                {
+                    // Box at acceleration_structure.time (renderer/utility/bbox.h:110-125):
+                    // lerp(a, b, k) = (1 - k) * a + k * b in float.
+                    const size_t prev = static_cast<size_t>(time * msc);
+                    const float k = static_cast<float>(time * msc - prev);
+                    const float w = 1.0f - k;
+                    for (int a = 0; a < 3; ++a)
+                    {
+                        build_box.lo[a] = w * pose_box[prev].lo[a] + k * pose_box[prev + 1].lo[a];
+                        build_box.hi[a] = w * pose_box[prev].hi[a] + k * pose_box[prev + 1].hi[a];
+                    }
+                    keep = build_box.rank() >= 2;
+                }
+                if (!keep) { out.vertices.resize(vertex_mark); continue; }
+            }
+
+            AsTriangleKey key; std::memset(&key, 0, sizeof(key));
+            key.object_instance_index = oi;
+            key.triangle_index = ti;
+            key.triangle_pa = mesh.triangle_pa ? mesh.triangle_pa[ti] : 0;
+            out.keys.push_back(key);
+            const TriInfo info = { vertex_cursor, msc, inst.vis_flags };
+            out.infos.push_back(info);
+            out.boxes.push_back(build_box);
+            vertex_cursor += uint64_t(msc + 1) * 3;
+        }
+    }
+}
+
+//
+// Motion boxes (triangletree.cpp:755-876), bottom-up with an explicit post-order walk.
+//
+
+typedef std::vector<BoundsF> BoxSeq;
+
+BoxSeq leaf_motion_boxes(const AsNode& node, const std::vector<uint32_t>& order, const Collected& c)
+{
+    uint32_t max_msc = 0;
+    BoundsF base; base.reset();
+    for (uint32_t i = 0; i < node.item_count; ++i)
+    {
+        const TriInfo& info = c.infos[order[node.index + i]];
+        max_msc = std::max(max_msc, info.msc);
+        for (int k = 0; k < 3; ++k)
+        {
+            const P3& p = c.vertices[info.first_vertex + k];
+            base.grow(p.x, p.y, p.z);
+        }
+    }
+    BoxSeq seq(max_msc + 1);
+    seq[0] = base;
+    if (max_msc == 0) return seq;
+
+    for (uint32_t s = 1; s < max_msc; ++s)
+    {
+        seq[s].reset();
+        const double time = static_cast<double>(s) / max_msc;
+        for (uint32_t i = 0; i < node.item_count; ++i)
+        {
+            const TriInfo& info = c.infos[order[node.index + i]];
+            const size_t prev = static_cast<size_t>(time * info.msc);
+            const float k = static_cast<float>(time * info.msc - prev);
+            const float w = 1.0f - k;
+            const P3* a = &c.vertices[info.first_vertex + prev * 3];
+            for (int v = 0; v < 3; ++v)
+                seq[s].grow(w * a[v].x + k * a[v + 3].x, w * a[v].y + k * a[v + 3].y, w * a[v].z + k * a[v + 3].z);
+        }
+    }
+    seq[max_msc].reset();
+    for (uint32_t i = 0; i < node.item_count; ++i)
+    {
+        const TriInfo& info = c.infos[order[node.index + i]];
+        const P3* a = &c.vertices[info.first_vertex + size_t(info.msc) * 3];
+        for (int v = 0; v < 3; ++v) seq[max_msc].grow(a[v].x, a[v].y, a[v].z);
+    }
+    return seq;
+}
+
+void append_swizzled(std::vector<double>& dst, const BoxSeq& seq)      // triangletree.cpp:725-738
+{
+    for (const BoundsF& b : seq)
+        for (int a = 0; a < 3; ++a)
+        {
+            dst.push_back(static_cast<double>(b.lo[a]));
+            dst.push_back(static_cast<double>(b.hi[a]));
+        }
+}
+
+// The reference recursion numbers m_node_bboxes entries in post-order (left subtree, right
+// subtree, then this node's left and right sequences); the explicit stack below reproduces it.
+void propagate_motion_boxes(HostTriangleTree& tree, const std::vector<uint32_t>& order, const Collected& c)
+{
+    if (tree.moving_triangle_count == 0)
+    {
+        // Every sequence has length one: the walk would only set both counts to 1.
+        for (AsNode& node : tree.nodes)
+            if (node.interior()) node.left_bbox_count = node.right_bbox_count = 1;
+        return;
+    }
+
+    struct Frame { uint32_t node; int stage; BoxSeq left; };
+    std::vector<Frame> stack;
+    std::vector<BoxSeq> results;        // return values travelling up
+    stack.push_back(Frame{ 0, 0, BoxSeq() });
+    while (!stack.empty())
+    {
+        Frame& f = stack.back();
+        AsNode& node = tree.nodes[f.node];
+        if (!node.interior())
+        {
+            results.push_back(leaf_motion_boxes(node, order, c));
+            stack.pop_back();
+            continue;
+        }
+        if (f.stage == 0)
+        {
+            f.stage = 1;
+            const uint32_t child = node.index;
+            stack.push_back(Frame{ child, 0, BoxSeq() });
+            continue;
+        }
+        if (f.stage == 1)
+        {
+            f.left = std::move(results.back());
+            results.pop_back();
+            f.stage = 2;
+            const uint32_t child = node.index + 1;
+            stack.push_back(Frame{ child, 0, BoxSeq() });
+            continue;
+        }
+        BoxSeq right = std::move(results.back());
+        results.pop_back();
+        const BoxSeq& left = f.left;
+
+        node.left_bbox_count = static_cast<uint32_t>(left.size());
+        node.right_bbox_count = static_cast<uint32_t>(right.size());
+        if (left.size() > 1)
+        {
+            node.left_bbox_index = static_cast<uint32_t>(tree.node_bboxes.size() / 6);
+            append_swizzled(tree.node_bboxes, left);
+        }
+        if (right.size() > 1)
+        {
+            node.right_bbox_index = static_cast<uint32_t>(tree.node_bboxes.size() / 6);
+            append_swizzled(tree.node_bboxes, right);
+        }
+        const size_t count = std::max(left.size(), right.size());
+        BoxSeq merged(count);
+        for (size_t i = 0; i < count; ++i)
+        {
+            merged[i] = left[i * left.size() / count];
+            merged[i].grow(right[i * right.size() / count]);
+        }
+        results.push_back(std::move(merged));
+        stack.pop_back();
+    }
+}
+
+//
+// Leaf payloads (triangleencoder.cpp:48-103, triangletree.cpp:878-978).
+//
+
+size_t payload_size(const AsNode& node, const std::vector<uint32_t>& order, const Collected& c)
+{
+    size_t s = 0;
+    for (uint32_t i = 0; i < node.item_count; ++i)
+    {
+        const uint32_t msc = c.infos[order[node.index + i]].msc;
+        s += 8 + (msc == 0 ? AsTriangleBytes : (size_t(msc) + 1) * AsPoseBytes);
+    }
+    return s;
+}
+
+uint8_t* write_payload(uint8_t* out, const uint32_t first, const uint32_t count, const std::vector<uint32_t>& order, const Collected& c)
+{
+    for (uint32_t i = 0; i < count; ++i)
+    {
+        const TriInfo& info = c.infos[order[first + i]];
+        std::memcpy(out, &info.vis, 4); out += 4;
+        std::memcpy(out, &info.msc, 4); out += 4;
+        const P3* v = &c.vertices[info.first_vertex];
+        if (info.msc == 0)
+        {
+            // TriangleMT<float>(v0, v1, v2): edges in float (raytrianglemt.h:128-137).
+            const float tri[9] = { v[0].x, v[0].y, v[0].z,
+                                   v[1].x - v[0].x, v[1].y - v[0].y, v[1].z - v[0].z,
+                                   v[2].x - v[0].x, v[2].y - v[0].y, v[2].z - v[0].z };
+            std::memcpy(out, tri, AsTriangleBytes); out += AsTriangleBytes;
+        }
+        else
+        {
+            const size_t bytes = (size_t(info.msc) + 1) * AsPoseBytes;
+            std::memcpy(out, v, bytes); out += bytes;
+        }
+    }
+    return out;
+}
+
+void store_leaves(HostTriangleTree& tree, const std::vector<uint32_t>& order, const Collected& c)
+{
+    const size_t in_node_limit = AsNodeUserDataSize - sizeof(uint32_t);     // 92 bytes
+    size_t spill = 0;
+    for (const AsNode& node : tree.nodes)
+        if (!node.interior())
+        {
+            const size_t s = payload_size(node, order, c);
+            if (s > in_node_limit) spill += s;
+        }
+    tree.leaf_data.resize(spill);
+    tree.keys.reserve(order.size());
+    uint8_t* spill_writer = tree.leaf_data.data();
+
+    for (AsNode& node : tree.nodes)
+    {
+        if (node.interior()) continue;
+        const uint32_t first = node.index, count = node.item_count;
+        const size_t s = payload_size(node, order, c);
+        node.index = static_cast<uint32_t>(tree.keys.size());
+        for (uint32_t j = 0; j < count; ++j) tree.keys.push_back(c.keys[order[first + j]]);
+        uint8_t* user = node.user_data();
+        if (s <= in_node_limit)
+        {
+            const uint32_t in_node = 0xFFFFFFFFu;
+            std::memcpy(user, &in_node, 4);
+            write_payload(user + 4, first, count, order, c);
+        }
+        else
+        {
+            const uint32_t offset = static_cast<uint32_t>(spill_writer - tree.leaf_data.data());
+            std::memcpy(user, &offset, 4);
+            spill_writer = write_payload(spill_writer, first, count, order, c);
+        }
+    }
+}
+
+bool check_desc(const asgpu_scene_desc& d, std::string& error)
+{
+    if ((d.mesh_count && !d.meshes) || (d.assembly_count && !d.assemblies) || (d.assembly_instance_count && !d.assembly_instances))
+    { error = "scene description has a null array"; return false; }
+    for (uint32_t i = 0; i < d.mesh_count; ++i)
+    {
+        const asgpu_mesh& m = d.meshes[i];
+        if ((m.vertex_count && !m.vertices) || (m.triangle_count && !m.triangles)) { error = "mesh with null vertex/triangle array"; return false; }
+        if (m.motion_segment_count && !m.vertex_poses) { error = "moving mesh without vertex poses"; return false; }
+        for (size_t k = 0; k < size_t(m.triangle_count) * 3; ++k)
+            if (m.triangles[k] >= m.vertex_count) { error = "triangle vertex index out of range"; return false; }
+    }
+    for (uint32_t a = 0; a < d.assembly_count; ++a)
+    {
+        const asgpu_assembly& as = d.assemblies[a];
+        if (as.object_instance_count && !as.object_instances) { error = "assembly with null object instance array"; return false; }
+        if (as.max_leaf_size == 0) { error = "max_leaf_size must be positive"; return false; }
+        if (!(as.time >= 0.0 && as.time < 1.0)) { error = "acceleration_structure.time must be in [0, 1)"; return false; }
+        for (uint32_t o = 0; o < as.object_instance_count; ++o)
+            if (as.object_instances[o].mesh_index >= d.mesh_count) { error = "object instance mesh index out of range"; return false; }
+    }
+    for (uint32_t i = 0; i < d.assembly_instance_count; ++i)
+        if (d.assembly_instances[i].assembly_index >= d.assembly_count) { error = "assembly instance index out of range"; return false; }
+    return true;
+}
+
+}   // anonymous namespace
+
+bool build_host_trees(const asgpu_scene_desc& desc, int threads, HostTrees& out, std::string& error)
+{
+    if (!check_desc(desc, error)) return false;
+    if (threads < 1) threads = std::max(1u, std::thread::hardware_concurrency());
+    const auto t0 = std::chrono::steady_clock::now();
+
+    // Assembly-space boxes: Assembly::compute_non_hierarchical_local_bbox
+    // (renderer/modeling/scene/assembly.cpp:219-225) over ObjectInstance::compute_parent_bbox
+    // (objectinstance.cpp:255-267) over StaticTessellation::compute_local_bbox
+    // (statictessellation.h:462-479).
+    std::vector<BoundsF> mesh_box(desc.mesh_count);
+    for (uint32_t i = 0; i < desc.mesh_count; ++i)
+    {
+        const asgpu_mesh& m = desc.meshes[i];
+        BoundsF b; b.reset();
+        for (uint32_t v = 0; v < m.vertex_count; ++v)
+        {
+            b.grow(m.vertices[size_t(v) * 3], m.vertices[size_t(v) * 3 + 1], m.vertices[size_t(v) * 3 + 2]);
+            for (uint32_t s = 0; s < m.motion_segment_count; ++s)
+            {
+                const P3 p = pose_at(m, v, s);
+                b.grow(p.x, p.y, p.z);
+            }
+        }
+        mesh_box[i] = b;
+    }
+
+    out.assembly_to_tree.assign(desc.assembly_count, -1);
+    std::vector<BoundsF> assembly_box(desc.assembly_count);
+    for (uint32_t a = 0; a < desc.assembly_count; ++a)
+    {
+        const asgpu_assembly& assembly = desc.assemblies[a];
+        BoundsF ab; ab.reset();
+        for (uint32_t o = 0; o < assembly.object_instance_count; ++o)
+        {
+            const asgpu_object_instance& oi = assembly.object_instances[o];
+            ab.grow(box_to_parent(oi.local_to_parent, mesh_box[oi.mesh_index]));
+        }
+        assembly_box[a] = ab;
+        if (assembly.object_instance_count == 0) continue;
+
+        // One triangle tree per assembly with mesh instances (assemblytree.cpp:372-420).
+        out.assembly_to_tree[a] = static_cast<int>(out.triangle_trees.size());
+        out.triangle_trees.emplace_back(new HostTriangleTree());
+        HostTriangleTree& tree = *out.triangle_trees.back();
+
+        Collected c;
+        collect(desc, assembly, ab, c);
+        if (c.keys.size() >= 0xFFFFFFFFull) { error = "too many triangles in one assembly"; return false; }
+        for (const TriInfo& info : c.infos) (info.msc == 0 ? tree.static_triangle_count : tree.moving_triangle_count) += 1;
+
+        SweepBuilder<float> builder(c.boxes, assembly.max_leaf_size, assembly.interior_node_traversal_cost,
+                                    assembly.triangle_intersection_cost, threads);
+        builder.build(tree.nodes);
+        propagate_motion_boxes(tree, builder.ordering(), c);
+        store_leaves(tree, builder.ordering(), c);
+    }
+
+    // Top level (assemblytree.cpp:111-245): one item per assembly instance whose assembly has
+    // object instances; box = to_parent(assembly box) widened to double and robust_grow(1e-15)
+    // (aabb.h:621-641); SAH with leaf size 1 and costs (1, 10) (intersectionsettings.h:51-53).
+    std::vector<asgpu_assembly_item> items;
+    std::vector<BoundsD> item_box;
+    for (uint32_t i = 0; i < desc.assembly_instance_count; ++i)
+    {
+        const asgpu_assembly_instance& inst = desc.assembly_instances[i];
+        if (desc.assemblies[inst.assembly_index].object_instance_count == 0) continue;
+        asgpu_assembly_item item; std::memset(&item, 0, sizeof(item));
+        std::memcpy(item.parent_to_local, inst.parent_to_local, sizeof(item.parent_to_local));
+        item.assembly_instance = i;
+        item.triangle_tree = static_cast<uint32_t>(out.assembly_to_tree[inst.assembly_index]);
+        item.vis_flags = inst.vis_flags;
+        items.push_back(item);
+
+        const BoundsF wb = box_to_parent(inst.local_to_parent, assembly_box[inst.assembly_index]);
+        BoundsD b;
+        for (int a = 0; a < 3; ++a)
+        {
+            b.lo[a] = static_cast<double>(wb.lo[a]);
+            b.hi[a] = static_cast<double>(wb.hi[a]);
+        }
+        for (int a = 0; a < 3; ++a)
+        {
+            const double centre = 0.5 * (b.lo[a] + b.hi[a]);
+            const double extent = b.hi[a] - b.lo[a];
+            double dominant = centre < 0.0 ? -centre : centre;
+            if (extent > dominant) dominant = extent;
+            if (!(dominant > 1.0)) dominant = 1.0;
+            const double delta = dominant * 1.0e-15;
+            b.lo[a] -= delta;
+            b.hi[a] += delta;
+        }
+        item_box.push_back(b);
+    }
+
+    SweepBuilder<double> top_builder(item_box, 1, 1.0, 10.0, threads);
+    top_builder.build(out.assembly_tree.nodes);
+    out.assembly_tree.items.resize(items.size());
+    for (size_t i = 0; i < items.size(); ++i)
+        out.assembly_tree.items[i] = items[top_builder.ordering()[i]];
+
+    out.build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return true;
+}
+
+}   // namespace asgpu

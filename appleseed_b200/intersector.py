@@ -1,0 +1,286 @@
+"""Host-side mirror of the reference interface for the path, over the C ABI.
+
+Names follow the reference (renderer/kernel/intersection):
+
+* ``TraceContext``  <-> ``renderer::TraceContext`` (tracecontext.h:52): owns the acceleration
+  structures of a scene; ``update()`` there == construction here (build the reference-format
+  trees, flatten them, upload the blob).  Immutable afterwards, shareable between intersectors.
+* ``Intersector``   <-> ``renderer::Intersector`` (intersector.h:66-145): ``trace`` (closest hit)
+  and ``trace_probe`` (any hit), but on BATCHES of rays (wavefront queues) instead of one ray per
+  call.  Results are ``asgpu_hit`` records (``scene.HIT_DTYPE``) mirroring the ShadingPoint
+  primary block.
+
+torch is used only for device memory, streams and (elsewhere) torch.distributed; every compute
+call goes through ``libasgpu.so``.  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+
+from . import _lib
+from .scene import HIT_DTYPE, CRays, RayBatch, SceneDesc
+
+HIT_BYTES = HIT_DTYPE.itemsize
+
+
+class AsgpuError(RuntimeError):
+    pass
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        raise AsgpuError("%s failed (%d): %s" % (what, rc, _lib.last_error()))
+
+
+class HostTrees:
+    """Reference-format trees built on the host (``asgpu_trees_build``)."""
+
+    def __init__(self, desc: SceneDesc, threads: int = 0):
+        self.lib = _lib.load()
+        self._cdesc, self._keep = desc.to_c()
+        self.handle = self.lib.asgpu_trees_build(C.byref(self._cdesc), threads)
+        if not self.handle:
+            raise AsgpuError("asgpu_trees_build failed: " + _lib.last_error())
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.asgpu_trees_destroy(self.handle)
+            self.handle = None
+
+    __del__ = close
+
+    @property
+    def build_seconds(self) -> float:
+        return float(self.lib.asgpu_trees_build_seconds(self.handle))
+
+    @property
+    def triangle_tree_count(self) -> int:
+        return int(self.lib.asgpu_trees_triangle_tree_count(self.handle))
+
+    def triangle_tree_view(self, i: int) -> "_lib.TriangleTreeView":
+        v = _lib.TriangleTreeView()
+        _check(self.lib.asgpu_trees_get_triangle_tree(self.handle, i, C.byref(v)), "asgpu_trees_get_triangle_tree")
+        return v
+
+    def assembly_tree_view(self) -> "_lib.AssemblyTreeView":
+        v = _lib.AssemblyTreeView()
+        _check(self.lib.asgpu_trees_get_assembly_tree(self.handle, C.byref(v)), "asgpu_trees_get_assembly_tree")
+        return v
+
+    @staticmethod
+    def _bytes(ptr, n):
+        if not ptr or n == 0:
+            return np.zeros(0, dtype=np.uint8)
+        return np.frombuffer((C.c_uint8 * n).from_address(ptr), dtype=np.uint8).copy()
+
+    def triangle_tree(self, i: int) -> dict:
+        v = self.triangle_tree_view(i)
+        return {
+            "nodes": self._bytes(v.nodes, v.node_count * 128),
+            "node_bboxes": self._bytes(v.node_bboxes, v.node_bbox_count * 48).view(np.float64),
+            "leaf_data": self._bytes(v.leaf_data, v.leaf_data_size),
+            "triangle_keys": self._bytes(v.triangle_keys, v.triangle_key_count * 12),
+            "static_triangle_count": int(v.static_triangle_count),
+            "moving_triangle_count": int(v.moving_triangle_count),
+        }
+
+    def assembly_tree(self) -> dict:
+        v = self.assembly_tree_view()
+        n = int(v.item_count)
+        items = [v.items[i] for i in range(n)]
+        return {
+            "nodes": self._bytes(v.nodes, v.node_count * 128),
+            "item_assembly_instance": np.array([it.assembly_instance for it in items], dtype=np.uint32),
+            "item_tree": np.array([it.triangle_tree for it in items], dtype=np.uint32),
+        }
+
+
+@dataclass
+class DeviceRays:
+    """A ray batch resident in HBM (torch CUDA tensors, one per ShadingRay field)."""
+    org: "torch.Tensor"
+    dir: "torch.Tensor"
+    tmin: "torch.Tensor"
+    tmax: "torch.Tensor"
+    time_absolute: Optional["torch.Tensor"] = None
+    time_normalized: Optional["torch.Tensor"] = None
+    flags: Optional["torch.Tensor"] = None
+
+    def __len__(self):
+        return int(self.tmin.shape[0])
+
+    @staticmethod
+    def from_host(rays: RayBatch, device, non_blocking: bool = False) -> "DeviceRays":
+        import torch
+
+        def up(a, dt):
+            if a is None:
+                return None
+            t = torch.from_numpy(a)
+            if dt is torch.uint32:
+                t = torch.from_numpy(a.view(np.int32))
+            return t.to(device, non_blocking=non_blocking)
+
+        return DeviceRays(up(rays.org, None), up(rays.dir, None), up(rays.tmin, None), up(rays.tmax, None),
+                          up(rays.time_absolute, None), up(rays.time_normalized, None), up(rays.flags, torch.uint32))
+
+    def to_c(self) -> CRays:
+        r = CRays()
+        r.org = self.org.data_ptr()
+        r.dir = self.dir.data_ptr()
+        r.tmin = self.tmin.data_ptr()
+        r.tmax = self.tmax.data_ptr()
+        r.time_absolute = self.time_absolute.data_ptr() if self.time_absolute is not None else None
+        r.time_normalized = self.time_normalized.data_ptr() if self.time_normalized is not None else None
+        r.flags = self.flags.data_ptr() if self.flags is not None else None
+        return r
+
+    @property
+    def bytes_per_ray(self) -> int:
+        b = 64
+        for t in (self.time_absolute, self.time_normalized, self.flags):
+            b += 4 if t is not None else 0
+        return b
+
+
+class TraceContext:
+    """Owns the flattened scene on one GPU."""
+
+    def __init__(self, desc: Optional[SceneDesc] = None, device: int = 0, flags: int = _lib.SCENE_DEFAULT,
+                 threads: int = 0, trees: Optional[HostTrees] = None, _handle=None):
+        self.lib = _lib.load()
+        self.device = device
+        self._borrowed_blob = None
+        if _handle is not None:
+            self.handle = _handle
+            self.build_seconds = 0.0
+        else:
+            own = trees is None
+            if own:
+                if desc is None:
+                    raise ValueError("TraceContext needs a SceneDesc or HostTrees")
+                trees = HostTrees(desc, threads)
+            n = trees.triangle_tree_count
+            views = (_lib.TriangleTreeView * max(1, n))()
+            for i in range(n):
+                views[i] = trees.triangle_tree_view(i)
+            top = trees.assembly_tree_view()
+            self.handle = self.lib.asgpu_scene_create(views, n, C.byref(top), flags, device)
+            self.build_seconds = trees.build_seconds
+            if own:
+                trees.close()
+        if not self.handle:
+            raise AsgpuError("scene creation failed: " + _lib.last_error())
+
+    @classmethod
+    def from_tree_views(cls, tree_views, top_view, device: int = 0, flags: int = _lib.SCENE_DEFAULT) -> "TraceContext":
+        """Flatten reference-format trees supplied by the caller (``asgpu_scene_create``)."""
+        lib = _lib.load()
+        n = len(tree_views)
+        arr = (_lib.TriangleTreeView * max(1, n))(*tree_views)
+        handle = lib.asgpu_scene_create(arr, n, C.byref(top_view), flags, device)
+        if not handle:
+            raise AsgpuError("asgpu_scene_create failed: " + _lib.last_error())
+        return cls(device=device, _handle=handle)
+
+    @classmethod
+    def from_blob(cls, blob: "torch.Tensor", adopt: bool = True) -> "TraceContext":
+        """Adopt a blob received from another rank (uint8 CUDA tensor)."""
+        lib = _lib.load()
+        device = blob.device.index
+        handle = lib.asgpu_scene_import_blob(blob.data_ptr(), blob.numel(), device, 1 if adopt else 0)
+        if not handle:
+            raise AsgpuError("asgpu_scene_import_blob failed: " + _lib.last_error())
+        ctx = cls(device=device, _handle=handle)
+        if adopt:
+            ctx._borrowed_blob = blob      # keep the memory alive
+        return ctx
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.asgpu_scene_destroy(self.handle)
+            self.handle = None
+
+    __del__ = close
+
+    @property
+    def blob_size(self) -> int:
+        return int(self.lib.asgpu_scene_blob_size(self.handle))
+
+    def blob_tensor(self) -> "torch.Tensor":
+        """A uint8 CUDA tensor holding a copy of the scene blob (the broadcast payload)."""
+        import torch
+        n = self.blob_size
+        out = torch.empty(n, dtype=torch.uint8, device="cuda:%d" % self.device)
+        src = self.lib.asgpu_scene_blob_device_ptr(self.handle)
+        cudart = torch.cuda.cudart()
+        rc = cudart.cudaMemcpy(out.data_ptr(), src, n, 3)   # cudaMemcpyDeviceToDevice
+        if int(rc) != 0:
+            raise AsgpuError("cudaMemcpy(blob) failed: %s" % rc)
+        return out
+
+    def info(self) -> dict:
+        v = _lib.SceneInfo()
+        _check(self.lib.asgpu_scene_get_info(self.handle, C.byref(v)), "asgpu_scene_get_info")
+        return v.as_dict()
+
+    def counters(self, reset: bool = False) -> dict:
+        v = _lib.Counters()
+        _check(self.lib.asgpu_get_counters(self.handle, C.byref(v), 1 if reset else 0), "asgpu_get_counters")
+        return v.as_dict()
+
+
+class Intersector:
+    """Batched ``trace`` / ``trace_probe`` on a ``TraceContext``."""
+
+    def __init__(self, trace_context: TraceContext):
+        self.ctx = trace_context
+        self.lib = trace_context.lib
+
+    # -- host buffers (copies inside the call) ---------------------------------------------------
+
+    def trace(self, rays: RayBatch, exact: bool = False, counters: bool = False, out: Optional[np.ndarray] = None) -> np.ndarray:
+        n = len(rays)
+        hits = np.empty(n, dtype=HIT_DTYPE) if out is None else out
+        cr = rays.to_c()
+        flags = (_lib.TRACE_EXACT if exact else 0) | (_lib.TRACE_COUNTERS if counters else 0)
+        _check(self.lib.asgpu_trace_host(self.ctx.handle, C.byref(cr), n, hits.ctypes.data if n else None, flags), "asgpu_trace_host")
+        return hits
+
+    def trace_probe(self, rays: RayBatch, exact: bool = False, counters: bool = False, out: Optional[np.ndarray] = None) -> np.ndarray:
+        n = len(rays)
+        occ = np.empty(n, dtype=np.uint8) if out is None else out
+        cr = rays.to_c()
+        flags = (_lib.TRACE_EXACT if exact else 0) | (_lib.TRACE_COUNTERS if counters else 0)
+        _check(self.lib.asgpu_trace_probe_host(self.ctx.handle, C.byref(cr), n, occ.ctypes.data if n else None, flags), "asgpu_trace_probe_host")
+        return occ
+
+    # -- device buffers (no copies; enqueued on torch's current stream) --------------------------
+
+    def trace_device(self, rays: DeviceRays, hits: "torch.Tensor", exact: bool = False, counters: bool = False):
+        """``hits``: uint8 CUDA tensor of n * 40 bytes receiving ``asgpu_hit`` records."""
+        import torch
+        n = len(rays)
+        assert hits.numel() * hits.element_size() >= n * HIT_BYTES
+        cr = rays.to_c()
+        flags = (_lib.TRACE_EXACT if exact else 0) | (_lib.TRACE_COUNTERS if counters else 0)
+        stream = torch.cuda.current_stream(self.ctx.device).cuda_stream
+        _check(self.lib.asgpu_trace(self.ctx.handle, C.byref(cr), n, hits.data_ptr(), flags, C.c_void_p(stream)), "asgpu_trace")
+
+    def trace_probe_device(self, rays: DeviceRays, occluded: "torch.Tensor", exact: bool = False, counters: bool = False):
+        import torch
+        n = len(rays)
+        assert occluded.numel() >= n
+        cr = rays.to_c()
+        flags = (_lib.TRACE_EXACT if exact else 0) | (_lib.TRACE_COUNTERS if counters else 0)
+        stream = torch.cuda.current_stream(self.ctx.device).cuda_stream
+        _check(self.lib.asgpu_trace_probe(self.ctx.handle, C.byref(cr), n, occluded.data_ptr(), flags, C.c_void_p(stream)), "asgpu_trace_probe")
+
+
+def hits_from_tensor(t: "torch.Tensor", n: int) -> np.ndarray:
+    """View a device hit buffer as ``HIT_DTYPE`` records on the host."""
+    return t.cpu().numpy().view(np.uint8)[: n * HIT_BYTES].view(HIT_DTYPE).copy()

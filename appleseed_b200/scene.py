@@ -105,7 +105,7 @@ class CRays(C.Structure):
     ]
 
 
-# Hit record, identical to asgpu_hit / orc_hit (40 bytes).
+# Hit record, identical to asgpu_hit in include/asgpu.h (40 bytes).
 HIT_DTYPE = np.dtype(
     [
         ("t", "<f8"),

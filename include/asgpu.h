@@ -1,0 +1,277 @@
+/*
+ * asgpu.h -- C ABI of the B200-native ray-intersection engine that stands in for
+ * appleseed's renderer::Intersector::trace() / trace_probe() path.
+ *
+ * Everything is plain C: opaque handles, plain pointers and sizes, no torch / CUDA types in
+ * the signatures (streams are passed as void*, i.e. a cudaStream_t).  Every function returns
+ * 0 on success or a negative ASGPU_E_* code (handles: NULL on failure); asgpu_last_error()
+ * returns a thread-local description.  Nothing throws across this boundary.
+ *
+ * Reference interfaces replaced (paths relative to src/appleseed/ of appleseedhq/appleseed):
+ *
+ *   asgpu_trees_build            TraceContext::update -> AssemblyTree::update
+ *                                  renderer/kernel/intersection/tracecontext.cpp:84-87,
+ *                                  assemblytree.cpp:95-245, triangletree.cpp:397-597
+ *   asgpu_scene_create           (new) flattens the reference's bvh::Tree arrays
+ *                                  foundation/math/bvh/bvh_tree.h:77-78, bvh_node.h:100-107,
+ *                                  triangletree.h:116-125, assemblytree.h:98-134
+ *   asgpu_trace                  Intersector::trace        intersector.cpp:124-189
+ *   asgpu_trace_probe            Intersector::trace_probe  intersector.cpp:191-238
+ *   asgpu_hit                    ShadingPoint primary block shading/shadingpoint.h:289-302,
+ *                                  written at assemblytree.cpp:733-744
+ *   asgpu_rays                   ShadingRay fields read by the path shading/shadingray.h:99-109
+ *   asgpu_get_counters           bvh::TraversalStatistics  foundation/math/bvh/bvh_statistics.h:84-93,
+ *                                  Intersector::get_statistics intersector.cpp:396-434
+ *   asgpu_scene_export_blob /
+ *   asgpu_scene_import_blob      (new) one contiguous device blob = the payload of the single
+ *                                  NCCL broadcast that replicates the scene to every GPU
+ */
+#ifndef ASGPU_H
+#define ASGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ASGPU_VERSION 1
+
+/* Error codes. */
+#define ASGPU_OK              0
+#define ASGPU_E_INVALID      -1     /* bad argument / malformed input */
+#define ASGPU_E_CUDA         -2     /* CUDA runtime error (no device, OOM, launch failure) */
+#define ASGPU_E_UNSUPPORTED  -3     /* input uses a feature outside the path */
+#define ASGPU_E_NOMEM        -4
+
+/* Ray visibility flags: renderer/modeling/scene/visibilityflags.h:50-64. */
+#define ASGPU_VIS_CAMERA        (1u << 0)
+#define ASGPU_VIS_LIGHT         (1u << 1)
+#define ASGPU_VIS_SHADOW        (1u << 2)
+#define ASGPU_VIS_TRANSPARENCY  (1u << 3)
+#define ASGPU_VIS_PROBE         (1u << 4)
+#define ASGPU_VIS_DIFFUSE       (1u << 5)
+#define ASGPU_VIS_GLOSSY        (1u << 6)
+#define ASGPU_VIS_SPECULAR      (1u << 7)
+#define ASGPU_VIS_SUBSURFACE    (1u << 8)
+#define ASGPU_VIS_NPR           (1u << 9)
+#define ASGPU_VIS_ALL           0xFFFFFFFFu
+
+#define ASGPU_MISS              0xFFFFFFFFu
+
+/* ------------------------------------------------------------------------------------------
+ * Scene description (input of the host builder).  Mirrors StaticTriangleTess, ObjectInstance,
+ * Assembly (+ its acceleration_structure parameters) and AssemblyInstance with a single-key
+ * TransformSequence.  Matrices are row-major 4x4 doubles, both directions supplied as
+ * foundation::Transformd stores them (foundation/math/transform.h:135-136).
+ * ------------------------------------------------------------------------------------------ */
+
+typedef struct asgpu_mesh {
+    const float*    vertices;               /* vertex_count * 3, object space */
+    const uint32_t* triangles;              /* triangle_count * 3 vertex indices */
+    const uint16_t* triangle_pa;            /* triangle_count primitive-attribute indices, or NULL */
+    const float*    vertex_poses;           /* vertex_count * motion_segment_count * 3, [v * msc + m], or NULL */
+    uint32_t        vertex_count;
+    uint32_t        triangle_count;
+    uint32_t        motion_segment_count;   /* 0 = static mesh */
+    uint32_t        reserved;
+} asgpu_mesh;
+
+typedef struct asgpu_object_instance {
+    double          local_to_parent[16];
+    double          parent_to_local[16];
+    uint32_t        mesh_index;
+    uint32_t        vis_flags;
+} asgpu_object_instance;
+
+typedef struct asgpu_assembly {
+    const asgpu_object_instance* object_instances;
+    uint32_t        object_instance_count;
+    uint32_t        max_leaf_size;                  /* acceleration_structure.max_leaf_size (default 2) */
+    float           interior_node_traversal_cost;   /* default 1 */
+    float           triangle_intersection_cost;     /* default 1 */
+    double          time;                           /* acceleration_structure.time (default 0.5) */
+} asgpu_assembly;
+
+typedef struct asgpu_assembly_instance {
+    double          local_to_parent[16];            /* cumulated: assembly space -> world */
+    double          parent_to_local[16];
+    uint32_t        assembly_index;
+    uint32_t        vis_flags;
+} asgpu_assembly_instance;
+
+typedef struct asgpu_scene_desc {
+    const asgpu_mesh*               meshes;
+    const asgpu_assembly*           assemblies;
+    const asgpu_assembly_instance*  assembly_instances;
+    uint32_t        mesh_count;
+    uint32_t        assembly_count;
+    uint32_t        assembly_instance_count;
+    uint32_t        reserved;
+} asgpu_scene_desc;
+
+/* ------------------------------------------------------------------------------------------
+ * Reference-format trees: exactly the arrays appleseed's own classes hold, so an in-tree
+ * integration passes pointers to its live data (INTEGRATION.md shows the friend accessors).
+ * ------------------------------------------------------------------------------------------ */
+
+typedef struct asgpu_triangle_tree_view {
+    const void*     nodes;              /* bvh::Node<AABB3d>[node_count], 128 B each, 64 B aligned */
+    const double*   node_bboxes;        /* Tree::m_node_bboxes: 6 doubles each, swizzled minx maxx miny maxy minz maxz */
+    const uint8_t*  leaf_data;          /* TriangleTree::m_leaf_data */
+    const void*     triangle_keys;      /* TriangleKey[triangle_key_count], 12 B each */
+    uint64_t        node_count;
+    uint64_t        node_bbox_count;
+    uint64_t        leaf_data_size;
+    uint64_t        triangle_key_count;
+    uint64_t        static_triangle_count;
+    uint64_t        moving_triangle_count;
+} asgpu_triangle_tree_view;
+
+/* One AssemblyTree::Item (assemblytree.h:103-122) with its TransformSequence already evaluated
+ * (single key: transformsequence.h:185-210). */
+typedef struct asgpu_assembly_item {
+    double          parent_to_local[16];    /* world -> assembly-instance space */
+    uint32_t        assembly_instance;      /* caller's id, reported back in asgpu_hit */
+    uint32_t        triangle_tree;          /* index into the triangle tree array, ASGPU_MISS = none */
+    uint32_t        vis_flags;              /* AssemblyInstance::get_vis_flags() */
+    uint32_t        reserved;
+} asgpu_assembly_item;
+
+typedef struct asgpu_assembly_tree_view {
+    const void*                 nodes;      /* bvh::Node<AABB3d>[node_count]; leaves address items by index/count */
+    const asgpu_assembly_item*  items;      /* tree order (AssemblyTree::m_items after reordering) */
+    uint64_t        node_count;
+    uint64_t        item_count;
+} asgpu_assembly_tree_view;
+
+/* ------------------------------------------------------------------------------------------
+ * Host builder: the CPU side that defines the data (sweep-SAH binary BVHs identical to the ones
+ * the reference builds).
+ * ------------------------------------------------------------------------------------------ */
+
+typedef struct asgpu_trees asgpu_trees;
+
+asgpu_trees*    asgpu_trees_build(const asgpu_scene_desc* desc, int threads);
+void            asgpu_trees_destroy(asgpu_trees* trees);
+int             asgpu_trees_triangle_tree_count(const asgpu_trees* trees);
+int             asgpu_trees_get_triangle_tree(const asgpu_trees* trees, int index, asgpu_triangle_tree_view* out);
+int             asgpu_trees_get_assembly_tree(const asgpu_trees* trees, asgpu_assembly_tree_view* out);
+double          asgpu_trees_build_seconds(const asgpu_trees* trees);
+
+/* ------------------------------------------------------------------------------------------
+ * GPU scene.
+ * ------------------------------------------------------------------------------------------ */
+
+typedef struct asgpu_scene asgpu_scene;
+
+/* Scene creation flags. */
+#define ASGPU_SCENE_EXACT   (1u << 0)   /* keep the 1:1 binary fp64 layout (bit-exact arbiter kernels) */
+#define ASGPU_SCENE_WIDE    (1u << 1)   /* build the wide quantised-box layout (throughput kernels) */
+#define ASGPU_SCENE_DEFAULT (ASGPU_SCENE_EXACT | ASGPU_SCENE_WIDE)
+
+/* Flatten reference-format trees into the GPU layouts and upload them to `device`. */
+asgpu_scene*    asgpu_scene_create(
+                    const asgpu_triangle_tree_view* triangle_trees,
+                    uint32_t                        triangle_tree_count,
+                    const asgpu_assembly_tree_view* assembly_tree,
+                    uint32_t                        flags,
+                    int                             device);
+
+/* Convenience: asgpu_trees_build + asgpu_scene_create. */
+asgpu_scene*    asgpu_scene_create_from_desc(const asgpu_scene_desc* desc, uint32_t flags, int device, int threads);
+
+void            asgpu_scene_destroy(asgpu_scene* scene);
+
+/* The whole flattened scene is one contiguous device allocation ("blob") addressed by offsets,
+ * so replication to other GPUs is one broadcast of blob_size bytes followed by import_blob on
+ * the receiving side (which adopts `blob`, a device pointer on `device`, without copying when
+ * `adopt` is non-zero; the caller then keeps the memory alive until asgpu_scene_destroy). */
+size_t          asgpu_scene_blob_size(const asgpu_scene* scene);
+const void*     asgpu_scene_blob_device_ptr(const asgpu_scene* scene);
+asgpu_scene*    asgpu_scene_import_blob(const void* device_blob, size_t size, int device, int adopt);
+
+typedef struct asgpu_scene_info {
+    uint64_t        blob_bytes;
+    uint64_t        triangle_tree_count;
+    uint64_t        instance_count;
+    uint64_t        triangle_count;             /* leaf slots over all trees */
+    uint64_t        moving_triangle_count;
+    uint64_t        binary_node_count;          /* exact layout */
+    uint64_t        wide_node_count;            /* wide layout */
+    uint64_t        binary_node_bytes;
+    uint64_t        wide_node_bytes;
+    uint64_t        triangle_bytes;             /* per-slot records + pose data */
+    uint32_t        flags;
+    uint32_t        reserved;
+} asgpu_scene_info;
+
+int             asgpu_scene_get_info(const asgpu_scene* scene, asgpu_scene_info* out);
+
+/* ------------------------------------------------------------------------------------------
+ * Rays and hit records.
+ * ------------------------------------------------------------------------------------------ */
+
+/* One array per ShadingRay field the path consumes.  NULL optional arrays mean: time 0,
+ * flags = all rays. */
+typedef struct asgpu_rays {
+    const double*   org;                /* n * 3  (Ray3d::m_org) */
+    const double*   dir;                /* n * 3  (Ray3d::m_dir, not necessarily unit length) */
+    const double*   tmin;               /* n      (inclusive) */
+    const double*   tmax;               /* n      (exclusive) */
+    const float*    time_absolute;      /* n or NULL (ShadingRay::Time::m_absolute) */
+    const float*    time_normalized;    /* n or NULL (ShadingRay::Time::m_normalized, in [0, 1)) */
+    const uint32_t* flags;              /* n or NULL (ShadingRay::m_flags) */
+} asgpu_rays;
+
+typedef struct asgpu_hit {              /* 40 bytes */
+    double          t;                      /* m_ray.m_tmax after the trace (unchanged on a miss) */
+    float           u, v;                   /* m_bary */
+    uint32_t        assembly_instance;      /* asgpu_assembly_item::assembly_instance, ASGPU_MISS on a miss */
+    uint32_t        object_instance_index;  /* m_object_instance_index */
+    uint32_t        primitive_index;        /* m_primitive_index: triangle index in its mesh */
+    uint32_t        tri_slot;               /* leaf-order slot in the triangle tree -> TriangleKey, support plane */
+    uint32_t        motion_segment;         /* pose interval used for a moving triangle, else 0 */
+    uint32_t        prim_type;              /* ShadingPoint::PrimitiveType: 0 none, 2 triangle */
+} asgpu_hit;
+
+/* Trace flags. */
+#define ASGPU_TRACE_EXACT       (1u << 0)   /* run the 1:1 binary fp64 kernels (reference visit order) */
+#define ASGPU_TRACE_COUNTERS    (1u << 1)   /* accumulate traversal counters (slower) */
+#define ASGPU_TRACE_SORT        (1u << 2)   /* reorder rays by origin/direction Morton key first */
+
+/* Closest hit for n rays.  All pointers are DEVICE pointers on the scene's device. */
+int             asgpu_trace(asgpu_scene* scene, const asgpu_rays* rays, size_t n, asgpu_hit* hits,
+                            uint32_t flags, void* stream);
+
+/* Any hit in [tmin, tmax) for n rays: occluded[i] = 1 or 0.  DEVICE pointers. */
+int             asgpu_trace_probe(asgpu_scene* scene, const asgpu_rays* rays, size_t n, uint8_t* occluded,
+                                  uint32_t flags, void* stream);
+
+/* Same with HOST buffers: rays are staged through pinned memory in chunks and the copies overlap
+ * the kernels; returns when the results are in `hits` / `occluded`. */
+int             asgpu_trace_host(asgpu_scene* scene, const asgpu_rays* rays, size_t n, asgpu_hit* hits, uint32_t flags);
+int             asgpu_trace_probe_host(asgpu_scene* scene, const asgpu_rays* rays, size_t n, uint8_t* occluded, uint32_t flags);
+
+typedef struct asgpu_counters {
+    uint64_t        rays;
+    uint64_t        assembly_nodes_visited;
+    uint64_t        instances_visited;
+    uint64_t        triangle_nodes_visited;
+    uint64_t        triangles_tested;
+    uint64_t        hits;
+    uint64_t        kernel_launches;        /* launches of this library's kernels since the last reset */
+    uint64_t        reserved;
+} asgpu_counters;
+
+int             asgpu_get_counters(asgpu_scene* scene, asgpu_counters* out, int reset);
+
+const char*     asgpu_last_error(void);
+int             asgpu_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* ASGPU_H */

@@ -1,0 +1,128 @@
+//
+// hostsim.cpp -- TEST-ONLY host build of the engine's per-ray traversal code.
+//
+// Compiles appleseed_b200/csrc/traverse_core.h with g++ (directed-rounding intrinsics emulated
+// through <cfenv>) together with the real host builder and flattener, so that the CPU-only test
+// tier (-m "not gpu") can check the traversal LOGIC of both GPU layouts against the oracle.
+// This library is never loaded by the product (appleseed_b200/); the CUDA kernels remain the only
+// execution path of the engine.
+//
+#include "../../appleseed_b200/csrc/flatten.h"
+#include "../../appleseed_b200/csrc/traverse_core.h"
+#include "../../appleseed_b200/csrc/tree_builder.h"
+
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace asgpu;
+
+namespace
+{
+    struct SimScene
+    {
+        std::vector<uint8_t>    blob;
+        SceneView               view;
+    };
+
+    std::string g_error;
+
+    template <bool ANY, bool WIDE>
+    void run(const SimScene& s, const asgpu_rays& rays, size_t n, asgpu_hit* hits, uint8_t* occluded, uint64_t* counters)
+    {
+        std::vector<uint2> stack(WideStackSize);
+        Stats stats; std::memset(&stats, 0, sizeof(stats));
+        uint64_t found_count = 0;
+        for (size_t i = 0; i < n; ++i)
+        {
+            Ray ray; load_ray(rays, i, ray);
+            Hit hit; bool found;
+            if (WIDE) found = wide_trace<ANY, true>(s.view, ray, hit, stats, stack.data(), 1);
+            else found = exact_trace<ANY, true>(s.view, ray, hit, stats);
+            found_count += found ? 1 : 0;
+            if (ANY) { occluded[i] = found ? 1 : 0; continue; }
+            asgpu_hit& h = hits[i];
+            std::memset(&h, 0, sizeof(h));
+            h.t = ray.tmax;
+            h.assembly_instance = ASGPU_MISS;
+            if (found)
+            {
+                const ItemRecord* item = reinterpret_cast<const ItemRecord*>(s.blob.data() + s.view.items) + hit.item;
+                const TreeDesc* td = reinterpret_cast<const TreeDesc*>(s.blob.data() + s.view.trees) + item->tree;
+                const HitKey* key = reinterpret_cast<const HitKey*>(s.blob.data() + td->keys) + hit.slot;
+                h.u = hit.u; h.v = hit.v;
+                h.assembly_instance = item->assembly_instance;
+                h.object_instance_index = key->object_instance_index;
+                h.primitive_index = key->triangle_index;
+                h.tri_slot = hit.slot;
+                h.motion_segment = hit.segment;
+                h.prim_type = 2;
+            }
+        }
+        if (counters)
+        {
+            counters[0] = n; counters[1] = stats.top_nodes; counters[2] = stats.instances;
+            counters[3] = stats.nodes; counters[4] = stats.triangles; counters[5] = found_count;
+        }
+    }
+}
+
+extern "C" {
+
+const char* hostsim_last_error() { return g_error.c_str(); }
+
+void* hostsim_scene_create(const asgpu_scene_desc* desc, uint32_t flags, int threads)
+{
+    HostTrees trees;
+    if (!build_host_trees(*desc, threads, trees, g_error)) return nullptr;
+    std::vector<asgpu_triangle_tree_view> views(trees.triangle_trees.size());
+    for (size_t i = 0; i < views.size(); ++i)
+    {
+        const HostTriangleTree& t = *trees.triangle_trees[i];
+        asgpu_triangle_tree_view& v = views[i];
+        v.nodes = t.nodes.data();
+        v.node_bboxes = t.node_bboxes.empty() ? nullptr : t.node_bboxes.data();
+        v.leaf_data = t.leaf_data.empty() ? nullptr : t.leaf_data.data();
+        v.triangle_keys = t.keys.empty() ? nullptr : t.keys.data();
+        v.node_count = t.nodes.size();
+        v.node_bbox_count = t.node_bboxes.size() / 6;
+        v.leaf_data_size = t.leaf_data.size();
+        v.triangle_key_count = t.keys.size();
+        v.static_triangle_count = t.static_triangle_count;
+        v.moving_triangle_count = t.moving_triangle_count;
+    }
+    asgpu_assembly_tree_view top;
+    top.nodes = trees.assembly_tree.nodes.data();
+    top.items = trees.assembly_tree.items.empty() ? nullptr : trees.assembly_tree.items.data();
+    top.node_count = trees.assembly_tree.nodes.size();
+    top.item_count = trees.assembly_tree.items.size();
+
+    SimScene* s = new SimScene();
+    const int rc = flatten_scene(views.empty() ? nullptr : views.data(), static_cast<uint32_t>(views.size()), top, flags, s->blob, g_error);
+    if (rc != ASGPU_OK) { delete s; return nullptr; }
+    BlobHeader h; std::memcpy(&h, s->blob.data(), sizeof(h));
+    s->view.blob = s->blob.data();
+    s->view.trees = h.trees; s->view.items = h.items; s->view.top_nodes = h.top_nodes;
+    s->view.top_wnodes = h.top_wnodes; s->view.top_witems = h.top_witems;
+    s->view.tree_count = h.tree_count; s->view.item_count = h.item_count;
+    s->view.top_node_count = h.top_node_count; s->view.top_wnode_count = h.top_wnode_count;
+    return s;
+}
+
+void hostsim_scene_destroy(void* scene) { delete static_cast<SimScene*>(scene); }
+
+size_t hostsim_blob_size(void* scene) { return static_cast<SimScene*>(scene)->blob.size(); }
+
+void hostsim_trace(void* scene, const asgpu_rays* rays, size_t n, asgpu_hit* hits, int wide, uint64_t* counters)
+{
+    if (wide) run<false, true>(*static_cast<SimScene*>(scene), *rays, n, hits, nullptr, counters);
+    else run<false, false>(*static_cast<SimScene*>(scene), *rays, n, hits, nullptr, counters);
+}
+
+void hostsim_trace_probe(void* scene, const asgpu_rays* rays, size_t n, uint8_t* occluded, int wide, uint64_t* counters)
+{
+    if (wide) run<true, true>(*static_cast<SimScene*>(scene), *rays, n, nullptr, occluded, counters);
+    else run<true, false>(*static_cast<SimScene*>(scene), *rays, n, nullptr, occluded, counters);
+}
+
+}   // extern "C"

@@ -1,0 +1,53 @@
+"""ctypes loader for the TEST-ONLY host build of the traversal core (tests/hostsim/hostsim.cpp)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from appleseed_b200.scene import HIT_DTYPE, CRays, CSceneDesc, RayBatch, SceneDesc
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SCENE_EXACT, SCENE_WIDE = 1, 2
+
+
+def load():
+    subprocess.run(["make", "-s", "-C", _HERE], check=True)
+    lib = C.CDLL(os.path.join(_HERE, "libhostsim.so"))
+    lib.hostsim_scene_create.restype = C.c_void_p
+    lib.hostsim_scene_create.argtypes = [C.POINTER(CSceneDesc), C.c_uint32, C.c_int]
+    lib.hostsim_scene_destroy.argtypes = [C.c_void_p]
+    lib.hostsim_last_error.restype = C.c_char_p
+    lib.hostsim_blob_size.restype = C.c_size_t
+    lib.hostsim_blob_size.argtypes = [C.c_void_p]
+    lib.hostsim_trace.argtypes = [C.c_void_p, C.POINTER(CRays), C.c_size_t, C.c_void_p, C.c_int, C.c_void_p]
+    lib.hostsim_trace_probe.argtypes = [C.c_void_p, C.POINTER(CRays), C.c_size_t, C.c_void_p, C.c_int, C.c_void_p]
+    return lib
+
+
+class SimScene:
+    def __init__(self, lib, desc: SceneDesc, flags=SCENE_EXACT | SCENE_WIDE, threads=4):
+        self.lib = lib
+        self._cdesc, self._keep = desc.to_c()
+        self.handle = lib.hostsim_scene_create(C.byref(self._cdesc), flags, threads)
+        if not self.handle:
+            raise RuntimeError(lib.hostsim_last_error().decode())
+
+    def __del__(self):
+        if getattr(self, "handle", None):
+            self.lib.hostsim_scene_destroy(self.handle)
+            self.handle = None
+
+    def trace(self, rays: RayBatch, wide: bool):
+        out = np.zeros(len(rays), dtype=HIT_DTYPE)
+        cnt = np.zeros(6, dtype=np.uint64)
+        cr = rays.to_c()
+        self.lib.hostsim_trace(self.handle, C.byref(cr), len(rays), out.ctypes.data, int(wide), cnt.ctypes.data)
+        return out, cnt
+
+    def trace_probe(self, rays: RayBatch, wide: bool):
+        out = np.zeros(len(rays), dtype=np.uint8)
+        cnt = np.zeros(6, dtype=np.uint64)
+        cr = rays.to_c()
+        self.lib.hostsim_trace_probe(self.handle, C.byref(cr), len(rays), out.ctypes.data, int(wide), cnt.ctypes.data)
+        return out, cnt

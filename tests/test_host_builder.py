@@ -1,0 +1,55 @@
+"""The product's host builder (asgpu_trees_build, through the C ABI) must produce the same
+reference-format trees as the oracle restatement and, where available, as the reference's own
+headers (oracle/_ref).  CPU only."""
+import numpy as np
+import pytest
+
+import cases
+from appleseed_b200 import scenes
+from appleseed_b200.intersector import AsgpuError, HostTrees
+from test_oracle_vs_ref import compare_tree
+
+
+def check_against(oracle, desc, threads):
+    a = oracle.scene(desc)
+    b = HostTrees(desc, threads=threads)
+    assert a.tree_count == b.triangle_tree_count
+    for i in range(a.tree_count):
+        compare_tree(a.triangle_tree(i), b.triangle_tree(i), True)
+    ta, tb = a.assembly_tree(), b.assembly_tree()
+    compare_tree(ta, tb, False)
+    assert np.array_equal(ta["item_assembly_instance"], tb["item_assembly_instance"])
+    assert np.array_equal(ta["item_tree"], tb["item_tree"])
+
+
+@pytest.mark.parametrize("name", list(cases.CASES))
+@pytest.mark.parametrize("threads", [1, 4])
+def test_trees_match_oracle(orc, name, threads):
+    check_against(orc, cases.CASES[name]()[0], threads)
+
+
+@pytest.mark.parametrize("name", ["cornell", "c3", "c4_msc3", "mixed"])
+def test_trees_match_reference_headers(asref, name):
+    check_against(asref, cases.CASES[name]()[0], 3)
+
+
+def test_parallel_subtree_stitching_matches_serial_order(orc):
+    # Large enough that the builder defers many subtrees to worker threads and stitches them back
+    # into the reference's depth-first node order.
+    desc = scenes.scene_c2(260)
+    check_against(orc, desc, 8)
+    check_against(orc, desc, 1)
+
+
+def test_many_instances_top_level_tree(orc):
+    check_against(orc, scenes.scene_c3(8, 12), 2)
+
+
+def test_rejects_malformed_input():
+    from appleseed_b200.scene import Assembly, AssemblyInstance, Mesh, ObjectInstance, SceneDesc
+    mesh = Mesh(np.zeros((3, 3), dtype=np.float32), np.array([[0, 1, 7]], dtype=np.uint32))
+    with pytest.raises(AsgpuError, match="out of range"):
+        HostTrees(SceneDesc([mesh], [Assembly([ObjectInstance(0)])], [AssemblyInstance(0)]))
+    ok = Mesh(np.eye(3, dtype=np.float32), np.array([[0, 1, 2]], dtype=np.uint32))
+    with pytest.raises(AsgpuError, match="assembly instance"):
+        HostTrees(SceneDesc([ok], [Assembly([ObjectInstance(0)])], [AssemblyInstance(3)]))
