@@ -1,0 +1,505 @@
+#!/usr/bin/env python
+"""Headline benchmark: Mrays/s of the Intersector::trace() / trace_probe() hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c4] [--impl reference]
+
+A "step" is one pass of the hot path over one batch of synthetic rays of the named workload
+(BASELINE.json configs):
+
+  c2 (default, the 1-GPU configuration):  999 698-triangle displaced grid, 16 Mi coherent pinhole
+      primaries + 16 Mi incoherent cosine-weighted bounce rays, closest hit
+  c3: 9 999 392-triangle fBm terrain x 64 assembly instances, 32 Mi incoherent closest-hit rays
+      (+ shadow probes reported as an extra figure)
+  c4: 2 000 000 moving triangles (msc = 1), 16 Mi incoherent closest-hit rays with random times
+
+`value`  = rays / device time with rays already resident in HBM (CUDA events on the launch stream).
+`e2e`    = the same step through the host-buffer C ABI call (asgpu_trace_host) with pinned host
+           buffers: H2D of the rays and D2H of the hit records inside the timed region.
+`roofline` = algorithmic bytes (measured node / triangle / instance visits per ray x record sizes
+           + ray in + hit out) / kernel time, against the measured HBM copy bandwidth.
+`cpu_baseline` = the reference's CPU path (oracle/_ref when present, else the oracle port) on all
+           host cores over a bounded sample of the same rays.
+
+With --gpus N > 1 (launched by torchrun, one rank per GPU) rank 0 builds and flattens the scene,
+broadcasts the blob once over NCCL, and every rank traces its own shard of rays (weak scaling, no
+data-path collective); time = max over ranks.
+
+--impl reference times the CPU reference path alone (rank 0 only) and prints the same line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from appleseed_b200 import scenes  # noqa: E402
+from appleseed_b200.scene import HIT_DTYPE, VIS_DIFFUSE, VIS_SHADOW, RayBatch  # noqa: E402
+
+METRIC = "Mrays/s closest-hit (wavefront batches, rays resident in HBM)"
+UNIT = "Mrays/s"
+MI = 1 << 20
+
+
+# ---------------------------------------------------------------------------------------------
+# Workloads
+# ---------------------------------------------------------------------------------------------
+
+def workload_name(args) -> str:
+    return {
+        "c2": "C2: 999698-triangle displaced grid, %d coherent primary + %d incoherent cosine bounce rays, closest hit",
+        "c3": "C3: 9999392-triangle fBm terrain x 64 assembly instances, %d incoherent closest-hit rays (+ %d shadow probes, extra)",
+        "c4": "C4: 2000000 moving triangles (msc=1), %d incoherent closest-hit rays with random time (+ %d probes, extra)",
+    }[args.workload] % (args.rays, args.rays)
+
+
+def make_scene(args):
+    if args.workload == "c2":
+        return scenes.scene_c2(args.res or 707)
+    if args.workload == "c3":
+        return scenes.scene_c3(args.res or 2236, 8)
+    if args.workload == "c4":
+        return scenes.scene_c4(args.res or 1000, 1)
+    raise ValueError(args.workload)
+
+
+def primary_rays_c2(n: int, rank: int) -> RayBatch:
+    side = int(round(math.sqrt(n)))
+    # Each rank looks at the terrain from its own camera position (its own image "tile").
+    ang = 0.37 * rank
+    eye = (0.35 * math.cos(ang), 3.0, 0.35 * math.sin(ang) + 0.001)
+    return scenes.pinhole_rays(side, side, eye, (0.0, 0.0, 0.0), up=(0, 0, 1), film=0.025, focal=0.05)
+
+
+def incoherent_rays(desc, n: int, seed: int, time: bool = False) -> RayBatch:
+    lo, hi = scenes.scene_bbox(desc)
+    ext = hi - lo
+    return scenes.uniform_sphere_rays(n, lo - 0.02 * ext, hi + np.array([0.02 * ext[0], 0.5 * max(ext[0], ext[2]) * 0.25, 0.02 * ext[2]]), seed, time=time)
+
+
+# ---------------------------------------------------------------------------------------------
+# Clocks sampling
+# ---------------------------------------------------------------------------------------------
+
+class ClockSampler:
+    QUERY = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            p = [x.strip() for x in line.split(",")]
+            if len(p) < 7:
+                continue
+            try:
+                sm.append(float(p[0])); mx.append(float(p[1]))
+            except ValueError:
+                continue
+            for k, name in enumerate(names):
+                if p[3 + k].lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU reference arm
+# ---------------------------------------------------------------------------------------------
+
+def cpu_oracle():
+    from oracle import oracle as orc
+    try:
+        orc.build("all")
+    except Exception:
+        pass
+    if orc.available("asref"):
+        return orc.Oracle("asref"), "reference"
+    return orc.Oracle("orc"), "port"
+
+
+def time_cpu(oscene, rays: RayBatch, probe: bool, threads: int, repeats: int = 1) -> float:
+    best = float("inf")
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        (oscene.trace_probe if probe else oscene.trace)(rays, threads=threads)
+        best = min(best, time.perf_counter() - t0)
+    return best
+
+
+def cpu_sample(args, desc, rank: int = 0):
+    """The bounded sample of the workload's rays the CPU arm is timed on."""
+    n = args.cpu_rays
+    if args.workload == "c2":
+        half = n // 2
+        prim = primary_rays_c2(args.rays // 2, rank)
+        stride = max(1, len(prim) // half)
+        coherent = prim.take(np.arange(0, len(prim), stride)[:half])
+        # Bounce rays need hit points: the CPU arm bounces from the sampled primaries it traces itself.
+        return coherent, half
+    return incoherent_rays(desc, n, 1000 + rank, time=(args.workload == "c4")), 0
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    desc = make_scene(args)
+    oracle, kind = cpu_oracle()
+    threads = os.cpu_count() or 1
+    t0 = time.perf_counter()
+    oscene = oracle.scene(desc)
+    build_s = time.perf_counter() - t0
+    sample, half = cpu_sample(args, desc)
+    if args.workload == "c2":
+        hits = oscene.trace(sample, threads=threads)
+        mask, pts, nrm = scenes.hit_points_and_normals(desc, sample, hits)
+        bounce = scenes.bounce_rays(pts, nrm, 1, flags=VIS_DIFFUSE)
+        batches = [sample, bounce]
+    else:
+        batches = [sample]
+    n_rays = sum(len(b) for b in batches)
+    for _ in range(max(1, min(args.warmup, 1))):
+        for b in batches:
+            oscene.trace(b, threads=threads)
+    times = []
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        for b in batches:
+            oscene.trace(b, threads=threads)
+        times.append(time.perf_counter() - t0)
+    ms = 1e3 * sum(times) / len(times)
+    value = n_rays / (ms * 1e-3) / 1e6
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args), "sample": "%d rays per step (bounded sample of the workload)" % n_rays,
+                   "scene_build_s": round(build_s, 2)},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind,
+                         "sample": "%d rays of the workload per step, %d threads" % (n_rays, threads)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+
+def pinned(a: np.ndarray):
+    import torch
+    t = torch.from_numpy(np.ascontiguousarray(a) if a.dtype != np.uint32 else np.ascontiguousarray(a).view(np.int32))
+    return t.pin_memory()
+
+
+class PinnedRays:
+    """Host ray batch in pinned memory + its device copy."""
+
+    def __init__(self, rays: RayBatch, device):
+        from appleseed_b200.intersector import DeviceRays
+        self.n = len(rays)
+        f = lambda a: None if a is None else pinned(a)
+        self.host_t = [f(rays.org), f(rays.dir), f(rays.tmin), f(rays.tmax), f(rays.time_absolute), f(rays.time_normalized), f(rays.flags)]
+        np_of = lambda t, dt: None if t is None else t.numpy().view(dt)
+        self.host = RayBatch(np_of(self.host_t[0], np.float64), np_of(self.host_t[1], np.float64), np_of(self.host_t[2], np.float64),
+                             np_of(self.host_t[3], np.float64), np_of(self.host_t[4], np.float32), np_of(self.host_t[5], np.float32),
+                             np_of(self.host_t[6], np.uint32))
+        dev = [None if t is None else t.to(device, non_blocking=True) for t in self.host_t]
+        self.dev = DeviceRays(*dev)
+        self.bytes_in = self.n * self.host.bytes_per_ray
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from appleseed_b200.intersector import HIT_BYTES, HostTrees, Intersector, TraceContext, hits_from_tensor
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- scene: built once on rank 0, replicated with ONE broadcast --------------------------
+    desc = make_scene(args)
+    t0 = time.perf_counter()
+    build_s = flatten_s = bcast_s = 0.0
+    if rank == 0:
+        trees = HostTrees(desc, threads=0)
+        build_s = trees.build_seconds
+        t1 = time.perf_counter()
+        ctx = TraceContext(device=local_rank, trees=trees)
+        trees.close()
+        flatten_s = time.perf_counter() - t1
+    if world > 1:
+        size = torch.tensor([ctx.blob_size if rank == 0 else 0], dtype=torch.int64, device=device)
+        dist.broadcast(size, 0)
+        blob = ctx.blob_tensor() if rank == 0 else torch.empty(int(size.item()), dtype=torch.uint8, device=device)
+        barrier()
+        t1 = time.perf_counter()
+        dist.broadcast(blob, 0)
+        torch.cuda.synchronize()
+        bcast_s = time.perf_counter() - t1
+        if rank != 0:
+            ctx = TraceContext.from_blob(blob, adopt=True)
+    isect = Intersector(ctx)
+    info = ctx.info()
+
+    # ---- rays (this rank's shard) ---------------------------------------------------------------
+    n = args.rays
+    batches = []          # (label, PinnedRays)
+    hits_dev = torch.empty(n * HIT_BYTES, dtype=torch.uint8, device=device)
+    if args.workload == "c2":
+        prim = primary_rays_c2(n, rank)
+        n = len(prim)
+        p = PinnedRays(prim, device)
+        isect.trace_device(p.dev, hits_dev)
+        torch.cuda.synchronize()
+        hits = hits_from_tensor(hits_dev, n)
+        mask, pts, nrm = scenes.hit_points_and_normals(desc, prim, hits)
+        if len(pts) < n:            # pad the bounce wavefront to n rays by wrapping around
+            idx = np.resize(np.arange(len(pts)), n)
+            pts, nrm = pts[idx], nrm[idx]
+        bounce = scenes.bounce_rays(pts, nrm, 1 + rank, flags=VIS_DIFFUSE)
+        batches = [("coherent_primary", p), ("incoherent_bounce", PinnedRays(bounce, device))]
+        probe_batch = None
+    else:
+        inc = incoherent_rays(desc, n, 2 + rank, time=(args.workload == "c4"))
+        p = PinnedRays(inc, device)
+        batches = [("incoherent", p)]
+        isect.trace_device(p.dev, hits_dev)
+        torch.cuda.synchronize()
+        hits = hits_from_tensor(hits_dev, n)
+        hit = hits["prim_type"] == 2
+        pts = inc.org + np.where(hit, hits["t"], 0.0)[:, None] * inc.dir
+        pts = pts - 1e-6 * inc.dir
+        lo, hi = scenes.scene_bbox(desc)
+        lights = np.array([[lo[0], hi[1] + 2.0, lo[2]], [hi[0], hi[1] + 2.0, lo[2]], [lo[0], hi[1] + 2.0, hi[2]], [hi[0], hi[1] + 2.0, hi[2]]])
+        sh = scenes.shadow_rays(pts, lights, 3 + rank, flags=VIS_SHADOW)
+        if args.workload == "c4":
+            sh.time_absolute, sh.time_normalized = inc.time_absolute, inc.time_normalized
+        probe_batch = PinnedRays(sh, device)
+    del hits
+    rays_per_step = sum(b.n for _, b in batches)
+    hit_bufs = [torch.empty(b.n * HIT_BYTES, dtype=torch.uint8, device=device) for _, b in batches]
+    torch.cuda.synchronize()
+
+    def step_device():
+        for (_, b), out in zip(batches, hit_bufs):
+            isect.trace_device(b.dev, out)
+
+    # ---- timed region: device-resident rays ----------------------------------------------------
+    for _ in range(max(3, args.warmup)):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    per_batch_ms = [0.0] * len(batches)
+    ev = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in batches] for _ in range(args.steps)]
+    barrier()
+    t_wall = time.perf_counter()
+    for s in range(args.steps):
+        for k, ((_, b), out) in enumerate(zip(batches, hit_bufs)):
+            ev[s][k][0].record()
+            isect.trace_device(b.dev, out)
+            ev[s][k][1].record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall
+    for s in range(args.steps):
+        for k in range(len(batches)):
+            per_batch_ms[k] += ev[s][k][0].elapsed_time(ev[s][k][1]) / args.steps
+    clocks = sampler.stop() if rank == 0 else None
+    ms_step = sum(per_batch_ms)
+    launches = args.steps * len(batches)
+
+    # ---- probes (extra figure) -------------------------------------------------------------------
+    probe_ms = None
+    if probe_batch is not None:
+        occ = torch.empty(probe_batch.n, dtype=torch.uint8, device=device)
+        for _ in range(3):
+            isect.trace_probe_device(probe_batch.dev, occ)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            isect.trace_probe_device(probe_batch.dev, occ)
+        e1.record()
+        torch.cuda.synchronize()
+        probe_ms = e0.elapsed_time(e1) / args.steps
+
+    # ---- end to end through the host-buffer ABI call (pinned host memory) ---------------------
+    host_hits = [torch.empty(b.n * HIT_BYTES, dtype=torch.uint8).pin_memory() for _, b in batches]
+    host_hits_np = [h.numpy().view(HIT_DTYPE) for h in host_hits]
+
+    def step_host():
+        for (_, b), out in zip(batches, host_hits_np):
+            isect.trace(b.host, out=out)
+
+    step_host()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(1, min(args.steps, 5))
+    for _ in range(e2e_steps):
+        step_host()
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    h2d = sum(b.bytes_in for _, b in batches)
+    d2h = sum(b.n * HIT_BYTES for _, b in batches)
+    # The e2e results must be the device results.
+    check = hits_from_tensor(hit_bufs[-1], batches[-1][1].n)
+    assert check.tobytes() == host_hits_np[-1].tobytes(), "host-path results differ from device-path results"
+
+    # ---- algorithmic bytes per ray (counters variant, untimed) ----------------------------------
+    ctx.counters(reset=True)
+    for (_, b), out in zip(batches, hit_bufs):
+        isect.trace_device(b.dev, out, counters=True)
+    c = ctx.counters(reset=True)
+    r = max(1, c["rays"])
+    per_ray = {
+        "top_nodes": c["assembly_nodes_visited"] / r, "instances": c["instances_visited"] / r,
+        "nodes": c["triangle_nodes_visited"] / r, "triangles": c["triangles_tested"] / r, "hit_rate": c["hits"] / r,
+    }
+    ray_in = h2d / rays_per_step
+    bytes_per_ray = (per_ray["top_nodes"] + per_ray["nodes"]) * 80 + per_ray["triangles"] * 48 + per_ray["instances"] * (128 + 88 + 4) \
+        + ray_in + HIT_BYTES
+    if args.workload == "c4":
+        bytes_per_ray += per_ray["triangles"] * 72       # two 36-byte poses per moving triangle
+
+    # ---- aggregate over ranks (max time) --------------------------------------------------------
+    t = torch.tensor([ms_step, e2e_ms, probe_ms or 0.0], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step, e2e_ms, probe_ms_max = (float(x) for x in t.cpu())
+    total_rays = rays_per_step * world
+    value = total_rays / (ms_step * 1e-3) / 1e6
+    e2e_value = total_rays / (e2e_ms * 1e-3) / 1e6
+
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        achieved = bytes_per_ray * rays_per_step / (ms_step * 1e-3) / 1e9      # per GPU
+        traffic = None
+        prof = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(prof):
+            try:
+                traffic = json.load(open(prof)).get(args.workload)
+            except Exception:
+                traffic = None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {
+                "workload": workload_name(args), "rays_per_step_per_gpu": rays_per_step,
+                "batches": {label: {"rays": b.n, "ms": round(ms, 4), "mrays_s": round(b.n / ms / 1e3, 1)}
+                            for (label, b), ms in zip(batches, per_batch_ms)},
+                "kernel": "wide (8-wide quantised BVH, fp32 interval box tests, exact fp64 triangle tests)",
+                "l2": "inputs larger than L2 (%.0f MB of rays + %.0f MB scene blob per step vs 126 MB L2)" % (h2d / 1e6, info["blob_bytes"] / 1e6),
+                "scene": {k: info[k] for k in ("triangle_count", "instance_count", "wide_node_count", "binary_node_count", "blob_bytes")},
+                "scene_build_s": round(build_s, 2), "flatten_upload_s": round(flatten_s, 2), "broadcast_s": round(bcast_s, 4),
+                "per_ray": {k: round(v, 3) for k, v in per_ray.items()},
+                "parallelism": "rays sharded by rank, scene replicated by one NCCL broadcast" if world > 1 else "1 GPU",
+            },
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "bytes_per_ray": round(bytes_per_ray, 1), "peak_source": peak_src,
+                         "kernel": "trace_kernel<closest, wide>"},
+            "clocks": clocks,
+        }
+        if probe_batch is not None:
+            line["config"]["shadow_probe"] = {"rays": probe_batch.n, "ms": round(probe_ms_max, 4),
+                                               "mrays_s": round(probe_batch.n * world / probe_ms_max / 1e3, 1)}
+        if world == 1 and not args.no_cpu:
+            oracle, kind = cpu_oracle()
+            threads = os.cpu_count() or 1
+            oscene = oracle.scene(desc)
+            cpu_n = min(args.cpu_rays, batches[-1][1].n)
+            sample = batches[-1][1].host.slice(0, cpu_n)
+            secs = time_cpu(oscene, sample, False, threads)
+            cpu_hits = oscene.trace(sample.slice(0, min(cpu_n, 200000)), threads=threads)
+            gpu_hits = host_hits_np[-1][: len(cpu_hits)]
+            agree = float((cpu_hits["tri_slot"] == gpu_hits["tri_slot"]).mean())
+            line["cpu_baseline"] = {"value": cpu_n / secs / 1e6, "unit": UNIT, "cores": threads, "kind": kind,
+                                    "sample": "first %d rays of the '%s' batch, %d threads, %.1f s" % (cpu_n, batches[-1][0], threads, secs),
+                                    "identity_agreement_with_gpu": agree}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4"])
+    ap.add_argument("--rays", type=int, default=0, help="rays per batch per GPU (default: the workload's)")
+    ap.add_argument("--res", type=int, default=0, help="override the grid resolution (smaller scene for quick runs)")
+    ap.add_argument("--cpu-rays", type=int, default=4 * MI, help="size of the CPU baseline sample")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.rays == 0:
+        args.rays = {"c2": 16 * MI, "c3": 32 * MI, "c4": 16 * MI}[args.workload]
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()
