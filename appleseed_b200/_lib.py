@@ -19,7 +19,8 @@ EXPORTS = [
     "asgpu_trees_build", "asgpu_trees_destroy", "asgpu_trees_triangle_tree_count",
     "asgpu_trees_get_triangle_tree", "asgpu_trees_get_assembly_tree", "asgpu_trees_build_seconds",
     "asgpu_scene_create", "asgpu_scene_create_from_desc", "asgpu_scene_destroy",
-    "asgpu_scene_blob_size", "asgpu_scene_blob_device_ptr", "asgpu_scene_import_blob", "asgpu_scene_get_info",
+    "asgpu_scene_blob_size", "asgpu_scene_blob_device_ptr", "asgpu_scene_export_blob", "asgpu_scene_import_blob",
+    "asgpu_scene_get_info",
     "asgpu_trace", "asgpu_trace_probe", "asgpu_trace_host", "asgpu_trace_probe_host",
     "asgpu_get_counters", "asgpu_last_error", "asgpu_version",
 ]
@@ -107,6 +108,7 @@ def load() -> C.CDLL:
     lib.asgpu_scene_blob_size.argtypes = [C.c_void_p]
     lib.asgpu_scene_blob_device_ptr.restype = C.c_void_p
     lib.asgpu_scene_blob_device_ptr.argtypes = [C.c_void_p]
+    lib.asgpu_scene_export_blob.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     lib.asgpu_scene_import_blob.restype = C.c_void_p
     lib.asgpu_scene_import_blob.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int]
     lib.asgpu_scene_get_info.argtypes = [C.c_void_p, P(SceneInfo)]

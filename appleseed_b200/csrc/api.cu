@@ -353,6 +353,15 @@ size_t asgpu_scene_blob_size(const asgpu_scene* scene) { return scene ? scene->b
 
 const void* asgpu_scene_blob_device_ptr(const asgpu_scene* scene) { return scene ? scene->blob : nullptr; }
 
+int asgpu_scene_export_blob(const asgpu_scene* scene, void* device_dst, size_t capacity, void* stream)
+{
+    if (!scene || !device_dst) return fail(ASGPU_E_INVALID, "null argument");
+    if (capacity < scene->blob_bytes) return fail(ASGPU_E_INVALID, "destination too small for the scene blob");
+    ASGPU_CUDA(cudaSetDevice(scene->device), "cudaSetDevice");
+    ASGPU_CUDA(cudaMemcpyAsync(device_dst, scene->blob, scene->blob_bytes, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)), "cudaMemcpyAsync(blob)");
+    return ASGPU_OK;
+}
+
 asgpu_scene* asgpu_scene_import_blob(const void* device_blob, size_t size, int device, int adopt)
 {
     if (!device_blob || size < sizeof(BlobHeader)) { fail(ASGPU_E_INVALID, "blob too small"); return nullptr; }

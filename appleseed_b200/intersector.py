@@ -216,11 +216,8 @@ class TraceContext:
         import torch
         n = self.blob_size
         out = torch.empty(n, dtype=torch.uint8, device="cuda:%d" % self.device)
-        src = self.lib.asgpu_scene_blob_device_ptr(self.handle)
-        cudart = torch.cuda.cudart()
-        rc = cudart.cudaMemcpy(out.data_ptr(), src, n, 3)   # cudaMemcpyDeviceToDevice
-        if int(rc) != 0:
-            raise AsgpuError("cudaMemcpy(blob) failed: %s" % rc)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _check(self.lib.asgpu_scene_export_blob(self.handle, out.data_ptr(), n, C.c_void_p(stream)), "asgpu_scene_export_blob")
         return out
 
     def info(self) -> dict:

@@ -190,6 +190,7 @@ void            asgpu_scene_destroy(asgpu_scene* scene);
  * `adopt` is non-zero; the caller then keeps the memory alive until asgpu_scene_destroy). */
 size_t          asgpu_scene_blob_size(const asgpu_scene* scene);
 const void*     asgpu_scene_blob_device_ptr(const asgpu_scene* scene);
+int             asgpu_scene_export_blob(const asgpu_scene* scene, void* device_dst, size_t capacity, void* stream);
 asgpu_scene*    asgpu_scene_import_blob(const void* device_blob, size_t size, int device, int adopt);
 
 typedef struct asgpu_scene_info {
