@@ -68,6 +68,17 @@ __device__ __forceinline__ void store_hit(asgpu_hit* out, const SceneView& s, co
     dst[4] = static_cast<unsigned long long>(segment) | (static_cast<unsigned long long>(prim_type) << 32);
 }
 
+// Lanes of a warp whose ray has finished are refilled from the queue as soon as at least
+// RefillThreshold of them are idle (or all are), so one long ray does not hold 31 lanes hostage.
+const int RefillThreshold = 8;
+
+template <bool ANY, bool COUNT>
+__device__ __forceinline__ void finish_ray(const KernelArgs& args, const unsigned long long i, const WideTraversal<ANY, COUNT>& tr)
+{
+    if (ANY) args.occluded[i] = tr.found() ? 1 : 0;
+    else store_hit(args.hits + i, args.scene, tr.ray, tr.hit, tr.found());
+}
+
 template <bool ANY, bool WIDE, bool COUNT>
 __global__ void __launch_bounds__(BlockThreads)
 trace_kernel(const KernelArgs args)
@@ -78,26 +89,71 @@ trace_kernel(const KernelArgs args)
     Stats stats; stats.top_nodes = stats.instances = stats.nodes = stats.triangles = 0;
     unsigned rays_done = 0, hits_found = 0;
 
-    for (;;)
+    if (WIDE)
     {
-        // Warp-level pull from the ray queue.
-        unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(args.queue, 32ull);
-        base = __shfl_sync(0xFFFFFFFFu, base, 0);
-        if (base >= args.n) break;
-        const unsigned long long pos = base + lane;
-        if (pos < args.n)
+        WideTraversal<ANY, COUNT> tr;
+        unsigned long long index = 0;
+        bool active = false;
+        bool exhausted = false;         // warp-uniform: the queue has no more rays
+        uint2* stack = wide_stack + threadIdx.x;
+
+        for (;;)
         {
-            const unsigned long long i = args.order ? args.order[pos] : pos;
-            Ray ray;
-            load_ray(args.rays, i, ray);
-            Hit hit;
-            bool found;
-            if (WIDE) found = wide_trace<ANY, COUNT>(args.scene, ray, hit, stats, wide_stack + threadIdx.x, BlockThreads);
-            else found = exact_trace<ANY, COUNT>(args.scene, ray, hit, stats);
-            if (ANY) args.occluded[i] = found ? 1 : 0;
-            else store_hit(args.hits + i, args.scene, ray, hit, found);
-            if (COUNT) { ++rays_done; hits_found += found ? 1 : 0; }
+            const unsigned idle = __ballot_sync(0xFFFFFFFFu, !active);
+            if (idle != 0 && !exhausted && (__popc(idle) >= RefillThreshold || idle == 0xFFFFFFFFu))
+            {
+                // Warp-aggregated pull: one atomic for all idle lanes.
+                const int leader = __ffs(idle) - 1;
+                unsigned long long base = 0;
+                if (lane == leader) base = atomicAdd(args.queue, static_cast<unsigned long long>(__popc(idle)));
+                base = __shfl_sync(0xFFFFFFFFu, base, leader);
+                if (!active)
+                {
+                    const unsigned long long pos = base + __popc(idle & ((1u << lane) - 1u));
+                    if (pos < args.n)
+                    {
+                        index = args.order ? args.order[pos] : pos;
+                        tr.begin(args.scene, args.rays, index);
+                        active = true;
+                    }
+                }
+                if (base + __popc(idle) >= args.n) exhausted = true;
+            }
+            else if (idle == 0xFFFFFFFFu) break;        // nothing active and nothing left to fetch
+            if (exhausted && __ballot_sync(0xFFFFFFFFu, active) == 0) break;
+
+            if (active)
+            {
+                if (tr.step(args.scene, args.rays, index, stats, stack, BlockThreads))
+                {
+                    finish_ray<ANY, COUNT>(args, index, tr);
+                    active = false;
+                    if (COUNT) { ++rays_done; hits_found += tr.found() ? 1 : 0; }
+                }
+            }
+        }
+    }
+    else
+    {
+        for (;;)
+        {
+            // Warp-level pull from the ray queue.
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(args.queue, 32ull);
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            if (base >= args.n) break;
+            const unsigned long long pos = base + lane;
+            if (pos < args.n)
+            {
+                const unsigned long long i = args.order ? args.order[pos] : pos;
+                Ray ray;
+                load_ray(args.rays, i, ray);
+                Hit hit;
+                const bool found = exact_trace<ANY, COUNT>(args.scene, ray, hit, stats);
+                if (ANY) args.occluded[i] = found ? 1 : 0;
+                else store_hit(args.hits + i, args.scene, ray, hit, found);
+                if (COUNT) { ++rays_done; hits_found += found ? 1 : 0; }
+            }
         }
     }
 

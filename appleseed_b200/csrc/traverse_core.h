@@ -684,29 +684,64 @@ ASGPU_HD void wide_node_test(const uint8_t* np, const WideRay& w, uint32_t& chil
 
 const uint32_t WideStackSize = 32;
 
-// `stack` must hold WideStackSize entries per thread, element i of this thread at stack[i * stride].
-template <bool ANY, bool COUNT>
-ASGPU_HD bool wide_trace(const SceneView& s, Ray& world, Hit& hit, Stats& stats, uint2* stack, const uint32_t stride)
+ASGPU_HD void load_ray_org_dir(const asgpu_rays& rays, const size_t i, Ray& r)
 {
-    hit.item = 0xFFFFFFFFu; hit.slot = 0; hit.segment = 0; hit.u = hit.v = 0.0f;
+#if ASGPU_DEVICE_CODE
+    r.org[0] = __ldg(rays.org + i * 3); r.org[1] = __ldg(rays.org + i * 3 + 1); r.org[2] = __ldg(rays.org + i * 3 + 2);
+    r.dir[0] = __ldg(rays.dir + i * 3); r.dir[1] = __ldg(rays.dir + i * 3 + 1); r.dir[2] = __ldg(rays.dir + i * 3 + 2);
+#else
+    for (int a = 0; a < 3; ++a) { r.org[a] = rays.org[i * 3 + a]; r.dir[a] = rays.dir[i * 3 + a]; }
+#endif
+}
 
-    Ray ray = world;                // current-space ray (world space first)
-    WideRay wr; make_wide_ray(ray, wr);
+// The wide traversal as an explicit per-ray state machine: begin() loads a ray, step() performs one
+// iteration (fetch + test one wide node, intersect its pending leaf items, choose what comes next)
+// and returns true when the ray is finished.  The kernel interleaves step() with a warp-level
+// refill of finished lanes from the ray queue, so a warp keeps most of its lanes busy even when
+// ray lengths differ wildly.
+//
+// Only the CURRENT-space origin and direction are kept in registers: in world space they are the
+// ray's own, inside an instance they are the transformed ones, and the world ones are re-read from
+// the ray arrays when the traversal returns to world space.  tmin / tmax / time / flags are shared
+// between spaces because the instance direction is not renormalised (assemblytree.cpp:556-596).
+//
+// `stack` holds WideStackSize entries per thread, element i of this thread at stack[i * stride].
+template <bool ANY, bool COUNT>
+struct WideTraversal
+{
+    Ray             ray;
+    WideRay         wr;
+    const uint8_t*  wnodes;
+    const uint8_t*  wtris;
+    const uint8_t*  poses;
+    uint2           ngroup, tgroup;
+    uint32_t        fetch;              // wide node to fetch next, 0xFFFFFFFF = none
+    uint32_t        sp;
+    uint32_t        cur_item;           // 0xFFFFFFFF while in world space
+    Hit             hit;
 
-    const uint8_t* wnodes = s.blob + s.top_wnodes;
-    const uint8_t* wtris = nullptr;
-    const uint8_t* poses = nullptr;
-    bool in_instance = false;
-    uint32_t cur_item = 0xFFFFFFFFu;
-
-    uint32_t sp = 0;
-    uint2 ngroup; ngroup.x = 0; ngroup.y = 0;
-    uint2 tgroup; tgroup.x = 0; tgroup.y = 0;
-    uint32_t fetch = 0;                             // node to fetch next, 0xFFFFFFFF = none
-    if (s.top_wnode_count == 0) return false;
-
-    while (true)
+    ASGPU_HD void begin(const SceneView& s, const asgpu_rays& rays, const size_t index)
     {
+        load_ray(rays, index, ray);
+        make_wide_ray(ray, wr);
+        wnodes = s.blob + s.top_wnodes;
+        wtris = nullptr;
+        poses = nullptr;
+        ngroup.x = 0; ngroup.y = 0;
+        tgroup.x = 0; tgroup.y = 0;
+        fetch = s.top_wnode_count != 0 ? 0u : 0xFFFFFFFFu;
+        sp = 0;
+        cur_item = 0xFFFFFFFFu;
+        hit.item = 0xFFFFFFFFu; hit.slot = 0; hit.segment = 0; hit.u = hit.v = 0.0f;
+    }
+
+    ASGPU_HD bool found() const { return hit.item != 0xFFFFFFFFu; }
+
+    // Returns true when the traversal of this ray is complete.
+    ASGPU_HD bool step(const SceneView& s, const asgpu_rays& rays, const size_t index, Stats& stats, uint2* stack, const uint32_t stride)
+    {
+        const bool in_instance = cur_item != 0xFFFFFFFFu;
+
         if (fetch != 0xFFFFFFFFu)
         {
             if (COUNT) { if (in_instance) ++stats.nodes; else ++stats.top_nodes; }
@@ -732,13 +767,12 @@ ASGPU_HD bool wide_trace(const SceneView& s, Ray& world, Hit& hit, Stats& stats,
                 double t, u, v;
                 if (mt_test<!ANY>(tri, ray, t, u, v))
                 {
+                    hit.item = cur_item;
                     if (ANY) return true;
                     ray.tmax = t;
-                    world.tmax = t;
                     shrink_wide_ray(ray, wr);
                     hit.u = static_cast<float>(u);
                     hit.v = static_cast<float>(v);
-                    hit.item = cur_item;
                     hit.slot = slot;
                     hit.segment = segment;
                 }
@@ -749,27 +783,27 @@ ASGPU_HD bool wide_trace(const SceneView& s, Ray& world, Hit& hit, Stats& stats,
                 const uint32_t item = load4(s.blob + s.top_witems + static_cast<uint64_t>(tgroup.x + bit) * 4);
                 const uint8_t* ip = s.blob + s.items + static_cast<uint64_t>(item) * sizeof(ItemRecord);
                 const uint4 meta = load16(ip + 96);
-                if (!(meta.y & world.flags) || meta.x == 0xFFFFFFFFu) continue;
+                if (!(meta.y & ray.flags) || meta.x == 0xFFFFFFFFu) continue;
                 if (COUNT) ++stats.instances;
                 // Save the world-space traversal state, then descend.
                 if (ngroup.y & 0xFF000000u) { stack[sp * stride] = ngroup; ++sp; }
                 if (tgroup.y) { stack[sp * stride] = tgroup; ++sp; }
                 uint2 sentinel; sentinel.x = 0xFFFFFFFFu; sentinel.y = 0;
                 stack[sp * stride] = sentinel; ++sp;
-                to_instance_space(ip, world, ray);
+                Ray local;
+                to_instance_space(ip, ray, local);
+                ray = local;
                 make_wide_ray(ray, wr);
                 TreeDesc td; load_tree_desc(s, meta.x, td);
                 wnodes = s.blob + td.wnodes;
                 wtris = s.blob + td.wtris;
                 poses = s.blob + td.poses;
-                in_instance = true;
                 cur_item = item;
                 ngroup.y = 0; tgroup.y = 0;
                 if (td.wnode_count != 0) fetch = 0;
-                break;
+                return false;
             }
         }
-        if (fetch != 0xFFFFFFFFu) continue;
 
         // Next internal child of the current group, nearest octant slot first.
         if (ngroup.y & 0xFF000000u)
@@ -778,26 +812,38 @@ ASGPU_HD bool wide_trace(const SceneView& s, Ray& world, Hit& hit, Stats& stats,
             ngroup.y &= ~(1u << bit);
             const uint32_t k = static_cast<uint32_t>(bit - 24) ^ (7 - wr.oct);
             fetch = ngroup.x + popc(ngroup.y & 0xFFu & ((1u << k) - 1u));
-            continue;
+            return false;
         }
 
-        if (sp == 0) break;
+        if (sp == 0) return true;
         --sp;
         const uint2 top = stack[sp * stride];
         if (top.x == 0xFFFFFFFFu && top.y == 0)
         {
-            // Back to world space.
-            ray = world;
+            // Back to world space: the world origin and direction come from the ray arrays again.
+            load_ray_org_dir(rays, index, ray);
             make_wide_ray(ray, wr);
             wnodes = s.blob + s.top_wnodes;
-            in_instance = false;
+            cur_item = 0xFFFFFFFFu;
             ngroup.y = 0; tgroup.y = 0;
-            continue;
+            return false;
         }
         if (top.y & 0xFF000000u) { ngroup = top; tgroup.y = 0; }
         else { tgroup = top; ngroup.y = 0; }
+        return false;
     }
-    return !ANY && hit.item != 0xFFFFFFFFu;
+};
+
+// One ray start to finish (host simulation; the kernel drives WideTraversal itself).
+template <bool ANY, bool COUNT>
+ASGPU_HD bool wide_trace(const SceneView& s, const asgpu_rays& rays, const size_t index, Ray& out_ray, Hit& hit, Stats& stats, uint2* stack, const uint32_t stride)
+{
+    WideTraversal<ANY, COUNT> tr;
+    tr.begin(s, rays, index);
+    while (!tr.step(s, rays, index, stats, stack, stride)) {}
+    out_ray = tr.ray;
+    hit = tr.hit;
+    return tr.found();
 }
 
 }   // namespace asgpu

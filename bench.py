@@ -82,9 +82,11 @@ def primary_rays_c2(n: int, rank: int) -> RayBatch:
 
 
 def incoherent_rays(desc, n: int, seed: int, time: bool = False) -> RayBatch:
+    """Origins uniform in the scene's bounding box (2 % margin), directions uniform on the sphere
+    (SURVEY.md section 8(d), C3 / C4)."""
     lo, hi = scenes.scene_bbox(desc)
     ext = hi - lo
-    return scenes.uniform_sphere_rays(n, lo - 0.02 * ext, hi + np.array([0.02 * ext[0], 0.5 * max(ext[0], ext[2]) * 0.25, 0.02 * ext[2]]), seed, time=time)
+    return scenes.uniform_sphere_rays(n, lo - 0.02 * ext, hi + 0.02 * ext, seed, time=time)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -165,7 +167,7 @@ def time_cpu(oscene, rays: RayBatch, probe: bool, threads: int, repeats: int = 1
 
 def cpu_sample(args, desc, rank: int = 0):
     """The bounded sample of the workload's rays the CPU arm is timed on."""
-    n = args.cpu_rays
+    n = args.cpu_rays if args.cpu_rays > 0 else args.rays
     if args.workload == "c2":
         half = n // 2
         prim = primary_rays_c2(args.rays // 2, rank)
@@ -466,7 +468,7 @@ def run_gpu(args):
             oracle, kind = cpu_oracle()
             threads = os.cpu_count() or 1
             oscene = oracle.scene(desc)
-            cpu_n = min(args.cpu_rays, batches[-1][1].n)
+            cpu_n = min(args.cpu_rays if args.cpu_rays > 0 else batches[-1][1].n, batches[-1][1].n)
             sample = batches[-1][1].host.slice(0, cpu_n)
             secs = time_cpu(oscene, sample, False, threads)
             cpu_hits = oscene.trace(sample.slice(0, min(cpu_n, 200000)), threads=threads)
@@ -490,7 +492,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4"])
     ap.add_argument("--rays", type=int, default=0, help="rays per batch per GPU (default: the workload's)")
     ap.add_argument("--res", type=int, default=0, help="override the grid resolution (smaller scene for quick runs)")
-    ap.add_argument("--cpu-rays", type=int, default=4 * MI, help="size of the CPU baseline sample")
+    ap.add_argument("--cpu-rays", type=int, default=0, help="size of the CPU baseline sample (default: one whole batch)")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.rays == 0:

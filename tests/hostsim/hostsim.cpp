@@ -37,7 +37,7 @@ namespace
         {
             Ray ray; load_ray(rays, i, ray);
             Hit hit; bool found;
-            if (WIDE) found = wide_trace<ANY, true>(s.view, ray, hit, stats, stack.data(), 1);
+            if (WIDE) found = wide_trace<ANY, true>(s.view, rays, i, ray, hit, stats, stack.data(), 1);
             else found = exact_trace<ANY, true>(s.view, ray, hit, stats);
             found_count += found ? 1 : 0;
             if (ANY) { occluded[i] = found ? 1 : 0; continue; }
