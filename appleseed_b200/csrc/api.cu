@@ -102,6 +102,7 @@ void make_view(asgpu_scene* s)
     s->view.item_count = s->header.item_count;
     s->view.top_node_count = s->header.top_node_count;
     s->view.top_wnode_count = s->header.top_wnode_count;
+    s->view.wide_stack_need = s->header.wide_stack_need;
 }
 
 int init_device_side(asgpu_scene* s)

@@ -268,6 +268,7 @@ struct WideOut
 {
     std::vector<WNode>      nodes;
     std::vector<uint32_t>   leaf_order;     // wide item order -> original item (slot) index
+    uint32_t                depth = 0;      // number of node levels (root = 1)
 };
 
 struct Element
@@ -349,18 +350,19 @@ int collapse(const BinaryView& bv, const uint32_t leaf_cap, WideOut& out, std::s
     out.nodes.clear();
     out.leaf_order.clear();
 
-    struct Pending { uint32_t wide_index; Element root; };
+    struct Pending { uint32_t wide_index; uint32_t depth; Element root; };
     std::vector<Pending> queue;
     {
         WNode blank; std::memset(&blank, 0, sizeof(blank));
         out.nodes.push_back(blank);
-        Pending p; p.wide_index = 0; make_element(bv, 0, p.root);
+        Pending p; p.wide_index = 0; p.depth = 1; make_element(bv, 0, p.root);
         queue.push_back(p);
     }
 
     for (size_t qi = 0; qi < queue.size(); ++qi)
     {
         const Pending cur = queue[qi];
+        if (cur.depth > out.depth) out.depth = cur.depth;
         Element kids[8];
         int n = 0;
 
@@ -445,7 +447,7 @@ int collapse(const BinaryView& bv, const uint32_t leaf_cap, WideOut& out, std::s
                 w.imask |= uint8_t(1u << s);
                 w.meta[s] = uint8_t(0x20 | (24 + s));
                 WNode blank; std::memset(&blank, 0, sizeof(blank));
-                Pending p; p.wide_index = static_cast<uint32_t>(out.nodes.size()); p.root = kids[i];
+                Pending p; p.wide_index = static_cast<uint32_t>(out.nodes.size()); p.depth = cur.depth + 1; p.root = kids[i];
                 out.nodes.push_back(blank);
                 queue.push_back(p);
             }
@@ -615,6 +617,7 @@ int flatten_scene(
     BlobWriter writer(blob);
     writer.append(&header, sizeof(header));     // rewritten at the end
 
+    uint32_t max_bottom_depth = 0;
     std::vector<TreeDesc> descs(tree_count);
     for (uint32_t ti = 0; ti < tree_count; ++ti)
     {
@@ -656,6 +659,7 @@ int flatten_scene(
             rc = collapse(bv, 3, wo, error);
             if (rc != ASGPU_OK) return rc;
             if (wo.leaf_order.size() != et.tris.size()) { error = "internal error: wide collapse lost triangles"; return ASGPU_E_INVALID; }
+            max_bottom_depth = std::max(max_bottom_depth, wo.depth);
             std::vector<TriRecord> wtris(wo.leaf_order.size());
             for (size_t i = 0; i < wtris.size(); ++i) wtris[i] = et.tris[wo.leaf_order[i]];
             d.wnodes = writer.append(wo.nodes);
@@ -708,6 +712,11 @@ int flatten_scene(
         header.top_wnodes = writer.append(wo.nodes);
         header.top_wnode_count = static_cast<uint32_t>(wo.nodes.size());
         header.top_witems = writer.append(wo.leaf_order);
+        // Deepest traversal stack of the wide kernels: one saved node group per level below the
+        // root in either tree, plus node group, instance group and sentinel when entering an instance.
+        header.wide_stack_need = (wo.depth > 0 ? wo.depth - 1 : 0) + 3 + (max_bottom_depth > 0 ? max_bottom_depth - 1 : 0);
+        if (header.wide_stack_need > WideStackMax)
+        { error = "wide trees too deep for the traversal stack"; return ASGPU_E_UNSUPPORTED; }
         header.wide_node_count += wo.nodes.size();
         header.wide_node_bytes += wo.nodes.size() * sizeof(WNode);
     }

@@ -28,7 +28,8 @@ namespace asgpu
 {
 
 const uint32_t BlobMagic = 0x42534131u;     // "1ASB"
-const uint32_t BlobVersion = 3;
+const uint32_t BlobVersion = 4;
+const uint32_t WideStackMax = 64;           // deepest traversal stack any wide kernel variant offers
 const uint64_t SectionAlign = 256;
 
 const uint32_t InteriorMark = 0xFFFFFFFFu;
@@ -140,7 +141,7 @@ struct BlobHeader
     uint32_t    item_count;
     uint32_t    top_node_count;
     uint32_t    top_wnode_count;
-    uint32_t    pad0;
+    uint32_t    wide_stack_need;    // entries of traversal stack the wide layout can require
     uint64_t    total_bytes;
     uint64_t    trees;              // TreeDesc[tree_count]
     uint64_t    items;              // ItemRecord[item_count]

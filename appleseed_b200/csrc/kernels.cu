@@ -1,22 +1,32 @@
 //
 // kernels.cu -- sm_100a kernels of the intersection engine.
 //
-// One kernel template, instantiated for {closest hit, any hit} x {EXACT, WIDE} x {counters}:
-// persistent CTAs (a multiple of the SM count) whose warps pull 32-ray chunks from a global ray
-// queue (an atomic cursor), one ray per lane, traversal state in registers and, for the wide
-// traversal, a per-thread stack in shared memory laid out [entry][thread] so that a warp's
-// accesses to one stack level hit 32 distinct banks.  Node and triangle records are fetched with
-// 16-byte read-only loads (ld.global.nc.v4).  B200 has no RT cores and the work is not a dense
-// contraction, so tensor cores are not involved; the bound is the memory system (gpu_layout.h
-// states the record sizes that make up the algorithmic bytes per ray).
+// Two kernel templates, each instantiated for {closest hit, any hit} x {counters}: persistent
+// CTAs (a multiple of the SM count) whose warps pull rays from a global ray queue (an atomic
+// cursor), one ray per lane.  Node and triangle records are fetched with 16-byte read-only loads
+// (ld.global.nc.v4).  B200 has no RT cores and the work is not a dense contraction, so tensor
+// cores are not involved (gpu_layout.h states the record sizes that make up the algorithmic bytes
+// per ray).
 //
-// The per-ray logic lives in traverse_core.h.
+//   trace_kernel   EXACT layout: the reference's traversal operation for operation, one ray per
+//                  lane start to finish (the arbiter path).
+//   wide_kernel    WIDE layout, the throughput path.  A warp advances its 32 rays in lock step:
+//                  every step each lane tests ONE 8-wide node (fp32 interval arithmetic), then the
+//                  warp gathers the (ray, triangle) candidates of all its lanes into a shared-memory
+//                  queue and tests them 32 at a time with the exact fp64 test, whichever lane a
+//                  candidate came from.  The fp64 ray, the hit record and the traversal stack
+//                  ([entry][thread], conflict free) live in shared memory; registers only hold the
+//                  fp32 interval form of the ray and the traversal cursor.
+//
+// The per-ray building blocks live in traverse_core.h.
 //
 
 #include "kernels.h"
 #include "traverse_core.h"
 
 #include <cuda_runtime.h>
+
+#include <cstdlib>
 
 namespace asgpu
 {
@@ -36,9 +46,12 @@ struct KernelArgs
     unsigned long long* queue;          // ray queue cursor
     unsigned long long* counters;       // asgpu_counters layout, or nullptr
     const uint32_t*     order;          // optional permutation: ray processed at position i is order[i]
+    int                 refill_threshold;   // idle lanes that trigger a pull from the ray queue
+    int                 flush_threshold;    // queued candidates that trigger a test batch
+    int                 stall_threshold;    // lanes idle or waiting for the queue that trigger one
 };
 
-__device__ __forceinline__ void store_hit(asgpu_hit* out, const SceneView& s, const Ray& ray, const Hit& hit, const bool found)
+__device__ __forceinline__ void store_hit(asgpu_hit* out, const SceneView& s, const double t, const Hit& hit, const bool found)
 {
     // 40-byte record written as five 8-byte stores.
     unsigned long long* dst = reinterpret_cast<unsigned long long*>(out);
@@ -61,122 +74,454 @@ __device__ __forceinline__ void store_hit(asgpu_hit* out, const SceneView& s, co
         prim_type = 2;
         u = hit.u; v = hit.v;
     }
-    dst[0] = static_cast<unsigned long long>(__double_as_longlong(ray.tmax));
+    dst[0] = static_cast<unsigned long long>(__double_as_longlong(t));
     dst[1] = static_cast<unsigned long long>(__float_as_uint(u)) | (static_cast<unsigned long long>(__float_as_uint(v)) << 32);
     dst[2] = static_cast<unsigned long long>(assembly_instance) | (static_cast<unsigned long long>(object_instance) << 32);
     dst[3] = static_cast<unsigned long long>(primitive) | (static_cast<unsigned long long>(slot) << 32);
     dst[4] = static_cast<unsigned long long>(segment) | (static_cast<unsigned long long>(prim_type) << 32);
 }
 
-// Lanes of a warp whose ray has finished are refilled from the queue as soon as at least
-// RefillThreshold of them are idle (or all are), so one long ray does not hold 31 lanes hostage.
-const int RefillThreshold = 8;
-
-template <bool ANY, bool COUNT>
-__device__ __forceinline__ void finish_ray(const KernelArgs& args, const unsigned long long i, const WideTraversal<ANY, COUNT>& tr)
+__device__ __forceinline__ void flush_counters(unsigned long long* counters, const unsigned lane, const unsigned rays_done, const Stats& stats, const unsigned hits_found)
 {
-    if (ANY) args.occluded[i] = tr.found() ? 1 : 0;
-    else store_hit(args.hits + i, args.scene, tr.ray, tr.hit, tr.found());
+    // Warp-reduce, then one atomic per counter per warp.
+    unsigned vals[6] = { rays_done, stats.top_nodes, stats.instances, stats.nodes, stats.triangles, hits_found };
+    #pragma unroll
+    for (int k = 0; k < 6; ++k)
+    {
+        unsigned v = vals[k];
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+        if (lane == 0 && v) atomicAdd(counters + k, static_cast<unsigned long long>(v));
+    }
 }
 
-template <bool ANY, bool WIDE, bool COUNT>
+// ------------------------------------------------------------------------------------------
+// EXACT layout.
+// ------------------------------------------------------------------------------------------
+
+template <bool ANY, bool COUNT>
 __global__ void __launch_bounds__(BlockThreads)
 trace_kernel(const KernelArgs args)
 {
-    __shared__ uint2 wide_stack[WIDE ? WideStackSize * BlockThreads : 1];
-
     const unsigned lane = threadIdx.x & 31;
     Stats stats; stats.top_nodes = stats.instances = stats.nodes = stats.triangles = 0;
     unsigned rays_done = 0, hits_found = 0;
 
-    if (WIDE)
+    for (;;)
     {
-        WideTraversal<ANY, COUNT> tr;
-        unsigned long long index = 0;
-        bool active = false;
-        bool exhausted = false;         // warp-uniform: the queue has no more rays
-        uint2* stack = wide_stack + threadIdx.x;
-
-        for (;;)
+        // Warp-level pull from the ray queue.
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(args.queue, 32ull);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (base >= args.n) break;
+        const unsigned long long pos = base + lane;
+        if (pos < args.n)
         {
-            const unsigned idle = __ballot_sync(0xFFFFFFFFu, !active);
-            if (idle != 0 && !exhausted && (__popc(idle) >= RefillThreshold || idle == 0xFFFFFFFFu))
-            {
-                // Warp-aggregated pull: one atomic for all idle lanes.
-                const int leader = __ffs(idle) - 1;
-                unsigned long long base = 0;
-                if (lane == leader) base = atomicAdd(args.queue, static_cast<unsigned long long>(__popc(idle)));
-                base = __shfl_sync(0xFFFFFFFFu, base, leader);
-                if (!active)
-                {
-                    const unsigned long long pos = base + __popc(idle & ((1u << lane) - 1u));
-                    if (pos < args.n)
-                    {
-                        index = args.order ? args.order[pos] : pos;
-                        tr.begin(args.scene, args.rays, index);
-                        active = true;
-                    }
-                }
-                if (base + __popc(idle) >= args.n) exhausted = true;
-            }
-            else if (idle == 0xFFFFFFFFu) break;        // nothing active and nothing left to fetch
-            if (exhausted && __ballot_sync(0xFFFFFFFFu, active) == 0) break;
-
-            if (active)
-            {
-                if (tr.step(args.scene, args.rays, index, stats, stack, BlockThreads))
-                {
-                    finish_ray<ANY, COUNT>(args, index, tr);
-                    active = false;
-                    if (COUNT) { ++rays_done; hits_found += tr.found() ? 1 : 0; }
-                }
-            }
-        }
-    }
-    else
-    {
-        for (;;)
-        {
-            // Warp-level pull from the ray queue.
-            unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(args.queue, 32ull);
-            base = __shfl_sync(0xFFFFFFFFu, base, 0);
-            if (base >= args.n) break;
-            const unsigned long long pos = base + lane;
-            if (pos < args.n)
-            {
-                const unsigned long long i = args.order ? args.order[pos] : pos;
-                Ray ray;
-                load_ray(args.rays, i, ray);
-                Hit hit;
-                const bool found = exact_trace<ANY, COUNT>(args.scene, ray, hit, stats);
-                if (ANY) args.occluded[i] = found ? 1 : 0;
-                else store_hit(args.hits + i, args.scene, ray, hit, found);
-                if (COUNT) { ++rays_done; hits_found += found ? 1 : 0; }
-            }
+            const unsigned long long i = args.order ? args.order[pos] : pos;
+            Ray ray;
+            load_ray(args.rays, i, ray);
+            Hit hit;
+            const bool found = exact_trace<ANY, COUNT>(args.scene, ray, hit, stats);
+            if (ANY) args.occluded[i] = found ? 1 : 0;
+            else store_hit(args.hits + i, args.scene, ray.tmax, hit, found);
+            if (COUNT) { ++rays_done; hits_found += found ? 1 : 0; }
         }
     }
 
-    if (COUNT)
-    {
-        // Warp-reduce, then one atomic per counter per warp.
-        unsigned vals[6] = { rays_done, stats.top_nodes, stats.instances, stats.nodes, stats.triangles, hits_found };
-        #pragma unroll
-        for (int k = 0; k < 6; ++k)
-        {
-            unsigned v = vals[k];
-            #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
-            if (lane == 0 && v) atomicAdd(args.counters + k, static_cast<unsigned long long>(v));
-        }
-    }
+    if (COUNT) flush_counters(args.counters, lane, rays_done, stats, hits_found);
 }
 
-template <bool ANY, bool WIDE, bool COUNT>
-cudaError_t launch(const KernelArgs& args, const int grid, cudaStream_t stream)
+// ------------------------------------------------------------------------------------------
+// WIDE layout.
+// ------------------------------------------------------------------------------------------
+
+// Lanes of a warp whose ray has finished are refilled from the queue as soon as at least
+// RefillThreshold of them are idle (or all are), so one long ray does not hold 31 lanes hostage.
+const int QueueSlots = 64;          // per warp: < 32 left over + at most 32 pushed per round
+const uint32_t None = 0xFFFFFFFFu;
+
+// Shared memory of one CTA, every per-thread array laid out [component][thread].
+template <int STACK>
+struct WideShared
 {
-    trace_kernel<ANY, WIDE, COUNT><<<grid, BlockThreads, 0, stream>>>(args);
+    uint2               stack[STACK][BlockThreads];
+    double              ray[8][BlockThreads];           // current-space org, dir; tmin; tmax (= closest t so far)
+    unsigned long long  tri_base[BlockThreads];         // blob offset of the current tree's wide triangle records
+    unsigned long long  pose_base[BlockThreads];        // blob offset of its pose pool
+    unsigned long long  best[BlockThreads];             // ordered key of the nearest hit of the running batch
+    unsigned long long  queue[BlockThreads / 32][QueueSlots];
+    uint32_t            flags[BlockThreads];
+    float               time_n[BlockThreads];
+    float               hit_u[BlockThreads], hit_v[BlockThreads];
+    uint32_t            hit_slot[BlockThreads], hit_item[BlockThreads], hit_segment[BlockThreads];
+    uint32_t            cur_item[BlockThreads];
+};
+
+// Monotone map from double to uint64 (for atomicMin on t).
+__device__ __forceinline__ unsigned long long ordered_key(const double t)
+{
+    const unsigned long long b = static_cast<unsigned long long>(__double_as_longlong(t));
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+
+// Tests `count` (<= 32) queued candidates, one per lane.  Entry = (blob offset of the triangle
+// record / 16) << 5 | source lane.  Closest hit: the nearest accepted candidate of each source lane
+// updates that lane's tmax and hit record (ties: lowest queue position).  Any hit: marks the lane.
+template <bool ANY, bool COUNT, int STACK>
+__device__ __forceinline__ void test_candidates(
+    WideShared<STACK>& sm, const uint8_t* blob, const unsigned long long* entries, const unsigned count,
+    const unsigned lane, const unsigned warp_thread0, Stats& stats)
+{
+    bool hit = false;
+    double t = 0.0, u = 0.0, v = 0.0;
+    uint32_t slot = 0, segment = 0;
+    unsigned st = warp_thread0;
+    if (!ANY) sm.best[warp_thread0 + lane] = ~0ull;
+    if (lane < count)
+    {
+        const unsigned long long e = entries[lane];
+        st = warp_thread0 + static_cast<unsigned>(e & 31u);
+        Ray ray;
+        #pragma unroll
+        for (int k = 0; k < 3; ++k) { ray.org[k] = sm.ray[k][st]; ray.dir[k] = sm.ray[3 + k][st]; }
+        ray.tmin = sm.ray[6][st];
+        ray.tmax = sm.ray[7][st];
+        ray.flags = sm.flags[st];
+        ray.time_normalized = sm.time_n[st];
+        ray.time_absolute = 0.0f;
+        if (COUNT) ++stats.triangles;
+        TriD tri;
+        if (fetch_triangle<ANY>(blob + ((e >> 5) << 4), blob + sm.pose_base[st], ray, tri, slot, segment))
+            hit = mt_test<!ANY>(tri, ray, t, u, v);
+    }
+    if (ANY)
+    {
+        if (hit) sm.hit_item[st] = sm.cur_item[st];
+        __syncwarp();
+        return;
+    }
+    const unsigned hits = __ballot_sync(0xFFFFFFFFu, hit);
+    if (hits == 0) return;
+    __syncwarp();                                   // best[] initialised
+    const unsigned long long key = ordered_key(t);
+    if (hit) atomicMin(&sm.best[st], key);
+    __syncwarp();
+    const bool win = hit && sm.best[st] == key;
+    const unsigned winners = __ballot_sync(0xFFFFFFFFu, win);
+    if (win)
+    {
+        const unsigned peers = __match_any_sync(winners, st);
+        if (lane == static_cast<unsigned>(__ffs(peers) - 1))
+        {
+            sm.ray[7][st] = t;
+            sm.hit_u[st] = static_cast<float>(u);
+            sm.hit_v[st] = static_cast<float>(v);
+            sm.hit_slot[st] = slot;
+            sm.hit_segment[st] = segment;
+            sm.hit_item[st] = sm.cur_item[st];
+        }
+    }
+    __syncwarp();
+}
+
+template <bool ANY, bool COUNT, int STACK>
+__global__ void __launch_bounds__(BlockThreads)
+wide_kernel(const KernelArgs args)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    WideShared<STACK>& sm = *reinterpret_cast<WideShared<STACK>*>(smem_raw);
+
+    const unsigned tid = threadIdx.x;
+    const unsigned lane = tid & 31;
+    const unsigned warp_thread0 = tid - lane;
+    const unsigned lanes_below = (1u << lane) - 1u;
+    unsigned long long* queue = sm.queue[tid >> 5];
+    const SceneView& s = args.scene;
+    const uint8_t* blob = s.blob;
+    uint2* stack = &sm.stack[0][tid];
+    const uint32_t stride = BlockThreads;
+
+    Stats stats; stats.top_nodes = stats.instances = stats.nodes = stats.triangles = 0;
+    unsigned rays_done = 0, hits_found = 0;
+
+    // Per-lane traversal cursor.
+    WideRay w;
+    const uint8_t* wnodes = blob;
+    uint2 ngroup, tgroup;               // pending internal children / pending instances (world space)
+    ngroup.x = ngroup.y = tgroup.x = tgroup.y = 0;
+    uint32_t fetch = None;              // wide node to test next
+    uint32_t sp = 0;
+    uint32_t cur_item = None;           // None while in world space
+    unsigned long long index = 0;
+    bool active = false;                // this lane owns a ray
+    bool traversed = false;             // ... whose traversal is complete (it may still wait for queued candidates)
+    bool waiting = false;               // ... and which has candidates in the queue
+    bool exhausted = false;             // warp-uniform: the ray queue has no more rays
+    unsigned queued = 0;                // warp-uniform: candidates waiting in the queue
+
+    for (;;)
+    {
+        // ---- refill idle lanes from the ray queue (one atomic per warp) -------------------------
+        const unsigned idle = __ballot_sync(0xFFFFFFFFu, !active);
+        if (idle != 0 && !exhausted && (__popc(idle) >= args.refill_threshold || idle == 0xFFFFFFFFu))
+        {
+            const int leader = __ffs(idle) - 1;
+            unsigned long long base = 0;
+            if (lane == leader) base = atomicAdd(args.queue, static_cast<unsigned long long>(__popc(idle)));
+            base = __shfl_sync(0xFFFFFFFFu, base, leader);
+            if (!active)
+            {
+                const unsigned long long pos = base + __popc(idle & lanes_below);
+                if (pos < args.n)
+                {
+                    index = args.order ? args.order[pos] : pos;
+                    Ray ray;
+                    load_ray(args.rays, index, ray);
+                    sm.ray[6][tid] = ray.tmin;
+                    sm.ray[7][tid] = ray.tmax;
+                    sm.flags[tid] = ray.flags;
+                    sm.time_n[tid] = ray.time_normalized;
+                    sm.hit_item[tid] = None;
+                    sm.hit_slot[tid] = 0; sm.hit_segment[tid] = 0;
+                    sm.hit_u[tid] = 0.0f; sm.hit_v[tid] = 0.0f;
+                    sm.cur_item[tid] = None;
+                    make_wide_ray(ray.org, ray.dir, ray.tmin, ray.tmax, w);
+                    wnodes = blob + s.top_wnodes;
+                    ngroup.y = 0; tgroup.y = 0;
+                    fetch = s.top_wnode_count != 0 ? 0u : None;
+                    sp = 0;
+                    cur_item = None;
+                    active = true; traversed = false; waiting = false;
+                }
+            }
+            if (base + __popc(idle) >= args.n) exhausted = true;
+        }
+        else if (idle == 0xFFFFFFFFu) break;            // nothing active and nothing left to fetch
+        if (exhausted && __ballot_sync(0xFFFFFFFFu, active) == 0) break;
+
+        // ---- one traversal step per active lane ---------------------------------------------------
+        uint32_t pending = 0, tri_first = 0;            // leaf triangles found by this step's node test
+        bool held = false;                              // this lane cannot advance before the queue drains
+        if (active && !traversed)
+        {
+            if (fetch == None)
+            {
+                if (tgroup.y && waiting)
+                {
+                    // Queued candidates still refer to this lane's instance-space ray: it must not
+                    // be replaced by the next instance's before they are tested.
+                    held = true;
+                }
+                else if (tgroup.y)
+                {
+                    // Next assembly instance: AssemblyLeafVisitor::visit (assemblytree.cpp:604-744).
+                    const int bit = high_bit(tgroup.y);
+                    tgroup.y &= ~(1u << bit);
+                    const uint32_t item = load4(blob + s.top_witems + static_cast<uint64_t>(tgroup.x + bit) * 4);
+                    const uint8_t* ip = blob + s.items + static_cast<uint64_t>(item) * sizeof(ItemRecord);
+                    const uint4 meta = load16(ip + 96);
+                    if ((meta.y & sm.flags[tid]) && meta.x != None)
+                    {
+                        if (COUNT) ++stats.instances;
+                        // Save the world-space cursor, then descend.  When nothing is left to do in
+                        // world space there is nothing to come back to: no sentinel, the ray ends
+                        // with the instance.
+                        if (ngroup.y & 0xFF000000u) { stack[sp * stride] = ngroup; ++sp; }
+                        if (tgroup.y) { stack[sp * stride] = tgroup; ++sp; }
+                        if (sp != 0)
+                        {
+                            uint2 sentinel; sentinel.x = None; sentinel.y = 0;
+                            stack[sp * stride] = sentinel; ++sp;
+                        }
+                        Ray world;
+                        load_ray_org_dir(args.rays, index, world);
+                        double lorg[3], ldir[3];
+                        instance_org_dir(ip, world.org, world.dir, lorg, ldir);
+                        #pragma unroll
+                        for (int k = 0; k < 3; ++k) { sm.ray[k][tid] = lorg[k]; sm.ray[3 + k][tid] = ldir[k]; }
+                        make_wide_ray(lorg, ldir, sm.ray[6][tid], sm.ray[7][tid], w);
+                        const uint8_t* tp = blob + s.trees + static_cast<uint64_t>(meta.x) * sizeof(TreeDesc);
+                        const uint2 o_nodes = load8(tp + offsetof(TreeDesc, wnodes));
+                        const uint2 o_tris = load8(tp + offsetof(TreeDesc, wtris));
+                        const uint2 o_poses = load8(tp + offsetof(TreeDesc, poses));
+                        const uint32_t wnode_count = load4(tp + offsetof(TreeDesc, wnode_count));
+                        wnodes = blob + (static_cast<uint64_t>(o_nodes.x) | (static_cast<uint64_t>(o_nodes.y) << 32));
+                        sm.tri_base[tid] = static_cast<uint64_t>(o_tris.x) | (static_cast<uint64_t>(o_tris.y) << 32);
+                        sm.pose_base[tid] = static_cast<uint64_t>(o_poses.x) | (static_cast<uint64_t>(o_poses.y) << 32);
+                        sm.cur_item[tid] = item;
+                        cur_item = item;
+                        ngroup.y = 0; tgroup.y = 0;
+                        if (wnode_count != 0) fetch = 0;
+                    }
+                }
+                else
+                {
+                    if (!(ngroup.y & 0xFF000000u))
+                    {
+                        if (sp == 0) traversed = true;
+                        else
+                        {
+                            --sp;
+                            const uint2 top = stack[sp * stride];
+                            if (top.x == None && top.y == 0)
+                            {
+                                // Back to world space: the world ray comes from the ray arrays again.
+                                // (Candidates of the instance still in the queue carry all they need.)
+                                Ray world;
+                                load_ray_org_dir(args.rays, index, world);
+                                make_wide_ray(world.org, world.dir, sm.ray[6][tid], sm.ray[7][tid], w);
+                                wnodes = blob + s.top_wnodes;
+                                cur_item = None;
+                            }
+                            else if (top.y & 0xFF000000u) ngroup = top;
+                            else tgroup = top;
+                        }
+                    }
+                    if (ngroup.y & 0xFF000000u)
+                    {
+                        // Next internal child of the current group, nearest octant slot first.
+                        const int bit = high_bit(ngroup.y);
+                        ngroup.y &= ~(1u << bit);
+                        const uint32_t k = static_cast<uint32_t>(bit - 24) ^ (7 - (w.oct & 7));
+                        fetch = ngroup.x + popc(ngroup.y & 0xFFu & ((1u << k) - 1u));
+                    }
+                }
+            }
+
+            if (fetch != None)
+            {
+                if (COUNT) { if (cur_item != None) ++stats.nodes; else ++stats.top_nodes; }
+                if (ngroup.y & 0xFF000000u) { stack[sp * stride] = ngroup; ++sp; }
+                uint32_t child_base, tri_base, nmask, tmask;
+                wide_node_test(wnodes + static_cast<uint64_t>(fetch) * sizeof(WNode), w, child_base, tri_base, nmask, tmask);
+                ngroup.x = child_base; ngroup.y = nmask;
+                if (cur_item != None) { pending = tmask; tri_first = tri_base; }
+                else { tgroup.x = tri_base; tgroup.y = tmask; }
+                fetch = None;
+            }
+        }
+
+        // ---- gather this step's triangle candidates -------------------------------------------------
+        bool tested = false;                            // warp-uniform: a batch ran in this iteration
+        unsigned pushers = __ballot_sync(0xFFFFFFFFu, pending != 0);
+        if (pushers != 0)
+        {
+            if (pending != 0) waiting = true;
+            __syncwarp();                               // the ray / tree data of new lanes is visible
+            do
+            {
+                if (pending != 0)
+                {
+                    const int bit = high_bit(pending);
+                    pending &= ~(1u << bit);
+                    const unsigned long long off = sm.tri_base[tid] + static_cast<unsigned long long>(tri_first + bit) * sizeof(TriRecord);
+                    queue[queued + __popc(pushers & lanes_below)] = ((off >> 4) << 5) | lane;
+                }
+                queued += __popc(pushers);
+                __syncwarp();
+                if (queued >= 32)
+                {
+                    queued -= 32;
+                    test_candidates<ANY, COUNT, STACK>(sm, blob, queue + queued, 32, lane, warp_thread0, stats);
+                    tested = true;
+                }
+                pushers = __ballot_sync(0xFFFFFFFFu, pending != 0);
+            } while (pushers != 0);
+        }
+
+        // ---- flush the queue when it is full enough or too many lanes wait for it -------------------
+        if (queued != 0)
+        {
+            const unsigned stalled = __ballot_sync(0xFFFFFFFFu, !active || held || (traversed && waiting));
+            if (queued >= args.flush_threshold || __popc(stalled) >= args.stall_threshold)
+            {
+                test_candidates<ANY, COUNT, STACK>(sm, blob, queue, queued, lane, warp_thread0, stats);
+                queued = 0;
+                tested = true;
+            }
+        }
+        if (queued == 0) waiting = false;
+
+        // ---- pick up the results, retire finished rays ---------------------------------------------
+        if (active)
+        {
+            if (tested)
+            {
+                if (ANY) { if (sm.hit_item[tid] != None) traversed = true; }    // retires once its queued candidates are gone
+                else
+                {
+                    const double tmin = sm.ray[6][tid];
+                    w.tmax_f = d2f_up(dsub(sm.ray[7][tid], tmin < 0.0 ? tmin : 0.0));
+                }
+            }
+            if (traversed && !waiting)
+            {
+                const bool found = sm.hit_item[tid] != None;
+                if (ANY) args.occluded[index] = found ? 1 : 0;
+                else
+                {
+                    Hit hit;
+                    hit.u = sm.hit_u[tid]; hit.v = sm.hit_v[tid];
+                    hit.item = sm.hit_item[tid]; hit.slot = sm.hit_slot[tid]; hit.segment = sm.hit_segment[tid];
+                    store_hit(args.hits + index, s, sm.ray[7][tid], hit, found);
+                }
+                if (COUNT) { ++rays_done; hits_found += found ? 1 : 0; }
+                active = false;
+            }
+        }
+    }
+
+    if (COUNT) flush_counters(args.counters, lane, rays_done, stats, hits_found);
+}
+
+// Scheduling knobs of the wide kernel.  Defaults are the measured optimum (profiles/README.md);
+// ASGPU_REFILL / ASGPU_FLUSH / ASGPU_STALL override them for experiments.
+struct Tuning { int refill, flush, stall; };
+
+Tuning tuning()
+{
+    Tuning v = { 8, 16, 16 };
+    if (const char* e = getenv("ASGPU_REFILL")) v.refill = atoi(e);
+    if (const char* e = getenv("ASGPU_FLUSH")) v.flush = atoi(e);
+    if (const char* e = getenv("ASGPU_STALL")) v.stall = atoi(e);
+    if (v.refill < 1) v.refill = 1;
+    if (v.flush < 1) v.flush = 1;
+    if (v.stall < 1) v.stall = 1;
+    if (v.stall > 32) v.stall = 32;         // 32 stalled lanes = nobody can advance: must flush
+    return v;
+}
+
+// Occupancy-sized persistent launch of one instantiation.
+template <typename Kernel>
+cudaError_t launch_persistent(Kernel kernel, const KernelArgs& args, const size_t smem, const int sm_count, cudaStream_t stream)
+{
+    cudaError_t err = cudaSuccess;
+    if (smem > 48 * 1024)
+    {
+        err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (err != cudaSuccess) return err;
+    }
+    int blocks_per_sm = 0;
+    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kernel, BlockThreads, smem);
+    if (err != cudaSuccess) return err;
+    if (blocks_per_sm < 1) blocks_per_sm = 1;
+    // Persistent grid: a multiple of the SM count, no larger than the work.
+    long long grid = static_cast<long long>(sm_count) * blocks_per_sm;
+    const long long needed = static_cast<long long>((args.n + BlockThreads - 1) / BlockThreads);
+    if (grid > needed) grid = needed;
+    if (grid < 1) grid = 1;
+    kernel<<<static_cast<unsigned>(grid), BlockThreads, smem, stream>>>(args);
     return cudaGetLastError();
+}
+
+template <int STACK>
+cudaError_t launch_wide(const KernelArgs& args, const bool any_hit, const bool count, const int sm_count, cudaStream_t stream)
+{
+    const size_t smem = sizeof(WideShared<STACK>);
+    if (any_hit) return count ? launch_persistent(wide_kernel<true, true, STACK>, args, smem, sm_count, stream)
+                              : launch_persistent(wide_kernel<true, false, STACK>, args, smem, sm_count, stream);
+    return count ? launch_persistent(wide_kernel<false, true, STACK>, args, smem, sm_count, stream)
+                 : launch_persistent(wide_kernel<false, false, STACK>, args, smem, sm_count, stream);
 }
 
 }   // anonymous namespace
@@ -205,38 +550,27 @@ int launch_trace(
     args.queue = queue;
     args.counters = counters;
     args.order = order;
+    const Tuning knobs = tuning();
+    args.refill_threshold = knobs.refill;
+    args.flush_threshold = knobs.flush;
+    args.stall_threshold = knobs.stall;
 
     cudaError_t err = cudaMemsetAsync(queue, 0, sizeof(unsigned long long), stream);
     if (err != cudaSuccess) return static_cast<int>(err);
 
-    // Persistent grid: a multiple of the SM count, no larger than the work.
-    int blocks_per_sm = 0;
-    const void* fn = nullptr;
-    #define ASGPU_PICK(A, W, C) (const void*)trace_kernel<A, W, C>
     const bool count = counters != nullptr;
-    if (any_hit) fn = wide ? (count ? ASGPU_PICK(true, true, true) : ASGPU_PICK(true, true, false))
-                           : (count ? ASGPU_PICK(true, false, true) : ASGPU_PICK(true, false, false));
-    else fn = wide ? (count ? ASGPU_PICK(false, true, true) : ASGPU_PICK(false, true, false))
-                   : (count ? ASGPU_PICK(false, false, true) : ASGPU_PICK(false, false, false));
-    #undef ASGPU_PICK
-    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, fn, BlockThreads, 0);
-    if (err != cudaSuccess) return static_cast<int>(err);
-    if (blocks_per_sm < 1) blocks_per_sm = 1;
-    long long grid = static_cast<long long>(sm_count) * blocks_per_sm;
-    const long long needed = static_cast<long long>((n + BlockThreads - 1) / BlockThreads);
-    if (grid > needed) grid = needed;
-    if (grid < 1) grid = 1;
-
-    if (any_hit)
+    if (wide)
     {
-        if (wide) err = count ? launch<true, true, true>(args, (int)grid, stream) : launch<true, true, false>(args, (int)grid, stream);
-        else      err = count ? launch<true, false, true>(args, (int)grid, stream) : launch<true, false, false>(args, (int)grid, stream);
+        // The traversal stack lives in shared memory; its depth is the scene's (flatten.cpp
+        // computes the bound), rounded up to one of the compiled variants.
+        if (scene.wide_stack_need <= 24) err = launch_wide<24>(args, any_hit, count, sm_count, stream);
+        else if (scene.wide_stack_need <= 40) err = launch_wide<40>(args, any_hit, count, sm_count, stream);
+        else err = launch_wide<WideStackMax>(args, any_hit, count, sm_count, stream);
     }
-    else
-    {
-        if (wide) err = count ? launch<false, true, true>(args, (int)grid, stream) : launch<false, true, false>(args, (int)grid, stream);
-        else      err = count ? launch<false, false, true>(args, (int)grid, stream) : launch<false, false, false>(args, (int)grid, stream);
-    }
+    else if (any_hit) err = count ? launch_persistent(trace_kernel<true, true>, args, 0, sm_count, stream)
+                                  : launch_persistent(trace_kernel<true, false>, args, 0, sm_count, stream);
+    else err = count ? launch_persistent(trace_kernel<false, true>, args, 0, sm_count, stream)
+                     : launch_persistent(trace_kernel<false, false>, args, 0, sm_count, stream);
     return static_cast<int>(err);
 }
 

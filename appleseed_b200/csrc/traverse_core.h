@@ -72,6 +72,23 @@ ASGPU_HD float  fma_dn(float a, float b, float c) { return __fmaf_rd(a, b, c); }
 ASGPU_HD float  fma_up(float a, float b, float c) { return __fmaf_ru(a, b, c); }
 ASGPU_HD float  d2f_dn(double a) { return __double2float_rd(a); }
 ASGPU_HD float  d2f_up(double a) { return __double2float_ru(a); }
+// Bounds of 1 / a for a >= 0 from the hardware approximation (rcp.approx.f32, relative error
+// <= 2^-23 per the PTX ISA; the margin allows 2^-21) instead of a correctly rounded division:
+// frcp_dn(a) <= 1 / a <= frcp_up(a).  The lower bound is kept finite (and 0 where the quotient
+// would be subnormal); frcp_dn(0) = frcp_up(0) = +inf.
+ASGPU_HD float  rcp_approx(float a) { float r; asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(a)); return r; }
+ASGPU_HD float  frcp_dn(float a)
+{
+    if (a == 0.0f) return __int_as_float(0x7F800000);
+    if (a > 4.0e37f) return 0.0f;
+    const float r = __fmul_rd(rcp_approx(a), 0.99999952316284f);        // 1 - 2^-21
+    return r == __int_as_float(0x7F800000) ? 3.402823466e38f : r;       // a NaN stays a NaN
+}
+ASGPU_HD float  frcp_up(float a)
+{
+    return fmaxf(__fmul_ru(rcp_approx(a), 1.00000047683716f), 3.0e-38f);    // 1 + 2^-21; NaN -> 3e-38 only for a NaN ray
+}
+ASGPU_HD bool   sign_bit(double a) { return __double2hiint(a) < 0; }
 ASGPU_HD float  fmin_nan(float a, float b) { return fminf(a, b); }     // returns the non-NaN operand
 ASGPU_HD float  fmax_nan(float a, float b) { return fmaxf(a, b); }
 ASGPU_HD float  bits_to_float(uint32_t u) { return __uint_as_float(u); }
@@ -114,6 +131,9 @@ inline float  fma_dn(float a, float b, float c) { RoundScope s(FE_DOWNWARD); vol
 inline float  fma_up(float a, float b, float c) { RoundScope s(FE_UPWARD);   volatile float x = a, y = b, z = c; volatile float r = std::fmaf(x, y, z); return r; }
 inline float  d2f_dn(double a) { RoundScope s(FE_DOWNWARD); volatile double x = a; volatile float r = static_cast<float>(x); return r; }
 inline float  d2f_up(double a) { RoundScope s(FE_UPWARD);   volatile double x = a; volatile float r = static_cast<float>(x); return r; }
+inline float  frcp_dn(float a) { RoundScope s(FE_DOWNWARD); volatile float x = a, one = 1.0f; volatile float r = one / x; return r; }
+inline float  frcp_up(float a) { RoundScope s(FE_UPWARD);   volatile float x = a, one = 1.0f; volatile float r = one / x; return r; }
+inline bool   sign_bit(double a) { return std::signbit(a); }
 inline float  fmin_nan(float a, float b) { return std::fmin(a, b); }
 inline float  fmax_nan(float a, float b) { return std::fmax(a, b); }
 inline float  bits_to_float(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
@@ -138,6 +158,7 @@ struct SceneView
     const uint8_t*  blob;
     uint64_t        trees, items, top_nodes, top_wnodes, top_witems;
     uint32_t        tree_count, item_count, top_node_count, top_wnode_count;
+    uint32_t        wide_stack_need;
 };
 
 struct Ray
@@ -184,7 +205,7 @@ ASGPU_HD void load_ray(const asgpu_rays& rays, const size_t i, Ray& r)
 // compute_assembly_instance_ray (assemblytree.cpp:556-596) with Transform::vector_to_local /
 // point_to_local (transform.h:311-344, 381-400): products accumulated left to right; the
 // instance matrix is affine so w == 1 and no division happens.
-ASGPU_HD void to_instance_space(const uint8_t* item, const Ray& world, Ray& local)
+ASGPU_HD void instance_org_dir(const uint8_t* item, const double worg[3], const double wdir[3], double lorg[3], double ldir[3])
 {
     double m[12];
 #if ASGPU_DEVICE_CODE
@@ -197,9 +218,14 @@ ASGPU_HD void to_instance_space(const uint8_t* item, const Ray& world, Ray& loca
     for (int r = 0; r < 3; ++r)
     {
         const double* row = m + r * 4;
-        local.dir[r] = dadd(dadd(dmul(row[0], world.dir[0]), dmul(row[1], world.dir[1])), dmul(row[2], world.dir[2]));
-        local.org[r] = dadd(dadd(dadd(dmul(row[0], world.org[0]), dmul(row[1], world.org[1])), dmul(row[2], world.org[2])), row[3]);
+        ldir[r] = dadd(dadd(dmul(row[0], wdir[0]), dmul(row[1], wdir[1])), dmul(row[2], wdir[2]));
+        lorg[r] = dadd(dadd(dadd(dmul(row[0], worg[0]), dmul(row[1], worg[1])), dmul(row[2], worg[2])), row[3]);
     }
+}
+
+ASGPU_HD void to_instance_space(const uint8_t* item, const Ray& world, Ray& local)
+{
+    instance_org_dir(item, world.org, world.dir, local.org, local.dir);
     local.tmin = world.tmin;
     local.tmax = world.tmax;
     local.time_absolute = world.time_absolute;
@@ -567,35 +593,40 @@ struct WideRay
     float       o_lo[3], o_hi[3];   // origin interval (already mirrored per axis)
     float       rn[3], rf[3];       // |1 / dir| interval
     float       tmin_f, tmax_f;     // shifted parameter interval, rounded outward
-    uint32_t    oct;                // bit a set: direction negative along axis a
+    uint32_t    oct;                // bit a (0-2) set: direction negative along axis a; bit 3: some component is exactly 0
     double      shift;
 };
 
-ASGPU_HD void make_wide_ray(const Ray& r, WideRay& w)
+ASGPU_HD void make_wide_ray(const double org[3], const double dir[3], const double tmin, const double tmax, WideRay& w)
 {
-    w.shift = r.tmin < 0.0 ? r.tmin : 0.0;
+    w.shift = tmin < 0.0 ? tmin : 0.0;
     w.oct = 0;
 #if ASGPU_DEVICE_CODE
     #pragma unroll
 #endif
     for (int a = 0; a < 3; ++a)
     {
-        const double rcp = ddiv(1.0, r.dir[a]);
-        // Same sign convention as RayInfo (ray.h:313-321): negative when rcp < 0 (incl. -inf for -0.0).
-        const bool neg = !(rcp >= 0.0);
+        // Same sign convention as RayInfo (ray.h:313-321), which tests 1 / dir >= 0: negative for
+        // dir < 0, -0.0 (1 / -0.0 = -inf) and NaN.
+        const double d = dir[a];
+        const bool neg = !(d > 0.0 || (d == 0.0 && !sign_bit(d)));
         if (neg) w.oct |= 1u << a;
-        const double mag = neg ? -rcp : rcp;
-        w.rn[a] = d2f_dn(mag);
-        w.rf[a] = d2f_up(mag);
-        double o = r.org[a];
+        if (d == 0.0) w.oct |= 8u;
+        // [rn, rf] encloses |1 / dir|: directed fp32 reciprocals of an fp32 enclosure of |dir|
+        // (no fp64 division).  |dir| = 0 gives rn = rf = +inf, a NaN gives NaNs (dropped by the
+        // min/max of the box test = "no constraint").
+        const double mag = fabs(d);                 // also clears the sign of -0.0
+        w.rn[a] = frcp_dn(d2f_up(mag));
+        w.rf[a] = frcp_up(d2f_dn(mag));
+        const double o = org[a];
         float lo, hi;
         if (w.shift != 0.0)
         {
             // Shifted origin o + shift * dir, widened by a bound on its fp64 rounding error.
-            const double step = dmul(w.shift, r.dir[a]);
+            const double step = dmul(w.shift, d);
             const double moved = dadd(o, step);
-            const double mag = dadd(o < 0.0 ? -o : o, step < 0.0 ? -step : step);
-            const double err = dmul(mag, 4.5e-16);
+            const double mag2 = dadd(o < 0.0 ? -o : o, step < 0.0 ? -step : step);
+            const double err = dmul(mag2, 4.5e-16);
             lo = d2f_dn(dsub(moved, err));
             hi = d2f_up(dadd(moved, err));
         }
@@ -604,9 +635,11 @@ ASGPU_HD void make_wide_ray(const Ray& r, WideRay& w)
         w.o_lo[a] = neg ? -hi : lo;
         w.o_hi[a] = neg ? -lo : hi;
     }
-    w.tmin_f = d2f_dn(dsub(r.tmin, w.shift));
-    w.tmax_f = d2f_up(dsub(r.tmax, w.shift));
+    w.tmin_f = d2f_dn(dsub(tmin, w.shift));
+    w.tmax_f = d2f_up(dsub(tmax, w.shift));
 }
+
+ASGPU_HD void make_wide_ray(const Ray& r, WideRay& w) { make_wide_ray(r.org, r.dir, r.tmin, r.tmax, w); }
 
 ASGPU_HD void shrink_wide_ray(const Ray& r, WideRay& w)
 {
@@ -623,9 +656,22 @@ ASGPU_HD float byte_to_float(const uint32_t word, const int k)
 #endif
 }
 
-// Tests the 8 children of a wide node.  Returns (internal-hit bits << 24 | imask) in `nmask` and
-// the triangle-hit bits in `tmask`; fills child_base / tri_base.
-ASGPU_HD void wide_node_test(const uint8_t* np, const WideRay& w, uint32_t& child_base, uint32_t& tri_base, uint32_t& nmask, uint32_t& tmask)
+// Tests the 8 children of a wide node.  Returns (internal-hit bits << 24 | imask) in `nmask` (the
+// internal-hit bits permuted so that the highest set bit is the child to visit first for this
+// ray's octant) and the triangle-hit bits in `tmask`; fills child_base / tri_base.
+//
+// Per axis, in the mirrored frame, a child plane sits at p + q * s (exact) and the entry / exit
+// parameters are bounded by
+//     tau_near >= (a_lo + q_near * s) * rn,    tau_far <= (a_hi + q_far * s) * rf
+// with a_lo <= p - o <= a_hi.  EXPANDED = false evaluates exactly that (one FMA and one multiply
+// per plane, directed rounding).  EXPANDED = true distributes the reciprocal once per node,
+//     tau_near >= q_near * (s * rn) + a_lo * rn,    tau_far <= q_far * (s * rf) + a_hi * rf,
+// one FMA per plane; every rounding still goes outward, so both forms never miss a box the
+// reference's fp64 slab test on the tighter binary box would enter.  The expanded form produces
+// NaNs (= "no constraint", conservative but useless) when a reciprocal is infinite, so rays with
+// an exactly zero direction component (oct bit 3) take the other form.
+template <bool EXPANDED>
+ASGPU_HD void wide_node_test_form(const uint8_t* np, const WideRay& w, uint32_t& child_base, uint32_t& tri_base, uint32_t& nmask, uint32_t& tmask)
 {
     const uint4 n0 = load16(np), n1 = load16(np + 16), n2 = load16(np + 32), n3 = load16(np + 48), n4 = load16(np + 64);
     child_base = n1.x;
@@ -637,7 +683,7 @@ ASGPU_HD void wide_node_test(const uint8_t* np, const WideRay& w, uint32_t& chil
     const uint32_t qhi[3][2] = { { n3.z, n3.w }, { n4.x, n4.y }, { n4.z, n4.w } };
     const float origin[3] = { u2f(n0.x), u2f(n0.y), u2f(n0.z) };
 
-    float s[3], a_lo[3], a_hi[3];
+    float cn[3], cf[3], bn[3], bf[3];       // EXPANDED: plane coefficients; else s, s, a_lo, a_hi
     uint32_t qn[3][2], qf[3][2];
 #if ASGPU_DEVICE_CODE
     #pragma unroll
@@ -647,42 +693,67 @@ ASGPU_HD void wide_node_test(const uint8_t* np, const WideRay& w, uint32_t& chil
         const bool neg = (w.oct >> a) & 1;
         const float scale = u2f(((n0.w >> (8 * a)) & 0xFF) << 23);
         const float p = neg ? -origin[a] : origin[a];       // node origin in the mirrored frame
-        s[a] = neg ? -scale : scale;
-        a_lo[a] = fsub_dn(p, w.o_hi[a]);
-        a_hi[a] = fsub_up(p, w.o_lo[a]);
+        const float s = neg ? -scale : scale;
+        const float a_lo = fsub_dn(p, w.o_hi[a]);
+        const float a_hi = fsub_up(p, w.o_lo[a]);
+        if (EXPANDED)
+        {
+            cn[a] = fmul_dn(s, w.rn[a]); bn[a] = fmul_dn(a_lo, w.rn[a]);
+            cf[a] = fmul_up(s, w.rf[a]); bf[a] = fmul_up(a_hi, w.rf[a]);
+        }
+        else { cn[a] = s; cf[a] = s; bn[a] = a_lo; bf[a] = a_hi; }
         qn[a][0] = neg ? qhi[a][0] : qlo[a][0]; qn[a][1] = neg ? qhi[a][1] : qlo[a][1];
         qf[a][0] = neg ? qlo[a][0] : qhi[a][0]; qf[a][1] = neg ? qlo[a][1] : qhi[a][1];
     }
 
-    const uint32_t oct_inv = 7 - w.oct;
-    nmask = 0; tmask = 0;
+    uint32_t hitmask = 0;
 #if ASGPU_DEVICE_CODE
     #pragma unroll
 #endif
     for (int k = 0; k < 8; ++k)
     {
-        const uint32_t meta = ((k < 4 ? meta_lo : meta_hi) >> (8 * (k & 3))) & 0xFF;
         float tn = w.tmin_f, tf = w.tmax_f;
 #if ASGPU_DEVICE_CODE
         #pragma unroll
 #endif
         for (int a = 0; a < 3; ++a)
         {
-            const float dn = fma_dn(byte_to_float(qn[a][k >> 2], k & 3), s[a], a_lo[a]);
-            const float df = fma_up(byte_to_float(qf[a][k >> 2], k & 3), s[a], a_hi[a]);
-            tn = fmax_nan(tn, fmul_dn(dn, w.rn[a]));
-            tf = fmin_nan(tf, fmul_up(df, w.rf[a]));
+            const float fn = byte_to_float(qn[a][k >> 2], k & 3);
+            const float ff = byte_to_float(qf[a][k >> 2], k & 3);
+            if (EXPANDED)
+            {
+                tn = fmax_nan(tn, fma_dn(fn, cn[a], bn[a]));
+                tf = fmin_nan(tf, fma_up(ff, cf[a], bf[a]));
+            }
+            else
+            {
+                tn = fmax_nan(tn, fmul_dn(fma_dn(fn, cn[a], bn[a]), w.rn[a]));
+                tf = fmin_nan(tf, fmul_up(fma_up(ff, cf[a], bf[a]), w.rf[a]));
+            }
         }
-        if (meta != 0 && tn <= tf)
-        {
-            if ((imask >> k) & 1) nmask |= 1u << (24 + (k ^ oct_inv));
-            else tmask |= (meta >> 5) << (meta & 31);
-        }
+        // meta: 0 = empty; internal child 0x20 | (24 + k); leaf (unary count << 5) | first slot.
+        const uint32_t meta = ((k < 4 ? meta_lo : meta_hi) >> (8 * (k & 3))) & 0xFF;
+        const uint32_t bits = (meta >> 5) << (meta & 31);
+        hitmask |= tn <= tf ? bits : 0u;
     }
-    nmask |= imask;
+
+    // Internal hits sit at bit 24 + k; move child k to bit 24 + (k ^ (7 - octant)).
+    uint32_t x = hitmask >> 24;
+    const uint32_t oct_inv = 7 - (w.oct & 7);
+    if (oct_inv & 1) x = ((x & 0xAAu) >> 1) | ((x & 0x55u) << 1);
+    if (oct_inv & 2) x = ((x & 0xCCu) >> 2) | ((x & 0x33u) << 2);
+    if (oct_inv & 4) x = ((x & 0xF0u) >> 4) | ((x & 0x0Fu) << 4);
+    nmask = (x << 24) | imask;
+    tmask = hitmask & 0x00FFFFFFu;
 }
 
-const uint32_t WideStackSize = 32;
+ASGPU_HD void wide_node_test(const uint8_t* np, const WideRay& w, uint32_t& child_base, uint32_t& tri_base, uint32_t& nmask, uint32_t& tmask)
+{
+    if (w.oct & 8) wide_node_test_form<false>(np, w, child_base, tri_base, nmask, tmask);
+    else wide_node_test_form<true>(np, w, child_base, tri_base, nmask, tmask);
+}
+
+const uint32_t WideStackSize = WideStackMax;       // host driver; the kernels pick a depth per scene
 
 ASGPU_HD void load_ray_org_dir(const asgpu_rays& rays, const size_t i, Ray& r)
 {
@@ -810,7 +881,7 @@ struct WideTraversal
         {
             const int bit = high_bit(ngroup.y);
             ngroup.y &= ~(1u << bit);
-            const uint32_t k = static_cast<uint32_t>(bit - 24) ^ (7 - wr.oct);
+            const uint32_t k = static_cast<uint32_t>(bit - 24) ^ (7 - (wr.oct & 7));
             fetch = ngroup.x + popc(ngroup.y & 0xFFu & ((1u << k) - 1u));
             return false;
         }

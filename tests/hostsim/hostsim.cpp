@@ -106,6 +106,7 @@ void* hostsim_scene_create(const asgpu_scene_desc* desc, uint32_t flags, int thr
     s->view.top_wnodes = h.top_wnodes; s->view.top_witems = h.top_witems;
     s->view.tree_count = h.tree_count; s->view.item_count = h.item_count;
     s->view.top_node_count = h.top_node_count; s->view.top_wnode_count = h.top_wnode_count;
+    s->view.wide_stack_need = h.wide_stack_need;
     return s;
 }
 
