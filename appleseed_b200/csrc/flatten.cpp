@@ -21,6 +21,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 
@@ -273,38 +274,11 @@ struct WideOut
 
 struct Element
 {
-    bool        is_node;        // binary interior node, else an item range
-    uint32_t    node;           // binary node index (is_node)
+    bool        is_node;        // subtree that becomes a wide node of its own, else an item range (leaf child)
+    uint32_t    node;           // node of the augmented binary tree (is_node)
     uint32_t    first, count;   // item range (!is_node)
     FBox        box;
 };
-
-void make_element(const BinaryView& bv, const uint32_t node, Element& e)
-{
-    e.box = bv.box[node];
-    if (bv.child[node] != InteriorMark) { e.is_node = true; e.node = node; e.first = e.count = 0; }
-    else { e.is_node = false; e.node = 0; e.first = bv.first[node]; e.count = bv.count[node]; }
-}
-
-bool splittable(const Element& e, const uint32_t leaf_cap) { return e.is_node || e.count > leaf_cap; }
-
-void split_element(const BinaryView& bv, const Element& e, Element& a, Element& b)
-{
-    if (e.is_node)
-    {
-        make_element(bv, bv.child[e.node], a);
-        make_element(bv, bv.child[e.node] + 1, b);
-    }
-    else
-    {
-        // An over-full leaf (max_leaf_size > cap, or a range the SAH refused to split) is halved;
-        // both halves keep the leaf's box.
-        a = e; b = e;
-        a.count = e.count / 2;
-        b.first = e.first + a.count;
-        b.count = e.count - a.count;
-    }
-}
 
 int quantise_node(WNode& w, const Element* kids, const int n, const int* slot_of, std::string& error)
 {
@@ -324,7 +298,8 @@ int quantise_node(WNode& w, const Element* kids, const int n, const int* slot_of
             while (e > -126 && std::ceil(extent / std::ldexp(1.0, e - 1)) <= 255.0) --e;
         }
         if (e < -126) e = -126;
-        if (e > 127) { error = "scene extent too large to quantise"; return ASGPU_E_UNSUPPORTED; }
+        // The kernels form 2^(e + 15) by adding to the exponent field.
+        if (e > 127 - 16) { error = "scene extent too large to quantise"; return ASGPU_E_UNSUPPORTED; }
         w.exp[a] = static_cast<uint8_t>(e + 127);
         const double scale = std::ldexp(1.0, e);
         for (int i = 0; i < n; ++i)
@@ -345,117 +320,234 @@ int quantise_node(WNode& w, const Element* kids, const int n, const int* slot_of
     return ASGPU_OK;
 }
 
-int collapse(const BinaryView& bv, const uint32_t leaf_cap, WideOut& out, std::string& error)
+// Relative costs of the collapse's surface-area heuristic: testing one wide node / one leaf item.
+// The defaults are the measured optimum for the wide kernels (profiles/README.md); the
+// environment variable ASGPU_COLLAPSE_ITEM_COST overrides the item cost for experiments.
+struct CollapseCosts { double node, item; };
+
+CollapseCosts collapse_costs()
+{
+    CollapseCosts c = { 1.0, 1.0 };
+    if (const char* e = std::getenv("ASGPU_COLLAPSE_ITEM_COST")) { const double v = std::atof(e); if (v > 0.0) c.item = v; }
+    return c;
+}
+
+// Collapses a binary tree into 8-wide nodes.  Which binary subtrees become wide nodes, which
+// become leaf children (up to leaf_cap items) and how the 8 child slots of a wide node are spent
+// is decided by the dynamic programme of Ylitie, Karras, Laine 2017 (section 4.1) minimising the
+// expected SAH cost: C(n, i) = cheapest way to cover subtree n with at most i children of one
+// wide node.  Every wide child box is the box of a binary subtree, so it contains all the binary
+// boxes below it.
+int collapse(const BinaryView& bv, const uint32_t leaf_cap, const CollapseCosts costs, WideOut& out, std::string& error)
 {
     out.nodes.clear();
     out.leaf_order.clear();
+    out.depth = 0;
 
-    struct Pending { uint32_t wide_index; uint32_t depth; Element root; };
+    // ---- augmented binary tree: leaves larger than leaf_cap are halved into virtual nodes --------
+    const uint32_t Leaf = InteriorMark;
+    std::vector<uint32_t> lc(bv.child.begin(), bv.child.end());     // left child (right = left + 1 for real nodes)
+    std::vector<uint32_t> rc(bv.node_count);
+    std::vector<uint32_t> first(bv.first.begin(), bv.first.end()), count(bv.count.begin(), bv.count.end());
+    std::vector<FBox> box(bv.box.begin(), bv.box.end());
+    for (uint64_t i = 0; i < bv.node_count; ++i) rc[i] = lc[i] == Leaf ? Leaf : lc[i] + 1;
+    for (uint64_t i = 0; i < lc.size(); ++i)
+    {
+        if (lc[i] != Leaf || count[i] <= leaf_cap) continue;
+        // An over-full leaf (max_leaf_size > cap, or a range the SAH refused to split): both halves keep its box.
+        const uint32_t a = static_cast<uint32_t>(lc.size());
+        const uint32_t half = count[i] / 2;
+        lc.push_back(Leaf); rc.push_back(Leaf); first.push_back(first[i]); count.push_back(half); box.push_back(box[i]);
+        lc.push_back(Leaf); rc.push_back(Leaf); first.push_back(first[i] + half); count.push_back(count[i] - half); box.push_back(box[i]);
+        lc[i] = a; rc[i] = a + 1;
+    }
+    const uint64_t n = lc.size();
+    if (n >= 0x7FFFFFFFull) { error = "binary tree too large to collapse"; return ASGPU_E_UNSUPPORTED; }
+
+    // ---- bottom-up: item range of every subtree, cost tables --------------------------------------
+    // Children have larger indices than their parent (bvh_builder.h:197-205; virtual nodes are
+    // appended), so a descending sweep sees children first.
+    const double Inf = std::numeric_limits<double>::infinity();
+    std::vector<uint32_t> sub_first(n), sub_count(n);
+    std::vector<uint8_t> contiguous(n);
+    std::vector<float> cost(n * 8);         // cost[x * 8 + i], i = 1..7
+    std::vector<uint8_t> choice(n * 8);     // i = 1: 0 leaf child, 1 wide node;  i > 1: 0 = same as i - 1, else children given to the left subtree
+    std::vector<uint8_t> split8(n);         // children given to the left subtree when x becomes a wide node
+    auto area_of = [&](const uint64_t x) -> double
+    {
+        if (!box[x].valid()) return 0.0;
+        const double a = box[x].half_area();
+        return a < 1.0e30 ? a : 1.0e30;
+    };
+    for (uint64_t xi = n; xi-- > 0; )
+    {
+        const uint64_t x = xi;
+        float* cx = &cost[x * 8];
+        uint8_t* hx = &choice[x * 8];
+        const double area = area_of(x);
+        if (lc[x] == Leaf)
+        {
+            sub_first[x] = first[x]; sub_count[x] = count[x]; contiguous[x] = 1;
+            for (int i = 1; i < 8; ++i) { cx[i] = static_cast<float>(area * count[x] * costs.item); hx[i] = 0; }
+            continue;
+        }
+        const uint64_t l = lc[x], r = rc[x];
+        if (l <= x || r <= x || l >= n || r >= n) { error = "binary tree is not in parent-before-child order"; return ASGPU_E_INVALID; }
+        contiguous[x] = contiguous[l] && contiguous[r] && (sub_count[l] == 0 || sub_count[r] == 0 || sub_first[l] + sub_count[l] == sub_first[r]);
+        sub_first[x] = sub_count[l] ? sub_first[l] : sub_first[r];
+        sub_count[x] = sub_count[l] + sub_count[r];
+        const float* cl = &cost[l * 8];
+        const float* cr = &cost[r * 8];
+        double dist[9]; int dist_k[9];
+        for (int j = 2; j <= 8; ++j)
+        {
+            dist[j] = Inf; dist_k[j] = 1;
+            for (int k = 1; k < j; ++k)
+            {
+                if (k > 7 || j - k > 7) continue;
+                const double c = static_cast<double>(cl[k]) + static_cast<double>(cr[j - k]);
+                if (c < dist[j]) { dist[j] = c; dist_k[j] = k; }
+            }
+        }
+        const double c_leaf = (contiguous[x] && sub_count[x] <= leaf_cap) ? area * sub_count[x] * costs.item : Inf;
+        const double c_node = dist[8] + area * costs.node;
+        split8[x] = static_cast<uint8_t>(dist_k[8]);
+        if (c_leaf <= c_node) { cx[1] = static_cast<float>(c_leaf); hx[1] = 0; }
+        else { cx[1] = static_cast<float>(c_node); hx[1] = 1; }
+        for (int i = 2; i < 8; ++i)
+        {
+            if (dist[i] < cx[i - 1]) { cx[i] = static_cast<float>(dist[i]); hx[i] = static_cast<uint8_t>(dist_k[i]); }
+            else { cx[i] = cx[i - 1]; hx[i] = 0; }
+        }
+    }
+
+    // ---- top-down: emit wide nodes breadth first ---------------------------------------------------
+    struct Pending { uint32_t wide_index; uint32_t depth; uint32_t node; };
     std::vector<Pending> queue;
     {
         WNode blank; std::memset(&blank, 0, sizeof(blank));
         out.nodes.push_back(blank);
-        Pending p; p.wide_index = 0; p.depth = 1; make_element(bv, 0, p.root);
+        Pending p; p.wide_index = 0; p.depth = 1; p.node = 0;
         queue.push_back(p);
     }
+    struct Work { uint32_t node; int budget; };
+    std::vector<Work> work;
 
     for (size_t qi = 0; qi < queue.size(); ++qi)
     {
         const Pending cur = queue[qi];
         if (cur.depth > out.depth) out.depth = cur.depth;
         Element kids[8];
-        int n = 0;
+        int n_kids = 0;
+        bool overflow = false;
 
-        if (splittable(cur.root, leaf_cap))
+        auto emit_leaf = [&](const uint32_t x)
         {
-            split_element(bv, cur.root, kids[0], kids[1]);
-            n = 2;
-            while (n < 8)
+            Element e; e.is_node = false; e.node = 0; e.first = sub_first[x]; e.count = sub_count[x]; e.box = box[x];
+            if (n_kids < 8) kids[n_kids++] = e; else overflow = true;
+        };
+        auto emit_node = [&](const uint32_t x)
+        {
+            Element e; e.is_node = true; e.node = x; e.first = e.count = 0; e.box = box[x];
+            if (n_kids < 8) kids[n_kids++] = e; else overflow = true;
+        };
+
+        if (lc[cur.node] == Leaf) { if (count[cur.node] > 0) emit_leaf(cur.node); }    // the whole tree is one small leaf
+        else
+        {
+            work.clear();
+            const int k8 = split8[cur.node];
+            Work wr; wr.node = rc[cur.node]; wr.budget = 8 - k8; work.push_back(wr);
+            Work wl; wl.node = lc[cur.node]; wl.budget = k8; work.push_back(wl);
+            while (!work.empty())
             {
-                int best = -1; float best_area = -1.0f;
-                for (int i = 0; i < n; ++i)
-                    if (splittable(kids[i], leaf_cap))
-                    {
-                        const float area = kids[i].box.half_area();
-                        if (area > best_area) { best_area = area; best = i; }
-                    }
-                if (best < 0) break;
-                Element a, b;
-                split_element(bv, kids[best], a, b);
-                kids[best] = a;
-                kids[n++] = b;
+                Work wk = work.back(); work.pop_back();
+                const uint32_t x = wk.node;
+                int i = wk.budget > 7 ? 7 : wk.budget;
+                if (lc[x] == Leaf) { if (count[x] > 0) emit_leaf(x); continue; }
+                while (i > 1 && choice[x * 8 + i] == 0) --i;
+                if (i == 1)
+                {
+                    if (choice[x * 8 + 1] == 0) emit_leaf(x); else emit_node(x);
+                    continue;
+                }
+                const int k = choice[x * 8 + i];
+                Work b; b.node = rc[x]; b.budget = i - k; work.push_back(b);
+                Work a; a.node = lc[x]; a.budget = k; work.push_back(a);
             }
         }
-        else if (cur.root.count > 0) { kids[0] = cur.root; n = 1; }     // the whole tree is one small leaf
+        if (overflow) { error = "internal error: wide collapse produced more than 8 children"; return ASGPU_E_INVALID; }
+        const int n_children = n_kids;
 
         // Octant slot assignment: slot s should hold the child that comes first for rays whose
         // direction signs are those of octant s (bit a set = negative along axis a).
         FBox nb; nb.reset();
-        for (int i = 0; i < n; ++i) nb.grow(kids[i].box);
+        for (int i = 0; i < n_children; ++i) nb.grow(kids[i].box);
         int slot_of[8];
         bool slot_used[8] = { false, false, false, false, false, false, false, false };
         bool kid_done[8] = { false, false, false, false, false, false, false, false };
-        float cost[8][8];
-        for (int i = 0; i < n; ++i)
-            for (int s = 0; s < 8; ++s)
+        float slot_cost[8][8];
+        for (int i = 0; i < n_children; ++i)
+            for (int sl = 0; sl < 8; ++sl)
             {
                 float c = 0.0f;
                 for (int a = 0; a < 3; ++a)
                 {
                     const float centre = kids[i].box.valid() ? 0.5f * (kids[i].box.lo[a] + kids[i].box.hi[a]) - 0.5f * (nb.lo[a] + nb.hi[a]) : 0.0f;
-                    c += ((s >> a) & 1) ? -centre : centre;
+                    c += ((sl >> a) & 1) ? -centre : centre;
                 }
-                cost[i][s] = c;
+                slot_cost[i][sl] = c;
             }
-        for (int round = 0; round < n; ++round)
+        for (int round = 0; round < n_children; ++round)
         {
             int bi = -1, bs = -1; float bc = std::numeric_limits<float>::max();
-            for (int i = 0; i < n; ++i)
+            for (int i = 0; i < n_children; ++i)
             {
                 if (kid_done[i]) continue;
-                for (int s = 0; s < 8; ++s)
-                    if (!slot_used[s] && cost[i][s] < bc) { bc = cost[i][s]; bi = i; bs = s; }
+                for (int sl = 0; sl < 8; ++sl)
+                    if (!slot_used[sl] && slot_cost[i][sl] < bc) { bc = slot_cost[i][sl]; bi = i; bs = sl; }
             }
             if (bi < 0)         // all remaining costs are +max/NaN: take any free pair
             {
-                for (int i = 0; i < n && bi < 0; ++i) if (!kid_done[i]) bi = i;
-                for (int s = 0; s < 8 && bs < 0; ++s) if (!slot_used[s]) bs = s;
+                for (int i = 0; i < n_children && bi < 0; ++i) if (!kid_done[i]) bi = i;
+                for (int sl = 0; sl < 8 && bs < 0; ++sl) if (!slot_used[sl]) bs = sl;
             }
             slot_of[bi] = bs; slot_used[bs] = true; kid_done[bi] = true;
         }
 
         WNode w; std::memset(&w, 0, sizeof(w));
-        for (int a = 0; a < 3; ++a) for (int s = 0; s < 8; ++s) { w.qlo[a][s] = 255; w.qhi[a][s] = 0; }
-        const int rc = quantise_node(w, kids, n, slot_of, error);
-        if (rc != ASGPU_OK) return rc;
+        for (int a = 0; a < 3; ++a) for (int sl = 0; sl < 8; ++sl) { w.qlo[a][sl] = 255; w.qhi[a][sl] = 0; }
+        const int rc_q = quantise_node(w, kids, n_children, slot_of, error);
+        if (rc_q != ASGPU_OK) return rc_q;
 
         // Internal children are allocated contiguously in slot order; leaves append their items
         // to the wide item order in slot order.
         int kid_in_slot[8];
-        for (int s = 0; s < 8; ++s) kid_in_slot[s] = -1;
-        for (int i = 0; i < n; ++i) kid_in_slot[slot_of[i]] = i;
+        for (int sl = 0; sl < 8; ++sl) kid_in_slot[sl] = -1;
+        for (int i = 0; i < n_children; ++i) kid_in_slot[slot_of[i]] = i;
 
         w.child_base = static_cast<uint32_t>(out.nodes.size());
         w.tri_base = static_cast<uint32_t>(out.leaf_order.size());
         uint32_t leaf_offset = 0;
-        for (int s = 0; s < 8; ++s)
+        for (int sl = 0; sl < 8; ++sl)
         {
-            const int i = kid_in_slot[s];
+            const int i = kid_in_slot[sl];
             if (i < 0) continue;
-            if (splittable(kids[i], leaf_cap))
+            if (kids[i].is_node)
             {
-                w.imask |= uint8_t(1u << s);
-                w.meta[s] = uint8_t(0x20 | (24 + s));
+                w.imask |= uint8_t(1u << sl);
+                w.meta[sl] = uint8_t(0x20 | (24 + sl));
                 WNode blank; std::memset(&blank, 0, sizeof(blank));
-                Pending p; p.wide_index = static_cast<uint32_t>(out.nodes.size()); p.depth = cur.depth + 1; p.root = kids[i];
+                Pending p; p.wide_index = static_cast<uint32_t>(out.nodes.size()); p.depth = cur.depth + 1; p.node = kids[i].node;
                 out.nodes.push_back(blank);
                 queue.push_back(p);
             }
             else
             {
-                if (kids[i].count == 0) { w.meta[s] = 0; continue; }
+                if (kids[i].count == 0) { w.meta[sl] = 0; continue; }
+                if (kids[i].count > 3 || leaf_offset + kids[i].count > 24) { error = "internal error: wide leaf does not fit its node"; return ASGPU_E_INVALID; }
                 const uint32_t unary = (1u << kids[i].count) - 1;       // 1 -> 001, 2 -> 011, 3 -> 111
-                w.meta[s] = uint8_t((unary << 5) | leaf_offset);
+                w.meta[sl] = uint8_t((unary << 5) | leaf_offset);
                 for (uint32_t k = 0; k < kids[i].count; ++k) out.leaf_order.push_back(kids[i].first + k);
                 leaf_offset += kids[i].count;
             }
@@ -565,8 +657,9 @@ int assembly_tree_boxes(const asgpu_assembly_tree_view& top, BinaryView& bv, std
     }
     else
     {
-        // A single-leaf assembly tree carries no box at all: use an unbounded one.
-        for (int a = 0; a < 3; ++a) { bv.box[0].lo[a] = -std::numeric_limits<float>::max(); bv.box[0].hi[a] = std::numeric_limits<float>::max(); }
+        // A single-leaf assembly tree carries no box at all: use one that is unbounded for every
+        // scene the quantiser accepts (extents beyond ~6e35 are rejected as unsupported anyway).
+        for (int a = 0; a < 3; ++a) { bv.box[0].lo[a] = -1.0e30f; bv.box[0].hi[a] = 1.0e30f; }
     }
     for (uint64_t i = 0; i < n; ++i)
     {
@@ -656,7 +749,7 @@ int flatten_scene(
             BinaryView bv;
             triangle_tree_boxes(trees[ti], et, bv);
             WideOut wo;
-            rc = collapse(bv, 3, wo, error);
+            rc = collapse(bv, 3, collapse_costs(), wo, error);
             if (rc != ASGPU_OK) return rc;
             if (wo.leaf_order.size() != et.tris.size()) { error = "internal error: wide collapse lost triangles"; return ASGPU_E_INVALID; }
             max_bottom_depth = std::max(max_bottom_depth, wo.depth);
@@ -706,7 +799,7 @@ int flatten_scene(
         int rc = assembly_tree_boxes(top, bv, error);
         if (rc != ASGPU_OK) return rc;
         WideOut wo;
-        rc = collapse(bv, 1, wo, error);
+        rc = collapse(bv, 1, collapse_costs(), wo, error);
         if (rc != ASGPU_OK) return rc;
         if (wo.leaf_order.size() != top.item_count) { error = "internal error: wide collapse lost instances"; return ASGPU_E_INVALID; }
         header.top_wnodes = writer.append(wo.nodes);

@@ -49,6 +49,7 @@ struct KernelArgs
     int                 refill_threshold;   // idle lanes that trigger a pull from the ray queue
     int                 flush_threshold;    // queued candidates that trigger a test batch
     int                 stall_threshold;    // lanes idle or waiting for the queue that trigger one
+    uint32_t            unit_bits;          // bits of 1.0f (see byte_to_unit)
 };
 
 __device__ __forceinline__ void store_hit(asgpu_hit* out, const SceneView& s, const double t, const Hit& hit, const bool found)
@@ -393,7 +394,7 @@ wide_kernel(const KernelArgs args)
                 if (COUNT) { if (cur_item != None) ++stats.nodes; else ++stats.top_nodes; }
                 if (ngroup.y & 0xFF000000u) { stack[sp * stride] = ngroup; ++sp; }
                 uint32_t child_base, tri_base, nmask, tmask;
-                wide_node_test(wnodes + static_cast<uint64_t>(fetch) * sizeof(WNode), w, child_base, tri_base, nmask, tmask);
+                wide_node_test(wnodes + static_cast<uint64_t>(fetch) * sizeof(WNode), w, args.unit_bits, child_base, tri_base, nmask, tmask);
                 ngroup.x = child_base; ngroup.y = nmask;
                 if (cur_item != None) { pending = tmask; tri_first = tri_base; }
                 else { tgroup.x = tri_base; tgroup.y = tmask; }
@@ -550,6 +551,7 @@ int launch_trace(
     args.queue = queue;
     args.counters = counters;
     args.order = order;
+    args.unit_bits = UnitBits;
     const Tuning knobs = tuning();
     args.refill_threshold = knobs.refill;
     args.flush_threshold = knobs.flush;

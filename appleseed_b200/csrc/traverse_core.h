@@ -646,13 +646,19 @@ ASGPU_HD void shrink_wide_ray(const Ray& r, WideRay& w)
     w.tmax_f = d2f_up(dsub(r.tmax, w.shift));
 }
 
-ASGPU_HD float byte_to_float(const uint32_t word, const int k)
+// Byte k of `word` as the float 1 + byte * 2^-15: the byte dropped into the mantissa of 1.0f by
+// ONE byte permute (no integer-to-float conversion, no subtraction).  The box test works with
+// plane coefficients pre-scaled by 2^15 and offsets pre-reduced by them, see wide_node_test_form.
+// `one` holds the bits of 1.0f; the kernels pass it through a kernel argument so that it stays in
+// a register and the permute selector is the instruction's immediate.
+const uint32_t UnitBits = 0x3F800000u;
+
+ASGPU_HD float byte_to_unit(const uint32_t word, const int k, const uint32_t one)
 {
 #if ASGPU_DEVICE_CODE
-    // 0x4B0000bb - 2^23 == bb exactly.
-    return __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7650 + k)) - 8388608.0f;
+    return __uint_as_float(__byte_perm(word, one, 0x7604 | (k << 4)));
 #else
-    return static_cast<float>((word >> (8 * k)) & 0xFF);
+    return bits_to_float(one | (((word >> (8 * k)) & 0xFFu) << 8));
 #endif
 }
 
@@ -670,8 +676,13 @@ ASGPU_HD float byte_to_float(const uint32_t word, const int k)
 // reference's fp64 slab test on the tighter binary box would enter.  The expanded form produces
 // NaNs (= "no constraint", conservative but useless) when a reciprocal is infinite, so rays with
 // an exactly zero direction component (oct bit 3) take the other form.
+//
+// The quantised byte q enters the FMA as m = 1 + q * 2^-15 (byte_to_unit): with S = s * 2^15
+// (exact, a power of two), q * s + a = m * S + (a - S), so the offset is reduced by S once per
+// node and axis (rounded outward; S is only 2^15 grid steps, so this costs 2^-8 of a grid step of
+// tightness) and no per-plane conversion remains.
 template <bool EXPANDED>
-ASGPU_HD void wide_node_test_form(const uint8_t* np, const WideRay& w, uint32_t& child_base, uint32_t& tri_base, uint32_t& nmask, uint32_t& tmask)
+ASGPU_HD void wide_node_test_form(const uint8_t* np, const WideRay& w, const uint32_t one, uint32_t& child_base, uint32_t& tri_base, uint32_t& nmask, uint32_t& tmask)
 {
     const uint4 n0 = load16(np), n1 = load16(np + 16), n2 = load16(np + 32), n3 = load16(np + 48), n4 = load16(np + 64);
     child_base = n1.x;
@@ -683,7 +694,7 @@ ASGPU_HD void wide_node_test_form(const uint8_t* np, const WideRay& w, uint32_t&
     const uint32_t qhi[3][2] = { { n3.z, n3.w }, { n4.x, n4.y }, { n4.z, n4.w } };
     const float origin[3] = { u2f(n0.x), u2f(n0.y), u2f(n0.z) };
 
-    float cn[3], cf[3], bn[3], bf[3];       // EXPANDED: plane coefficients; else s, s, a_lo, a_hi
+    float cn[3], cf[3], bn[3], bf[3];       // coefficients and offsets of the near / far plane FMAs
     uint32_t qn[3][2], qf[3][2];
 #if ASGPU_DEVICE_CODE
     #pragma unroll
@@ -691,17 +702,18 @@ ASGPU_HD void wide_node_test_form(const uint8_t* np, const WideRay& w, uint32_t&
     for (int a = 0; a < 3; ++a)
     {
         const bool neg = (w.oct >> a) & 1;
-        const float scale = u2f(((n0.w >> (8 * a)) & 0xFF) << 23);
+        // S = 2^(e + 15); the flattener keeps e + 15 below the exponent range.
+        const float scale15 = u2f((((n0.w >> (8 * a)) & 0xFF) + 15u) << 23);
         const float p = neg ? -origin[a] : origin[a];       // node origin in the mirrored frame
-        const float s = neg ? -scale : scale;
+        const float s15 = neg ? -scale15 : scale15;
         const float a_lo = fsub_dn(p, w.o_hi[a]);
         const float a_hi = fsub_up(p, w.o_lo[a]);
         if (EXPANDED)
         {
-            cn[a] = fmul_dn(s, w.rn[a]); bn[a] = fmul_dn(a_lo, w.rn[a]);
-            cf[a] = fmul_up(s, w.rf[a]); bf[a] = fmul_up(a_hi, w.rf[a]);
+            cn[a] = fmul_dn(s15, w.rn[a]); bn[a] = fma_dn(a_lo, w.rn[a], -cn[a]);
+            cf[a] = fmul_up(s15, w.rf[a]); bf[a] = fma_up(a_hi, w.rf[a], -cf[a]);
         }
-        else { cn[a] = s; cf[a] = s; bn[a] = a_lo; bf[a] = a_hi; }
+        else { cn[a] = s15; cf[a] = s15; bn[a] = fsub_dn(a_lo, s15); bf[a] = fsub_up(a_hi, s15); }
         qn[a][0] = neg ? qhi[a][0] : qlo[a][0]; qn[a][1] = neg ? qhi[a][1] : qlo[a][1];
         qf[a][0] = neg ? qlo[a][0] : qhi[a][0]; qf[a][1] = neg ? qlo[a][1] : qhi[a][1];
     }
@@ -718,17 +730,17 @@ ASGPU_HD void wide_node_test_form(const uint8_t* np, const WideRay& w, uint32_t&
 #endif
         for (int a = 0; a < 3; ++a)
         {
-            const float fn = byte_to_float(qn[a][k >> 2], k & 3);
-            const float ff = byte_to_float(qf[a][k >> 2], k & 3);
+            const float mn = byte_to_unit(qn[a][k >> 2], k & 3, one);
+            const float mf = byte_to_unit(qf[a][k >> 2], k & 3, one);
             if (EXPANDED)
             {
-                tn = fmax_nan(tn, fma_dn(fn, cn[a], bn[a]));
-                tf = fmin_nan(tf, fma_up(ff, cf[a], bf[a]));
+                tn = fmax_nan(tn, fma_dn(mn, cn[a], bn[a]));
+                tf = fmin_nan(tf, fma_up(mf, cf[a], bf[a]));
             }
             else
             {
-                tn = fmax_nan(tn, fmul_dn(fma_dn(fn, cn[a], bn[a]), w.rn[a]));
-                tf = fmin_nan(tf, fmul_up(fma_up(ff, cf[a], bf[a]), w.rf[a]));
+                tn = fmax_nan(tn, fmul_dn(fma_dn(mn, cn[a], bn[a]), w.rn[a]));
+                tf = fmin_nan(tf, fmul_up(fma_up(mf, cf[a], bf[a]), w.rf[a]));
             }
         }
         // meta: 0 = empty; internal child 0x20 | (24 + k); leaf (unary count << 5) | first slot.
@@ -747,10 +759,10 @@ ASGPU_HD void wide_node_test_form(const uint8_t* np, const WideRay& w, uint32_t&
     tmask = hitmask & 0x00FFFFFFu;
 }
 
-ASGPU_HD void wide_node_test(const uint8_t* np, const WideRay& w, uint32_t& child_base, uint32_t& tri_base, uint32_t& nmask, uint32_t& tmask)
+ASGPU_HD void wide_node_test(const uint8_t* np, const WideRay& w, const uint32_t one, uint32_t& child_base, uint32_t& tri_base, uint32_t& nmask, uint32_t& tmask)
 {
-    if (w.oct & 8) wide_node_test_form<false>(np, w, child_base, tri_base, nmask, tmask);
-    else wide_node_test_form<true>(np, w, child_base, tri_base, nmask, tmask);
+    if (w.oct & 8) wide_node_test_form<false>(np, w, one, child_base, tri_base, nmask, tmask);
+    else wide_node_test_form<true>(np, w, one, child_base, tri_base, nmask, tmask);
 }
 
 const uint32_t WideStackSize = WideStackMax;       // host driver; the kernels pick a depth per scene
@@ -818,7 +830,7 @@ struct WideTraversal
             if (COUNT) { if (in_instance) ++stats.nodes; else ++stats.top_nodes; }
             if (ngroup.y & 0xFF000000u) { stack[sp * stride] = ngroup; ++sp; }
             uint32_t child_base, tri_base, nmask, tmask;
-            wide_node_test(wnodes + static_cast<uint64_t>(fetch) * sizeof(WNode), wr, child_base, tri_base, nmask, tmask);
+            wide_node_test(wnodes + static_cast<uint64_t>(fetch) * sizeof(WNode), wr, UnitBits, child_base, tri_base, nmask, tmask);
             ngroup.x = child_base; ngroup.y = nmask;
             tgroup.x = tri_base; tgroup.y = tmask;
             fetch = 0xFFFFFFFFu;
