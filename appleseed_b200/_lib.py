@@ -57,7 +57,7 @@ class SceneInfo(C.Structure):
         ("blob_bytes", C.c_uint64), ("triangle_tree_count", C.c_uint64), ("instance_count", C.c_uint64),
         ("triangle_count", C.c_uint64), ("moving_triangle_count", C.c_uint64), ("binary_node_count", C.c_uint64),
         ("wide_node_count", C.c_uint64), ("binary_node_bytes", C.c_uint64), ("wide_node_bytes", C.c_uint64),
-        ("triangle_bytes", C.c_uint64), ("flags", C.c_uint32), ("reserved", C.c_uint32),
+        ("triangle_bytes", C.c_uint64), ("flags", C.c_uint32), ("wide_stack_depth", C.c_uint32),
     ]
 
     def as_dict(self):

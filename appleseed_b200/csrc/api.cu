@@ -407,7 +407,7 @@ int asgpu_scene_get_info(const asgpu_scene* scene, asgpu_scene_info* out)
     out->wide_node_bytes = h.wide_node_bytes;
     out->triangle_bytes = h.triangle_bytes;
     out->flags = h.flags;
-    out->reserved = 0;
+    out->wide_stack_depth = h.wide_stack_need;
     return ASGPU_OK;
 }
 

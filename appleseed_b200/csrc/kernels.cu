@@ -138,7 +138,7 @@ trace_kernel(const KernelArgs args)
 
 // Lanes of a warp whose ray has finished are refilled from the queue as soon as at least
 // RefillThreshold of them are idle (or all are), so one long ray does not hold 31 lanes hostage.
-const int QueueSlots = 64;          // per warp: < 32 left over + at most 32 pushed per round
+const int QueueSlots = 128;         // per warp: < 32 left over + one step's candidates (more are pushed in rounds)
 const uint32_t None = 0xFFFFFFFFu;
 
 // Shared memory of one CTA, every per-thread array laid out [component][thread].
@@ -165,8 +165,8 @@ __device__ __forceinline__ unsigned long long ordered_key(const double t)
     return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
 }
 
-// Tests `count` (<= 32) queued candidates, one per lane.  Entry = (blob offset of the triangle
-// record / 16) << 5 | source lane.  Closest hit: the nearest accepted candidate of each source lane
+// Tests `count` (<= 32) queued candidates, one per lane.  Entry = (index of the triangle record in
+// the source lane's current tree) << 5 | source lane.  Closest hit: the nearest accepted candidate of each source lane
 // updates that lane's tmax and hit record (ties: lowest queue position).  Any hit: marks the lane.
 template <bool ANY, bool COUNT, int STACK>
 __device__ __forceinline__ void test_candidates(
@@ -192,7 +192,7 @@ __device__ __forceinline__ void test_candidates(
         ray.time_absolute = 0.0f;
         if (COUNT) ++stats.triangles;
         TriD tri;
-        if (fetch_triangle<ANY>(blob + ((e >> 5) << 4), blob + sm.pose_base[st], ray, tri, slot, segment))
+        if (fetch_triangle<ANY>(blob + sm.tri_base[st] + (e >> 5) * sizeof(TriRecord), blob + sm.pose_base[st], ray, tri, slot, segment))
             hit = mt_test<!ANY>(tri, ray, t, u, v);
     }
     if (ANY)
@@ -225,8 +225,8 @@ __device__ __forceinline__ void test_candidates(
     __syncwarp();
 }
 
-template <bool ANY, bool COUNT, int STACK>
-__global__ void __launch_bounds__(BlockThreads)
+template <bool ANY, bool COUNT, int STACK, int MINB>
+__global__ void __launch_bounds__(BlockThreads, MINB)
 wide_kernel(const KernelArgs args)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -404,30 +404,62 @@ wide_kernel(const KernelArgs args)
 
         // ---- gather this step's triangle candidates -------------------------------------------------
         bool tested = false;                            // warp-uniform: a batch ran in this iteration
-        unsigned pushers = __ballot_sync(0xFFFFFFFFu, pending != 0);
-        if (pushers != 0)
+        if (__ballot_sync(0xFFFFFFFFu, pending != 0) != 0)
         {
-            if (pending != 0) waiting = true;
-            __syncwarp();                               // the ray / tree data of new lanes is visible
-            do
+            // Exclusive prefix sum of the lanes' candidate counts = their places in the queue.
+            const unsigned mine = __popc(pending);
+            unsigned upto = mine;
+            #pragma unroll
+            for (int o = 1; o < 32; o <<= 1)
             {
-                if (pending != 0)
+                const unsigned v = __shfl_up_sync(0xFFFFFFFFu, upto, o);
+                if (lane >= o) upto += v;
+            }
+            const unsigned total = __shfl_sync(0xFFFFFFFFu, upto, 31);
+            if (mine != 0) waiting = true;
+            __syncwarp();                               // the ray / tree data of new lanes is visible
+            if (queued + total <= QueueSlots)
+            {
+                unsigned pos = queued + upto - mine;
+                const unsigned long long base = (static_cast<unsigned long long>(tri_first) << 5) | lane;
+                while (pending != 0)
                 {
                     const int bit = high_bit(pending);
                     pending &= ~(1u << bit);
-                    const unsigned long long off = sm.tri_base[tid] + static_cast<unsigned long long>(tri_first + bit) * sizeof(TriRecord);
-                    queue[queued + __popc(pushers & lanes_below)] = ((off >> 4) << 5) | lane;
+                    queue[pos++] = base + (static_cast<unsigned long long>(bit) << 5);
                 }
-                queued += __popc(pushers);
+                queued += total;
                 __syncwarp();
-                if (queued >= 32)
+                while (queued >= 32)
                 {
                     queued -= 32;
                     test_candidates<ANY, COUNT, STACK>(sm, blob, queue + queued, 32, lane, warp_thread0, stats);
                     tested = true;
                 }
-                pushers = __ballot_sync(0xFFFFFFFFu, pending != 0);
-            } while (pushers != 0);
+            }
+            else
+            {
+                // More candidates than the queue holds (rare): one per lane and round.
+                unsigned pushers = __ballot_sync(0xFFFFFFFFu, pending != 0);
+                do
+                {
+                    if (pending != 0)
+                    {
+                        const int bit = high_bit(pending);
+                        pending &= ~(1u << bit);
+                        queue[queued + __popc(pushers & lanes_below)] = (static_cast<unsigned long long>(tri_first + bit) << 5) | lane;
+                    }
+                    queued += __popc(pushers);
+                    __syncwarp();
+                    if (queued >= 32)
+                    {
+                        queued -= 32;
+                        test_candidates<ANY, COUNT, STACK>(sm, blob, queue + queued, 32, lane, warp_thread0, stats);
+                        tested = true;
+                    }
+                    pushers = __ballot_sync(0xFFFFFFFFu, pending != 0);
+                } while (pushers != 0);
+            }
         }
 
         // ---- flush the queue when it is full enough or too many lanes wait for it -------------------
@@ -515,14 +547,18 @@ cudaError_t launch_persistent(Kernel kernel, const KernelArgs& args, const size_
     return cudaGetLastError();
 }
 
+// 5 resident CTAs per SM (<= 102 registers): the measured optimum; 6 CTAs at 80 registers spill
+// and run ~10 % slower (profiles/README.md).
+const int WideMinBlocks = 5;
+
 template <int STACK>
 cudaError_t launch_wide(const KernelArgs& args, const bool any_hit, const bool count, const int sm_count, cudaStream_t stream)
 {
     const size_t smem = sizeof(WideShared<STACK>);
-    if (any_hit) return count ? launch_persistent(wide_kernel<true, true, STACK>, args, smem, sm_count, stream)
-                              : launch_persistent(wide_kernel<true, false, STACK>, args, smem, sm_count, stream);
-    return count ? launch_persistent(wide_kernel<false, true, STACK>, args, smem, sm_count, stream)
-                 : launch_persistent(wide_kernel<false, false, STACK>, args, smem, sm_count, stream);
+    if (any_hit) return count ? launch_persistent(wide_kernel<true, true, STACK, WideMinBlocks>, args, smem, sm_count, stream)
+                              : launch_persistent(wide_kernel<true, false, STACK, WideMinBlocks>, args, smem, sm_count, stream);
+    return count ? launch_persistent(wide_kernel<false, true, STACK, WideMinBlocks>, args, smem, sm_count, stream)
+                 : launch_persistent(wide_kernel<false, false, STACK, WideMinBlocks>, args, smem, sm_count, stream);
 }
 
 }   // anonymous namespace
@@ -565,7 +601,8 @@ int launch_trace(
     {
         // The traversal stack lives in shared memory; its depth is the scene's (flatten.cpp
         // computes the bound), rounded up to one of the compiled variants.
-        if (scene.wide_stack_need <= 24) err = launch_wide<24>(args, any_hit, count, sm_count, stream);
+        if (scene.wide_stack_need <= 16) err = launch_wide<16>(args, any_hit, count, sm_count, stream);
+        else if (scene.wide_stack_need <= 24) err = launch_wide<24>(args, any_hit, count, sm_count, stream);
         else if (scene.wide_stack_need <= 40) err = launch_wide<40>(args, any_hit, count, sm_count, stream);
         else err = launch_wide<WideStackMax>(args, any_hit, count, sm_count, stream);
     }

@@ -94,31 +94,87 @@ def incoherent_rays(desc, n: int, seed: int, time: bool = False) -> RayBatch:
 # ---------------------------------------------------------------------------------------------
 
 class ClockSampler:
+    """Samples SM clock, power and throttle reasons of one GPU DURING the timed region: NVML polled
+    from a thread every few milliseconds (nvidia-smi -lms as a fallback)."""
     QUERY = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
-    def __init__(self, index: int):
+    def __init__(self, index: int, period_s: float = 0.004):
         self.index = index
+        self.period = period_s
+        self.samples = []           # (sm_mhz, power_w, reasons bitmask)
+        self.max_mhz = None
+        self.stop_flag = threading.Event()
+        self.thread = None
         self.proc = None
         self.lines = []
+        self.nvml = None
 
     def start(self):
         try:
+            import pynvml
+            pynvml.nvmlInit()
+            # CUDA_VISIBLE_DEVICES may renumber devices: resolve through the PCI bus id of the CUDA device.
+            import torch
+            bus = getattr(torch.cuda.get_device_properties(self.index), "pci_bus_id", None)
+            handle = None
+            if bus is not None:
+                for i in range(pynvml.nvmlDeviceGetCount()):
+                    h = pynvml.nvmlDeviceGetHandleByIndex(i)
+                    if pynvml.nvmlDeviceGetPciInfo(h).bus == bus:
+                        handle = h
+                        break
+            if handle is None:
+                handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.nvml, self.handle = pynvml, handle
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(handle, pynvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        while not self.stop_flag.is_set():
+            try:
+                mhz = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+                reasons = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                try:
+                    power = n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+                except Exception:
+                    power = None
+                self.samples.append((float(mhz), power, int(reasons)))
+            except Exception:
+                pass
+            time.sleep(self.period)
+
     def _read(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
     def stop(self) -> dict:
+        if self.nvml is not None:
+            self.stop_flag.set()
+            self.thread.join(timeout=1.0)
+            n = self.nvml
+            names = [("hw_slowdown", n.nvmlClocksThrottleReasonHwSlowdown), ("hw_thermal_slowdown", n.nvmlClocksThrottleReasonHwThermalSlowdown),
+                     ("sw_thermal_slowdown", n.nvmlClocksThrottleReasonSwThermalSlowdown), ("sw_power_cap", n.nvmlClocksThrottleReasonSwPowerCap)]
+            reasons = sorted({name for _, _, r in self.samples for name, bit in names if r & bit})
+            sm = [x[0] for x in self.samples]
+            pw = [x[1] for x in self.samples if x[1] is not None]
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz, "samples": len(sm),
+                    "power_w_max": max(pw) if pw else None, "reasons": reasons, "source": "nvml"}
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml and nvidia-smi unavailable"]}
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -138,7 +194,7 @@ class ClockSampler:
                 if p[3 + k].lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi"}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -432,13 +488,21 @@ def run_gpu(args):
         else:
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         achieved = bytes_per_ray * rays_per_step / (ms_step * 1e-3) / 1e9      # per GPU
+        # DRAM traffic per launch: measured bytes per ray of the committed ncu capture of this
+        # workload's launches (profiles/traffic.json, written by tools/ncu_traffic.py) x this run's
+        # rays per launch, averaged over the step's launches; null when no capture is committed.
         traffic = None
+        traffic_src = None
         prof = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(prof):
             try:
-                traffic = json.load(open(prof)).get(args.workload)
+                entry = json.load(open(prof)).get(args.workload)
+                per_launch = [entry["launches"][label]["dram_bytes_per_ray"] * b.n for label, b in batches]
+                traffic = sum(per_launch) / len(per_launch)
+                traffic_src = "ncu --set full capture %s (dram__bytes_read+write per ray x rays per launch)" % entry["source"]
             except Exception:
                 traffic = None
+        algorithmic_per_launch = bytes_per_ray * rays_per_step / len(batches)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -447,7 +511,7 @@ def run_gpu(args):
                 "workload": workload_name(args), "rays_per_step_per_gpu": rays_per_step,
                 "batches": {label: {"rays": b.n, "ms": round(ms, 4), "mrays_s": round(b.n / ms / 1e3, 1)}
                             for (label, b), ms in zip(batches, per_batch_ms)},
-                "kernel": "wide (8-wide quantised BVH, fp32 interval box tests, exact fp64 triangle tests)",
+                "kernel": "wide_kernel (8-wide quantised BVH, fp32 interval box tests, warp-cooperative exact fp64 triangle tests)",
                 "l2": "inputs larger than L2 (%.0f MB of rays + %.0f MB scene blob per step vs 126 MB L2)" % (h2d / 1e6, info["blob_bytes"] / 1e6),
                 "scene": {k: info[k] for k in ("triangle_count", "instance_count", "wide_node_count", "binary_node_count", "blob_bytes")},
                 "scene_build_s": round(build_s, 2), "flatten_upload_s": round(flatten_s, 2), "broadcast_s": round(bcast_s, 4),
@@ -457,8 +521,11 @@ def run_gpu(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "bytes_per_ray": round(bytes_per_ray, 1), "peak_source": peak_src,
-                         "kernel": "trace_kernel<closest, wide>"},
+                         "algorithmic_bytes_per_launch": algorithmic_per_launch, "bytes_per_ray": round(bytes_per_ray, 1),
+                         "peak_source": peak_src, "traffic_source": traffic_src,
+                         "kernel": "wide_kernel<closest>",
+                         "note": "algorithmic bytes are mostly served by L1/L2 (scene smaller than or comparable to the 126 MB L2): "
+                                 "the kernel is instruction-issue bound, see profiles/README.md"},
             "clocks": clocks,
         }
         if probe_batch is not None:

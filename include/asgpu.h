@@ -205,7 +205,7 @@ typedef struct asgpu_scene_info {
     uint64_t        wide_node_bytes;
     uint64_t        triangle_bytes;             /* per-slot records + pose data */
     uint32_t        flags;
-    uint32_t        reserved;
+    uint32_t        wide_stack_depth;           /* traversal stack entries the wide layout can need */
 } asgpu_scene_info;
 
 int             asgpu_scene_get_info(const asgpu_scene* scene, asgpu_scene_info* out);

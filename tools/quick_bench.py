@@ -39,6 +39,8 @@ def main():
         desc = bench.make_scene(a)
         ctx = TraceContext(desc, device=0)
         isect = Intersector(ctx)
+        info = ctx.info()
+        print(json.dumps({"workload": wl, "wide_nodes": info["wide_node_count"], "wide_stack_depth": info["wide_stack_depth"], "blob_MB": round(info["blob_bytes"] / 1e6, 1)}), flush=True)
         n = args.rays
         waves = []
         if wl == "c2":
