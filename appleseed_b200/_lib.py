@@ -23,6 +23,11 @@ EXPORTS = [
     "asgpu_scene_get_info",
     "asgpu_trace", "asgpu_trace_probe", "asgpu_trace_host", "asgpu_trace_probe_host",
     "asgpu_get_counters", "asgpu_last_error", "asgpu_version",
+    "asgpu_queue_create", "asgpu_queue_destroy", "asgpu_queue_capacity", "asgpu_queue_device_arrays",
+    "asgpu_queue_reset", "asgpu_queue_count", "asgpu_queue_push_host", "asgpu_trace_queue", "asgpu_trace_probe_queue",
+    "asgpu_path_stream_create", "asgpu_path_stream_destroy", "asgpu_path_stream_tile_count", "asgpu_path_stream_render",
+    "asgpu_path_stream_read_image", "asgpu_path_stream_clear", "asgpu_path_stream_get_stats",
+    "asgpu_path_stream_capture", "asgpu_path_stream_capture_count", "asgpu_path_stream_capture_get",
 ]
 
 SCENE_EXACT = 1 << 0
@@ -75,6 +80,27 @@ class Counters(C.Structure):
         return {k: int(getattr(self, k)) for k, _ in self._fields_ if k != "reserved"}
 
 
+class PathStreamDesc(C.Structure):
+    _fields_ = [
+        ("width", C.c_uint32), ("height", C.c_uint32), ("spp", C.c_uint32), ("max_bounces", C.c_uint32),
+        ("tile_size", C.c_uint32), ("light_count", C.c_uint32), ("trace_flags", C.c_uint32), ("reserved", C.c_uint32),
+        ("seed", C.c_uint64), ("camera_to_world", C.c_double * 12),
+        ("film_width", C.c_double), ("film_height", C.c_double), ("focal_length", C.c_double),
+        ("lights", (C.c_double * 3) * 8), ("offset_eps", C.c_double),
+    ]
+
+
+class PathStreamStats(C.Structure):
+    _fields_ = [
+        ("camera_rays", C.c_uint64), ("bounce_rays", C.c_uint64), ("probe_rays", C.c_uint64),
+        ("surface_hits", C.c_uint64), ("escaped", C.c_uint64), ("unoccluded", C.c_uint64),
+        ("wavefronts", C.c_uint64), ("kernel_launches", C.c_uint64),
+    ]
+
+    def as_dict(self):
+        return {k: int(getattr(self, k)) for k, _ in self._fields_}
+
+
 _lib = None
 
 
@@ -117,6 +143,30 @@ def load() -> C.CDLL:
     lib.asgpu_trace_host.argtypes = [C.c_void_p, P(CRays), C.c_size_t, C.c_void_p, C.c_uint32]
     lib.asgpu_trace_probe_host.argtypes = [C.c_void_p, P(CRays), C.c_size_t, C.c_void_p, C.c_uint32]
     lib.asgpu_get_counters.argtypes = [C.c_void_p, P(Counters), C.c_int]
+    lib.asgpu_queue_create.restype = C.c_void_p
+    lib.asgpu_queue_create.argtypes = [C.c_void_p, C.c_size_t]
+    lib.asgpu_queue_destroy.argtypes = [C.c_void_p]
+    lib.asgpu_queue_capacity.restype = C.c_size_t
+    lib.asgpu_queue_capacity.argtypes = [C.c_void_p]
+    lib.asgpu_queue_device_arrays.argtypes = [C.c_void_p, P(CRays), P(C.c_void_p), P(C.c_void_p)]
+    lib.asgpu_queue_reset.argtypes = [C.c_void_p, C.c_void_p]
+    lib.asgpu_queue_count.argtypes = [C.c_void_p, C.c_void_p, P(C.c_uint64)]
+    lib.asgpu_queue_push_host.argtypes = [C.c_void_p, P(CRays), C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.asgpu_trace_queue.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
+    lib.asgpu_trace_probe_queue.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
+    lib.asgpu_path_stream_create.restype = C.c_void_p
+    lib.asgpu_path_stream_create.argtypes = [C.c_void_p, P(PathStreamDesc), C.c_size_t]
+    lib.asgpu_path_stream_destroy.argtypes = [C.c_void_p]
+    lib.asgpu_path_stream_tile_count.restype = C.c_uint32
+    lib.asgpu_path_stream_tile_count.argtypes = [C.c_void_p]
+    lib.asgpu_path_stream_render.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.asgpu_path_stream_read_image.argtypes = [C.c_void_p, C.c_void_p]
+    lib.asgpu_path_stream_clear.argtypes = [C.c_void_p]
+    lib.asgpu_path_stream_get_stats.argtypes = [C.c_void_p, P(PathStreamStats)]
+    lib.asgpu_path_stream_capture.argtypes = [C.c_void_p, C.c_size_t]
+    lib.asgpu_path_stream_capture_count.argtypes = [C.c_void_p]
+    lib.asgpu_path_stream_capture_get.restype = C.c_longlong
+    lib.asgpu_path_stream_capture_get.argtypes = [C.c_void_p, C.c_int, P(C.c_int), P(C.c_uint32)] + [C.c_void_p] * 7
     _lib = lib
     return lib
 

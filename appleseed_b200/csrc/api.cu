@@ -9,6 +9,7 @@
 
 #include "../../include/asgpu.h"
 #include "flatten.h"
+#include "api_internal.h"
 #include "kernels.h"
 #include "tree_builder.h"
 
@@ -24,7 +25,7 @@
 
 using namespace asgpu;
 
-namespace
+namespace asgpu
 {
 
 thread_local std::string g_last_error;
@@ -41,50 +42,11 @@ int fail_cuda(const cudaError_t err, const char* what)
     return ASGPU_E_CUDA;
 }
 
-#define ASGPU_CUDA(call, what) do { const cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail_cuda(e_, what); } while (0)
-
-const size_t HostChunkRays = size_t(1) << 20;
-const int HostStreams = 3;
-const uint64_t QueueRing = 256;
-
-struct Staging
-{
-    cudaStream_t    stream = nullptr;
-    double*         org = nullptr;
-    double*         dir = nullptr;
-    double*         tmin = nullptr;
-    double*         tmax = nullptr;
-    float*          time_absolute = nullptr;
-    float*          time_normalized = nullptr;
-    uint32_t*       flags = nullptr;
-    asgpu_hit*      hits = nullptr;
-    uint8_t*        occluded = nullptr;
-    unsigned long long* queue = nullptr;
-};
-
-}   // anonymous namespace
+}   // namespace asgpu
 
 struct asgpu_trees
 {
     HostTrees trees;
-};
-
-struct asgpu_scene
-{
-    int                 device = 0;
-    int                 sm_count = 0;
-    uint8_t*            blob = nullptr;         // device
-    bool                owns_blob = true;
-    size_t              blob_bytes = 0;
-    BlobHeader          header;
-    SceneView           view;
-    unsigned long long* queue = nullptr;        // device, ring of QueueRing cursors (one per launch)
-    uint64_t            queue_next = 0;
-    unsigned long long* counters = nullptr;     // device, asgpu_counters layout (first 6 words)
-    uint64_t            launches = 0;
-    std::mutex          mutex;
-    Staging             staging[HostStreams];
-    bool                staging_ready = false;
 };
 
 namespace

@@ -46,13 +46,15 @@ struct KernelArgs
     unsigned long long* queue;          // ray queue cursor
     unsigned long long* counters;       // asgpu_counters layout, or nullptr
     const uint32_t*     order;          // optional permutation: ray processed at position i is order[i]
+    const unsigned long long* n_dev;    // optional: the ray count lives in device memory (wavefront queues)
+    uint32_t            raw_item;           // hit records carry the ItemRecord index instead of the caller's instance id
     int                 refill_threshold;   // idle lanes that trigger a pull from the ray queue
     int                 flush_threshold;    // queued candidates that trigger a test batch
     int                 stall_threshold;    // lanes idle or waiting for the queue that trigger one
     uint32_t            unit_bits;          // bits of 1.0f (see byte_to_unit)
 };
 
-__device__ __forceinline__ void store_hit(asgpu_hit* out, const SceneView& s, const double t, const Hit& hit, const bool found)
+__device__ __forceinline__ void store_hit(asgpu_hit* out, const SceneView& s, const double t, const Hit& hit, const bool found, const bool raw_item)
 {
     // 40-byte record written as five 8-byte stores.
     unsigned long long* dst = reinterpret_cast<unsigned long long*>(out);
@@ -62,7 +64,7 @@ __device__ __forceinline__ void store_hit(asgpu_hit* out, const SceneView& s, co
     {
         const uint8_t* ip = s.blob + s.items + static_cast<uint64_t>(hit.item) * sizeof(ItemRecord);
         const uint4 meta = load16(ip + 96);
-        assembly_instance = meta.z;
+        assembly_instance = raw_item ? hit.item : meta.z;
         // read_hit_triangle_data (triangletree.cpp:1483-1499): identity from the key of the hit slot.
         const uint8_t* tp = s.blob + s.trees + static_cast<uint64_t>(meta.x) * sizeof(TreeDesc);
         const uint2 keys_off = load8(tp + offsetof(TreeDesc, keys));
@@ -105,6 +107,7 @@ __global__ void __launch_bounds__(BlockThreads)
 trace_kernel(const KernelArgs args)
 {
     const unsigned lane = threadIdx.x & 31;
+    const unsigned long long n = args.n_dev ? *args.n_dev : args.n;
     Stats stats; stats.top_nodes = stats.instances = stats.nodes = stats.triangles = 0;
     unsigned rays_done = 0, hits_found = 0;
 
@@ -114,9 +117,9 @@ trace_kernel(const KernelArgs args)
         unsigned long long base = 0;
         if (lane == 0) base = atomicAdd(args.queue, 32ull);
         base = __shfl_sync(0xFFFFFFFFu, base, 0);
-        if (base >= args.n) break;
+        if (base >= n) break;
         const unsigned long long pos = base + lane;
-        if (pos < args.n)
+        if (pos < n)
         {
             const unsigned long long i = args.order ? args.order[pos] : pos;
             Ray ray;
@@ -124,7 +127,7 @@ trace_kernel(const KernelArgs args)
             Hit hit;
             const bool found = exact_trace<ANY, COUNT>(args.scene, ray, hit, stats);
             if (ANY) args.occluded[i] = found ? 1 : 0;
-            else store_hit(args.hits + i, args.scene, ray.tmax, hit, found);
+            else store_hit(args.hits + i, args.scene, ray.tmax, hit, found, args.raw_item != 0);
             if (COUNT) { ++rays_done; hits_found += found ? 1 : 0; }
         }
     }
@@ -239,6 +242,7 @@ wide_kernel(const KernelArgs args)
     unsigned long long* queue = sm.queue[tid >> 5];
     const SceneView& s = args.scene;
     const uint8_t* blob = s.blob;
+    const unsigned long long n = args.n_dev ? *args.n_dev : args.n;
     uint2* stack = &sm.stack[0][tid];
     const uint32_t stride = BlockThreads;
 
@@ -273,7 +277,7 @@ wide_kernel(const KernelArgs args)
             if (!active)
             {
                 const unsigned long long pos = base + __popc(idle & lanes_below);
-                if (pos < args.n)
+                if (pos < n)
                 {
                     index = args.order ? args.order[pos] : pos;
                     Ray ray;
@@ -295,7 +299,7 @@ wide_kernel(const KernelArgs args)
                     active = true; traversed = false; waiting = false;
                 }
             }
-            if (base + __popc(idle) >= args.n) exhausted = true;
+            if (base + __popc(idle) >= n) exhausted = true;
         }
         else if (idle == 0xFFFFFFFFu) break;            // nothing active and nothing left to fetch
         if (exhausted && __ballot_sync(0xFFFFFFFFu, active) == 0) break;
@@ -496,7 +500,7 @@ wide_kernel(const KernelArgs args)
                     Hit hit;
                     hit.u = sm.hit_u[tid]; hit.v = sm.hit_v[tid];
                     hit.item = sm.hit_item[tid]; hit.slot = sm.hit_slot[tid]; hit.segment = sm.hit_segment[tid];
-                    store_hit(args.hits + index, s, sm.ray[7][tid], hit, found);
+                    store_hit(args.hits + index, s, sm.ray[7][tid], hit, found, args.raw_item != 0);
                 }
                 if (COUNT) { ++rays_done; hits_found += found ? 1 : 0; }
                 active = false;
@@ -575,7 +579,9 @@ int launch_trace(
     unsigned long long* counters,
     const uint32_t*     order,
     const int           sm_count,
-    void*               stream_)
+    void*               stream_,
+    const unsigned long long* n_dev,
+    const bool          raw_item)
 {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     KernelArgs args;
@@ -587,6 +593,8 @@ int launch_trace(
     args.queue = queue;
     args.counters = counters;
     args.order = order;
+    args.n_dev = n_dev;
+    args.raw_item = raw_item ? 1u : 0u;
     args.unit_bits = UnitBits;
     const Tuning knobs = tuning();
     args.refill_threshold = knobs.refill;

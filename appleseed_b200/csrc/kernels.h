@@ -23,6 +23,8 @@ int launch_trace(
     unsigned long long* counters,   // device: asgpu_counters or nullptr
     const uint32_t*     order,      // device: optional ray permutation
     int                 sm_count,
-    void*               stream);
+    void*               stream,
+    const unsigned long long* n_dev = nullptr,  // device: when set, the ray count is read from here (n = capacity bound)
+    bool                raw_item = false);      // hit records carry the ItemRecord index instead of the caller's instance id
 
 }   // namespace asgpu

@@ -54,6 +54,13 @@ def tile_shard(width: int, height: int, world: int, rank: int, tile: int = 32) -
     return np.concatenate(out) if out else np.zeros(0, dtype=np.int64)
 
 
+def tile_ids_shard(width: int, height: int, world: int, rank: int, tile: int = 32) -> np.ndarray:
+    """Row-major tile indices (ty * tiles_x + tx) owned by ``rank``, in Hilbert order: the tile list
+    ``asgpu_path_stream_render`` takes.  Same deal as ``tile_shard``."""
+    tx = (width + tile - 1) // tile
+    return np.array([(y0 // tile) * tx + (x0 // tile) for x0, y0, _, _ in tile_grid(width, height, tile)[rank::world]], dtype=np.uint32)
+
+
 def broadcast_bytes(buf: Optional["torch.Tensor"], src: int = 0, device=None, group=None) -> "torch.Tensor":
     """Broadcast a uint8 tensor whose size only ``src`` knows (two collectives: size, payload).
     Works with NCCL (CUDA tensors) and gloo (CPU tensors)."""

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Headline benchmark: Mrays/s of the Intersector::trace() / trace_probe() hot path.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c4] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c4|c5] [--impl reference]
 
 A "step" is one pass of the hot path over one batch of synthetic rays of the named workload
 (BASELINE.json configs):
@@ -11,6 +11,9 @@ A "step" is one pass of the hot path over one batch of synthetic rays of the nam
   c3: 9 999 392-triangle fBm terrain x 64 assembly instances, 32 Mi incoherent closest-hit rays
       (+ shadow probes reported as an extra figure)
   c4: 2 000 000 moving triangles (msc = 1), 16 Mi incoherent closest-hit rays with random times
+  c5: the C3 scene, 1920 x 1080 x 64 spp synthetic path stream (camera ray + 3 cosine bounces + one
+      shadow probe per vertex, ~1 G rays per frame) through the wavefront queues (asgpu_path_stream_*),
+      32 x 32 tiles dealt to the ranks in Hilbert order: a step is one frame, scaling is STRONG
 
 `value`  = rays / device time with rays already resident in HBM (CUDA events on the launch stream).
 `e2e`    = the same step through the host-buffer C ABI call (asgpu_trace_host) with pinned host
@@ -60,13 +63,14 @@ def workload_name(args) -> str:
         "c2": "C2: 999698-triangle displaced grid, %d coherent primary + %d incoherent cosine bounce rays, closest hit",
         "c3": "C3: 9999392-triangle fBm terrain x 64 assembly instances, %d incoherent closest-hit rays (+ %d shadow probes, extra)",
         "c4": "C4: 2000000 moving triangles (msc=1), %d incoherent closest-hit rays with random time (+ %d probes, extra)",
-    }[args.workload] % (args.rays, args.rays)
+        "c5": "C5: %dx%dx%d spp path stream (camera + 3 cosine bounces + 1 shadow probe per vertex) on the 9999392-triangle x 64-instance scene, wavefront queues, 32x32 tiles",
+    }[args.workload] % ((args.width, args.height, args.spp) if args.workload == "c5" else (args.rays, args.rays))
 
 
 def make_scene(args):
     if args.workload == "c2":
         return scenes.scene_c2(args.res or 707)
-    if args.workload == "c3":
+    if args.workload in ("c3", "c5"):
         return scenes.scene_c3(args.res or 2236, 8)
     if args.workload == "c4":
         return scenes.scene_c4(args.res or 1000, 1)
@@ -244,6 +248,26 @@ def run_reference(args):
     t0 = time.perf_counter()
     oscene = oracle.scene(desc)
     build_s = time.perf_counter() - t0
+    if args.workload == "c5":
+        cfg = c5_config(args, desc)
+        w, h = max(32, args.width // 2), max(32, args.height // 2)
+        cpu_path_stream(desc, oscene, cfg, w // 4, h // 4, threads)
+        ns, ts = [], []
+        for k in range(args.steps):
+            n, secs = cpu_path_stream(desc, oscene, cfg, w, h, threads, seed=7 + k)
+            ns.append(n); ts.append(secs)
+        ms = 1e3 * sum(ts) / len(ts)
+        value = sum(ns) / sum(ts) / 1e6
+        print(json.dumps({
+            "impl": "reference", "metric": "Mrays/s closest-hit + shadow-probe (wavefront path stream, queues resident in HBM)",
+            "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": 1, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args), "sample": "%dx%d x 1 spp of the path stream per step (%d rays)" % (w, h, ns[0]),
+                       "scene_build_s": round(build_s, 2)},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind,
+                             "sample": "%dx%d x 1 spp of the path stream per step, %d threads" % (w, h, threads)},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+        return
     sample, half = cpu_sample(args, desc)
     if args.workload == "c2":
         hits = oscene.trace(sample, threads=threads)
@@ -549,6 +573,199 @@ def run_gpu(args):
         dist.barrier()
         dist.destroy_process_group()
 
+# ---------------------------------------------------------------------------------------------
+# C5: the wavefront path stream
+# ---------------------------------------------------------------------------------------------
+
+def c5_config(args, desc) -> dict:
+    """Camera above one corner of the instance lattice looking at its centre; 4 point lights above
+    the corners (the C3 lights)."""
+    from appleseed_b200.wavefront import look_at
+    lo, hi = scenes.scene_bbox(desc)
+    centre = 0.5 * (lo + hi)
+    diag = float(np.linalg.norm(hi - lo))
+    eye = centre + np.array([0.32, 0.55, 0.45]) * diag
+    lights = np.array([[lo[0], hi[1] + 2.0, lo[2]], [hi[0], hi[1] + 2.0, lo[2]], [lo[0], hi[1] + 2.0, hi[2]], [hi[0], hi[1] + 2.0, hi[2]]])
+    return dict(width=args.width, height=args.height, spp=args.spp, camera_to_world=look_at(eye, centre), lights=lights,
+                max_bounces=3, tile_size=32, seed=5, offset_eps=1.0e-6 * diag)
+
+
+def cpu_path_stream(desc, oscene, cfg: dict, width: int, height: int, threads: int, seed: int = 7):
+    """The same path stream restated on the host for the CPU arm: rays generated with numpy (same
+    camera, same sampling distributions), traced by the reference's CPU path.  Returns (rays traced,
+    seconds spent in the trace calls)."""
+    cam = scenes.camera_rays(width, height, cfg["camera_to_world"], (0.025, 0.025 * height / width), 0.035)
+    rays, total, secs = cam, 0, 0.0
+    for depth in range(cfg["max_bounces"] + 1):
+        t0 = time.perf_counter()
+        hits = oscene.trace(rays, threads=threads)
+        secs += time.perf_counter() - t0
+        total += len(rays)
+        mask, pts, nrm = scenes.hit_points_and_normals(desc, rays, hits)
+        if len(pts) == 0:
+            break
+        org = pts + cfg["offset_eps"] * nrm
+        sh = scenes.shadow_rays(org, np.asarray(cfg["lights"]), seed + 100 + depth)
+        t0 = time.perf_counter()
+        oscene.trace_probe(sh, threads=threads)
+        secs += time.perf_counter() - t0
+        total += len(sh)
+        rays = scenes.bounce_rays(pts, nrm, seed + depth, flags=VIS_DIFFUSE, offset=cfg["offset_eps"])
+    return total, secs
+
+
+def run_gpu_c5(args):
+    import torch
+    import torch.distributed as dist
+    from appleseed_b200.distributed import tile_ids_shard
+    from appleseed_b200.intersector import HostTrees, TraceContext
+    from appleseed_b200.wavefront import PathStream, PathStreamConfig
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    desc = make_scene(args)
+    build_s = flatten_s = bcast_s = 0.0
+    if rank == 0:
+        trees = HostTrees(desc, threads=0)
+        build_s = trees.build_seconds
+        t1 = time.perf_counter()
+        ctx = TraceContext(device=local_rank, trees=trees)
+        trees.close()
+        flatten_s = time.perf_counter() - t1
+    if world > 1:
+        size = torch.tensor([ctx.blob_size if rank == 0 else 0], dtype=torch.int64, device=device)
+        dist.broadcast(size, 0)
+        blob = ctx.blob_tensor() if rank == 0 else torch.empty(int(size.item()), dtype=torch.uint8, device=device)
+        barrier()
+        t1 = time.perf_counter()
+        dist.broadcast(blob, 0)
+        torch.cuda.synchronize()
+        bcast_s = time.perf_counter() - t1
+        if rank != 0:
+            ctx = TraceContext.from_blob(blob, adopt=True)
+    info = ctx.info()
+
+    cfg = c5_config(args, desc)
+    tiles = tile_ids_shard(args.width, args.height, world, rank, 32)
+    ps = PathStream(ctx, PathStreamConfig(**cfg), queue_capacity=args.rays)
+
+    def frame():
+        ps.render(tiles)
+
+    for _ in range(max(3, args.warmup) if args.spp <= 8 else 1):
+        frame()
+    torch.cuda.synchronize()
+    ps.clear()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for s in range(args.steps):
+        ev[s][0].record()
+        frame()
+        ev[s][1].record()
+    barrier()
+    ms_step = sum(a.elapsed_time(b) for a, b in ev) / args.steps
+    clocks = sampler.stop() if rank == 0 else None
+    st = ps.stats()
+    image = ps.image()
+    rays_step = (st["camera_rays"] + st["bounce_rays"] + st["probe_rays"]) // args.steps
+    closest_step = (st["camera_rays"] + st["bounce_rays"]) // args.steps
+    launches = st["kernel_launches"]
+    checksum = int(image.astype(np.uint64).sum()) // args.steps
+
+    # ---- end to end: tile list in, image out, through the public API (host buffers) -----------
+    ps.clear()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(1, min(args.steps, 3))
+    for _ in range(e2e_steps):
+        frame()
+        ps.image()
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+
+    # ---- algorithmic bytes per ray (counters variant of the same frame, untimed) --------------
+    ps.close()
+    psc = PathStream(ctx, PathStreamConfig(**{**cfg, "counters": True}), queue_capacity=args.rays)
+    ctx.counters(reset=True)
+    psc.render(tiles[: max(1, len(tiles) // 8)])
+    c = ctx.counters(reset=True)
+    psc.close()
+    r = max(1, c["rays"])
+    per_ray = {"top_nodes": c["assembly_nodes_visited"] / r, "instances": c["instances_visited"] / r,
+               "nodes": c["triangle_nodes_visited"] / r, "triangles": c["triangles_tested"] / r, "hit_rate": c["hits"] / r}
+    closest_frac = closest_step / max(1, rays_step)
+    bytes_per_ray = (per_ray["top_nodes"] + per_ray["nodes"]) * 80 + per_ray["triangles"] * 48 + per_ray["instances"] * (128 + 88 + 4) \
+        + 72 + closest_frac * 40 + (1 - closest_frac) * 1
+
+    t = torch.tensor([ms_step, e2e_ms], dtype=torch.float64, device=device)
+    counts = torch.tensor([rays_step, closest_step, checksum, launches], dtype=torch.int64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+    ms_step, e2e_ms = (float(x) for x in t.cpu())
+    total_rays, total_closest, checksum, launches = (int(x) for x in counts.cpu())
+    value = total_rays / (ms_step * 1e-3) / 1e6
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        achieved = bytes_per_ray * (total_rays / world) / (ms_step * 1e-3) / 1e9
+        line = {
+            "metric": "Mrays/s closest-hit + shadow-probe (wavefront path stream, queues resident in HBM)", "value": value, "unit": UNIT,
+            "n_gpus": world, "steps": args.steps, "warmup": 3 if args.spp <= 8 else 1,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {
+                "workload": workload_name(args), "rays_per_frame": total_rays, "closest_rays_per_frame": total_closest,
+                "probe_rays_per_frame": total_rays - total_closest, "tiles_per_gpu": int(len(tiles)), "queue_capacity": args.rays,
+                "image_checksum": checksum,
+                "l2": "inputs larger than L2 (%.0f MB scene blob, %.0f MB of queued rays per wavefront vs 126 MB L2)" % (info["blob_bytes"] / 1e6, args.rays * 72 / 1e6),
+                "scene": {k: info[k] for k in ("triangle_count", "instance_count", "wide_node_count", "binary_node_count", "blob_bytes")},
+                "scene_build_s": round(build_s, 2), "flatten_upload_s": round(flatten_s, 2), "broadcast_s": round(bcast_s, 4),
+                "per_ray": {k: round(v, 3) for k, v in per_ray.items()},
+                "parallelism": "tiles dealt to ranks in Hilbert order, scene replicated by one NCCL broadcast" if world > 1 else "1 GPU",
+            },
+            "e2e": {"value": total_rays / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(len(tiles)) * 4 * world,
+                    "d2h_bytes_per_step": args.width * args.height * 16 * world, "ms_per_step": e2e_ms},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "bytes_per_ray": round(bytes_per_ray, 1), "peak_source": peak_src, "kernel": "wide_kernel (closest + any hit)",
+                         "note": "whole-frame figure: trace kernels plus the generate / shade / accumulate stages"},
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu:
+            oracle, kind = cpu_oracle()
+            threads = os.cpu_count() or 1
+            oscene = oracle.scene(desc)
+            w = max(32, args.width // 4)
+            h = max(32, args.height // 4)
+            n, secs = cpu_path_stream(desc, oscene, cfg, w, h, threads)
+            line["cpu_baseline"] = {"value": n / secs / 1e6, "unit": UNIT, "cores": threads, "kind": kind,
+                                    "sample": "%dx%d x 1 spp of the same path stream (%d rays), %d threads, %.1f s" % (w, h, n, threads, secs)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
 
 def main():
     ap = argparse.ArgumentParser()
@@ -556,16 +773,21 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"])
+    ap.add_argument("--width", type=int, default=1920, help="c5: image width")
+    ap.add_argument("--height", type=int, default=1080, help="c5: image height")
+    ap.add_argument("--spp", type=int, default=64, help="c5: camera paths per pixel")
     ap.add_argument("--rays", type=int, default=0, help="rays per batch per GPU (default: the workload's)")
     ap.add_argument("--res", type=int, default=0, help="override the grid resolution (smaller scene for quick runs)")
     ap.add_argument("--cpu-rays", type=int, default=0, help="size of the CPU baseline sample (default: one whole batch)")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.rays == 0:
-        args.rays = {"c2": 16 * MI, "c3": 32 * MI, "c4": 16 * MI}[args.workload]
+        args.rays = {"c2": 16 * MI, "c3": 32 * MI, "c4": 16 * MI, "c5": 16 * MI}[args.workload]
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "c5":
+        run_gpu_c5(args)
     else:
         run_gpu(args)
 

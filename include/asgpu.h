@@ -268,6 +268,91 @@ typedef struct asgpu_counters {
 
 int             asgpu_get_counters(asgpu_scene* scene, asgpu_counters* out, int reset);
 
+/* ------------------------------------------------------------------------------------------
+ * Wavefront ray queues: the renderer's recursive per-sample trace
+ * loop -- GenericSampleRenderer::render_sample (generic/genericsamplerenderer.cpp:164-299) ->
+ * PathTracer::trace (lighting/pathtracer.h:218-...) -> Tracer::trace_between (lighting/tracer.h:
+ * 252-259) -- restructured into stages over device-resident queues:
+ *
+ *     generate -> [closest-hit queue] -> asgpu_trace -> shade / enqueue -> [closest-hit queue']
+ *                                                                  \-> [shadow-probe queue] -> asgpu_trace_probe -> accumulate
+ *
+ * A queue is a ray batch in HBM (the same SoA arrays as asgpu_rays) plus a path id per ray and a
+ * device-side ray count, so that a stage can be enqueued without the host knowing how many rays
+ * the previous stage produced: no host round trip between wavefronts.
+ * ------------------------------------------------------------------------------------------ */
+
+typedef struct asgpu_ray_queue asgpu_ray_queue;
+
+asgpu_ray_queue* asgpu_queue_create(asgpu_scene* scene, size_t capacity);
+void            asgpu_queue_destroy(asgpu_ray_queue* queue);
+size_t          asgpu_queue_capacity(const asgpu_ray_queue* queue);
+/* Device pointers of the queue's arrays (for a caller's own generate / shade kernels):
+ * rays->org ... flags as in asgpu_rays; path_ids = uint32_t[capacity]; count = uint64_t in device memory. */
+int             asgpu_queue_device_arrays(asgpu_ray_queue* queue, asgpu_rays* rays, uint32_t** path_ids, uint64_t** count);
+int             asgpu_queue_reset(asgpu_ray_queue* queue, void* stream);                    /* count = 0 */
+int             asgpu_queue_count(asgpu_ray_queue* queue, void* stream, uint64_t* count);   /* synchronises `stream` */
+/* Appends n rays from HOST arrays (path_ids may be NULL: ids = position). */
+int             asgpu_queue_push_host(asgpu_ray_queue* queue, const asgpu_rays* rays, const uint32_t* path_ids, size_t n, void* stream);
+/* Trace everything in the queue (the ray count is read on the device).  hits / occluded: DEVICE
+ * arrays of at least `capacity` entries. */
+int             asgpu_trace_queue(asgpu_scene* scene, asgpu_ray_queue* queue, asgpu_hit* hits, uint32_t flags, void* stream);
+int             asgpu_trace_probe_queue(asgpu_scene* scene, asgpu_ray_queue* queue, uint8_t* occluded, uint32_t flags, void* stream);
+
+/* The synthetic path stream of BASELINE.json configs[4]: per pixel
+ * sample one pinhole camera ray (PinholeCamera::spawn_ray, renderer/modeling/camera/
+ * pinholecamera.cpp:159-195), then up to max_bounces cosine-weighted bounces
+ * (sample_hemisphere_cosine, foundation/math/sampling/mappings.h:299-314) about the geometric
+ * normal, and at every path vertex one shadow probe to one of the point lights with
+ * tmax = distance * (1 - 1e-6) (Tracer::trace_between, renderer/kernel/lighting/tracer.h:252-259).
+ * Random numbers are a counter-based hash of (seed, pixel, sample, depth): the result does not
+ * depend on batching, queue order or the number of GPUs. */
+typedef struct asgpu_path_stream_desc {
+    uint32_t        width, height;          /* image resolution */
+    uint32_t        spp;                    /* camera paths per pixel */
+    uint32_t        max_bounces;            /* bounces after the primary ray (3 for C5) */
+    uint32_t        tile_size;              /* 32: Frame's default tile size (frame.cpp:1331) */
+    uint32_t        light_count;            /* 1..8 */
+    uint32_t        trace_flags;            /* ASGPU_TRACE_* used for the stream's trace launches */
+    uint32_t        reserved;
+    uint64_t        seed;
+    double          camera_to_world[12];    /* 3 x 4 row-major: rotation | translation */
+    double          film_width, film_height, focal_length;
+    double          lights[8][3];           /* point light positions, world space */
+    double          offset_eps;             /* next-ray origin offset along the geometric normal (parent == nullptr convention) */
+} asgpu_path_stream_desc;
+
+typedef struct asgpu_path_stream_stats {
+    uint64_t        camera_rays, bounce_rays, probe_rays;   /* rays traced, by kind */
+    uint64_t        surface_hits, escaped, unoccluded;
+    uint64_t        wavefronts;             /* closest-hit wavefronts processed */
+    uint64_t        kernel_launches;        /* launches of this library's kernels (generate, trace, shade, accumulate) */
+} asgpu_path_stream_stats;
+
+typedef struct asgpu_path_stream asgpu_path_stream;
+
+/* queue_capacity: rays per wavefront (rounded down to whole tiles' worth of paths). */
+asgpu_path_stream* asgpu_path_stream_create(asgpu_scene* scene, const asgpu_path_stream_desc* desc, size_t queue_capacity);
+void            asgpu_path_stream_destroy(asgpu_path_stream* stream);
+uint32_t        asgpu_path_stream_tile_count(const asgpu_path_stream* stream);
+/* Renders the given tiles (HOST array of tile indices, row-major tile grid) in as many batches as
+ * the queue capacity requires; asynchronous on `stream` except for the upload of the tile list. */
+int             asgpu_path_stream_render(asgpu_path_stream* stream, const uint32_t* tiles, size_t tile_count, void* cuda_stream);
+/* Per pixel accumulators, HOST array of width * height * 4 uint32_t:
+ * [0] surface hits, [1] unoccluded shadow probes, [2] escaped rays, [3] sum of hit-identity hashes.  Synchronises. */
+int             asgpu_path_stream_read_image(asgpu_path_stream* stream, uint32_t* accum);
+int             asgpu_path_stream_clear(asgpu_path_stream* stream);
+int             asgpu_path_stream_get_stats(asgpu_path_stream* stream, asgpu_path_stream_stats* out);
+/* Test hook: keep a copy of every wavefront's rays and results of the NEXT render call (HOST side,
+ * bounded by max_rays); asgpu_path_stream_capture_get returns wavefront k: kind 0 = closest hit
+ * (results = asgpu_hit[n]), 1 = shadow probe (results = uint8_t[n]).  Returns the number of rays
+ * or a negative error; arrays may be NULL to query the size. */
+int             asgpu_path_stream_capture(asgpu_path_stream* stream, size_t max_rays);
+int             asgpu_path_stream_capture_count(const asgpu_path_stream* stream);
+long long       asgpu_path_stream_capture_get(const asgpu_path_stream* stream, int k, int* kind, uint32_t* depth,
+                                              double* org, double* dir, double* tmin, double* tmax, uint32_t* flags,
+                                              uint32_t* path_ids, void* results);
+
 const char*     asgpu_last_error(void);
 int             asgpu_version(void);
 

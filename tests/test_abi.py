@@ -34,6 +34,7 @@ def test_struct_sizes_match_header():
     assert C.sizeof(CMesh) == 48 and C.sizeof(CObjectInstance) == 264 and C.sizeof(CAssemblyInstance) == 264
     assert C.sizeof(CRays) == 56
     assert C.sizeof(_lib.AssemblyItem) == 144 and C.sizeof(_lib.TriangleTreeView) == 80
+    assert C.sizeof(_lib.PathStreamDesc) == 360 and C.sizeof(_lib.PathStreamStats) == 64      # gcc sizeof of the header's structs
 
 
 def test_null_arguments_are_rejected_with_a_message():

@@ -32,6 +32,24 @@ def test_tile_shards_partition_the_frame(world):
     assert (max(sizes) - min(sizes)) / (w * h / world) < 0.02     # round-robin over tiles: near-perfect balance
 
 
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_tile_id_shards_cover_the_same_pixels_as_the_pixel_shards(world):
+    w, h, tile = 1920, 1080, 32
+    tx = (w + tile - 1) // tile
+    seen = []
+    for r in range(world):
+        ids = D.tile_ids_shard(w, h, world, r, tile)
+        seen.append(ids)
+        pix = []
+        for t in ids.tolist():
+            x0, y0 = (t % tx) * tile, (t // tx) * tile
+            ys, xs = np.meshgrid(np.arange(y0, min(h, y0 + tile)), np.arange(x0, min(w, x0 + tile)), indexing="ij")
+            pix.append((ys * w + xs).reshape(-1))
+        assert np.array_equal(np.concatenate(pix), D.tile_shard(w, h, world, r, tile))
+    every = np.concatenate(seen)
+    assert len(every) == tx * ((h + tile - 1) // tile) == len(np.unique(every))
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))

@@ -1,0 +1,173 @@
+"""Wavefront queues and the path stream (include/asgpu.h, "Wavefront ray queues") on the GPU.
+
+* every wavefront the stream traces (captured rays + results) matches the oracle on the identical
+  ray set under the north-star parity rule (tests/parity.py);
+* the queue bookkeeping is consistent: one probe per surface hit, one bounce per surface hit while
+  depth < max_bounces, accumulators = recount from the captured results;
+* size-independent properties: the image does not depend on the queue capacity (batching), on the
+  split of tiles between renderers (tile sharding = the multi-GPU decomposition), nor on the
+  kernel (exact vs wide)."""
+import numpy as np
+import pytest
+
+import cases
+import parity
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def setup():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from appleseed_b200 import scenes, wavefront
+    from appleseed_b200.intersector import TraceContext
+    desc = scenes.scene_c3(48, 3)
+    lo, hi = scenes.scene_bbox(desc)
+    centre = 0.5 * (lo + hi)
+    eye = centre + np.array([0.3, 1.6, 1.1]) * np.linalg.norm(hi - lo) * 0.45
+    lights = np.array([[lo[0], hi[1] + 2.0, lo[2]], [hi[0], hi[1] + 2.0, lo[2]], [lo[0], hi[1] + 2.0, hi[2]], [hi[0], hi[1] + 2.0, hi[2]]])
+    cfg = dict(width=80, height=56, spp=3, camera_to_world=wavefront.look_at(eye, centre), lights=lights, max_bounces=3,
+               tile_size=16, seed=11, offset_eps=1.0e-6 * float(np.linalg.norm(hi - lo)))
+    ctx = TraceContext(desc, device=0)
+    return desc, ctx, wavefront, cfg
+
+
+def render(wavefront, ctx, cfg, capacity, tiles=None, capture=0, **over):
+    ps = wavefront.PathStream(ctx, wavefront.PathStreamConfig(**{**cfg, **over}), queue_capacity=capacity)
+    if capture:
+        ps.capture(capture)
+    ps.render(tiles)
+    img, stats = ps.image(), ps.stats()
+    caps = ps.captured() if capture else []
+    ps.close()
+    return img, stats, caps
+
+
+def test_every_wavefront_matches_the_oracle(setup, orc):
+    desc, ctx, wavefront, cfg = setup
+    o = orc.scene(desc)
+    img, stats, caps = render(wavefront, ctx, cfg, 1 << 20, capture=1 << 22)
+    assert len(caps) == 2 * (cfg["max_bounces"] + 1)          # one batch: (closest, probe) per depth
+    spp, w = cfg["spp"], cfg["width"]
+    recount = np.zeros_like(img)
+    prev_hits = None
+    total = {"closest": 0, "probe": 0}
+    for c in caps:
+        n = len(c.rays)
+        total[c.kind] += n
+        assert n > 0
+        pixel = c.path_ids // spp
+        if c.kind == "closest":
+            ref = o.trace(c.rays, threads=4)
+            s = parity.compare_hits(o, c.rays, c.results, ref)
+            assert s["identity_equal"] == n - s["tie_exempt"]
+            if c.depth == 0:
+                assert n == cfg["width"] * cfg["height"] * spp
+                assert len(np.unique(c.path_ids)) == n
+                assert np.all(c.rays.flags == 1) and np.allclose(np.linalg.norm(c.rays.dir, axis=1), 1.0, atol=1e-12)
+            else:
+                assert n == prev_hits                         # one bounce per surface hit of the previous depth
+            hit = c.results["prim_type"] == 2
+            prev_hits = int(hit.sum())
+            np.add.at(recount[..., 0].reshape(-1), pixel[hit], 1)
+            np.add.at(recount[..., 2].reshape(-1), pixel[~hit], 1)
+            h = c.results[hit]
+            ident = (h["primitive_index"].astype(np.uint64) * 2654435761 + h["object_instance_index"].astype(np.uint64) * 0x9E3779B1
+                     + h["assembly_instance"].astype(np.uint64) * 0x85EBCA6B + h["tri_slot"].astype(np.uint64)) & 0xFFFFFFFF
+            np.add.at(recount[..., 3].reshape(-1), pixel[hit], ident.astype(np.uint32))
+        else:
+            assert n == prev_hits                             # one shadow probe per path vertex
+            ref = o.trace_probe(c.rays, threads=4)
+            parity.compare_probes(o, c.rays, c.results, ref)
+            assert np.all(c.rays.flags == 4)
+            np.add.at(recount[..., 1].reshape(-1), pixel[c.results == 0], 1)
+    assert np.array_equal(img, recount)
+    assert stats["camera_rays"] + stats["bounce_rays"] == total["closest"]
+    assert stats["probe_rays"] == total["probe"] == stats["surface_hits"]
+    assert stats["surface_hits"] == int(img[..., 0].sum()) and stats["escaped"] == int(img[..., 2].sum())
+    assert stats["unoccluded"] == int(img[..., 1].sum())
+    assert stats["wavefronts"] == cfg["max_bounces"] + 1
+    assert stats["kernel_launches"] == 1 + 4 * (cfg["max_bounces"] + 1)
+
+
+def test_bounce_rays_start_on_the_surface_they_hit(setup):
+    desc, ctx, wavefront, cfg = setup
+    _, _, caps = render(wavefront, ctx, cfg, 1 << 20, capture=1 << 22)
+    closest = [c for c in caps if c.kind == "closest"]
+    probes = [c for c in caps if c.kind == "probe"]
+    for parent, child, probe in zip(closest[:-1], closest[1:], probes[:-1]):
+        hit = parent.results["prim_type"] == 2
+        pts = parent.rays.org[hit] + parent.results["t"][hit][:, None] * parent.rays.dir[hit]
+        by_path = dict(zip(parent.path_ids[hit].tolist(), range(int(hit.sum()))))
+        idx = np.array([by_path[p] for p in child.path_ids.tolist()])
+        d = np.linalg.norm(child.rays.org - pts[idx], axis=1)
+        assert np.allclose(d, cfg["offset_eps"], rtol=1e-6, atol=1e-12)
+        assert np.allclose(np.linalg.norm(child.rays.dir, axis=1), 1.0, atol=1e-12)
+        # Cosine-weighted about the offset normal: every direction leaves the surface.
+        nrm = (child.rays.org - pts[idx]) / d[:, None]
+        assert np.all(np.einsum("ij,ij->i", nrm, child.rays.dir) >= -1e-12)
+        # The probe of the same vertex starts at the same point and stops just short of its light.
+        pidx = np.array([by_path[p] for p in probe.path_ids.tolist()])
+        assert np.allclose(np.linalg.norm(probe.rays.org - pts[pidx], axis=1), cfg["offset_eps"], rtol=1e-6, atol=1e-12)
+        reach = probe.rays.org + probe.rays.dir * (probe.rays.tmax / (1.0 - 1.0e-6))[:, None]
+        dist = np.min(np.linalg.norm(reach[:, None, :] - np.asarray(cfg["lights"])[None], axis=2), axis=1)
+        assert np.all(dist < 1e-9)
+
+
+def test_image_is_independent_of_batching_sharding_and_kernel(setup):
+    desc, ctx, wavefront, cfg = setup
+    full, stats, _ = render(wavefront, ctx, cfg, 1 << 20)
+    per_tile = cfg["tile_size"] ** 2 * cfg["spp"]
+    small, stats_small, _ = render(wavefront, ctx, cfg, 3 * per_tile)           # many batches
+    assert np.array_equal(full, small)
+    assert stats_small["wavefronts"] > stats["wavefronts"]
+    for k in ("camera_rays", "bounce_rays", "probe_rays", "surface_hits", "escaped", "unoccluded"):
+        assert stats[k] == stats_small[k], k
+    # Tile sharding (the multi-GPU decomposition): shards render disjoint pixels that add up to the frame.
+    from appleseed_b200.distributed import tile_ids_shard
+    parts = [render(wavefront, ctx, cfg, 1 << 20, tiles=tile_ids_shard(cfg["width"], cfg["height"], 3, r, cfg["tile_size"]))[0] for r in range(3)]
+    assert np.array_equal(full, parts[0] + parts[1] + parts[2])
+    touched = [(p.reshape(-1, 4).sum(axis=1) > 0) for p in parts]
+    assert not np.any(touched[0] & touched[1]) and not np.any(touched[1] & touched[2])
+    # The exact kernels (reference visit order) produce the same image.
+    exact, _, _ = render(wavefront, ctx, cfg, 1 << 20, exact=True)
+    assert np.array_equal(full, exact)
+
+
+def test_queue_api_round_trip(setup, orc):
+    import torch
+    desc, ctx, wavefront, cfg = setup
+    from appleseed_b200.intersector import HIT_BYTES, hits_from_tensor
+    _, rays, probes = cases.case_c3()
+    rays = rays.slice(0, 5000)
+    rays = type(rays)(rays.org, rays.dir, rays.tmin, rays.tmax, flags=rays.flags)       # queues carry no time
+    q = wavefront.RayQueue(ctx, 8192)
+    assert len(q) == 0
+    q.push(rays.slice(0, 2000))
+    q.push(rays.slice(2000, 5000))
+    assert len(q) == 5000
+    hits = torch.empty(q.capacity * HIT_BYTES, dtype=torch.uint8, device="cuda:0")
+    q.trace(hits)
+    torch.cuda.synchronize()
+    got = hits_from_tensor(hits, 5000)
+    from appleseed_b200.intersector import Intersector
+    assert got.tobytes() == Intersector(ctx).trace(rays).tobytes()
+    with pytest.raises(Exception, match="overflow"):
+        q.push(rays)
+    q.reset()
+    assert len(q) == 0
+    q.close()
+
+
+def test_path_stream_rejects_bad_input(setup):
+    desc, ctx, wavefront, cfg = setup
+    from appleseed_b200.intersector import AsgpuError
+    with pytest.raises(AsgpuError, match="capacity"):
+        wavefront.PathStream(ctx, wavefront.PathStreamConfig(**cfg), queue_capacity=10)
+    with pytest.raises(AsgpuError, match="light_count"):
+        wavefront.PathStream(ctx, wavefront.PathStreamConfig(**{**cfg, "lights": np.zeros((9, 3))}), queue_capacity=1 << 16)
+    ps = wavefront.PathStream(ctx, wavefront.PathStreamConfig(**cfg), queue_capacity=1 << 16)
+    with pytest.raises(AsgpuError, match="range"):
+        ps.render([ps.tile_count])
+    ps.close()
