@@ -22,7 +22,7 @@ EXPORTS = [
     "asgpu_scene_blob_size", "asgpu_scene_blob_device_ptr", "asgpu_scene_export_blob", "asgpu_scene_import_blob",
     "asgpu_scene_get_info",
     "asgpu_trace", "asgpu_trace_probe", "asgpu_trace_host", "asgpu_trace_probe_host",
-    "asgpu_get_counters", "asgpu_last_error", "asgpu_version",
+    "asgpu_get_counters", "asgpu_last_error", "asgpu_version", "asgpu_sort_rays",
     "asgpu_queue_create", "asgpu_queue_destroy", "asgpu_queue_capacity", "asgpu_queue_device_arrays",
     "asgpu_queue_reset", "asgpu_queue_count", "asgpu_queue_push_host", "asgpu_trace_queue", "asgpu_trace_probe_queue",
     "asgpu_path_stream_create", "asgpu_path_stream_destroy", "asgpu_path_stream_tile_count", "asgpu_path_stream_render",
@@ -143,6 +143,7 @@ def load() -> C.CDLL:
     lib.asgpu_trace_host.argtypes = [C.c_void_p, P(CRays), C.c_size_t, C.c_void_p, C.c_uint32]
     lib.asgpu_trace_probe_host.argtypes = [C.c_void_p, P(CRays), C.c_size_t, C.c_void_p, C.c_uint32]
     lib.asgpu_get_counters.argtypes = [C.c_void_p, P(Counters), C.c_int]
+    lib.asgpu_sort_rays.argtypes = [C.c_void_p, P(CRays), C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.asgpu_queue_create.restype = C.c_void_p
     lib.asgpu_queue_create.argtypes = [C.c_void_p, C.c_size_t]
     lib.asgpu_queue_destroy.argtypes = [C.c_void_p]

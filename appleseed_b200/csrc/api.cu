@@ -85,7 +85,7 @@ void free_staging(asgpu_scene* s)
     {
         cudaFree(st.org); cudaFree(st.dir); cudaFree(st.tmin); cudaFree(st.tmax);
         cudaFree(st.time_absolute); cudaFree(st.time_normalized); cudaFree(st.flags);
-        cudaFree(st.hits); cudaFree(st.occluded); cudaFree(st.queue);
+        cudaFree(st.hits); cudaFree(st.occluded); cudaFree(st.queue); cudaFree(st.sort_ws);
         if (st.stream) cudaStreamDestroy(st.stream);
         st = Staging();
     }
@@ -108,6 +108,7 @@ int ensure_staging(asgpu_scene* s)
         ASGPU_CUDA(cudaMalloc(&st.hits, HostChunkRays * sizeof(asgpu_hit)), "cudaMalloc(staging)");
         ASGPU_CUDA(cudaMalloc(&st.occluded, HostChunkRays), "cudaMalloc(staging)");
         ASGPU_CUDA(cudaMalloc(&st.queue, 64), "cudaMalloc(staging)");
+        ASGPU_CUDA(cudaMalloc(&st.sort_ws, ray_sort_workspace_bytes(HostChunkRays) + HostChunkRays * 4), "cudaMalloc(staging)");
     }
     s->staging_ready = true;
     return ASGPU_OK;
@@ -132,8 +133,19 @@ int trace_device(asgpu_scene* scene, const asgpu_rays* rays, const size_t n, asg
     const int rc = check_trace_args(scene, rays, n, any_hit ? static_cast<const void*>(occluded) : static_cast<const void*>(hits), flags, wide);
     if (rc != ASGPU_OK || n == 0) return rc;
     ASGPU_CUDA(cudaSetDevice(scene->device), "cudaSetDevice");
+    const uint32_t* order = nullptr;
+    if (flags & ASGPU_TRACE_SORT)
+    {
+        if (n > 0xFFFFFFFFull) return fail(ASGPU_E_UNSUPPORTED, "ASGPU_TRACE_SORT handles at most 2^32 - 1 rays per call");
+        const int rs = ensure_sort_scratch(scene, n);
+        if (rs != ASGPU_OK) return rs;
+        const int es = launch_ray_sort(*rays, n, nullptr, scene->sort.order, nullptr, scene->sort.ws, scene->sm_count, stream);
+        if (es != 0) return fail_cuda(static_cast<cudaError_t>(es), "ray sort launch");
+        scene->launches += ray_sort_launch_count();
+        order = scene->sort.order;
+    }
     const int err = launch_trace(scene->view, *rays, n, hits, occluded, any_hit, wide, queue,
-                                 (flags & ASGPU_TRACE_COUNTERS) ? scene->counters : nullptr, nullptr, scene->sm_count, stream);
+                                 (flags & ASGPU_TRACE_COUNTERS) ? scene->counters : nullptr, order, scene->sm_count, stream);
     if (err != 0) return fail_cuda(static_cast<cudaError_t>(err), "kernel launch");
     ++scene->launches;
     return ASGPU_OK;
@@ -178,8 +190,17 @@ int trace_host(asgpu_scene* scene, const asgpu_rays* rays, const size_t n, asgpu
             ASGPU_CUDA(cudaMemcpyAsync(st.flags, rays->flags + begin, count * 4, cudaMemcpyHostToDevice, st.stream), "H2D flags");
             dev.flags = st.flags;
         }
+        const uint32_t* order = nullptr;
+        if (flags & ASGPU_TRACE_SORT)
+        {
+            uint32_t* chunk_order = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(st.sort_ws) + ray_sort_workspace_bytes(HostChunkRays));
+            const int es = launch_ray_sort(dev, count, nullptr, chunk_order, nullptr, st.sort_ws, scene->sm_count, st.stream);
+            if (es != 0) return fail_cuda(static_cast<cudaError_t>(es), "ray sort launch");
+            scene->launches += ray_sort_launch_count();
+            order = chunk_order;
+        }
         const int err = launch_trace(scene->view, dev, count, st.hits, st.occluded, any_hit, wide, st.queue,
-                                     (flags & ASGPU_TRACE_COUNTERS) ? scene->counters : nullptr, nullptr, scene->sm_count, st.stream);
+                                     (flags & ASGPU_TRACE_COUNTERS) ? scene->counters : nullptr, order, scene->sm_count, st.stream);
         if (err != 0) return fail_cuda(static_cast<cudaError_t>(err), "kernel launch");
         ++scene->launches;
         if (any_hit)
@@ -191,6 +212,23 @@ int trace_host(asgpu_scene* scene, const asgpu_rays* rays, const size_t n, asgpu
         ASGPU_CUDA(cudaStreamSynchronize(st.stream), "cudaStreamSynchronize");
     return ASGPU_OK;
 }
+
+}   // anonymous namespace
+
+int asgpu::ensure_sort_scratch(asgpu_scene* scene, const size_t n)
+{
+    if (n <= scene->sort.capacity) return ASGPU_OK;
+    ASGPU_CUDA(cudaDeviceSynchronize(), "cudaDeviceSynchronize");
+    cudaFree(scene->sort.ws); cudaFree(scene->sort.order);
+    scene->sort = SortScratch();
+    ASGPU_CUDA(cudaMalloc(&scene->sort.ws, ray_sort_workspace_bytes(n)), "cudaMalloc(sort workspace)");
+    ASGPU_CUDA(cudaMalloc(&scene->sort.order, n * sizeof(uint32_t)), "cudaMalloc(sort order)");
+    scene->sort.capacity = n;
+    return ASGPU_OK;
+}
+
+namespace
+{
 
 asgpu_scene* adopt_blob_image(const std::vector<uint8_t>& image, const int device)
 {
@@ -309,6 +347,8 @@ void asgpu_scene_destroy(asgpu_scene* scene)
     if (scene->owns_blob) cudaFree(scene->blob);
     cudaFree(scene->queue);
     cudaFree(scene->counters);
+    cudaFree(scene->sort.ws);
+    cudaFree(scene->sort.order);
     delete scene;
 }
 
@@ -393,6 +433,21 @@ int asgpu_trace_host(asgpu_scene* scene, const asgpu_rays* rays, size_t n, asgpu
 int asgpu_trace_probe_host(asgpu_scene* scene, const asgpu_rays* rays, size_t n, uint8_t* occluded, uint32_t flags)
 {
     return trace_host(scene, rays, n, nullptr, occluded, true, flags);
+}
+
+int asgpu_sort_rays(asgpu_scene* scene, const asgpu_rays* rays, size_t n, uint32_t* order, uint32_t* keys, void* stream)
+{
+    if (!scene) return fail(ASGPU_E_INVALID, "null scene");
+    if (n == 0) return ASGPU_OK;
+    if (!rays || !rays->org || !rays->dir || !order) return fail(ASGPU_E_INVALID, "null argument");
+    if (n > 0xFFFFFFFFull) return fail(ASGPU_E_UNSUPPORTED, "at most 2^32 - 1 rays per sort");
+    ASGPU_CUDA(cudaSetDevice(scene->device), "cudaSetDevice");
+    const int rs = ensure_sort_scratch(scene, n);
+    if (rs != ASGPU_OK) return rs;
+    const int es = launch_ray_sort(*rays, n, nullptr, order, keys, scene->sort.ws, scene->sm_count, stream);
+    if (es != 0) return fail_cuda(static_cast<cudaError_t>(es), "ray sort launch");
+    scene->launches += ray_sort_launch_count();
+    return ASGPU_OK;
 }
 
 int asgpu_get_counters(asgpu_scene* scene, asgpu_counters* out, int reset)

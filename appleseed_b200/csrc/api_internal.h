@@ -41,6 +41,15 @@ struct Staging
     asgpu_hit*      hits = nullptr;
     uint8_t*        occluded = nullptr;
     unsigned long long* queue = nullptr;
+    void*           sort_ws = nullptr;      // coherence-sort workspace + permutation of one chunk
+};
+
+// Coherence-sort scratch of the device entry points: grown on demand, one user at a time.
+struct SortScratch
+{
+    void*           ws = nullptr;
+    uint32_t*       order = nullptr;
+    size_t          capacity = 0;           // rays
 };
 
 }   // namespace asgpu
@@ -61,4 +70,11 @@ struct asgpu_scene
     std::mutex          mutex;
     asgpu::Staging      staging[asgpu::HostStreams];
     bool                staging_ready = false;
+    asgpu::SortScratch  sort;
 };
+
+namespace asgpu
+{
+// Makes sure scene->sort can take n rays (reallocates after synchronising the device).
+int ensure_sort_scratch(asgpu_scene* scene, size_t n);
+}

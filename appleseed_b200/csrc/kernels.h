@@ -27,4 +27,18 @@ int launch_trace(
     const unsigned long long* n_dev = nullptr,  // device: when set, the ray count is read from here (n = capacity bound)
     bool                raw_item = false);      // hit records carry the ItemRecord index instead of the caller's instance id
 
+// Coherence sort (sort.cu): fills `order` with the permutation that sorts the rays by their
+// origin / direction Morton key.  Returns a cudaError_t value.
+size_t ray_sort_workspace_bytes(size_t n);
+int ray_sort_launch_count();
+int launch_ray_sort(
+    const asgpu_rays&   rays,       // device pointers
+    size_t              n,
+    const unsigned long long* n_dev,    // optional device-side count (<= n)
+    uint32_t*           order,      // device: n entries
+    uint32_t*           keys_out,   // device: n sorted keys, or nullptr
+    void*               workspace,  // device: ray_sort_workspace_bytes(n)
+    int                 sm_count,
+    void*               stream);
+
 }   // namespace asgpu

@@ -240,42 +240,60 @@ class Intersector:
 
     # -- host buffers (copies inside the call) ---------------------------------------------------
 
-    def trace(self, rays: RayBatch, exact: bool = False, counters: bool = False, out: Optional[np.ndarray] = None) -> np.ndarray:
+    @staticmethod
+    def _flags(exact: bool, counters: bool, sort: bool) -> int:
+        return (_lib.TRACE_EXACT if exact else 0) | (_lib.TRACE_COUNTERS if counters else 0) | (_lib.TRACE_SORT if sort else 0)
+
+    def trace(self, rays: RayBatch, exact: bool = False, counters: bool = False, out: Optional[np.ndarray] = None, sort: bool = False) -> np.ndarray:
         n = len(rays)
         hits = np.empty(n, dtype=HIT_DTYPE) if out is None else out
         cr = rays.to_c()
-        flags = (_lib.TRACE_EXACT if exact else 0) | (_lib.TRACE_COUNTERS if counters else 0)
+        flags = self._flags(exact, counters, sort)
         _check(self.lib.asgpu_trace_host(self.ctx.handle, C.byref(cr), n, hits.ctypes.data if n else None, flags), "asgpu_trace_host")
         return hits
 
-    def trace_probe(self, rays: RayBatch, exact: bool = False, counters: bool = False, out: Optional[np.ndarray] = None) -> np.ndarray:
+    def trace_probe(self, rays: RayBatch, exact: bool = False, counters: bool = False, out: Optional[np.ndarray] = None, sort: bool = False) -> np.ndarray:
         n = len(rays)
         occ = np.empty(n, dtype=np.uint8) if out is None else out
         cr = rays.to_c()
-        flags = (_lib.TRACE_EXACT if exact else 0) | (_lib.TRACE_COUNTERS if counters else 0)
+        flags = self._flags(exact, counters, sort)
         _check(self.lib.asgpu_trace_probe_host(self.ctx.handle, C.byref(cr), n, occ.ctypes.data if n else None, flags), "asgpu_trace_probe_host")
         return occ
 
     # -- device buffers (no copies; enqueued on torch's current stream) --------------------------
 
-    def trace_device(self, rays: DeviceRays, hits: "torch.Tensor", exact: bool = False, counters: bool = False):
+    def trace_device(self, rays: DeviceRays, hits: "torch.Tensor", exact: bool = False, counters: bool = False, sort: bool = False):
         """``hits``: uint8 CUDA tensor of n * 40 bytes receiving ``asgpu_hit`` records."""
         import torch
         n = len(rays)
         assert hits.numel() * hits.element_size() >= n * HIT_BYTES
         cr = rays.to_c()
-        flags = (_lib.TRACE_EXACT if exact else 0) | (_lib.TRACE_COUNTERS if counters else 0)
+        flags = self._flags(exact, counters, sort)
         stream = torch.cuda.current_stream(self.ctx.device).cuda_stream
         _check(self.lib.asgpu_trace(self.ctx.handle, C.byref(cr), n, hits.data_ptr(), flags, C.c_void_p(stream)), "asgpu_trace")
 
-    def trace_probe_device(self, rays: DeviceRays, occluded: "torch.Tensor", exact: bool = False, counters: bool = False):
+    def trace_probe_device(self, rays: DeviceRays, occluded: "torch.Tensor", exact: bool = False, counters: bool = False, sort: bool = False):
         import torch
         n = len(rays)
         assert occluded.numel() >= n
         cr = rays.to_c()
-        flags = (_lib.TRACE_EXACT if exact else 0) | (_lib.TRACE_COUNTERS if counters else 0)
+        flags = self._flags(exact, counters, sort)
         stream = torch.cuda.current_stream(self.ctx.device).cuda_stream
         _check(self.lib.asgpu_trace_probe(self.ctx.handle, C.byref(cr), n, occluded.data_ptr(), flags, C.c_void_p(stream)), "asgpu_trace_probe")
+
+
+    def sort_rays(self, rays: DeviceRays):
+        """``asgpu_sort_rays``: (order, keys) int32 CUDA tensors -- the permutation by ascending
+        origin / direction Morton key and the sorted keys."""
+        import torch
+        n = len(rays)
+        dev = "cuda:%d" % self.ctx.device
+        order = torch.empty(n, dtype=torch.int32, device=dev)
+        keys = torch.empty(n, dtype=torch.int32, device=dev)
+        cr = rays.to_c()
+        stream = torch.cuda.current_stream(self.ctx.device).cuda_stream
+        _check(self.lib.asgpu_sort_rays(self.ctx.handle, C.byref(cr), n, order.data_ptr(), keys.data_ptr(), C.c_void_p(stream)), "asgpu_sort_rays")
+        return order, keys
 
 
 def hits_from_tensor(t: "torch.Tensor", n: int) -> np.ndarray:

@@ -255,6 +255,12 @@ int             asgpu_trace_probe(asgpu_scene* scene, const asgpu_rays* rays, si
 int             asgpu_trace_host(asgpu_scene* scene, const asgpu_rays* rays, size_t n, asgpu_hit* hits, uint32_t flags);
 int             asgpu_trace_probe_host(asgpu_scene* scene, const asgpu_rays* rays, size_t n, uint8_t* occluded, uint32_t flags);
 
+/* The coherence sort behind ASGPU_TRACE_SORT on its own: order[i] = index of the ray to process
+ * at position i (a permutation of 0..n-1, device array) by ascending 24-bit origin / direction
+ * Morton key; keys (optional, device) receives the sorted keys.  One sort at a time per scene
+ * (the scratch memory belongs to the scene handle). */
+int             asgpu_sort_rays(asgpu_scene* scene, const asgpu_rays* rays, size_t n, uint32_t* order, uint32_t* keys, void* stream);
+
 typedef struct asgpu_counters {
     uint64_t        rays;
     uint64_t        assembly_nodes_visited;

@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--rays", type=int, default=8 << 20)
     ap.add_argument("--res", type=int, default=0)
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--sort", action="store_true", help="also time every wavefront with ASGPU_TRACE_SORT (sort + trace) and the sort alone")
     ap.add_argument("--sweep", action="append", default=[], help="ENV=v1,v2,... (cartesian product of all sweeps)")
     args = ap.parse_args()
     dev = "cuda:0"
@@ -97,6 +98,23 @@ def main():
                         res[name + "_changed_rays"] = int((a != b).any(dim=1).sum())
                 else:
                     ref_out[name] = got
+                if args.sort:
+                    def timed(fn):
+                        for _ in range(2):
+                            fn()
+                        torch.cuda.synchronize()
+                        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        a.record()
+                        for _ in range(args.reps):
+                            fn()
+                        b.record()
+                        torch.cuda.synchronize()
+                        return a.elapsed_time(b) / args.reps
+                    ms_sorted = timed((lambda: isect.trace_probe_device(rays, occ, sort=True)) if probe else (lambda: isect.trace_device(rays, out, sort=True)))
+                    same = torch.equal(occ if probe else out, ref_out[name])
+                    ms_sort = timed(lambda: isect.sort_rays(rays))
+                    res[name + "_sorted"] = {"mrays_s_incl_sort": round(n / ms_sorted / 1e3, 1), "sort_ms": round(ms_sort, 3),
+                                             "trace_only_mrays_s": round(n / max(1e-6, ms_sorted - ms_sort) / 1e3, 1), "identical": bool(same)}
                 ctx.counters(reset=True)
                 (isect.trace_probe_device(rays, occ, counters=True) if probe else isect.trace_device(rays, out, counters=True))
                 c = ctx.counters(reset=True)
