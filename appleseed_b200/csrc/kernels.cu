@@ -52,6 +52,9 @@ struct KernelArgs
     int                 flush_threshold;    // queued candidates that trigger a test batch
     int                 stall_threshold;    // lanes idle or waiting for the queue that trigger one
     uint32_t            unit_bits;          // bits of 1.0f (see byte_to_unit)
+    int                 prefetch;           // start the fetch of the next node as soon as it is chosen
+    int                 max_steps;          // node tests per lane and loop iteration
+    int                 step_threshold;     // lanes that must be able to advance for another step
 };
 
 __device__ __forceinline__ void store_hit(asgpu_hit* out, const SceneView& s, const double t, const Hit& hit, const bool found, const bool raw_item)
@@ -160,6 +163,13 @@ struct WideShared
     uint32_t            hit_slot[BlockThreads], hit_item[BlockThreads], hit_segment[BlockThreads];
     uint32_t            cur_item[BlockThreads];
 };
+
+// Starts the fetch of one wide node (80 bytes, 16-byte aligned: at most two 128-byte lines) into L1.
+__device__ __forceinline__ void prefetch_node(const uint8_t* p)
+{
+    asm volatile("prefetch.global.L1 [%0];" :: "l"(p));
+    asm volatile("prefetch.global.L1 [%0];" :: "l"(p + 64));
+}
 
 // Monotone map from double to uint64 (for atomicMin on t).
 __device__ __forceinline__ unsigned long long ordered_key(const double t)
@@ -305,10 +315,29 @@ wide_kernel(const KernelArgs args)
         if (exhausted && __ballot_sync(0xFFFFFFFFu, active) == 0) break;
 
         // ---- one traversal step per active lane ---------------------------------------------------
-        uint32_t pending = 0, tri_first = 0;            // leaf triangles found by this step's node test
+        // Several steps per iteration: a lane keeps walking internal nodes until it finds leaf
+        // triangles (most node tests find none), so the warp-level bookkeeping below (refill,
+        // gather, flush, pick-up) is paid once per `max_steps` node tests instead of once per test.
+        // The extra rounds only run while enough lanes can still advance.
+        uint32_t pending = 0, tri_first = 0;            // leaf triangles found by this iteration's node tests
         bool held = false;                              // this lane cannot advance before the queue drains
-        if (active && !traversed)
+        for (int round = 0; ; ++round)
         {
+        if (active && !traversed && !held && pending == 0)
+        {
+            if (fetch != None)
+            {
+                if (COUNT) { if (cur_item != None) ++stats.nodes; else ++stats.top_nodes; }
+                if (ngroup.y & 0xFF000000u) { stack[sp * stride] = ngroup; ++sp; }
+                uint32_t child_base, tri_base, nmask, tmask;
+                wide_node_test(wnodes + static_cast<uint64_t>(fetch) * sizeof(WNode), w, args.unit_bits, child_base, tri_base, nmask, tmask);
+                ngroup.x = child_base; ngroup.y = nmask;
+                if (cur_item != None) { pending = tmask; tri_first = tri_base; }
+                else { tgroup.x = tri_base; tgroup.y = tmask; }
+                fetch = None;
+            }
+
+            // Choose what comes next (and start fetching it: the node is in L1 by the time it is tested).
             if (fetch == None)
             {
                 if (tgroup.y && waiting)
@@ -392,18 +421,10 @@ wide_kernel(const KernelArgs args)
                     }
                 }
             }
-
-            if (fetch != None)
-            {
-                if (COUNT) { if (cur_item != None) ++stats.nodes; else ++stats.top_nodes; }
-                if (ngroup.y & 0xFF000000u) { stack[sp * stride] = ngroup; ++sp; }
-                uint32_t child_base, tri_base, nmask, tmask;
-                wide_node_test(wnodes + static_cast<uint64_t>(fetch) * sizeof(WNode), w, args.unit_bits, child_base, tri_base, nmask, tmask);
-                ngroup.x = child_base; ngroup.y = nmask;
-                if (cur_item != None) { pending = tmask; tri_first = tri_base; }
-                else { tgroup.x = tri_base; tgroup.y = tmask; }
-                fetch = None;
-            }
+            if (args.prefetch && fetch != None) prefetch_node(wnodes + static_cast<uint64_t>(fetch) * sizeof(WNode));
+        }
+        if (round + 1 >= args.max_steps) break;
+        if (__popc(__ballot_sync(0xFFFFFFFFu, active && !traversed && !held && pending == 0)) < args.step_threshold) break;
         }
 
         // ---- gather this step's triangle candidates -------------------------------------------------
@@ -511,20 +532,28 @@ wide_kernel(const KernelArgs args)
     if (COUNT) flush_counters(args.counters, lane, rays_done, stats, hits_found);
 }
 
-// Scheduling knobs of the wide kernel.  Defaults are the measured optimum (profiles/README.md);
-// ASGPU_REFILL / ASGPU_FLUSH / ASGPU_STALL override them for experiments.
-struct Tuning { int refill, flush, stall; };
+// Scheduling knobs of the wide kernel.  Defaults are the measured optima (profiles/README.md, sweeps
+// r1/quick_steps*.log): scenes with a single assembly instance pay the ray set-up once per ray and
+// prefer fuller refills and more steps per iteration; instanced scenes re-do the set-up on every
+// instance entry and prefer to refill earlier.  ASGPU_REFILL / ASGPU_FLUSH / ASGPU_STALL /
+// ASGPU_STEPS / ASGPU_STEPTHR / ASGPU_PREFETCH override them for experiments.
+struct Tuning { int refill, flush, stall, prefetch, steps, step_threshold; };
 
-Tuning tuning()
+Tuning tuning(const bool single_instance)
 {
-    Tuning v = { 8, 16, 16 };
+    Tuning v = { 8, 16, 16, 0, 3, 8 };              // prefetch: measured neutral (C2) to -5 % (C3 probes), off
+    if (single_instance) { v.refill = 16; v.stall = 24; v.steps = 4; }
     if (const char* e = getenv("ASGPU_REFILL")) v.refill = atoi(e);
     if (const char* e = getenv("ASGPU_FLUSH")) v.flush = atoi(e);
     if (const char* e = getenv("ASGPU_STALL")) v.stall = atoi(e);
+    if (const char* e = getenv("ASGPU_PREFETCH")) v.prefetch = atoi(e);
+    if (const char* e = getenv("ASGPU_STEPS")) v.steps = atoi(e);
+    if (const char* e = getenv("ASGPU_STEPTHR")) v.step_threshold = atoi(e);
     if (v.refill < 1) v.refill = 1;
     if (v.flush < 1) v.flush = 1;
     if (v.stall < 1) v.stall = 1;
     if (v.stall > 32) v.stall = 32;         // 32 stalled lanes = nobody can advance: must flush
+    if (v.steps < 1) v.steps = 1;
     return v;
 }
 
@@ -596,10 +625,13 @@ int launch_trace(
     args.n_dev = n_dev;
     args.raw_item = raw_item ? 1u : 0u;
     args.unit_bits = UnitBits;
-    const Tuning knobs = tuning();
+    const Tuning knobs = tuning(scene.item_count <= 1);
     args.refill_threshold = knobs.refill;
     args.flush_threshold = knobs.flush;
     args.stall_threshold = knobs.stall;
+    args.prefetch = knobs.prefetch;
+    args.max_steps = knobs.steps;
+    args.step_threshold = knobs.step_threshold;
 
     cudaError_t err = cudaMemsetAsync(queue, 0, sizeof(unsigned long long), stream);
     if (err != cudaSuccess) return static_cast<int>(err);
