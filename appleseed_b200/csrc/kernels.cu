@@ -55,6 +55,7 @@ struct KernelArgs
     int                 prefetch;           // start the fetch of the next node as soon as it is chosen
     int                 max_steps;          // node tests per lane and loop iteration
     int                 step_threshold;     // lanes that must be able to advance for another step
+    int                 enter_late;         // enter assembly instances once per iteration, all lanes together
 };
 
 __device__ __forceinline__ void store_hit(asgpu_hit* out, const SceneView& s, const double t, const Hit& hit, const bool found, const bool raw_item)
@@ -162,6 +163,8 @@ struct WideShared
     float               hit_u[BlockThreads], hit_v[BlockThreads];
     uint32_t            hit_slot[BlockThreads], hit_item[BlockThreads], hit_segment[BlockThreads];
     uint32_t            cur_item[BlockThreads];
+    float               world_rcp[6][BlockThreads];     // world-space reciprocal bounds (rn, rf), saved while inside an instance
+    uint32_t            world_oct[BlockThreads];
 };
 
 // Starts the fetch of one wide node (80 bytes, 16-byte aligned: at most two 128-byte lines) into L1.
@@ -238,6 +241,37 @@ __device__ __forceinline__ void test_candidates(
     __syncwarp();
 }
 
+// Back from an instance: the world-space interval ray again.  Its reciprocal bounds and octant were
+// saved at instance entry; the origin interval is two conversions per axis.  (A negative tmin
+// shifts the origin along the direction: that rare case takes the full set-up.)
+template <int STACK>
+__device__ __forceinline__ void restore_world_ray(const asgpu_rays& rays, const unsigned long long index, const double tmin, const double tmax,
+                                                  const WideShared<STACK>& sm, const unsigned tid, WideRay& w)
+{
+    if (tmin < 0.0)
+    {
+        Ray world;
+        load_ray_org_dir(rays, index, world);
+        make_wide_ray(world.org, world.dir, tmin, tmax, w);
+        return;
+    }
+    w.shift = 0.0;
+    w.oct = sm.world_oct[tid];
+    #pragma unroll
+    for (int a = 0; a < 3; ++a)
+    {
+        const double o = __ldg(rays.org + index * 3 + a);
+        const float lo = d2f_dn(o), hi = d2f_up(o);
+        const bool neg = (w.oct >> a) & 1;
+        w.o_lo[a] = neg ? -hi : lo;
+        w.o_hi[a] = neg ? -lo : hi;
+        w.rn[a] = sm.world_rcp[a][tid];
+        w.rf[a] = sm.world_rcp[3 + a][tid];
+    }
+    w.tmin_f = d2f_dn(tmin);
+    w.tmax_f = d2f_up(tmax);
+}
+
 template <bool ANY, bool COUNT, int STACK, int MINB>
 __global__ void __launch_bounds__(BlockThreads, MINB)
 wide_kernel(const KernelArgs args)
@@ -273,6 +307,60 @@ wide_kernel(const KernelArgs args)
     bool waiting = false;               // ... and which has candidates in the queue
     bool exhausted = false;             // warp-uniform: the ray queue has no more rays
     unsigned queued = 0;                // warp-uniform: candidates waiting in the queue
+
+    // Entering an assembly instance (AssemblyLeafVisitor::visit, assemblytree.cpp:604-744): ~250
+    // instructions of ray set-up.  Scenes with one instance do it in line (every ray enters right after
+    // the root test, so the lanes of a refill do it together anyway); instanced scenes collect the
+    // lanes that reach an instance during an iteration and enter together after the last round.
+    auto enter_instance = [&]()
+    {
+        // Next assembly instance: AssemblyLeafVisitor::visit (assemblytree.cpp:604-744).
+        const int bit = high_bit(tgroup.y);
+        tgroup.y &= ~(1u << bit);
+        const uint32_t item = load4(blob + s.top_witems + static_cast<uint64_t>(tgroup.x + bit) * 4);
+        const uint8_t* ip = blob + s.items + static_cast<uint64_t>(item) * sizeof(ItemRecord);
+        const uint4 meta = load16(ip + 96);
+        if ((meta.y & sm.flags[tid]) && meta.x != None)
+        {
+            if (COUNT) ++stats.instances;
+            // Save the world-space cursor, then descend.  When nothing is left to do in
+            // world space there is nothing to come back to: no sentinel, the ray ends
+            // with the instance.
+            if (ngroup.y & 0xFF000000u) { stack[sp * stride] = ngroup; ++sp; }
+            if (tgroup.y) { stack[sp * stride] = tgroup; ++sp; }
+            if (sp != 0)
+            {
+                uint2 sentinel; sentinel.x = None; sentinel.y = 0;
+                stack[sp * stride] = sentinel; ++sp;
+            }
+            Ray world;
+            load_ray_org_dir(args.rays, index, world);
+            double lorg[3], ldir[3];
+            instance_org_dir(ip, world.org, world.dir, lorg, ldir);
+            #pragma unroll
+            for (int k = 0; k < 3; ++k) { sm.ray[k][tid] = lorg[k]; sm.ray[3 + k][tid] = ldir[k]; }
+            if (sp != 0)
+            {
+                // Something is left to do in world space: keep the expensive part of the world ray.
+                #pragma unroll
+                for (int k = 0; k < 3; ++k) { sm.world_rcp[k][tid] = w.rn[k]; sm.world_rcp[3 + k][tid] = w.rf[k]; }
+                sm.world_oct[tid] = w.oct;
+            }
+            make_wide_ray(lorg, ldir, sm.ray[6][tid], sm.ray[7][tid], w);
+            const uint8_t* tp = blob + s.trees + static_cast<uint64_t>(meta.x) * sizeof(TreeDesc);
+            const uint2 o_nodes = load8(tp + offsetof(TreeDesc, wnodes));
+            const uint2 o_tris = load8(tp + offsetof(TreeDesc, wtris));
+            const uint2 o_poses = load8(tp + offsetof(TreeDesc, poses));
+            const uint32_t wnode_count = load4(tp + offsetof(TreeDesc, wnode_count));
+            wnodes = blob + (static_cast<uint64_t>(o_nodes.x) | (static_cast<uint64_t>(o_nodes.y) << 32));
+            sm.tri_base[tid] = static_cast<uint64_t>(o_tris.x) | (static_cast<uint64_t>(o_tris.y) << 32);
+            sm.pose_base[tid] = static_cast<uint64_t>(o_poses.x) | (static_cast<uint64_t>(o_poses.y) << 32);
+            sm.cur_item[tid] = item;
+            cur_item = item;
+            ngroup.y = 0; tgroup.y = 0;
+            if (wnode_count != 0) fetch = 0;
+        }
+    };
 
     for (;;)
     {
@@ -321,9 +409,10 @@ wide_kernel(const KernelArgs args)
         // The extra rounds only run while enough lanes can still advance.
         uint32_t pending = 0, tri_first = 0;            // leaf triangles found by this iteration's node tests
         bool held = false;                              // this lane cannot advance before the queue drains
+        bool want_enter = false;                        // this lane's next move is to enter an assembly instance
         for (int round = 0; ; ++round)
         {
-        if (active && !traversed && !held && pending == 0)
+        if (active && !traversed && !held && !want_enter && pending == 0)
         {
             if (fetch != None)
             {
@@ -348,45 +437,8 @@ wide_kernel(const KernelArgs args)
                 }
                 else if (tgroup.y)
                 {
-                    // Next assembly instance: AssemblyLeafVisitor::visit (assemblytree.cpp:604-744).
-                    const int bit = high_bit(tgroup.y);
-                    tgroup.y &= ~(1u << bit);
-                    const uint32_t item = load4(blob + s.top_witems + static_cast<uint64_t>(tgroup.x + bit) * 4);
-                    const uint8_t* ip = blob + s.items + static_cast<uint64_t>(item) * sizeof(ItemRecord);
-                    const uint4 meta = load16(ip + 96);
-                    if ((meta.y & sm.flags[tid]) && meta.x != None)
-                    {
-                        if (COUNT) ++stats.instances;
-                        // Save the world-space cursor, then descend.  When nothing is left to do in
-                        // world space there is nothing to come back to: no sentinel, the ray ends
-                        // with the instance.
-                        if (ngroup.y & 0xFF000000u) { stack[sp * stride] = ngroup; ++sp; }
-                        if (tgroup.y) { stack[sp * stride] = tgroup; ++sp; }
-                        if (sp != 0)
-                        {
-                            uint2 sentinel; sentinel.x = None; sentinel.y = 0;
-                            stack[sp * stride] = sentinel; ++sp;
-                        }
-                        Ray world;
-                        load_ray_org_dir(args.rays, index, world);
-                        double lorg[3], ldir[3];
-                        instance_org_dir(ip, world.org, world.dir, lorg, ldir);
-                        #pragma unroll
-                        for (int k = 0; k < 3; ++k) { sm.ray[k][tid] = lorg[k]; sm.ray[3 + k][tid] = ldir[k]; }
-                        make_wide_ray(lorg, ldir, sm.ray[6][tid], sm.ray[7][tid], w);
-                        const uint8_t* tp = blob + s.trees + static_cast<uint64_t>(meta.x) * sizeof(TreeDesc);
-                        const uint2 o_nodes = load8(tp + offsetof(TreeDesc, wnodes));
-                        const uint2 o_tris = load8(tp + offsetof(TreeDesc, wtris));
-                        const uint2 o_poses = load8(tp + offsetof(TreeDesc, poses));
-                        const uint32_t wnode_count = load4(tp + offsetof(TreeDesc, wnode_count));
-                        wnodes = blob + (static_cast<uint64_t>(o_nodes.x) | (static_cast<uint64_t>(o_nodes.y) << 32));
-                        sm.tri_base[tid] = static_cast<uint64_t>(o_tris.x) | (static_cast<uint64_t>(o_tris.y) << 32);
-                        sm.pose_base[tid] = static_cast<uint64_t>(o_poses.x) | (static_cast<uint64_t>(o_poses.y) << 32);
-                        sm.cur_item[tid] = item;
-                        cur_item = item;
-                        ngroup.y = 0; tgroup.y = 0;
-                        if (wnode_count != 0) fetch = 0;
-                    }
+                    if (args.enter_late) want_enter = true;     // performed below, with the other lanes of the warp that got here
+                    else enter_instance();
                 }
                 else
                 {
@@ -401,9 +453,7 @@ wide_kernel(const KernelArgs args)
                             {
                                 // Back to world space: the world ray comes from the ray arrays again.
                                 // (Candidates of the instance still in the queue carry all they need.)
-                                Ray world;
-                                load_ray_org_dir(args.rays, index, world);
-                                make_wide_ray(world.org, world.dir, sm.ray[6][tid], sm.ray[7][tid], w);
+                                restore_world_ray(args.rays, index, sm.ray[6][tid], sm.ray[7][tid], sm, tid, w);
                                 wnodes = blob + s.top_wnodes;
                                 cur_item = None;
                             }
@@ -424,7 +474,13 @@ wide_kernel(const KernelArgs args)
             if (args.prefetch && fetch != None) prefetch_node(wnodes + static_cast<uint64_t>(fetch) * sizeof(WNode));
         }
         if (round + 1 >= args.max_steps) break;
-        if (__popc(__ballot_sync(0xFFFFFFFFu, active && !traversed && !held && pending == 0)) < args.step_threshold) break;
+        if (__popc(__ballot_sync(0xFFFFFFFFu, active && !traversed && !held && !want_enter && pending == 0)) < args.step_threshold) break;
+        }
+
+        // ---- enter assembly instances: every lane that reached one in this iteration, together ------
+        if (__ballot_sync(0xFFFFFFFFu, want_enter) != 0)
+        {
+            if (want_enter) enter_instance();
         }
 
         // ---- gather this step's triangle candidates -------------------------------------------------
@@ -537,18 +593,19 @@ wide_kernel(const KernelArgs args)
 // prefer fuller refills and more steps per iteration; instanced scenes re-do the set-up on every
 // instance entry and prefer to refill earlier.  ASGPU_REFILL / ASGPU_FLUSH / ASGPU_STALL /
 // ASGPU_STEPS / ASGPU_STEPTHR / ASGPU_PREFETCH override them for experiments.
-struct Tuning { int refill, flush, stall, prefetch, steps, step_threshold; };
+struct Tuning { int refill, flush, stall, prefetch, steps, step_threshold, enter_late; };
 
 Tuning tuning(const bool single_instance)
 {
-    Tuning v = { 8, 16, 16, 0, 3, 8 };              // prefetch: measured neutral (C2) to -5 % (C3 probes), off
-    if (single_instance) { v.refill = 16; v.stall = 24; v.steps = 4; }
+    Tuning v = { 8, 16, 16, 0, 3, 8, 1 };              // prefetch: measured neutral (C2) to -5 % (C3 probes), off
+    if (single_instance) { v.refill = 16; v.stall = 24; v.steps = 4; v.enter_late = 0; }
     if (const char* e = getenv("ASGPU_REFILL")) v.refill = atoi(e);
     if (const char* e = getenv("ASGPU_FLUSH")) v.flush = atoi(e);
     if (const char* e = getenv("ASGPU_STALL")) v.stall = atoi(e);
     if (const char* e = getenv("ASGPU_PREFETCH")) v.prefetch = atoi(e);
     if (const char* e = getenv("ASGPU_STEPS")) v.steps = atoi(e);
     if (const char* e = getenv("ASGPU_STEPTHR")) v.step_threshold = atoi(e);
+    if (const char* e = getenv("ASGPU_ENTERLATE")) v.enter_late = atoi(e);
     if (v.refill < 1) v.refill = 1;
     if (v.flush < 1) v.flush = 1;
     if (v.stall < 1) v.stall = 1;
@@ -632,6 +689,7 @@ int launch_trace(
     args.prefetch = knobs.prefetch;
     args.max_steps = knobs.steps;
     args.step_threshold = knobs.step_threshold;
+    args.enter_late = knobs.enter_late;
 
     cudaError_t err = cudaMemsetAsync(queue, 0, sizeof(unsigned long long), stream);
     if (err != cudaSuccess) return static_cast<int>(err);

@@ -20,6 +20,7 @@
 #include "oracle_api.h"
 
 #include <algorithm>
+#include <cmath>
 #include <cstdint>
 #include <cstring>
 #include <limits>
@@ -453,6 +454,7 @@ struct TriTree
     std::vector<double>     node_bboxes;        // 6 doubles each: minx maxx miny maxy minz maxz
     std::vector<uint8_t>    leaf_data;
     std::vector<Key>        keys;
+    std::vector<float>      slot_tri;           // 9 floats per leaf slot: TriangleMT<float> of a static triangle (zeros if moving)
     size_t                  static_count = 0;
     size_t                  moving_count = 0;
     size_t                  undecided = 0;
@@ -691,7 +693,19 @@ void store_triangles(TriTree& tree, const std::vector<size_t>& order, const TriC
         if (is_interior(node)) continue;
         const size_t begin = node.index, count = node.item_count;
         node.index = static_cast<uint32_t>(tree.keys.size());
-        for (size_t j = 0; j < count; ++j) tree.keys.push_back(c.keys[order[begin + j]]);
+        for (size_t j = 0; j < count; ++j)
+        {
+            tree.keys.push_back(c.keys[order[begin + j]]);
+            const VertexInfo& info = c.infos[order[begin + j]];
+            float t[9] = { 0, 0, 0, 0, 0, 0, 0, 0, 0 };
+            if (info.msc == 0)
+            {
+                const V3f& v0 = c.vertices[info.vertex_index], &v1 = c.vertices[info.vertex_index + 1], &v2 = c.vertices[info.vertex_index + 2];
+                const float u[9] = { v0.x, v0.y, v0.z, v1.x - v0.x, v1.y - v0.y, v1.z - v0.z, v2.x - v0.x, v2.y - v0.y, v2.z - v0.z };
+                std::memcpy(t, u, 36);
+            }
+            tree.slot_tri.insert(tree.slot_tri.end(), t, t + 9);
+        }
         const size_t s = encoded_size(c, order, begin, count);
         uint8_t* user = reinterpret_cast<uint8_t*>(node.bbox);
         if (s <= 92)
@@ -1195,7 +1209,7 @@ struct WorldHit
 };
 
 template <Mode M>
-bool traverse_scene(const Scene& s, Ray& ray, WorldHit& wh, TwoBest* two, orc_counters& cnt)
+bool traverse_scene(const Scene& s, Ray& ray, WorldHit& wh, TwoBest* two, orc_counters& cnt, const orc_parent* parent = nullptr)
 {
     const RayInfo info(ray);
     const Node* stack[64];
@@ -1235,10 +1249,18 @@ bool traverse_scene(const Scene& s, Ray& ray, WorldHit& wh, TwoBest* two, orc_co
             if (!(item.vis_flags & ray.flags)) continue;
             ++cnt.instances_visited;
 
-            // compute_assembly_instance_ray (assemblytree.cpp:556-596), parent == nullptr.
+            // compute_assembly_instance_ray (assemblytree.cpp:556-596): inside the assembly instance
+            // that holds the parent's hit the origin is the parent's offset point
+            // (ShadingPoint::get_offset_point, shadingpoint.h:604-613), elsewhere the transformed origin.
             Ray local;
             local.dir = xform_vector_d(item.parent_to_local, ray.dir);
-            local.org = xform_point_d(item.parent_to_local, ray.org);
+            if (parent && parent->assembly_instance == item.assembly_instance)
+            {
+                const double d = 0.0 + parent->geo_normal[0] * local.dir.x + parent->geo_normal[1] * local.dir.y + parent->geo_normal[2] * local.dir.z;
+                const double* p = d > 0.0 ? parent->front : parent->back;
+                local.org.x = p[0]; local.org.y = p[1]; local.org.z = p[2];
+            }
+            else local.org = xform_point_d(item.parent_to_local, ray.org);
             local.tmin = ray.tmin;
             local.tmax = ray.tmax;
             local.time_absolute = ray.time_absolute;
@@ -1434,6 +1456,173 @@ void orc_two_nearest(const void* scene, const orc_rays* rays, size_t n, double* 
         }
     });
 }
+
+}   // extern "C" (reopened below)
+
+// ---------------------------------------------------------------------------------------------
+// ShadingPoint::refine_and_offset (shadingpoint.cpp:362-466), triangle branch with
+// RENDERER_ADAPTIVE_OFFSET (intersectionsettings.h:150); refine / adaptive_offset of
+// renderer/kernel/intersection/refining.h:97-221; TriangleMTSupportPlane::intersect
+// (raytrianglemt.h:300-309).  Vector / scalar is a multiplication by the reciprocal
+// (vector.h:638-642).
+// ---------------------------------------------------------------------------------------------
+
+namespace
+{
+
+inline double plane_intersect(const MTd& tri, const double org[3], const double dir[3])
+{
+    const double tvec[3] = { org[0] - tri.v0[0], org[1] - tri.v0[1], org[2] - tri.v0[2] };
+    double qvec[3], pvec[3];
+    cross3(tvec, tri.e0, qvec);
+    cross3(dir, tri.e1, pvec);
+    return dot3(tri.e1, qvec) / dot3(tri.e0, pvec);
+}
+
+inline void offset_step(const double p[3], const double n[3], const int64_t mag, double out[3])
+{
+    const double Threshold = 1.0e-25;
+    const int64_t eps_lut[2] = { mag, -mag };
+    for (int i = 0; i < 3; ++i)
+    {
+        if (std::fabs(p[i]) < Threshold) out[i] = p[i] + n[i] * Threshold;
+        else
+        {
+            uint64_t pi, ni;
+            std::memcpy(&pi, &p[i], 8); std::memcpy(&ni, &n[i], 8);
+            const uint64_t r = pi + static_cast<uint64_t>(eps_lut[(pi ^ ni) >> 63]);
+            std::memcpy(&out[i], &r, 8);
+        }
+    }
+}
+
+inline void offset_point(const MTd& tri, const double p[3], const double n[3], double out[3])
+{
+    int64_t mag = 8;
+    double result[3] = { p[0], p[1], p[2] };
+    for (int i = 0; i < 64; ++i)
+    {
+        double next[3];
+        offset_step(result, n, mag, next);
+        result[0] = next[0]; result[1] = next[1]; result[2] = next[2];
+        if (plane_intersect(tri, result, n) < 0.0) break;
+        mag *= 2;
+    }
+    out[0] = result[0]; out[1] = result[1]; out[2] = result[2];
+}
+
+void refine_offset_one(const Scene& s, const Ray& ray, const orc_hit& h, orc_parent& out)
+{
+    std::memset(&out, 0, sizeof(out));
+    out.assembly_instance = ~uint32_t(0);
+    if (h.prim_type != 2) return;
+    const orc_assembly_instance& ai = s.desc.assembly_instances[h.assembly_instance];
+    const orc_assembly& assembly = s.desc.assemblies[ai.assembly_index];
+    const TriTree& tree = *s.trees[s.assembly_tree[ai.assembly_index]];
+    out.assembly_instance = h.assembly_instance;
+
+    // refine_space_ray = m_assembly_instance_transform.to_local(m_ray); m_ray.m_tmax is the hit distance.
+    const V3d lo = xform_point_d(ai.parent_to_local, ray.org), ld = xform_vector_d(ai.parent_to_local, ray.dir);
+    const double dir[3] = { ld.x, ld.y, ld.z };
+    double p[3] = { lo.x + dir[0] * h.t, lo.y + dir[1] * h.t, lo.z + dir[2] * h.t };
+
+    MTd tri;
+    const float* f = tree.slot_tri.data() + size_t(h.tri_slot) * 9;
+    for (int i = 0; i < 3; ++i) { tri.v0[i] = f[i]; tri.e0[i] = f[3 + i]; tri.e1[i] = f[6 + i]; }
+
+    for (int step = 0; step < 2; ++step)
+    {
+        const double t = plane_intersect(tri, p, dir);
+        p[0] += dir[0] * t; p[1] += dir[1] * t; p[2] += dir[2] * t;
+    }
+
+    // Geometric normal from the source vertices (object space, float), to assembly space, facing the ray.
+    const orc_object_instance& oi = assembly.object_instances[h.object_instance_index];
+    const orc_mesh& mesh = s.desc.meshes[oi.mesh_index];
+    const uint32_t* t3 = mesh.triangles + size_t(h.primitive_index) * 3;
+    const V3f v0 = mesh_vertex(mesh, t3[0]), v1 = mesh_vertex(mesh, t3[1]), v2 = mesh_vertex(mesh, t3[2]);
+    const float a[3] = { v1.x - v0.x, v1.y - v0.y, v1.z - v0.z }, b[3] = { v2.x - v0.x, v2.y - v0.y, v2.z - v0.z };
+    const float nf[3] = { a[1] * b[2] - b[1] * a[2], a[2] * b[0] - b[2] * a[0], a[0] * b[1] - b[0] * a[1] };
+    const double nd[3] = { nf[0], nf[1], nf[2] };
+    const double* m = oi.parent_to_local;
+    double n[3] = { m[0] * nd[0] + m[4] * nd[1] + m[8] * nd[2], m[1] * nd[0] + m[5] * nd[1] + m[9] * nd[2], m[2] * nd[0] + m[6] * nd[1] + m[10] * nd[2] };
+    if (!(dot3(n, dir) < 0.0)) { n[0] = -n[0]; n[1] = -n[1]; n[2] = -n[2]; }
+    out.geo_normal[0] = n[0]; out.geo_normal[1] = n[1]; out.geo_normal[2] = n[2];
+
+    // adaptive_offset: n = normalize(n) = n * (1 / norm).
+    const double rcp = 1.0 / std::sqrt(dot3(n, n));
+    const double un[3] = { n[0] * rcp, n[1] * rcp, n[2] * rcp }, mn[3] = { -un[0], -un[1], -un[2] };
+    offset_point(tri, p, un, out.front);
+    offset_point(tri, p, mn, out.back);
+}
+
+}   // namespace
+
+extern "C" {
+
+void orc_refine_offset(const void* scene, const orc_rays* rays, const orc_hit* hits, size_t n, orc_parent* out, int threads)
+{
+    const Scene& s = *static_cast<const Scene*>(scene);
+    parallel_ranges(n, threads, [&](int, size_t begin, size_t end)
+    {
+        for (size_t i = begin; i < end; ++i)
+        {
+            Ray ray; load_ray(*rays, i, ray);
+            refine_offset_one(s, ray, hits[i], out[i]);
+        }
+    });
+}
+
+void orc_trace_parents(const void* scene, const orc_rays* rays, const orc_parent* parents, size_t n, orc_hit* out, int threads)
+{
+    const Scene& s = *static_cast<const Scene*>(scene);
+    parallel_ranges(n, threads, [&](int, size_t begin, size_t end)
+    {
+        orc_counters local; std::memset(&local, 0, sizeof(local));
+        for (size_t i = begin; i < end; ++i)
+        {
+            Ray ray; load_ray(*rays, i, ray);
+            WorldHit wh;
+            const orc_parent* parent = parents[i].assembly_instance != ~uint32_t(0) ? &parents[i] : nullptr;
+            traverse_scene<ClosestHit>(s, ray, wh, nullptr, local, parent);
+            orc_hit& h = out[i];
+            std::memset(&h, 0, sizeof(h));
+            h.t = ray.tmax;
+            h.assembly_instance = ~uint32_t(0);
+            if (wh.hit)
+            {
+                const Key& key = s.trees[wh.tree]->keys[wh.slot];
+                h.u = wh.u; h.v = wh.v;
+                h.assembly_instance = wh.assembly_instance;
+                h.object_instance_index = key.object_instance_index;
+                h.primitive_index = key.triangle_index;
+                h.tri_slot = wh.slot;
+                h.motion_segment = wh.motion_segment;
+                h.prim_type = 2;
+            }
+        }
+    });
+}
+
+void orc_trace_probe_parents(const void* scene, const orc_rays* rays, const orc_parent* parents, size_t n, uint8_t* out, int threads)
+{
+    const Scene& s = *static_cast<const Scene*>(scene);
+    parallel_ranges(n, threads, [&](int, size_t begin, size_t end)
+    {
+        orc_counters local; std::memset(&local, 0, sizeof(local));
+        for (size_t i = begin; i < end; ++i)
+        {
+            Ray ray; load_ray(*rays, i, ray);
+            WorldHit wh;
+            const orc_parent* parent = parents[i].assembly_instance != ~uint32_t(0) ? &parents[i] : nullptr;
+            out[i] = traverse_scene<AnyHit>(s, ray, wh, nullptr, local, parent) ? 1 : 0;
+        }
+    });
+}
+
+}   // extern "C"
+
+extern "C" {
 
 static void make_mt(const double v0[3], const double v1[3], const double v2[3], MTd& tri)
 {

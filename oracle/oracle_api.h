@@ -130,6 +130,18 @@ typedef struct orc_counters {
     uint64_t        hits;
 } orc_counters;
 
+/* What Intersector::trace reads of the PARENT ShadingPoint (intersector.cpp:145-149,
+ * assemblytree.cpp:556-596): the assembly instance that holds the previous hit and the refined,
+ * offset points of ShadingPoint::refine_and_offset (shadingpoint.cpp:362-466, triangle branch,
+ * RENDERER_ADAPTIVE_OFFSET) in that instance's space. */
+typedef struct orc_parent {
+    uint32_t        assembly_instance;      /* 0xFFFFFFFF = no parent (parent_shading_point == nullptr) */
+    uint32_t        reserved;
+    double          front[3];               /* m_refine_space_front_point */
+    double          back[3];                /* m_refine_space_back_point */
+    double          geo_normal[3];          /* m_refine_space_geo_normal (face-forwarded, not unit length) */
+} orc_parent;
+
 #define ORC_DECLARE(prefix)                                                                         \
     void*   prefix##_scene_create(const orc_scene_desc* desc);                                      \
     void    prefix##_scene_destroy(void* scene);                                                    \
@@ -140,7 +152,15 @@ typedef struct orc_counters {
     void    prefix##_trace(const void* scene, const orc_rays* rays, size_t n, orc_hit* out,         \
                            int threads, orc_counters* counters);                                    \
     void    prefix##_trace_probe(const void* scene, const orc_rays* rays, size_t n, uint8_t* out,   \
-                                 int threads, orc_counters* counters);
+                                 int threads, orc_counters* counters);                              \
+    /* rays = the rays that produced `hits` (world space); static triangles only. */                \
+    void    prefix##_refine_offset(const void* scene, const orc_rays* rays, const orc_hit* hits,    \
+                                   size_t n, orc_parent* out, int threads);                         \
+    /* trace / trace_probe with a parent shading point per ray. */                                  \
+    void    prefix##_trace_parents(const void* scene, const orc_rays* rays,                         \
+                                   const orc_parent* parents, size_t n, orc_hit* out, int threads); \
+    void    prefix##_trace_probe_parents(const void* scene, const orc_rays* rays,                   \
+                                   const orc_parent* parents, size_t n, uint8_t* out, int threads);
 
 ORC_DECLARE(orc)
 ORC_DECLARE(asref)

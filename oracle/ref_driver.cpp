@@ -30,6 +30,9 @@
 #include "foundation/math/transform.h"
 #include "foundation/math/vector.h"
 #include "foundation/memory/alignedallocator.h"
+#include "foundation/utility/casts.h"
+#include "renderer/kernel/intersection/refining.h"
+#include "renderer/utility/triangle.h"
 
 #include "oracle_api.h"
 
@@ -118,6 +121,7 @@ class RefTriangleTree
 
     std::vector<TriangleKey>    m_triangle_keys;
     std::vector<std::uint8_t>   m_leaf_data;
+    std::vector<GTriangleType>  m_slot_triangles;       // per leaf slot: the static triangle the leaf stores (checker convenience)
     size_t                      m_static_triangle_count = 0;
     size_t                      m_moving_triangle_count = 0;
 
@@ -602,7 +606,15 @@ class RefTriangleTree
                 node.set_item_index(m_triangle_keys.size());
 
                 for (size_t j = 0; j < item_count; ++j)
+                {
                     m_triangle_keys.push_back(triangle_keys[triangle_indices[item_begin + j]]);
+                    const TriangleVertexInfo& info = triangle_vertex_infos[triangle_indices[item_begin + j]];
+                    GTriangleType triangle;
+                    triangle.m_v0 = triangle.m_e0 = triangle.m_e1 = GVector3(0.0f);
+                    if (info.m_motion_segment_count == 0)
+                        triangle = GTriangleType(triangle_vertices[info.m_vertex_index], triangle_vertices[info.m_vertex_index + 1], triangle_vertices[info.m_vertex_index + 2]);
+                    m_slot_triangles.push_back(triangle);
+                }
 
                 const size_t leaf_size =
                     encoded_size(triangle_vertex_infos, triangle_indices, item_begin, item_count);
@@ -997,14 +1009,23 @@ class RefAssemblyTree
     }
 };
 
-// compute_assembly_instance_ray (assemblytree.cpp:556-596), parent_sp == nullptr branch.
+// compute_assembly_instance_ray (assemblytree.cpp:556-596).  `parent` stands for parent_sp: its
+// assembly instance uid, and get_offset_point (shadingpoint.h:604-613) over the refined points.
 inline void compute_assembly_instance_ray(
     const Transformd&       transform,
+    const std::uint32_t     assembly_instance,
+    const orc_parent*       parent,
     const RefShadingRay&    input_ray,
     RefShadingRay&          output_ray)
 {
     output_ray.m_dir = transform.vector_to_local(input_ray.m_dir);
-    output_ray.m_org = transform.point_to_local(input_ray.m_org);
+    if (parent && parent->assembly_instance == assembly_instance)
+    {
+        const Vector3d geo_normal(parent->geo_normal[0], parent->geo_normal[1], parent->geo_normal[2]);
+        const double* p = dot(geo_normal, output_ray.m_dir) > 0.0 ? parent->front : parent->back;
+        output_ray.m_org = Vector3d(p[0], p[1], p[2]);
+    }
+    else output_ray.m_org = transform.point_to_local(input_ray.m_org);
     output_ray.m_tmin = input_ray.m_tmin;
     output_ray.m_tmax = input_ray.m_tmax;
     output_ray.m_time_absolute = input_ray.m_time_absolute;
@@ -1021,6 +1042,7 @@ struct AsmLeafVisitor
     RefShadingPoint&        m_shading_point;
     const RefAssemblyTree&  m_tree;
     orc_counters*           m_counters;
+    const orc_parent*       m_parent = nullptr;
 
     bool visit(
         const NodeType&         node,
@@ -1042,7 +1064,7 @@ struct AsmLeafVisitor
             ++m_counters->instances_visited;
 
             RefShadingPoint asm_inst_shading_point;
-            compute_assembly_instance_ray(item.m_transform, ray, asm_inst_shading_point.m_ray);
+            compute_assembly_instance_ray(item.m_transform, item.m_assembly_instance, m_parent, ray, asm_inst_shading_point.m_ray);
             const RayInfo3d asm_inst_ray_info(asm_inst_shading_point.m_ray);
 
             if (item.m_tree != ~std::uint32_t(0))
@@ -1095,6 +1117,7 @@ struct AsmLeafProbeVisitor
     const RefAssemblyTree&  m_tree;
     orc_counters*           m_counters;
     bool                    m_hit = false;
+    const orc_parent*       m_parent = nullptr;
 
     bool visit(
         const NodeType&         node,
@@ -1115,7 +1138,7 @@ struct AsmLeafProbeVisitor
             ++m_counters->instances_visited;
 
             RefShadingRay asm_inst_ray;
-            compute_assembly_instance_ray(item.m_transform, ray, asm_inst_ray);
+            compute_assembly_instance_ray(item.m_transform, item.m_assembly_instance, m_parent, ray, asm_inst_ray);
             const RayInfo3d asm_inst_ray_info(asm_inst_ray);
 
             if (item.m_tree != ~std::uint32_t(0))
@@ -1330,6 +1353,118 @@ void asref_trace_probe(const void* scene_, const orc_rays* rays, size_t n, uint8
     });
 
     accumulate(counters, parts);
+}
+
+// ShadingPoint::refine_and_offset (shadingpoint.cpp:362-425), triangle branch, calling the
+// reference's own refine() / adaptive_offset() (renderer/kernel/intersection/refining.h),
+// TriangleMTSupportPlane, compute_triangle_normal, Transform::normal_to_parent and faceforward.
+void asref_refine_offset(const void* scene_, const orc_rays* rays, const orc_hit* hits, size_t n, orc_parent* out, int threads)
+{
+    const RefScene& scene = *static_cast<const RefScene*>(scene_);
+    const orc_scene_desc& desc = scene.m_desc;
+    parallel_ranges(n, threads, [&](int, size_t begin, size_t end)
+    {
+        for (size_t i = begin; i < end; ++i)
+        {
+            orc_parent& p = out[i];
+            std::memset(&p, 0, sizeof(p));
+            p.assembly_instance = ~std::uint32_t(0);
+            const orc_hit& hit = hits[i];
+            if (hit.prim_type != 2) continue;
+            p.assembly_instance = hit.assembly_instance;
+
+            RefShadingRay m_ray;
+            load_ray(*rays, i, m_ray);
+            m_ray.m_tmax = hit.t;
+
+            const orc_assembly_instance& inst = desc.assembly_instances[hit.assembly_instance];
+            const orc_assembly& assembly = desc.assemblies[inst.assembly_index];
+            const Transformd assembly_instance_transform = make_transform(inst.local_to_parent, inst.parent_to_local);
+            const RefTriangleTree& tree = *scene.m_assembly_tree.m_triangle_trees[scene.m_assembly_tree.m_assembly_tree_index[inst.assembly_index]];
+
+            // m_triangle_support_plane.initialize(TriangleType(triangle)) (triangletree.cpp:1483-1499).
+            const TriangleMTSupportPlane<double> support_plane{TriangleType(tree.m_slot_triangles[hit.tri_slot])};
+
+            // Source geometry (fetch_triangle_source_geometry, shadingpoint.cpp:186-256, static mesh).
+            const orc_object_instance& oi = assembly.object_instances[hit.object_instance_index];
+            const orc_mesh& mesh = desc.meshes[oi.mesh_index];
+            const std::uint32_t* t3 = mesh.triangles + size_t(hit.primitive_index) * 3;
+            const GVector3 v0(mesh.vertices[t3[0] * 3], mesh.vertices[t3[0] * 3 + 1], mesh.vertices[t3[0] * 3 + 2]);
+            const GVector3 v1(mesh.vertices[t3[1] * 3], mesh.vertices[t3[1] * 3 + 1], mesh.vertices[t3[1] * 3 + 2]);
+            const GVector3 v2(mesh.vertices[t3[2] * 3], mesh.vertices[t3[2] * 3 + 1], mesh.vertices[t3[2] * 3 + 2]);
+            const Transformd object_instance_transform = make_transform(oi.local_to_parent, oi.parent_to_local);
+
+            Ray3d refine_space_ray = assembly_instance_transform.to_local(static_cast<const Ray3d&>(m_ray));
+            refine_space_ray.m_org += refine_space_ray.m_tmax * refine_space_ray.m_dir;
+
+            const auto intersection_handling = [&support_plane](const Vector3d& pt, const Vector3d& nn)
+            {
+                return support_plane.intersect(pt, nn);
+            };
+
+            refine_space_ray.m_org = renderer::refine(refine_space_ray.m_org, refine_space_ray.m_dir, intersection_handling);
+
+            Vector3d geo_normal = Vector3d(renderer::compute_triangle_normal(v0, v1, v2));
+            geo_normal = object_instance_transform.normal_to_parent(geo_normal);
+            geo_normal = faceforward(geo_normal, refine_space_ray.m_dir);
+
+            Vector3d front, back;
+            renderer::adaptive_offset(refine_space_ray.m_org, geo_normal, front, back, intersection_handling);
+
+            for (int k = 0; k < 3; ++k) { p.front[k] = front[k]; p.back[k] = back[k]; p.geo_normal[k] = geo_normal[k]; }
+        }
+    });
+}
+
+void asref_trace_parents(const void* scene_, const orc_rays* rays, const orc_parent* parents, size_t n, orc_hit* out, int threads)
+{
+    const RefScene& scene = *static_cast<const RefScene*>(scene_);
+    parallel_ranges(n, threads, [&](int, size_t begin, size_t end)
+    {
+        orc_counters local;
+        std::memset(&local, 0, sizeof(local));
+        for (size_t i = begin; i < end; ++i)
+        {
+            RefShadingPoint shading_point;
+            load_ray(*rays, i, shading_point.m_ray);
+            const RayInfo3d ray_info(shading_point.m_ray);
+            AssemblyTreeIntersector intersector;
+            AsmLeafVisitor visitor{shading_point, scene.m_assembly_tree, &local,
+                                   parents[i].assembly_instance != ~std::uint32_t(0) ? &parents[i] : nullptr};
+            intersector.intersect_no_motion(scene.m_assembly_tree, shading_point.m_ray, ray_info, visitor);
+            orc_hit& hit = out[i];
+            hit.t = shading_point.m_ray.m_tmax;
+            hit.u = shading_point.m_hit ? shading_point.m_bary[0] : 0.0f;
+            hit.v = shading_point.m_hit ? shading_point.m_bary[1] : 0.0f;
+            hit.assembly_instance = shading_point.m_hit ? shading_point.m_assembly_instance : ~std::uint32_t(0);
+            hit.object_instance_index = shading_point.m_hit ? shading_point.m_object_instance_index : 0;
+            hit.primitive_index = shading_point.m_hit ? shading_point.m_primitive_index : 0;
+            hit.tri_slot = shading_point.m_hit ? shading_point.m_tri_slot : 0;
+            hit.motion_segment = shading_point.m_hit ? shading_point.m_motion_segment : 0;
+            hit.prim_type = shading_point.m_hit ? 2 : 0;
+        }
+    });
+}
+
+void asref_trace_probe_parents(const void* scene_, const orc_rays* rays, const orc_parent* parents, size_t n, uint8_t* out, int threads)
+{
+    const RefScene& scene = *static_cast<const RefScene*>(scene_);
+    parallel_ranges(n, threads, [&](int, size_t begin, size_t end)
+    {
+        orc_counters local;
+        std::memset(&local, 0, sizeof(local));
+        for (size_t i = begin; i < end; ++i)
+        {
+            RefShadingRay ray;
+            load_ray(*rays, i, ray);
+            const RayInfo3d ray_info(ray);
+            AssemblyTreeProbeIntersector intersector;
+            AsmLeafProbeVisitor visitor{scene.m_assembly_tree, &local, false,
+                                        parents[i].assembly_instance != ~std::uint32_t(0) ? &parents[i] : nullptr};
+            intersector.intersect_no_motion(scene.m_assembly_tree, ray, ray_info, visitor);
+            out[i] = visitor.m_hit ? 1 : 0;
+        }
+    });
 }
 
 int asref_kat_ray_triangle(
