@@ -23,6 +23,8 @@ EXPORTS = [
     "asgpu_scene_get_info",
     "asgpu_trace", "asgpu_trace_probe", "asgpu_trace_host", "asgpu_trace_probe_host",
     "asgpu_get_counters", "asgpu_last_error", "asgpu_version", "asgpu_sort_rays",
+    "asgpu_trees_get_source_geometry", "asgpu_scene_create_ex", "asgpu_refine_and_offset",
+    "asgpu_trace_with_parents", "asgpu_trace_probe_with_parents",
     "asgpu_queue_create", "asgpu_queue_destroy", "asgpu_queue_capacity", "asgpu_queue_device_arrays",
     "asgpu_queue_reset", "asgpu_queue_count", "asgpu_queue_push_host", "asgpu_trace_queue", "asgpu_trace_probe_queue",
     "asgpu_path_stream_create", "asgpu_path_stream_destroy", "asgpu_path_stream_tile_count", "asgpu_path_stream_render",
@@ -55,6 +57,10 @@ class AssemblyItem(C.Structure):
 
 class AssemblyTreeView(C.Structure):
     _fields_ = [("nodes", C.c_void_p), ("items", C.POINTER(AssemblyItem)), ("node_count", C.c_uint64), ("item_count", C.c_uint64)]
+
+
+class SourceGeometry(C.Structure):
+    _fields_ = [("objects", C.c_void_p), ("object_count", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class SceneInfo(C.Structure):
@@ -143,6 +149,12 @@ def load() -> C.CDLL:
     lib.asgpu_trace_host.argtypes = [C.c_void_p, P(CRays), C.c_size_t, C.c_void_p, C.c_uint32]
     lib.asgpu_trace_probe_host.argtypes = [C.c_void_p, P(CRays), C.c_size_t, C.c_void_p, C.c_uint32]
     lib.asgpu_get_counters.argtypes = [C.c_void_p, P(Counters), C.c_int]
+    lib.asgpu_trees_get_source_geometry.argtypes = [C.c_void_p, C.c_int, P(SourceGeometry)]
+    lib.asgpu_scene_create_ex.restype = C.c_void_p
+    lib.asgpu_scene_create_ex.argtypes = [P(TriangleTreeView), C.c_uint32, P(AssemblyTreeView), P(SourceGeometry), C.c_uint32, C.c_int]
+    lib.asgpu_refine_and_offset.argtypes = [C.c_void_p, P(CRays), C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+    lib.asgpu_trace_with_parents.argtypes = [C.c_void_p, P(CRays), C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint32, C.c_void_p]
+    lib.asgpu_trace_probe_with_parents.argtypes = [C.c_void_p, P(CRays), C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint32, C.c_void_p]
     lib.asgpu_sort_rays.argtypes = [C.c_void_p, P(CRays), C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.asgpu_queue_create.restype = C.c_void_p
     lib.asgpu_queue_create.argtypes = [C.c_void_p, C.c_size_t]

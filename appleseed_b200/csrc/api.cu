@@ -65,6 +65,12 @@ void make_view(asgpu_scene* s)
     s->view.top_node_count = s->header.top_node_count;
     s->view.top_wnode_count = s->header.top_wnode_count;
     s->view.wide_stack_need = s->header.wide_stack_need;
+    // Source geometry present for every tree?  (Small table: read it back.)
+    s->has_source = s->header.tree_count != 0;
+    std::vector<TreeDesc> descs(s->header.tree_count);
+    if (!descs.empty() && cudaMemcpy(descs.data(), s->blob + s->header.trees, descs.size() * sizeof(TreeDesc), cudaMemcpyDeviceToHost) != cudaSuccess)
+        s->has_source = false;
+    for (const TreeDesc& d : descs) if (d.src_objects == 0) s->has_source = false;
 }
 
 int init_device_side(asgpu_scene* s)
@@ -127,7 +133,7 @@ int check_trace_args(asgpu_scene* scene, const asgpu_rays* rays, const size_t n,
 }
 
 int trace_device(asgpu_scene* scene, const asgpu_rays* rays, const size_t n, asgpu_hit* hits, uint8_t* occluded,
-                 const bool any_hit, const uint32_t flags, unsigned long long* queue, void* stream)
+                 const bool any_hit, const uint32_t flags, unsigned long long* queue, void* stream, const asgpu_parent* parents = nullptr)
 {
     bool wide = true;
     const int rc = check_trace_args(scene, rays, n, any_hit ? static_cast<const void*>(occluded) : static_cast<const void*>(hits), flags, wide);
@@ -145,7 +151,8 @@ int trace_device(asgpu_scene* scene, const asgpu_rays* rays, const size_t n, asg
         order = scene->sort.order;
     }
     const int err = launch_trace(scene->view, *rays, n, hits, occluded, any_hit, wide, queue,
-                                 (flags & ASGPU_TRACE_COUNTERS) ? scene->counters : nullptr, order, scene->sm_count, stream);
+                                 (flags & ASGPU_TRACE_COUNTERS) ? scene->counters : nullptr, order, scene->sm_count, stream,
+                                 nullptr, false, parents);
     if (err != 0) return fail_cuda(static_cast<cudaError_t>(err), "kernel launch");
     ++scene->launches;
     return ASGPU_OK;
@@ -224,6 +231,27 @@ int asgpu::ensure_sort_scratch(asgpu_scene* scene, const size_t n)
     ASGPU_CUDA(cudaMalloc(&scene->sort.ws, ray_sort_workspace_bytes(n)), "cudaMalloc(sort workspace)");
     ASGPU_CUDA(cudaMalloc(&scene->sort.order, n * sizeof(uint32_t)), "cudaMalloc(sort order)");
     scene->sort.capacity = n;
+    return ASGPU_OK;
+}
+
+int asgpu::ensure_id_table(asgpu_scene* scene)
+{
+    if (scene->id_to_item) return ASGPU_OK;
+    std::vector<ItemRecord> items(scene->header.item_count);
+    if (items.empty()) return fail(ASGPU_E_INVALID, "scene without assembly instances");
+    ASGPU_CUDA(cudaMemcpy(items.data(), scene->blob + scene->header.items, items.size() * sizeof(ItemRecord), cudaMemcpyDeviceToHost), "cudaMemcpy(items)");
+    uint32_t max_id = 0;
+    for (const ItemRecord& it : items) max_id = std::max(max_id, it.assembly_instance);
+    if (max_id >= (1u << 24)) return fail(ASGPU_E_UNSUPPORTED, "assembly-instance ids above 2^24 - 1");
+    std::vector<uint32_t> table(size_t(max_id) + 1, 0xFFFFFFFFu);
+    for (size_t i = 0; i < items.size(); ++i)
+    {
+        if (table[items[i].assembly_instance] != 0xFFFFFFFFu) return fail(ASGPU_E_INVALID, "assembly-instance ids are not unique");
+        table[items[i].assembly_instance] = static_cast<uint32_t>(i);
+    }
+    ASGPU_CUDA(cudaMalloc(&scene->id_to_item, table.size() * 4), "cudaMalloc(id table)");
+    ASGPU_CUDA(cudaMemcpy(scene->id_to_item, table.data(), table.size() * 4, cudaMemcpyHostToDevice), "cudaMemcpy(id table)");
+    scene->id_count = static_cast<uint32_t>(table.size());
     return ASGPU_OK;
 }
 
@@ -307,6 +335,17 @@ int asgpu_trees_get_assembly_tree(const asgpu_trees* trees, asgpu_assembly_tree_
 
 double asgpu_trees_build_seconds(const asgpu_trees* trees) { return trees ? trees->trees.build_seconds : 0.0; }
 
+int asgpu_trees_get_source_geometry(const asgpu_trees* trees, int index, asgpu_source_geometry* out)
+{
+    if (!trees || !out) return fail(ASGPU_E_INVALID, "null argument");
+    if (index < 0 || index >= static_cast<int>(trees->trees.triangle_trees.size())) return fail(ASGPU_E_INVALID, "triangle tree index out of range");
+    const HostTriangleTree& t = *trees->trees.triangle_trees[index];
+    out->objects = t.source_objects.empty() ? nullptr : t.source_objects.data();
+    out->object_count = static_cast<uint32_t>(t.source_objects.size());
+    out->reserved = 0;
+    return ASGPU_OK;
+}
+
 // ---- GPU scene ----------------------------------------------------------------------------
 
 asgpu_scene* asgpu_scene_create(
@@ -316,11 +355,22 @@ asgpu_scene* asgpu_scene_create(
     uint32_t                        flags,
     int                             device)
 {
+    return asgpu_scene_create_ex(triangle_trees, triangle_tree_count, assembly_tree, nullptr, flags, device);
+}
+
+asgpu_scene* asgpu_scene_create_ex(
+    const asgpu_triangle_tree_view* triangle_trees,
+    uint32_t                        triangle_tree_count,
+    const asgpu_assembly_tree_view* assembly_tree,
+    const asgpu_source_geometry*    sources,
+    uint32_t                        flags,
+    int                             device)
+{
     if (!assembly_tree) { fail(ASGPU_E_INVALID, "null assembly tree"); return nullptr; }
     std::vector<uint8_t> image;
     std::string error;
     int rc;
-    try { rc = flatten_scene(triangle_trees, triangle_tree_count, *assembly_tree, flags ? flags : ASGPU_SCENE_DEFAULT, image, error); }
+    try { rc = flatten_scene(triangle_trees, triangle_tree_count, *assembly_tree, sources, flags ? flags : ASGPU_SCENE_DEFAULT, image, error); }
     catch (const std::exception& e) { rc = ASGPU_E_NOMEM; error = e.what(); }
     if (rc != ASGPU_OK) { fail(rc, error); return nullptr; }
     return adopt_blob_image(image, device);
@@ -331,10 +381,16 @@ asgpu_scene* asgpu_scene_create_from_desc(const asgpu_scene_desc* desc, uint32_t
     asgpu_trees* trees = asgpu_trees_build(desc, threads);
     if (!trees) return nullptr;
     std::vector<asgpu_triangle_tree_view> views(trees->trees.triangle_trees.size());
-    for (size_t i = 0; i < views.size(); ++i) asgpu_trees_get_triangle_tree(trees, static_cast<int>(i), &views[i]);
+    std::vector<asgpu_source_geometry> sources(views.size());
+    for (size_t i = 0; i < views.size(); ++i)
+    {
+        asgpu_trees_get_triangle_tree(trees, static_cast<int>(i), &views[i]);
+        asgpu_trees_get_source_geometry(trees, static_cast<int>(i), &sources[i]);
+    }
     asgpu_assembly_tree_view top;
     asgpu_trees_get_assembly_tree(trees, &top);
-    asgpu_scene* scene = asgpu_scene_create(views.empty() ? nullptr : views.data(), static_cast<uint32_t>(views.size()), &top, flags, device);
+    asgpu_scene* scene = asgpu_scene_create_ex(views.empty() ? nullptr : views.data(), static_cast<uint32_t>(views.size()), &top,
+                                               sources.empty() ? nullptr : sources.data(), flags, device);
     asgpu_trees_destroy(trees);
     return scene;
 }
@@ -349,6 +405,7 @@ void asgpu_scene_destroy(asgpu_scene* scene)
     cudaFree(scene->counters);
     cudaFree(scene->sort.ws);
     cudaFree(scene->sort.order);
+    cudaFree(scene->id_to_item);
     delete scene;
 }
 
@@ -433,6 +490,35 @@ int asgpu_trace_host(asgpu_scene* scene, const asgpu_rays* rays, size_t n, asgpu
 int asgpu_trace_probe_host(asgpu_scene* scene, const asgpu_rays* rays, size_t n, uint8_t* occluded, uint32_t flags)
 {
     return trace_host(scene, rays, n, nullptr, occluded, true, flags);
+}
+
+int asgpu_trace_with_parents(asgpu_scene* scene, const asgpu_rays* rays, const asgpu_parent* parents, size_t n, asgpu_hit* hits, uint32_t flags, void* stream)
+{
+    if (n != 0 && !parents) return fail(ASGPU_E_INVALID, "null parent array");
+    return trace_device(scene, rays, n, hits, nullptr, false, flags, scene ? scene->queue + (scene->queue_next++ % QueueRing) : nullptr, stream, parents);
+}
+
+int asgpu_trace_probe_with_parents(asgpu_scene* scene, const asgpu_rays* rays, const asgpu_parent* parents, size_t n, uint8_t* occluded, uint32_t flags, void* stream)
+{
+    if (n != 0 && !parents) return fail(ASGPU_E_INVALID, "null parent array");
+    return trace_device(scene, rays, n, nullptr, occluded, true, flags, scene ? scene->queue + (scene->queue_next++ % QueueRing) : nullptr, stream, parents);
+}
+
+int asgpu_refine_and_offset(asgpu_scene* scene, const asgpu_rays* rays, const asgpu_hit* hits, size_t n, asgpu_parent* parents, void* stream)
+{
+    if (!scene) return fail(ASGPU_E_INVALID, "null scene");
+    if (n == 0) return ASGPU_OK;
+    if (!rays || !rays->org || !rays->dir || !hits || !parents) return fail(ASGPU_E_INVALID, "null argument");
+    if (!(scene->header.flags & ASGPU_SCENE_EXACT)) return fail(ASGPU_E_INVALID, "refine_and_offset needs the per-slot triangle records of the exact layout");
+    if (!scene->has_source) return fail(ASGPU_E_INVALID, "the scene was created without source geometry (asgpu_scene_create_ex)");
+    if (scene->header.moving_triangle_count != 0) return fail(ASGPU_E_UNSUPPORTED, "refine_and_offset handles static triangles only");
+    ASGPU_CUDA(cudaSetDevice(scene->device), "cudaSetDevice");
+    const int rt = ensure_id_table(scene);
+    if (rt != ASGPU_OK) return rt;
+    const int err = launch_refine_offset(scene->view, *rays, hits, n, nullptr, false, scene->id_to_item, scene->id_count, parents, scene->sm_count, stream);
+    if (err != 0) return fail_cuda(static_cast<cudaError_t>(err), "kernel launch");
+    ++scene->launches;
+    return ASGPU_OK;
 }
 
 int asgpu_sort_rays(asgpu_scene* scene, const asgpu_rays* rays, size_t n, uint32_t* order, uint32_t* keys, void* stream)

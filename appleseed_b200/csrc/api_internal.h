@@ -71,10 +71,15 @@ struct asgpu_scene
     asgpu::Staging      staging[asgpu::HostStreams];
     bool                staging_ready = false;
     asgpu::SortScratch  sort;
+    bool                has_source = false;     // every triangle tree carries source geometry
+    uint32_t*           id_to_item = nullptr;   // device: caller's assembly-instance id -> ItemRecord index (built on demand)
+    uint32_t            id_count = 0;
 };
 
 namespace asgpu
 {
 // Makes sure scene->sort can take n rays (reallocates after synchronising the device).
 int ensure_sort_scratch(asgpu_scene* scene, size_t n);
+// Builds scene->id_to_item (needs unique instance ids below 2^24).
+int ensure_id_table(asgpu_scene* scene);
 }

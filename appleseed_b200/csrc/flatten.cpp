@@ -687,6 +687,7 @@ int flatten_scene(
     const asgpu_triangle_tree_view* trees,
     uint32_t                        tree_count,
     const asgpu_assembly_tree_view& top,
+    const asgpu_source_geometry*    sources,
     uint32_t                        flags,
     std::vector<uint8_t>&           blob,
     std::string&                    error)
@@ -742,6 +743,42 @@ int flatten_scene(
             header.binary_node_count += et.bnodes.size();
             header.binary_node_bytes += et.bnodes.size() * sizeof(BNodeF) + et.mnodes.size() * sizeof(MNode) + et.mboxes.size() * sizeof(MBox);
             header.triangle_bytes += et.tris.size() * sizeof(TriRecord);
+        }
+
+        if (sources && sources[ti].object_count != 0)
+        {
+            // Source geometry for the device-side refine_and_offset: packed copies of every object
+            // instance's vertices and vertex indices.
+            const asgpu_source_geometry& sg = sources[ti];
+            if (!sg.objects) { error = "null source object array"; return ASGPU_E_INVALID; }
+            std::vector<SrcObject> objs(sg.object_count);
+            for (uint32_t o = 0; o < sg.object_count; ++o)
+            {
+                const asgpu_source_object& so = sg.objects[o];
+                SrcObject& dst = objs[o];
+                std::memset(&dst, 0, sizeof(dst));
+                if ((so.vertex_count && !so.vertices) || (so.triangle_count && !so.triangles) || (so.triangle_count && so.triangle_stride < 12))
+                { error = "malformed source object"; return ASGPU_E_INVALID; }
+                for (int r = 0; r < 3; ++r)
+                    for (int c = 0; c < 3; ++c) dst.parent_to_local[r * 3 + c] = so.parent_to_local[r * 4 + c];
+                dst.vertex_count = so.vertex_count;
+                dst.triangle_count = so.triangle_count;
+                dst.vertices = writer.append(so.vertices, size_t(so.vertex_count) * 12);
+                std::vector<uint32_t> packed(size_t(so.triangle_count) * 3);
+                const uint8_t* src = static_cast<const uint8_t*>(so.triangles);
+                for (size_t t = 0; t < so.triangle_count; ++t)
+                {
+                    std::memcpy(&packed[t * 3], src + t * so.triangle_stride, 12);
+                    for (int k = 0; k < 3; ++k)
+                        if (packed[t * 3 + k] >= so.vertex_count) { error = "source triangle references a missing vertex"; return ASGPU_E_INVALID; }
+                }
+                dst.triangles = writer.append(packed);
+            }
+            for (const HitKey& key : et.keys)
+                if (key.object_instance_index >= sg.object_count || key.triangle_index >= objs[key.object_instance_index].triangle_count)
+                { error = "triangle key outside the source geometry"; return ASGPU_E_INVALID; }
+            d.src_objects = writer.append(objs);
+            d.src_object_count = sg.object_count;
         }
 
         if (want_wide)

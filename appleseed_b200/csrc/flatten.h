@@ -18,6 +18,7 @@ int flatten_scene(
     const asgpu_triangle_tree_view* trees,
     uint32_t                        tree_count,
     const asgpu_assembly_tree_view& top,
+    const asgpu_source_geometry*    sources,    // tree_count entries or nullptr
     uint32_t                        flags,
     std::vector<uint8_t>&           blob,
     std::string&                    error);

@@ -28,7 +28,7 @@ namespace asgpu
 {
 
 const uint32_t BlobMagic = 0x42534131u;     // "1ASB"
-const uint32_t BlobVersion = 4;
+const uint32_t BlobVersion = 5;
 const uint32_t WideStackMax = 64;           // deepest traversal stack any wide kernel variant offers
 const uint64_t SectionAlign = 256;
 
@@ -108,9 +108,23 @@ struct TreeDesc
     uint32_t    slot_count;
     uint32_t    moving;         // number of moving triangles
     uint32_t    mbox_count;
-    uint32_t    pad;
+    uint32_t    src_object_count;
+    uint64_t    src_objects;    // SrcObject[src_object_count] or 0: source geometry for refine_and_offset
 };
-static_assert(sizeof(TreeDesc) == 88, "TreeDesc");
+static_assert(sizeof(TreeDesc) == 96, "TreeDesc");
+
+// Source geometry of one object instance of an assembly (what ShadingPoint::
+// fetch_triangle_source_geometry reads, shadingpoint.cpp:186-256): object-space vertices, vertex
+// indices, and the rows of ObjectInstance's parent_to_local that Transform::normal_to_parent uses
+// (transform.h:446-463).
+struct SrcObject
+{
+    double      parent_to_local[9];     // m[0] m[1] m[2] / m[4] m[5] m[6] / m[8] m[9] m[10]
+    uint64_t    vertices;               // float[vertex_count * 3]
+    uint64_t    triangles;              // uint32_t[triangle_count * 3]
+    uint32_t    vertex_count, triangle_count;
+};
+static_assert(sizeof(SrcObject) == 96, "SrcObject");
 
 // One assembly-tree item (tree order): world -> instance rows of parent_to_local.
 struct ItemRecord

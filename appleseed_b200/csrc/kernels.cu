@@ -48,6 +48,7 @@ struct KernelArgs
     const uint32_t*     order;          // optional permutation: ray processed at position i is order[i]
     const unsigned long long* n_dev;    // optional: the ray count lives in device memory (wavefront queues)
     uint32_t            raw_item;           // hit records carry the ItemRecord index instead of the caller's instance id
+    const asgpu_parent* parents;        // optional parent shading point per ray (assemblytree.cpp:565-576)
     int                 refill_threshold;   // idle lanes that trigger a pull from the ray queue
     int                 flush_threshold;    // queued candidates that trigger a test batch
     int                 stall_threshold;    // lanes idle or waiting for the queue that trigger one
@@ -129,7 +130,8 @@ trace_kernel(const KernelArgs args)
             Ray ray;
             load_ray(args.rays, i, ray);
             Hit hit;
-            const bool found = exact_trace<ANY, COUNT>(args.scene, ray, hit, stats);
+            const bool found = exact_trace<ANY, COUNT>(args.scene, ray, hit, stats,
+                                                       args.parents ? reinterpret_cast<const uint8_t*>(args.parents + i) : nullptr);
             if (ANY) args.occluded[i] = found ? 1 : 0;
             else store_hit(args.hits + i, args.scene, ray.tmax, hit, found, args.raw_item != 0);
             if (COUNT) { ++rays_done; hits_found += found ? 1 : 0; }
@@ -337,6 +339,7 @@ wide_kernel(const KernelArgs args)
             load_ray_org_dir(args.rays, index, world);
             double lorg[3], ldir[3];
             instance_org_dir(ip, world.org, world.dir, lorg, ldir);
+            if (args.parents) parent_origin(reinterpret_cast<const uint8_t*>(args.parents + index), meta.z, ldir, lorg);
             #pragma unroll
             for (int k = 0; k < 3; ++k) { sm.ray[k][tid] = lorg[k]; sm.ray[3 + k][tid] = ldir[k]; }
             if (sp != 0)
@@ -667,7 +670,8 @@ int launch_trace(
     const int           sm_count,
     void*               stream_,
     const unsigned long long* n_dev,
-    const bool          raw_item)
+    const bool          raw_item,
+    const asgpu_parent* parents)
 {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     KernelArgs args;
@@ -681,6 +685,7 @@ int launch_trace(
     args.order = order;
     args.n_dev = n_dev;
     args.raw_item = raw_item ? 1u : 0u;
+    args.parents = parents;
     args.unit_bits = UnitBits;
     const Tuning knobs = tuning(scene.item_count <= 1);
     args.refill_threshold = knobs.refill;

@@ -25,7 +25,23 @@ int launch_trace(
     int                 sm_count,
     void*               stream,
     const unsigned long long* n_dev = nullptr,  // device: when set, the ray count is read from here (n = capacity bound)
-    bool                raw_item = false);      // hit records carry the ItemRecord index instead of the caller's instance id
+    bool                raw_item = false,       // hit records carry the ItemRecord index instead of the caller's instance id
+    const asgpu_parent* parents = nullptr);     // device: optional parent shading point per ray
+
+// ShadingPoint::refine_and_offset for n hits (refine.cu).  `raw_item`: hits carry ItemRecord
+// indices (wavefront launches); the parents written always carry the caller's instance id.
+int launch_refine_offset(
+    const SceneView&    scene,
+    const asgpu_rays&   rays,
+    const asgpu_hit*    hits,
+    size_t              n,
+    const unsigned long long* n_dev,
+    bool                raw_item,
+    const uint32_t*     id_to_item,     // device: caller's instance id -> ItemRecord index (unused for raw hits)
+    uint32_t            id_count,
+    asgpu_parent*       parents,
+    int                 sm_count,
+    void*               stream);
 
 // Coherence sort (sort.cu): fills `order` with the permutation that sorts the rays by their
 // origin / direction Morton key.  Returns a cudaError_t value.

@@ -233,6 +233,21 @@ ASGPU_HD void to_instance_space(const uint8_t* item, const Ray& world, Ray& loca
     local.flags = world.flags;
 }
 
+// compute_assembly_instance_ray with a parent shading point (assemblytree.cpp:565-576): inside the
+// assembly instance that holds the parent's hit, the child ray starts from the parent's offset
+// point -- front when dot(geo_normal, dir) > 0, else back (ShadingPoint::get_offset_point,
+// shadingpoint.h:604-613; dot accumulates from 0, vector.h:745-753).  `parent` points at this ray's
+// asgpu_parent record (80 bytes: id, pad, front, back, geo_normal) or is null.
+ASGPU_HD void parent_origin(const uint8_t* parent, const uint32_t assembly_instance, const double ldir[3], double lorg[3])
+{
+    if (parent == nullptr || load4(parent) != assembly_instance) return;
+    double d = dadd(0.0, dmul(load_f64(parent + 56), ldir[0]));
+    d = dadd(d, dmul(load_f64(parent + 64), ldir[1]));
+    d = dadd(d, dmul(load_f64(parent + 72), ldir[2]));
+    const uint8_t* src = parent + (d > 0.0 ? 8 : 32);
+    lorg[0] = load_f64(src); lorg[1] = load_f64(src + 8); lorg[2] = load_f64(src + 16);
+}
+
 // ------------------------------------------------------------------------------------------
 // Exact Moeller-Trumbore (raytrianglemt.h:148-268) on a float triangle widened to double
 // (raytrianglemt.h:139-146).  cross: vector.h:1239-1246; dot accumulates from 0: vector.h:745-753.
@@ -512,7 +527,7 @@ ASGPU_HD void load_tree_desc(const SceneView& s, const uint32_t tree, TreeDesc& 
 // Top level: generic scalar intersector + assembly leaf visitors.  On return ray.tmax is the hit
 // distance (closest hit).  Returns true when something was hit.
 template <bool ANY, bool COUNT>
-ASGPU_HD bool exact_trace(const SceneView& s, Ray& ray, Hit& hit, Stats& stats)
+ASGPU_HD bool exact_trace(const SceneView& s, Ray& ray, Hit& hit, Stats& stats, const uint8_t* parent = nullptr)
 {
     hit.item = 0xFFFFFFFFu; hit.slot = 0; hit.segment = 0; hit.u = hit.v = 0.0f;
     RayInfoD info; make_ray_info(ray, info);
@@ -563,6 +578,7 @@ ASGPU_HD bool exact_trace(const SceneView& s, Ray& ray, Hit& hit, Stats& stats)
             if (COUNT) ++stats.instances;
             Ray local;
             to_instance_space(ip, ray, local);
+            parent_origin(parent, meta.z, local.dir, local.org);
             if (meta.x == 0xFFFFFFFFu) continue;
             TreeDesc td; load_tree_desc(s, meta.x, td);
             const bool found = exact_triangle_tree<ANY, COUNT>(s.blob, td, local, hit, item, stats);

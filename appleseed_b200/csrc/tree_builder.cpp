@@ -907,6 +907,27 @@ bool build_host_trees(const asgpu_scene_desc& desc, int threads, HostTrees& out,
         out.triangle_trees.emplace_back(new HostTriangleTree());
         HostTriangleTree& tree = *out.triangle_trees.back();
 
+        // Source geometry (for the device-side refine_and_offset): private copies of the meshes.
+        if (out.mesh_vertices.empty()) { out.mesh_vertices.resize(desc.mesh_count); out.mesh_triangles.resize(desc.mesh_count); }
+        tree.source_objects.resize(assembly.object_instance_count);
+        for (uint32_t o = 0; o < assembly.object_instance_count; ++o)
+        {
+            const asgpu_object_instance& oi = assembly.object_instances[o];
+            const asgpu_mesh& mesh = desc.meshes[oi.mesh_index];
+            std::vector<float>& mv = out.mesh_vertices[oi.mesh_index];
+            std::vector<uint32_t>& mt = out.mesh_triangles[oi.mesh_index];
+            if (mv.empty() && mesh.vertex_count) mv.assign(mesh.vertices, mesh.vertices + size_t(mesh.vertex_count) * 3);
+            if (mt.empty() && mesh.triangle_count) mt.assign(mesh.triangles, mesh.triangles + size_t(mesh.triangle_count) * 3);
+            asgpu_source_object& so = tree.source_objects[o];
+            std::memset(&so, 0, sizeof(so));
+            so.vertices = mv.data();
+            so.triangles = mt.data();
+            so.vertex_count = mesh.vertex_count;
+            so.triangle_count = mesh.triangle_count;
+            so.triangle_stride = 12;
+            std::memcpy(so.parent_to_local, oi.parent_to_local, sizeof(so.parent_to_local));
+        }
+
         Collected c;
         collect(desc, assembly, ab, c);
         if (c.keys.size() >= 0xFFFFFFFFull) { error = "too many triangles in one assembly"; return false; }

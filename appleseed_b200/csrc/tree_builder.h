@@ -47,6 +47,8 @@ struct HostTriangleTree
     std::vector<AsTriangleKey>  keys;
     uint64_t                    static_triangle_count = 0;
     uint64_t                    moving_triangle_count = 0;
+    // Source geometry of the assembly's object instances (views into HostTrees::mesh_*).
+    std::vector<asgpu_source_object> source_objects;
 };
 
 struct HostAssemblyTree
@@ -60,6 +62,8 @@ struct HostTrees
     std::vector<std::unique_ptr<HostTriangleTree>>  triangle_trees;
     std::vector<int>                                assembly_to_tree;   // -1 = assembly without geometry
     HostAssemblyTree                                assembly_tree;
+    std::vector<std::vector<float>>                 mesh_vertices;      // copies of the static meshes (source geometry)
+    std::vector<std::vector<uint32_t>>              mesh_triangles;
     double                                          build_seconds = 0.0;
 };
 

@@ -22,7 +22,7 @@ from typing import Optional
 import numpy as np
 
 from . import _lib
-from .scene import HIT_DTYPE, CRays, RayBatch, SceneDesc
+from .scene import HIT_DTYPE, PARENT_DTYPE, CRays, RayBatch, SceneDesc
 
 HIT_BYTES = HIT_DTYPE.itemsize
 
@@ -64,6 +64,11 @@ class HostTrees:
     def triangle_tree_view(self, i: int) -> "_lib.TriangleTreeView":
         v = _lib.TriangleTreeView()
         _check(self.lib.asgpu_trees_get_triangle_tree(self.handle, i, C.byref(v)), "asgpu_trees_get_triangle_tree")
+        return v
+
+    def source_geometry(self, i: int) -> "_lib.SourceGeometry":
+        v = _lib.SourceGeometry()
+        _check(self.lib.asgpu_trees_get_source_geometry(self.handle, i, C.byref(v)), "asgpu_trees_get_source_geometry")
         return v
 
     def assembly_tree_view(self) -> "_lib.AssemblyTreeView":
@@ -151,7 +156,7 @@ class TraceContext:
     """Owns the flattened scene on one GPU."""
 
     def __init__(self, desc: Optional[SceneDesc] = None, device: int = 0, flags: int = _lib.SCENE_DEFAULT,
-                 threads: int = 0, trees: Optional[HostTrees] = None, _handle=None):
+                 threads: int = 0, trees: Optional[HostTrees] = None, _handle=None, source_geometry: bool = True):
         self.lib = _lib.load()
         self.device = device
         self._borrowed_blob = None
@@ -166,10 +171,12 @@ class TraceContext:
                 trees = HostTrees(desc, threads)
             n = trees.triangle_tree_count
             views = (_lib.TriangleTreeView * max(1, n))()
+            sources = (_lib.SourceGeometry * max(1, n))()
             for i in range(n):
                 views[i] = trees.triangle_tree_view(i)
+                sources[i] = trees.source_geometry(i)
             top = trees.assembly_tree_view()
-            self.handle = self.lib.asgpu_scene_create(views, n, C.byref(top), flags, device)
+            self.handle = self.lib.asgpu_scene_create_ex(views, n, C.byref(top), sources if source_geometry else None, flags, device)
             self.build_seconds = trees.build_seconds
             if own:
                 trees.close()
@@ -281,6 +288,63 @@ class Intersector:
         stream = torch.cuda.current_stream(self.ctx.device).cuda_stream
         _check(self.lib.asgpu_trace_probe(self.ctx.handle, C.byref(cr), n, occluded.data_ptr(), flags, C.c_void_p(stream)), "asgpu_trace_probe")
 
+
+    # -- parent shading points (refine_and_offset + the parent origin rule) ----------------------
+
+    def refine_and_offset_device(self, rays: DeviceRays, hits: "torch.Tensor", parents: "torch.Tensor"):
+        """``parents``: uint8 CUDA tensor of n * 80 bytes receiving ``asgpu_parent`` records."""
+        import torch
+        n = len(rays)
+        assert parents.numel() * parents.element_size() >= n * PARENT_DTYPE.itemsize
+        cr = rays.to_c()
+        stream = torch.cuda.current_stream(self.ctx.device).cuda_stream
+        _check(self.lib.asgpu_refine_and_offset(self.ctx.handle, C.byref(cr), hits.data_ptr(), n, parents.data_ptr(), C.c_void_p(stream)),
+               "asgpu_refine_and_offset")
+
+    def trace_with_parents_device(self, rays: DeviceRays, parents: "torch.Tensor", hits: "torch.Tensor", exact: bool = False):
+        import torch
+        cr = rays.to_c()
+        stream = torch.cuda.current_stream(self.ctx.device).cuda_stream
+        _check(self.lib.asgpu_trace_with_parents(self.ctx.handle, C.byref(cr), parents.data_ptr(), len(rays), hits.data_ptr(),
+                                                 self._flags(exact, False, False), C.c_void_p(stream)), "asgpu_trace_with_parents")
+
+    def trace_probe_with_parents_device(self, rays: DeviceRays, parents: "torch.Tensor", occluded: "torch.Tensor", exact: bool = False):
+        import torch
+        cr = rays.to_c()
+        stream = torch.cuda.current_stream(self.ctx.device).cuda_stream
+        _check(self.lib.asgpu_trace_probe_with_parents(self.ctx.handle, C.byref(cr), parents.data_ptr(), len(rays), occluded.data_ptr(),
+                                                       self._flags(exact, False, False), C.c_void_p(stream)), "asgpu_trace_probe_with_parents")
+
+    # Host-array conveniences over the three calls above (upload, run, download).
+    def refine_and_offset(self, rays: RayBatch, hits: np.ndarray) -> np.ndarray:
+        import torch
+        dev = "cuda:%d" % self.ctx.device
+        d = DeviceRays.from_host(rays, dev)
+        h = torch.from_numpy(np.ascontiguousarray(hits).view(np.uint8)).to(dev)
+        out = torch.empty(max(1, len(rays)) * PARENT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+        self.refine_and_offset_device(d, h, out)
+        torch.cuda.synchronize()
+        return out.cpu().numpy()[: len(rays) * PARENT_DTYPE.itemsize].view(PARENT_DTYPE).copy()
+
+    def trace_with_parents(self, rays: RayBatch, parents: np.ndarray, exact: bool = False) -> np.ndarray:
+        import torch
+        dev = "cuda:%d" % self.ctx.device
+        d = DeviceRays.from_host(rays, dev)
+        p = torch.from_numpy(np.ascontiguousarray(parents).view(np.uint8)).to(dev)
+        out = torch.empty(max(1, len(rays)) * HIT_BYTES, dtype=torch.uint8, device=dev)
+        self.trace_with_parents_device(d, p, out, exact=exact)
+        torch.cuda.synchronize()
+        return hits_from_tensor(out, len(rays))
+
+    def trace_probe_with_parents(self, rays: RayBatch, parents: np.ndarray, exact: bool = False) -> np.ndarray:
+        import torch
+        dev = "cuda:%d" % self.ctx.device
+        d = DeviceRays.from_host(rays, dev)
+        p = torch.from_numpy(np.ascontiguousarray(parents).view(np.uint8)).to(dev)
+        out = torch.empty(max(1, len(rays)), dtype=torch.uint8, device=dev)
+        self.trace_probe_with_parents_device(d, p, out, exact=exact)
+        torch.cuda.synchronize()
+        return out.cpu().numpy()[: len(rays)].copy()
 
     def sort_rays(self, rays: DeviceRays):
         """``asgpu_sort_rays``: (order, keys) int32 CUDA tensors -- the permutation by ascending

@@ -121,6 +121,12 @@ HIT_DTYPE = np.dtype(
 )
 assert HIT_DTYPE.itemsize == 40
 
+# asgpu_parent (include/asgpu.h): what Intersector::trace reads of the parent ShadingPoint.
+PARENT_DTYPE = np.dtype(
+    [("assembly_instance", np.uint32), ("reserved", np.uint32), ("front", np.float64, 3), ("back", np.float64, 3),
+     ("geo_normal", np.float64, 3)], align=True)
+assert PARENT_DTYPE.itemsize == 80
+
 
 def _mat(m) -> np.ndarray:
     m = np.ascontiguousarray(np.asarray(m, dtype=np.float64).reshape(4, 4))

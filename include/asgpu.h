@@ -146,6 +146,26 @@ typedef struct asgpu_assembly_tree_view {
     uint64_t        item_count;
 } asgpu_assembly_tree_view;
 
+/* Optional source geometry, one asgpu_source_geometry per triangle tree: what
+ * ShadingPoint::fetch_triangle_source_geometry (renderer/kernel/shading/shadingpoint.cpp:186-256)
+ * reads for a static mesh -- StaticTriangleTess::m_vertices / m_primitives and the ObjectInstance
+ * transform.  Only needed for asgpu_refine_and_offset. */
+typedef struct asgpu_source_object {
+    const float*    vertices;           /* vertex_count * 3, object space */
+    const void*     triangles;          /* triangle i: three uint32_t vertex indices at triangles + i * triangle_stride */
+    uint32_t        vertex_count;
+    uint32_t        triangle_count;
+    uint32_t        triangle_stride;    /* bytes: 12 for a packed index array, sizeof(renderer::Triangle) for m_primitives */
+    uint32_t        reserved;
+    double          parent_to_local[16];    /* ObjectInstance::get_transform().get_parent_to_local() */
+} asgpu_source_object;
+
+typedef struct asgpu_source_geometry {
+    const asgpu_source_object* objects; /* indexed by object_instance_index (TriangleKey) */
+    uint32_t        object_count;
+    uint32_t        reserved;
+} asgpu_source_geometry;
+
 /* ------------------------------------------------------------------------------------------
  * Host builder: the CPU side that defines the data (sweep-SAH binary BVHs identical to the ones
  * the reference builds).
@@ -159,6 +179,8 @@ int             asgpu_trees_triangle_tree_count(const asgpu_trees* trees);
 int             asgpu_trees_get_triangle_tree(const asgpu_trees* trees, int index, asgpu_triangle_tree_view* out);
 int             asgpu_trees_get_assembly_tree(const asgpu_trees* trees, asgpu_assembly_tree_view* out);
 double          asgpu_trees_build_seconds(const asgpu_trees* trees);
+/* Source geometry of triangle tree `index` (pointers into the handle's own copies). */
+int             asgpu_trees_get_source_geometry(const asgpu_trees* trees, int index, asgpu_source_geometry* out);
 
 /* ------------------------------------------------------------------------------------------
  * GPU scene.
@@ -179,7 +201,16 @@ asgpu_scene*    asgpu_scene_create(
                     uint32_t                        flags,
                     int                             device);
 
-/* Convenience: asgpu_trees_build + asgpu_scene_create. */
+/* Same with source geometry (`sources`: triangle_tree_count entries, or NULL = asgpu_scene_create). */
+asgpu_scene*    asgpu_scene_create_ex(
+                    const asgpu_triangle_tree_view* triangle_trees,
+                    uint32_t                        triangle_tree_count,
+                    const asgpu_assembly_tree_view* assembly_tree,
+                    const asgpu_source_geometry*    sources,
+                    uint32_t                        flags,
+                    int                             device);
+
+/* Convenience: asgpu_trees_build + asgpu_scene_create_ex (source geometry included). */
 asgpu_scene*    asgpu_scene_create_from_desc(const asgpu_scene_desc* desc, uint32_t flags, int device, int threads);
 
 void            asgpu_scene_destroy(asgpu_scene* scene);
@@ -254,6 +285,37 @@ int             asgpu_trace_probe(asgpu_scene* scene, const asgpu_rays* rays, si
  * the kernels; returns when the results are in `hits` / `occluded`. */
 int             asgpu_trace_host(asgpu_scene* scene, const asgpu_rays* rays, size_t n, asgpu_hit* hits, uint32_t flags);
 int             asgpu_trace_probe_host(asgpu_scene* scene, const asgpu_rays* rays, size_t n, uint8_t* occluded, uint32_t flags);
+
+/* ------------------------------------------------------------------------------------------
+ * Parent shading points.  Intersector::trace(ray, shading_point,
+ * parent) refines and offsets the parent's hit point once (ShadingPoint::refine_and_offset,
+ * shadingpoint.cpp:362-466: refine() and adaptive_offset() of renderer/kernel/intersection/
+ * refining.h:97-221 against the triangle's support plane) and, inside the assembly instance that
+ * holds the parent's hit, starts the child ray from the front or back point
+ * (compute_assembly_instance_ray, assemblytree.cpp:556-596; get_offset_point, shadingpoint.h:604-613).
+ * Here both halves run on the device, so that bounce and shadow rays never go back to the host.
+ * ------------------------------------------------------------------------------------------ */
+
+typedef struct asgpu_parent {           /* 80 bytes */
+    uint32_t        assembly_instance;      /* asgpu_hit::assembly_instance of the parent, ASGPU_MISS = no parent */
+    uint32_t        reserved;
+    double          front[3];               /* m_refine_space_front_point */
+    double          back[3];                /* m_refine_space_back_point */
+    double          geo_normal[3];          /* m_refine_space_geo_normal (faces the parent ray, not unit length) */
+} asgpu_parent;
+
+/* For every hit of a closest-hit trace: the parent record its ShadingPoint would hold.  rays =
+ * the rays that produced `hits`.  DEVICE pointers.  Needs source geometry (asgpu_scene_create_ex)
+ * and the exact layout; static triangles only. */
+int             asgpu_refine_and_offset(asgpu_scene* scene, const asgpu_rays* rays, const asgpu_hit* hits, size_t n,
+                                        asgpu_parent* parents, void* stream);
+
+/* asgpu_trace / asgpu_trace_probe with a parent per ray (parents[i].assembly_instance ==
+ * ASGPU_MISS: none).  DEVICE pointers. */
+int             asgpu_trace_with_parents(asgpu_scene* scene, const asgpu_rays* rays, const asgpu_parent* parents, size_t n,
+                                         asgpu_hit* hits, uint32_t flags, void* stream);
+int             asgpu_trace_probe_with_parents(asgpu_scene* scene, const asgpu_rays* rays, const asgpu_parent* parents, size_t n,
+                                               uint8_t* occluded, uint32_t flags, void* stream);
 
 /* The coherence sort behind ASGPU_TRACE_SORT on its own: order[i] = index of the ray to process
  * at position i (a permutation of 0..n-1, device array) by ascending 24-bit origin / direction

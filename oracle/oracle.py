@@ -15,7 +15,7 @@ import subprocess
 
 import numpy as np
 
-from appleseed_b200.scene import HIT_DTYPE, CRays, CSceneDesc, RayBatch, SceneDesc
+from appleseed_b200.scene import HIT_DTYPE, PARENT_DTYPE, CRays, CSceneDesc, RayBatch, SceneDesc
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _PATHS = {
@@ -110,6 +110,12 @@ class Oracle:
         self._trace.argtypes = [C.c_void_p, C.POINTER(CRays), C.c_size_t, C.c_void_p, C.c_int, C.POINTER(Counters)]
         self._probe = getattr(L, p + "_trace_probe")
         self._probe.argtypes = [C.c_void_p, C.POINTER(CRays), C.c_size_t, C.c_void_p, C.c_int, C.POINTER(Counters)]
+        self._refine = getattr(L, p + "_refine_offset")
+        self._refine.argtypes = [C.c_void_p, C.POINTER(CRays), C.c_void_p, C.c_size_t, C.c_void_p, C.c_int]
+        self._trace_par = getattr(L, p + "_trace_parents")
+        self._trace_par.argtypes = [C.c_void_p, C.POINTER(CRays), C.c_void_p, C.c_size_t, C.c_void_p, C.c_int]
+        self._probe_par = getattr(L, p + "_trace_probe_parents")
+        self._probe_par.argtypes = [C.c_void_p, C.POINTER(CRays), C.c_void_p, C.c_size_t, C.c_void_p, C.c_int]
         if prefix == "orc":
             self._two = L.orc_two_nearest
             self._two.argtypes = [C.c_void_p, C.POINTER(CRays), C.c_size_t, C.c_void_p, C.c_void_p, C.c_int]
@@ -221,6 +227,31 @@ class OracleScene:
         cnt = Counters()
         self.oracle._probe(self.handle, C.byref(cr), n, out.ctypes.data, threads, C.byref(cnt))
         return (out, cnt.as_dict()) if counters else out
+
+    def refine_offset(self, rays: RayBatch, hits: np.ndarray, threads: int = 1) -> np.ndarray:
+        """ShadingPoint::refine_and_offset for every hit: PARENT_DTYPE records (orc_parent)."""
+        n = len(rays)
+        out = np.zeros(n, dtype=PARENT_DTYPE)
+        cr = rays.to_c()
+        hits = np.ascontiguousarray(hits)
+        self.oracle._refine(self.handle, C.byref(cr), hits.ctypes.data, n, out.ctypes.data, threads)
+        return out
+
+    def trace_parents(self, rays: RayBatch, parents: np.ndarray, threads: int = 1) -> np.ndarray:
+        n = len(rays)
+        out = np.zeros(n, dtype=HIT_DTYPE)
+        cr = rays.to_c()
+        parents = np.ascontiguousarray(parents)
+        self.oracle._trace_par(self.handle, C.byref(cr), parents.ctypes.data, n, out.ctypes.data, threads)
+        return out
+
+    def trace_probe_parents(self, rays: RayBatch, parents: np.ndarray, threads: int = 1) -> np.ndarray:
+        n = len(rays)
+        out = np.zeros(n, dtype=np.uint8)
+        cr = rays.to_c()
+        parents = np.ascontiguousarray(parents)
+        self.oracle._probe_par(self.handle, C.byref(cr), parents.ctypes.data, n, out.ctypes.data, threads)
+        return out
 
     def two_nearest(self, rays: RayBatch, threads: int = 1):
         n = len(rays)

@@ -98,7 +98,7 @@ void* hostsim_scene_create(const asgpu_scene_desc* desc, uint32_t flags, int thr
     top.item_count = trees.assembly_tree.items.size();
 
     SimScene* s = new SimScene();
-    const int rc = flatten_scene(views.empty() ? nullptr : views.data(), static_cast<uint32_t>(views.size()), top, flags, s->blob, g_error);
+    const int rc = flatten_scene(views.empty() ? nullptr : views.data(), static_cast<uint32_t>(views.size()), top, nullptr, flags, s->blob, g_error);
     if (rc != ASGPU_OK) { delete s; return nullptr; }
     BlobHeader h; std::memcpy(&h, s->blob.data(), sizeof(h));
     s->view.blob = s->blob.data();
