@@ -38,6 +38,7 @@ SCENE_DEFAULT = SCENE_EXACT | SCENE_WIDE
 TRACE_EXACT = 1 << 0
 TRACE_COUNTERS = 1 << 1
 TRACE_SORT = 1 << 2
+STREAM_PARENTS = 1 << 0
 
 
 class TriangleTreeView(C.Structure):
@@ -89,7 +90,7 @@ class Counters(C.Structure):
 class PathStreamDesc(C.Structure):
     _fields_ = [
         ("width", C.c_uint32), ("height", C.c_uint32), ("spp", C.c_uint32), ("max_bounces", C.c_uint32),
-        ("tile_size", C.c_uint32), ("light_count", C.c_uint32), ("trace_flags", C.c_uint32), ("reserved", C.c_uint32),
+        ("tile_size", C.c_uint32), ("light_count", C.c_uint32), ("trace_flags", C.c_uint32), ("stream_flags", C.c_uint32),
         ("seed", C.c_uint64), ("camera_to_world", C.c_double * 12),
         ("film_width", C.c_double), ("film_height", C.c_double), ("focal_length", C.c_double),
         ("lights", (C.c_double * 3) * 8), ("offset_eps", C.c_double),
@@ -179,7 +180,7 @@ def load() -> C.CDLL:
     lib.asgpu_path_stream_capture.argtypes = [C.c_void_p, C.c_size_t]
     lib.asgpu_path_stream_capture_count.argtypes = [C.c_void_p]
     lib.asgpu_path_stream_capture_get.restype = C.c_longlong
-    lib.asgpu_path_stream_capture_get.argtypes = [C.c_void_p, C.c_int, P(C.c_int), P(C.c_uint32)] + [C.c_void_p] * 7
+    lib.asgpu_path_stream_capture_get.argtypes = [C.c_void_p, C.c_int, P(C.c_int), P(C.c_uint32)] + [C.c_void_p] * 8
     _lib = lib
     return lib
 

@@ -56,6 +56,7 @@ struct asgpu_ray_queue
     uint32_t*           flags = nullptr;
     uint32_t*           path = nullptr;
     unsigned long long* count = nullptr;
+    asgpu_parent*       parents = nullptr;      // only for the queues of a path stream with ASGPU_STREAM_PARENTS
 };
 
 namespace
@@ -63,6 +64,7 @@ namespace
 
 struct QueueView
 {
+    asgpu_parent*       parents;
     double*             org;
     double*             dir;
     double*             tmin;
@@ -77,7 +79,7 @@ QueueView view_of(const asgpu_ray_queue* q)
 {
     QueueView v;
     v.org = q->org; v.dir = q->dir; v.tmin = q->tmin; v.tmax = q->tmax;
-    v.flags = q->flags; v.path = q->path; v.count = q->count; v.capacity = q->capacity;
+    v.flags = q->flags; v.path = q->path; v.count = q->count; v.capacity = q->capacity; v.parents = q->parents;
     return v;
 }
 
@@ -150,6 +152,17 @@ __device__ __forceinline__ void write_ray(const QueueView& q, const unsigned lon
     q.path[slot] = path;
 }
 
+// Copies one 80-byte parent record (or marks "no parent").
+__device__ __forceinline__ void write_parent(const QueueView& q, const unsigned long long slot, const asgpu_parent* src)
+{
+    if (q.parents == nullptr) return;
+    unsigned long long* dst = reinterpret_cast<unsigned long long*>(q.parents + slot);
+    if (src == nullptr) { dst[0] = 0xFFFFFFFFull; return; }
+    const unsigned long long* s8 = reinterpret_cast<const unsigned long long*>(src);
+    #pragma unroll
+    for (int k = 0; k < 10; ++k) dst[k] = s8[k];
+}
+
 __device__ __forceinline__ void add_stats(unsigned long long* stats, const unsigned (&local)[StatCount])
 {
     const unsigned lane = threadIdx.x & 31;
@@ -217,6 +230,7 @@ generate_kernel(const StreamParams p, const uint32_t* __restrict__ tiles, const 
         if (slot != ~0ull)
         {
             write_ray(out, slot, o, d, 0.0, DBL_MAX, ASGPU_VIS_CAMERA, path);
+            write_parent(out, slot, nullptr);
             ++local[StatCamera];
         }
     }
@@ -231,7 +245,7 @@ generate_kernel(const StreamParams p, const uint32_t* __restrict__ tiles, const 
 //   * when depth < max_bounces, one cosine-weighted bounce (mappings.h:299-314), flags DiffuseRay.
 // hit.assembly_instance holds the ItemRecord index here (raw_item launches).
 __global__ void __launch_bounds__(StageThreads)
-shade_kernel(const StreamParams p, const SceneView s, const QueueView in, const asgpu_hit* __restrict__ hits,
+shade_kernel(const StreamParams p, const SceneView s, const QueueView in, const asgpu_hit* __restrict__ hits, const asgpu_parent* refined,
              const QueueView probes, const QueueView next, const uint32_t depth, uint32_t* image, unsigned long long* stats)
 {
     const unsigned long long n = min(*in.count, in.capacity);
@@ -278,8 +292,13 @@ shade_kernel(const StreamParams p, const SceneView s, const QueueView in, const 
                     nrm[k] = load_f64(ip + k * 8) * nl[0] + load_f64(ip + (4 + k) * 8) * nl[1] + load_f64(ip + (8 + k) * 8) * nl[2];
                 normalize3(nrm);
                 if (nrm[0] * dir[0] + nrm[1] * dir[1] + nrm[2] * dir[2] > 0.0) { nrm[0] = -nrm[0]; nrm[1] = -nrm[1]; nrm[2] = -nrm[2]; }
-                #pragma unroll
-                for (int k = 0; k < 3; ++k) o[k] += p.eps * nrm[k];
+                // Next origin: the hit point itself when the child rays carry the refined parent record,
+                // else offset along the normal.
+                if (refined == nullptr)
+                {
+                    #pragma unroll
+                    for (int k = 0; k < 3; ++k) o[k] += p.eps * nrm[k];
+                }
                 atomicAdd(image + static_cast<size_t>(pixel) * 4 + 0, 1u);
                 atomicAdd(image + static_cast<size_t>(pixel) * 4 + 3, primitive * 2654435761u + object_instance * 0x9E3779B1u + meta.z * 0x85EBCA6Bu + slot);
                 ++local[StatHits];
@@ -304,6 +323,7 @@ shade_kernel(const StreamParams p, const SceneView s, const QueueView in, const 
             if (slot != ~0ull)
             {
                 write_ray(probes, slot, o, d, 0.0, tmax, ASGPU_VIS_SHADOW, path);
+                write_parent(probes, slot, refined ? refined + i : nullptr);
                 ++local[StatProbe];
             }
         }
@@ -333,6 +353,7 @@ shade_kernel(const StreamParams p, const SceneView s, const QueueView in, const 
             if (slot != ~0ull)
             {
                 write_ray(next, slot, o, d, 0.0, DBL_MAX, ASGPU_VIS_DIFFUSE, path);
+                write_parent(next, slot, refined ? refined + i : nullptr);
                 ++local[StatBounce];
             }
         }
@@ -374,6 +395,7 @@ struct Captured
     std::vector<double>     org, dir, tmin, tmax;
     std::vector<uint32_t>   flags, path;
     std::vector<uint8_t>    results;
+    std::vector<asgpu_parent> parents;
 };
 
 }   // anonymous namespace
@@ -389,6 +411,7 @@ struct asgpu_path_stream
     asgpu_ray_queue*        qb = nullptr;
     asgpu_ray_queue*        qp = nullptr;
     asgpu_hit*              hits = nullptr;
+    asgpu_parent*           refined = nullptr;      // refine_and_offset of the current wavefront's hits (ASGPU_STREAM_PARENTS)
     uint8_t*                occluded = nullptr;
     uint32_t*               image = nullptr;
     uint32_t*               tiles_dev = nullptr;
@@ -421,6 +444,7 @@ int capture_wavefront(asgpu_path_stream* ps, const asgpu_ray_queue* q, const int
     c.kind = kind; c.depth = depth;
     c.org.resize(n * 3); c.dir.resize(n * 3); c.tmin.resize(n); c.tmax.resize(n); c.flags.resize(n); c.path.resize(n);
     c.results.resize(n * (kind == 0 ? sizeof(asgpu_hit) : 1));
+    c.parents.clear();
     if (n == 0) return ASGPU_OK;
     ASGPU_CUDA(cudaMemcpy(c.org.data(), q->org, n * 24, cudaMemcpyDeviceToHost), "capture");
     ASGPU_CUDA(cudaMemcpy(c.dir.data(), q->dir, n * 24, cudaMemcpyDeviceToHost), "capture");
@@ -428,6 +452,9 @@ int capture_wavefront(asgpu_path_stream* ps, const asgpu_ray_queue* q, const int
     ASGPU_CUDA(cudaMemcpy(c.tmax.data(), q->tmax, n * 8, cudaMemcpyDeviceToHost), "capture");
     ASGPU_CUDA(cudaMemcpy(c.flags.data(), q->flags, n * 4, cudaMemcpyDeviceToHost), "capture");
     ASGPU_CUDA(cudaMemcpy(c.path.data(), q->path, n * 4, cudaMemcpyDeviceToHost), "capture");
+    c.parents.resize(n);
+    if (q->parents) ASGPU_CUDA(cudaMemcpy(c.parents.data(), q->parents, n * sizeof(asgpu_parent), cudaMemcpyDeviceToHost), "capture");
+    else for (asgpu_parent& pr : c.parents) { std::memset(&pr, 0, sizeof(pr)); pr.assembly_instance = ASGPU_MISS; }
     if (kind == 0)
     {
         ASGPU_CUDA(cudaMemcpy(c.results.data(), ps->hits, n * sizeof(asgpu_hit), cudaMemcpyDeviceToHost), "capture");
@@ -448,7 +475,8 @@ int trace_queue(asgpu_scene* scene, asgpu_ray_queue* q, asgpu_hit* hits, uint8_t
     if (!wide && !(scene->header.flags & ASGPU_SCENE_EXACT)) return fail(ASGPU_E_INVALID, "scene was created without the exact layout");
     const asgpu_rays rays = rays_of(q);
     const int err = launch_trace(scene->view, rays, q->capacity, hits, occluded, any_hit, wide, cursor,
-                                 (flags & ASGPU_TRACE_COUNTERS) ? scene->counters : nullptr, nullptr, scene->sm_count, stream, q->count, raw_item);
+                                 (flags & ASGPU_TRACE_COUNTERS) ? scene->counters : nullptr, nullptr, scene->sm_count, stream, q->count, raw_item,
+                                 q->parents);
     if (err != 0) return fail_cuda(static_cast<cudaError_t>(err), "kernel launch");
     ++scene->launches;
     return ASGPU_OK;
@@ -487,7 +515,7 @@ void asgpu_queue_destroy(asgpu_ray_queue* q)
     if (!q) return;
     cudaSetDevice(q->scene->device);
     cudaFree(q->org); cudaFree(q->dir); cudaFree(q->tmin); cudaFree(q->tmax);
-    cudaFree(q->flags); cudaFree(q->path); cudaFree(q->count);
+    cudaFree(q->flags); cudaFree(q->path); cudaFree(q->count); cudaFree(q->parents);
     delete q;
 }
 
@@ -570,6 +598,8 @@ asgpu_path_stream* asgpu_path_stream_create(asgpu_scene* scene, const asgpu_path
     if (static_cast<uint64_t>(desc->width) * desc->height * desc->spp > 0xFFFFFFFFull) { fail(ASGPU_E_UNSUPPORTED, "more than 2^32 - 1 paths per frame"); return nullptr; }
     if (scene->header.moving_triangle_count != 0) { fail(ASGPU_E_UNSUPPORTED, "the path stream handles static triangles only"); return nullptr; }
     if (!(scene->header.flags & ASGPU_SCENE_EXACT)) { fail(ASGPU_E_INVALID, "the path stream needs the per-slot triangle records of the exact layout"); return nullptr; }
+    const bool with_parents = (desc->stream_flags & ASGPU_STREAM_PARENTS) != 0;
+    if (with_parents && !scene->has_source) { fail(ASGPU_E_INVALID, "ASGPU_STREAM_PARENTS needs a scene with source geometry (asgpu_scene_create_ex)"); return nullptr; }
     const size_t per_tile = static_cast<size_t>(desc->tile_size) * desc->tile_size * desc->spp;
     if (queue_capacity < per_tile) { fail(ASGPU_E_INVALID, "queue capacity below one tile's paths"); return nullptr; }
 
@@ -597,6 +627,13 @@ asgpu_path_stream* asgpu_path_stream_create(asgpu_scene* scene, const asgpu_path
     ps->qp = asgpu_queue_create(scene, capacity);
     cudaError_t e = cudaSuccess;
     const size_t pixels = static_cast<size_t>(desc->width) * desc->height;
+    if (with_parents && ps->qa && ps->qb && ps->qp)
+    {
+        if (e == cudaSuccess) e = cudaMalloc(&ps->qa->parents, capacity * sizeof(asgpu_parent));
+        if (e == cudaSuccess) e = cudaMalloc(&ps->qb->parents, capacity * sizeof(asgpu_parent));
+        if (e == cudaSuccess) e = cudaMalloc(&ps->qp->parents, capacity * sizeof(asgpu_parent));
+        if (e == cudaSuccess) e = cudaMalloc(&ps->refined, capacity * sizeof(asgpu_parent));
+    }
     if (e == cudaSuccess) e = cudaMalloc(&ps->hits, capacity * sizeof(asgpu_hit));
     if (e == cudaSuccess) e = cudaMalloc(&ps->occluded, capacity);
     if (e == cudaSuccess) e = cudaMalloc(&ps->image, pixels * 16);
@@ -624,7 +661,7 @@ void asgpu_path_stream_destroy(asgpu_path_stream* ps)
     if (!ps) return;
     cudaSetDevice(ps->scene->device);
     asgpu_queue_destroy(ps->qa); asgpu_queue_destroy(ps->qb); asgpu_queue_destroy(ps->qp);
-    cudaFree(ps->hits); cudaFree(ps->occluded); cudaFree(ps->image); cudaFree(ps->tiles_dev);
+    cudaFree(ps->hits); cudaFree(ps->refined); cudaFree(ps->occluded); cudaFree(ps->image); cudaFree(ps->tiles_dev);
     cudaFree(ps->stats_dev); cudaFree(ps->cursors);
     delete ps;
 }
@@ -668,7 +705,13 @@ int asgpu_path_stream_render(asgpu_path_stream* ps, const uint32_t* tiles, size_
             if (ps->capture_armed && (rc = capture_wavefront(ps, qa, 0, depth, stream)) != ASGPU_OK) return rc;
             ASGPU_CUDA(cudaMemsetAsync(qb->count, 0, 8, stream), "cudaMemsetAsync");
             ASGPU_CUDA(cudaMemsetAsync(ps->qp->count, 0, 8, stream), "cudaMemsetAsync");
-            shade_kernel<<<grid, StageThreads, 0, stream>>>(ps->params, scene->view, view_of(qa), ps->hits, vp, view_of(qb), depth, ps->image, ps->stats_dev);
+            if (ps->refined)
+            {
+                const int er = launch_refine_offset(scene->view, rays_of(qa), ps->hits, qa->capacity, qa->count, true, nullptr, 0, ps->refined, scene->sm_count, stream);
+                if (er != 0) return fail_cuda(static_cast<cudaError_t>(er), "refine_offset_kernel");
+                ++ps->launches;
+            }
+            shade_kernel<<<grid, StageThreads, 0, stream>>>(ps->params, scene->view, view_of(qa), ps->hits, ps->refined, vp, view_of(qb), depth, ps->image, ps->stats_dev);
             ASGPU_CUDA(cudaGetLastError(), "shade_kernel");
             ++ps->launches;
             rc = trace_queue(scene, ps->qp, nullptr, ps->occluded, true, flags, ps->cursors + (ps->cursor_next++ % QueueRing), true, stream);
@@ -733,7 +776,7 @@ int asgpu_path_stream_capture_count(const asgpu_path_stream* ps) { return ps ? s
 
 long long asgpu_path_stream_capture_get(const asgpu_path_stream* ps, int k, int* kind, uint32_t* depth,
                                         double* org, double* dir, double* tmin, double* tmax, uint32_t* flags,
-                                        uint32_t* path_ids, void* results)
+                                        uint32_t* path_ids, void* results, asgpu_parent* parents)
 {
     if (!ps || k < 0 || k >= static_cast<int>(ps->captured.size())) return fail(ASGPU_E_INVALID, "no such captured wavefront");
     const Captured& c = ps->captured[k];
@@ -747,6 +790,7 @@ long long asgpu_path_stream_capture_get(const asgpu_path_stream* ps, int k, int*
     if (flags) std::memcpy(flags, c.flags.data(), n * 4);
     if (path_ids) std::memcpy(path_ids, c.path.data(), n * 4);
     if (results) std::memcpy(results, c.results.data(), c.results.size());
+    if (parents && !c.parents.empty()) std::memcpy(parents, c.parents.data(), c.parents.size() * sizeof(asgpu_parent));
     return static_cast<long long>(n);
 }
 

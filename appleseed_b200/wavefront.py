@@ -17,7 +17,7 @@ import numpy as np
 
 from . import _lib
 from .intersector import AsgpuError, TraceContext, _check
-from .scene import HIT_DTYPE, RayBatch
+from .scene import HIT_DTYPE, PARENT_DTYPE, RayBatch
 
 
 class RayQueue:
@@ -82,6 +82,7 @@ class PathStreamConfig:
     offset_eps: float = 1.0e-6
     exact: bool = False
     counters: bool = False                 # accumulate the scene's traversal counters (slower)
+    parents: bool = False                  # child rays carry their refined parent shading point (ASGPU_STREAM_PARENTS)
 
     def to_c(self) -> "_lib.PathStreamDesc":
         d = _lib.PathStreamDesc()
@@ -89,6 +90,7 @@ class PathStreamConfig:
         lights = np.asarray(self.lights, dtype=np.float64).reshape(-1, 3)
         d.light_count = lights.shape[0]
         d.trace_flags = (_lib.TRACE_EXACT if self.exact else 0) | (_lib.TRACE_COUNTERS if self.counters else 0)
+        d.stream_flags = _lib.STREAM_PARENTS if self.parents else 0
         d.seed = self.seed
         m = np.asarray(self.camera_to_world, dtype=np.float64).reshape(-1, 4)[:3]
         for i, v in enumerate(m.reshape(-1)):
@@ -110,6 +112,7 @@ class CapturedWavefront:
     rays: RayBatch
     path_ids: np.ndarray
     results: np.ndarray        # HIT_DTYPE records or uint8 occlusion flags
+    parents: Optional[np.ndarray] = None       # PARENT_DTYPE records the rays carried
 
 
 def look_at(origin, target, up=(0.0, 1.0, 0.0)) -> np.ndarray:
@@ -172,15 +175,16 @@ class PathStream:
         out = []
         for k in range(int(self.lib.asgpu_path_stream_capture_count(self.handle))):
             kind, depth = C.c_int(0), C.c_uint32(0)
-            n = int(self.lib.asgpu_path_stream_capture_get(self.handle, k, C.byref(kind), C.byref(depth), *([None] * 7)))
+            n = int(self.lib.asgpu_path_stream_capture_get(self.handle, k, C.byref(kind), C.byref(depth), *([None] * 8)))
             if n < 0:
                 raise AsgpuError("asgpu_path_stream_capture_get failed: " + _lib.last_error())
             org, dirs = np.empty((n, 3)), np.empty((n, 3))
             tmin, tmax = np.empty(n), np.empty(n)
             flags, ids = np.empty(n, dtype=np.uint32), np.empty(n, dtype=np.uint32)
             res = np.empty(n, dtype=HIT_DTYPE if kind.value == 0 else np.uint8)
+            par = np.zeros(n, dtype=PARENT_DTYPE)
             ptr = lambda a: a.ctypes.data if n else None
-            self.lib.asgpu_path_stream_capture_get(self.handle, k, None, None, ptr(org), ptr(dirs), ptr(tmin), ptr(tmax), ptr(flags), ptr(ids), ptr(res))
+            self.lib.asgpu_path_stream_capture_get(self.handle, k, None, None, ptr(org), ptr(dirs), ptr(tmin), ptr(tmax), ptr(flags), ptr(ids), ptr(res), ptr(par))
             out.append(CapturedWavefront("closest" if kind.value == 0 else "probe", int(depth.value),
-                                         RayBatch(org, dirs, tmin, tmax, flags=flags), ids, res))
+                                         RayBatch(org, dirs, tmin, tmax, flags=flags), ids, res, par))
         return out

@@ -587,7 +587,7 @@ def c5_config(args, desc) -> dict:
     eye = centre + np.array([0.32, 0.55, 0.45]) * diag
     lights = np.array([[lo[0], hi[1] + 2.0, lo[2]], [hi[0], hi[1] + 2.0, lo[2]], [lo[0], hi[1] + 2.0, hi[2]], [hi[0], hi[1] + 2.0, hi[2]]])
     return dict(width=args.width, height=args.height, spp=args.spp, camera_to_world=look_at(eye, centre), lights=lights,
-                max_bounces=3, tile_size=32, seed=5, offset_eps=1.0e-6 * diag)
+                max_bounces=3, tile_size=32, seed=5, offset_eps=1.0e-6 * diag, parents=not getattr(args, "no_parents", False))
 
 
 def cpu_path_stream(desc, oscene, cfg: dict, width: int, height: int, threads: int, seed: int = 7):
@@ -737,6 +737,7 @@ def run_gpu_c5(args):
             "config": {
                 "workload": workload_name(args), "rays_per_frame": total_rays, "closest_rays_per_frame": total_closest,
                 "probe_rays_per_frame": total_rays - total_closest, "tiles_per_gpu": int(len(tiles)), "queue_capacity": args.rays,
+                "next_ray_origin": "parent shading point, refined + offset on the device (ShadingPoint::refine_and_offset)" if cfg["parents"] else "hit point + eps * normal",
                 "image_checksum": checksum,
                 "l2": "inputs larger than L2 (%.0f MB scene blob, %.0f MB of queued rays per wavefront vs 126 MB L2)" % (info["blob_bytes"] / 1e6, args.rays * 72 / 1e6),
                 "scene": {k: info[k] for k in ("triangle_count", "instance_count", "wide_node_count", "binary_node_count", "blob_bytes")},
@@ -777,6 +778,7 @@ def main():
     ap.add_argument("--width", type=int, default=1920, help="c5: image width")
     ap.add_argument("--height", type=int, default=1080, help="c5: image height")
     ap.add_argument("--spp", type=int, default=64, help="c5: camera paths per pixel")
+    ap.add_argument("--no-parents", action="store_true", help="c5: offset next origins by eps * normal instead of carrying parent shading points")
     ap.add_argument("--rays", type=int, default=0, help="rays per batch per GPU (default: the workload's)")
     ap.add_argument("--res", type=int, default=0, help="override the grid resolution (smaller scene for quick runs)")
     ap.add_argument("--cpu-rays", type=int, default=0, help="size of the CPU baseline sample (default: one whole batch)")

@@ -375,6 +375,12 @@ int             asgpu_trace_probe_queue(asgpu_scene* scene, asgpu_ray_queue* que
  * tmax = distance * (1 - 1e-6) (Tracer::trace_between, renderer/kernel/lighting/tracer.h:252-259).
  * Random numbers are a counter-based hash of (seed, pixel, sample, depth): the result does not
  * depend on batching, queue order or the number of GPUs. */
+/* Child rays start AT the hit point and carry their parent shading point, refined and offset on the
+ * device (asgpu_refine_and_offset + the parent origin rule): what the reference's path tracer does
+ * by passing parent_shading_point to Intersector::trace.  Without it they start offset_eps along
+ * the geometric normal (the parent == nullptr convention).  Needs source geometry. */
+#define ASGPU_STREAM_PARENTS    (1u << 0)
+
 typedef struct asgpu_path_stream_desc {
     uint32_t        width, height;          /* image resolution */
     uint32_t        spp;                    /* camera paths per pixel */
@@ -382,7 +388,7 @@ typedef struct asgpu_path_stream_desc {
     uint32_t        tile_size;              /* 32: Frame's default tile size (frame.cpp:1331) */
     uint32_t        light_count;            /* 1..8 */
     uint32_t        trace_flags;            /* ASGPU_TRACE_* used for the stream's trace launches */
-    uint32_t        reserved;
+    uint32_t        stream_flags;           /* ASGPU_STREAM_* */
     uint64_t        seed;
     double          camera_to_world[12];    /* 3 x 4 row-major: rotation | translation */
     double          film_width, film_height, focal_length;
@@ -413,13 +419,14 @@ int             asgpu_path_stream_clear(asgpu_path_stream* stream);
 int             asgpu_path_stream_get_stats(asgpu_path_stream* stream, asgpu_path_stream_stats* out);
 /* Test hook: keep a copy of every wavefront's rays and results of the NEXT render call (HOST side,
  * bounded by max_rays); asgpu_path_stream_capture_get returns wavefront k: kind 0 = closest hit
- * (results = asgpu_hit[n]), 1 = shadow probe (results = uint8_t[n]).  Returns the number of rays
- * or a negative error; arrays may be NULL to query the size. */
+ * (results = asgpu_hit[n]), 1 = shadow probe (results = uint8_t[n]); parents = the parent records
+ * the rays carried (ASGPU_STREAM_PARENTS; assembly_instance = ASGPU_MISS otherwise).  Returns the
+ * number of rays or a negative error; arrays may be NULL to query the size. */
 int             asgpu_path_stream_capture(asgpu_path_stream* stream, size_t max_rays);
 int             asgpu_path_stream_capture_count(const asgpu_path_stream* stream);
 long long       asgpu_path_stream_capture_get(const asgpu_path_stream* stream, int k, int* kind, uint32_t* depth,
                                               double* org, double* dir, double* tmin, double* tmax, uint32_t* flags,
-                                              uint32_t* path_ids, void* results);
+                                              uint32_t* path_ids, void* results, asgpu_parent* parents);
 
 const char*     asgpu_last_error(void);
 int             asgpu_version(void);

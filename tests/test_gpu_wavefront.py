@@ -171,3 +171,34 @@ def test_path_stream_rejects_bad_input(setup):
     with pytest.raises(AsgpuError, match="range"):
         ps.render([ps.tile_count])
     ps.close()
+
+
+def test_stream_with_parent_shading_points(setup, orc):
+    """ASGPU_STREAM_PARENTS: child rays start at the hit point and carry the refined parent record."""
+    desc, ctx, wavefront, cfg = setup
+    o = orc.scene(desc)
+    img, stats, caps = render(wavefront, ctx, cfg, 1 << 20, capture=1 << 22, parents=True)
+    closest = [c for c in caps if c.kind == "closest"]
+    probes = [c for c in caps if c.kind == "probe"]
+    assert np.all(closest[0].parents["assembly_instance"] == 0xFFFFFFFF)       # camera rays have no parent
+    for d, (parent, probe) in enumerate(zip(closest, probes)):
+        # The wavefront's own results, parents honoured.
+        ref = o.trace_parents(parent.rays, parent.parents, threads=4)
+        parity.compare_hits(o, parent.rays, parent.results, ref)
+        assert int(((parent.results["prim_type"] == 2) & (parent.results["t"] < 1e-9)).sum()) == 0     # no self-intersection
+        # What the children carry = refine_and_offset of these hits, bit for bit.
+        hit = parent.results["prim_type"] == 2
+        refined = o.refine_offset(parent.rays, parent.results, threads=4)
+        by_path = dict(zip(parent.path_ids.tolist(), range(len(parent.path_ids))))
+        children = [probe] + ([closest[d + 1]] if d + 1 < len(closest) else [])
+        for child in children:
+            idx = np.array([by_path[p] for p in child.path_ids.tolist()])
+            assert child.parents.tobytes() == refined[idx].tobytes()
+            pts = parent.rays.org[idx] + parent.results["t"][idx][:, None] * parent.rays.dir[idx]
+            assert np.allclose(child.rays.org, pts, rtol=0, atol=1e-12)                                # no epsilon offset
+        pref = o.trace_probe_parents(probe.rays, probe.parents, threads=4)
+        parity.compare_probes(o, probe.rays, probe.results, pref)
+    assert stats["kernel_launches"] == 1 + 5 * (cfg["max_bounces"] + 1)
+    # Same image from the exact kernels.
+    exact, _, _ = render(wavefront, ctx, cfg, 1 << 20, parents=True, exact=True)
+    assert np.array_equal(img, exact)
