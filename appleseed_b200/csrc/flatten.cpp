@@ -23,6 +23,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <limits>
 
 namespace asgpu
@@ -263,10 +264,13 @@ struct BinaryView
     std::vector<uint32_t>       child;          // first child or InteriorMark^... (leaf: InteriorMark)
     std::vector<uint32_t>       first, count;   // leaf item range
     std::vector<FBox>           box;            // conservative all-time box of each node
+    // Trees with motion: box of node x over the ray-time interval [t0, t1] (empty = use `box`).
+    std::function<FBox(uint32_t x, float t0, float t1)> timed_box;
 };
 
 struct WideOut
 {
+    std::vector<WSlice>     slices;         // nodes.size() * slice_count entries (trees with motion)
     std::vector<WNode>      nodes;
     std::vector<uint32_t>   leaf_order;     // wide item order -> original item (slot) index
     uint32_t                depth = 0;      // number of node levels (root = 1)
@@ -276,6 +280,7 @@ struct Element
 {
     bool        is_node;        // subtree that becomes a wide node of its own, else an item range (leaf child)
     uint32_t    node;           // node of the augmented binary tree (is_node)
+    uint32_t    src;            // node of the ORIGINAL binary tree whose box this is
     uint32_t    first, count;   // item range (!is_node)
     FBox        box;
 };
@@ -320,10 +325,46 @@ int quantise_node(WNode& w, const Element* kids, const int n, const int* slot_of
     return ASGPU_OK;
 }
 
+// Child planes of one time slice in the frame quantise_node chose (rounded outward, clamped into
+// the all-time planes, which contain them).
+int quantise_slice(const WNode& w, WSlice& out, const FBox* boxes, const int n, const int* slot_of, std::string& error)
+{
+    for (int a = 0; a < 3; ++a)
+    {
+        for (int sl = 0; sl < 8; ++sl) { out.qlo[a][sl] = 255; out.qhi[a][sl] = 0; }
+        const double scale = std::ldexp(1.0, int(w.exp[a]) - 127);
+        for (int i = 0; i < n; ++i)
+        {
+            const int s = slot_of[i];
+            if (!boxes[i].valid()) continue;
+            double lo = std::floor((double(boxes[i].lo[a]) - double(w.origin[a])) / scale);
+            double hi = std::ceil((double(boxes[i].hi[a]) - double(w.origin[a])) / scale);
+            lo = std::min(double(w.qhi[a][s]), std::max(double(w.qlo[a][s]), lo));
+            hi = std::min(double(w.qhi[a][s]), std::max(lo, hi));
+            out.qlo[a][s] = static_cast<uint8_t>(lo);
+            out.qhi[a][s] = static_cast<uint8_t>(hi);
+            // A slice plane may only be clamped where the all-time plane already bounds the child.
+            const double plo = double(w.origin[a]) + lo * scale, phi = double(w.origin[a]) + hi * scale;
+            const double alo = double(w.origin[a]) + double(w.qlo[a][s]) * scale, ahi = double(w.origin[a]) + double(w.qhi[a][s]) * scale;
+            if ((plo > double(boxes[i].lo[a]) && plo > alo) || (phi < double(boxes[i].hi[a]) && phi < ahi))
+            { error = "internal error: time-slice box does not contain its child"; return ASGPU_E_INVALID; }
+        }
+    }
+    return ASGPU_OK;
+}
+
 // Relative costs of the collapse's surface-area heuristic: testing one wide node / one leaf item.
 // The defaults are the measured optimum for the wide kernels (profiles/README.md); the
 // environment variable ASGPU_COLLAPSE_ITEM_COST overrides the item cost for experiments.
 struct CollapseCosts { double node, item; };
+
+// Time slices per wide node of a tree with moving triangles (ASGPU_TIME_SLICES overrides; 0 = none).
+uint32_t time_slices()
+{
+    uint32_t t = 16;        // measured on C4: 8 -> 1784, 16 -> 1976, 32 -> 2050 Mrays/s (no slices: 567); 768 B per node at 16
+    if (const char* e = std::getenv("ASGPU_TIME_SLICES")) { const int v = std::atoi(e); t = v < 0 ? 0u : static_cast<uint32_t>(std::min(v, 64)); }
+    return t;
+}
 
 CollapseCosts collapse_costs()
 {
@@ -338,8 +379,9 @@ CollapseCosts collapse_costs()
 // expected SAH cost: C(n, i) = cheapest way to cover subtree n with at most i children of one
 // wide node.  Every wide child box is the box of a binary subtree, so it contains all the binary
 // boxes below it.
-int collapse(const BinaryView& bv, const uint32_t leaf_cap, const CollapseCosts costs, WideOut& out, std::string& error)
+int collapse(const BinaryView& bv, const uint32_t leaf_cap, const CollapseCosts costs, WideOut& out, std::string& error, const uint32_t slice_count = 0)
 {
+    out.slices.clear();
     out.nodes.clear();
     out.leaf_order.clear();
     out.depth = 0;
@@ -350,6 +392,8 @@ int collapse(const BinaryView& bv, const uint32_t leaf_cap, const CollapseCosts 
     std::vector<uint32_t> rc(bv.node_count);
     std::vector<uint32_t> first(bv.first.begin(), bv.first.end()), count(bv.count.begin(), bv.count.end());
     std::vector<FBox> box(bv.box.begin(), bv.box.end());
+    std::vector<uint32_t> src(bv.node_count);
+    for (uint64_t i = 0; i < bv.node_count; ++i) src[i] = static_cast<uint32_t>(i);
     for (uint64_t i = 0; i < bv.node_count; ++i) rc[i] = lc[i] == Leaf ? Leaf : lc[i] + 1;
     for (uint64_t i = 0; i < lc.size(); ++i)
     {
@@ -357,8 +401,8 @@ int collapse(const BinaryView& bv, const uint32_t leaf_cap, const CollapseCosts 
         // An over-full leaf (max_leaf_size > cap, or a range the SAH refused to split): both halves keep its box.
         const uint32_t a = static_cast<uint32_t>(lc.size());
         const uint32_t half = count[i] / 2;
-        lc.push_back(Leaf); rc.push_back(Leaf); first.push_back(first[i]); count.push_back(half); box.push_back(box[i]);
-        lc.push_back(Leaf); rc.push_back(Leaf); first.push_back(first[i] + half); count.push_back(count[i] - half); box.push_back(box[i]);
+        lc.push_back(Leaf); rc.push_back(Leaf); first.push_back(first[i]); count.push_back(half); box.push_back(box[i]); src.push_back(src[i]);
+        lc.push_back(Leaf); rc.push_back(Leaf); first.push_back(first[i] + half); count.push_back(count[i] - half); box.push_back(box[i]); src.push_back(src[i]);
         lc[i] = a; rc[i] = a + 1;
     }
     const uint64_t n = lc.size();
@@ -443,12 +487,12 @@ int collapse(const BinaryView& bv, const uint32_t leaf_cap, const CollapseCosts 
 
         auto emit_leaf = [&](const uint32_t x)
         {
-            Element e; e.is_node = false; e.node = 0; e.first = sub_first[x]; e.count = sub_count[x]; e.box = box[x];
+            Element e; e.is_node = false; e.node = 0; e.src = src[x]; e.first = sub_first[x]; e.count = sub_count[x]; e.box = box[x];
             if (n_kids < 8) kids[n_kids++] = e; else overflow = true;
         };
         auto emit_node = [&](const uint32_t x)
         {
-            Element e; e.is_node = true; e.node = x; e.first = e.count = 0; e.box = box[x];
+            Element e; e.is_node = true; e.node = x; e.src = src[x]; e.first = e.count = 0; e.box = box[x];
             if (n_kids < 8) kids[n_kids++] = e; else overflow = true;
         };
 
@@ -554,7 +598,24 @@ int collapse(const BinaryView& bv, const uint32_t leaf_cap, const CollapseCosts 
         }
         if (out.nodes.size() >= 0xFFFFFFFFull) { error = "wide tree too large"; return ASGPU_E_UNSUPPORTED; }
         out.nodes[cur.wide_index] = w;
+
+        if (slice_count != 0 && bv.timed_box)
+        {
+            // Time slices: the same children in the same frame, bounded over 1 / T of the time axis
+            // each (a small overlap absorbs the rounding of the ray's slice index).
+            if (out.slices.size() < out.nodes.size() * slice_count) out.slices.resize(out.nodes.size() * slice_count);
+            for (uint32_t j = 0; j < slice_count; ++j)
+            {
+                const float t0 = std::max(0.0f, (float(j) - 1.0e-3f) / float(slice_count));
+                const float t1 = std::min(1.0f, (float(j) + 1.0f + 1.0e-3f) / float(slice_count));
+                FBox boxes[8];
+                for (int i = 0; i < n_children; ++i) boxes[i] = bv.timed_box(kids[i].src, t0, t1);
+                const int rs = quantise_slice(w, out.slices[size_t(cur.wide_index) * slice_count + j], boxes, n_children, slot_of, error);
+                if (rs != ASGPU_OK) return rs;
+            }
+        }
     }
+    if (slice_count != 0 && bv.timed_box) out.slices.resize(out.nodes.size() * slice_count);
     return ASGPU_OK;
 }
 
@@ -602,6 +663,10 @@ void triangle_tree_boxes(const asgpu_triangle_tree_view& v, const ExactTree& t, 
         return b;
     };
 
+    // Where the motion boxes of node x live (as a child of its parent): index / count into t.mboxes.
+    std::vector<uint32_t> mindex, mcount;
+    if (motion) { mindex.assign(n, 0); mcount.assign(n, 0); }
+
     // Children always have larger indices than their parent (bvh_builder.h:197-205), so one
     // forward pass assigns every box before it is needed.
     if (nodes[0].interior())
@@ -622,12 +687,65 @@ void triangle_tree_boxes(const asgpu_triangle_tree_view& v, const ExactTree& t, 
             bv.child[i] = node.index;
             bv.box[node.index] = child_box(node, 0);
             bv.box[node.index + 1] = child_box(node, 1);
+            if (motion)
+            {
+                mindex[node.index] = node.left_bbox_index; mcount[node.index] = node.left_bbox_count;
+                mindex[node.index + 1] = node.right_bbox_index; mcount[node.index + 1] = node.right_bbox_count;
+            }
         }
         else
         {
             bv.first[i] = node.index;
             bv.count[i] = node.item_count;
         }
+    }
+
+    if (motion)
+    {
+        // Box of node x over the ray times [t0, t1]: the reference interpolates consecutive motion
+        // boxes linearly in the ray time (bvh_intersector.h:680-722), so the union over an interval
+        // is the union of the interpolants at its ends and at the knots inside it.  Padded for the
+        // float rounding of the interpolation and of the time products.
+        const std::vector<FBox> all = bv.box;
+        const std::vector<MBox>* mboxes = &t.mboxes;
+        bv.timed_box = [all, mindex, mcount, mboxes](const uint32_t x, const float t0, const float t1) -> FBox
+        {
+            if (x == 0 || mcount[x] <= 1) return all[x];
+            const uint32_t segments = mcount[x] - 1;
+            const MBox* mb = mboxes->data() + mindex[x];
+            FBox b; b.reset();
+            double span[3] = { 0.0, 0.0, 0.0 };
+            auto add_at = [&](const double time)
+            {
+                const double ts = std::min(double(segments), std::max(0.0, time * segments));
+                uint32_t k = static_cast<uint32_t>(ts);
+                if (k >= segments) k = segments - 1;
+                const double f = ts - k;
+                for (int a = 0; a < 3; ++a)
+                {
+                    const double lo = double(mb[k].v[a * 2]) * (1.0 - f) + double(mb[k + 1].v[a * 2]) * f;
+                    const double hi = double(mb[k].v[a * 2 + 1]) * (1.0 - f) + double(mb[k + 1].v[a * 2 + 1]) * f;
+                    b.lo[a] = std::min(b.lo[a], float_below(lo));
+                    b.hi[a] = std::max(b.hi[a], float_above(hi));
+                    span[a] = std::max(span[a], std::max(std::fabs(double(mb[k + 1].v[a * 2]) - double(mb[k].v[a * 2])),
+                                                         std::fabs(double(mb[k + 1].v[a * 2 + 1]) - double(mb[k].v[a * 2 + 1]))));
+                }
+            };
+            add_at(t0);
+            add_at(t1);
+            for (uint32_t k = 1; k < segments; ++k)
+            {
+                const double knot = double(k) / segments;
+                if (knot > t0 && knot < t1) add_at(knot);
+            }
+            for (int a = 0; a < 3; ++a)
+            {
+                const float m = static_cast<float>(std::max(std::fabs(double(b.lo[a])), std::fabs(double(b.hi[a]))) * 4.0e-7 + span[a] * 1.0e-5)
+                              + std::numeric_limits<float>::min();
+                b.lo[a] -= m; b.hi[a] += m;
+            }
+            return b;
+        };
     }
 }
 
@@ -786,7 +904,8 @@ int flatten_scene(
             BinaryView bv;
             triangle_tree_boxes(trees[ti], et, bv);
             WideOut wo;
-            rc = collapse(bv, 3, collapse_costs(), wo, error);
+            const uint32_t slice_count = et.moving > 0 ? time_slices() : 0;
+            rc = collapse(bv, 3, collapse_costs(), wo, error, slice_count);
             if (rc != ASGPU_OK) return rc;
             if (wo.leaf_order.size() != et.tris.size()) { error = "internal error: wide collapse lost triangles"; return ASGPU_E_INVALID; }
             max_bottom_depth = std::max(max_bottom_depth, wo.depth);
@@ -795,8 +914,13 @@ int flatten_scene(
             d.wnodes = writer.append(wo.nodes);
             d.wnode_count = static_cast<uint32_t>(wo.nodes.size());
             d.wtris = writer.append(wtris);
+            if (slice_count != 0 && !wo.slices.empty())
+            {
+                d.wslices = writer.append(wo.slices);
+                d.wslice_count = slice_count;
+            }
             header.wide_node_count += wo.nodes.size();
-            header.wide_node_bytes += wo.nodes.size() * sizeof(WNode);
+            header.wide_node_bytes += wo.nodes.size() * sizeof(WNode) + wo.slices.size() * sizeof(WSlice);
             if (!want_exact) header.triangle_bytes += wtris.size() * sizeof(TriRecord);
         }
     }
@@ -874,7 +998,8 @@ int validate_blob(const uint8_t* blob, size_t size, std::string& error)
         std::memcpy(&d, blob + h.trees + uint64_t(i) * sizeof(TreeDesc), sizeof(d));
         if (!inside(d.bnodes, uint64_t(d.bnode_count) * sizeof(BNodeF)) || !inside(d.wnodes, uint64_t(d.wnode_count) * sizeof(WNode)) ||
             !inside(d.keys, uint64_t(d.slot_count) * sizeof(HitKey)) || !inside(d.tris, d.tris ? uint64_t(d.slot_count) * sizeof(TriRecord) : 0) ||
-            !inside(d.wtris, d.wtris ? uint64_t(d.slot_count) * sizeof(TriRecord) : 0))
+            !inside(d.wtris, d.wtris ? uint64_t(d.slot_count) * sizeof(TriRecord) : 0) ||
+            !inside(d.wslices, uint64_t(d.wnode_count) * d.wslice_count * sizeof(WSlice)))
         { error = "blob tree section out of range"; return ASGPU_E_INVALID; }
     }
     return ASGPU_OK;

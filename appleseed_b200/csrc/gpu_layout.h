@@ -28,7 +28,7 @@ namespace asgpu
 {
 
 const uint32_t BlobMagic = 0x42534131u;     // "1ASB"
-const uint32_t BlobVersion = 5;
+const uint32_t BlobVersion = 6;
 const uint32_t WideStackMax = 64;           // deepest traversal stack any wide kernel variant offers
 const uint64_t SectionAlign = 256;
 
@@ -110,8 +110,23 @@ struct TreeDesc
     uint32_t    mbox_count;
     uint32_t    src_object_count;
     uint64_t    src_objects;    // SrcObject[src_object_count] or 0: source geometry for refine_and_offset
+    uint64_t    wslices;        // WSlice[wnode_count * wslice_count] or 0: time-sliced child boxes (trees with motion)
+    uint32_t    wslice_count;   // T: slice j bounds the children over ray times [j / T, (j + 1) / T]
+    uint32_t    pad;
 };
-static_assert(sizeof(TreeDesc) == 96, "TreeDesc");
+static_assert(sizeof(TreeDesc) == 112, "TreeDesc");
+
+// WIDE, trees with moving triangles: the quantised child planes of one wide node for one slice of
+// the ray-time axis, same frame (origin, exp) and same slots as the node's own qlo / qhi (which
+// bound the whole motion).  The reference interpolates motion boxes at the ray time
+// (bvh_intersector.h:675-836); a time slice is the cheap equivalent for a quantised wide node:
+// no per-plane arithmetic, only a different 48-byte block per ray.
+struct WSlice
+{
+    uint8_t     qlo[3][8];
+    uint8_t     qhi[3][8];
+};
+static_assert(sizeof(WSlice) == 48, "WSlice");
 
 // Source geometry of one object instance of an assembly (what ShadingPoint::
 // fetch_triangle_source_geometry reads, shadingpoint.cpp:186-256): object-space vertices, vertex

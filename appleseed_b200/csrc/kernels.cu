@@ -298,6 +298,8 @@ wide_kernel(const KernelArgs args)
     // Per-lane traversal cursor.
     WideRay w;
     const uint8_t* wnodes = blob;
+    const uint8_t* qbase = blob;        // quantised child planes of node i: qbase + i * qstride (the node's own, or its time slice)
+    uint32_t qstride = sizeof(WNode);
     uint2 ngroup, tgroup;               // pending internal children / pending instances (world space)
     ngroup.x = ngroup.y = tgroup.x = tgroup.y = 0;
     uint32_t fetch = None;              // wide node to test next
@@ -355,7 +357,17 @@ wide_kernel(const KernelArgs args)
             const uint2 o_tris = load8(tp + offsetof(TreeDesc, wtris));
             const uint2 o_poses = load8(tp + offsetof(TreeDesc, poses));
             const uint32_t wnode_count = load4(tp + offsetof(TreeDesc, wnode_count));
+            const uint32_t wslice_count = load4(tp + offsetof(TreeDesc, wslice_count));
             wnodes = blob + (static_cast<uint64_t>(o_nodes.x) | (static_cast<uint64_t>(o_nodes.y) << 32));
+            if (wslice_count != 0)
+            {
+                // Tree with moving triangles: child planes of this ray's time slice.
+                const uint2 o_slices = load8(tp + offsetof(TreeDesc, wslices));
+                qbase = blob + (static_cast<uint64_t>(o_slices.x) | (static_cast<uint64_t>(o_slices.y) << 32))
+                      + static_cast<uint64_t>(time_slice(sm.time_n[tid], wslice_count)) * sizeof(WSlice);
+                qstride = wslice_count * static_cast<uint32_t>(sizeof(WSlice));
+            }
+            else { qbase = wnodes + 32; qstride = sizeof(WNode); }
             sm.tri_base[tid] = static_cast<uint64_t>(o_tris.x) | (static_cast<uint64_t>(o_tris.y) << 32);
             sm.pose_base[tid] = static_cast<uint64_t>(o_poses.x) | (static_cast<uint64_t>(o_poses.y) << 32);
             sm.cur_item[tid] = item;
@@ -393,6 +405,7 @@ wide_kernel(const KernelArgs args)
                     sm.cur_item[tid] = None;
                     make_wide_ray(ray.org, ray.dir, ray.tmin, ray.tmax, w);
                     wnodes = blob + s.top_wnodes;
+                    qbase = wnodes + 32; qstride = sizeof(WNode);
                     ngroup.y = 0; tgroup.y = 0;
                     fetch = s.top_wnode_count != 0 ? 0u : None;
                     sp = 0;
@@ -422,7 +435,8 @@ wide_kernel(const KernelArgs args)
                 if (COUNT) { if (cur_item != None) ++stats.nodes; else ++stats.top_nodes; }
                 if (ngroup.y & 0xFF000000u) { stack[sp * stride] = ngroup; ++sp; }
                 uint32_t child_base, tri_base, nmask, tmask;
-                wide_node_test(wnodes + static_cast<uint64_t>(fetch) * sizeof(WNode), w, args.unit_bits, child_base, tri_base, nmask, tmask);
+                wide_node_test(wnodes + static_cast<uint64_t>(fetch) * sizeof(WNode), qbase + static_cast<uint64_t>(fetch) * qstride, w, args.unit_bits,
+                               child_base, tri_base, nmask, tmask);
                 ngroup.x = child_base; ngroup.y = nmask;
                 if (cur_item != None) { pending = tmask; tri_first = tri_base; }
                 else { tgroup.x = tri_base; tgroup.y = tmask; }
@@ -458,6 +472,7 @@ wide_kernel(const KernelArgs args)
                                 // (Candidates of the instance still in the queue carry all they need.)
                                 restore_world_ray(args.rays, index, sm.ray[6][tid], sm.ray[7][tid], sm, tid, w);
                                 wnodes = blob + s.top_wnodes;
+                                qbase = wnodes + 32; qstride = sizeof(WNode);
                                 cur_item = None;
                             }
                             else if (top.y & 0xFF000000u) ngroup = top;

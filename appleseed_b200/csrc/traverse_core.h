@@ -697,10 +697,14 @@ ASGPU_HD float byte_to_unit(const uint32_t word, const int k, const uint32_t one
 // (exact, a power of two), q * s + a = m * S + (a - S), so the offset is reduced by S once per
 // node and axis (rounded outward; S is only 2^15 grid steps, so this costs 2^-8 of a grid step of
 // tightness) and no per-plane conversion remains.
+//
+// `np` is the wide node (origin, exponents, imask, bases, meta in its first 32 bytes), `qp` its 48
+// bytes of quantised child planes: the node's own (np + 32, bounding the whole motion) or the
+// WSlice of the ray's time slice in a tree with moving triangles.
 template <bool EXPANDED>
-ASGPU_HD void wide_node_test_form(const uint8_t* np, const WideRay& w, const uint32_t one, uint32_t& child_base, uint32_t& tri_base, uint32_t& nmask, uint32_t& tmask)
+ASGPU_HD void wide_node_test_form(const uint8_t* np, const uint8_t* qp, const WideRay& w, const uint32_t one, uint32_t& child_base, uint32_t& tri_base, uint32_t& nmask, uint32_t& tmask)
 {
-    const uint4 n0 = load16(np), n1 = load16(np + 16), n2 = load16(np + 32), n3 = load16(np + 48), n4 = load16(np + 64);
+    const uint4 n0 = load16(np), n1 = load16(np + 16), n2 = load16(qp), n3 = load16(qp + 16), n4 = load16(qp + 32);
     child_base = n1.x;
     tri_base = n1.y;
     const uint32_t imask = n0.w >> 24;
@@ -775,10 +779,19 @@ ASGPU_HD void wide_node_test_form(const uint8_t* np, const WideRay& w, const uin
     tmask = hitmask & 0x00FFFFFFu;
 }
 
-ASGPU_HD void wide_node_test(const uint8_t* np, const WideRay& w, const uint32_t one, uint32_t& child_base, uint32_t& tri_base, uint32_t& nmask, uint32_t& tmask)
+ASGPU_HD void wide_node_test(const uint8_t* np, const uint8_t* qp, const WideRay& w, const uint32_t one, uint32_t& child_base, uint32_t& tri_base, uint32_t& nmask, uint32_t& tmask)
 {
-    if (w.oct & 8) wide_node_test_form<false>(np, w, one, child_base, tri_base, nmask, tmask);
-    else wide_node_test_form<true>(np, w, one, child_base, tri_base, nmask, tmask);
+    if (w.oct & 8) wide_node_test_form<false>(np, qp, w, one, child_base, tri_base, nmask, tmask);
+    else wide_node_test_form<true>(np, qp, w, one, child_base, tri_base, nmask, tmask);
+}
+
+// Time slice of a ray in a tree with `slices` slices: floor(time * slices), clamped.  The slices
+// overlap by 1e-3 of their width (flatten.cpp), far more than the rounding of this product.
+ASGPU_HD uint32_t time_slice(const float time_normalized, const uint32_t slices)
+{
+    const float x = fmul(time_normalized, static_cast<float>(slices));
+    uint32_t j = x > 0.0f ? static_cast<uint32_t>(x) : 0u;
+    return j < slices ? j : slices - 1;
 }
 
 const uint32_t WideStackSize = WideStackMax;       // host driver; the kernels pick a depth per scene
@@ -811,6 +824,8 @@ struct WideTraversal
     Ray             ray;
     WideRay         wr;
     const uint8_t*  wnodes;
+    const uint8_t*  qbase;              // child planes of node i at qbase + i * qstride
+    uint32_t        qstride;
     const uint8_t*  wtris;
     const uint8_t*  poses;
     uint2           ngroup, tgroup;
@@ -824,6 +839,7 @@ struct WideTraversal
         load_ray(rays, index, ray);
         make_wide_ray(ray, wr);
         wnodes = s.blob + s.top_wnodes;
+        qbase = wnodes + 32; qstride = sizeof(WNode);
         wtris = nullptr;
         poses = nullptr;
         ngroup.x = 0; ngroup.y = 0;
@@ -846,7 +862,7 @@ struct WideTraversal
             if (COUNT) { if (in_instance) ++stats.nodes; else ++stats.top_nodes; }
             if (ngroup.y & 0xFF000000u) { stack[sp * stride] = ngroup; ++sp; }
             uint32_t child_base, tri_base, nmask, tmask;
-            wide_node_test(wnodes + static_cast<uint64_t>(fetch) * sizeof(WNode), wr, UnitBits, child_base, tri_base, nmask, tmask);
+            wide_node_test(wnodes + static_cast<uint64_t>(fetch) * sizeof(WNode), qbase + static_cast<uint64_t>(fetch) * qstride, wr, UnitBits, child_base, tri_base, nmask, tmask);
             ngroup.x = child_base; ngroup.y = nmask;
             tgroup.x = tri_base; tgroup.y = tmask;
             fetch = 0xFFFFFFFFu;
@@ -895,6 +911,12 @@ struct WideTraversal
                 make_wide_ray(ray, wr);
                 TreeDesc td; load_tree_desc(s, meta.x, td);
                 wnodes = s.blob + td.wnodes;
+                if (td.wslice_count != 0)
+                {
+                    qbase = s.blob + td.wslices + static_cast<uint64_t>(time_slice(ray.time_normalized, td.wslice_count)) * sizeof(WSlice);
+                    qstride = td.wslice_count * static_cast<uint32_t>(sizeof(WSlice));
+                }
+                else { qbase = wnodes + 32; qstride = sizeof(WNode); }
                 wtris = s.blob + td.wtris;
                 poses = s.blob + td.poses;
                 cur_item = item;
@@ -923,6 +945,7 @@ struct WideTraversal
             load_ray_org_dir(rays, index, ray);
             make_wide_ray(ray, wr);
             wnodes = s.blob + s.top_wnodes;
+            qbase = wnodes + 32; qstride = sizeof(WNode);
             cur_item = 0xFFFFFFFFu;
             ngroup.y = 0; tgroup.y = 0;
             return false;
