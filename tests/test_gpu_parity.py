@@ -250,3 +250,45 @@ def test_full_size_c2_properties(engine, orc):
     ref = o.trace(sub, threads=8)
     assert exact[idx].tobytes() == ref.tobytes()
     parity.compare_hits(o, sub, wide[idx], ref)
+
+
+@pytest.mark.parametrize("msc", [1, 2, 3])
+def test_moving_triangles_at_scale_time_slices_change_nothing(engine, orc, msc, monkeypatch):
+    """C4-like scene (180 000 moving triangles): the time-sliced wide boxes are an acceleration
+    only -- results equal those of the all-motion boxes, of the exact kernels, and of the oracle on
+    a sample; rays exactly on slice boundaries and at both ends of the time axis included."""
+    from appleseed_b200 import scenes
+    desc = scenes.scene_c4(300, msc)
+    lo, hi = scenes.scene_bbox(desc)
+    rays = scenes.uniform_sphere_rays(600_000, lo - 0.05, hi + 0.05, 17 + msc, time=True)
+    t = rays.time_normalized
+    t[:4096] = (np.arange(4096) % 17).astype(np.float32) / np.float32(16.0)       # slice boundaries k / 16
+    t[:4096] = np.minimum(t[:4096], np.float32(1.0) - np.float32(2.0 ** -24))
+    t[4096:8192] = np.nextafter(t[:4096], np.float32(0.0))
+    rays.time_absolute = rays.time_normalized = t
+    ctx, isect = make(engine, desc)
+    sliced = isect.trace(rays)
+    exact = isect.trace(rays, exact=True)
+    assert np.array_equal(sliced["prim_type"], exact["prim_type"])
+    hit = exact["prim_type"] == 2
+    assert hit.sum() > 100_000
+    assert np.allclose(sliced["t"][hit], exact["t"][hit], rtol=1e-5, atol=0.0)
+    assert (sliced["tri_slot"] == exact["tri_slot"]).mean() > 0.9999
+    occ = isect.trace_probe(rays)
+    assert np.array_equal(occ, isect.trace_probe(rays, exact=True))
+    monkeypatch.setenv("ASGPU_TIME_SLICES", "0")
+    ctx0, isect0 = make(engine, desc)
+    assert ctx0.info()["wide_node_bytes"] < ctx.info()["wide_node_bytes"]
+    plain = isect0.trace(rays)
+    same = plain.tobytes() == sliced.tobytes()
+    if not same:            # only exact-t ties may be resolved differently (different visit sets)
+        diff = np.nonzero((plain["tri_slot"] != sliced["tri_slot"]) | (plain["t"] != sliced["t"]))[0]
+        assert len(diff) < 20 and np.allclose(plain["t"][diff], sliced["t"][diff], rtol=1e-6, atol=0.0)
+    assert np.array_equal(isect0.trace_probe(rays), occ)
+    idx = np.arange(0, len(rays), 25)
+    o = orc.scene(desc)
+    sub = rays.take(idx)
+    ref = o.trace(sub, threads=8)
+    assert exact[idx].tobytes() == ref.tobytes()
+    parity.compare_hits(o, sub, sliced[idx], ref)
+    parity.compare_probes(o, sub, occ[idx], o.trace_probe(sub, threads=8))
