@@ -274,7 +274,10 @@ __device__ __forceinline__ void restore_world_ray(const asgpu_rays& rays, const 
     w.tmax_f = d2f_up(tmax);
 }
 
-template <bool ANY, bool COUNT, int STACK, int MINB>
+// LEAN = the scene has one assembly instance and no moving triangles (e.g. C2): nothing ever comes
+// back to world space and no tree has time slices, so the instantiation drops the batched instance
+// entry, the saved world-space ray and the indirection to the child planes (measured: 3-5 %).
+template <bool ANY, bool COUNT, int STACK, int MINB, bool LEAN>
 __global__ void __launch_bounds__(BlockThreads, MINB)
 wide_kernel(const KernelArgs args)
 {
@@ -344,7 +347,7 @@ wide_kernel(const KernelArgs args)
             if (args.parents) parent_origin(reinterpret_cast<const uint8_t*>(args.parents + index), meta.z, ldir, lorg);
             #pragma unroll
             for (int k = 0; k < 3; ++k) { sm.ray[k][tid] = lorg[k]; sm.ray[3 + k][tid] = ldir[k]; }
-            if (sp != 0)
+            if (!LEAN && sp != 0)
             {
                 // Something is left to do in world space: keep the expensive part of the world ray.
                 #pragma unroll
@@ -359,7 +362,7 @@ wide_kernel(const KernelArgs args)
             const uint32_t wnode_count = load4(tp + offsetof(TreeDesc, wnode_count));
             const uint32_t wslice_count = load4(tp + offsetof(TreeDesc, wslice_count));
             wnodes = blob + (static_cast<uint64_t>(o_nodes.x) | (static_cast<uint64_t>(o_nodes.y) << 32));
-            if (wslice_count != 0)
+            if (!LEAN && wslice_count != 0)
             {
                 // Tree with moving triangles: child planes of this ray's time slice.
                 const uint2 o_slices = load8(tp + offsetof(TreeDesc, wslices));
@@ -435,8 +438,8 @@ wide_kernel(const KernelArgs args)
                 if (COUNT) { if (cur_item != None) ++stats.nodes; else ++stats.top_nodes; }
                 if (ngroup.y & 0xFF000000u) { stack[sp * stride] = ngroup; ++sp; }
                 uint32_t child_base, tri_base, nmask, tmask;
-                wide_node_test(wnodes + static_cast<uint64_t>(fetch) * sizeof(WNode), qbase + static_cast<uint64_t>(fetch) * qstride, w, args.unit_bits,
-                               child_base, tri_base, nmask, tmask);
+                const uint8_t* np = wnodes + static_cast<uint64_t>(fetch) * sizeof(WNode);
+                wide_node_test(np, LEAN ? np + 32 : qbase + static_cast<uint64_t>(fetch) * qstride, w, args.unit_bits, child_base, tri_base, nmask, tmask);
                 ngroup.x = child_base; ngroup.y = nmask;
                 if (cur_item != None) { pending = tmask; tri_first = tri_base; }
                 else { tgroup.x = tri_base; tgroup.y = tmask; }
@@ -454,7 +457,7 @@ wide_kernel(const KernelArgs args)
                 }
                 else if (tgroup.y)
                 {
-                    if (args.enter_late) want_enter = true;     // performed below, with the other lanes of the warp that got here
+                    if (!LEAN && args.enter_late) want_enter = true;    // performed below, with the other lanes of the warp that got here
                     else enter_instance();
                 }
                 else
@@ -470,7 +473,13 @@ wide_kernel(const KernelArgs args)
                             {
                                 // Back to world space: the world ray comes from the ray arrays again.
                                 // (Candidates of the instance still in the queue carry all they need.)
-                                restore_world_ray(args.rays, index, sm.ray[6][tid], sm.ray[7][tid], sm, tid, w);
+                                if (LEAN)
+                                {
+                                    Ray world;
+                                    load_ray_org_dir(args.rays, index, world);
+                                    make_wide_ray(world.org, world.dir, sm.ray[6][tid], sm.ray[7][tid], w);
+                                }
+                                else restore_world_ray(args.rays, index, sm.ray[6][tid], sm.ray[7][tid], sm, tid, w);
                                 wnodes = blob + s.top_wnodes;
                                 qbase = wnodes + 32; qstride = sizeof(WNode);
                                 cur_item = None;
@@ -496,7 +505,7 @@ wide_kernel(const KernelArgs args)
         }
 
         // ---- enter assembly instances: every lane that reached one in this iteration, together ------
-        if (__ballot_sync(0xFFFFFFFFu, want_enter) != 0)
+        if (!LEAN && __ballot_sync(0xFFFFFFFFu, want_enter) != 0)
         {
             if (want_enter) enter_instance();
         }
@@ -659,14 +668,24 @@ cudaError_t launch_persistent(Kernel kernel, const KernelArgs& args, const size_
 // and run ~10 % slower (profiles/README.md).
 const int WideMinBlocks = 5;
 
-template <int STACK>
+template <int STACK, bool LEAN>
 cudaError_t launch_wide(const KernelArgs& args, const bool any_hit, const bool count, const int sm_count, cudaStream_t stream)
 {
     const size_t smem = sizeof(WideShared<STACK>);
-    if (any_hit) return count ? launch_persistent(wide_kernel<true, true, STACK, WideMinBlocks>, args, smem, sm_count, stream)
-                              : launch_persistent(wide_kernel<true, false, STACK, WideMinBlocks>, args, smem, sm_count, stream);
-    return count ? launch_persistent(wide_kernel<false, true, STACK, WideMinBlocks>, args, smem, sm_count, stream)
-                 : launch_persistent(wide_kernel<false, false, STACK, WideMinBlocks>, args, smem, sm_count, stream);
+    if (any_hit) return count ? launch_persistent(wide_kernel<true, true, STACK, WideMinBlocks, LEAN>, args, smem, sm_count, stream)
+                              : launch_persistent(wide_kernel<true, false, STACK, WideMinBlocks, LEAN>, args, smem, sm_count, stream);
+    return count ? launch_persistent(wide_kernel<false, true, STACK, WideMinBlocks, LEAN>, args, smem, sm_count, stream)
+                 : launch_persistent(wide_kernel<false, false, STACK, WideMinBlocks, LEAN>, args, smem, sm_count, stream);
+}
+
+template <bool LEAN>
+cudaError_t launch_wide_depth(const KernelArgs& args, const uint32_t stack_need, const bool any_hit, const bool count, const int sm_count, cudaStream_t stream)
+{
+    // The traversal stack lives in shared memory; its depth is the scene's (flatten.cpp computes
+    // the bound), rounded up to one of the compiled variants.
+    if (stack_need <= 16) return launch_wide<16, LEAN>(args, any_hit, count, sm_count, stream);
+    if (stack_need <= 24) return launch_wide<24, LEAN>(args, any_hit, count, sm_count, stream);
+    return launch_wide<WideStackMax, LEAN>(args, any_hit, count, sm_count, stream);
 }
 
 }   // anonymous namespace
@@ -717,12 +736,9 @@ int launch_trace(
     const bool count = counters != nullptr;
     if (wide)
     {
-        // The traversal stack lives in shared memory; its depth is the scene's (flatten.cpp
-        // computes the bound), rounded up to one of the compiled variants.
-        if (scene.wide_stack_need <= 16) err = launch_wide<16>(args, any_hit, count, sm_count, stream);
-        else if (scene.wide_stack_need <= 24) err = launch_wide<24>(args, any_hit, count, sm_count, stream);
-        else if (scene.wide_stack_need <= 40) err = launch_wide<40>(args, any_hit, count, sm_count, stream);
-        else err = launch_wide<WideStackMax>(args, any_hit, count, sm_count, stream);
+        const bool lean = scene.item_count <= 1 && !scene.has_motion && getenv("ASGPU_NO_LEAN") == nullptr;
+        err = lean ? launch_wide_depth<true>(args, scene.wide_stack_need, any_hit, count, sm_count, stream)
+                   : launch_wide_depth<false>(args, scene.wide_stack_need, any_hit, count, sm_count, stream);
     }
     else if (any_hit) err = count ? launch_persistent(trace_kernel<true, true>, args, 0, sm_count, stream)
                                   : launch_persistent(trace_kernel<true, false>, args, 0, sm_count, stream);

@@ -159,6 +159,7 @@ struct SceneView
     uint64_t        trees, items, top_nodes, top_wnodes, top_witems;
     uint32_t        tree_count, item_count, top_node_count, top_wnode_count;
     uint32_t        wide_stack_need;
+    uint32_t        has_motion;         // some tree has moving triangles (time-sliced child planes)
 };
 
 struct Ray
