@@ -17,6 +17,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -105,17 +106,17 @@ int ensure_staging(asgpu_scene* s)
     for (Staging& st : s->staging)
     {
         ASGPU_CUDA(cudaStreamCreateWithFlags(&st.stream, cudaStreamNonBlocking), "cudaStreamCreate");
-        ASGPU_CUDA(cudaMalloc(&st.org, HostChunkRays * 24), "cudaMalloc(staging)");
-        ASGPU_CUDA(cudaMalloc(&st.dir, HostChunkRays * 24), "cudaMalloc(staging)");
-        ASGPU_CUDA(cudaMalloc(&st.tmin, HostChunkRays * 8), "cudaMalloc(staging)");
-        ASGPU_CUDA(cudaMalloc(&st.tmax, HostChunkRays * 8), "cudaMalloc(staging)");
-        ASGPU_CUDA(cudaMalloc(&st.time_absolute, HostChunkRays * 4), "cudaMalloc(staging)");
-        ASGPU_CUDA(cudaMalloc(&st.time_normalized, HostChunkRays * 4), "cudaMalloc(staging)");
-        ASGPU_CUDA(cudaMalloc(&st.flags, HostChunkRays * 4), "cudaMalloc(staging)");
-        ASGPU_CUDA(cudaMalloc(&st.hits, HostChunkRays * sizeof(asgpu_hit)), "cudaMalloc(staging)");
-        ASGPU_CUDA(cudaMalloc(&st.occluded, HostChunkRays), "cudaMalloc(staging)");
+        ASGPU_CUDA(cudaMalloc(&st.org, host_chunk_rays() * 24), "cudaMalloc(staging)");
+        ASGPU_CUDA(cudaMalloc(&st.dir, host_chunk_rays() * 24), "cudaMalloc(staging)");
+        ASGPU_CUDA(cudaMalloc(&st.tmin, host_chunk_rays() * 8), "cudaMalloc(staging)");
+        ASGPU_CUDA(cudaMalloc(&st.tmax, host_chunk_rays() * 8), "cudaMalloc(staging)");
+        ASGPU_CUDA(cudaMalloc(&st.time_absolute, host_chunk_rays() * 4), "cudaMalloc(staging)");
+        ASGPU_CUDA(cudaMalloc(&st.time_normalized, host_chunk_rays() * 4), "cudaMalloc(staging)");
+        ASGPU_CUDA(cudaMalloc(&st.flags, host_chunk_rays() * 4), "cudaMalloc(staging)");
+        ASGPU_CUDA(cudaMalloc(&st.hits, host_chunk_rays() * sizeof(asgpu_hit)), "cudaMalloc(staging)");
+        ASGPU_CUDA(cudaMalloc(&st.occluded, host_chunk_rays()), "cudaMalloc(staging)");
         ASGPU_CUDA(cudaMalloc(&st.queue, 64), "cudaMalloc(staging)");
-        ASGPU_CUDA(cudaMalloc(&st.sort_ws, ray_sort_workspace_bytes(HostChunkRays) + HostChunkRays * 4), "cudaMalloc(staging)");
+        ASGPU_CUDA(cudaMalloc(&st.sort_ws, ray_sort_workspace_bytes(host_chunk_rays()) + host_chunk_rays() * 4), "cudaMalloc(staging)");
     }
     s->staging_ready = true;
     return ASGPU_OK;
@@ -171,9 +172,9 @@ int trace_host(asgpu_scene* scene, const asgpu_rays* rays, const size_t n, asgpu
     if (rc != ASGPU_OK) return rc;
 
     size_t chunk_index = 0;
-    for (size_t begin = 0; begin < n; begin += HostChunkRays, ++chunk_index)
+    for (size_t begin = 0; begin < n; begin += host_chunk_rays(), ++chunk_index)
     {
-        const size_t count = std::min(HostChunkRays, n - begin);
+        const size_t count = std::min(host_chunk_rays(), n - begin);
         Staging& st = scene->staging[chunk_index % HostStreams];
         // Stream order guarantees the previous use of this staging slot has drained.
         ASGPU_CUDA(cudaMemcpyAsync(st.org, rays->org + begin * 3, count * 24, cudaMemcpyHostToDevice, st.stream), "H2D org");
@@ -201,7 +202,7 @@ int trace_host(asgpu_scene* scene, const asgpu_rays* rays, const size_t n, asgpu
         const uint32_t* order = nullptr;
         if (flags & ASGPU_TRACE_SORT)
         {
-            uint32_t* chunk_order = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(st.sort_ws) + ray_sort_workspace_bytes(HostChunkRays));
+            uint32_t* chunk_order = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(st.sort_ws) + ray_sort_workspace_bytes(host_chunk_rays()));
             const int es = launch_ray_sort(dev, count, nullptr, chunk_order, nullptr, st.sort_ws, scene->sm_count, st.stream);
             if (es != 0) return fail_cuda(static_cast<cudaError_t>(es), "ray sort launch");
             scene->launches += ray_sort_launch_count();
@@ -233,6 +234,17 @@ int asgpu::ensure_sort_scratch(asgpu_scene* scene, const size_t n)
     ASGPU_CUDA(cudaMalloc(&scene->sort.order, n * sizeof(uint32_t)), "cudaMalloc(sort order)");
     scene->sort.capacity = n;
     return ASGPU_OK;
+}
+
+size_t asgpu::host_chunk_rays()
+{
+    static const size_t value = []() -> size_t
+    {
+        size_t v = size_t(1) << 20;
+        if (const char* e = getenv("ASGPU_HOST_CHUNK")) { const long long x = atoll(e); if (x > 0) v = static_cast<size_t>(x); }
+        return std::min(size_t(4) << 20, std::max(size_t(64) << 10, v));
+    }();
+    return value;
 }
 
 int asgpu::ensure_id_table(asgpu_scene* scene)

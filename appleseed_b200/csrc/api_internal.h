@@ -23,7 +23,8 @@ int fail_cuda(cudaError_t err, const char* what);
 
 #define ASGPU_CUDA(call, what) do { const cudaError_t e_ = (call); if (e_ != cudaSuccess) return ::asgpu::fail_cuda(e_, what); } while (0)
 
-const size_t HostChunkRays = size_t(1) << 20;
+// Rays per chunk of the host-buffer entry points (ASGPU_HOST_CHUNK overrides, 64 Ki .. 4 Mi).
+size_t host_chunk_rays();
 const int HostStreams = 3;
 const uint64_t QueueRing = 256;
 

@@ -57,6 +57,8 @@ struct KernelArgs
     int                 max_steps;          // node tests per lane and loop iteration
     int                 step_threshold;     // lanes that must be able to advance for another step
     int                 enter_late;         // enter assembly instances once per iteration, all lanes together
+    int                 enter_threshold;    // ... once this many lanes want to
+    int                 enter_min_busy;     // ... or fewer lanes than this can advance without entering
 };
 
 __device__ __forceinline__ void store_hit(asgpu_hit* out, const SceneView& s, const double t, const Hit& hit, const bool found, const bool raw_item)
@@ -505,9 +507,16 @@ wide_kernel(const KernelArgs args)
         }
 
         // ---- enter assembly instances: every lane that reached one in this iteration, together ------
-        if (!LEAN && __ballot_sync(0xFFFFFFFFu, want_enter) != 0)
+        if (!LEAN)
         {
-            if (want_enter) enter_instance();
+            const unsigned want = __ballot_sync(0xFFFFFFFFu, want_enter);
+            if (want != 0)
+            {
+                // Enter when enough lanes wait for it, or when too few lanes could go on without.
+                bool go = __popc(want) >= args.enter_threshold;
+                if (!go) go = __popc(__ballot_sync(0xFFFFFFFFu, active && !traversed && !held && !want_enter)) < args.enter_min_busy;
+                if (go && want_enter) enter_instance();
+            }
         }
 
         // ---- gather this step's triangle candidates -------------------------------------------------
@@ -620,11 +629,11 @@ wide_kernel(const KernelArgs args)
 // prefer fuller refills and more steps per iteration; instanced scenes re-do the set-up on every
 // instance entry and prefer to refill earlier.  ASGPU_REFILL / ASGPU_FLUSH / ASGPU_STALL /
 // ASGPU_STEPS / ASGPU_STEPTHR / ASGPU_PREFETCH override them for experiments.
-struct Tuning { int refill, flush, stall, prefetch, steps, step_threshold, enter_late; };
+struct Tuning { int refill, flush, stall, prefetch, steps, step_threshold, enter_late, enter_threshold, enter_min_busy; };
 
 Tuning tuning(const bool single_instance)
 {
-    Tuning v = { 8, 16, 16, 0, 3, 8, 1 };              // prefetch: measured neutral (C2) to -5 % (C3 probes), off
+    Tuning v = { 8, 16, 16, 0, 3, 8, 1, 6, 8 };              // prefetch: measured neutral (C2) to -5 % (C3 probes), off
     if (single_instance) { v.refill = 16; v.stall = 24; v.steps = 4; v.enter_late = 0; }
     if (const char* e = getenv("ASGPU_REFILL")) v.refill = atoi(e);
     if (const char* e = getenv("ASGPU_FLUSH")) v.flush = atoi(e);
@@ -633,6 +642,8 @@ Tuning tuning(const bool single_instance)
     if (const char* e = getenv("ASGPU_STEPS")) v.steps = atoi(e);
     if (const char* e = getenv("ASGPU_STEPTHR")) v.step_threshold = atoi(e);
     if (const char* e = getenv("ASGPU_ENTERLATE")) v.enter_late = atoi(e);
+    if (const char* e = getenv("ASGPU_ENTERTHR")) v.enter_threshold = atoi(e);
+    if (const char* e = getenv("ASGPU_ENTERBUSY")) v.enter_min_busy = atoi(e);
     if (v.refill < 1) v.refill = 1;
     if (v.flush < 1) v.flush = 1;
     if (v.stall < 1) v.stall = 1;
@@ -729,6 +740,8 @@ int launch_trace(
     args.max_steps = knobs.steps;
     args.step_threshold = knobs.step_threshold;
     args.enter_late = knobs.enter_late;
+    args.enter_threshold = knobs.enter_threshold;
+    args.enter_min_busy = knobs.enter_min_busy;
 
     cudaError_t err = cudaMemsetAsync(queue, 0, sizeof(unsigned long long), stream);
     if (err != cudaSuccess) return static_cast<int>(err);

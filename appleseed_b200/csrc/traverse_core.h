@@ -633,8 +633,30 @@ ASGPU_HD void make_wide_ray(const double org[3], const double dir[3], const doub
         // (no fp64 division).  |dir| = 0 gives rn = rf = +inf, a NaN gives NaNs (dropped by the
         // min/max of the box test = "no constraint").
         const double mag = fabs(d);                 // also clears the sign of -0.0
+#if ASGPU_DEVICE_CODE
+        {
+            // One conversion and one rcp.approx: |magf / mag - 1| <= 2^-24 for a normal magf and
+            // rcp.approx.f32 is within 2^-23 (PTX ISA), so r * (1 -+ 2^-21), rounded outward,
+            // brackets 1 / mag.  Outside the normal range the bounds are set by hand.
+            const float magf = __double2float_rn(mag);
+            float rn, rf;
+            if (magf >= 1.17549435e-38f && magf <= 4.0e37f)
+            {
+                const float r = rcp_approx(magf);
+                rn = __fmul_rd(r, 0.99999952316284f);
+                rf = __fmul_ru(r, 1.00000047683716f);
+            }
+            else if (mag == 0.0) rn = rf = __int_as_float(0x7F800000);
+            else if (magf > 4.0e37f) { rn = 0.0f; rf = 3.0e-38f; }         // 1 / mag < 2.5e-38
+            else if (magf == magf) { rn = 8.0e37f; rf = __int_as_float(0x7F800000); }     // 1 / mag > 8.5e37
+            else { rn = magf; rf = 3.0e-38f; }                              // NaN direction
+            w.rn[a] = rn;
+            w.rf[a] = rf;
+        }
+#else
         w.rn[a] = frcp_dn(d2f_up(mag));
         w.rf[a] = frcp_up(d2f_dn(mag));
+#endif
         const double o = org[a];
         float lo, hi;
         if (w.shift != 0.0)

@@ -6,6 +6,8 @@
 A "step" is one pass of the hot path over one batch of synthetic rays of the named workload
 (BASELINE.json configs):
 
+  c1: the reference's own CPU-runnable case -- Cornell box (32 triangles), 512 x 512 pinhole primaries
+      (+ one ambient-occlusion probe per primary hit, extra figure); tiny: launch-latency bound on a GPU
   c2 (default, the 1-GPU configuration):  999 698-triangle displaced grid, 16 Mi coherent pinhole
       primaries + 16 Mi incoherent cosine-weighted bounce rays, closest hit
   c3: 9 999 392-triangle fBm terrain x 64 assembly instances, 32 Mi incoherent closest-hit rays
@@ -60,6 +62,7 @@ MI = 1 << 20
 
 def workload_name(args) -> str:
     return {
+        "c1": "C1: Cornell box (32 triangles), %d pinhole primary rays, closest hit (+ AO probes, extra)%.0s",
         "c2": "C2: 999698-triangle displaced grid, %d coherent primary + %d incoherent cosine bounce rays, closest hit",
         "c3": "C3: 9999392-triangle fBm terrain x 64 assembly instances, %d incoherent closest-hit rays (+ %d shadow probes, extra)",
         "c4": "C4: 2000000 moving triangles (msc=1), %d incoherent closest-hit rays with random time (+ %d probes, extra)",
@@ -68,6 +71,8 @@ def workload_name(args) -> str:
 
 
 def make_scene(args):
+    if args.workload == "c1":
+        return scenes.scene_c1()
     if args.workload == "c2":
         return scenes.scene_c2(args.res or 707)
     if args.workload in ("c3", "c5"):
@@ -228,6 +233,8 @@ def time_cpu(oscene, rays: RayBatch, probe: bool, threads: int, repeats: int = 1
 def cpu_sample(args, desc, rank: int = 0):
     """The bounded sample of the workload's rays the CPU arm is timed on."""
     n = args.cpu_rays if args.cpu_rays > 0 else args.rays
+    if args.workload == "c1":
+        return scenes.rays_c1_primary(), 0
     if args.workload == "c2":
         half = n // 2
         prim = primary_rays_c2(args.rays // 2, rank)
@@ -393,6 +400,17 @@ def run_gpu(args):
         bounce = scenes.bounce_rays(pts, nrm, 1 + rank, flags=VIS_DIFFUSE)
         batches = [("coherent_primary", p), ("incoherent_bounce", PinnedRays(bounce, device))]
         probe_batch = None
+    elif args.workload == "c1":
+        prim = scenes.rays_c1_primary()
+        n = len(prim)
+        hits_dev = torch.empty(n * HIT_BYTES, dtype=torch.uint8, device=device)
+        p = PinnedRays(prim, device)
+        isect.trace_device(p.dev, hits_dev)
+        torch.cuda.synchronize()
+        hits = hits_from_tensor(hits_dev, n)
+        _, ao = scenes.rays_c1_ao(desc, prim, hits)
+        batches = [("primary", p)]
+        probe_batch = PinnedRays(ao, device)
     else:
         inc = incoherent_rays(desc, n, 2 + rank, time=(args.workload == "c4"))
         p = PinnedRays(inc, device)
@@ -774,7 +792,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"])
+    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--width", type=int, default=1920, help="c5: image width")
     ap.add_argument("--height", type=int, default=1080, help="c5: image height")
     ap.add_argument("--spp", type=int, default=64, help="c5: camera paths per pixel")
@@ -785,7 +803,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.rays == 0:
-        args.rays = {"c2": 16 * MI, "c3": 32 * MI, "c4": 16 * MI, "c5": 16 * MI}[args.workload]
+        args.rays = {"c1": 512 * 512, "c2": 16 * MI, "c3": 32 * MI, "c4": 16 * MI, "c5": 16 * MI}[args.workload]
     if args.impl == "reference":
         run_reference(args)
     elif args.workload == "c5":

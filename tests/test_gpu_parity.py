@@ -292,3 +292,38 @@ def test_moving_triangles_at_scale_time_slices_change_nothing(engine, orc, msc, 
     assert exact[idx].tobytes() == ref.tobytes()
     parity.compare_hits(o, sub, sliced[idx], ref)
     parity.compare_probes(o, sub, occ[idx], o.trace_probe(sub, threads=8))
+
+
+def test_full_size_c3_properties(engine, orc):
+    """BASELINE config C3 at full size (9 999 392 triangles x 64 assembly instances): the two
+    independent kernels agree everywhere, probes agree with closest hit, oracle on a sample."""
+    from appleseed_b200 import scenes
+    desc = scenes.scene_c3(2236, 8)
+    ctx, isect = make(engine, desc)
+    info = ctx.info()
+    assert info["triangle_count"] == 9_999_392 and info["instance_count"] == 64
+    lo, hi = scenes.scene_bbox(desc)
+    ext = hi - lo
+    rays = scenes.uniform_sphere_rays(2_000_000, lo - 0.02 * ext, hi + 0.02 * ext, 23)
+    wide = isect.trace(rays)
+    exact = isect.trace(rays, exact=True)
+    assert np.array_equal(wide["prim_type"], exact["prim_type"])
+    hit = exact["prim_type"] == 2
+    assert 0.1 < hit.mean() < 0.9
+    assert np.allclose(wide["t"][hit], exact["t"][hit], rtol=1e-5, atol=0.0)
+    same = (wide["tri_slot"] == exact["tri_slot"]) & (wide["assembly_instance"] == exact["assembly_instance"])
+    assert same.mean() > 0.9999
+    assert len(np.unique(exact["assembly_instance"][hit])) == 64             # every instance is reachable
+    occ = isect.trace_probe(rays)
+    assert np.array_equal(occ.astype(bool), hit)
+    assert np.array_equal(isect.trace_probe(rays, exact=True), occ)
+    # Parent shading points at scale: refined points sit within a few ulps of the hit point.
+    par = isect.refine_and_offset(rays, exact)
+    assert np.all(par["assembly_instance"][hit] == exact["assembly_instance"][hit]) and np.all(par["assembly_instance"][~hit] == 0xFFFFFFFF)
+    idx = np.arange(0, len(rays), 100)
+    o = orc.scene(desc)
+    sub = rays.take(idx)
+    ref = o.trace(sub, threads=8)
+    assert exact[idx].tobytes() == ref.tobytes()
+    parity.compare_hits(o, sub, wide[idx], ref)
+    assert par[idx].tobytes() == o.refine_offset(sub, ref, threads=8).tobytes()
