@@ -10,6 +10,7 @@
 
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdint>
 #include <mutex>
 #include <string>
@@ -65,9 +66,9 @@ struct asgpu_scene
     asgpu::BlobHeader   header;
     asgpu::SceneView    view;
     unsigned long long* queue = nullptr;        // device, ring of QueueRing cursors (one per launch)
-    uint64_t            queue_next = 0;
+    std::atomic<uint64_t> queue_next{0};    // trace calls may come from several threads (one stream each)
     unsigned long long* counters = nullptr;     // device, asgpu_counters layout (first 6 words)
-    uint64_t            launches = 0;
+    std::atomic<uint64_t> launches{0};
     std::mutex          mutex;
     asgpu::Staging      staging[asgpu::HostStreams];
     bool                staging_ready = false;
