@@ -582,9 +582,14 @@ ASGPU_HD bool exact_trace(const SceneView& s, Ray& ray, Hit& hit, Stats& stats, 
             parent_origin(parent, meta.z, local.dir, local.org);
             if (meta.x == 0xFFFFFFFFu) continue;
             TreeDesc td; load_tree_desc(s, meta.x, td);
-            const bool found = exact_triangle_tree<ANY, COUNT>(s.blob, td, local, hit, item, stats);
+            // The instance gets its own record (AssemblyLeafVisitor's asm_inst_shading_point) and is
+            // committed only when it is strictly nearer (assemblytree.cpp:727-744): a triangle that
+            // re-computes exactly the current t in a coincident instance must not replace the hit.
+            Hit local_hit;
+            local_hit.item = 0xFFFFFFFFu; local_hit.slot = 0; local_hit.segment = 0; local_hit.u = local_hit.v = 0.0f;
+            const bool found = exact_triangle_tree<ANY, COUNT>(s.blob, td, local, local_hit, item, stats);
             if (ANY) { if (found) return true; }
-            else if (local.tmax < ray.tmax) ray.tmax = local.tmax;      // only a hit shrinks local.tmax
+            else if (local_hit.item != 0xFFFFFFFFu && local.tmax < ray.tmax) { ray.tmax = local.tmax; hit = local_hit; }
         }
         if (ray_tmax > ray.tmax) ray_tmax = ray.tmax;
         if (sp == 0) break;

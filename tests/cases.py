@@ -115,3 +115,85 @@ CASES = {
     "c4_msc3": lambda: case_c4(3),
     "mixed": case_mixed,
 }
+
+
+# ---------------------------------------------------------------------------------------------
+# Random scenes: triangle soups, arbitrary affine object / assembly instances (rotations about
+# any axis, non-uniform and negative scales = handedness swaps), random leaf sizes and SAH costs,
+# random visibility masks, overlapping and coincident geometry (exact-t ties), rays with random
+# intervals and flags.  Used by the differential tests of both tiers.
+# ---------------------------------------------------------------------------------------------
+
+def _random_affine(rng, spread, allow_flip=True):
+    q = rng.normal(size=4)
+    q /= np.linalg.norm(q)
+    w, x, y, z = q
+    r = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                  [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                  [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+    s = rng.uniform(0.4, 1.8, size=3)
+    if allow_flip and rng.random() < 0.3:
+        s[rng.integers(0, 3)] *= -1.0
+    m = np.eye(4)
+    m[:3, :3] = r @ np.diag(s)
+    m[:3, 3] = rng.uniform(-spread, spread, size=3)
+    return m
+
+
+def _random_mesh(rng, moving):
+    kind = rng.integers(0, 3)
+    if kind == 0:           # soup of small random triangles
+        nt = int(rng.integers(20, 400))
+        centres = rng.uniform(-1, 1, size=(nt, 1, 3))
+        v = (centres + rng.normal(scale=rng.uniform(0.02, 0.3), size=(nt, 3, 3))).reshape(-1, 3)
+        t = np.arange(nt * 3, dtype=np.uint32).reshape(nt, 3)
+    elif kind == 1:         # displaced grid, some triangles duplicated (coincident geometry)
+        g = scenes.grid_mesh(int(rng.integers(3, 14)), "sines")
+        v, t = g.vertices.copy(), g.triangles.copy()
+        dup = rng.integers(0, len(t), size=max(1, len(t) // 10))
+        t = np.concatenate([t, t[dup]])
+    else:                   # a few large triangles spanning everything (big leaves, deep overlap)
+        nt = int(rng.integers(1, 12))
+        v = rng.uniform(-1.5, 1.5, size=(nt * 3, 3))
+        t = np.arange(nt * 3, dtype=np.uint32).reshape(nt, 3)
+    v = v.astype(np.float32)
+    poses = None
+    if moving:
+        msc = int(rng.choice([1, 2, 3]))
+        drift = rng.normal(scale=0.08, size=(1, msc, 3)).cumsum(axis=1) + rng.normal(scale=0.02, size=(len(v), msc, 3))
+        poses = (v[:, None, :] + drift).astype(np.float32)
+    return Mesh(v, t, triangle_pa=(np.arange(len(t)) % 7).astype(np.uint16), vertex_poses=poses)
+
+
+def random_scene(seed, n_rays=6000, moving=True):
+    rng = np.random.default_rng(1000 + seed)
+    vis_choices = np.array([VIS_ALL, VIS_ALL, VIS_CAMERA | VIS_DIFFUSE, VIS_SHADOW, VIS_ALL & ~VIS_SHADOW], dtype=np.uint64)
+    n_static = int(rng.integers(1, 4))
+    meshes = [_random_mesh(rng, False) for _ in range(n_static)]
+    if moving and rng.random() < 0.6:
+        meshes.append(_random_mesh(rng, True))
+    assemblies = []
+    for _ in range(int(rng.integers(1, 4))):
+        # One triangle tree holds either static or moving meshes with a single msc (the reference's
+        # Debug build asserts a uniform pose count per tree, triangletree.cpp:824).
+        want_moving = len(meshes) > n_static and rng.random() < 0.4
+        pool = [len(meshes) - 1] if want_moving else list(range(n_static))
+        ois = [ObjectInstance(int(rng.choice(pool)), _random_affine(rng, 0.8), int(rng.choice(vis_choices)))
+               for _ in range(int(rng.integers(1, 4)))]
+        assemblies.append(Assembly(ois, max_leaf_size=int(rng.choice([1, 2, 2, 4, 8])),
+                                   interior_node_traversal_cost=float(rng.choice([1.0, 1.0, 2.5])),
+                                   triangle_intersection_cost=float(rng.choice([1.0, 1.0, 0.5]))))
+    insts = [AssemblyInstance(int(rng.integers(0, len(assemblies))), _random_affine(rng, 2.5), int(rng.choice(vis_choices)))
+             for _ in range(int(rng.integers(1, 7)))]
+    if rng.random() < 0.3:
+        insts.append(AssemblyInstance(insts[0].assembly_index, insts[0].local_to_parent.copy()))       # coincident instance: exact ties
+    desc = SceneDesc(meshes, assemblies, insts)
+    lo, hi = scenes.scene_bbox(desc)
+    ext = np.maximum(hi - lo, 1e-3)
+    rays = scenes.uniform_sphere_rays(n_rays, lo - 0.1 * ext, hi + 0.1 * ext, 77 + seed, time=True)
+    rays.flags = rng.choice(np.array([VIS_CAMERA, VIS_SHADOW, VIS_DIFFUSE, VIS_ALL], dtype=np.uint32), size=n_rays)
+    diag = float(np.linalg.norm(ext))
+    rays.tmin = rng.choice(np.array([0.0, 0.0, 0.1 * diag, -0.2 * diag]), size=n_rays)
+    rays.tmax = rng.choice(np.array([scenes.DBL_MAX, scenes.DBL_MAX, 0.5 * diag, 1.2 * diag]), size=n_rays)
+    rays.dir[::11] *= rng.uniform(0.2, 5.0)                # directions need not be unit length (instance space)
+    return desc, rays
