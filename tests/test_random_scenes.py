@@ -64,7 +64,7 @@ def test_kernels_on_random_scenes(orc, seed):
     for k in ("rays", "assembly_nodes_visited", "instances_visited", "triangle_nodes_visited", "triangles_tested", "hits"):
         assert c[k] == cref[k], k
     parity.compare_hits(o, rays, isect.trace(rays), ref)
-    assert isect.trace(rays, sort=True).tobytes() == isect.trace(rays).tobytes()
+    parity.compare_hits(o, rays, isect.trace(rays, sort=True), ref)      # coincident geometry: ties may resolve differently
     pref = o.trace_probe(rays, threads=4)
     assert np.array_equal(isect.trace_probe(rays, exact=True), pref)
     parity.compare_probes(o, rays, isect.trace_probe(rays), pref)
