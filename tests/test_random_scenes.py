@@ -68,3 +68,52 @@ def test_kernels_on_random_scenes(orc, seed):
     pref = o.trace_probe(rays, threads=4)
     assert np.array_equal(isect.trace_probe(rays, exact=True), pref)
     parity.compare_probes(o, rays, isect.trace_probe(rays), pref)
+
+
+def _static_rays(rays):
+    from appleseed_b200.scene import RayBatch
+    return RayBatch(rays.org, rays.dir, rays.tmin, rays.tmax, flags=rays.flags)
+
+
+@pytest.mark.parametrize("seed", SEEDS[:20])
+def test_refine_and_parents_on_random_static_scenes(orc, asref, seed):
+    """refine_and_offset with arbitrary affine (also handedness-swapping) object and assembly
+    instances and unnormalised ray directions: restatement == reference headers."""
+    desc, rays = cases.random_scene(seed, moving=False)
+    rays = _static_rays(rays)
+    o, r = orc.scene(desc), asref.scene(desc)
+    hits = o.trace(rays, threads=2)
+    pa, pb = o.refine_offset(rays, hits, threads=2), r.refine_offset(rays, hits, threads=2)
+    assert pa.tobytes() == pb.tobytes()
+    h = hits["prim_type"] == 2
+    child = rays.take(np.nonzero(h)[0])
+    child.org = child.org + hits["t"][h][:, None] * child.dir          # from the hit point, onwards and backwards
+    child.dir[1::2] *= -1.0
+    child.tmin = np.zeros(len(child))
+    assert o.trace_parents(child, pa[h], threads=2).tobytes() == r.trace_parents(child, pa[h], threads=2).tobytes()
+    assert np.array_equal(o.trace_probe_parents(child, pa[h], threads=2), r.trace_probe_parents(child, pa[h], threads=2))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", GPU_SEEDS[:10])
+def test_refine_and_parents_kernels_on_random_static_scenes(orc, seed):
+    from appleseed_b200.intersector import Intersector, TraceContext
+    desc, rays = cases.random_scene(seed, n_rays=20000, moving=False)
+    rays = _static_rays(rays)
+    o = orc.scene(desc)
+    isect = Intersector(TraceContext(desc, device=0))
+    hits = o.trace(rays, threads=4)
+    assert isect.trace(rays, exact=True).tobytes() == hits.tobytes()
+    par = isect.refine_and_offset(rays, hits)
+    assert par.tobytes() == o.refine_offset(rays, hits, threads=4).tobytes()
+    h = hits["prim_type"] == 2
+    child = rays.take(np.nonzero(h)[0])
+    child.org = child.org + hits["t"][h][:, None] * child.dir
+    child.dir[1::2] *= -1.0
+    child.tmin = np.zeros(len(child))
+    ref = o.trace_parents(child, par[h], threads=4)
+    assert isect.trace_with_parents(child, par[h], exact=True).tobytes() == ref.tobytes()
+    parity.compare_hits(o, child, isect.trace_with_parents(child, par[h]), ref)
+    pref = o.trace_probe_parents(child, par[h], threads=4)
+    assert np.array_equal(isect.trace_probe_with_parents(child, par[h], exact=True), pref)
+    parity.compare_probes(o, child, isect.trace_probe_with_parents(child, par[h]), pref)
