@@ -113,7 +113,14 @@ def test_refine_and_parents_kernels_on_random_static_scenes(orc, seed):
     child.tmin = np.zeros(len(child))
     ref = o.trace_parents(child, par[h], threads=4)
     assert isect.trace_with_parents(child, par[h], exact=True).tobytes() == ref.tobytes()
-    parity.compare_hits(o, child, isect.trace_with_parents(child, par[h]), ref)
+    # orc_two_nearest knows nothing about parents, so the tie rule is applied by hand: wherever the
+    # identity differs the two candidates must be an EXACT tie (duplicated triangles: same t, u, v).
+    wide = isect.trace_with_parents(child, par[h])
+    same = wide.view(np.uint8).reshape(len(ref), -1) == ref.view(np.uint8).reshape(len(ref), -1)
+    differs = np.nonzero(~same.all(axis=1))[0]
+    for k in ("t", "u", "v", "prim_type", "assembly_instance"):
+        assert np.array_equal(wide[k][differs], ref[k][differs]), k
+    assert len(differs) <= 0.02 * len(ref) + 5
     pref = o.trace_probe_parents(child, par[h], threads=4)
     assert np.array_equal(isect.trace_probe_with_parents(child, par[h], exact=True), pref)
     parity.compare_probes(o, child, isect.trace_probe_with_parents(child, par[h]), pref)
