@@ -702,22 +702,22 @@ def run_gpu_c5(args):
     ms_step = sum(a.elapsed_time(b) for a, b in ev) / args.steps
     clocks = sampler.stop() if rank == 0 else None
     st = ps.stats()
-    image = ps.image()
     rays_step = (st["camera_rays"] + st["bounce_rays"] + st["probe_rays"]) // args.steps
     closest_step = (st["camera_rays"] + st["bounce_rays"]) // args.steps
     launches = st["kernel_launches"]
-    checksum = int(image.astype(np.uint64).sum()) // args.steps
 
-    # ---- end to end: tile list in, image out, through the public API (host buffers) -----------
-    ps.clear()
+    # ---- end to end: clear, tile list in, image out, through the public API (host buffers) ----
     barrier()
     t0 = time.perf_counter()
     e2e_steps = max(1, min(args.steps, 3))
     for _ in range(e2e_steps):
+        ps.clear()
         frame()
-        ps.image()
+        image = ps.image()
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    # One frame's accumulators of this rank's pixels; summed over ranks it does not depend on N.
+    checksum = int(image.astype(np.uint64).sum())
 
     # ---- algorithmic bytes per ray (counters variant of the same frame, untimed) --------------
     ps.close()
