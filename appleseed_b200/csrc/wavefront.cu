@@ -178,7 +178,7 @@ __device__ __forceinline__ void add_stats(unsigned long long* stats, const unsig
 
 __device__ __forceinline__ void normalize3(double v[3])
 {
-    const double inv = 1.0 / sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+    const double inv = rsqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
     v[0] *= inv; v[1] *= inv; v[2] *= inv;
 }
 
@@ -256,19 +256,15 @@ shade_kernel(const StreamParams p, const SceneView s, const QueueView in, const 
          i += static_cast<unsigned long long>(gridDim.x) * blockDim.x)
     {
         bool vertex = false;
-        uint32_t path = 0;
+        uint32_t path = 0, pixel = 0, identity = 0;
         double o[3] = { 0.0, 0.0, 0.0 }, nrm[3] = { 0.0, 1.0, 0.0 };
         if (i < n)
         {
             path = in.path[i];
-            const uint32_t pixel = path / p.spp;
+            pixel = path / p.spp;
             const unsigned long long* hw = reinterpret_cast<const unsigned long long*>(hits + i);
             const unsigned long long w0 = hw[0], w2 = hw[2], w3 = hw[3], w4 = hw[4];
-            if (static_cast<uint32_t>(w4 >> 32) == 0)
-            {
-                atomicAdd(image + static_cast<size_t>(pixel) * 4 + 2, 1u);
-                ++local[StatEscaped];
-            }
+            if (static_cast<uint32_t>(w4 >> 32) == 0) ++local[StatEscaped];
             else
             {
                 vertex = true;
@@ -299,9 +295,28 @@ shade_kernel(const StreamParams p, const SceneView s, const QueueView in, const 
                     #pragma unroll
                     for (int k = 0; k < 3; ++k) o[k] += p.eps * nrm[k];
                 }
-                atomicAdd(image + static_cast<size_t>(pixel) * 4 + 0, 1u);
-                atomicAdd(image + static_cast<size_t>(pixel) * 4 + 3, primitive * 2654435761u + object_instance * 0x9E3779B1u + meta.z * 0x85EBCA6Bu + slot);
+                identity = primitive * 2654435761u + object_instance * 0x9E3779B1u + meta.z * 0x85EBCA6Bu + slot;
                 ++local[StatHits];
+            }
+        }
+
+        // Per-pixel accumulators.  Consecutive rays of a queue are mostly samples of the same pixel
+        // (64 per pixel): the lanes of a pixel are summed in the warp first (match + reduce), one
+        // atomic per pixel, counter and warp instead of one per ray.
+        {
+            const unsigned live = __ballot_sync(0xFFFFFFFFu, i < n);
+            if (i < n)
+            {
+                const unsigned peers = __match_any_sync(live, pixel);
+                const unsigned hits_here = __reduce_add_sync(peers, vertex ? 1u : 0u);
+                const unsigned escaped_here = __popc(peers) - hits_here;
+                const unsigned identity_sum = __reduce_add_sync(peers, identity);
+                if ((threadIdx.x & 31) == static_cast<unsigned>(__ffs(peers) - 1))
+                {
+                    uint32_t* px = image + static_cast<size_t>(pixel) * 4;
+                    if (hits_here) { atomicAdd(px + 0, hits_here); atomicAdd(px + 3, identity_sum); }
+                    if (escaped_here) atomicAdd(px + 2, escaped_here);
+                }
             }
         }
 
@@ -335,9 +350,11 @@ shade_kernel(const StreamParams p, const SceneView s, const QueueView in, const 
             if (vertex)
             {
                 const double s0 = rng(p.seed, path, depth + 1, 0), s1 = rng(p.seed, path, depth + 1, 1);
-                double sin_phi, cos_phi;
-                sincospi(2.0 * s0, &sin_phi, &cos_phi);
-                const double cos_theta = sqrt(1.0 - s1), sin_theta = sqrt(s1);
+                // The local direction in float (it is renormalised in double below; the sampling
+                // pattern does not need more, the unit length does).
+                float sin_phi, cos_phi;
+                sincospif(2.0f * static_cast<float>(s0), &sin_phi, &cos_phi);
+                const float cos_theta = sqrtf(1.0f - static_cast<float>(s1)), sin_theta = sqrtf(static_cast<float>(s1));
                 // Orthonormal frame (u, nrm, v).
                 double aux[3] = { 1.0, 0.0, 0.0 };
                 if (fabs(nrm[0]) > 0.9) { aux[0] = 0.0; aux[1] = 1.0; }
@@ -366,12 +383,17 @@ accumulate_kernel(const StreamParams p, const QueueView probes, const uint8_t* _
 {
     const unsigned long long n = min(*probes.count, probes.capacity);
     unsigned local[StatCount] = { 0, 0, 0, 0, 0, 0 };
-    for (unsigned long long i = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+    const unsigned long long padded = (n + 31ull) & ~31ull;
+    for (unsigned long long i = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < padded;
          i += static_cast<unsigned long long>(gridDim.x) * blockDim.x)
     {
-        if (occluded[i] == 0)
+        const bool lit = i < n && occluded[i] == 0;
+        const unsigned live = __ballot_sync(0xFFFFFFFFu, lit);
+        if (lit)
         {
-            atomicAdd(image + static_cast<size_t>(probes.path[i] / p.spp) * 4 + 1, 1u);
+            const uint32_t pixel = probes.path[i] / p.spp;
+            const unsigned peers = __match_any_sync(live, pixel);
+            if ((threadIdx.x & 31) == static_cast<unsigned>(__ffs(peers) - 1)) atomicAdd(image + static_cast<size_t>(pixel) * 4 + 1, static_cast<uint32_t>(__popc(peers)));
             ++local[StatUnoccluded];
         }
     }
