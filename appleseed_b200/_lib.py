@@ -9,7 +9,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-from .scene import CRays, CSceneDesc
+from .scene import CIntersectionFilter, CRays, CSceneDesc
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libasgpu.so")
@@ -61,7 +61,7 @@ class AssemblyTreeView(C.Structure):
 
 
 class SourceGeometry(C.Structure):
-    _fields_ = [("objects", C.c_void_p), ("object_count", C.c_uint32), ("reserved", C.c_uint32)]
+    _fields_ = [("objects", C.c_void_p), ("object_count", C.c_uint32), ("reserved", C.c_uint32), ("filters", C.c_void_p)]
 
 
 class SceneInfo(C.Structure):

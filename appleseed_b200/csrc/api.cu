@@ -67,6 +67,7 @@ void make_view(asgpu_scene* s)
     s->view.top_wnode_count = s->header.top_wnode_count;
     s->view.wide_stack_need = s->header.wide_stack_need;
     s->view.has_motion = s->header.moving_triangle_count != 0 ? 1u : 0u;
+    s->view.has_filters = (s->header.flags & BlobHasFilters) ? 1u : 0u;
     // Source geometry present for every tree?  (Small table: read it back.)
     s->has_source = s->header.tree_count != 0;
     std::vector<TreeDesc> descs(s->header.tree_count);

@@ -897,6 +897,46 @@ int flatten_scene(
                 { error = "triangle key outside the source geometry"; return ASGPU_E_INVALID; }
             d.src_objects = writer.append(objs);
             d.src_object_count = sg.object_count;
+
+            if (sg.filters)
+            {
+                // Intersection filters: masks and UVs copied as they are, plus the primitive-attribute
+                // index of every leaf slot (the material mask is chosen by it).
+                std::vector<FilterRecord> frs(sg.object_count);
+                bool any = false;
+                auto put_mask = [&](const asgpu_alpha_mask& m, MaskRecord& out)
+                {
+                    std::memset(&out, 0, sizeof(out));
+                    if (!m.bits || m.width == 0 || m.height == 0) return;
+                    out.bits = writer.append(m.bits, size_t((m.width + 7) / 8) * m.height);
+                    out.width = m.width; out.height = m.height;
+                };
+                for (uint32_t o = 0; o < sg.object_count; ++o)
+                {
+                    const asgpu_intersection_filter& f = sg.filters[o];
+                    FilterRecord& fr = frs[o];
+                    std::memset(&fr, 0, sizeof(fr));
+                    if (!f.uv) continue;
+                    if (f.material_mask_count && !f.material_masks) { error = "null material mask array"; return ASGPU_E_INVALID; }
+                    any = true;
+                    fr.uv = writer.append(f.uv, size_t(sg.objects[o].triangle_count) * 6 * sizeof(float));
+                    put_mask(f.object_mask, fr.object_mask);
+                    std::vector<MaskRecord> mats(f.material_mask_count);
+                    for (uint32_t k = 0; k < f.material_mask_count; ++k) put_mask(f.material_masks[k], mats[k]);
+                    if (!mats.empty()) fr.material_masks = writer.append(mats);
+                    fr.material_mask_count = f.material_mask_count;
+                }
+                if (any)
+                {
+                    const AsTriangleKey* keys = static_cast<const AsTriangleKey*>(trees[ti].triangle_keys);
+                    std::vector<uint16_t> pa(et.keys.size());
+                    for (size_t k = 0; k < pa.size(); ++k) pa[k] = keys[k].triangle_pa;
+                    d.key_pa = writer.append(pa);
+                    d.filters = writer.append(frs);
+                    d.filter_count = sg.object_count;
+                    header.flags |= BlobHasFilters;
+                }
+            }
         }
 
         if (want_wide)

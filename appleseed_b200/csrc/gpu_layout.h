@@ -28,11 +28,12 @@ namespace asgpu
 {
 
 const uint32_t BlobMagic = 0x42534131u;     // "1ASB"
-const uint32_t BlobVersion = 6;
+const uint32_t BlobVersion = 7;
 const uint32_t WideStackMax = 64;           // deepest traversal stack any wide kernel variant offers
 const uint64_t SectionAlign = 256;
 
 const uint32_t InteriorMark = 0xFFFFFFFFu;
+const uint32_t BlobHasFilters = 1u << 8;     // BlobHeader::flags: some tree carries intersection filters
 
 // EXACT: binary node of a triangle tree, 64 bytes.  box[] = [minL minR maxL maxR] x (x, y, z),
 // the order of bvh::Node::m_bbox_data (bvh_node.h:141-162).
@@ -112,9 +113,29 @@ struct TreeDesc
     uint64_t    src_objects;    // SrcObject[src_object_count] or 0: source geometry for refine_and_offset
     uint64_t    wslices;        // WSlice[wnode_count * wslice_count] or 0: time-sliced child boxes (trees with motion)
     uint32_t    wslice_count;   // T: slice j bounds the children over ray times [j / T, (j + 1) / T]
+    uint32_t    filter_count;   // entries of `filters` (0 = the tree has no intersection filters)
+    uint64_t    filters;        // FilterRecord[filter_count], indexed by object instance
+    uint64_t    key_pa;         // uint16_t[slot_count]: TriangleKey::m_triangle_pa per leaf slot (trees with filters)
+};
+static_assert(sizeof(TreeDesc) == 128, "TreeDesc");
+
+// Intersection filter of one object instance (intersectionfilter.h): uv == 0 means "no filter".
+struct MaskRecord
+{
+    uint64_t    bits;           // BitMask2 storage, 0 = no mask
+    uint32_t    width, height;
+};
+static_assert(sizeof(MaskRecord) == 16, "MaskRecord");
+
+struct FilterRecord
+{
+    uint64_t    uv;             // float[triangle_count * 6] or 0
+    MaskRecord  object_mask;
+    uint64_t    material_masks; // MaskRecord[material_mask_count]
+    uint32_t    material_mask_count;
     uint32_t    pad;
 };
-static_assert(sizeof(TreeDesc) == 112, "TreeDesc");
+static_assert(sizeof(FilterRecord) == 40, "FilterRecord");
 
 // WIDE, trees with moving triangles: the quantised child planes of one wide node for one slice of
 // the ray-time axis, same frame (origin, exp) and same slots as the node's own qlo / qhi (which

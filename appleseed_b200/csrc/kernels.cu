@@ -169,6 +169,7 @@ struct WideShared
     uint32_t            cur_item[BlockThreads];
     float               world_rcp[6][BlockThreads];     // world-space reciprocal bounds (rn, rf), saved while inside an instance
     uint32_t            world_oct[BlockThreads];
+    unsigned long long  filter_tree[BlockThreads];      // blob offset of the current tree's TreeDesc when it has intersection filters, else 0
 };
 
 // Starts the fetch of one wide node (80 bytes, 16-byte aligned: at most two 128-byte lines) into L1.
@@ -185,10 +186,17 @@ __device__ __forceinline__ unsigned long long ordered_key(const double t)
     return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
 }
 
+// Out of line on purpose: the filter is a rare path (scenes with cut-out geometry only) and must
+// not cost the traversal loop registers.
+__device__ __noinline__ bool filter_accept_call(const uint8_t* blob, const uint8_t* tree, const uint32_t slot, const double u, const double v)
+{
+    return filter_accept(blob, tree, slot, u, v);
+}
+
 // Tests `count` (<= 32) queued candidates, one per lane.  Entry = (index of the triangle record in
 // the source lane's current tree) << 5 | source lane.  Closest hit: the nearest accepted candidate of each source lane
 // updates that lane's tmax and hit record (ties: lowest queue position).  Any hit: marks the lane.
-template <bool ANY, bool COUNT, int STACK>
+template <bool ANY, bool COUNT, int STACK, bool FILTERS>
 __device__ __forceinline__ void test_candidates(
     WideShared<STACK>& sm, const uint8_t* blob, const unsigned long long* entries, const unsigned count,
     const unsigned lane, const unsigned warp_thread0, Stats& stats)
@@ -214,6 +222,8 @@ __device__ __forceinline__ void test_candidates(
         TriD tri;
         if (fetch_triangle<ANY>(blob + sm.tri_base[st] + (e >> 5) * sizeof(TriRecord), blob + sm.pose_base[st], ray, tri, slot, segment))
             hit = mt_test<!ANY>(tri, ray, t, u, v);
+        // Optionally filter intersections (triangletree.cpp:1404-1411; closest hit only).
+        if (!ANY && FILTERS && hit && sm.filter_tree[st] != 0) hit = filter_accept_call(blob, blob + sm.filter_tree[st], slot, u, v);
     }
     if (ANY)
     {
@@ -279,7 +289,10 @@ __device__ __forceinline__ void restore_world_ray(const asgpu_rays& rays, const 
 // LEAN = the scene has one assembly instance and no moving triangles (e.g. C2): nothing ever comes
 // back to world space and no tree has time slices, so the instantiation drops the batched instance
 // entry, the saved world-space ray and the indirection to the child planes (measured: 3-5 %).
-template <bool ANY, bool COUNT, int STACK, int MINB, bool LEAN>
+// FILTERS = some tree carries intersection filters (cut-out geometry): only then does the
+// closest-hit instantiation contain the alpha-mask lookup (it costs registers: -3 % when compiled
+// into the common kernel).
+template <bool ANY, bool COUNT, int STACK, int MINB, bool LEAN, bool FILTERS>
 __global__ void __launch_bounds__(BlockThreads, MINB)
 wide_kernel(const KernelArgs args)
 {
@@ -376,6 +389,8 @@ wide_kernel(const KernelArgs args)
             sm.tri_base[tid] = static_cast<uint64_t>(o_tris.x) | (static_cast<uint64_t>(o_tris.y) << 32);
             sm.pose_base[tid] = static_cast<uint64_t>(o_poses.x) | (static_cast<uint64_t>(o_poses.y) << 32);
             sm.cur_item[tid] = item;
+            if (FILTERS)
+                sm.filter_tree[tid] = load4(tp + offsetof(TreeDesc, filter_count)) != 0 ? s.trees + static_cast<uint64_t>(meta.x) * sizeof(TreeDesc) : 0ull;
             cur_item = item;
             ngroup.y = 0; tgroup.y = 0;
             if (wnode_count != 0) fetch = 0;
@@ -550,7 +565,7 @@ wide_kernel(const KernelArgs args)
                 while (queued >= 32)
                 {
                     queued -= 32;
-                    test_candidates<ANY, COUNT, STACK>(sm, blob, queue + queued, 32, lane, warp_thread0, stats);
+                    test_candidates<ANY, COUNT, STACK, FILTERS>(sm, blob, queue + queued, 32, lane, warp_thread0, stats);
                     tested = true;
                 }
             }
@@ -571,7 +586,7 @@ wide_kernel(const KernelArgs args)
                     if (queued >= 32)
                     {
                         queued -= 32;
-                        test_candidates<ANY, COUNT, STACK>(sm, blob, queue + queued, 32, lane, warp_thread0, stats);
+                        test_candidates<ANY, COUNT, STACK, FILTERS>(sm, blob, queue + queued, 32, lane, warp_thread0, stats);
                         tested = true;
                     }
                     pushers = __ballot_sync(0xFFFFFFFFu, pending != 0);
@@ -585,7 +600,7 @@ wide_kernel(const KernelArgs args)
             const unsigned stalled = __ballot_sync(0xFFFFFFFFu, !active || held || (traversed && waiting));
             if (queued >= args.flush_threshold || __popc(stalled) >= args.stall_threshold)
             {
-                test_candidates<ANY, COUNT, STACK>(sm, blob, queue, queued, lane, warp_thread0, stats);
+                test_candidates<ANY, COUNT, STACK, FILTERS>(sm, blob, queue, queued, lane, warp_thread0, stats);
                 queued = 0;
                 tested = true;
             }
@@ -679,24 +694,25 @@ cudaError_t launch_persistent(Kernel kernel, const KernelArgs& args, const size_
 // and run ~10 % slower (profiles/README.md).
 const int WideMinBlocks = 5;
 
-template <int STACK, bool LEAN>
+template <int STACK, bool LEAN, bool FILTERS>
 cudaError_t launch_wide(const KernelArgs& args, const bool any_hit, const bool count, const int sm_count, cudaStream_t stream)
 {
     const size_t smem = sizeof(WideShared<STACK>);
-    if (any_hit) return count ? launch_persistent(wide_kernel<true, true, STACK, WideMinBlocks, LEAN>, args, smem, sm_count, stream)
-                              : launch_persistent(wide_kernel<true, false, STACK, WideMinBlocks, LEAN>, args, smem, sm_count, stream);
-    return count ? launch_persistent(wide_kernel<false, true, STACK, WideMinBlocks, LEAN>, args, smem, sm_count, stream)
-                 : launch_persistent(wide_kernel<false, false, STACK, WideMinBlocks, LEAN>, args, smem, sm_count, stream);
+    // Shadow probes ignore intersection filters (TriangleLeafProbeVisitor has none).
+    if (any_hit) return count ? launch_persistent(wide_kernel<true, true, STACK, WideMinBlocks, LEAN, false>, args, smem, sm_count, stream)
+                              : launch_persistent(wide_kernel<true, false, STACK, WideMinBlocks, LEAN, false>, args, smem, sm_count, stream);
+    return count ? launch_persistent(wide_kernel<false, true, STACK, WideMinBlocks, LEAN, FILTERS>, args, smem, sm_count, stream)
+                 : launch_persistent(wide_kernel<false, false, STACK, WideMinBlocks, LEAN, FILTERS>, args, smem, sm_count, stream);
 }
 
-template <bool LEAN>
+template <bool LEAN, bool FILTERS>
 cudaError_t launch_wide_depth(const KernelArgs& args, const uint32_t stack_need, const bool any_hit, const bool count, const int sm_count, cudaStream_t stream)
 {
     // The traversal stack lives in shared memory; its depth is the scene's (flatten.cpp computes
     // the bound), rounded up to one of the compiled variants.
-    if (stack_need <= 16) return launch_wide<16, LEAN>(args, any_hit, count, sm_count, stream);
-    if (stack_need <= 24) return launch_wide<24, LEAN>(args, any_hit, count, sm_count, stream);
-    return launch_wide<WideStackMax, LEAN>(args, any_hit, count, sm_count, stream);
+    if (stack_need <= 16) return launch_wide<16, LEAN, FILTERS>(args, any_hit, count, sm_count, stream);
+    if (stack_need <= 24) return launch_wide<24, LEAN, FILTERS>(args, any_hit, count, sm_count, stream);
+    return launch_wide<WideStackMax, LEAN, FILTERS>(args, any_hit, count, sm_count, stream);
 }
 
 }   // anonymous namespace
@@ -749,9 +765,10 @@ int launch_trace(
     const bool count = counters != nullptr;
     if (wide)
     {
-        const bool lean = scene.item_count <= 1 && !scene.has_motion && getenv("ASGPU_NO_LEAN") == nullptr;
-        err = lean ? launch_wide_depth<true>(args, scene.wide_stack_need, any_hit, count, sm_count, stream)
-                   : launch_wide_depth<false>(args, scene.wide_stack_need, any_hit, count, sm_count, stream);
+        const bool lean = scene.item_count <= 1 && !scene.has_motion && !scene.has_filters && getenv("ASGPU_NO_LEAN") == nullptr;
+        if (lean) err = launch_wide_depth<true, false>(args, scene.wide_stack_need, any_hit, count, sm_count, stream);
+        else if (scene.has_filters) err = launch_wide_depth<false, true>(args, scene.wide_stack_need, any_hit, count, sm_count, stream);
+        else err = launch_wide_depth<false, false>(args, scene.wide_stack_need, any_hit, count, sm_count, stream);
     }
     else if (any_hit) err = count ? launch_persistent(trace_kernel<true, true>, args, 0, sm_count, stream)
                                   : launch_persistent(trace_kernel<true, false>, args, 0, sm_count, stream);

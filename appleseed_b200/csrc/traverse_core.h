@@ -160,6 +160,7 @@ struct SceneView
     uint32_t        tree_count, item_count, top_node_count, top_wnode_count;
     uint32_t        wide_stack_need;
     uint32_t        has_motion;         // some tree has moving triangles (time-sliced child planes)
+    uint32_t        has_filters;        // some tree carries intersection filters
 };
 
 struct Ray
@@ -369,6 +370,69 @@ ASGPU_HD bool fetch_triangle(const uint8_t* record, const uint8_t* poses, const 
 }
 
 // ------------------------------------------------------------------------------------------
+// IntersectionFilter::accept (intersectionfilter.h:169-205) with AlphaMask::is_opaque (:103-112):
+// float arithmetic in the reference's order (Vector2f * float, sums left to right, clamp, truncate).
+// `tree` points at the TreeDesc of a tree with filters; `slot` is the reference leaf slot.
+// ------------------------------------------------------------------------------------------
+
+ASGPU_HD uint64_t load_u64(const void* p)
+{
+    const uint2 w = load8(p);
+    return static_cast<uint64_t>(w.x) | (static_cast<uint64_t>(w.y) << 32);
+}
+
+ASGPU_HD bool mask_is_opaque(const uint8_t* blob, const uint8_t* mask, const float ux, const float uy)
+{
+    const uint64_t bits = load_u64(mask);
+    const uint2 dim = load8(mask + 8);
+    const float max_x = fsub(static_cast<float>(dim.x), 1.0f), max_y = fsub(static_cast<float>(dim.y), 1.0f);
+    float fx = fmul(ux, static_cast<float>(dim.x)), fy = fmul(uy, static_cast<float>(dim.y));
+    fx = fx < 0.0f ? 0.0f : fx > max_x ? max_x : fx;
+    fy = fy < 0.0f ? 0.0f : fy > max_y ? max_y : fy;
+    const uint64_t ix = static_cast<uint64_t>(fx), iy = static_cast<uint64_t>(fy);
+    const uint8_t byte = blob[bits + iy * ((dim.x + 7u) / 8u) + ix / 8u];
+    return ((byte >> (ix & 7u)) & 1u) != 0;
+}
+
+ASGPU_HD bool filter_accept(const uint8_t* blob, const uint8_t* tree, const uint32_t slot, const double u, const double v)
+{
+    if (u != u || v != v) return true;
+    const uint2 key = load8(blob + load_u64(tree + offsetof(TreeDesc, keys)) + static_cast<uint64_t>(slot) * sizeof(HitKey));
+    if (key.x >= load4(tree + offsetof(TreeDesc, filter_count))) return true;
+    const uint8_t* fr = blob + load_u64(tree + offsetof(TreeDesc, filters)) + static_cast<uint64_t>(key.x) * sizeof(FilterRecord);
+    const uint64_t uv_off = load_u64(fr + offsetof(FilterRecord, uv));
+    if (uv_off == 0) return true;                                           // no filter on this object instance
+    const uint8_t* pap = blob + load_u64(tree + offsetof(TreeDesc, key_pa)) + static_cast<uint64_t>(slot) * 2;
+    const uint32_t pa = static_cast<uint32_t>(pap[0]) | (static_cast<uint32_t>(pap[1]) << 8);
+    const uint8_t* obj_mask = fr + offsetof(FilterRecord, object_mask);
+    const bool has_obj = load_u64(obj_mask) != 0;
+    const uint8_t* mtl_mask = nullptr;
+    if (pa < load4(fr + offsetof(FilterRecord, material_mask_count)))
+    {
+        mtl_mask = blob + load_u64(fr + offsetof(FilterRecord, material_masks)) + static_cast<uint64_t>(pa) * sizeof(MaskRecord);
+        if (load_u64(mtl_mask) == 0) mtl_mask = nullptr;
+    }
+    if (!has_obj && mtl_mask == nullptr) return true;
+    const float fu = static_cast<float>(u), fv = static_cast<float>(v);
+    const float w = fsub(fsub(1.0f, fu), fv);
+    const uint8_t* t = blob + uv_off + static_cast<uint64_t>(key.y) * 24;
+    float uv[2];
+#if ASGPU_DEVICE_CODE
+    #pragma unroll
+#endif
+    for (int c = 0; c < 2; ++c)
+    {
+        float x = fmul(u2f(load4(t + c * 4)), w);
+        x = fadd(x, fmul(u2f(load4(t + 8 + c * 4)), fu));
+        x = fadd(x, fmul(u2f(load4(t + 16 + c * 4)), fv));
+        uv[c] = x;
+    }
+    if (has_obj && !mask_is_opaque(blob, obj_mask, uv[0], uv[1])) return false;
+    if (mtl_mask != nullptr) return mask_is_opaque(blob, mtl_mask, uv[0], uv[1]);
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------
 // EXACT traversal.
 // ------------------------------------------------------------------------------------------
 
@@ -415,7 +479,7 @@ ASGPU_HD bool slab_child(const double box[12], const int side, const Ray& ray, c
 // Bottom level on one triangle tree.  `ray` is the instance-space ray; its tmax shrinks on hits
 // (closest hit).  Returns true on the first hit for ANY.
 template <bool ANY, bool COUNT>
-ASGPU_HD bool exact_triangle_tree(const uint8_t* blob, const TreeDesc& td, Ray& ray, Hit& hit, const uint32_t item, Stats& stats)
+ASGPU_HD bool exact_triangle_tree(const uint8_t* blob, const TreeDesc& td, const uint8_t* td_ptr, Ray& ray, Hit& hit, const uint32_t item, Stats& stats)
 {
     RayInfoD info; make_ray_info(ray, info);
     const bool motion = td.moving > 0;
@@ -496,6 +560,8 @@ ASGPU_HD bool exact_triangle_tree(const uint8_t* blob, const TreeDesc& td, Ray& 
             if (mt_test<!ANY>(tri, ray, t, u, v))
             {
                 if (ANY) return true;
+                // Optionally filter intersections (triangletree.cpp:1404-1411; closest hit only).
+                if (td.filter_count != 0 && !filter_accept(blob, td_ptr, slot, u, v)) continue;
                 ray.tmax = t;
                 hit.u = static_cast<float>(u);
                 hit.v = static_cast<float>(v);
@@ -587,7 +653,8 @@ ASGPU_HD bool exact_trace(const SceneView& s, Ray& ray, Hit& hit, Stats& stats, 
             // re-computes exactly the current t in a coincident instance must not replace the hit.
             Hit local_hit;
             local_hit.item = 0xFFFFFFFFu; local_hit.slot = 0; local_hit.segment = 0; local_hit.u = local_hit.v = 0.0f;
-            const bool found = exact_triangle_tree<ANY, COUNT>(s.blob, td, local, local_hit, item, stats);
+            const bool found = exact_triangle_tree<ANY, COUNT>(s.blob, td, s.blob + s.trees + static_cast<uint64_t>(meta.x) * sizeof(TreeDesc),
+                                                               local, local_hit, item, stats);
             if (ANY) { if (found) return true; }
             else if (local_hit.item != 0xFFFFFFFFu && local.tmax < ray.tmax) { ray.tmax = local.tmax; hit = local_hit; }
         }
@@ -856,6 +923,7 @@ struct WideTraversal
     uint32_t        qstride;
     const uint8_t*  wtris;
     const uint8_t*  poses;
+    const uint8_t*  filter_tree;        // TreeDesc of the current tree when it has intersection filters
     uint2           ngroup, tgroup;
     uint32_t        fetch;              // wide node to fetch next, 0xFFFFFFFF = none
     uint32_t        sp;
@@ -870,6 +938,7 @@ struct WideTraversal
         qbase = wnodes + 32; qstride = sizeof(WNode);
         wtris = nullptr;
         poses = nullptr;
+        filter_tree = nullptr;
         ngroup.x = 0; ngroup.y = 0;
         tgroup.x = 0; tgroup.y = 0;
         fetch = s.top_wnode_count != 0 ? 0u : 0xFFFFFFFFu;
@@ -910,6 +979,7 @@ struct WideTraversal
                 double t, u, v;
                 if (mt_test<!ANY>(tri, ray, t, u, v))
                 {
+                    if (!ANY && filter_tree != nullptr && !filter_accept(s.blob, filter_tree, slot, u, v)) continue;
                     hit.item = cur_item;
                     if (ANY) return true;
                     ray.tmax = t;
@@ -947,6 +1017,7 @@ struct WideTraversal
                 else { qbase = wnodes + 32; qstride = sizeof(WNode); }
                 wtris = s.blob + td.wtris;
                 poses = s.blob + td.poses;
+                filter_tree = td.filter_count != 0 ? s.blob + s.trees + static_cast<uint64_t>(meta.x) * sizeof(TreeDesc) : nullptr;
                 cur_item = item;
                 ngroup.y = 0; tgroup.y = 0;
                 if (td.wnode_count != 0) fetch = 0;

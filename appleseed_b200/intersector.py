@@ -156,7 +156,10 @@ class TraceContext:
     """Owns the flattened scene on one GPU."""
 
     def __init__(self, desc: Optional[SceneDesc] = None, device: int = 0, flags: int = _lib.SCENE_DEFAULT,
-                 threads: int = 0, trees: Optional[HostTrees] = None, _handle=None, source_geometry: bool = True):
+                 threads: int = 0, trees: Optional[HostTrees] = None, _handle=None, source_geometry: bool = True,
+                 filters: Optional[dict] = None):
+        """``filters``: {(triangle tree index, object instance index): scene.IntersectionFilter} --
+        ``TriangleTree::m_intersection_filters`` (cut-out geometry, closest hit only)."""
         self.lib = _lib.load()
         self.device = device
         self._borrowed_blob = None
@@ -172,9 +175,18 @@ class TraceContext:
             n = trees.triangle_tree_count
             views = (_lib.TriangleTreeView * max(1, n))()
             sources = (_lib.SourceGeometry * max(1, n))()
+            keep = []
             for i in range(n):
                 views[i] = trees.triangle_tree_view(i)
                 sources[i] = trees.source_geometry(i)
+                mine = {o: f for (t, o), f in (filters or {}).items() if t == i}
+                if mine:
+                    arr = (_lib.CIntersectionFilter * max(1, sources[i].object_count))()
+                    for o, f in mine.items():
+                        arr[o], k = f.to_c()
+                        keep.append(k)
+                    keep.append(arr)
+                    sources[i].filters = C.cast(arr, C.c_void_p)
             top = trees.assembly_tree_view()
             self.handle = self.lib.asgpu_scene_create_ex(views, n, C.byref(top), sources if source_geometry else None, flags, device)
             self.build_seconds = trees.build_seconds

@@ -251,6 +251,59 @@ class SceneDesc:
         return desc, keep
 
 
+class CAlphaMask(C.Structure):
+    _fields_ = [("bits", C.c_void_p), ("width", C.c_uint32), ("height", C.c_uint32)]
+
+
+class CIntersectionFilter(C.Structure):
+    _fields_ = [("object_mask", CAlphaMask), ("material_masks", C.POINTER(CAlphaMask)), ("material_mask_count", C.c_uint32),
+                ("reserved", C.c_uint32), ("uv", C.c_void_p)]
+
+
+def pack_mask(opaque: np.ndarray) -> np.ndarray:
+    """A boolean image [height, width] as foundation::BitMask2 storage (bitmask.h:
+    bits[y * ((width + 7) / 8) + x / 8] bit (x & 7))."""
+    opaque = np.asarray(opaque, dtype=bool)
+    h, w = opaque.shape
+    padded = np.zeros((h, (w + 7) // 8 * 8), dtype=bool)
+    padded[:, :w] = opaque
+    return np.ascontiguousarray(np.packbits(padded, axis=1, bitorder="little"))
+
+
+@dataclass
+class IntersectionFilter:
+    """``renderer::IntersectionFilter`` of one object instance (intersectionfilter.h): an optional
+    object alpha mask, optional per-material alpha masks (indexed by the triangle's
+    primitive-attribute index) and three UV pairs per triangle.  Masks are boolean images
+    [height, width], True = opaque."""
+    uv: np.ndarray                                  # (triangle_count, 3, 2) float32
+    object_mask: Optional[np.ndarray] = None
+    material_masks: Optional[List[Optional[np.ndarray]]] = None
+
+    def to_c(self):
+        keep = []
+        f = CIntersectionFilter()
+
+        def mask(m):
+            c = CAlphaMask()
+            if m is not None:
+                bits = pack_mask(m)
+                keep.append(bits)
+                c.bits, c.width, c.height = bits.ctypes.data, m.shape[1], m.shape[0]
+            return c
+
+        f.object_mask = mask(self.object_mask)
+        mats = self.material_masks or []
+        arr = (CAlphaMask * max(1, len(mats)))(*[mask(m) for m in mats])
+        keep.append(arr)
+        f.material_masks = C.cast(arr, C.POINTER(CAlphaMask))
+        f.material_mask_count = len(mats)
+        uv = np.ascontiguousarray(self.uv, dtype=np.float32).reshape(-1)
+        keep.append(uv)
+        f.uv = uv.ctypes.data
+        return f, keep
+
+
 @dataclass
 class RayBatch:
     """The ShadingRay fields the path consumes (renderer/kernel/shading/shadingray.h:99-109,

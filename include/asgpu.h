@@ -160,10 +160,29 @@ typedef struct asgpu_source_object {
     double          parent_to_local[16];    /* ObjectInstance::get_transform().get_parent_to_local() */
 } asgpu_source_object;
 
+/* renderer::IntersectionFilter of one object instance (renderer/kernel/intersection/
+ * intersectionfilter.h:84-128, 169-205): cut-out geometry.  A closest-hit candidate is dropped when
+ * its interpolated UV falls on a transparent texel of the object's or its material's alpha mask
+ * (triangletree.cpp:1404-1411, 1455-1462); shadow probes ignore filters, as in the reference.
+ * Masks are foundation::BitMask2 images: bits[y * ((width + 7) / 8) + x / 8] >> (x & 7). */
+typedef struct asgpu_alpha_mask {
+    const uint8_t*  bits;               /* AlphaMask::m_bitmask storage, NULL = no mask */
+    uint32_t        width, height;
+} asgpu_alpha_mask;
+
+typedef struct asgpu_intersection_filter {
+    asgpu_alpha_mask        object_mask;            /* m_obj_alpha_mask */
+    const asgpu_alpha_mask* material_masks;         /* m_material_alpha_masks, indexed by TriangleKey::get_triangle_pa() */
+    uint32_t                material_mask_count;
+    uint32_t                reserved;
+    const float*            uv;                     /* m_uv: three (u, v) pairs per triangle; NULL = this object has no filter */
+} asgpu_intersection_filter;
+
 typedef struct asgpu_source_geometry {
     const asgpu_source_object* objects; /* indexed by object_instance_index (TriangleKey) */
     uint32_t        object_count;
     uint32_t        reserved;
+    const asgpu_intersection_filter* filters;   /* TriangleTree::m_intersection_filters: object_count entries, or NULL */
 } asgpu_source_geometry;
 
 /* ------------------------------------------------------------------------------------------

@@ -448,8 +448,51 @@ inline bool box_overlaps_triangle(const Box3f& b, const V3f& v0, const V3f& v1, 
     return true;
 }
 
+// IntersectionFilter (intersectionfilter.h:84-128, 169-205).
+struct AlphaMask
+{
+    std::vector<uint8_t>    bits;
+    uint32_t                width = 0, height = 0;
+    bool present() const { return width != 0 && height != 0; }
+    bool is_opaque(const float ux, const float uy) const
+    {
+        const float max_x = static_cast<float>(width) - 1.0f, max_y = static_cast<float>(height) - 1.0f;
+        float fx = ux * static_cast<float>(width), fy = uy * static_cast<float>(height);
+        fx = fx < 0.0f ? 0.0f : fx > max_x ? max_x : fx;
+        fy = fy < 0.0f ? 0.0f : fy > max_y ? max_y : fy;
+        const size_t ix = static_cast<size_t>(fx), iy = static_cast<size_t>(fy);
+        return (bits[iy * ((width + 7) / 8) + ix / 8] & (1u << (ix & 7))) != 0;
+    }
+};
+
+struct Filter
+{
+    AlphaMask               object_mask;
+    std::vector<AlphaMask>  material_masks;
+    std::vector<float>      uv;
+
+    bool accept(const uint32_t triangle_index, const uint32_t pa, const double u, const double v) const
+    {
+        if (u != u || v != v) return true;
+        const AlphaMask* mtl = pa < material_masks.size() && material_masks[pa].present() ? &material_masks[pa] : nullptr;
+        if (object_mask.present() || mtl)
+        {
+            const float fu = static_cast<float>(u), fv = static_cast<float>(v);
+            const float w = 1.0f - fu - fv;
+            const float* t = uv.data() + size_t(triangle_index) * 6;
+            float ux = t[0] * w, uy = t[1] * w;
+            ux += t[2] * fu; uy += t[3] * fu;
+            ux += t[4] * fv; uy += t[5] * fv;
+            if (object_mask.present() && !object_mask.is_opaque(ux, uy)) return false;
+            if (mtl) return mtl->is_opaque(ux, uy);
+        }
+        return true;
+    }
+};
+
 struct TriTree
 {
+    std::vector<std::unique_ptr<Filter>> filters;   // per object instance, or empty
     std::vector<Node>       nodes;
     std::vector<double>     node_bboxes;        // 6 doubles each: minx maxx miny maxy minz maxz
     std::vector<uint8_t>    leaf_data;
@@ -1055,6 +1098,12 @@ bool traverse_triangle_tree(const TriTree& tree, Ray& ray, const bool motion, Lo
                 double t, u, v;
                 if (mt_intersect(tri, ray, t, u, v))
                 {
+                    if (!tree.filters.empty())
+                    {
+                        const Key& key = tree.keys[slot];
+                        const Filter* f = key.object_instance_index < tree.filters.size() ? tree.filters[key.object_instance_index].get() : nullptr;
+                        if (f && !f->accept(key.triangle_index, key.pa, u, v)) continue;
+                    }
                     hit.hit = true;
                     hit.slot = slot;
                     hit.motion_segment = base_index;
@@ -1070,7 +1119,12 @@ bool traverse_triangle_tree(const TriTree& tree, Ray& ray, const bool motion, Lo
             else
             {
                 double t, u, v;
-                if (mt_intersect(tri, ray, t, u, v)) two->add(t);
+                if (mt_intersect(tri, ray, t, u, v))
+                {
+                    const Key& key = tree.keys[slot];
+                    const Filter* f = key.object_instance_index < tree.filters.size() ? tree.filters[key.object_instance_index].get() : nullptr;
+                    if (!f || f->accept(key.triangle_index, key.pa, u, v)) two->add(t);
+                }
             }
         }
 
@@ -1439,6 +1493,30 @@ void orc_trace_probe(const void* scene, const orc_rays* rays, size_t n, uint8_t*
         parts[tid] = local;
     });
     accumulate(counters, parts);
+}
+
+void orc_set_filter(void* scene, uint32_t assembly, uint32_t object_instance, const orc_intersection_filter* filter)
+{
+    Scene& s = *static_cast<Scene*>(scene);
+    const int ti = s.assembly_tree[assembly];
+    if (ti < 0 || !filter) return;
+    TriTree& tree = *s.trees[ti];
+    const orc_assembly& a = s.desc.assemblies[assembly];
+    if (tree.filters.empty()) tree.filters.resize(a.object_instance_count);
+    const uint32_t triangle_count = s.desc.meshes[a.object_instances[object_instance].mesh_index].triangle_count;
+    auto copy_mask = [](const orc_alpha_mask& m, AlphaMask& out)
+    {
+        if (!m.bits || m.width == 0 || m.height == 0) return;
+        out.width = m.width; out.height = m.height;
+        out.bits.assign(m.bits, m.bits + size_t((m.width + 7) / 8) * m.height);
+    };
+    std::unique_ptr<Filter> f(new Filter());
+    copy_mask(filter->object_mask, f->object_mask);
+    f->material_masks.resize(filter->material_mask_count);
+    for (uint32_t i = 0; i < filter->material_mask_count; ++i) copy_mask(filter->material_masks[i], f->material_masks[i]);
+    if (filter->uv) f->uv.assign(filter->uv, filter->uv + size_t(triangle_count) * 6);
+    else f->uv.assign(size_t(triangle_count) * 6, 0.0f);
+    tree.filters[object_instance] = std::move(f);
 }
 
 void orc_two_nearest(const void* scene, const orc_rays* rays, size_t n, double* t1, double* t2, int threads)

@@ -116,6 +116,8 @@ class Oracle:
         self._trace_par.argtypes = [C.c_void_p, C.POINTER(CRays), C.c_void_p, C.c_size_t, C.c_void_p, C.c_int]
         self._probe_par = getattr(L, p + "_trace_probe_parents")
         self._probe_par.argtypes = [C.c_void_p, C.POINTER(CRays), C.c_void_p, C.c_size_t, C.c_void_p, C.c_int]
+        self._set_filter = getattr(L, p + "_set_filter")
+        self._set_filter.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
         if prefix == "orc":
             self._two = L.orc_two_nearest
             self._two.argtypes = [C.c_void_p, C.POINTER(CRays), C.c_size_t, C.c_void_p, C.c_void_p, C.c_int]
@@ -252,6 +254,11 @@ class OracleScene:
         parents = np.ascontiguousarray(parents)
         self.oracle._probe_par(self.handle, C.byref(cr), parents.ctypes.data, n, out.ctypes.data, threads)
         return out
+
+    def set_filter(self, assembly: int, object_instance: int, flt) -> None:
+        """Attach an ``appleseed_b200.scene.IntersectionFilter`` to one object instance (copied)."""
+        c, keep = flt.to_c()
+        self.oracle._set_filter(self.handle, assembly, object_instance, C.byref(c))
 
     def two_nearest(self, rays: RayBatch, threads: int = 1):
         n = len(rays)

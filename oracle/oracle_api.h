@@ -142,6 +142,23 @@ typedef struct orc_parent {
     double          geo_normal[3];          /* m_refine_space_geo_normal (face-forwarded, not unit length) */
 } orc_parent;
 
+/* renderer::IntersectionFilter of one object instance (renderer/kernel/intersection/
+ * intersectionfilter.h): alpha masks are foundation::BitMask2 images
+ * (bits[y * ((width + 7) / 8) + x / 8] >> (x & 7)), uv = m_uv (three Vector2f per triangle).
+ * Applied by the closest-hit leaf visitor only (triangletree.cpp:1404-1411, 1455-1462). */
+typedef struct orc_alpha_mask {
+    const uint8_t*  bits;                   /* NULL = no mask */
+    uint32_t        width, height;
+} orc_alpha_mask;
+
+typedef struct orc_intersection_filter {
+    orc_alpha_mask          object_mask;            /* m_obj_alpha_mask */
+    const orc_alpha_mask*   material_masks;         /* m_material_alpha_masks, indexed by TriangleKey::get_triangle_pa() */
+    uint32_t                material_mask_count;
+    uint32_t                reserved;
+    const float*            uv;                     /* triangle_count * 6 floats */
+} orc_intersection_filter;
+
 #define ORC_DECLARE(prefix)                                                                         \
     void*   prefix##_scene_create(const orc_scene_desc* desc);                                      \
     void    prefix##_scene_destroy(void* scene);                                                    \
@@ -160,7 +177,10 @@ typedef struct orc_parent {
     void    prefix##_trace_parents(const void* scene, const orc_rays* rays,                         \
                                    const orc_parent* parents, size_t n, orc_hit* out, int threads); \
     void    prefix##_trace_probe_parents(const void* scene, const orc_rays* rays,                   \
-                                   const orc_parent* parents, size_t n, uint8_t* out, int threads);
+                                   const orc_parent* parents, size_t n, uint8_t* out, int threads); \
+    /* Attach (a copy of) an intersection filter to one object instance of one assembly. */        \
+    void    prefix##_set_filter(void* scene, uint32_t assembly, uint32_t object_instance,           \
+                                const orc_intersection_filter* filter);
 
 ORC_DECLARE(orc)
 ORC_DECLARE(asref)

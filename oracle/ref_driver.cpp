@@ -30,6 +30,7 @@
 #include "foundation/math/transform.h"
 #include "foundation/math/vector.h"
 #include "foundation/memory/alignedallocator.h"
+#include "foundation/utility/bitmask.h"
 #include "foundation/utility/casts.h"
 #include "renderer/kernel/intersection/refining.h"
 #include "renderer/utility/triangle.h"
@@ -106,6 +107,72 @@ struct TriLeafProbeVisitor;
 // TriangleTree (renderer/kernel/intersection/triangletree.h:72-125).
 //
 
+// IntersectionFilter (renderer/kernel/intersection/intersectionfilter.h:84-128, 169-205) over the
+// reference's own BitMask2, Vector2f, clamp and truncate.  (The class itself needs the texture
+// system to BUILD its masks and cannot be compiled here; masks arrive ready-made.)
+struct RefAlphaMask
+{
+    const float     m_max_x, m_max_y;
+    BitMask2        m_bitmask;
+
+    RefAlphaMask(const orc_alpha_mask& src)
+      : m_max_x(static_cast<float>(src.width) - 1.0f)
+      , m_max_y(static_cast<float>(src.height) - 1.0f)
+      , m_bitmask(src.width, src.height)
+    {
+        const size_t block_width = (src.width + 7) / 8;
+        for (size_t y = 0; y < src.height; ++y)
+            for (size_t x = 0; x < src.width; ++x)
+                m_bitmask.set(x, y, (src.bits[y * block_width + x / 8] >> (x & 7)) & 1);
+    }
+
+    bool is_opaque(const Vector2f& uv) const
+    {
+        const float fx = clamp(uv[0] * m_bitmask.get_width(), 0.0f, m_max_x);
+        const float fy = clamp(uv[1] * m_bitmask.get_height(), 0.0f, m_max_y);
+        const size_t ix = truncate<size_t>(fx);
+        const size_t iy = truncate<size_t>(fy);
+        return m_bitmask.is_set(ix, iy);
+    }
+
+    bool is_transparent(const Vector2f& uv) const { return !is_opaque(uv); }
+};
+
+struct RefIntersectionFilter
+{
+    std::unique_ptr<RefAlphaMask>               m_obj_alpha_mask;
+    std::vector<std::unique_ptr<RefAlphaMask>>  m_material_alpha_masks;
+    std::vector<Vector2f>                       m_uv;
+
+    bool accept(const TriangleKey& triangle_key, const double u, const double v) const
+    {
+        if (u != u || v != v)
+            return true;
+
+        const RefAlphaMask* mtl_alpha_mask =
+            triangle_key.m_triangle_pa < m_material_alpha_masks.size() ? m_material_alpha_masks[triangle_key.m_triangle_pa].get() : nullptr;
+
+        if (m_obj_alpha_mask || mtl_alpha_mask)
+        {
+            const size_t triangle_index = triangle_key.m_triangle_index;
+            const float fu = static_cast<float>(u);
+            const float fv = static_cast<float>(v);
+            const Vector2f uv =
+                  m_uv[triangle_index * 3 + 0] * (1.0f - fu - fv)
+                + m_uv[triangle_index * 3 + 1] * fu
+                + m_uv[triangle_index * 3 + 2] * fv;
+
+            if (m_obj_alpha_mask && m_obj_alpha_mask->is_transparent(uv))
+                return false;
+
+            if (mtl_alpha_mask)
+                return mtl_alpha_mask->is_opaque(uv);
+        }
+
+        return true;
+    }
+};
+
 class RefTriangleTree
   : public bvh::Tree<NodeVector>
 {
@@ -122,6 +189,7 @@ class RefTriangleTree
     std::vector<TriangleKey>    m_triangle_keys;
     std::vector<std::uint8_t>   m_leaf_data;
     std::vector<GTriangleType>  m_slot_triangles;       // per leaf slot: the static triangle the leaf stores (checker convenience)
+    std::vector<std::unique_ptr<RefIntersectionFilter>> m_intersection_filters;    // per object instance, or empty
     size_t                      m_static_triangle_count = 0;
     size_t                      m_moving_triangle_count = 0;
 
@@ -719,6 +787,14 @@ struct TriLeafVisitor
                 double t, u, v;
                 if (triangle.intersect(ray, t, u, v))
                 {
+                    // Optionally filter intersections (triangletree.cpp:1404-1411).
+                    if (!m_tree.m_intersection_filters.empty())
+                    {
+                        const TriangleKey& triangle_key = m_tree.m_triangle_keys[triangle_index];
+                        const RefIntersectionFilter* filter = m_tree.m_intersection_filters[triangle_key.m_object_instance_index].get();
+                        if (filter && !filter->accept(triangle_key, u, v))
+                            continue;
+                    }
                     m_has_hit = true;
                     m_hit_triangle_index = triangle_index;
                     m_hit_motion_segment = 0;
@@ -761,6 +837,14 @@ struct TriLeafVisitor
                 double t, u, v;
                 if (triangle.intersect(ray, t, u, v))
                 {
+                    // Optionally filter intersections (triangletree.cpp:1455-1462).
+                    if (!m_tree.m_intersection_filters.empty())
+                    {
+                        const TriangleKey& triangle_key = m_tree.m_triangle_keys[triangle_index];
+                        const RefIntersectionFilter* filter = m_tree.m_intersection_filters[triangle_key.m_object_instance_index].get();
+                        if (filter && !filter->accept(triangle_key, u, v))
+                            continue;
+                    }
                     m_has_hit = true;
                     m_hit_triangle_index = triangle_index;
                     m_hit_motion_segment = static_cast<std::uint32_t>(base_index);
@@ -1465,6 +1549,28 @@ void asref_trace_probe_parents(const void* scene_, const orc_rays* rays, const o
             out[i] = visitor.m_hit ? 1 : 0;
         }
     });
+}
+
+void asref_set_filter(void* scene_, uint32_t assembly, uint32_t object_instance, const orc_intersection_filter* filter)
+{
+    RefScene& scene = *static_cast<RefScene*>(scene_);
+    const int ti = scene.m_assembly_tree.m_assembly_tree_index[assembly];
+    if (ti < 0 || !filter) return;
+    RefTriangleTree& tree = *scene.m_assembly_tree.m_triangle_trees[ti];
+    const orc_assembly& a = scene.m_desc.assemblies[assembly];
+    if (tree.m_intersection_filters.empty()) tree.m_intersection_filters.resize(a.object_instance_count);
+    const size_t triangle_count = scene.m_desc.meshes[a.object_instances[object_instance].mesh_index].triangle_count;
+    std::unique_ptr<RefIntersectionFilter> f(new RefIntersectionFilter());
+    if (filter->object_mask.bits && filter->object_mask.width && filter->object_mask.height)
+        f->m_obj_alpha_mask.reset(new RefAlphaMask(filter->object_mask));
+    f->m_material_alpha_masks.resize(filter->material_mask_count);
+    for (uint32_t i = 0; i < filter->material_mask_count; ++i)
+        if (filter->material_masks[i].bits && filter->material_masks[i].width && filter->material_masks[i].height)
+            f->m_material_alpha_masks[i].reset(new RefAlphaMask(filter->material_masks[i]));
+    f->m_uv.resize(triangle_count * 3, Vector2f(0.0f));
+    if (filter->uv)
+        for (size_t i = 0; i < triangle_count * 3; ++i) f->m_uv[i] = Vector2f(filter->uv[i * 2], filter->uv[i * 2 + 1]);
+    tree.m_intersection_filters[object_instance] = std::move(f);
 }
 
 int asref_kat_ray_triangle(
