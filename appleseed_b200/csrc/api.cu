@@ -274,6 +274,12 @@ namespace
 
 asgpu_scene* adopt_blob_image(const std::vector<uint8_t>& image, const int device)
 {
+    {
+        // Structural check of what the flattener produced (offsets and counts of every table).
+        std::string error;
+        const int rc = validate_blob(image.data(), image.size(), error);
+        if (rc != ASGPU_OK) { fail(rc, "flattened scene failed validation: " + error); return nullptr; }
+    }
     asgpu_scene* s = new (std::nothrow) asgpu_scene();
     if (!s) { fail(ASGPU_E_NOMEM, "out of host memory"); return nullptr; }
     s->device = device;

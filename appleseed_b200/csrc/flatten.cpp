@@ -1039,8 +1039,32 @@ int validate_blob(const uint8_t* blob, size_t size, std::string& error)
         if (!inside(d.bnodes, uint64_t(d.bnode_count) * sizeof(BNodeF)) || !inside(d.wnodes, uint64_t(d.wnode_count) * sizeof(WNode)) ||
             !inside(d.keys, uint64_t(d.slot_count) * sizeof(HitKey)) || !inside(d.tris, d.tris ? uint64_t(d.slot_count) * sizeof(TriRecord) : 0) ||
             !inside(d.wtris, d.wtris ? uint64_t(d.slot_count) * sizeof(TriRecord) : 0) ||
-            !inside(d.wslices, uint64_t(d.wnode_count) * d.wslice_count * sizeof(WSlice)))
+            !inside(d.wslices, uint64_t(d.wnode_count) * d.wslice_count * sizeof(WSlice)) ||
+            !inside(d.src_objects, uint64_t(d.src_object_count) * sizeof(SrcObject)) ||
+            !inside(d.filters, uint64_t(d.filter_count) * sizeof(FilterRecord)) ||
+            !inside(d.key_pa, d.key_pa ? uint64_t(d.slot_count) * 2 : 0))
         { error = "blob tree section out of range"; return ASGPU_E_INVALID; }
+        for (uint32_t o = 0; o < d.src_object_count; ++o)
+        {
+            SrcObject so;
+            std::memcpy(&so, blob + d.src_objects + uint64_t(o) * sizeof(SrcObject), sizeof(so));
+            if (!inside(so.vertices, uint64_t(so.vertex_count) * 12) || !inside(so.triangles, uint64_t(so.triangle_count) * 12))
+            { error = "blob source geometry out of range"; return ASGPU_E_INVALID; }
+        }
+        for (uint32_t o = 0; o < d.filter_count; ++o)
+        {
+            FilterRecord fr;
+            std::memcpy(&fr, blob + d.filters + uint64_t(o) * sizeof(FilterRecord), sizeof(fr));
+            auto mask_ok = [&](const MaskRecord& m) { return m.bits == 0 || inside(m.bits, uint64_t((m.width + 7) / 8) * m.height); };
+            bool ok = mask_ok(fr.object_mask) && inside(fr.material_masks, uint64_t(fr.material_mask_count) * sizeof(MaskRecord));
+            for (uint32_t k = 0; ok && k < fr.material_mask_count; ++k)
+            {
+                MaskRecord m;
+                std::memcpy(&m, blob + fr.material_masks + uint64_t(k) * sizeof(MaskRecord), sizeof(m));
+                ok = mask_ok(m);
+            }
+            if (!ok) { error = "blob intersection filter out of range"; return ASGPU_E_INVALID; }
+        }
     }
     return ASGPU_OK;
 }

@@ -71,7 +71,17 @@ extern "C" {
 
 const char* hostsim_last_error() { return g_error.c_str(); }
 
+void* hostsim_scene_create_filtered(const asgpu_scene_desc* desc, uint32_t flags, int threads, uint32_t filter_count,
+                                    const uint32_t* filter_tree, const uint32_t* filter_object, const asgpu_intersection_filter* filters);
+
 void* hostsim_scene_create(const asgpu_scene_desc* desc, uint32_t flags, int threads)
+{
+    return hostsim_scene_create_filtered(desc, flags, threads, 0, nullptr, nullptr, nullptr);
+}
+
+// Same with intersection filters: filters[k] belongs to object instance filter_object[k] of triangle tree filter_tree[k].
+void* hostsim_scene_create_filtered(const asgpu_scene_desc* desc, uint32_t flags, int threads, uint32_t filter_count,
+                                    const uint32_t* filter_tree, const uint32_t* filter_object, const asgpu_intersection_filter* filters)
 {
     HostTrees trees;
     if (!build_host_trees(*desc, threads, trees, g_error)) return nullptr;
@@ -97,9 +107,34 @@ void* hostsim_scene_create(const asgpu_scene_desc* desc, uint32_t flags, int thr
     top.node_count = trees.assembly_tree.nodes.size();
     top.item_count = trees.assembly_tree.items.size();
 
+    // Source geometry (always) and the filters of the trees that have some.
+    std::vector<asgpu_source_geometry> sources(views.size());
+    std::vector<std::vector<asgpu_intersection_filter>> per_tree(views.size());
+    for (size_t i = 0; i < views.size(); ++i)
+    {
+        const HostTriangleTree& t = *trees.triangle_trees[i];
+        sources[i].objects = t.source_objects.empty() ? nullptr : t.source_objects.data();
+        sources[i].object_count = static_cast<uint32_t>(t.source_objects.size());
+        sources[i].reserved = 0;
+        sources[i].filters = nullptr;
+    }
+    for (uint32_t k = 0; k < filter_count; ++k)
+    {
+        std::vector<asgpu_intersection_filter>& v = per_tree[filter_tree[k]];
+        if (v.empty())
+        {
+            asgpu_intersection_filter none; std::memset(&none, 0, sizeof(none));
+            v.assign(sources[filter_tree[k]].object_count, none);
+        }
+        v[filter_object[k]] = filters[k];
+        sources[filter_tree[k]].filters = v.data();
+    }
+
     SimScene* s = new SimScene();
-    const int rc = flatten_scene(views.empty() ? nullptr : views.data(), static_cast<uint32_t>(views.size()), top, nullptr, flags, s->blob, g_error);
+    const int rc = flatten_scene(views.empty() ? nullptr : views.data(), static_cast<uint32_t>(views.size()), top,
+                                 sources.empty() ? nullptr : sources.data(), flags, s->blob, g_error);
     if (rc != ASGPU_OK) { delete s; return nullptr; }
+    if (validate_blob(s->blob.data(), s->blob.size(), g_error) != ASGPU_OK) { delete s; return nullptr; }
     BlobHeader h; std::memcpy(&h, s->blob.data(), sizeof(h));
     s->view.blob = s->blob.data();
     s->view.trees = h.trees; s->view.items = h.items; s->view.top_nodes = h.top_nodes;

@@ -16,6 +16,8 @@ def load():
     lib = C.CDLL(os.path.join(_HERE, "libhostsim.so"))
     lib.hostsim_scene_create.restype = C.c_void_p
     lib.hostsim_scene_create.argtypes = [C.POINTER(CSceneDesc), C.c_uint32, C.c_int]
+    lib.hostsim_scene_create_filtered.restype = C.c_void_p
+    lib.hostsim_scene_create_filtered.argtypes = [C.POINTER(CSceneDesc), C.c_uint32, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.hostsim_scene_destroy.argtypes = [C.c_void_p]
     lib.hostsim_last_error.restype = C.c_char_p
     lib.hostsim_blob_size.restype = C.c_size_t
@@ -26,10 +28,21 @@ def load():
 
 
 class SimScene:
-    def __init__(self, lib, desc: SceneDesc, flags=SCENE_EXACT | SCENE_WIDE, threads=4):
+    def __init__(self, lib, desc: SceneDesc, flags=SCENE_EXACT | SCENE_WIDE, threads=4, filters=None):
+        """``filters``: {(triangle tree index, object instance index): scene.IntersectionFilter}."""
+        from appleseed_b200.scene import CIntersectionFilter
         self.lib = lib
         self._cdesc, self._keep = desc.to_c()
-        self.handle = lib.hostsim_scene_create(C.byref(self._cdesc), flags, threads)
+        items = sorted((filters or {}).items())
+        n = len(items)
+        trees = np.array([k[0] for k, _ in items], dtype=np.uint32)
+        objs = np.array([k[1] for k, _ in items], dtype=np.uint32)
+        arr = (CIntersectionFilter * max(1, n))()
+        for i, (_, f) in enumerate(items):
+            arr[i], keep = f.to_c()
+            self._keep.append(keep)
+        self.handle = lib.hostsim_scene_create_filtered(C.byref(self._cdesc), flags, threads, n, trees.ctypes.data if n else None,
+                                                        objs.ctypes.data if n else None, C.cast(arr, C.c_void_p))
         if not self.handle:
             raise RuntimeError(lib.hostsim_last_error().decode())
 

@@ -71,6 +71,22 @@ def test_restatement_equals_reference_headers(orc, asref, name):
     assert np.array_equal(r.trace_probe(probes, threads=4), pplain)
 
 
+@pytest.mark.parametrize("name", ["c2_object_mask", "c3_instanced", "mixed_material_masks"])
+def test_host_build_of_product_code_with_filters(orc, name):
+    """The product's flattener (filter tables in the blob) and filter_accept, compiled for the host."""
+    from hostsim import hostsim
+    desc, rays, probes, filters = filtered_cases()[name]
+    o = orc.scene(desc)
+    pplain = o.trace_probe(probes, threads=4)
+    _attach(o, desc, filters)
+    ref = o.trace(rays, threads=4)
+    sim = hostsim.SimScene(hostsim.load(), desc, filters=filters)
+    assert sim.trace(rays, wide=False)[0].tobytes() == ref.tobytes()
+    parity.compare_hits(o, rays, sim.trace(rays, wide=True)[0], ref)
+    assert np.array_equal(sim.trace_probe(probes, wide=False)[0], pplain)
+    parity.compare_probes(o, probes, sim.trace_probe(probes, wide=True)[0], pplain)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", ["c2_object_mask", "c3_instanced", "mixed_material_masks"])
 def test_kernels_with_filters(orc, name):
