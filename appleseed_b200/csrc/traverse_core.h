@@ -924,6 +924,7 @@ struct WideTraversal
     const uint8_t*  wtris;
     const uint8_t*  poses;
     const uint8_t*  filter_tree;        // TreeDesc of the current tree when it has intersection filters
+    const uint8_t*  parent;             // this ray's asgpu_parent record or null (set after begin())
     uint2           ngroup, tgroup;
     uint32_t        fetch;              // wide node to fetch next, 0xFFFFFFFF = none
     uint32_t        sp;
@@ -939,6 +940,7 @@ struct WideTraversal
         wtris = nullptr;
         poses = nullptr;
         filter_tree = nullptr;
+        parent = nullptr;
         ngroup.x = 0; ngroup.y = 0;
         tgroup.x = 0; tgroup.y = 0;
         fetch = s.top_wnode_count != 0 ? 0u : 0xFFFFFFFFu;
@@ -1005,6 +1007,7 @@ struct WideTraversal
                 stack[sp * stride] = sentinel; ++sp;
                 Ray local;
                 to_instance_space(ip, ray, local);
+                parent_origin(parent, meta.z, local.dir, local.org);
                 ray = local;
                 make_wide_ray(ray, wr);
                 TreeDesc td; load_tree_desc(s, meta.x, td);
@@ -1057,10 +1060,12 @@ struct WideTraversal
 
 // One ray start to finish (host simulation; the kernel drives WideTraversal itself).
 template <bool ANY, bool COUNT>
-ASGPU_HD bool wide_trace(const SceneView& s, const asgpu_rays& rays, const size_t index, Ray& out_ray, Hit& hit, Stats& stats, uint2* stack, const uint32_t stride)
+ASGPU_HD bool wide_trace(const SceneView& s, const asgpu_rays& rays, const size_t index, Ray& out_ray, Hit& hit, Stats& stats, uint2* stack, const uint32_t stride,
+                         const uint8_t* parent = nullptr)
 {
     WideTraversal<ANY, COUNT> tr;
     tr.begin(s, rays, index);
+    tr.parent = parent;
     while (!tr.step(s, rays, index, stats, stack, stride)) {}
     out_ray = tr.ray;
     hit = tr.hit;

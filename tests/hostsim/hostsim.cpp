@@ -8,6 +8,7 @@
 // execution path of the engine.
 //
 #include "../../appleseed_b200/csrc/flatten.h"
+#include "../../appleseed_b200/csrc/refine_core.h"
 #include "../../appleseed_b200/csrc/traverse_core.h"
 #include "../../appleseed_b200/csrc/tree_builder.h"
 
@@ -28,7 +29,8 @@ namespace
     std::string g_error;
 
     template <bool ANY, bool WIDE>
-    void run(const SimScene& s, const asgpu_rays& rays, size_t n, asgpu_hit* hits, uint8_t* occluded, uint64_t* counters)
+    void run(const SimScene& s, const asgpu_rays& rays, size_t n, asgpu_hit* hits, uint8_t* occluded, uint64_t* counters,
+             const asgpu_parent* parents = nullptr)
     {
         std::vector<uint2> stack(WideStackSize);
         Stats stats; std::memset(&stats, 0, sizeof(stats));
@@ -37,8 +39,9 @@ namespace
         {
             Ray ray; load_ray(rays, i, ray);
             Hit hit; bool found;
-            if (WIDE) found = wide_trace<ANY, true>(s.view, rays, i, ray, hit, stats, stack.data(), 1);
-            else found = exact_trace<ANY, true>(s.view, ray, hit, stats);
+            const uint8_t* parent = parents ? reinterpret_cast<const uint8_t*>(parents + i) : nullptr;
+            if (WIDE) found = wide_trace<ANY, true>(s.view, rays, i, ray, hit, stats, stack.data(), 1, parent);
+            else found = exact_trace<ANY, true>(s.view, ray, hit, stats, parent);
             found_count += found ? 1 : 0;
             if (ANY) { occluded[i] = found ? 1 : 0; continue; }
             asgpu_hit& h = hits[i];
@@ -153,6 +156,39 @@ void hostsim_trace(void* scene, const asgpu_rays* rays, size_t n, asgpu_hit* hit
 {
     if (wide) run<false, true>(*static_cast<SimScene*>(scene), *rays, n, hits, nullptr, counters);
     else run<false, false>(*static_cast<SimScene*>(scene), *rays, n, hits, nullptr, counters);
+}
+
+// asgpu_trace_with_parents / asgpu_trace_probe_with_parents on the host build.
+void hostsim_trace_parents(void* scene, const asgpu_rays* rays, const asgpu_parent* parents, size_t n, asgpu_hit* hits, int wide)
+{
+    if (wide) run<false, true>(*static_cast<SimScene*>(scene), *rays, n, hits, nullptr, nullptr, parents);
+    else run<false, false>(*static_cast<SimScene*>(scene), *rays, n, hits, nullptr, nullptr, parents);
+}
+
+void hostsim_trace_probe_parents(void* scene, const asgpu_rays* rays, const asgpu_parent* parents, size_t n, uint8_t* occluded, int wide)
+{
+    if (wide) run<true, true>(*static_cast<SimScene*>(scene), *rays, n, nullptr, occluded, nullptr, parents);
+    else run<true, false>(*static_cast<SimScene*>(scene), *rays, n, nullptr, occluded, nullptr, parents);
+}
+
+// asgpu_refine_and_offset on the host build (refine_core.h).
+void hostsim_refine_offset(void* scene, const asgpu_rays* rays, const asgpu_hit* hits, size_t n, asgpu_parent* out)
+{
+    const SimScene& s = *static_cast<SimScene*>(scene);
+    const ItemRecord* items = reinterpret_cast<const ItemRecord*>(s.blob.data() + s.view.items);
+    for (size_t i = 0; i < n; ++i)
+    {
+        double* dst = reinterpret_cast<double*>(out + i);
+        std::memset(dst, 0, sizeof(asgpu_parent));
+        out[i].assembly_instance = ASGPU_MISS;
+        if (hits[i].prim_type != 2) continue;
+        uint32_t item = ASGPU_MISS;
+        for (uint32_t k = 0; k < s.view.item_count; ++k) if (items[k].assembly_instance == hits[i].assembly_instance) { item = k; break; }
+        if (item == ASGPU_MISS) continue;
+        const double org[3] = { rays->org[i * 3], rays->org[i * 3 + 1], rays->org[i * 3 + 2] };
+        const double dir[3] = { rays->dir[i * 3], rays->dir[i * 3 + 1], rays->dir[i * 3 + 2] };
+        refine_offset_one(s.view, org, dir, hits[i].t, item, hits[i].object_instance_index, hits[i].primitive_index, hits[i].tri_slot, dst);
+    }
 }
 
 void hostsim_trace_probe(void* scene, const asgpu_rays* rays, size_t n, uint8_t* occluded, int wide, uint64_t* counters)

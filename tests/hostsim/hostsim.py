@@ -24,6 +24,9 @@ def load():
     lib.hostsim_blob_size.argtypes = [C.c_void_p]
     lib.hostsim_trace.argtypes = [C.c_void_p, C.POINTER(CRays), C.c_size_t, C.c_void_p, C.c_int, C.c_void_p]
     lib.hostsim_trace_probe.argtypes = [C.c_void_p, C.POINTER(CRays), C.c_size_t, C.c_void_p, C.c_int, C.c_void_p]
+    lib.hostsim_trace_parents.argtypes = [C.c_void_p, C.POINTER(CRays), C.c_void_p, C.c_size_t, C.c_void_p, C.c_int]
+    lib.hostsim_trace_probe_parents.argtypes = [C.c_void_p, C.POINTER(CRays), C.c_void_p, C.c_size_t, C.c_void_p, C.c_int]
+    lib.hostsim_refine_offset.argtypes = [C.c_void_p, C.POINTER(CRays), C.c_void_p, C.c_size_t, C.c_void_p]
     return lib
 
 
@@ -57,6 +60,28 @@ class SimScene:
         cr = rays.to_c()
         self.lib.hostsim_trace(self.handle, C.byref(cr), len(rays), out.ctypes.data, int(wide), cnt.ctypes.data)
         return out, cnt
+
+    def refine_offset(self, rays: RayBatch, hits: np.ndarray) -> np.ndarray:
+        from appleseed_b200.scene import PARENT_DTYPE
+        out = np.zeros(len(rays), dtype=PARENT_DTYPE)
+        cr = rays.to_c()
+        hits = np.ascontiguousarray(hits)
+        self.lib.hostsim_refine_offset(self.handle, C.byref(cr), hits.ctypes.data, len(rays), out.ctypes.data)
+        return out
+
+    def trace_parents(self, rays: RayBatch, parents: np.ndarray, wide: bool) -> np.ndarray:
+        out = np.zeros(len(rays), dtype=HIT_DTYPE)
+        cr = rays.to_c()
+        parents = np.ascontiguousarray(parents)
+        self.lib.hostsim_trace_parents(self.handle, C.byref(cr), parents.ctypes.data, len(rays), out.ctypes.data, int(wide))
+        return out
+
+    def trace_probe_parents(self, rays: RayBatch, parents: np.ndarray, wide: bool) -> np.ndarray:
+        out = np.zeros(len(rays), dtype=np.uint8)
+        cr = rays.to_c()
+        parents = np.ascontiguousarray(parents)
+        self.lib.hostsim_trace_probe_parents(self.handle, C.byref(cr), parents.ctypes.data, len(rays), out.ctypes.data, int(wide))
+        return out
 
     def trace_probe(self, rays: RayBatch, wide: bool):
         out = np.zeros(len(rays), dtype=np.uint8)

@@ -94,6 +94,33 @@ def test_refine_and_parents_on_random_static_scenes(orc, asref, seed):
     assert np.array_equal(o.trace_probe_parents(child, pa[h], threads=2), r.trace_probe_parents(child, pa[h], threads=2))
 
 
+@pytest.mark.parametrize("seed", SEEDS[:20])
+def test_host_build_of_refine_and_parent_code(sim, orc, seed):
+    """The product's refine_core.h and parent_origin, compiled for the host, against the oracle."""
+    from hostsim import hostsim
+    desc, rays = cases.random_scene(seed, moving=False)
+    rays = _static_rays(rays)
+    o = orc.scene(desc)
+    s = hostsim.SimScene(sim, desc)
+    hits = o.trace(rays, threads=2)
+    par = s.refine_offset(rays, hits)
+    assert par.tobytes() == o.refine_offset(rays, hits, threads=2).tobytes()
+    h = hits["prim_type"] == 2
+    child = rays.take(np.nonzero(h)[0])
+    child.org = child.org + hits["t"][h][:, None] * child.dir
+    child.dir[1::2] *= -1.0
+    child.tmin = np.zeros(len(child))
+    ref = o.trace_parents(child, par[h], threads=2)
+    assert s.trace_parents(child, par[h], wide=False).tobytes() == ref.tobytes()
+    wide = s.trace_parents(child, par[h], wide=True)
+    differs = np.nonzero(~(wide.view(np.uint8).reshape(len(ref), -1) == ref.view(np.uint8).reshape(len(ref), -1)).all(axis=1))[0]
+    for k in ("t", "u", "v", "prim_type"):          # exact ties only (coincident triangles / instances)
+        assert np.array_equal(wide[k][differs], ref[k][differs]), k
+    pref = o.trace_probe_parents(child, par[h], threads=2)
+    assert np.array_equal(s.trace_probe_parents(child, par[h], wide=False), pref)
+    assert np.array_equal(s.trace_probe_parents(child, par[h], wide=True), pref)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("seed", GPU_SEEDS[:10])
 def test_refine_and_parents_kernels_on_random_static_scenes(orc, seed):
