@@ -67,3 +67,17 @@ def test_product_does_not_reference_the_oracle():
     assert "oracle" not in out and "asref" not in out
     syms = os.popen("nm -D %s" % _lib.LIB_PATH).read()
     assert "orc_" not in syms and "asref_" not in syms and "hostsim" not in syms
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/asgpu.h is the whole boundary: it must compile as C99 and as C++ on its own."""
+    import subprocess
+    src = tmp_path / "use.c"
+    src.write_text('#include "asgpu.h"\nint main(void) { asgpu_hit h; asgpu_parent p; (void) h; (void) p; return asgpu_version() == ASGPU_VERSION ? 0 : 1; }\n')
+    inc = os.path.join(ROOT, "include")
+    subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-fsyntax-only", "-I", inc, str(src)], check=True)
+    subprocess.run(["g++", "-std=c++11", "-Wall", "-Werror", "-fsyntax-only", "-x", "c++", "-I", inc, str(src)], check=True)
+    # ... and link against the library from C.
+    exe = tmp_path / "use"
+    subprocess.run(["gcc", "-std=c99", "-I", inc, str(src), "-o", str(exe), _lib.LIB_PATH, "-Wl,-rpath," + os.path.dirname(_lib.LIB_PATH)], check=True)
+    assert subprocess.run([str(exe)]).returncode == 0
