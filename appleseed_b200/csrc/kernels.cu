@@ -649,7 +649,7 @@ struct Tuning { int refill, flush, stall, prefetch, steps, step_threshold, enter
 Tuning tuning(const bool single_instance)
 {
     Tuning v = { 8, 16, 16, 0, 3, 8, 1, 6, 8 };              // prefetch: measured neutral (C2) to -5 % (C3 probes), off
-    if (single_instance) { v.refill = 16; v.stall = 24; v.steps = 4; v.enter_late = 0; }
+    if (single_instance) { v.refill = 22; v.flush = 24; v.stall = 24; v.steps = 4; v.enter_late = 0; }
     if (const char* e = getenv("ASGPU_REFILL")) v.refill = atoi(e);
     if (const char* e = getenv("ASGPU_FLUSH")) v.flush = atoi(e);
     if (const char* e = getenv("ASGPU_STALL")) v.stall = atoi(e);
