@@ -52,6 +52,10 @@ from appleseed_b200 import scenes  # noqa: E402
 from appleseed_b200.scene import HIT_DTYPE, VIS_DIFFUSE, VIS_SHADOW, RayBatch  # noqa: E402
 
 METRIC = "Mrays/s closest-hit (wavefront batches, rays resident in HBM)"
+# Bytes the kernel fetches when a ray enters an assembly instance: 112 of the 128-byte ItemRecord
+# (3 x 4 matrix + tree / visibility / id), 32 bytes of TreeDesc fields (node, triangle and pose
+# offsets, node and slice counts) and the 4-byte item index of the wide top-level leaf.
+INSTANCE_BYTES = 112 + 32 + 4
 UNIT = "Mrays/s"
 MI = 1 << 20
 
@@ -509,7 +513,7 @@ def run_gpu(args):
         "nodes": c["triangle_nodes_visited"] / r, "triangles": c["triangles_tested"] / r, "hit_rate": c["hits"] / r,
     }
     ray_in = h2d / rays_per_step
-    bytes_per_ray = (per_ray["top_nodes"] + per_ray["nodes"]) * 80 + per_ray["triangles"] * 48 + per_ray["instances"] * (128 + 88 + 4) \
+    bytes_per_ray = (per_ray["top_nodes"] + per_ray["nodes"]) * 80 + per_ray["triangles"] * 48 + per_ray["instances"] * INSTANCE_BYTES \
         + ray_in + HIT_BYTES
     if args.workload == "c4":
         bytes_per_ray += per_ray["triangles"] * 72       # two 36-byte poses per moving triangle
@@ -730,7 +734,7 @@ def run_gpu_c5(args):
     per_ray = {"top_nodes": c["assembly_nodes_visited"] / r, "instances": c["instances_visited"] / r,
                "nodes": c["triangle_nodes_visited"] / r, "triangles": c["triangles_tested"] / r, "hit_rate": c["hits"] / r}
     closest_frac = closest_step / max(1, rays_step)
-    bytes_per_ray = (per_ray["top_nodes"] + per_ray["nodes"]) * 80 + per_ray["triangles"] * 48 + per_ray["instances"] * (128 + 88 + 4) \
+    bytes_per_ray = (per_ray["top_nodes"] + per_ray["nodes"]) * 80 + per_ray["triangles"] * 48 + per_ray["instances"] * INSTANCE_BYTES \
         + 72 + closest_frac * 40 + (1 - closest_frac) * 1
 
     t = torch.tensor([ms_step, e2e_ms], dtype=torch.float64, device=device)
