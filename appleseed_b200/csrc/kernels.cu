@@ -6,17 +6,20 @@
 // cursor), one ray per lane.  Node and triangle records are fetched with 16-byte read-only loads
 // (ld.global.nc.v4).  B200 has no RT cores and the work is not a dense contraction, so tensor
 // cores are not involved (gpu_layout.h states the record sizes that make up the algorithmic bytes
-// per ray).
+// per ray).  Measured limiter: instruction issue, not memory (profiles/README.md).
 //
 //   trace_kernel   EXACT layout: the reference's traversal operation for operation, one ray per
 //                  lane start to finish (the arbiter path).
-//   wide_kernel    WIDE layout, the throughput path.  A warp advances its 32 rays in lock step:
-//                  every step each lane tests ONE 8-wide node (fp32 interval arithmetic), then the
-//                  warp gathers the (ray, triangle) candidates of all its lanes into a shared-memory
-//                  queue and tests them 32 at a time with the exact fp64 test, whichever lane a
-//                  candidate came from.  The fp64 ray, the hit record and the traversal stack
-//                  ([entry][thread], conflict free) live in shared memory; registers only hold the
-//                  fp32 interval form of the ray and the traversal cursor.
+//   wide_kernel    WIDE layout, the throughput path.  A warp advances its 32 rays together: per
+//                  loop iteration each lane tests up to 3-4 8-wide nodes (fp32 interval arithmetic,
+//                  stopping at the first node with leaf triangles), lanes that reached an assembly
+//                  instance enter it together, then the warp gathers the (ray, triangle)
+//                  candidates of all its lanes into a shared-memory queue and tests them 32 at a
+//                  time with the exact fp64 test, whichever lane a candidate came from.  The fp64
+//                  ray, the hit record and the traversal stack ([entry][thread], conflict free) live
+//                  in shared memory; registers only hold the fp32 interval form of the ray and the
+//                  traversal cursor.  Instantiations: {closest, any hit} x {counters} x stack depth
+//                  {16, 24, 64} x LEAN (one static instance) x FILTERS (alpha masks, closest only).
 //
 // The per-ray building blocks live in traverse_core.h.
 //
