@@ -57,7 +57,8 @@ class AssemblyItem(C.Structure):
 
 
 class AssemblyTreeView(C.Structure):
-    _fields_ = [("nodes", C.c_void_p), ("items", C.POINTER(AssemblyItem)), ("node_count", C.c_uint64), ("item_count", C.c_uint64)]
+    _fields_ = [("nodes", C.c_void_p), ("items", C.POINTER(AssemblyItem)), ("node_count", C.c_uint64), ("item_count", C.c_uint64),
+                ("item_motion", C.c_void_p)]
 
 
 class SourceGeometry(C.Structure):

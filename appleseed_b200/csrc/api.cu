@@ -68,6 +68,7 @@ void make_view(asgpu_scene* s)
     s->view.wide_stack_need = s->header.wide_stack_need;
     s->view.has_motion = s->header.moving_triangle_count != 0 ? 1u : 0u;
     s->view.has_filters = (s->header.flags & BlobHasFilters) ? 1u : 0u;
+    s->view.has_animated = (s->header.flags & BlobHasAnimatedInstances) ? 1u : 0u;
     // Source geometry present for every tree?  (Small table: read it back.)
     s->has_source = s->header.tree_count != 0;
     std::vector<TreeDesc> descs(s->header.tree_count);
@@ -350,6 +351,7 @@ int asgpu_trees_get_assembly_tree(const asgpu_trees* trees, asgpu_assembly_tree_
     out->items = t.items.empty() ? nullptr : t.items.data();
     out->node_count = t.nodes.size();
     out->item_count = t.items.size();
+    out->item_motion = nullptr;         // the host builder handles single-key transform sequences
     return ASGPU_OK;
 }
 
@@ -532,6 +534,7 @@ int asgpu_refine_and_offset(asgpu_scene* scene, const asgpu_rays* rays, const as
     if (!(scene->header.flags & ASGPU_SCENE_EXACT)) return fail(ASGPU_E_INVALID, "refine_and_offset needs the per-slot triangle records of the exact layout");
     if (!scene->has_source) return fail(ASGPU_E_INVALID, "the scene was created without source geometry (asgpu_scene_create_ex)");
     if (scene->header.moving_triangle_count != 0) return fail(ASGPU_E_UNSUPPORTED, "refine_and_offset handles static triangles only");
+    if (scene->header.flags & BlobHasAnimatedInstances) return fail(ASGPU_E_UNSUPPORTED, "refine_and_offset does not handle animated assembly instances");
     ASGPU_CUDA(cudaSetDevice(scene->device), "cudaSetDevice");
     const int rt = ensure_id_table(scene);
     if (rt != ASGPU_OK) return rt;

@@ -982,6 +982,27 @@ int flatten_scene(
         dst.tree = src.triangle_tree;
         dst.vis_flags = src.vis_flags;
         dst.assembly_instance = src.assembly_instance;
+        if (top.item_motion && top.item_motion[i].key_count >= 2)
+        {
+            // Animated instance: key times, key matrices (3 x 4 rows) and interpolator segments.
+            const asgpu_item_motion& mo = top.item_motion[i];
+            if (!mo.key_times || !mo.key_parent_to_local || !mo.segments) { error = "animated assembly instance misses an array"; return ASGPU_E_INVALID; }
+            const uint32_t k = mo.key_count;
+            const size_t time_doubles = (size_t(k) * 4 + 15) / 16 * 2;
+            std::vector<double> block(time_doubles + size_t(k) * 12 + size_t(k - 1) * 20, 0.0);
+            std::memcpy(block.data(), mo.key_times, size_t(k) * 4);
+            for (uint32_t key = 0; key < k; ++key)
+            {
+                const double* m = mo.key_parent_to_local + size_t(key) * 16;
+                if (key > 0 && !(mo.key_times[key] > mo.key_times[key - 1])) { error = "transform keys are not in ascending time order"; return ASGPU_E_INVALID; }
+                if (m[12] != 0.0 || m[13] != 0.0 || m[14] != 0.0 || m[15] != 1.0) { error = "projective assembly-instance transforms are not supported"; return ASGPU_E_UNSUPPORTED; }
+                std::memcpy(block.data() + time_doubles + size_t(key) * 12, m, 12 * sizeof(double));
+            }
+            std::memcpy(block.data() + time_doubles + size_t(k) * 12, mo.segments, size_t(k - 1) * sizeof(asgpu_transform_segment));
+            dst.key_count = k;
+            dst.motion = writer.append(block);
+            header.flags |= BlobHasAnimatedInstances;
+        }
     }
     header.items = writer.append(items);
 

@@ -28,12 +28,13 @@ namespace asgpu
 {
 
 const uint32_t BlobMagic = 0x42534131u;     // "1ASB"
-const uint32_t BlobVersion = 7;
+const uint32_t BlobVersion = 8;
 const uint32_t WideStackMax = 64;           // deepest traversal stack any wide kernel variant offers
 const uint64_t SectionAlign = 256;
 
 const uint32_t InteriorMark = 0xFFFFFFFFu;
-const uint32_t BlobHasFilters = 1u << 8;     // BlobHeader::flags: some tree carries intersection filters
+const uint32_t BlobHasFilters = 1u << 8;
+const uint32_t BlobHasAnimatedInstances = 1u << 9;     // BlobHeader::flags: some tree carries intersection filters
 
 // EXACT: binary node of a triangle tree, 64 bytes.  box[] = [minL minR maxL maxR] x (x, y, z),
 // the order of bvh::Node::m_bbox_data (bvh_node.h:141-162).
@@ -169,7 +170,10 @@ struct ItemRecord
     uint32_t    tree;           // TreeDesc index or 0xFFFFFFFF
     uint32_t    vis_flags;
     uint32_t    assembly_instance;
-    uint32_t    pad[5];
+    uint32_t    key_count;      // >= 2: animated instance, `motion` holds its keys; else m[] is the transform
+    uint64_t    motion;         // animated: float times[key_count] (padded to 16 bytes), double parent_to_local[key_count][12],
+                                //           double segments[key_count - 1][20] (asgpu_transform_segment)
+    uint32_t    pad[2];
 };
 static_assert(sizeof(ItemRecord) == 128, "ItemRecord");
 

@@ -189,6 +189,16 @@ __device__ __forceinline__ unsigned long long ordered_key(const double t)
     return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
 }
 
+// Out of line on purpose (rare path, must not cost the traversal loop registers): the ray in the
+// space of an ANIMATED assembly instance.  io[0..5] = world org, dir in; instance org, dir out.
+__device__ __noinline__ void animated_instance_ray(const uint8_t* blob, const uint8_t* item, const uint32_t key_count, const float time_absolute, double* io)
+{
+    double lorg[3], ldir[3];
+    instance_org_dir_at(blob, item, key_count, time_absolute, io, io + 3, lorg, ldir);
+    io[0] = lorg[0]; io[1] = lorg[1]; io[2] = lorg[2];
+    io[3] = ldir[0]; io[4] = ldir[1]; io[5] = ldir[2];
+}
+
 // Out of line on purpose: the filter is a rare path (scenes with cut-out geometry only) and must
 // not cost the traversal loop registers.
 __device__ __noinline__ bool filter_accept_call(const uint8_t* blob, const uint8_t* tree, const uint32_t slot, const double u, const double v)
@@ -199,7 +209,7 @@ __device__ __noinline__ bool filter_accept_call(const uint8_t* blob, const uint8
 // Tests `count` (<= 32) queued candidates, one per lane.  Entry = (index of the triangle record in
 // the source lane's current tree) << 5 | source lane.  Closest hit: the nearest accepted candidate of each source lane
 // updates that lane's tmax and hit record (ties: lowest queue position).  Any hit: marks the lane.
-template <bool ANY, bool COUNT, int STACK, bool FILTERS>
+template <bool ANY, bool COUNT, int STACK, bool EXTRAS>
 __device__ __forceinline__ void test_candidates(
     WideShared<STACK>& sm, const uint8_t* blob, const unsigned long long* entries, const unsigned count,
     const unsigned lane, const unsigned warp_thread0, Stats& stats)
@@ -226,7 +236,7 @@ __device__ __forceinline__ void test_candidates(
         if (fetch_triangle<ANY>(blob + sm.tri_base[st] + (e >> 5) * sizeof(TriRecord), blob + sm.pose_base[st], ray, tri, slot, segment))
             hit = mt_test<!ANY>(tri, ray, t, u, v);
         // Optionally filter intersections (triangletree.cpp:1404-1411; closest hit only).
-        if (!ANY && FILTERS && hit && sm.filter_tree[st] != 0) hit = filter_accept_call(blob, blob + sm.filter_tree[st], slot, u, v);
+        if (!ANY && EXTRAS && hit && sm.filter_tree[st] != 0) hit = filter_accept_call(blob, blob + sm.filter_tree[st], slot, u, v);
     }
     if (ANY)
     {
@@ -292,10 +302,11 @@ __device__ __forceinline__ void restore_world_ray(const asgpu_rays& rays, const 
 // LEAN = the scene has one assembly instance and no moving triangles (e.g. C2): nothing ever comes
 // back to world space and no tree has time slices, so the instantiation drops the batched instance
 // entry, the saved world-space ray and the indirection to the child planes (measured: 3-5 %).
-// FILTERS = some tree carries intersection filters (cut-out geometry): only then does the
-// closest-hit instantiation contain the alpha-mask lookup (it costs registers: -3 % when compiled
-// into the common kernel).
-template <bool ANY, bool COUNT, int STACK, int MINB, bool LEAN, bool FILTERS>
+// EXTRAS = the scene has intersection filters (cut-out geometry) or animated assembly instances:
+// only then does the instantiation contain the alpha-mask lookup (closest hit) and the evaluation
+// of a transform sequence at the ray time (both cost registers: -3 % when compiled into the common
+// kernel).
+template <bool ANY, bool COUNT, int STACK, int MINB, bool LEAN, bool EXTRAS>
 __global__ void __launch_bounds__(BlockThreads, MINB)
 wide_kernel(const KernelArgs args)
 {
@@ -361,7 +372,16 @@ wide_kernel(const KernelArgs args)
             Ray world;
             load_ray_org_dir(args.rays, index, world);
             double lorg[3], ldir[3];
-            instance_org_dir(ip, world.org, world.dir, lorg, ldir);
+            if (EXTRAS && meta.w >= 2)
+            {
+                // Animated instance: its transform at the ray's absolute time (assemblytree.cpp:635-639).
+                const float time_absolute = args.rays.time_absolute ? __ldg(args.rays.time_absolute + index) : 0.0f;
+                double io[6] = { world.org[0], world.org[1], world.org[2], world.dir[0], world.dir[1], world.dir[2] };
+                animated_instance_ray(blob, ip, meta.w, time_absolute, io);
+                #pragma unroll
+                for (int k = 0; k < 3; ++k) { lorg[k] = io[k]; ldir[k] = io[3 + k]; }
+            }
+            else instance_org_dir(ip, world.org, world.dir, lorg, ldir);
             if (args.parents) parent_origin(reinterpret_cast<const uint8_t*>(args.parents + index), meta.z, ldir, lorg);
             #pragma unroll
             for (int k = 0; k < 3; ++k) { sm.ray[k][tid] = lorg[k]; sm.ray[3 + k][tid] = ldir[k]; }
@@ -392,7 +412,7 @@ wide_kernel(const KernelArgs args)
             sm.tri_base[tid] = static_cast<uint64_t>(o_tris.x) | (static_cast<uint64_t>(o_tris.y) << 32);
             sm.pose_base[tid] = static_cast<uint64_t>(o_poses.x) | (static_cast<uint64_t>(o_poses.y) << 32);
             sm.cur_item[tid] = item;
-            if (FILTERS)
+            if (EXTRAS)
                 sm.filter_tree[tid] = load4(tp + offsetof(TreeDesc, filter_count)) != 0 ? s.trees + static_cast<uint64_t>(meta.x) * sizeof(TreeDesc) : 0ull;
             cur_item = item;
             ngroup.y = 0; tgroup.y = 0;
@@ -568,7 +588,7 @@ wide_kernel(const KernelArgs args)
                 while (queued >= 32)
                 {
                     queued -= 32;
-                    test_candidates<ANY, COUNT, STACK, FILTERS>(sm, blob, queue + queued, 32, lane, warp_thread0, stats);
+                    test_candidates<ANY, COUNT, STACK, EXTRAS>(sm, blob, queue + queued, 32, lane, warp_thread0, stats);
                     tested = true;
                 }
             }
@@ -589,7 +609,7 @@ wide_kernel(const KernelArgs args)
                     if (queued >= 32)
                     {
                         queued -= 32;
-                        test_candidates<ANY, COUNT, STACK, FILTERS>(sm, blob, queue + queued, 32, lane, warp_thread0, stats);
+                        test_candidates<ANY, COUNT, STACK, EXTRAS>(sm, blob, queue + queued, 32, lane, warp_thread0, stats);
                         tested = true;
                     }
                     pushers = __ballot_sync(0xFFFFFFFFu, pending != 0);
@@ -603,7 +623,7 @@ wide_kernel(const KernelArgs args)
             const unsigned stalled = __ballot_sync(0xFFFFFFFFu, !active || held || (traversed && waiting));
             if (queued >= args.flush_threshold || __popc(stalled) >= args.stall_threshold)
             {
-                test_candidates<ANY, COUNT, STACK, FILTERS>(sm, blob, queue, queued, lane, warp_thread0, stats);
+                test_candidates<ANY, COUNT, STACK, EXTRAS>(sm, blob, queue, queued, lane, warp_thread0, stats);
                 queued = 0;
                 tested = true;
             }
@@ -697,25 +717,25 @@ cudaError_t launch_persistent(Kernel kernel, const KernelArgs& args, const size_
 // and run ~10 % slower (profiles/README.md).
 const int WideMinBlocks = 5;
 
-template <int STACK, bool LEAN, bool FILTERS>
+template <int STACK, bool LEAN, bool EXTRAS>
 cudaError_t launch_wide(const KernelArgs& args, const bool any_hit, const bool count, const int sm_count, cudaStream_t stream)
 {
     const size_t smem = sizeof(WideShared<STACK>);
-    // Shadow probes ignore intersection filters (TriangleLeafProbeVisitor has none).
-    if (any_hit) return count ? launch_persistent(wide_kernel<true, true, STACK, WideMinBlocks, LEAN, false>, args, smem, sm_count, stream)
-                              : launch_persistent(wide_kernel<true, false, STACK, WideMinBlocks, LEAN, false>, args, smem, sm_count, stream);
-    return count ? launch_persistent(wide_kernel<false, true, STACK, WideMinBlocks, LEAN, FILTERS>, args, smem, sm_count, stream)
-                 : launch_persistent(wide_kernel<false, false, STACK, WideMinBlocks, LEAN, FILTERS>, args, smem, sm_count, stream);
+    // (Shadow probes ignore intersection filters -- TriangleLeafProbeVisitor has none -- but do see animated instances.)
+    if (any_hit) return count ? launch_persistent(wide_kernel<true, true, STACK, WideMinBlocks, LEAN, EXTRAS>, args, smem, sm_count, stream)
+                              : launch_persistent(wide_kernel<true, false, STACK, WideMinBlocks, LEAN, EXTRAS>, args, smem, sm_count, stream);
+    return count ? launch_persistent(wide_kernel<false, true, STACK, WideMinBlocks, LEAN, EXTRAS>, args, smem, sm_count, stream)
+                 : launch_persistent(wide_kernel<false, false, STACK, WideMinBlocks, LEAN, EXTRAS>, args, smem, sm_count, stream);
 }
 
-template <bool LEAN, bool FILTERS>
+template <bool LEAN, bool EXTRAS>
 cudaError_t launch_wide_depth(const KernelArgs& args, const uint32_t stack_need, const bool any_hit, const bool count, const int sm_count, cudaStream_t stream)
 {
     // The traversal stack lives in shared memory; its depth is the scene's (flatten.cpp computes
     // the bound), rounded up to one of the compiled variants.
-    if (stack_need <= 16) return launch_wide<16, LEAN, FILTERS>(args, any_hit, count, sm_count, stream);
-    if (stack_need <= 24) return launch_wide<24, LEAN, FILTERS>(args, any_hit, count, sm_count, stream);
-    return launch_wide<WideStackMax, LEAN, FILTERS>(args, any_hit, count, sm_count, stream);
+    if (stack_need <= 16) return launch_wide<16, LEAN, EXTRAS>(args, any_hit, count, sm_count, stream);
+    if (stack_need <= 24) return launch_wide<24, LEAN, EXTRAS>(args, any_hit, count, sm_count, stream);
+    return launch_wide<WideStackMax, LEAN, EXTRAS>(args, any_hit, count, sm_count, stream);
 }
 
 }   // anonymous namespace
@@ -768,9 +788,10 @@ int launch_trace(
     const bool count = counters != nullptr;
     if (wide)
     {
-        const bool lean = scene.item_count <= 1 && !scene.has_motion && !scene.has_filters && getenv("ASGPU_NO_LEAN") == nullptr;
+        const bool extras = scene.has_filters || scene.has_animated;
+        const bool lean = scene.item_count <= 1 && !scene.has_motion && !extras && getenv("ASGPU_NO_LEAN") == nullptr;
         if (lean) err = launch_wide_depth<true, false>(args, scene.wide_stack_need, any_hit, count, sm_count, stream);
-        else if (scene.has_filters) err = launch_wide_depth<false, true>(args, scene.wide_stack_need, any_hit, count, sm_count, stream);
+        else if (extras) err = launch_wide_depth<false, true>(args, scene.wide_stack_need, any_hit, count, sm_count, stream);
         else err = launch_wide_depth<false, false>(args, scene.wide_stack_need, any_hit, count, sm_count, stream);
     }
     else if (any_hit) err = count ? launch_persistent(trace_kernel<true, true>, args, 0, sm_count, stream)

@@ -161,6 +161,7 @@ struct SceneView
     uint32_t        wide_stack_need;
     uint32_t        has_motion;         // some tree has moving triangles (time-sliced child planes)
     uint32_t        has_filters;        // some tree carries intersection filters
+    uint32_t        has_animated;       // some assembly instance has a multi-key transform sequence
 };
 
 struct Ray
@@ -225,9 +226,110 @@ ASGPU_HD void instance_org_dir(const uint8_t* item, const double worg[3], const 
     }
 }
 
-ASGPU_HD void to_instance_space(const uint8_t* item, const Ray& world, Ray& local)
+// Animated assembly instance: world -> instance rows of the transform at the ray's absolute time.
+// TransformSequence::evaluate (transformsequence.h:185-210): the first / last key outside the key
+// range, else interpolate (transformsequence.cpp:331-356: binary search over the key times,
+// t = (time - begin) / (end - begin) in float) and TransformInterpolator::evaluate
+// (transform.h:694-789: fast_slerp of the rotations, quaternion.h:500-511, lerp of scale and
+// translation, analytic inverse).  fp64, the reference's operation order, no contraction.
+ASGPU_HD void animated_item_matrix(const uint8_t* blob, const uint8_t* item, const uint32_t key_count, const float time, double m[12])
 {
-    instance_org_dir(item, world.org, world.dir, local.org, local.dir);
+    const uint2 mo = load8(item + 112);
+    const uint8_t* motion = blob + (static_cast<uint64_t>(mo.x) | (static_cast<uint64_t>(mo.y) << 32));
+    const uint8_t* keys = motion + (static_cast<uint64_t>(key_count) * 4 + 15) / 16 * 16;
+    const uint8_t* segments = keys + static_cast<uint64_t>(key_count) * 96;
+    const float first = u2f(load4(motion)), last = u2f(load4(motion + static_cast<uint64_t>(key_count - 1) * 4));
+    if (time <= first || time >= last)
+    {
+        const uint8_t* k = time <= first ? keys : keys + static_cast<uint64_t>(key_count - 1) * 96;
+        for (int e = 0; e < 12; ++e) m[e] = load_f64(k + e * 8);
+        return;
+    }
+    uint32_t begin = 0, end = key_count;
+    while (end - begin > 1)
+    {
+        const uint32_t mid = (begin + end) / 2;
+        if (time < u2f(load4(motion + static_cast<uint64_t>(mid) * 4))) end = mid; else begin = mid;
+    }
+    const float begin_time = u2f(load4(motion + static_cast<uint64_t>(begin) * 4)), end_time = u2f(load4(motion + static_cast<uint64_t>(end) * 4));
+#if ASGPU_DEVICE_CODE
+    const double t = static_cast<double>(__fdiv_rn(fsub(time, begin_time), fsub(end_time, begin_time)));
+#else
+    volatile float tf = fsub(time, begin_time) / fsub(end_time, begin_time);
+    const double t = static_cast<double>(tf);
+#endif
+    const uint8_t* sg = segments + static_cast<uint64_t>(begin) * 160;
+    double s0[3], q0[4], t0[3], s1[3], q1[4], t1[3];
+    for (int a = 0; a < 3; ++a)
+    {
+        s0[a] = load_f64(sg + a * 8);          t0[a] = load_f64(sg + (7 + a) * 8);
+        s1[a] = load_f64(sg + (10 + a) * 8);   t1[a] = load_f64(sg + (17 + a) * 8);
+    }
+    for (int a = 0; a < 4; ++a) { q0[a] = load_f64(sg + (3 + a) * 8); q1[a] = load_f64(sg + (13 + a) * 8); }
+
+    // fast_slerp: d = dot(p, q) = p.s * q.s + dot(p.v, q.v) (dot accumulates from 0).
+    double dv = dadd(0.0, dmul(q0[1], q1[1])); dv = dadd(dv, dmul(q0[2], q1[2])); dv = dadd(dv, dmul(q0[3], q1[3]));
+    const double d = dadd(dmul(q0[0], q1[0]), dv);
+    const double pa = dadd(1.0904, dmul(d, dadd(-3.2452, dmul(d, dadd(3.55645, dmul(d, -1.43519))))));
+    const double pb = dadd(0.848013, dmul(d, dadd(-1.06021, dmul(d, 0.215638))));
+    const double u = dsub(t, 1.0), v = dsub(t, 0.5);
+    const double k = dadd(dmul(dmul(pa, v), v), pb);
+    const double w = dadd(dmul(dmul(dmul(k, u), v), t), t);
+    // normalize(lerp(p, q, w)): lerp = (1 - w) * p + w * q, normalize = q * (1 / sqrt(dot(q, q))).
+    const double omw = dsub(1.0, w);
+    double q[4];
+    for (int a = 0; a < 4; ++a) q[a] = dadd(dmul(q0[a], omw), dmul(q1[a], w));
+    double nv = dadd(0.0, dmul(q[1], q[1])); nv = dadd(nv, dmul(q[2], q[2])); nv = dadd(nv, dmul(q[3], q[3]));
+    const double nn = dadd(dmul(q[0], q[0]), nv);
+#if ASGPU_DEVICE_CODE
+    const double rn = ddiv(1.0, __dsqrt_rn(nn));
+#else
+    volatile double sq = std::sqrt(nn);
+    const double rn = ddiv(1.0, sq);
+#endif
+    const double qs = dmul(q[0], rn), qx = dmul(q[1], rn), qy = dmul(q[2], rn), qz = dmul(q[3], rn);
+
+    const double rtx = dadd(qx, qx), rty = dadd(qy, qy), rtz = dadd(qz, qz);
+    const double twx = dmul(rtx, qs), twy = dmul(rty, qs), twz = dmul(rtz, qs);
+    const double txx = dmul(rtx, qx), txy = dmul(rty, qx), txz = dmul(rtz, qx);
+    const double tyy = dmul(rty, qy), tyz = dmul(rtz, qy), tzz = dmul(rtz, qz);
+    // parent_to_local rotation block (the transpose of local_to_parent's).
+    m[0] = dsub(1.0, dadd(tyy, tzz));  m[1] = dadd(txy, twz);             m[2] = dsub(txz, twy);
+    m[4] = dsub(txy, twz);             m[5] = dsub(1.0, dadd(txx, tzz));  m[6] = dadd(tyz, twx);
+    m[8] = dadd(txz, twy);             m[9] = dsub(tyz, twx);             m[10] = dsub(1.0, dadd(txx, tyy));
+    // s = lerp(s0, s1, t); rows scaled by 1 / s.
+    const double omt = dsub(1.0, t);
+    for (int r = 0; r < 3; ++r)
+    {
+        const double sr = dadd(dmul(omt, s0[r]), dmul(t, s1[r]));
+        const double rcp = ddiv(1.0, sr);
+        m[r * 4 + 0] = dmul(m[r * 4 + 0], rcp); m[r * 4 + 1] = dmul(m[r * 4 + 1], rcp); m[r * 4 + 2] = dmul(m[r * 4 + 2], rcp);
+    }
+    // p = lerp(t0, t1, t); translation column = -(row . p).
+    double p[3];
+    for (int a = 0; a < 3; ++a) p[a] = dadd(dmul(omt, t0[a]), dmul(t, t1[a]));
+    for (int r = 0; r < 3; ++r)
+        m[r * 4 + 3] = -dadd(dadd(dmul(m[r * 4 + 0], p[0]), dmul(m[r * 4 + 1], p[1])), dmul(m[r * 4 + 2], p[2]));
+}
+
+// instance_org_dir for an item that may be animated (key_count = the item's meta word 3).
+ASGPU_HD void instance_org_dir_at(const uint8_t* blob, const uint8_t* item, const uint32_t key_count, const float time_absolute,
+                                  const double worg[3], const double wdir[3], double lorg[3], double ldir[3])
+{
+    if (key_count < 2) { instance_org_dir(item, worg, wdir, lorg, ldir); return; }
+    double m[12];
+    animated_item_matrix(blob, item, key_count, time_absolute, m);
+    for (int r = 0; r < 3; ++r)
+    {
+        const double* row = m + r * 4;
+        ldir[r] = dadd(dadd(dmul(row[0], wdir[0]), dmul(row[1], wdir[1])), dmul(row[2], wdir[2]));
+        lorg[r] = dadd(dadd(dadd(dmul(row[0], worg[0]), dmul(row[1], worg[1])), dmul(row[2], worg[2])), row[3]);
+    }
+}
+
+ASGPU_HD void to_instance_space(const uint8_t* blob, const uint8_t* item, const uint32_t key_count, const Ray& world, Ray& local)
+{
+    instance_org_dir_at(blob, item, key_count, world.time_absolute, world.org, world.dir, local.org, local.dir);
     local.tmin = world.tmin;
     local.tmax = world.tmax;
     local.time_absolute = world.time_absolute;
@@ -644,7 +746,7 @@ ASGPU_HD bool exact_trace(const SceneView& s, Ray& ray, Hit& hit, Stats& stats, 
             if (!(meta.y & ray.flags)) continue;
             if (COUNT) ++stats.instances;
             Ray local;
-            to_instance_space(ip, ray, local);
+            to_instance_space(s.blob, ip, meta.w, ray, local);
             parent_origin(parent, meta.z, local.dir, local.org);
             if (meta.x == 0xFFFFFFFFu) continue;
             TreeDesc td; load_tree_desc(s, meta.x, td);
@@ -1006,7 +1108,7 @@ struct WideTraversal
                 uint2 sentinel; sentinel.x = 0xFFFFFFFFu; sentinel.y = 0;
                 stack[sp * stride] = sentinel; ++sp;
                 Ray local;
-                to_instance_space(ip, ray, local);
+                to_instance_space(s.blob, ip, meta.w, ray, local);
                 parent_origin(parent, meta.z, local.dir, local.org);
                 ray = local;
                 make_wide_ray(ray, wr);

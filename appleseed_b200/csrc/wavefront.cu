@@ -619,6 +619,7 @@ asgpu_path_stream* asgpu_path_stream_create(asgpu_scene* scene, const asgpu_path
     if (desc->max_bounces > 200) { fail(ASGPU_E_INVALID, "max_bounces above 200"); return nullptr; }
     if (static_cast<uint64_t>(desc->width) * desc->height * desc->spp > 0xFFFFFFFFull) { fail(ASGPU_E_UNSUPPORTED, "more than 2^32 - 1 paths per frame"); return nullptr; }
     if (scene->header.moving_triangle_count != 0) { fail(ASGPU_E_UNSUPPORTED, "the path stream handles static triangles only"); return nullptr; }
+    if (scene->header.flags & BlobHasAnimatedInstances) { fail(ASGPU_E_UNSUPPORTED, "the path stream handles static assembly instances only"); return nullptr; }
     if (!(scene->header.flags & ASGPU_SCENE_EXACT)) { fail(ASGPU_E_INVALID, "the path stream needs the per-slot triangle records of the exact layout"); return nullptr; }
     const bool with_parents = (desc->stream_flags & ASGPU_STREAM_PARENTS) != 0;
     if (with_parents && !scene->has_source) { fail(ASGPU_E_INVALID, "ASGPU_STREAM_PARENTS needs a scene with source geometry (asgpu_scene_create_ex)"); return nullptr; }

@@ -304,6 +304,31 @@ class IntersectionFilter:
         return f, keep
 
 
+class CInstanceKeys(C.Structure):
+    _fields_ = [("times", C.c_void_p), ("local_to_parent", C.c_void_p), ("parent_to_local", C.c_void_p),
+                ("key_count", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class CItemMotion(C.Structure):
+    """asgpu_item_motion / orc_item_motion."""
+    _fields_ = [("key_times", C.c_void_p), ("key_parent_to_local", C.c_void_p), ("segments", C.c_void_p),
+                ("key_count", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+@dataclass
+class InstanceKeys:
+    """Keys of an animated assembly instance (``TransformSequence``): ascending times and one
+    local-to-parent matrix per key."""
+    times: np.ndarray                      # (k,) float32
+    local_to_parent: np.ndarray            # (k, 4, 4) float64
+
+    def __post_init__(self):
+        self.times = np.ascontiguousarray(self.times, dtype=np.float32).reshape(-1)
+        self.local_to_parent = np.ascontiguousarray(self.local_to_parent, dtype=np.float64).reshape(-1, 4, 4)
+        self.parent_to_local = np.ascontiguousarray(np.linalg.inv(self.local_to_parent))
+        assert len(self.times) == len(self.local_to_parent) and np.all(np.diff(self.times) > 0)
+
+
 @dataclass
 class RayBatch:
     """The ShadingRay fields the path consumes (renderer/kernel/shading/shadingray.h:99-109,

@@ -139,11 +139,31 @@ typedef struct asgpu_assembly_item {
     uint32_t        reserved;
 } asgpu_assembly_item;
 
+/* Animated assembly instance: a TransformSequence with two or more keys
+ * (renderer/utility/transformsequence.h).  The traversal evaluates the instance transform at the
+ * ray's absolute time (assemblytree.cpp:635-639 -> TransformSequence::evaluate,
+ * transformsequence.h:185-210 -> interpolate, transformsequence.cpp:331-356 ->
+ * TransformInterpolator::evaluate, foundation/math/transform.h:694-789).  A segment is what
+ * TransformSequence::prepare() keeps in its TransformInterpolator (get_s0() ... get_t1()):
+ * scale, rotation quaternion (s, v.x, v.y, v.z) and translation at both ends. */
+typedef struct asgpu_transform_segment {
+    double          s0[3], q0[4], t0[3], s1[3], q1[4], t1[3];
+} asgpu_transform_segment;
+
+typedef struct asgpu_item_motion {
+    const float*                    key_times;              /* key_count, ascending (m_keys[k].m_time) */
+    const double*                   key_parent_to_local;    /* key_count * 16 (m_keys[k].m_transform), used outside the key range */
+    const asgpu_transform_segment*  segments;               /* key_count - 1 */
+    uint32_t                        key_count;              /* < 2: not animated, asgpu_assembly_item::parent_to_local is used */
+    uint32_t                        reserved;
+} asgpu_item_motion;
+
 typedef struct asgpu_assembly_tree_view {
     const void*                 nodes;      /* bvh::Node<AABB3d>[node_count]; leaves address items by index/count */
     const asgpu_assembly_item*  items;      /* tree order (AssemblyTree::m_items after reordering) */
     uint64_t        node_count;
     uint64_t        item_count;
+    const asgpu_item_motion*    item_motion;    /* item_count entries or NULL: animated instances (the node boxes already bound the motion) */
 } asgpu_assembly_tree_view;
 
 /* Optional source geometry, one asgpu_source_geometry per triangle tree: what

@@ -15,7 +15,7 @@ import subprocess
 
 import numpy as np
 
-from appleseed_b200.scene import HIT_DTYPE, PARENT_DTYPE, CRays, CSceneDesc, RayBatch, SceneDesc
+from appleseed_b200.scene import HIT_DTYPE, PARENT_DTYPE, CInstanceKeys, CItemMotion, CRays, CSceneDesc, RayBatch, SceneDesc
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _PATHS = {
@@ -118,6 +118,14 @@ class Oracle:
         self._probe_par.argtypes = [C.c_void_p, C.POINTER(CRays), C.c_void_p, C.c_size_t, C.c_void_p, C.c_int]
         self._set_filter = getattr(L, p + "_set_filter")
         self._set_filter.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
+        if prefix == "asref":
+            self._create_animated = L.asref_scene_create_animated
+            self._create_animated.restype = C.c_void_p
+            self._create_animated.argtypes = [C.POINTER(CSceneDesc), C.c_void_p]
+            self._item_motion = L.asref_get_item_motion
+            self._item_motion.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(CItemMotion)]
+            self._item_p2l = L.asref_get_item_parent_to_local
+            self._item_p2l.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
         if prefix == "orc":
             self._two = L.orc_two_nearest
             self._two.argtypes = [C.c_void_p, C.POINTER(CRays), C.c_size_t, C.c_void_p, C.c_void_p, C.c_int]
@@ -133,8 +141,10 @@ class Oracle:
 
     # -- scenes -------------------------------------------------------------------------------
 
-    def scene(self, desc: SceneDesc) -> "OracleScene":
-        return OracleScene(self, desc)
+    def scene(self, desc: SceneDesc, keys=None) -> "OracleScene":
+        """``keys``: {assembly instance index: scene.InstanceKeys} -- animated assembly instances
+        (asref only: it links the reference's own TransformSequence)."""
+        return OracleScene(self, desc, keys)
 
     # -- known-answer entry points ------------------------------------------------------------
 
@@ -169,11 +179,21 @@ class Oracle:
 
 
 class OracleScene:
-    def __init__(self, oracle: Oracle, desc: SceneDesc):
+    def __init__(self, oracle: Oracle, desc: SceneDesc, keys=None):
         self.oracle = oracle
         self.desc = desc
         self._cdesc, self._keep = desc.to_c()
-        self.handle = oracle._create(C.byref(self._cdesc))
+        if keys:
+            if oracle.prefix != "asref":
+                raise ValueError("animated assembly instances are checked against the reference-header build (asref) only")
+            arr = (CInstanceKeys * len(desc.assembly_instances))()
+            for i, k in keys.items():
+                arr[i].times, arr[i].local_to_parent, arr[i].parent_to_local = k.times.ctypes.data, k.local_to_parent.ctypes.data, k.parent_to_local.ctypes.data
+                arr[i].key_count = len(k.times)
+            self._keep += [arr, keys]
+            self.handle = oracle._create_animated(C.byref(self._cdesc), C.cast(arr, C.c_void_p))
+        else:
+            self.handle = oracle._create(C.byref(self._cdesc))
         if not self.handle:
             raise RuntimeError("oracle scene_create failed")
 
@@ -213,6 +233,21 @@ class OracleScene:
             "item_assembly_instance": _view_bytes(v.item_assembly_instance, v.item_count * 4).view(np.uint32),
             "item_tree": _view_bytes(v.item_tree, v.item_count * 4).view(np.uint32),
         }
+
+    def item_motion(self, item: int):
+        """(key times, key parent_to_local [k, 16], segments [k - 1, 20]) of tree-order item ``item`` or None."""
+        m = CItemMotion()
+        self.oracle._item_motion(self.handle, item, C.byref(m))
+        k = int(m.key_count)
+        if k < 2:
+            return None
+        return (_view_bytes(m.key_times, k * 4).view(np.float32).copy(), _view_bytes(m.key_parent_to_local, k * 128).view(np.float64).reshape(k, 16).copy(),
+                _view_bytes(m.segments, (k - 1) * 160).view(np.float64).reshape(k - 1, 20).copy())
+
+    def item_parent_to_local(self, item: int) -> np.ndarray:
+        out = np.zeros(16)
+        self.oracle._item_p2l(self.handle, item, out.ctypes.data)
+        return out
 
     def trace(self, rays: RayBatch, threads: int = 1, counters: bool = False):
         n = len(rays)

@@ -159,6 +159,35 @@ typedef struct orc_intersection_filter {
     const float*            uv;                     /* triangle_count * 6 floats */
 } orc_intersection_filter;
 
+/* Animated assembly instances (asref only: the reference's own renderer/utility/
+ * transformsequence.cpp is compiled into oracle/_ref).  keys: TransformSequence keys in ascending
+ * time order; key_count < 2 = not animated. */
+typedef struct orc_instance_keys {
+    const float*    times;              /* key_count */
+    const double*   local_to_parent;    /* key_count * 16 */
+    const double*   parent_to_local;    /* key_count * 16 */
+    uint32_t        key_count;
+    uint32_t        reserved;
+} orc_instance_keys;
+
+/* What TransformSequence::prepare() keeps per segment in its TransformInterpolator
+ * (foundation/math/transform.h:640-655): scale, rotation (s, v.x, v.y, v.z), translation at both ends. */
+typedef struct orc_transform_segment {
+    double          s0[3], q0[4], t0[3], s1[3], q1[4], t1[3];
+} orc_transform_segment;
+
+typedef struct orc_item_motion {
+    const float*                    key_times;
+    const double*                   key_parent_to_local;    /* key_count * 16 */
+    const orc_transform_segment*    segments;               /* key_count - 1 */
+    uint32_t                        key_count;
+    uint32_t                        reserved;
+} orc_item_motion;
+
+void*   asref_scene_create_animated(const orc_scene_desc* desc, const orc_instance_keys* keys /* per assembly instance */);
+void    asref_get_item_motion(const void* scene, uint32_t item /* tree order */, orc_item_motion* out);
+void    asref_get_item_parent_to_local(const void* scene, uint32_t item, double out[16]);
+
 #define ORC_DECLARE(prefix)                                                                         \
     void*   prefix##_scene_create(const orc_scene_desc* desc);                                      \
     void    prefix##_scene_destroy(void* scene);                                                    \

@@ -33,6 +33,7 @@
 #include "foundation/utility/bitmask.h"
 #include "foundation/utility/casts.h"
 #include "renderer/kernel/intersection/refining.h"
+#include "renderer/utility/transformsequence.h"
 #include "renderer/utility/triangle.h"
 
 #include "oracle_api.h"
@@ -983,6 +984,13 @@ struct RefItem
     std::uint32_t   m_tree;                 // triangle tree index or ~0
     std::uint32_t   m_vis_flags;
     Transformd      m_transform;
+    // Animated instances: the reference's own TransformSequence (several keys), plus what an
+    // in-tree flattener would read out of it for the GPU engine.
+    bool                                m_animated = false;
+    renderer::TransformSequence         m_transform_sequence;
+    std::vector<float>                  m_key_times;
+    std::vector<double>                 m_key_parent_to_local;
+    std::vector<orc_transform_segment>  m_segments;
 };
 
 class RefAssemblyTree
@@ -1029,7 +1037,7 @@ class RefAssemblyTree
         return bbox;
     }
 
-    void build(const orc_scene_desc& desc)
+    void build(const orc_scene_desc& desc, const orc_instance_keys* keys = nullptr)
     {
         // update_tree_hierarchy / create_triangle_tree (assemblytree.cpp:247-298, 394-420):
         // one triangle tree per assembly that has mesh object instances.
@@ -1061,9 +1069,42 @@ class RefAssemblyTree
             item.m_tree = static_cast<std::uint32_t>(m_assembly_tree_index[inst.assembly_index]);
             item.m_vis_flags = inst.vis_flags;
             item.m_transform = make_transform(inst.local_to_parent, inst.parent_to_local);
+            if (keys && keys[i].key_count >= 2)
+            {
+                // cumulated_transform_seq of an animated instance (assemblytree.cpp:124-127).
+                item.m_animated = true;
+                for (std::uint32_t k = 0; k < keys[i].key_count; ++k)
+                {
+                    const Transformd xf = make_transform(keys[i].local_to_parent + k * 16, keys[i].parent_to_local + k * 16);
+                    item.m_transform_sequence.set_transform(keys[i].times[k], xf);
+                    item.m_key_times.push_back(keys[i].times[k]);
+                    for (int e = 0; e < 16; ++e) item.m_key_parent_to_local.push_back(xf.get_parent_to_local()[e]);
+                }
+                item.m_transform_sequence.prepare();
+                for (std::uint32_t k = 0; k + 1 < keys[i].key_count; ++k)
+                {
+                    // TransformSequence::prepare builds exactly these (transformsequence.cpp:218-226).
+                    const TransformInterpolatord interp(
+                        make_transform(keys[i].local_to_parent + k * 16, keys[i].parent_to_local + k * 16),
+                        make_transform(keys[i].local_to_parent + (k + 1) * 16, keys[i].parent_to_local + (k + 1) * 16));
+                    orc_transform_segment seg;
+                    for (int a = 0; a < 3; ++a)
+                    {
+                        seg.s0[a] = interp.get_s0()[a]; seg.s1[a] = interp.get_s1()[a];
+                        seg.t0[a] = interp.get_t0()[a]; seg.t1[a] = interp.get_t1()[a];
+                        seg.q0[1 + a] = interp.get_q0().v[a]; seg.q1[1 + a] = interp.get_q1().v[a];
+                    }
+                    seg.q0[0] = interp.get_q0().s; seg.q1[0] = interp.get_q1().s;
+                    item.m_segments.push_back(seg);
+                }
+            }
             m_items.push_back(item);
 
-            AABB3d assembly_instance_bbox(item.m_transform.to_parent(assembly_bboxes[inst.assembly_index]));
+            // cumulated_transform_seq.to_parent(...) (assemblytree.cpp:146-149): for an animated
+            // instance the reference's motion bounding box (transformsequence.h:215-241).
+            AABB3d assembly_instance_bbox(
+                item.m_animated ? item.m_transform_sequence.to_parent(assembly_bboxes[inst.assembly_index])
+                                : item.m_transform.to_parent(assembly_bboxes[inst.assembly_index]));
             assembly_instance_bbox.robust_grow(1.0e-15);
             assembly_instance_bboxes.push_back(assembly_instance_bbox);
         }
@@ -1148,7 +1189,11 @@ struct AsmLeafVisitor
             ++m_counters->instances_visited;
 
             RefShadingPoint asm_inst_shading_point;
-            compute_assembly_instance_ray(item.m_transform, item.m_assembly_instance, m_parent, ray, asm_inst_shading_point.m_ray);
+            // Evaluate the transformation of the assembly instance at ray time (assemblytree.cpp:635-639).
+            Transformd scratch;
+            const Transformd& assembly_instance_transform =
+                item.m_animated ? item.m_transform_sequence.evaluate(ray.m_time_absolute, scratch) : item.m_transform;
+            compute_assembly_instance_ray(assembly_instance_transform, item.m_assembly_instance, m_parent, ray, asm_inst_shading_point.m_ray);
             const RayInfo3d asm_inst_ray_info(asm_inst_shading_point.m_ray);
 
             if (item.m_tree != ~std::uint32_t(0))
@@ -1222,7 +1267,10 @@ struct AsmLeafProbeVisitor
             ++m_counters->instances_visited;
 
             RefShadingRay asm_inst_ray;
-            compute_assembly_instance_ray(item.m_transform, item.m_assembly_instance, m_parent, ray, asm_inst_ray);
+            Transformd scratch;
+            const Transformd& assembly_instance_transform =
+                item.m_animated ? item.m_transform_sequence.evaluate(ray.m_time_absolute, scratch) : item.m_transform;
+            compute_assembly_instance_ray(assembly_instance_transform, item.m_assembly_instance, m_parent, ray, asm_inst_ray);
             const RayInfo3d asm_inst_ray_info(asm_inst_ray);
 
             if (item.m_tree != ~std::uint32_t(0))
@@ -1549,6 +1597,30 @@ void asref_trace_probe_parents(const void* scene_, const orc_rays* rays, const o
             out[i] = visitor.m_hit ? 1 : 0;
         }
     });
+}
+
+void* asref_scene_create_animated(const orc_scene_desc* desc, const orc_instance_keys* keys)
+{
+    RefScene* scene = new RefScene();
+    scene->m_desc = *desc;
+    scene->m_assembly_tree.build(scene->m_desc, keys);
+    return scene;
+}
+
+void asref_get_item_motion(const void* scene_, uint32_t item_index, orc_item_motion* out)
+{
+    const RefItem& item = static_cast<const RefScene*>(scene_)->m_assembly_tree.m_items[item_index];
+    out->key_times = item.m_key_times.empty() ? nullptr : item.m_key_times.data();
+    out->key_parent_to_local = item.m_key_parent_to_local.empty() ? nullptr : item.m_key_parent_to_local.data();
+    out->segments = item.m_segments.empty() ? nullptr : item.m_segments.data();
+    out->key_count = static_cast<uint32_t>(item.m_key_times.size());
+    out->reserved = 0;
+}
+
+void asref_get_item_parent_to_local(const void* scene_, uint32_t item_index, double out[16])
+{
+    const RefItem& item = static_cast<const RefScene*>(scene_)->m_assembly_tree.m_items[item_index];
+    for (int e = 0; e < 16; ++e) out[e] = item.m_transform.get_parent_to_local()[e];
 }
 
 void asref_set_filter(void* scene_, uint32_t assembly, uint32_t object_instance, const orc_intersection_filter* filter)

@@ -109,6 +109,7 @@ void* hostsim_scene_create_filtered(const asgpu_scene_desc* desc, uint32_t flags
     top.items = trees.assembly_tree.items.empty() ? nullptr : trees.assembly_tree.items.data();
     top.node_count = trees.assembly_tree.nodes.size();
     top.item_count = trees.assembly_tree.items.size();
+    top.item_motion = nullptr;
 
     // Source geometry (always) and the filters of the trees that have some.
     std::vector<asgpu_source_geometry> sources(views.size());
@@ -136,6 +137,23 @@ void* hostsim_scene_create_filtered(const asgpu_scene_desc* desc, uint32_t flags
     SimScene* s = new SimScene();
     const int rc = flatten_scene(views.empty() ? nullptr : views.data(), static_cast<uint32_t>(views.size()), top,
                                  sources.empty() ? nullptr : sources.data(), flags, s->blob, g_error);
+    if (rc != ASGPU_OK) { delete s; return nullptr; }
+    if (validate_blob(s->blob.data(), s->blob.size(), g_error) != ASGPU_OK) { delete s; return nullptr; }
+    BlobHeader h; std::memcpy(&h, s->blob.data(), sizeof(h));
+    s->view.blob = s->blob.data();
+    s->view.trees = h.trees; s->view.items = h.items; s->view.top_nodes = h.top_nodes;
+    s->view.top_wnodes = h.top_wnodes; s->view.top_witems = h.top_witems;
+    s->view.tree_count = h.tree_count; s->view.item_count = h.item_count;
+    s->view.top_node_count = h.top_node_count; s->view.top_wnode_count = h.top_wnode_count;
+    s->view.wide_stack_need = h.wide_stack_need;
+    return s;
+}
+
+// The product's flattener on reference-format trees supplied by the caller (what asgpu_scene_create takes).
+void* hostsim_scene_create_views(const asgpu_triangle_tree_view* views, uint32_t view_count, const asgpu_assembly_tree_view* top, uint32_t flags)
+{
+    SimScene* s = new SimScene();
+    const int rc = flatten_scene(views, view_count, *top, nullptr, flags, s->blob, g_error);
     if (rc != ASGPU_OK) { delete s; return nullptr; }
     if (validate_blob(s->blob.data(), s->blob.size(), g_error) != ASGPU_OK) { delete s; return nullptr; }
     BlobHeader h; std::memcpy(&h, s->blob.data(), sizeof(h));
