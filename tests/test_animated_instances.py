@@ -110,5 +110,5 @@ def test_kernels_with_animated_instances(asref):
     ref = o.trace(rays, threads=4)
     check(ref, isect.trace(rays, exact=True), isect.trace(rays), o.trace_probe(probes, threads=4),
           isect.trace_probe(probes, exact=True), isect.trace_probe(probes))
-    with pytest.raises(AsgpuError, match="animated"):
+    with pytest.raises(AsgpuError, match="animated|source geometry"):
         isect.refine_and_offset(rays, ref)
