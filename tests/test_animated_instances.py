@@ -112,3 +112,81 @@ def test_kernels_with_animated_instances(asref):
           isect.trace_probe(probes, exact=True), isect.trace_probe(probes))
     with pytest.raises(AsgpuError, match="animated|source geometry"):
         isect.refine_and_offset(rays, ref)
+
+
+def _random_rigid(rng, spread):
+    q = rng.normal(size=4)
+    q /= np.linalg.norm(q)
+    w, x, y, z = q
+    r = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                  [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                  [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+    m = np.eye(4)
+    m[:3, :3] = r @ np.diag(rng.uniform(0.5, 1.6, size=3))
+    m[:3, 3] = rng.uniform(-spread, spread, size=3)
+    return m
+
+
+@pytest.mark.parametrize("seed", list(range(12)))
+def test_random_animated_scenes_on_the_host_build(asref, seed):
+    """Random static scenes (tests/cases.py::random_scene) whose assembly instances get 2-5 random
+    keys (arbitrary rotations, non-uniform scales, translations, uneven key times)."""
+    from hostsim import hostsim
+    desc, rays = cases.random_scene(seed, moving=False)
+    rng = np.random.default_rng(500 + seed)
+    rays.time_absolute = (rng.random(len(rays)) * 1.4 - 0.2).astype(np.float32)
+    rays.time_normalized = np.zeros(len(rays), dtype=np.float32)
+    keys = {}
+    for i in range(len(desc.assembly_instances)):
+        if rng.random() < 0.7:
+            k = int(rng.integers(2, 6))
+            times = np.sort(rng.random(k)).astype(np.float32)
+            times += np.arange(k, dtype=np.float32) * np.float32(1e-3)             # strictly ascending
+            mats = [desc.assembly_instances[i].local_to_parent] + [_random_rigid(rng, 2.5) for _ in range(k - 1)]
+            keys[i] = InstanceKeys(times, np.stack(mats))
+    if not keys:
+        pytest.skip("no animated instance drawn")
+    o = asref.scene(desc, keys=keys)
+    views, top, keep = product_views(asref, o, desc)
+    sim = hostsim.SimScene.from_views(hostsim.load(), views, top, keep)
+    ref = o.trace(rays, threads=2)
+    assert sim.trace(rays, wide=False)[0].tobytes() == ref.tobytes()
+    wide = sim.trace(rays, wide=True)[0]
+    same = (wide.view(np.uint8).reshape(len(ref), -1) == ref.view(np.uint8).reshape(len(ref), -1)).all(axis=1)
+    for k in ("t", "u", "v", "prim_type"):                     # coincident triangles / instances tie exactly
+        assert np.array_equal(wide[k][~same], ref[k][~same]), k
+    pref = o.trace_probe(rays, threads=2)
+    assert np.array_equal(sim.trace_probe(rays, wide=False)[0], pref)
+    assert (sim.trace_probe(rays, wide=True)[0] != pref).sum() <= 2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", list(range(8)))
+def test_random_animated_scenes_on_the_kernels(asref, seed):
+    from appleseed_b200.intersector import Intersector, TraceContext
+    desc, rays = cases.random_scene(seed, n_rays=20000, moving=False)
+    rng = np.random.default_rng(500 + seed)
+    rays.time_absolute = (rng.random(len(rays)) * 1.4 - 0.2).astype(np.float32)
+    rays.time_normalized = np.zeros(len(rays), dtype=np.float32)
+    keys = {}
+    for i in range(len(desc.assembly_instances)):
+        if rng.random() < 0.7:
+            k = int(rng.integers(2, 6))
+            times = np.sort(rng.random(k)).astype(np.float32)
+            times += np.arange(k, dtype=np.float32) * np.float32(1e-3)
+            mats = [desc.assembly_instances[i].local_to_parent] + [_random_rigid(rng, 2.5) for _ in range(k - 1)]
+            keys[i] = InstanceKeys(times, np.stack(mats))
+    if not keys:
+        pytest.skip("no animated instance drawn")
+    o = asref.scene(desc, keys=keys)
+    views, top, keep = product_views(asref, o, desc)
+    isect = Intersector(TraceContext.from_tree_views(views, top))
+    ref = o.trace(rays, threads=4)
+    assert isect.trace(rays, exact=True).tobytes() == ref.tobytes()
+    wide = isect.trace(rays)
+    same = (wide.view(np.uint8).reshape(len(ref), -1) == ref.view(np.uint8).reshape(len(ref), -1)).all(axis=1)
+    for k in ("t", "u", "v", "prim_type"):
+        assert np.array_equal(wide[k][~same], ref[k][~same]), k
+    pref = o.trace_probe(rays, threads=4)
+    assert np.array_equal(isect.trace_probe(rays, exact=True), pref)
+    assert (isect.trace_probe(rays) != pref).sum() <= 2
