@@ -534,7 +534,6 @@ int asgpu_refine_and_offset(asgpu_scene* scene, const asgpu_rays* rays, const as
     if (!(scene->header.flags & ASGPU_SCENE_EXACT)) return fail(ASGPU_E_INVALID, "refine_and_offset needs the per-slot triangle records of the exact layout");
     if (!scene->has_source) return fail(ASGPU_E_INVALID, "the scene was created without source geometry (asgpu_scene_create_ex)");
     if (scene->header.moving_triangle_count != 0) return fail(ASGPU_E_UNSUPPORTED, "refine_and_offset handles static triangles only");
-    if (scene->header.flags & BlobHasAnimatedInstances) return fail(ASGPU_E_UNSUPPORTED, "refine_and_offset does not handle animated assembly instances");
     ASGPU_CUDA(cudaSetDevice(scene->device), "cudaSetDevice");
     const int rt = ensure_id_table(scene);
     if (rt != ASGPU_OK) return rt;

@@ -50,7 +50,8 @@ refine_offset_kernel(const SceneView s, const asgpu_rays rays, const asgpu_hit* 
         const double t = __longlong_as_double(static_cast<long long>(w0));
         Ray world;
         load_ray_org_dir(rays, i, world);
-        refine_offset_one(s, world.org, world.dir, t, item, static_cast<uint32_t>(w2 >> 32), static_cast<uint32_t>(w3), static_cast<uint32_t>(w3 >> 32), dst);
+        const float time_absolute = rays.time_absolute ? __ldg(rays.time_absolute + i) : 0.0f;
+        refine_offset_one(s, world.org, world.dir, time_absolute, t, item, static_cast<uint32_t>(w2 >> 32), static_cast<uint32_t>(w3), static_cast<uint32_t>(w3 >> 32), dst);
     }
 }
 

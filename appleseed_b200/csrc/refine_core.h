@@ -3,6 +3,10 @@
 // (refine.cu) and the TEST-ONLY host build (tests/hostsim), like traverse_core.h.
 //
 //   refine_space_ray = assembly_instance_transform.to_local(ray);  org += tmax * dir
+//                                                       (the transform the traversal stored in the
+//                                                       ShadingPoint, assemblytree.cpp:738-739: for an
+//                                                       animated instance the one evaluated at the
+//                                                       ray's absolute time)
 //   org = refine(org, dir, plane)                       two Newton steps onto the triangle's
 //                                                       support plane (refining.h:97-113,
 //                                                       raytrianglemt.h:300-309)
@@ -71,16 +75,17 @@ ASGPU_HD void offset_point(const TriD& tri, const double p[3], const double n[3]
     }
 }
 
-// One hit.  `item` = ItemRecord index of the hit's assembly instance; writes the 80-byte
-// asgpu_parent record (id, pad, front, back, geo_normal) as ten 8-byte words.
-ASGPU_HD void refine_offset_one(const SceneView& s, const double world_org[3], const double world_dir[3], const double t, const uint32_t item,
-                                const uint32_t object_instance, const uint32_t primitive, const uint32_t slot, double* dst)
+// One hit.  `item` = ItemRecord index of the hit's assembly instance; `time_absolute` = the ray's
+// absolute time (read by animated instances only); writes the 80-byte asgpu_parent record (id, pad,
+// front, back, geo_normal) as ten 8-byte words.
+ASGPU_HD void refine_offset_one(const SceneView& s, const double world_org[3], const double world_dir[3], const float time_absolute, const double t,
+                                const uint32_t item, const uint32_t object_instance, const uint32_t primitive, const uint32_t slot, double* dst)
 {
     // refine_space_ray = to_local(ray), moved to the hit point.
     const uint8_t* ip = s.blob + s.items + static_cast<uint64_t>(item) * sizeof(ItemRecord);
     const uint4 meta = load16(ip + 96);
     double p[3], dir[3];
-    instance_org_dir(ip, world_org, world_dir, p, dir);
+    instance_org_dir_at(s.blob, ip, meta.w, time_absolute, world_org, world_dir, p, dir);
     for (int k = 0; k < 3; ++k) p[k] = dadd(p[k], dmul(dir[k], t));
 
     // Support plane = the triangle the leaf stores, widened to double.

@@ -196,12 +196,17 @@ class TraceContext:
             raise AsgpuError("scene creation failed: " + _lib.last_error())
 
     @classmethod
-    def from_tree_views(cls, tree_views, top_view, device: int = 0, flags: int = _lib.SCENE_DEFAULT) -> "TraceContext":
-        """Flatten reference-format trees supplied by the caller (``asgpu_scene_create``)."""
+    def from_tree_views(cls, tree_views, top_view, device: int = 0, flags: int = _lib.SCENE_DEFAULT, sources=None) -> "TraceContext":
+        """Flatten reference-format trees supplied by the caller (``asgpu_scene_create``; with
+        ``sources``, one ``_lib.SourceGeometry`` per tree: ``asgpu_scene_create_ex``)."""
         lib = _lib.load()
         n = len(tree_views)
         arr = (_lib.TriangleTreeView * max(1, n))(*tree_views)
-        handle = lib.asgpu_scene_create(arr, n, C.byref(top_view), flags, device)
+        if sources is None:
+            handle = lib.asgpu_scene_create(arr, n, C.byref(top_view), flags, device)
+        else:
+            src = (_lib.SourceGeometry * max(1, n))(*sources)
+            handle = lib.asgpu_scene_create_ex(arr, n, C.byref(top_view), src, flags, device)
         if not handle:
             raise AsgpuError("asgpu_scene_create failed: " + _lib.last_error())
         return cls(device=device, _handle=handle)

@@ -1511,7 +1511,17 @@ void asref_refine_offset(const void* scene_, const orc_rays* rays, const orc_hit
 
             const orc_assembly_instance& inst = desc.assembly_instances[hit.assembly_instance];
             const orc_assembly& assembly = desc.assemblies[inst.assembly_index];
-            const Transformd assembly_instance_transform = make_transform(inst.local_to_parent, inst.parent_to_local);
+            // m_assembly_instance_transform as the traversal stored it (assemblytree.cpp:738-739): the
+            // transform sequence evaluated at the ray's absolute time for an animated instance.
+            Transformd assembly_instance_transform = make_transform(inst.local_to_parent, inst.parent_to_local);
+            for (const RefItem& item : scene.m_assembly_tree.m_items)
+            {
+                if (item.m_assembly_instance == hit.assembly_instance && item.m_animated)
+                {
+                    Transformd scratch;
+                    assembly_instance_transform = item.m_transform_sequence.evaluate(m_ray.m_time_absolute, scratch);
+                }
+            }
             const RefTriangleTree& tree = *scene.m_assembly_tree.m_triangle_trees[scene.m_assembly_tree.m_assembly_tree_index[inst.assembly_index]];
 
             // m_triangle_support_plane.initialize(TriangleType(triangle)) (triangletree.cpp:1483-1499).

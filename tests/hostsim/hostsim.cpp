@@ -150,10 +150,12 @@ void* hostsim_scene_create_filtered(const asgpu_scene_desc* desc, uint32_t flags
 }
 
 // The product's flattener on reference-format trees supplied by the caller (what asgpu_scene_create takes).
-void* hostsim_scene_create_views(const asgpu_triangle_tree_view* views, uint32_t view_count, const asgpu_assembly_tree_view* top, uint32_t flags)
+// `sources`: view_count entries (what asgpu_scene_create_ex takes) or null.
+void* hostsim_scene_create_views(const asgpu_triangle_tree_view* views, uint32_t view_count, const asgpu_assembly_tree_view* top,
+                                 const asgpu_source_geometry* sources, uint32_t flags)
 {
     SimScene* s = new SimScene();
-    const int rc = flatten_scene(views, view_count, *top, nullptr, flags, s->blob, g_error);
+    const int rc = flatten_scene(views, view_count, *top, sources, flags, s->blob, g_error);
     if (rc != ASGPU_OK) { delete s; return nullptr; }
     if (validate_blob(s->blob.data(), s->blob.size(), g_error) != ASGPU_OK) { delete s; return nullptr; }
     BlobHeader h; std::memcpy(&h, s->blob.data(), sizeof(h));
@@ -205,7 +207,8 @@ void hostsim_refine_offset(void* scene, const asgpu_rays* rays, const asgpu_hit*
         if (item == ASGPU_MISS) continue;
         const double org[3] = { rays->org[i * 3], rays->org[i * 3 + 1], rays->org[i * 3 + 2] };
         const double dir[3] = { rays->dir[i * 3], rays->dir[i * 3 + 1], rays->dir[i * 3 + 2] };
-        refine_offset_one(s.view, org, dir, hits[i].t, item, hits[i].object_instance_index, hits[i].primitive_index, hits[i].tri_slot, dst);
+        const float time_absolute = rays->time_absolute ? rays->time_absolute[i] : 0.0f;
+        refine_offset_one(s.view, org, dir, time_absolute, hits[i].t, item, hits[i].object_instance_index, hits[i].primitive_index, hits[i].tri_slot, dst);
     }
 }
 

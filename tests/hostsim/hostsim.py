@@ -19,7 +19,7 @@ def load():
     lib.hostsim_scene_create_filtered.restype = C.c_void_p
     lib.hostsim_scene_create_filtered.argtypes = [C.POINTER(CSceneDesc), C.c_uint32, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.hostsim_scene_create_views.restype = C.c_void_p
-    lib.hostsim_scene_create_views.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
+    lib.hostsim_scene_create_views.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32]
     lib.hostsim_scene_destroy.argtypes = [C.c_void_p]
     lib.hostsim_last_error.restype = C.c_char_p
     lib.hostsim_blob_size.restype = C.c_size_t
@@ -52,15 +52,21 @@ class SimScene:
             raise RuntimeError(lib.hostsim_last_error().decode())
 
     @classmethod
-    def from_views(cls, lib, tree_views, top_view, keep, flags=SCENE_EXACT | SCENE_WIDE):
-        """The product's flattener on caller-supplied reference-format trees (``_lib`` view structs)."""
+    def from_views(cls, lib, tree_views, top_view, keep, flags=SCENE_EXACT | SCENE_WIDE, sources=None):
+        """The product's flattener on caller-supplied reference-format trees (``_lib`` view structs);
+        ``sources``: one ``_lib.SourceGeometry`` per tree (needed by refine_offset) or None."""
         from appleseed_b200 import _lib
         self = cls.__new__(cls)
         self.lib = lib
         self._keep = [tree_views, top_view, keep]
         arr = (_lib.TriangleTreeView * max(1, len(tree_views)))(*tree_views)
         self._keep.append(arr)
-        self.handle = lib.hostsim_scene_create_views(C.cast(arr, C.c_void_p), len(tree_views), C.cast(C.pointer(top_view), C.c_void_p), flags)
+        src = None
+        if sources is not None:
+            src = (_lib.SourceGeometry * max(1, len(sources)))(*sources)
+            self._keep += [sources, src]
+        self.handle = lib.hostsim_scene_create_views(C.cast(arr, C.c_void_p), len(tree_views), C.cast(C.pointer(top_view), C.c_void_p),
+                                                     C.cast(src, C.c_void_p) if src is not None else None, flags)
         if not self.handle:
             raise RuntimeError(lib.hostsim_last_error().decode())
         return self

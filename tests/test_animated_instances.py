@@ -110,8 +110,130 @@ def test_kernels_with_animated_instances(asref):
     ref = o.trace(rays, threads=4)
     check(ref, isect.trace(rays, exact=True), isect.trace(rays), o.trace_probe(probes, threads=4),
           isect.trace_probe(probes, exact=True), isect.trace_probe(probes))
-    with pytest.raises(AsgpuError, match="animated|source geometry"):
+    with pytest.raises(AsgpuError, match="source geometry"):        # asgpu_scene_create: no source geometry
         isect.refine_and_offset(rays, ref)
+
+
+def product_sources(desc):
+    """Source geometry per triangle tree (what asgpu_scene_create_ex takes), from the product's own
+    host builder: the triangle trees do not depend on the instance animation."""
+    from appleseed_b200.intersector import HostTrees
+    trees = HostTrees(desc)
+    return [trees.source_geometry(i) for i in range(trees.triangle_tree_count)], trees
+
+
+def child_rays(rays, hits, seed):
+    """Bounce rays from the un-offset world hit points, at their parent ray's time."""
+    from appleseed_b200.scene import RayBatch
+    h = hits["prim_type"] == 2
+    rng = np.random.default_rng(seed)
+    d = rng.normal(size=(int(h.sum()), 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    pts = rays.org[h] + hits["t"][h][:, None] * rays.dir[h]
+    return h, RayBatch(pts, d, 0.0, np.finfo(np.float64).max, time_absolute=rays.time_absolute[h],
+                       time_normalized=rays.time_normalized[h], flags=rays.flags[h] if rays.flags is not None else None)
+
+
+def test_refine_and_offset_with_animated_instances_host_build(asref):
+    """ShadingPoint::refine_and_offset works in the space of m_assembly_instance_transform, which the
+    traversal set to the sequence evaluated at the ray time (assemblytree.cpp:738-739)."""
+    from hostsim import hostsim
+    desc, rays, probes, keys = animated_case()
+    o = asref.scene(desc, keys=keys)
+    views, top, keep = product_views(asref, o, desc)
+    sources, trees = product_sources(desc)
+    sim = hostsim.SimScene.from_views(hostsim.load(), views, top, keep + [trees], sources=sources)
+    hits = o.trace(rays, threads=4)
+    ref = o.refine_offset(rays, hits, threads=4)
+    assert sim.refine_offset(rays, hits).tobytes() == ref.tobytes()
+    # The animation matters: the same hits refined under the first key's transform differ.
+    frozen = asref.scene(desc).refine_offset(rays, hits, threads=4)
+    assert (frozen["front"] != ref["front"]).any(axis=1).sum() > 500
+    # Child rays with their parents, through both traversals of the product code.
+    h, bounce = child_rays(rays, hits, 11)
+    par = ref[h]
+    want = o.trace_parents(bounce, par, threads=4)
+    assert sim.trace_parents(bounce, par, wide=False).tobytes() == want.tobytes()
+    wide = sim.trace_parents(bounce, par, wide=True)
+    assert (wide["t"] != want["t"]).sum() <= 5
+    assert int(((want["prim_type"] == 2) & (want["t"] < 1e-9)).sum()) == 0                 # no self-intersection
+    assert int(((o.trace(bounce, threads=4)["t"] < 1e-9)).sum()) > 0.2 * len(bounce)      # ... which a parentless child ray has
+
+
+@pytest.mark.gpu
+def test_refine_and_offset_with_animated_instances_on_the_kernels(asref):
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from appleseed_b200.intersector import Intersector, TraceContext
+    desc, rays, probes, keys = animated_case()
+    o = asref.scene(desc, keys=keys)
+    views, top, keep = product_views(asref, o, desc)
+    sources, trees = product_sources(desc)
+    isect = Intersector(TraceContext.from_tree_views(views, top, sources=sources))
+    hits = isect.trace(rays, exact=True)
+    assert hits.tobytes() == o.trace(rays, threads=4).tobytes()
+    ref = o.refine_offset(rays, hits, threads=4)
+    assert isect.refine_and_offset(rays, hits).tobytes() == ref.tobytes()
+    h, bounce = child_rays(rays, hits, 11)
+    want = o.trace_parents(bounce, ref[h], threads=4)
+    assert isect.trace_with_parents(bounce, ref[h], exact=True).tobytes() == want.tobytes()
+    assert (isect.trace_with_parents(bounce, ref[h])["t"] != want["t"]).sum() <= 5
+
+
+# renderer/meta/tests/test_transformsequence.cpp:335-406 (TwoTransformsFixture): keys at times 1 and 3,
+# translations (1,2,3) and (4,5,6); evaluate(0) = the first key, evaluate(4) = the last,
+# evaluate(2) = the interpolator at 0.5 = translation (2.5, 3.5, 4.5) (EXPECT_FEQ).  Seen through the
+# path: a unit quad in the x = 0 plane of the instance, rays along +x from (0, y, z) of the key.
+TS_KAT = [(0.0, (1.0, 2.0, 3.0), True), (1.0, (1.0, 2.0, 3.0), True), (4.0, (4.0, 5.0, 6.0), True), (3.0, (4.0, 5.0, 6.0), True),
+          (2.0, (2.5, 3.5, 4.5), False)]
+
+
+def transformsequence_kat():
+    import kat
+    from appleseed_b200.scene import Assembly, AssemblyInstance, ObjectInstance, RayBatch, SceneDesc
+    first, second = scenes.translation(1.0, 2.0, 3.0), scenes.translation(4.0, 5.0, 6.0)
+    desc = SceneDesc([kat.unit_quad()], [Assembly([ObjectInstance(0)])], [AssemblyInstance(0, first)])
+    # (:384-406 sets the keys in reverse order: TransformSequence::prepare sorts them, upstream of the
+    # boundary -- the engine receives keys in time order.)
+    keys = {0: InstanceKeys([1.0, 3.0], np.stack([first, second]))}
+    org = np.array([[0.0, p[1], p[2]] for _, p, _ in TS_KAT])
+    rays = RayBatch(org, np.tile([1.0, 0.0, 0.0], (len(TS_KAT), 1)), 0.0, np.finfo(np.float64).max,
+                    time_absolute=np.array([t for t, _, _ in TS_KAT], dtype=np.float32), time_normalized=np.zeros(len(TS_KAT), dtype=np.float32))
+    return desc, keys, rays
+
+
+def check_transformsequence_kat(hits):
+    assert np.all(hits["prim_type"] == 2)
+    for h, (_, p, exact) in zip(hits, TS_KAT):
+        assert h["t"] == p[0] if exact else abs(h["t"] - p[0]) <= 1e-14 * p[0]
+        assert abs(h["u"] + h["v"] - 0.5) <= 1e-6 or abs(h["u"] - 0.5) <= 1e-6 or abs(h["v"] - 0.5) <= 1e-6     # the quad's centre lies on its diagonal
+
+
+def test_transformsequence_known_answers(asref):
+    from hostsim import hostsim
+    desc, keys, rays = transformsequence_kat()
+    o = asref.scene(desc, keys=keys)
+    ref = o.trace(rays)
+    check_transformsequence_kat(ref)
+    views, top, keep = product_views(asref, o, desc)
+    sim = hostsim.SimScene.from_views(hostsim.load(), views, top, keep)
+    assert sim.trace(rays, wide=False)[0].tobytes() == ref.tobytes()
+    check_transformsequence_kat(sim.trace(rays, wide=True)[0])
+    assert list(o.trace_probe(rays)) == [1] * len(rays) == list(sim.trace_probe(rays, wide=True)[0])
+
+
+@pytest.mark.gpu
+def test_transformsequence_known_answers_on_the_kernels(asref):
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from appleseed_b200.intersector import Intersector, TraceContext
+    desc, keys, rays = transformsequence_kat()
+    o = asref.scene(desc, keys=keys)
+    views, top, keep = product_views(asref, o, desc)
+    isect = Intersector(TraceContext.from_tree_views(views, top))
+    assert isect.trace(rays, exact=True).tobytes() == o.trace(rays).tobytes()
+    check_transformsequence_kat(isect.trace(rays))
+    assert list(isect.trace_probe(rays)) == [1] * len(rays) == list(isect.trace_probe(rays, exact=True))
 
 
 def _random_rigid(rng, spread):
