@@ -345,7 +345,8 @@ typedef struct asgpu_parent {           /* 80 bytes */
 
 /* For every hit of a closest-hit trace: the parent record its ShadingPoint would hold.  rays =
  * the rays that produced `hits`.  DEVICE pointers.  Needs source geometry (asgpu_scene_create_ex)
- * and the exact layout; static triangles only. */
+ * and the exact layout; static triangles only (animated assembly instances are handled: the refine
+ * space is the instance transform at rays->time_absolute[i]). */
 int             asgpu_refine_and_offset(asgpu_scene* scene, const asgpu_rays* rays, const asgpu_hit* hits, size_t n,
                                         asgpu_parent* parents, void* stream);
 
