@@ -30,6 +30,7 @@ EXPORTS = [
     "asgpu_path_stream_create", "asgpu_path_stream_destroy", "asgpu_path_stream_tile_count", "asgpu_path_stream_render",
     "asgpu_path_stream_read_image", "asgpu_path_stream_clear", "asgpu_path_stream_get_stats",
     "asgpu_path_stream_capture", "asgpu_path_stream_capture_count", "asgpu_path_stream_capture_get",
+    "asgpu_trees_build_on_device",
 ]
 
 SCENE_EXACT = 1 << 0
@@ -127,6 +128,8 @@ def load() -> C.CDLL:
     lib.asgpu_version.restype = C.c_int
     lib.asgpu_trees_build.restype = C.c_void_p
     lib.asgpu_trees_build.argtypes = [P(CSceneDesc), C.c_int]
+    lib.asgpu_trees_build_on_device.restype = C.c_void_p
+    lib.asgpu_trees_build_on_device.argtypes = [P(CSceneDesc), C.c_int, C.c_int]
     lib.asgpu_trees_destroy.argtypes = [C.c_void_p]
     lib.asgpu_trees_triangle_tree_count.argtypes = [C.c_void_p]
     lib.asgpu_trees_get_triangle_tree.argtypes = [C.c_void_p, C.c_int, P(TriangleTreeView)]

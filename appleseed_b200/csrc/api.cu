@@ -318,6 +318,22 @@ asgpu_trees* asgpu_trees_build(const asgpu_scene_desc* desc, int threads)
     return t;
 }
 
+asgpu_trees* asgpu_trees_build_on_device(const asgpu_scene_desc* desc, int threads, int device)
+{
+    if (!desc) { fail(ASGPU_E_INVALID, "null scene description"); return nullptr; }
+    int device_count = 0;
+    if (cudaGetDeviceCount(&device_count) != cudaSuccess || device < 0 || device >= device_count)
+    { fail(ASGPU_E_CUDA, "asgpu_trees_build_on_device: no such CUDA device"); return nullptr; }
+    asgpu_trees* t = new (std::nothrow) asgpu_trees();
+    if (!t) { fail(ASGPU_E_NOMEM, "out of host memory"); return nullptr; }
+    std::string error;
+    bool ok = false;
+    try { ok = build_host_trees(*desc, threads, t->trees, error, lbvh_topology_device, &device); }
+    catch (const std::exception& e) { error = e.what(); }
+    if (!ok) { fail(error.compare(0, 18, "device tree build:") == 0 ? ASGPU_E_CUDA : ASGPU_E_INVALID, error); delete t; return nullptr; }
+    return t;
+}
+
 void asgpu_trees_destroy(asgpu_trees* trees) { delete trees; }
 
 int asgpu_trees_triangle_tree_count(const asgpu_trees* trees)

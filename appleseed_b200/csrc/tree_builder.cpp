@@ -23,6 +23,7 @@
 //
 
 #include "tree_builder.h"
+#include "lbvh_core.h"
 
 #include <algorithm>
 #include <atomic>
@@ -861,7 +862,97 @@ bool check_desc(const asgpu_scene_desc& d, std::string& error)
 
 }   // anonymous namespace
 
-bool build_host_trees(const asgpu_scene_desc& desc, int threads, HostTrees& out, std::string& error)
+//
+// Linear BVH -> reference node format.
+//
+// The topology arrives from lbvh.cu (or its host simulation); this lays it out exactly like
+// bvh::Builder does (bvh_builder.h:197-228: the two children of a node are adjacent, followed by
+// the whole left subtree, then the right one), with child boxes widened from float
+// (bvh_builder.h:193-204) and every subtree of at most max_leaf_size items folded into one leaf,
+// so that motion boxes, leaf payloads and the flattener see a tree of the usual shape.
+//
+
+static bool emit_lbvh(const LbvhTopology& t, const std::vector<BoundsF>& boxes, const size_t max_leaf_size, AsNodeVector& nodes, std::string& error)
+{
+    const size_t n = boxes.size();
+    if (t.order.size() != n || t.left.size() != n - 1 || t.right.size() != n - 1 || t.first.size() != n - 1 || t.last.size() != n - 1 ||
+        t.node_boxes.size() != (n - 1) * 6)
+    { error = "device tree build returned arrays of the wrong size"; return false; }
+    std::vector<uint8_t> seen(n, 0);
+    for (const uint32_t o : t.order)
+    {
+        if (o >= n || seen[o]) { error = "device tree build returned an ordering that is not a permutation"; return false; }
+        seen[o] = 1;
+    }
+
+    auto child_box = [&](const uint32_t ref) -> BoundsD
+    {
+        BoundsD b;
+        if (ref & LbvhLeafFlag)
+        {
+            const BoundsF& f = boxes[t.order[ref & ~LbvhLeafFlag]];
+            for (int a = 0; a < 3; ++a) { b.lo[a] = static_cast<double>(f.lo[a]); b.hi[a] = static_cast<double>(f.hi[a]); }
+        }
+        else
+        {
+            const float* f = t.node_boxes.data() + size_t(ref) * 6;
+            for (int a = 0; a < 3; ++a) { b.lo[a] = static_cast<double>(f[a]); b.hi[a] = static_cast<double>(f[3 + a]); }
+        }
+        return b;
+    };
+
+    struct Task { size_t slot; uint32_t ref; uint32_t first, last; uint32_t depth; };
+    AsNode blank; std::memset(&blank, 0, sizeof(blank));
+    nodes.clear();
+    nodes.reserve(2 * n / (max_leaf_size ? max_leaf_size : 1) + 2);
+    nodes.push_back(blank);
+    std::vector<Task> stack;
+    stack.push_back(Task{ 0, 0u, 0u, static_cast<uint32_t>(n - 1), 1u });
+    size_t placed = 0;
+    while (!stack.empty())
+    {
+        const Task k = stack.back();
+        stack.pop_back();
+        uint32_t first = k.first, last = k.last;
+        if (!(k.ref & LbvhLeafFlag))
+        {
+            // The range an interior node reports must be the one its parent handed down.
+            if (k.ref >= n - 1 || t.first[k.ref] != first || t.last[k.ref] != last) { error = "device tree build returned an inconsistent hierarchy"; return false; }
+        }
+        const size_t count = size_t(last) - first + 1;
+        if ((k.ref & LbvhLeafFlag) || count <= max_leaf_size)
+        {
+            nodes[k.slot].item_count = static_cast<uint32_t>(count);
+            nodes[k.slot].index = first;
+            placed += count;
+            continue;
+        }
+        // The exact traversal keeps the reference's 64-entry stack (intersectionsettings.h:95).
+        if (k.depth >= 64) { error = "linear BVH deeper than the 64-entry traversal stack (too many coincident centroids)"; return false; }
+        const uint32_t l = t.left[k.ref], r = t.right[k.ref];
+        const uint32_t split = (l & LbvhLeafFlag) ? (l & ~LbvhLeafFlag) : t.last[l < n - 1 ? l : 0];
+        if ((!(l & LbvhLeafFlag) && l >= n - 1) || split < first || split >= last) { error = "device tree build returned an inconsistent split"; return false; }
+        const size_t pair = nodes.size();
+        nodes.push_back(blank);
+        nodes.push_back(blank);
+        AsNode& node = nodes[k.slot];
+        node.item_count = 0xFFFFFFFFu;
+        node.index = static_cast<uint32_t>(pair);
+        const BoundsD lb = child_box(l), rb = child_box(r);
+        for (int a = 0; a < 3; ++a)
+        {
+            node.bbox[a * 4 + 0] = lb.lo[a]; node.bbox[a * 4 + 2] = lb.hi[a];
+            node.bbox[a * 4 + 1] = rb.lo[a]; node.bbox[a * 4 + 3] = rb.hi[a];
+        }
+        // Left subtree first: push right, then left.
+        stack.push_back(Task{ pair + 1, r, split + 1, last, k.depth + 1 });
+        stack.push_back(Task{ pair, l, first, split, k.depth + 1 });
+    }
+    if (placed != n) { error = "device tree build lost triangles"; return false; }
+    return true;
+}
+
+bool build_host_trees(const asgpu_scene_desc& desc, int threads, HostTrees& out, std::string& error, LbvhTopologyFn lbvh, void* lbvh_context)
 {
     if (!check_desc(desc, error)) return false;
     if (threads < 1) threads = std::max(1u, std::thread::hardware_concurrency());
@@ -932,6 +1023,20 @@ bool build_host_trees(const asgpu_scene_desc& desc, int threads, HostTrees& out,
         collect(desc, assembly, ab, c);
         if (c.keys.size() >= 0xFFFFFFFFull) { error = "too many triangles in one assembly"; return false; }
         for (const TriInfo& info : c.infos) (info.msc == 0 ? tree.static_triangle_count : tree.moving_triangle_count) += 1;
+
+        if (lbvh && c.boxes.size() >= 2 && c.boxes.size() > assembly.max_leaf_size)
+        {
+            if (c.boxes.size() >= LbvhLeafFlag) { error = "too many triangles in one assembly for the device tree build"; return false; }
+            BoundsF root; root.reset();
+            for (const BoundsF& b : c.boxes) root.grow(b);
+            LbvhTopology topology;
+            static_assert(sizeof(BoundsF) == 24, "boxes are passed as lo[3], hi[3]");
+            if (!lbvh(&c.boxes[0].lo[0], c.boxes.size(), root.lo, root.hi, lbvh_context, topology, error)) return false;
+            if (!emit_lbvh(topology, c.boxes, assembly.max_leaf_size, tree.nodes, error)) return false;
+            propagate_motion_boxes(tree, topology.order, c);
+            store_leaves(tree, topology.order, c);
+            continue;
+        }
 
         SweepBuilder<float> builder(c.boxes, assembly.max_leaf_size, assembly.interior_node_traversal_cost,
                                     assembly.triangle_intersection_cost, threads);

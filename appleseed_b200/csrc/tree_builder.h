@@ -67,7 +67,28 @@ struct HostTrees
     double                                          build_seconds = 0.0;
 };
 
-// Returns false and fills `error` on malformed input.
-bool build_host_trees(const asgpu_scene_desc& desc, int threads, HostTrees& out, std::string& error);
+// Topology of a linear BVH over n >= 2 boxes (lbvh_core.h): interior node i of n - 1 covers the
+// positions [first[i], last[i]] of `order` (box indices in Morton order); a child reference is an
+// interior node index, or a position | LbvhLeafFlag; node_boxes = lo[3], hi[3] per interior node.
+struct LbvhTopology
+{
+    std::vector<uint32_t>   order, left, right, first, last;
+    std::vector<float>      node_boxes;
+};
+
+// Computes the topology for `n` boxes (lo[3], hi[3] each) inside the root box: lbvh.cu on the
+// device in the product, a sequential host run of the same lbvh_core.h in tests/hostsim.
+typedef bool (*LbvhTopologyFn)(const float* boxes, size_t n, const float root_lo[3], const float root_hi[3], void* context,
+                               LbvhTopology& out, std::string& error);
+
+// The product's LbvhTopologyFn (lbvh.cu): `context` points at an int, the CUDA device ordinal.
+bool lbvh_topology_device(const float* boxes, size_t n, const float root_lo[3], const float root_hi[3], void* context,
+                          LbvhTopology& out, std::string& error);
+
+// Returns false and fills `error` on malformed input.  `lbvh` = null: the reference's sweep SAH for
+// every tree (result-identical to the reference); else the triangle trees take their topology from
+// `lbvh(..., lbvh_context, ...)` (the small assembly tree always uses the sweep).
+bool build_host_trees(const asgpu_scene_desc& desc, int threads, HostTrees& out, std::string& error,
+                      LbvhTopologyFn lbvh = nullptr, void* lbvh_context = nullptr);
 
 }   // namespace asgpu

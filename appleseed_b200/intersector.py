@@ -37,12 +37,17 @@ def _check(rc: int, what: str):
 
 
 class HostTrees:
-    """Reference-format trees built on the host (``asgpu_trees_build``)."""
+    """Reference-format trees: the reference's sweep SAH on the host (``asgpu_trees_build``), or,
+    with ``build_device`` = a CUDA device ordinal, triangle-tree topology built on that device as a
+    linear BVH (``asgpu_trees_build_on_device``)."""
 
-    def __init__(self, desc: SceneDesc, threads: int = 0):
+    def __init__(self, desc: SceneDesc, threads: int = 0, build_device: Optional[int] = None):
         self.lib = _lib.load()
         self._cdesc, self._keep = desc.to_c()
-        self.handle = self.lib.asgpu_trees_build(C.byref(self._cdesc), threads)
+        if build_device is None:
+            self.handle = self.lib.asgpu_trees_build(C.byref(self._cdesc), threads)
+        else:
+            self.handle = self.lib.asgpu_trees_build_on_device(C.byref(self._cdesc), threads, int(build_device))
         if not self.handle:
             raise AsgpuError("asgpu_trees_build failed: " + _lib.last_error())
 

@@ -213,6 +213,14 @@ typedef struct asgpu_source_geometry {
 typedef struct asgpu_trees asgpu_trees;
 
 asgpu_trees*    asgpu_trees_build(const asgpu_scene_desc* desc, int threads);
+
+/* Same trees-from-description entry point with the triangle-tree topology built on CUDA device
+ * `device`: a linear BVH in Morton order of the triangle centroids
+ * (Karras 2012), every node in parallel, instead of the reference's single-threaded sweep SAH
+ * (foundation/math/bvh/bvh_sahpartitioner.h:99-170, bvh_builder.h:163-229).  Same node format, same
+ * leaf payloads, same motion boxes; the TREE differs from the reference's (so traversal counters
+ * and exact-t tie order do), hit records do not.  No host fallback: fails without a device. */
+asgpu_trees*    asgpu_trees_build_on_device(const asgpu_scene_desc* desc, int threads, int device);
 void            asgpu_trees_destroy(asgpu_trees* trees);
 int             asgpu_trees_triangle_tree_count(const asgpu_trees* trees);
 int             asgpu_trees_get_triangle_tree(const asgpu_trees* trees, int index, asgpu_triangle_tree_view* out);

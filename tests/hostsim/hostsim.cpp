@@ -9,9 +9,11 @@
 //
 #include "../../appleseed_b200/csrc/flatten.h"
 #include "../../appleseed_b200/csrc/refine_core.h"
+#include "../../appleseed_b200/csrc/lbvh_core.h"
 #include "../../appleseed_b200/csrc/traverse_core.h"
 #include "../../appleseed_b200/csrc/tree_builder.h"
 
+#include <algorithm>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -70,6 +72,56 @@ namespace
     }
 }
 
+// Sequential host run of lbvh_core.h -- what lbvh.cu computes with one thread per element (keys,
+// stable sort by key as the radix sort is, every interior node, boxes bottom-up).
+static bool lbvh_topology_host(const float* boxes, size_t n, const float root_lo[3], const float root_hi[3], void*, LbvhTopology& out, std::string& error)
+{
+    float origin[3], scale[3];
+    for (int a = 0; a < 3; ++a)
+    {
+        const float extent = 2.0f * (root_hi[a] - root_lo[a]);
+        origin[a] = 2.0f * root_lo[a];
+        scale[a] = extent > 0.0f ? 2097152.0f / extent : 0.0f;
+    }
+    std::vector<uint64_t> keys(n), sorted(n);
+    out.order.resize(n);
+    for (size_t i = 0; i < n; ++i) { keys[i] = lbvh_morton(boxes + i * 6, origin, scale); out.order[i] = static_cast<uint32_t>(i); }
+    std::stable_sort(out.order.begin(), out.order.end(), [&keys](uint32_t a, uint32_t b) { return keys[a] < keys[b]; });
+    for (size_t i = 0; i < n; ++i) sorted[i] = keys[out.order[i]];
+    out.left.resize(n - 1); out.right.resize(n - 1); out.first.resize(n - 1); out.last.resize(n - 1);
+    out.node_boxes.assign((n - 1) * 6, 0.0f);
+    for (size_t i = 0; i + 1 < n; ++i)
+        lbvh_node(sorted.data(), static_cast<int64_t>(n), static_cast<int64_t>(i), out.left[i], out.right[i], out.first[i], out.last[i]);
+    // Bottom-up boxes: post-order over the interior nodes.
+    std::vector<uint32_t> stack(1, 0u), post;
+    while (!stack.empty())
+    {
+        const uint32_t x = stack.back(); stack.pop_back();
+        post.push_back(x);
+        if (post.size() > n) { error = "hierarchy has a cycle"; return false; }
+        if (!(out.left[x] & LbvhLeafFlag)) stack.push_back(out.left[x]);
+        if (!(out.right[x] & LbvhLeafFlag)) stack.push_back(out.right[x]);
+    }
+    for (size_t k = post.size(); k-- > 0; )
+    {
+        const uint32_t x = post[k];
+        const uint32_t c[2] = { out.left[x], out.right[x] };
+        float* dst = out.node_boxes.data() + size_t(x) * 6;
+        for (int side = 0; side < 2; ++side)
+        {
+            const float* src = (c[side] & LbvhLeafFlag) ? boxes + size_t(out.order[c[side] & ~LbvhLeafFlag]) * 6 : out.node_boxes.data() + size_t(c[side]) * 6;
+            for (int a = 0; a < 3; ++a)
+            {
+                dst[a] = side == 0 ? src[a] : std::min(dst[a], src[a]);
+                dst[3 + a] = side == 0 ? src[3 + a] : std::max(dst[3 + a], src[3 + a]);
+            }
+        }
+    }
+    return true;
+}
+
+static bool g_use_lbvh = false;
+
 extern "C" {
 
 const char* hostsim_last_error() { return g_error.c_str(); }
@@ -87,7 +139,7 @@ void* hostsim_scene_create_filtered(const asgpu_scene_desc* desc, uint32_t flags
                                     const uint32_t* filter_tree, const uint32_t* filter_object, const asgpu_intersection_filter* filters)
 {
     HostTrees trees;
-    if (!build_host_trees(*desc, threads, trees, g_error)) return nullptr;
+    if (!build_host_trees(*desc, threads, trees, g_error, g_use_lbvh ? lbvh_topology_host : nullptr)) return nullptr;
     std::vector<asgpu_triangle_tree_view> views(trees.triangle_trees.size());
     for (size_t i = 0; i < views.size(); ++i)
     {
@@ -146,6 +198,15 @@ void* hostsim_scene_create_filtered(const asgpu_scene_desc* desc, uint32_t flags
     s->view.tree_count = h.tree_count; s->view.item_count = h.item_count;
     s->view.top_node_count = h.top_node_count; s->view.top_wnode_count = h.top_wnode_count;
     s->view.wide_stack_need = h.wide_stack_need;
+    return s;
+}
+
+// Triangle trees as asgpu_trees_build_on_device makes them, with the topology from the host run above.
+void* hostsim_scene_create_lbvh(const asgpu_scene_desc* desc, uint32_t flags, int threads)
+{
+    g_use_lbvh = true;
+    void* s = hostsim_scene_create_filtered(desc, flags, threads, 0, nullptr, nullptr, nullptr);
+    g_use_lbvh = false;
     return s;
 }
 
