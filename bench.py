@@ -366,7 +366,7 @@ def run_gpu(args):
     t0 = time.perf_counter()
     build_s = flatten_s = bcast_s = 0.0
     if rank == 0:
-        trees = HostTrees(desc, threads=0)
+        trees = HostTrees(desc, threads=0, build_device=local_rank if args.tree_build == "device" else None)
         build_s = trees.build_seconds
         t1 = time.perf_counter()
         ctx = TraceContext(device=local_rank, trees=trees)
@@ -560,7 +560,7 @@ def run_gpu(args):
                 "kernel": "wide_kernel (8-wide quantised BVH, fp32 interval box tests, warp-cooperative exact fp64 triangle tests)",
                 "l2": "inputs larger than L2 (%.0f MB of rays + %.0f MB scene blob per step vs 126 MB L2)" % (h2d / 1e6, info["blob_bytes"] / 1e6),
                 "scene": {k: info[k] for k in ("triangle_count", "instance_count", "wide_node_count", "binary_node_count", "blob_bytes")},
-                "scene_build_s": round(build_s, 2), "flatten_upload_s": round(flatten_s, 2), "broadcast_s": round(bcast_s, 4),
+                "scene_build_s": round(build_s, 2), "tree_build": args.tree_build, "flatten_upload_s": round(flatten_s, 2), "broadcast_s": round(bcast_s, 4),
                 "per_ray": {k: round(v, 3) for k, v in per_ray.items()},
                 "parallelism": "rays sharded by rank, scene replicated by one NCCL broadcast" if world > 1 else "1 GPU",
             },
@@ -662,7 +662,7 @@ def run_gpu_c5(args):
     desc = make_scene(args)
     build_s = flatten_s = bcast_s = 0.0
     if rank == 0:
-        trees = HostTrees(desc, threads=0)
+        trees = HostTrees(desc, threads=0, build_device=local_rank if args.tree_build == "device" else None)
         build_s = trees.build_seconds
         t1 = time.perf_counter()
         ctx = TraceContext(device=local_rank, trees=trees)
@@ -763,7 +763,7 @@ def run_gpu_c5(args):
                 "image_checksum": checksum,
                 "l2": "inputs larger than L2 (%.0f MB scene blob, %.0f MB of queued rays per wavefront vs 126 MB L2)" % (info["blob_bytes"] / 1e6, args.rays * 72 / 1e6),
                 "scene": {k: info[k] for k in ("triangle_count", "instance_count", "wide_node_count", "binary_node_count", "blob_bytes")},
-                "scene_build_s": round(build_s, 2), "flatten_upload_s": round(flatten_s, 2), "broadcast_s": round(bcast_s, 4),
+                "scene_build_s": round(build_s, 2), "tree_build": args.tree_build, "flatten_upload_s": round(flatten_s, 2), "broadcast_s": round(bcast_s, 4),
                 "per_ray": {k: round(v, 3) for k, v in per_ray.items()},
                 "parallelism": "tiles dealt to ranks in Hilbert order, scene replicated by one NCCL broadcast" if world > 1 else "1 GPU",
             },
@@ -805,6 +805,8 @@ def main():
     ap.add_argument("--res", type=int, default=0, help="override the grid resolution (smaller scene for quick runs)")
     ap.add_argument("--cpu-rays", type=int, default=0, help="size of the CPU baseline sample (default: one whole batch)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--tree-build", default="sah", choices=["sah", "device"],
+                    help="sah: the reference's sweep SAH on the host (default, result-identical trees); device: linear BVH built by lbvh.cu")
     args = ap.parse_args()
     if args.rays == 0:
         args.rays = {"c1": 512 * 512, "c2": 16 * MI, "c3": 32 * MI, "c4": 16 * MI, "c5": 16 * MI}[args.workload]
