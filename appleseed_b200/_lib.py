@@ -30,7 +30,7 @@ EXPORTS = [
     "asgpu_path_stream_create", "asgpu_path_stream_destroy", "asgpu_path_stream_tile_count", "asgpu_path_stream_render",
     "asgpu_path_stream_read_image", "asgpu_path_stream_clear", "asgpu_path_stream_get_stats",
     "asgpu_path_stream_capture", "asgpu_path_stream_capture_count", "asgpu_path_stream_capture_get",
-    "asgpu_trees_build_on_device",
+    "asgpu_trees_build_on_device", "asgpu_trees_device_seconds",
 ]
 
 SCENE_EXACT = 1 << 0
@@ -136,6 +136,8 @@ def load() -> C.CDLL:
     lib.asgpu_trees_get_assembly_tree.argtypes = [C.c_void_p, P(AssemblyTreeView)]
     lib.asgpu_trees_build_seconds.restype = C.c_double
     lib.asgpu_trees_build_seconds.argtypes = [C.c_void_p]
+    lib.asgpu_trees_device_seconds.restype = C.c_double
+    lib.asgpu_trees_device_seconds.argtypes = [C.c_void_p]
     lib.asgpu_scene_create.restype = C.c_void_p
     lib.asgpu_scene_create.argtypes = [P(TriangleTreeView), C.c_uint32, P(AssemblyTreeView), C.c_uint32, C.c_int]
     lib.asgpu_scene_create_from_desc.restype = C.c_void_p

@@ -372,6 +372,7 @@ int asgpu_trees_get_assembly_tree(const asgpu_trees* trees, asgpu_assembly_tree_
 }
 
 double asgpu_trees_build_seconds(const asgpu_trees* trees) { return trees ? trees->trees.build_seconds : 0.0; }
+double asgpu_trees_device_seconds(const asgpu_trees* trees) { return trees ? trees->trees.topology_seconds : 0.0; }
 
 int asgpu_trees_get_source_geometry(const asgpu_trees* trees, int index, asgpu_source_geometry* out)
 {

@@ -28,6 +28,8 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <future>
 #include <limits>
@@ -1019,8 +1021,18 @@ bool build_host_trees(const asgpu_scene_desc& desc, int threads, HostTrees& out,
             std::memcpy(so.parent_to_local, oi.parent_to_local, sizeof(so.parent_to_local));
         }
 
+        const bool timing = std::getenv("ASGPU_BUILD_TIMING") != nullptr;
+        auto stamp = [timing, last = std::chrono::steady_clock::now()](const char* what) mutable
+        {
+            if (!timing) return;
+            const auto now = std::chrono::steady_clock::now();
+            std::fprintf(stderr, "asgpu build: %-24s %.3f s\n", what, std::chrono::duration<double>(now - last).count());
+            last = now;
+        };
+        stamp("source geometry");
         Collected c;
         collect(desc, assembly, ab, c);
+        stamp("collect");
         if (c.keys.size() >= 0xFFFFFFFFull) { error = "too many triangles in one assembly"; return false; }
         for (const TriInfo& info : c.infos) (info.msc == 0 ? tree.static_triangle_count : tree.moving_triangle_count) += 1;
 
@@ -1031,18 +1043,27 @@ bool build_host_trees(const asgpu_scene_desc& desc, int threads, HostTrees& out,
             for (const BoundsF& b : c.boxes) root.grow(b);
             LbvhTopology topology;
             static_assert(sizeof(BoundsF) == 24, "boxes are passed as lo[3], hi[3]");
+            const auto l0 = std::chrono::steady_clock::now();
             if (!lbvh(&c.boxes[0].lo[0], c.boxes.size(), root.lo, root.hi, lbvh_context, topology, error)) return false;
+            out.topology_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - l0).count();
+            stamp("topology (device)");
             if (!emit_lbvh(topology, c.boxes, assembly.max_leaf_size, tree.nodes, error)) return false;
+            stamp("emit nodes");
             propagate_motion_boxes(tree, topology.order, c);
+            stamp("motion boxes");
             store_leaves(tree, topology.order, c);
+            stamp("store leaves");
             continue;
         }
 
         SweepBuilder<float> builder(c.boxes, assembly.max_leaf_size, assembly.interior_node_traversal_cost,
                                     assembly.triangle_intersection_cost, threads);
         builder.build(tree.nodes);
+        stamp("sweep SAH");
         propagate_motion_boxes(tree, builder.ordering(), c);
+        stamp("motion boxes");
         store_leaves(tree, builder.ordering(), c);
+        stamp("store leaves");
     }
 
     // Top level (assemblytree.cpp:111-245): one item per assembly instance whose assembly has

@@ -65,6 +65,7 @@ struct HostTrees
     std::vector<std::vector<float>>                 mesh_vertices;      // copies of the static meshes (source geometry)
     std::vector<std::vector<uint32_t>>              mesh_triangles;
     double                                          build_seconds = 0.0;
+    double                                          topology_seconds = 0.0;    // inside the LbvhTopologyFn calls (device build only)
 };
 
 // Topology of a linear BVH over n >= 2 boxes (lbvh_core.h): interior node i of n - 1 covers the

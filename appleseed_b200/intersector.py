@@ -63,6 +63,10 @@ class HostTrees:
         return float(self.lib.asgpu_trees_build_seconds(self.handle))
 
     @property
+    def device_seconds(self) -> float:
+        return float(self.lib.asgpu_trees_device_seconds(self.handle))
+
+    @property
     def triangle_tree_count(self) -> int:
         return int(self.lib.asgpu_trees_triangle_tree_count(self.handle))
 

@@ -226,6 +226,8 @@ int             asgpu_trees_triangle_tree_count(const asgpu_trees* trees);
 int             asgpu_trees_get_triangle_tree(const asgpu_trees* trees, int index, asgpu_triangle_tree_view* out);
 int             asgpu_trees_get_assembly_tree(const asgpu_trees* trees, asgpu_assembly_tree_view* out);
 double          asgpu_trees_build_seconds(const asgpu_trees* trees);
+/* Part of it spent in the device topology build (upload, kernels, download); 0 for asgpu_trees_build. */
+double          asgpu_trees_device_seconds(const asgpu_trees* trees);
 /* Source geometry of triangle tree `index` (pointers into the handle's own copies). */
 int             asgpu_trees_get_source_geometry(const asgpu_trees* trees, int index, asgpu_source_geometry* out);
 
