@@ -104,6 +104,27 @@ struct ExactTree
     uint64_t                moving = 0;
 };
 
+// Shape of a binary tree in the reference's layout, whichever GPU layout it is flattened into:
+// bvh::Builder appends the two children of a node after every node that exists so far
+// (bvh_builder.h:197-205), so child indices grow towards the leaves -- which rules out cycles --
+// and the exact traversal keeps the reference's 64-entry stack, one entry per level at most
+// (intersectionsettings.h:95; the reference itself does not check).
+int check_hierarchy(const AsNode* nodes, const uint64_t count, const char* what, std::string& error)
+{
+    std::vector<uint8_t> depth(count, 0);
+    depth[0] = 1;
+    for (uint64_t n = 0; n < count; ++n)
+    {
+        if (!nodes[n].interior() || depth[n] == 0) continue;       // depth 0: not reachable from the root
+        const uint64_t child = nodes[n].index;
+        if (child <= n || child + 1 >= count) { error = std::string(what) + " is not in parent-before-child order"; return ASGPU_E_INVALID; }
+        if (depth[child] != 0 || depth[child + 1] != 0) { error = std::string(what) + " node has two parents"; return ASGPU_E_INVALID; }
+        if (depth[n] >= 64) { error = std::string(what) + " deeper than the 64-entry traversal stack"; return ASGPU_E_UNSUPPORTED; }
+        depth[child] = depth[child + 1] = static_cast<uint8_t>(depth[n] + 1);
+    }
+    return ASGPU_OK;
+}
+
 int decode_tree(const asgpu_triangle_tree_view& v, ExactTree& out, std::string& error)
 {
     if (v.node_count == 0 || !v.nodes) { error = "triangle tree without nodes"; return ASGPU_E_INVALID; }
@@ -111,6 +132,8 @@ int decode_tree(const asgpu_triangle_tree_view& v, ExactTree& out, std::string& 
     const AsNode* nodes = static_cast<const AsNode*>(v.nodes);
     const AsTriangleKey* keys = static_cast<const AsTriangleKey*>(v.triangle_keys);
     const bool motion = v.moving_triangle_count > 0;
+    const int shape = check_hierarchy(nodes, v.node_count, "triangle tree", error);
+    if (shape != ASGPU_OK) return shape;
 
     out.bnodes.resize(v.node_count);
     if (motion) out.mnodes.resize(v.node_count);
@@ -815,6 +838,15 @@ int flatten_scene(
     if (!top.nodes || top.node_count == 0) { error = "assembly tree without nodes"; return ASGPU_E_INVALID; }
     if (top.item_count && !top.items) { error = "null assembly item array"; return ASGPU_E_INVALID; }
     if (top.node_count >= 0xFFFFFFFFull || top.item_count >= 0xFFFFFFFFull) { error = "assembly tree too large"; return ASGPU_E_UNSUPPORTED; }
+    {
+        // The exact layout uploads these nodes as they are: check them whatever the layout flags say.
+        const AsNode* top_nodes = static_cast<const AsNode*>(top.nodes);
+        const int shape = check_hierarchy(top_nodes, top.node_count, "assembly tree", error);
+        if (shape != ASGPU_OK) return shape;
+        for (uint64_t i = 0; i < top.node_count; ++i)
+            if (!top_nodes[i].interior() && uint64_t(top_nodes[i].index) + top_nodes[i].item_count > top.item_count)
+            { error = "assembly tree item range out of range"; return ASGPU_E_INVALID; }
+    }
 
     const bool want_exact = (flags & ASGPU_SCENE_EXACT) != 0;
     const bool want_wide = (flags & ASGPU_SCENE_WIDE) != 0;

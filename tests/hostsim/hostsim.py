@@ -12,8 +12,10 @@ SCENE_EXACT, SCENE_WIDE = 1, 2
 
 
 def load():
-    subprocess.run(["make", "-s", "-C", _HERE], check=True)
-    lib = C.CDLL(os.path.join(_HERE, "libhostsim.so"))
+    override = os.environ.get("HOSTSIM_LIB")        # e.g. an AddressSanitizer build (tests/fuzz_views.py)
+    if not override:
+        subprocess.run(["make", "-s", "-C", _HERE], check=True)
+    lib = C.CDLL(override or os.path.join(_HERE, "libhostsim.so"))
     lib.hostsim_scene_create.restype = C.c_void_p
     lib.hostsim_scene_create.argtypes = [C.POINTER(CSceneDesc), C.c_uint32, C.c_int]
     lib.hostsim_scene_create_filtered.restype = C.c_void_p
