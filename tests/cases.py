@@ -197,3 +197,30 @@ def random_scene(seed, n_rays=6000, moving=True):
     rays.tmax = rng.choice(np.array([scenes.DBL_MAX, scenes.DBL_MAX, 0.5 * diag, 1.2 * diag]), size=n_rays)
     rays.dir[::11] *= rng.uniform(0.2, 5.0)                # directions need not be unit length (instance space)
     return desc, rays
+
+
+# Extreme but finite ray fields, and infinities where the reference's arithmetic stays meaningful
+# (an infinite origin misses everything, an infinite tmax is "no limit", tmin = +inf is an empty
+# interval): the wide kernels must still meet the parity rule on these.
+EXTREME_OK = {"org": [0.0, -0.0, 5e-324, -5e-324, 1e-300, 1e308, -1e308, np.inf, -np.inf],
+              "dir": [0.0, -0.0, 5e-324, -5e-324, 1e-300, 1e308, -1e308],
+              "tmin": [0.0, -0.0, 5e-324, -5e-324, 1e-300, 1e308, -1e308, np.inf],
+              "tmax": [0.0, -0.0, 5e-324, -5e-324, 1e-300, 1e308, -1e308, np.inf, -np.inf]}
+# Values with no meaning for a ray (NaN anywhere, an infinite direction, tmin = -inf): the exact
+# kernels still repeat the reference's arithmetic bit for bit; the wide kernels only promise to terminate.
+EXTREME_UNDEFINED = {"org": [np.nan], "dir": [np.nan, np.inf, -np.inf], "tmin": [np.nan, -np.inf], "tmax": [np.nan]}
+
+
+def extreme_rays(rays: RayBatch, table: dict, seed: int) -> RayBatch:
+    """`rays` with one field of every ray replaced by a value of `table`."""
+    rng = np.random.default_rng(seed)
+    f = {"org": rays.org.copy(), "dir": rays.dir.copy(), "tmin": rays.tmin.copy(), "tmax": rays.tmax.copy()}
+    names = sorted(table)
+    for k in range(len(rays)):
+        name = names[int(rng.integers(0, len(names)))]
+        value = table[name][int(rng.integers(0, len(table[name])))]
+        if f[name].ndim == 2:
+            f[name][k, int(rng.integers(0, 3))] = value
+        else:
+            f[name][k] = value
+    return RayBatch(f["org"], f["dir"], f["tmin"], f["tmax"], rays.time_absolute, rays.time_normalized, rays.flags)

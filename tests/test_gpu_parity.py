@@ -327,3 +327,24 @@ def test_full_size_c3_properties(engine, orc):
     assert exact[idx].tobytes() == ref.tobytes()
     parity.compare_hits(o, sub, wide[idx], ref)
     assert par[idx].tobytes() == o.refine_offset(sub, ref, threads=8).tobytes()
+
+
+@pytest.mark.parametrize("name", ["c3", "mixed"])
+def test_extreme_and_non_finite_rays(engine, orc, name):
+    desc, rays, _ = cases.CASES[name]()
+    o = orc.scene(desc)
+    ctx, isect = make(engine, desc)
+    ok = cases.extreme_rays(rays.slice(0, 6000), cases.EXTREME_OK, 5)
+    ref = o.trace(ok, threads=4)
+    assert isect.trace(ok, exact=True).tobytes() == ref.tobytes()
+    parity.compare_hits(o, ok, isect.trace(ok), ref)
+    pref = o.trace_probe(ok, threads=4)
+    assert np.array_equal(isect.trace_probe(ok, exact=True), pref)
+    parity.compare_probes(o, ok, isect.trace_probe(ok), pref)
+    # No meaning as rays (NaN, infinite direction, tmin = -inf): the exact kernels still repeat the
+    # reference bit for bit, the wide kernels terminate.
+    bad = cases.extreme_rays(rays.slice(0, 6000), cases.EXTREME_UNDEFINED, 6)
+    assert isect.trace(bad, exact=True).tobytes() == o.trace(bad, threads=4).tobytes()
+    assert np.array_equal(isect.trace_probe(bad, exact=True), o.trace_probe(bad, threads=4))
+    assert len(isect.trace(bad)) == len(bad) and len(isect.trace_probe(bad)) == len(bad)
+    ctx.close()

@@ -88,3 +88,22 @@ def test_reference_known_answers(sim):
         h, _ = s.trace(kat.empty_bbox_ray(), wide=wide)
         assert h["prim_type"][0] == 0 and h["t"][0] == 2.0
         assert s.trace_probe(kat.empty_bbox_ray(), wide=wide)[0][0] == 0
+
+
+@pytest.mark.parametrize("name", ["c3", "mixed"])
+def test_extreme_and_non_finite_rays(sim, orc, name):
+    desc, rays, _ = cases.CASES[name]()
+    o, s = orc.scene(desc), hostsim.SimScene(sim, desc)
+    ok = cases.extreme_rays(rays.slice(0, 6000), cases.EXTREME_OK, 5)
+    ref = o.trace(ok, threads=4)
+    assert s.trace(ok, wide=False)[0].tobytes() == ref.tobytes()
+    parity.compare_hits(o, ok, s.trace(ok, wide=True)[0], ref)
+    pref = o.trace_probe(ok, threads=4)
+    assert np.array_equal(s.trace_probe(ok, wide=False)[0], pref)
+    parity.compare_probes(o, ok, s.trace_probe(ok, wide=True)[0], pref)
+    assert (ref["prim_type"] == 2).sum() > 300
+    # No meaning as rays: the exact layout still repeats the reference bit for bit, the wide one terminates.
+    bad = cases.extreme_rays(rays.slice(0, 6000), cases.EXTREME_UNDEFINED, 6)
+    assert s.trace(bad, wide=False)[0].tobytes() == o.trace(bad, threads=4).tobytes()
+    assert np.array_equal(s.trace_probe(bad, wide=False)[0], o.trace_probe(bad, threads=4))
+    assert len(s.trace(bad, wide=True)[0]) == len(bad) and len(s.trace_probe(bad, wide=True)[0]) == len(bad)
