@@ -349,6 +349,10 @@ class SweepBuilder
         for (int a = 0; a < 3; ++a)
             if (best_cost > cand[a].cost) { best_cost = cand[a].cost; best_axis = a; best_pivot = cand[a].pivot; }
 
+        // No candidate at all: every cost overflowed or is NaN (coordinates near FLT_MAX, non-finite
+        // vertices).  The reference would split at `begin` and recurse for ever; make a leaf instead.
+        if (best_pivot == 0) return end;
+
         const T split_cost = m_ct + best_cost / box.half_area() * m_ci;
         const T leaf_cost = count * m_ci;
         if (leaf_cost <= split_cost) return end;
