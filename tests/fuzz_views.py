@@ -20,6 +20,11 @@ from appleseed_b200 import _lib  # noqa: E402
 from appleseed_b200.intersector import HostTrees  # noqa: E402
 from hostsim import hostsim  # noqa: E402
 
+class SourceObject(C.Structure):       # asgpu_source_object
+    _fields_ = [("vertices", C.c_void_p), ("triangles", C.c_void_p), ("vertex_count", C.c_uint32), ("triangle_count", C.c_uint32),
+                ("triangle_stride", C.c_uint32), ("reserved", C.c_uint32), ("parent_to_local", C.c_double * 16)]
+
+
 NODE_U32 = 32       # 128-byte node = 32 words: item_count, index, 4 motion box words, 2 pad, 24 words of boxes / user data
 
 
@@ -32,7 +37,16 @@ def snapshot(desc):
     for i in range(int(v.item_count)):
         C.memmove(C.byref(items[i]), C.byref(v.items[i]), C.sizeof(_lib.AssemblyItem))
     top = {"nodes": HostTrees._bytes(v.nodes, v.node_count * 128), "items": items, "item_count": int(v.item_count)}
-    trees.close()
+    # Source geometry: private copies of the object records; the vertex / index arrays they point at
+    # stay owned by `trees`, which therefore has to outlive the snapshot.
+    top["sources"] = []
+    for i in range(trees.triangle_tree_count):
+        g = trees.source_geometry(i)
+        objs = (SourceObject * max(1, g.object_count))()
+        if g.object_count:
+            C.memmove(objs, g.objects, C.sizeof(SourceObject) * g.object_count)
+        top["sources"].append((objs, int(g.object_count)))
+    top["keep"] = trees
     return tt, top
 
 
@@ -60,11 +74,39 @@ def views_of(tt, top):
     return views, a
 
 
+def sources_of(top):
+    out = []
+    for objs, count in top["sources"]:
+        g = _lib.SourceGeometry()
+        g.objects = C.cast(objs, C.c_void_p)
+        g.object_count = count
+        g.reserved = 0
+        g.filters = None
+        out.append(g)
+    return out
+
+
 def mutate(rng, tt, top):
     """One random corruption; returns a short description."""
     interesting = [0, 1, 2, 3, 0x7FFFFFFF, 0x80000000, 0xFFFFFFFE, 0xFFFFFFFF]
-    kind = int(rng.integers(0, 10))
+    kind = int(rng.integers(0, 12))
     t = tt[int(rng.integers(0, len(tt)))]
+    if kind >= 10 and top.get("sources"):           # source geometry: counts that no longer cover the keys, odd matrices
+        k = int(rng.integers(0, len(top["sources"])))
+        objs, count = top["sources"][k]
+        if count and rng.random() < 0.7:
+            o = objs[int(rng.integers(0, count))]
+            which = int(rng.integers(0, 3))
+            if which == 0:
+                o.vertex_count = int(rng.integers(0, max(1, o.vertex_count)))
+                return "source vertex_count = %d" % o.vertex_count
+            if which == 1:
+                o.triangle_count = int(rng.integers(0, max(1, o.triangle_count)))
+                return "source triangle_count = %d" % o.triangle_count
+            o.parent_to_local[int(rng.integers(0, 16))] = float(rng.choice([np.nan, np.inf, 0.0, 1e300]))
+            return "source matrix entry odd"
+        top["sources"][k] = (objs, int(rng.integers(0, count + 1)))
+        return "source object_count = %d" % top["sources"][k][1]
     nodes = t["nodes"].view(np.uint32).reshape(-1, NODE_U32)
     n = nodes.shape[0]
     value = int(rng.choice(interesting)) if rng.random() < 0.5 else int(rng.integers(0, max(2, 2 * n)))
@@ -125,14 +167,19 @@ def main():
                    triangle_keys=t["triangle_keys"].copy()) for t in tt0]
         items = (_lib.AssemblyItem * max(1, top0["item_count"]))()
         C.memmove(items, top0["items"], C.sizeof(items))
-        top = {"nodes": top0["nodes"].copy(), "items": items, "item_count": top0["item_count"]}
+        top = {"nodes": top0["nodes"].copy(), "items": items, "item_count": top0["item_count"], "sources": []}
+        for objs0, count0 in top0["sources"]:
+            objs = (SourceObject * max(1, count0))()
+            C.memmove(objs, objs0, C.sizeof(objs))
+            top["sources"].append((objs, count0))
         what = [mutate(rng, tt, top) for _ in range(int(rng.integers(1, 4)))]
         views, a = views_of(tt, top)
         sys.stdout.write("%d: %s\n" % (k, "; ".join(what)))
         sys.stdout.flush()
         try:
             flags = int(rng.choice([hostsim.SCENE_EXACT, hostsim.SCENE_WIDE, hostsim.SCENE_EXACT | hostsim.SCENE_WIDE]))
-            s = hostsim.SimScene.from_views(sim, views, a, [tt, top], flags=flags)
+            with_sources = bool(rng.integers(0, 2))
+            s = hostsim.SimScene.from_views(sim, views, a, [tt, top], flags=flags, sources=sources_of(top) if with_sources else None)
         except RuntimeError:
             rejected += 1
             continue
@@ -140,8 +187,12 @@ def main():
         # Accepted: the blob passed the product's own validation, so the traversals must stay inside it
         # and terminate.
         if flags & hostsim.SCENE_EXACT:
-            s.trace(rays, wide=False)
+            hits = s.trace(rays, wide=False)[0]
             s.trace_probe(rays, wide=False)
+            # refine_and_offset: static triangles only, and only when every tree has source geometry
+            # (asgpu_refine_and_offset refuses anything else before the kernel is launched: api.cu).
+            if with_sources and k % len(pristine) != 2 and all(count > 0 for _, count in top["sources"]):
+                s.refine_offset(rays, hits)
         if flags & hostsim.SCENE_WIDE:
             s.trace(rays, wide=True)
             s.trace_probe(rays, wide=True)
