@@ -53,3 +53,16 @@ def test_rejects_malformed_input():
     ok = Mesh(np.eye(3, dtype=np.float32), np.array([[0, 1, 2]], dtype=np.uint32))
     with pytest.raises(AsgpuError, match="assembly instance"):
         HostTrees(SceneDesc([ok], [Assembly([ObjectInstance(0)])], [AssemblyInstance(3)]))
+
+
+def test_collection_of_larger_meshes_and_dropped_triangles(orc):
+    # Moving triangles (pose-major vertices) and a static mesh with triangles that the collection
+    # drops (degenerate ones), which shifts every later triangle's vertex offset, at sizes where the
+    # builder works with several threads.  (A chunked, concurrent collection was tried against this
+    # test: byte-identical, but no faster than the serial walk -- it is copy bound -- and reverted.)
+    check_against(orc, scenes.scene_c4(200, msc=3), 8)
+    desc = scenes.scene_c2(200)
+    t = desc.meshes[0].triangles
+    t[::7, 2] = t[::7, 1]
+    check_against(orc, desc, 8)
+    check_against(orc, desc, 1)
