@@ -31,6 +31,7 @@ def main():
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--sort", action="store_true", help="also time every wavefront with ASGPU_TRACE_SORT (sort + trace) and the sort alone")
     ap.add_argument("--sweep", action="append", default=[], help="ENV=v1,v2,... (cartesian product of all sweeps)")
+    ap.add_argument("--tree-build", default="sah", choices=["sah", "device"], help="device: triangle trees from asgpu_trees_build_on_device (linear BVH)")
     args = ap.parse_args()
     dev = "cuda:0"
     sweeps = [(sw.split("=")[0], sw.split("=")[1].split(",")) for sw in args.sweep]
@@ -38,7 +39,11 @@ def main():
     for wl in args.workloads.split(","):
         a = argparse.Namespace(workload=wl, res=args.res, rays=args.rays)
         desc = bench.make_scene(a)
-        ctx = TraceContext(desc, device=0)
+        if args.tree_build == "device":
+            from appleseed_b200.intersector import HostTrees
+            ctx = TraceContext(trees=HostTrees(desc, build_device=0), device=0)
+        else:
+            ctx = TraceContext(desc, device=0)
         isect = Intersector(ctx)
         info = ctx.info()
         print(json.dumps({"workload": wl, "wide_nodes": info["wide_node_count"], "wide_stack_depth": info["wide_stack_depth"], "blob_MB": round(info["blob_bytes"] / 1e6, 1)}), flush=True)
