@@ -184,6 +184,8 @@ typedef struct orc_item_motion {
     uint32_t                        reserved;
 } orc_item_motion;
 
+/* bvh::Node<AABB3d> of the reference: store two child boxes, read them back, copy the raw node. */
+void    asref_kat_node_pack(const double left[6], const double right[6], uint32_t child_index, double back[12], unsigned char raw[128]);
 void*   asref_scene_create_animated(const orc_scene_desc* desc, const orc_instance_keys* keys /* per assembly instance */);
 void    asref_get_item_motion(const void* scene, uint32_t item /* tree order */, orc_item_motion* out);
 void    asref_get_item_parent_to_local(const void* scene, uint32_t item, double out[16]);

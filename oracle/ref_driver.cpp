@@ -1702,4 +1702,25 @@ void asref_kat_ray_info(const double dir[3], double rcp[3], uint32_t sgn[3])
     }
 }
 
+// foundation/meta/tests/test_bvh.cpp:62-75 through the reference's own bvh::Node<AABB3d>: stores
+// the two child boxes, reads them back, and hands out the node's 128 raw bytes -- the layout the
+// product's as_format.h (AsNode) and flattener rely on.
+void asref_kat_node_pack(const double left[6], const double right[6], uint32_t child_index, double back[12], unsigned char raw[128])
+{
+    static_assert(sizeof(bvh::Node<AABB3d>) == 128, "reference node size");
+    bvh::Node<AABB3d> node;
+    std::memset(&node, 0, sizeof(node));
+    node.make_interior();
+    node.set_child_node_index(child_index);
+    node.set_left_bbox(AABB3d(Vector3d(left[0], left[1], left[2]), Vector3d(left[3], left[4], left[5])));
+    node.set_right_bbox(AABB3d(Vector3d(right[0], right[1], right[2]), Vector3d(right[3], right[4], right[5])));
+    const AABB3d l = node.get_left_bbox(), r = node.get_right_bbox();
+    for (int k = 0; k < 3; ++k)
+    {
+        back[k] = l.min[k]; back[3 + k] = l.max[k];
+        back[6 + k] = r.min[k]; back[9 + k] = r.max[k];
+    }
+    std::memcpy(raw, &node, 128);
+}
+
 }   // extern "C"

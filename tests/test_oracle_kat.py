@@ -104,3 +104,44 @@ def test_visibility_flags(oracle):
     h = s.trace(kat.x_ray(flags=VIS_SHADOW))                              # only instance 1 visible
     assert h["t"][0] == 3.0 and h["assembly_instance"][0] == 1
     assert s.trace(kat.x_ray(flags=1 << 5))["prim_type"][0] == 0          # diffuse rays see nothing
+
+
+def test_node_packing(asref):
+    # foundation/meta/tests/test_bvh.cpp:62-75 (TestStorageAndRetrievalOf3DBoundingBoxes) on the
+    # reference's own bvh::Node<AABB3d>, plus the raw layout the product's AsNode / flattener assume
+    # (appleseed_b200/csrc/as_format.h; bvh_node.h:100-107, 141-162).
+    import ctypes as C
+    left = np.array([1.0, 2.0, 3.0, 4.0, 5.0, 6.0])
+    right = np.array([7.0, 8.0, 9.0, 10.0, 11.0, 12.0])
+    back, raw = np.zeros(12), np.zeros(128, dtype=np.uint8)
+    f = asref.lib.asref_kat_node_pack
+    f.restype = None
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+    f(left.ctypes.data, right.ctypes.data, 42, back.ctypes.data, raw.ctypes.data)
+    assert np.array_equal(back[:6], left) and np.array_equal(back[6:], right)          # EXPECT_EQ(LeftBBox, get_left_bbox()) ...
+    words = raw.view(np.uint32)
+    assert words[0] == 0xFFFFFFFF and words[1] == 42                                      # interior marker, first child
+    boxes = raw[32:].view(np.float64)
+    for axis in range(3):                                                                 # [minL minR maxL maxR] per axis
+        assert list(boxes[axis * 4: axis * 4 + 4]) == [left[axis], right[axis], left[3 + axis], right[3 + axis]]
+    # The product's flattener reads exactly this node: a root over two empty leaves.
+    from appleseed_b200 import _lib
+    from hostsim import hostsim
+    nodes = np.zeros(3 * 128, dtype=np.uint8)
+    f(left.ctypes.data, right.ctypes.data, 1, back.ctypes.data, raw.ctypes.data)
+    nodes[:128] = raw
+    nodes[128 + 32: 128 + 36] = 0xFF                                                       # leaves: no items, payload "in node"
+    nodes[256 + 32: 256 + 36] = 0xFF
+    view = _lib.TriangleTreeView()
+    view.nodes, view.node_count = nodes.ctypes.data, 3
+    item = (_lib.AssemblyItem * 1)()
+    item[0].parent_to_local[:] = np.eye(4).reshape(-1).tolist()
+    item[0].assembly_instance, item[0].triangle_tree, item[0].vis_flags = 0, 0, 0xFFFFFFFF
+    top_nodes = np.zeros(128, dtype=np.uint8)
+    top_nodes.view(np.uint32)[0] = 1                                                       # one leaf holding item 0
+    top = _lib.AssemblyTreeView()
+    top.nodes, top.items, top.node_count, top.item_count = top_nodes.ctypes.data, C.cast(item, C.POINTER(_lib.AssemblyItem)), 1, 1
+    s = hostsim.SimScene.from_views(hostsim.load(), [view], top, [nodes, top_nodes, item])
+    rays = kat.x_ray()
+    hits, counters = s.trace(rays, wide=False)
+    assert hits["prim_type"][0] == 0 and int(counters[3]) >= 1                              # the root was visited, nothing to hit
