@@ -186,6 +186,9 @@ typedef struct orc_item_motion {
 
 /* bvh::Node<AABB3d> of the reference: store two child boxes, read them back, copy the raw node. */
 void    asref_kat_node_pack(const double left[6], const double right[6], uint32_t child_index, double back[12], unsigned char raw[128]);
+/* foundation::BitMask2 of the reference after `count` set(x, y, value) calls: get() of every pixel and the raw storage. */
+void    asref_kat_bitmask(uint32_t width, uint32_t height, const uint32_t* xs, const uint32_t* ys, const unsigned char* values, uint32_t count,
+                          unsigned char* got, unsigned char* storage);
 void*   asref_scene_create_animated(const orc_scene_desc* desc, const orc_instance_keys* keys /* per assembly instance */);
 void    asref_get_item_motion(const void* scene, uint32_t item /* tree order */, orc_item_motion* out);
 void    asref_get_item_parent_to_local(const void* scene, uint32_t item, double out[16]);

@@ -1723,4 +1723,21 @@ void asref_kat_node_pack(const double left[6], const double right[6], uint32_t c
     std::memcpy(raw, &node, 128);
 }
 
+// foundation/meta/tests/test_bitmask.cpp:101-128 (StressTest) on the reference's own BitMask2: applies
+// `count` set(x, y, value) calls, then reports get(x, y) for every pixel and the object's raw
+// storage (m_bits, reached through the object layout: four size_t, then the pointer) -- the bytes an
+// in-tree integration hands to asgpu_alpha_mask::bits.
+void asref_kat_bitmask(uint32_t width, uint32_t height, const uint32_t* xs, const uint32_t* ys, const unsigned char* values, uint32_t count,
+                       unsigned char* got /* width * height */, unsigned char* storage /* ((width + 7) / 8) * height */)
+{
+    static_assert(sizeof(BitMask2) == 4 * sizeof(size_t) + sizeof(void*), "BitMask2 layout");
+    BitMask2 mask(width, height);
+    mask.clear();
+    for (uint32_t i = 0; i < count; ++i) mask.set(xs[i], ys[i], values[i] != 0);
+    for (uint32_t y = 0; y < height; ++y)
+        for (uint32_t x = 0; x < width; ++x) got[y * width + x] = mask.get(x, y) ? 1 : 0;
+    const std::uint8_t* bits = *reinterpret_cast<const std::uint8_t* const*>(reinterpret_cast<const char*>(&mask) + 4 * sizeof(size_t));
+    std::memcpy(storage, bits, mask.get_memory_size() > 0 ? ((width + 7) / 8) * size_t(height) : 0);
+}
+
 }   // extern "C"

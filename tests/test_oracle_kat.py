@@ -145,3 +145,31 @@ def test_node_packing(asref):
     rays = kat.x_ray()
     hits, counters = s.trace(rays, wide=False)
     assert hits["prim_type"][0] == 0 and int(counters[3]) >= 1                              # the root was visited, nothing to hit
+
+
+def test_bitmask_storage(asref):
+    # foundation/meta/tests/test_bitmask.cpp:101-128 (StressTest: 17 x 9, 1000 random set(x, y, value)
+    # calls, the mask must equal a plain bool array after each) on the reference's own BitMask2 -- and
+    # its raw storage must be the byte layout asgpu_alpha_mask::bits documents, i.e. what
+    # scene.pack_mask produces for every filter test of the product.
+    import ctypes as C
+    from appleseed_b200.scene import pack_mask
+    width, height, count = 17, 9, 1000
+    rng = np.random.default_rng(7)
+    xs = rng.integers(0, width, count).astype(np.uint32)
+    ys = rng.integers(0, height, count).astype(np.uint32)
+    vs = rng.integers(0, 2, count).astype(np.uint8)
+    f = asref.lib.asref_kat_bitmask
+    f.restype = None
+    f.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+    values = np.zeros((height, width), dtype=np.uint8)
+    for n in (0, 1, 10, 500, count):                                   # the reference checks after every call; a few prefixes here
+        values[:] = 0
+        for i in range(n):
+            values[ys[i], xs[i]] = vs[i]
+        got = np.zeros(width * height, dtype=np.uint8)
+        storage = np.zeros(((width + 7) // 8) * height, dtype=np.uint8)
+        f(width, height, xs.ctypes.data, ys.ctypes.data, vs.ctypes.data, n, got.ctypes.data, storage.ctypes.data)
+        assert np.array_equal(got.reshape(height, width), values)
+        assert storage.tobytes() == np.ascontiguousarray(pack_mask(values.astype(bool))).tobytes()
+    assert values.sum() > 30
