@@ -312,3 +312,69 @@ def test_random_animated_scenes_on_the_kernels(asref, seed):
     pref = o.trace_probe(rays, threads=4)
     assert np.array_equal(isect.trace_probe(rays, exact=True), pref)
     assert (isect.trace_probe(rays) != pref).sum() <= 2
+
+
+# foundation/meta/tests/test_transform.cpp:240-301 (TransformInterpolator), seen through the path: a unit
+# quad in the x = 1 plane of the instance (object instance translated by (1, 0, 0)), rays along +x.
+def interpolator_kat(first, second):
+    import kat
+    from appleseed_b200.scene import Assembly, AssemblyInstance, ObjectInstance, SceneDesc
+    desc = SceneDesc([kat.unit_quad()], [Assembly([ObjectInstance(0, scenes.translation(1.0, 0.0, 0.0))])], [AssemblyInstance(0, first)])
+    return desc, {0: InstanceKeys([0.0, 1.0], np.stack([first, second]))}
+
+
+def _x_rays(points, time):
+    from appleseed_b200.scene import RayBatch
+    org = np.array(points, dtype=np.float64)
+    return RayBatch(org, np.tile([1.0, 0.0, 0.0], (len(org), 1)), 0.0, np.finfo(np.float64).max,
+                    time_absolute=np.full(len(org), time, dtype=np.float32), time_normalized=np.zeros(len(org), dtype=np.float32))
+
+
+def _both(asref, desc, keys, rays):
+    from hostsim import hostsim
+    o = asref.scene(desc, keys=keys)
+    ref = o.trace(rays)
+    views, top, keep = product_views(asref, o, desc)
+    sim = hostsim.SimScene.from_views(hostsim.load(), views, top, keep)
+    assert sim.trace(rays, wide=False)[0].tobytes() == ref.tobytes()
+    wide = sim.trace(rays, wide=True)[0]
+    assert np.array_equal(wide["prim_type"], ref["prim_type"]) and np.array_equal(wide["t"], ref["t"])
+    return ref
+
+
+def test_interpolator_scaling_known_answer(asref):
+    # :240-251: identity -> scaling (3, 5, 0.6), evaluated at 0.5, has scaling (2, 3, 0.8) (EXPECT_FEQ).
+    desc, keys = interpolator_kat(np.eye(4), scenes.scaling(3.0, 5.0, 0.6))
+    rays = _x_rays([[0, 0, 0], [0, 1.49, 0], [0, 1.51, 0], [0, 0, 0.39], [0, 0, 0.41]], 0.5)
+    h = _both(asref, desc, keys, rays)
+    assert list(h["prim_type"]) == [2, 2, 0, 2, 0]                      # the quad spans +-0.5 * 3 in y and +-0.5 * 0.8 in z
+    assert np.all(np.abs(h["t"][h["prim_type"] == 2] - 2.0) <= 1e-14)   # and sits at x = 1 * 2
+
+
+def test_interpolator_mirroring_known_answers(asref):
+    # :253-270: identical mirrored from / to matrices -> the input transform (EXPECT_FEQ).
+    mirror = np.array([[-1.0, 0, 0, 4.0], [0, 1.0, 0, 6.0], [0, 0, 1.0, 8.0], [0, 0, 0, 1.0]])
+    desc, keys = interpolator_kat(mirror, mirror)
+    h = _both(asref, desc, keys, _x_rays([[0, 6, 8], [0, 6.49, 8.49], [0, 6.51, 8]], 0.5))
+    assert list(h["prim_type"]) == [2, 2, 0] and np.all(np.abs(h["t"][:2] - 3.0) <= 1e-14)     # x = 4 - 1
+    # :272-301: real-world matrices with mirroring, evaluated at 0.02432: a valid transform (its two
+    # halves are inverses of each other to 1e-9) -- here: a ray aimed at the image of the quad's
+    # centre under the evaluated local_to_parent hits it in the middle.
+    a = np.array([[-0.99702130594062099, 0.077087478205260004, -0.0025112020321310003, 0.76365516185966298],
+                  [0.077096829499781999, 0.99701625983943298, -0.0039071886356200000, 146.27250157945070],
+                  [-0.0022025165107730001, 0.0040890970283240001, 0.99998953373952104, 8.9871358181588690],
+                  [0.0, 0.0, 0.0, 1.0]])
+    b = np.array([[-0.99665231953250000, 0.081673207457143002, -0.0036906925368350003, 0.65271732495429602],
+                  [0.081677812416244000, 0.99665822601435605, -0.0011578872622540000, 145.34519371726373],
+                  [-0.0035839072864200005, 0.0014554931967890000, 0.99999257746504999, 9.0022056937678983],
+                  [0.0, 0.0, 0.0, 1.0]])
+    desc, keys = interpolator_kat(a, b)
+    t = np.float32(0.024320000000000008)
+    # The centre of the quad in world space (the keys are 2.4 % apart in time and nearly equal, so a
+    # linear blend of its two images locates it well within the quad): shoot at it from 10 units away.
+    centre_guess = (1.0 - t) * (a @ [1, 0, 0, 1])[:3] + t * (b @ [1, 0, 0, 1])[:3]
+    rays = _x_rays([[centre_guess[0] - 10.0, centre_guess[1], centre_guess[2]]], t)
+    rays.dir[0] = [1.0, 0.0, 0.0]
+    h = _both(asref, desc, keys, rays)
+    assert h["prim_type"][0] == 2 and abs(h["t"][0] - 10.0) < 1e-3
+    assert abs(h["u"][0] + h["v"][0] - 0.5) < 5e-3 or abs(max(h["u"][0], h["v"][0]) - 0.5) < 5e-3       # near the quad's centre (on its diagonal)
