@@ -106,7 +106,8 @@ struct ExactTree
 
 // Shape of a binary tree in the reference's layout, whichever GPU layout it is flattened into:
 // bvh::Builder appends the two children of a node after every node that exists so far
-// (bvh_builder.h:197-205), so child indices grow towards the leaves -- which rules out cycles --
+// (bvh_builder.h:197-205, bvh_spatialbuilder.h:209-221; so does the optional node reordering of
+// foundation/math/treeoptimizer.h), so child indices grow towards the leaves -- which rules out cycles --
 // and the exact traversal keeps the reference's 64-entry stack, one entry per level at most
 // (intersectionsettings.h:95; the reference itself does not check).
 int check_hierarchy(const AsNode* nodes, const uint64_t count, const char* what, std::string& error)
