@@ -31,6 +31,8 @@ EXPORTS = [
     "asgpu_path_stream_read_image", "asgpu_path_stream_clear", "asgpu_path_stream_get_stats",
     "asgpu_path_stream_capture", "asgpu_path_stream_capture_count", "asgpu_path_stream_capture_get",
     "asgpu_trees_build_on_device", "asgpu_trees_device_seconds",
+    "asgpu_get_support_planes", "asgpu_pin_host", "asgpu_unpin_host", "asgpu_reload_tuning",
+    "asgpu_path_stream_capture_get_times", "asgpu_path_stream_set_profiling", "asgpu_path_stream_get_profile",
 ]
 
 SCENE_EXACT = 1 << 0
@@ -96,7 +98,18 @@ class PathStreamDesc(C.Structure):
         ("seed", C.c_uint64), ("camera_to_world", C.c_double * 12),
         ("film_width", C.c_double), ("film_height", C.c_double), ("focal_length", C.c_double),
         ("lights", (C.c_double * 3) * 8), ("offset_eps", C.c_double),
+        ("shutter_open", C.c_float), ("shutter_close", C.c_float),
     ]
+
+
+class PathStreamProfile(C.Structure):
+    _fields_ = [
+        ("closest_ms", C.c_double), ("probe_ms", C.c_double), ("refine_ms", C.c_double), ("stage_ms", C.c_double),
+        ("closest_launches", C.c_uint64), ("probe_launches", C.c_uint64),
+    ]
+
+    def as_dict(self):
+        return {k: (float if "ms" in k else int)(getattr(self, k)) for k, _ in self._fields_}
 
 
 class PathStreamStats(C.Structure):
@@ -187,6 +200,15 @@ def load() -> C.CDLL:
     lib.asgpu_path_stream_capture_count.argtypes = [C.c_void_p]
     lib.asgpu_path_stream_capture_get.restype = C.c_longlong
     lib.asgpu_path_stream_capture_get.argtypes = [C.c_void_p, C.c_int, P(C.c_int), P(C.c_uint32)] + [C.c_void_p] * 8
+    lib.asgpu_path_stream_capture_get_times.restype = C.c_longlong
+    lib.asgpu_path_stream_capture_get_times.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    lib.asgpu_path_stream_set_profiling.argtypes = [C.c_void_p, C.c_int]
+    lib.asgpu_path_stream_get_profile.argtypes = [C.c_void_p, P(PathStreamProfile)]
+    lib.asgpu_get_support_planes.argtypes = [C.c_void_p, P(CRays), C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+    lib.asgpu_pin_host.argtypes = [C.c_void_p, C.c_size_t]
+    lib.asgpu_unpin_host.argtypes = [C.c_void_p]
+    lib.asgpu_reload_tuning.restype = None
+    lib.asgpu_reload_tuning.argtypes = []
     _lib = lib
     return lib
 

@@ -102,9 +102,8 @@ void free_staging(asgpu_scene* s)
     s->staging_ready = false;
 }
 
-int ensure_staging(asgpu_scene* s)
+int allocate_staging(asgpu_scene* s)
 {
-    if (s->staging_ready) return ASGPU_OK;
     for (Staging& st : s->staging)
     {
         ASGPU_CUDA(cudaStreamCreateWithFlags(&st.stream, cudaStreamNonBlocking), "cudaStreamCreate");
@@ -119,6 +118,22 @@ int ensure_staging(asgpu_scene* s)
         ASGPU_CUDA(cudaMalloc(&st.occluded, host_chunk_rays()), "cudaMalloc(staging)");
         ASGPU_CUDA(cudaMalloc(&st.queue, 64), "cudaMalloc(staging)");
         ASGPU_CUDA(cudaMalloc(&st.sort_ws, ray_sort_workspace_bytes(host_chunk_rays()) + host_chunk_rays() * 4), "cudaMalloc(staging)");
+    }
+    return ASGPU_OK;
+}
+
+int ensure_staging(asgpu_scene* s)
+{
+    if (s->staging_ready) return ASGPU_OK;
+    const int rc = allocate_staging(s);
+    if (rc != ASGPU_OK)
+    {
+        // Nothing half-allocated survives: the next call starts from scratch instead of
+        // overwriting (and leaking) the streams and buffers that did get created.
+        const std::string message = g_last_error;
+        free_staging(s);
+        g_last_error = message;
+        return rc;
     }
     s->staging_ready = true;
     return ASGPU_OK;
@@ -143,20 +158,27 @@ int trace_device(asgpu_scene* scene, const asgpu_rays* rays, const size_t n, asg
     const int rc = check_trace_args(scene, rays, n, any_hit ? static_cast<const void*>(occluded) : static_cast<const void*>(hits), flags, wide);
     if (rc != ASGPU_OK || n == 0) return rc;
     ASGPU_CUDA(cudaSetDevice(scene->device), "cudaSetDevice");
+    // ASGPU_TRACE_SORT: the permutation and the sort workspace are stream-ordered allocations of
+    // THIS call (cudaMallocAsync / cudaFreeAsync on the caller's stream), so any number of sorted
+    // traces may be in flight on different streams or threads without sharing scratch memory.
+    cudaStream_t cs = static_cast<cudaStream_t>(stream);
+    uint8_t* scratch = nullptr;
     const uint32_t* order = nullptr;
     if (flags & ASGPU_TRACE_SORT)
     {
         if (n > 0xFFFFFFFFull) return fail(ASGPU_E_UNSUPPORTED, "ASGPU_TRACE_SORT handles at most 2^32 - 1 rays per call");
-        const int rs = ensure_sort_scratch(scene, n);
-        if (rs != ASGPU_OK) return rs;
-        const int es = launch_ray_sort(*rays, n, nullptr, scene->sort.order, nullptr, scene->sort.ws, scene->sm_count, stream);
-        if (es != 0) return fail_cuda(static_cast<cudaError_t>(es), "ray sort launch");
+        const size_t ws_bytes = (ray_sort_workspace_bytes(n) + 255) / 256 * 256;
+        ASGPU_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&scratch), ws_bytes + n * sizeof(uint32_t), cs), "cudaMallocAsync(sort scratch)");
+        uint32_t* call_order = reinterpret_cast<uint32_t*>(scratch + ws_bytes);
+        const int es = launch_ray_sort(*rays, n, nullptr, call_order, nullptr, scratch, scene->sm_count, stream);
+        if (es != 0) { cudaFreeAsync(scratch, cs); return fail_cuda(static_cast<cudaError_t>(es), "ray sort launch"); }
         scene->launches += ray_sort_launch_count();
-        order = scene->sort.order;
+        order = call_order;
     }
     const int err = launch_trace(scene->view, *rays, n, hits, occluded, any_hit, wide, queue,
                                  (flags & ASGPU_TRACE_COUNTERS) ? scene->counters : nullptr, order, scene->sm_count, stream,
                                  nullptr, false, parents);
+    if (scratch) cudaFreeAsync(scratch, cs);        // ordered after the trace kernel on `stream`
     if (err != 0) return fail_cuda(static_cast<cudaError_t>(err), "kernel launch");
     ++scene->launches;
     return ASGPU_OK;
@@ -173,11 +195,11 @@ int trace_host(asgpu_scene* scene, const asgpu_rays* rays, const size_t n, asgpu
     rc = ensure_staging(scene);
     if (rc != ASGPU_OK) return rc;
 
-    size_t chunk_index = 0;
-    for (size_t begin = 0; begin < n; begin += host_chunk_rays(), ++chunk_index)
+    // One chunk: H2D of its rays, optional sort, trace, D2H of its results, all on one of the
+    // staging streams.  The copies are asynchronous when the caller's arrays are page-locked
+    // (asgpu_pin_host); from pageable memory the driver stages them synchronously.
+    auto run_chunk = [&](const size_t begin, const size_t count, Staging& st) -> int
     {
-        const size_t count = std::min(host_chunk_rays(), n - begin);
-        Staging& st = scene->staging[chunk_index % HostStreams];
         // Stream order guarantees the previous use of this staging slot has drained.
         ASGPU_CUDA(cudaMemcpyAsync(st.org, rays->org + begin * 3, count * 24, cudaMemcpyHostToDevice, st.stream), "H2D org");
         ASGPU_CUDA(cudaMemcpyAsync(st.dir, rays->dir + begin * 3, count * 24, cudaMemcpyHostToDevice, st.stream), "H2D dir");
@@ -218,25 +240,25 @@ int trace_host(asgpu_scene* scene, const asgpu_rays* rays, const size_t n, asgpu
             ASGPU_CUDA(cudaMemcpyAsync(occluded + begin, st.occluded, count, cudaMemcpyDeviceToHost, st.stream), "D2H occluded");
         else
             ASGPU_CUDA(cudaMemcpyAsync(hits + begin, st.hits, count * sizeof(asgpu_hit), cudaMemcpyDeviceToHost, st.stream), "D2H hits");
-    }
+        return ASGPU_OK;
+    };
+
+    size_t chunk_index = 0;
+    for (size_t begin = 0; begin < n && rc == ASGPU_OK; begin += host_chunk_rays(), ++chunk_index)
+        rc = run_chunk(begin, std::min(host_chunk_rays(), n - begin), scene->staging[chunk_index % HostStreams]);
+    // Also on an error: earlier chunks may still be copying into the caller's arrays, which must
+    // not be released before those copies have drained.
+    const std::string message = g_last_error;
     for (Staging& st : scene->staging)
-        ASGPU_CUDA(cudaStreamSynchronize(st.stream), "cudaStreamSynchronize");
-    return ASGPU_OK;
+    {
+        const cudaError_t e = cudaStreamSynchronize(st.stream);
+        if (e != cudaSuccess && rc == ASGPU_OK) rc = fail_cuda(e, "cudaStreamSynchronize");
+        else if (rc != ASGPU_OK) g_last_error = message;
+    }
+    return rc;
 }
 
 }   // anonymous namespace
-
-int asgpu::ensure_sort_scratch(asgpu_scene* scene, const size_t n)
-{
-    if (n <= scene->sort.capacity) return ASGPU_OK;
-    ASGPU_CUDA(cudaDeviceSynchronize(), "cudaDeviceSynchronize");
-    cudaFree(scene->sort.ws); cudaFree(scene->sort.order);
-    scene->sort = SortScratch();
-    ASGPU_CUDA(cudaMalloc(&scene->sort.ws, ray_sort_workspace_bytes(n)), "cudaMalloc(sort workspace)");
-    ASGPU_CUDA(cudaMalloc(&scene->sort.order, n * sizeof(uint32_t)), "cudaMalloc(sort order)");
-    scene->sort.capacity = n;
-    return ASGPU_OK;
-}
 
 size_t asgpu::host_chunk_rays()
 {
@@ -442,8 +464,6 @@ void asgpu_scene_destroy(asgpu_scene* scene)
     if (scene->owns_blob) cudaFree(scene->blob);
     cudaFree(scene->queue);
     cudaFree(scene->counters);
-    cudaFree(scene->sort.ws);
-    cudaFree(scene->sort.order);
     cudaFree(scene->id_to_item);
     delete scene;
 }
@@ -469,11 +489,27 @@ asgpu_scene* asgpu_scene_import_blob(const void* device_blob, size_t size, int d
     s->device = device;
     s->blob_bytes = size;
     if (init_device_side(s) != ASGPU_OK) { asgpu_scene_destroy(s); return nullptr; }
-    // Only the header and the small tables are inspected on the host.
-    cudaError_t e = cudaMemcpy(&s->header, device_blob, sizeof(BlobHeader), cudaMemcpyDeviceToHost);
+    // The payload usually arrives by a collective on some stream of the caller's (the NCCL broadcast
+    // of distributed.replicate_scene): everything enqueued on the device must have landed before the
+    // header is read.  Import happens once per scene, a device-wide wait is cheap here.
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { fail_cuda(e, "cudaDeviceSynchronize"); asgpu_scene_destroy(s); return nullptr; }
+    // Only the header and the small tables are inspected on the host -- with the same structural
+    // checks the flattener's own output goes through, so a truncated or corrupted payload is
+    // refused here instead of being dereferenced by the kernels.
+    {
+        const uint8_t* src = static_cast<const uint8_t*>(device_blob);
+        std::string error;
+        const int rc = validate_blob_tables(
+            [src, size](uint64_t offset, void* dst, size_t bytes) -> bool
+            {
+                if (offset > size || bytes > size - offset) return false;
+                return cudaMemcpy(dst, src + offset, bytes, cudaMemcpyDeviceToHost) == cudaSuccess;
+            }, size, error);
+        if (rc != ASGPU_OK) { fail(rc, "imported blob failed validation: " + error); asgpu_scene_destroy(s); return nullptr; }
+    }
+    e = cudaMemcpy(&s->header, device_blob, sizeof(BlobHeader), cudaMemcpyDeviceToHost);
     if (e != cudaSuccess) { fail_cuda(e, "cudaMemcpy(blob header)"); asgpu_scene_destroy(s); return nullptr; }
-    if (s->header.magic != BlobMagic || s->header.version != BlobVersion || s->header.total_bytes != size)
-    { fail(ASGPU_E_INVALID, "blob header mismatch"); asgpu_scene_destroy(s); return nullptr; }
     if (adopt)
     {
         s->blob = const_cast<uint8_t*>(static_cast<const uint8_t*>(device_blob));
@@ -550,7 +586,6 @@ int asgpu_refine_and_offset(asgpu_scene* scene, const asgpu_rays* rays, const as
     if (!rays || !rays->org || !rays->dir || !hits || !parents) return fail(ASGPU_E_INVALID, "null argument");
     if (!(scene->header.flags & ASGPU_SCENE_EXACT)) return fail(ASGPU_E_INVALID, "refine_and_offset needs the per-slot triangle records of the exact layout");
     if (!scene->has_source) return fail(ASGPU_E_INVALID, "the scene was created without source geometry (asgpu_scene_create_ex)");
-    if (scene->header.moving_triangle_count != 0) return fail(ASGPU_E_UNSUPPORTED, "refine_and_offset handles static triangles only");
     ASGPU_CUDA(cudaSetDevice(scene->device), "cudaSetDevice");
     const int rt = ensure_id_table(scene);
     if (rt != ASGPU_OK) return rt;
@@ -560,6 +595,37 @@ int asgpu_refine_and_offset(asgpu_scene* scene, const asgpu_rays* rays, const as
     return ASGPU_OK;
 }
 
+int asgpu_get_support_planes(asgpu_scene* scene, const asgpu_rays* rays, const asgpu_hit* hits, size_t n, double* planes, void* stream)
+{
+    if (!scene) return fail(ASGPU_E_INVALID, "null scene");
+    if (n == 0) return ASGPU_OK;
+    if (!rays || !hits || !planes) return fail(ASGPU_E_INVALID, "null argument");
+    if (!(scene->header.flags & ASGPU_SCENE_EXACT)) return fail(ASGPU_E_INVALID, "support planes need the per-slot triangle records of the exact layout");
+    ASGPU_CUDA(cudaSetDevice(scene->device), "cudaSetDevice");
+    const int rt = ensure_id_table(scene);
+    if (rt != ASGPU_OK) return rt;
+    const int err = launch_support_planes(scene->view, *rays, hits, n, false, scene->id_to_item, scene->id_count, planes, scene->sm_count, stream);
+    if (err != 0) return fail_cuda(static_cast<cudaError_t>(err), "kernel launch");
+    ++scene->launches;
+    return ASGPU_OK;
+}
+
+int asgpu_pin_host(void* ptr, size_t bytes)
+{
+    if (!ptr || bytes == 0) return fail(ASGPU_E_INVALID, "null range");
+    ASGPU_CUDA(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable), "cudaHostRegister");
+    return ASGPU_OK;
+}
+
+int asgpu_unpin_host(void* ptr)
+{
+    if (!ptr) return fail(ASGPU_E_INVALID, "null range");
+    ASGPU_CUDA(cudaHostUnregister(ptr), "cudaHostUnregister");
+    return ASGPU_OK;
+}
+
+void asgpu_reload_tuning(void) { reload_tuning(); }
+
 int asgpu_sort_rays(asgpu_scene* scene, const asgpu_rays* rays, size_t n, uint32_t* order, uint32_t* keys, void* stream)
 {
     if (!scene) return fail(ASGPU_E_INVALID, "null scene");
@@ -567,9 +633,11 @@ int asgpu_sort_rays(asgpu_scene* scene, const asgpu_rays* rays, size_t n, uint32
     if (!rays || !rays->org || !rays->dir || !order) return fail(ASGPU_E_INVALID, "null argument");
     if (n > 0xFFFFFFFFull) return fail(ASGPU_E_UNSUPPORTED, "at most 2^32 - 1 rays per sort");
     ASGPU_CUDA(cudaSetDevice(scene->device), "cudaSetDevice");
-    const int rs = ensure_sort_scratch(scene, n);
-    if (rs != ASGPU_OK) return rs;
-    const int es = launch_ray_sort(*rays, n, nullptr, order, keys, scene->sort.ws, scene->sm_count, stream);
+    cudaStream_t cs = static_cast<cudaStream_t>(stream);
+    void* ws = nullptr;
+    ASGPU_CUDA(cudaMallocAsync(&ws, ray_sort_workspace_bytes(n), cs), "cudaMallocAsync(sort workspace)");
+    const int es = launch_ray_sort(*rays, n, nullptr, order, keys, ws, scene->sm_count, stream);
+    cudaFreeAsync(ws, cs);
     if (es != 0) return fail_cuda(static_cast<cudaError_t>(es), "ray sort launch");
     scene->launches += ray_sort_launch_count();
     return ASGPU_OK;

@@ -46,14 +46,6 @@ struct Staging
     void*           sort_ws = nullptr;      // coherence-sort workspace + permutation of one chunk
 };
 
-// Coherence-sort scratch of the device entry points: grown on demand, one user at a time.
-struct SortScratch
-{
-    void*           ws = nullptr;
-    uint32_t*       order = nullptr;
-    size_t          capacity = 0;           // rays
-};
-
 }   // namespace asgpu
 
 struct asgpu_scene
@@ -72,7 +64,6 @@ struct asgpu_scene
     std::mutex          mutex;
     asgpu::Staging      staging[asgpu::HostStreams];
     bool                staging_ready = false;
-    asgpu::SortScratch  sort;
     bool                has_source = false;     // every triangle tree carries source geometry
     uint32_t*           id_to_item = nullptr;   // device: caller's assembly-instance id -> ItemRecord index (built on demand)
     uint32_t            id_count = 0;
@@ -80,8 +71,6 @@ struct asgpu_scene
 
 namespace asgpu
 {
-// Makes sure scene->sort can take n rays (reallocates after synchronising the device).
-int ensure_sort_scratch(asgpu_scene* scene, size_t n);
 // Builds scene->id_to_item (needs unique instance ids below 2^24).
 int ensure_id_table(asgpu_scene* scene);
 }

@@ -908,13 +908,19 @@ int flatten_scene(
                 const asgpu_source_object& so = sg.objects[o];
                 SrcObject& dst = objs[o];
                 std::memset(&dst, 0, sizeof(dst));
-                if ((so.vertex_count && !so.vertices) || (so.triangle_count && !so.triangles) || (so.triangle_count && so.triangle_stride < 12))
+                if ((so.vertex_count && !so.vertices) || (so.triangle_count && !so.triangles) || (so.triangle_count && so.triangle_stride < 12) ||
+                    (so.motion_segment_count && so.vertex_count && !so.vertex_poses))
                 { error = "malformed source object"; return ASGPU_E_INVALID; }
                 for (int r = 0; r < 3; ++r)
                     for (int c = 0; c < 3; ++c) dst.parent_to_local[r * 3 + c] = so.parent_to_local[r * 4 + c];
                 dst.vertex_count = so.vertex_count;
                 dst.triangle_count = so.triangle_count;
                 dst.vertices = writer.append(so.vertices, size_t(so.vertex_count) * 12);
+                if (so.motion_segment_count && so.vertex_count)
+                {
+                    dst.poses = writer.append(so.vertex_poses, size_t(so.vertex_count) * so.motion_segment_count * 12);
+                    dst.motion_segment_count = so.motion_segment_count;
+                }
                 std::vector<uint32_t> packed(size_t(so.triangle_count) * 3);
                 const uint8_t* src = static_cast<const uint8_t*>(so.triangles);
                 for (size_t t = 0; t < so.triangle_count; ++t)
@@ -1075,24 +1081,27 @@ int flatten_scene(
     return ASGPU_OK;
 }
 
-int validate_blob(const uint8_t* blob, size_t size, std::string& error)
+int validate_blob_tables(const BlobReader& read, const uint64_t size, std::string& error)
 {
-    if (!blob || size < sizeof(BlobHeader)) { error = "blob too small"; return ASGPU_E_INVALID; }
+    if (size < sizeof(BlobHeader)) { error = "blob too small"; return ASGPU_E_INVALID; }
     BlobHeader h;
-    std::memcpy(&h, blob, sizeof(h));
+    if (!read(0, &h, sizeof(h))) { error = "blob header unreadable"; return ASGPU_E_INVALID; }
     if (h.magic != BlobMagic || h.version != BlobVersion) { error = "blob magic/version mismatch"; return ASGPU_E_INVALID; }
     if (h.total_bytes != size) { error = "blob size mismatch"; return ASGPU_E_INVALID; }
     auto inside = [&](uint64_t off, uint64_t bytes) { return off <= size && bytes <= size - off; };
     if (!inside(h.trees, uint64_t(h.tree_count) * sizeof(TreeDesc)) || !inside(h.items, uint64_t(h.item_count) * sizeof(ItemRecord)) ||
-        !inside(h.top_nodes, uint64_t(h.top_node_count) * sizeof(BNodeD)) || !inside(h.top_wnodes, uint64_t(h.top_wnode_count) * sizeof(WNode)))
+        !inside(h.top_nodes, uint64_t(h.top_node_count) * sizeof(BNodeD)) || !inside(h.top_wnodes, uint64_t(h.top_wnode_count) * sizeof(WNode)) ||
+        !inside(h.top_witems, h.top_witems ? uint64_t(h.item_count) * 4 : 0))
     { error = "blob section out of range"; return ASGPU_E_INVALID; }
     for (uint32_t i = 0; i < h.tree_count; ++i)
     {
         TreeDesc d;
-        std::memcpy(&d, blob + h.trees + uint64_t(i) * sizeof(TreeDesc), sizeof(d));
+        if (!read(h.trees + uint64_t(i) * sizeof(TreeDesc), &d, sizeof(d))) { error = "blob tree table unreadable"; return ASGPU_E_INVALID; }
         if (!inside(d.bnodes, uint64_t(d.bnode_count) * sizeof(BNodeF)) || !inside(d.wnodes, uint64_t(d.wnode_count) * sizeof(WNode)) ||
             !inside(d.keys, uint64_t(d.slot_count) * sizeof(HitKey)) || !inside(d.tris, d.tris ? uint64_t(d.slot_count) * sizeof(TriRecord) : 0) ||
             !inside(d.wtris, d.wtris ? uint64_t(d.slot_count) * sizeof(TriRecord) : 0) ||
+            !inside(d.mnodes, d.mnodes ? uint64_t(d.bnode_count) * sizeof(MNode) : 0) ||
+            !inside(d.mboxes, uint64_t(d.mbox_count) * sizeof(MBox)) ||
             !inside(d.wslices, uint64_t(d.wnode_count) * d.wslice_count * sizeof(WSlice)) ||
             !inside(d.src_objects, uint64_t(d.src_object_count) * sizeof(SrcObject)) ||
             !inside(d.filters, uint64_t(d.filter_count) * sizeof(FilterRecord)) ||
@@ -1101,26 +1110,38 @@ int validate_blob(const uint8_t* blob, size_t size, std::string& error)
         for (uint32_t o = 0; o < d.src_object_count; ++o)
         {
             SrcObject so;
-            std::memcpy(&so, blob + d.src_objects + uint64_t(o) * sizeof(SrcObject), sizeof(so));
-            if (!inside(so.vertices, uint64_t(so.vertex_count) * 12) || !inside(so.triangles, uint64_t(so.triangle_count) * 12))
+            if (!read(d.src_objects + uint64_t(o) * sizeof(SrcObject), &so, sizeof(so))) { error = "blob source table unreadable"; return ASGPU_E_INVALID; }
+            if (!inside(so.vertices, uint64_t(so.vertex_count) * 12) || !inside(so.triangles, uint64_t(so.triangle_count) * 12) ||
+                !inside(so.poses, so.poses ? uint64_t(so.vertex_count) * so.motion_segment_count * 12 : 0) || (so.motion_segment_count && so.vertex_count && !so.poses))
             { error = "blob source geometry out of range"; return ASGPU_E_INVALID; }
         }
         for (uint32_t o = 0; o < d.filter_count; ++o)
         {
             FilterRecord fr;
-            std::memcpy(&fr, blob + d.filters + uint64_t(o) * sizeof(FilterRecord), sizeof(fr));
+            if (!read(d.filters + uint64_t(o) * sizeof(FilterRecord), &fr, sizeof(fr))) { error = "blob filter table unreadable"; return ASGPU_E_INVALID; }
             auto mask_ok = [&](const MaskRecord& m) { return m.bits == 0 || inside(m.bits, uint64_t((m.width + 7) / 8) * m.height); };
             bool ok = mask_ok(fr.object_mask) && inside(fr.material_masks, uint64_t(fr.material_mask_count) * sizeof(MaskRecord));
             for (uint32_t k = 0; ok && k < fr.material_mask_count; ++k)
             {
                 MaskRecord m;
-                std::memcpy(&m, blob + fr.material_masks + uint64_t(k) * sizeof(MaskRecord), sizeof(m));
-                ok = mask_ok(m);
+                ok = read(fr.material_masks + uint64_t(k) * sizeof(MaskRecord), &m, sizeof(m)) && mask_ok(m);
             }
             if (!ok) { error = "blob intersection filter out of range"; return ASGPU_E_INVALID; }
         }
     }
     return ASGPU_OK;
+}
+
+int validate_blob(const uint8_t* blob, size_t size, std::string& error)
+{
+    if (!blob) { error = "blob too small"; return ASGPU_E_INVALID; }
+    return validate_blob_tables(
+        [blob, size](uint64_t offset, void* dst, size_t bytes) -> bool
+        {
+            if (offset > size || bytes > size - offset) return false;
+            std::memcpy(dst, blob + offset, bytes);
+            return true;
+        }, size, error);
 }
 
 }   // namespace asgpu

@@ -6,6 +6,7 @@
 #include "../../include/asgpu.h"
 #include "gpu_layout.h"
 
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -23,7 +24,12 @@ int flatten_scene(
     std::vector<uint8_t>&           blob,
     std::string&                    error);
 
-// Structural validation of a blob received from elsewhere (import path).
+// Structural validation of a blob (offsets and counts of every table stay inside it).  The
+// flattener's own output goes through validate_blob; a blob received from elsewhere (the import
+// path, where it lives in device memory) through validate_blob_tables with a reader that copies the
+// header and the small tables to the host.
+typedef std::function<bool(uint64_t offset, void* dst, size_t bytes)> BlobReader;
+int validate_blob_tables(const BlobReader& read, uint64_t size, std::string& error);
 int validate_blob(const uint8_t* blob, size_t size, std::string& error);
 
 }   // namespace asgpu

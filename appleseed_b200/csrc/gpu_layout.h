@@ -28,7 +28,7 @@ namespace asgpu
 {
 
 const uint32_t BlobMagic = 0x42534131u;     // "1ASB"
-const uint32_t BlobVersion = 8;
+const uint32_t BlobVersion = 9;
 const uint32_t WideStackMax = 64;           // deepest traversal stack any wide kernel variant offers
 const uint64_t SectionAlign = 256;
 
@@ -152,16 +152,19 @@ static_assert(sizeof(WSlice) == 48, "WSlice");
 
 // Source geometry of one object instance of an assembly (what ShadingPoint::
 // fetch_triangle_source_geometry reads, shadingpoint.cpp:186-256): object-space vertices, vertex
-// indices, and the rows of ObjectInstance's parent_to_local that Transform::normal_to_parent uses
-// (transform.h:446-463).
+// indices, the vertex poses of a deforming mesh (StaticTriangleTess::get_vertex_pose) and the rows
+// of ObjectInstance's parent_to_local that Transform::normal_to_parent uses (transform.h:446-463).
 struct SrcObject
 {
     double      parent_to_local[9];     // m[0] m[1] m[2] / m[4] m[5] m[6] / m[8] m[9] m[10]
     uint64_t    vertices;               // float[vertex_count * 3]
     uint64_t    triangles;              // uint32_t[triangle_count * 3]
     uint32_t    vertex_count, triangle_count;
+    uint64_t    poses;                  // float[vertex_count * motion_segment_count * 3], [v * msc + m], or 0
+    uint32_t    motion_segment_count;   // 0 = static mesh
+    uint32_t    pad;
 };
-static_assert(sizeof(SrcObject) == 96, "SrcObject");
+static_assert(sizeof(SrcObject) == 112, "SrcObject");
 
 // One assembly-tree item (tree order): world -> instance rows of parent_to_local.
 struct ItemRecord

@@ -29,7 +29,9 @@
 
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdlib>
+#include <mutex>
 
 namespace asgpu
 {
@@ -117,7 +119,9 @@ __global__ void __launch_bounds__(BlockThreads)
 trace_kernel(const KernelArgs args)
 {
     const unsigned lane = threadIdx.x & 31;
-    const unsigned long long n = args.n_dev ? *args.n_dev : args.n;
+    // A device-side count (wavefront queues) is clamped to the capacity of the arrays: producers
+    // keep counting past it when a queue overflows.
+    const unsigned long long n = args.n_dev ? min(*args.n_dev, args.n) : args.n;
     Stats stats; stats.top_nodes = stats.instances = stats.nodes = stats.triangles = 0;
     unsigned rays_done = 0, hits_found = 0;
 
@@ -320,7 +324,7 @@ wide_kernel(const KernelArgs args)
     unsigned long long* queue = sm.queue[tid >> 5];
     const SceneView& s = args.scene;
     const uint8_t* blob = s.blob;
-    const unsigned long long n = args.n_dev ? *args.n_dev : args.n;
+    const unsigned long long n = args.n_dev ? min(*args.n_dev, args.n) : args.n;     // clamped: see trace_kernel
     uint2* stack = &sm.stack[0][tid];
     const uint32_t stride = BlockThreads;
 
@@ -669,7 +673,7 @@ wide_kernel(const KernelArgs args)
 // ASGPU_STEPS / ASGPU_STEPTHR / ASGPU_PREFETCH override them for experiments.
 struct Tuning { int refill, flush, stall, prefetch, steps, step_threshold, enter_late, enter_threshold, enter_min_busy; };
 
-Tuning tuning(const bool single_instance)
+Tuning read_tuning(const bool single_instance)
 {
     Tuning v = { 8, 16, 16, 0, 3, 8, 1, 6, 8 };              // prefetch: measured neutral (C2) to -5 % (C3 probes), off
     if (single_instance) { v.refill = 22; v.flush = 24; v.stall = 24; v.steps = 4; v.enter_late = 0; }
@@ -690,20 +694,51 @@ Tuning tuning(const bool single_instance)
     return v;
 }
 
-// Occupancy-sized persistent launch of one instantiation.
+// The environment is read once (and again after asgpu_reload_tuning()), not once per launch: a C1
+// launch is 44 us of device time and a C5 frame is hundreds of launches.
+std::mutex g_tuning_mutex;
+bool g_tuning_loaded = false;
+Tuning g_tuning[2];
+bool g_lean_allowed = true;
+
+Tuning tuning(const bool single_instance, bool& lean_allowed)
+{
+    std::lock_guard<std::mutex> lock(g_tuning_mutex);
+    if (!g_tuning_loaded)
+    {
+        g_tuning[0] = read_tuning(false);
+        g_tuning[1] = read_tuning(true);
+        g_lean_allowed = getenv("ASGPU_NO_LEAN") == nullptr;
+        g_tuning_loaded = true;
+    }
+    lean_allowed = g_lean_allowed;
+    return g_tuning[single_instance ? 1 : 0];
+}
+
+// Occupancy-sized persistent launch of one instantiation.  The opt-in to large dynamic shared
+// memory and the occupancy query happen once per (instantiation, device), not per launch.
+const int MaxDevices = 64;
+
 template <typename Kernel>
 cudaError_t launch_persistent(Kernel kernel, const KernelArgs& args, const size_t smem, const int sm_count, cudaStream_t stream)
 {
-    cudaError_t err = cudaSuccess;
-    if (smem > 48 * 1024)
-    {
-        err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-        if (err != cudaSuccess) return err;
-    }
-    int blocks_per_sm = 0;
-    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kernel, BlockThreads, smem);
+    static std::atomic<int> cached_blocks[MaxDevices];      // zero-initialised: 0 = not queried yet
+    int device = 0;
+    cudaError_t err = cudaGetDevice(&device);
     if (err != cudaSuccess) return err;
-    if (blocks_per_sm < 1) blocks_per_sm = 1;
+    int blocks_per_sm = device < MaxDevices ? cached_blocks[device].load(std::memory_order_acquire) : 0;
+    if (blocks_per_sm == 0)
+    {
+        if (smem > 48 * 1024)
+        {
+            err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+            if (err != cudaSuccess) return err;
+        }
+        err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kernel, BlockThreads, smem);
+        if (err != cudaSuccess) return err;
+        if (blocks_per_sm < 1) blocks_per_sm = 1;
+        if (device < MaxDevices) cached_blocks[device].store(blocks_per_sm, std::memory_order_release);
+    }
     // Persistent grid: a multiple of the SM count, no larger than the work.
     long long grid = static_cast<long long>(sm_count) * blocks_per_sm;
     const long long needed = static_cast<long long>((args.n + BlockThreads - 1) / BlockThreads);
@@ -740,6 +775,12 @@ cudaError_t launch_wide_depth(const KernelArgs& args, const uint32_t stack_need,
 
 }   // anonymous namespace
 
+void reload_tuning()
+{
+    std::lock_guard<std::mutex> lock(g_tuning_mutex);
+    g_tuning_loaded = false;
+}
+
 int launch_trace(
     const SceneView&    scene,
     const asgpu_rays&   rays,
@@ -771,7 +812,8 @@ int launch_trace(
     args.raw_item = raw_item ? 1u : 0u;
     args.parents = parents;
     args.unit_bits = UnitBits;
-    const Tuning knobs = tuning(scene.item_count <= 1);
+    bool lean_allowed = true;
+    const Tuning knobs = tuning(scene.item_count <= 1, lean_allowed);
     args.refill_threshold = knobs.refill;
     args.flush_threshold = knobs.flush;
     args.stall_threshold = knobs.stall;
@@ -789,7 +831,7 @@ int launch_trace(
     if (wide)
     {
         const bool extras = scene.has_filters || scene.has_animated;
-        const bool lean = scene.item_count <= 1 && !scene.has_motion && !extras && getenv("ASGPU_NO_LEAN") == nullptr;
+        const bool lean = scene.item_count <= 1 && !scene.has_motion && !extras && lean_allowed;
         if (lean) err = launch_wide_depth<true, false>(args, scene.wide_stack_need, any_hit, count, sm_count, stream);
         else if (extras) err = launch_wide_depth<false, true>(args, scene.wide_stack_need, any_hit, count, sm_count, stream);
         else err = launch_wide_depth<false, false>(args, scene.wide_stack_need, any_hit, count, sm_count, stream);

@@ -28,6 +28,9 @@ int launch_trace(
     bool                raw_item = false,       // hit records carry the ItemRecord index instead of the caller's instance id
     const asgpu_parent* parents = nullptr);     // device: optional parent shading point per ray
 
+// Forgets the cached ASGPU_* scheduling knobs: the next launch reads the environment again.
+void reload_tuning();
+
 // ShadingPoint::refine_and_offset for n hits (refine.cu).  `raw_item`: hits carry ItemRecord
 // indices (wavefront launches); the parents written always carry the caller's instance id.
 int launch_refine_offset(
@@ -40,6 +43,19 @@ int launch_refine_offset(
     const uint32_t*     id_to_item,     // device: caller's instance id -> ItemRecord index (unused for raw hits)
     uint32_t            id_count,
     asgpu_parent*       parents,
+    int                 sm_count,
+    void*               stream);
+
+// ShadingPoint::m_triangle_support_plane for n hits (refine.cu): 9 doubles per hit.
+int launch_support_planes(
+    const SceneView&    scene,
+    const asgpu_rays&   rays,           // only time_normalized is read
+    const asgpu_hit*    hits,
+    size_t              n,
+    bool                raw_item,
+    const uint32_t*     id_to_item,
+    uint32_t            id_count,
+    double*             planes,
     int                 sm_count,
     void*               stream);
 

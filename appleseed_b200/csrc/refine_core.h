@@ -12,7 +12,11 @@
 //                                                       raytrianglemt.h:300-309)
 //   n   = faceforward(object_instance.normal_to_parent(cross(v1 - v0, v2 - v0)), dir)
 //                                                       source vertices, float cross product
-//                                                       (renderer/utility/triangle.h:57-64)
+//                                                       (renderer/utility/triangle.h:57-64); for a
+//                                                       deforming mesh the vertices interpolated between
+//                                                       the two poses around the ray time
+//                                                       (fetch_triangle_source_geometry,
+//                                                       shadingpoint.cpp:186-256)
 //   front / back = adaptive_offset(org, normalize(n))   ulp steps of doubling size until the point
 //                                                       is off the plane (refining.h:168-221)
 //
@@ -75,11 +79,46 @@ ASGPU_HD void offset_point(const TriD& tri, const double p[3], const double n[3]
     }
 }
 
+// Source vertices of triangle `primitive` of one object instance (object space, float):
+// fetch_triangle_source_geometry, shadingpoint.cpp:186-256.  Static mesh: m_vertices.  Deforming
+// mesh: base_time = time_normalized * motion_segment_count (a FLOAT product: float x size_t),
+// previous pose = m_vertices for base_index 0 else pose base_index - 1, next pose = pose base_index,
+// v = previous * (1 - frac) + next * frac in float, two roundings per term.
+ASGPU_HD void source_vertices(const uint8_t* blob, const uint8_t* so, const uint32_t primitive, const float time_normalized, float v[3][3])
+{
+    const uint2 ov = load8(so + offsetof(SrcObject, vertices)), ot = load8(so + offsetof(SrcObject, triangles));
+    const uint8_t* verts = blob + (static_cast<uint64_t>(ov.x) | (static_cast<uint64_t>(ov.y) << 32));
+    const uint8_t* tris = blob + (static_cast<uint64_t>(ot.x) | (static_cast<uint64_t>(ot.y) << 32)) + static_cast<uint64_t>(primitive) * 12;
+    const uint32_t idx[3] = { load4(tris), load4(tris + 4), load4(tris + 8) };
+    const uint32_t msc = load4(so + offsetof(SrcObject, motion_segment_count));
+    if (msc == 0)
+    {
+        for (int c = 0; c < 3; ++c)
+            for (int k = 0; k < 3; ++k) v[c][k] = u2f(load4(verts + static_cast<uint64_t>(idx[c]) * 12 + k * 4));
+        return;
+    }
+    const uint2 op = load8(so + offsetof(SrcObject, poses));
+    const uint8_t* poses = blob + (static_cast<uint64_t>(op.x) | (static_cast<uint64_t>(op.y) << 32));
+    const double base_time = static_cast<double>(fmul(time_normalized, static_cast<float>(msc)));
+    const uint32_t base_index = static_cast<uint32_t>(base_time);
+    const float frac = static_cast<float>(dsub(base_time, static_cast<double>(base_index)));
+    const float omf = fsub(1.0f, frac);
+    for (int c = 0; c < 3; ++c)
+    {
+        const uint8_t* prev = base_index == 0 ? verts + static_cast<uint64_t>(idx[c]) * 12
+                                              : poses + (static_cast<uint64_t>(idx[c]) * msc + (base_index - 1)) * 12;
+        const uint8_t* next = poses + (static_cast<uint64_t>(idx[c]) * msc + base_index) * 12;
+        for (int k = 0; k < 3; ++k)
+            v[c][k] = fadd(fmul(u2f(load4(prev + k * 4)), omf), fmul(u2f(load4(next + k * 4)), frac));
+    }
+}
+
 // One hit.  `item` = ItemRecord index of the hit's assembly instance; `time_absolute` = the ray's
-// absolute time (read by animated instances only); writes the 80-byte asgpu_parent record (id, pad,
-// front, back, geo_normal) as ten 8-byte words.
-ASGPU_HD void refine_offset_one(const SceneView& s, const double world_org[3], const double world_dir[3], const float time_absolute, const double t,
-                                const uint32_t item, const uint32_t object_instance, const uint32_t primitive, const uint32_t slot, double* dst)
+// absolute time (read by animated instances only), `time_normalized` its normalized time (read for
+// moving triangles only); writes the 80-byte asgpu_parent record (id, pad, front, back, geo_normal)
+// as ten 8-byte words.
+ASGPU_HD void refine_offset_one(const SceneView& s, const double world_org[3], const double world_dir[3], const float time_absolute, const float time_normalized,
+                                const double t, const uint32_t item, const uint32_t object_instance, const uint32_t primitive, const uint32_t slot, double* dst)
 {
     // refine_space_ray = to_local(ray), moved to the hit point.
     const uint8_t* ip = s.blob + s.items + static_cast<uint64_t>(item) * sizeof(ItemRecord);
@@ -88,16 +127,10 @@ ASGPU_HD void refine_offset_one(const SceneView& s, const double world_org[3], c
     instance_org_dir_at(s.blob, ip, meta.w, time_absolute, world_org, world_dir, p, dir);
     for (int k = 0; k < 3; ++k) p[k] = dadd(p[k], dmul(dir[k], t));
 
-    // Support plane = the triangle the leaf stores, widened to double.
+    // Support plane = the hit triangle (stored, or interpolated at the ray time), widened to double.
     TreeDesc td; load_tree_desc(s, meta.x, td);
     TriD tri;
-    {
-        const uint8_t* rec = s.blob + td.tris + static_cast<uint64_t>(slot) * sizeof(TriRecord);
-        const uint4 a = load16(rec), b = load16(rec + 16), c = load16(rec + 32);
-        tri.v0[0] = u2f(a.x); tri.v0[1] = u2f(a.y); tri.v0[2] = u2f(a.z);
-        tri.e0[0] = u2f(a.w); tri.e0[1] = u2f(b.x); tri.e0[2] = u2f(b.y);
-        tri.e1[0] = u2f(b.z); tri.e1[1] = u2f(b.w); tri.e1[2] = u2f(c.x);
-    }
+    hit_triangle(s.blob + td.tris + static_cast<uint64_t>(slot) * sizeof(TriRecord), s.blob + td.poses, time_normalized, tri);
     for (int step = 0; step < 2; ++step)
     {
         const double tt = plane_intersect(tri, p, dir);
@@ -108,13 +141,8 @@ ASGPU_HD void refine_offset_one(const SceneView& s, const double world_org[3], c
     double nrm[3];
     {
         const uint8_t* so = s.blob + td.src_objects + static_cast<uint64_t>(object_instance) * sizeof(SrcObject);
-        const uint2 ov = load8(so + offsetof(SrcObject, vertices)), ot = load8(so + offsetof(SrcObject, triangles));
-        const uint8_t* verts = s.blob + (static_cast<uint64_t>(ov.x) | (static_cast<uint64_t>(ov.y) << 32));
-        const uint8_t* tris = s.blob + (static_cast<uint64_t>(ot.x) | (static_cast<uint64_t>(ot.y) << 32)) + static_cast<uint64_t>(primitive) * 12;
-        const uint32_t idx[3] = { load4(tris), load4(tris + 4), load4(tris + 8) };
         float v[3][3];
-        for (int c = 0; c < 3; ++c)
-            for (int k = 0; k < 3; ++k) v[c][k] = u2f(load4(verts + static_cast<uint64_t>(idx[c]) * 12 + k * 4));
+        source_vertices(s.blob, so, primitive, time_normalized, v);
         const float a[3] = { fsub(v[1][0], v[0][0]), fsub(v[1][1], v[0][1]), fsub(v[1][2], v[0][2]) };
         const float b[3] = { fsub(v[2][0], v[0][0]), fsub(v[2][1], v[0][1]), fsub(v[2][2], v[0][2]) };
         const double nf[3] = {

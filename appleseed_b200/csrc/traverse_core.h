@@ -471,6 +471,20 @@ ASGPU_HD bool fetch_triangle(const uint8_t* record, const uint8_t* poses, const 
     return true;
 }
 
+// The triangle the closest-hit visitor leaves behind for a hit (m_hit_triangle, triangletree.cpp:
+// 1413, 1468-1469): the leaf's stored triangle, or for a moving triangle the one interpolated at
+// the ray's normalized time (m_interpolated_triangle, a member: triangletree.h:232), widened to
+// double by TriangleReader.  read_hit_triangle_data (:1483-1499) initialises the ShadingPoint's
+// support plane from it.  `record` = the slot's TriRecord of the EXACT layout.
+ASGPU_HD void hit_triangle(const uint8_t* record, const uint8_t* poses, const float time_normalized, TriD& tri)
+{
+    Ray r;
+    r.flags = 0xFFFFFFFFu;
+    r.time_normalized = time_normalized;
+    uint32_t slot, segment;
+    fetch_triangle<false>(record, poses, r, tri, slot, segment);
+}
+
 // ------------------------------------------------------------------------------------------
 // IntersectionFilter::accept (intersectionfilter.h:169-205) with AlphaMask::is_opaque (:103-112):
 // float arithmetic in the reference's order (Vector2f * float, sums left to right, clamp, truncate).

@@ -1005,7 +1005,7 @@ bool build_host_trees(const asgpu_scene_desc& desc, int threads, HostTrees& out,
         HostTriangleTree& tree = *out.triangle_trees.back();
 
         // Source geometry (for the device-side refine_and_offset): private copies of the meshes.
-        if (out.mesh_vertices.empty()) { out.mesh_vertices.resize(desc.mesh_count); out.mesh_triangles.resize(desc.mesh_count); }
+        if (out.mesh_vertices.empty()) { out.mesh_vertices.resize(desc.mesh_count); out.mesh_triangles.resize(desc.mesh_count); out.mesh_poses.resize(desc.mesh_count); }
         tree.source_objects.resize(assembly.object_instance_count);
         for (uint32_t o = 0; o < assembly.object_instance_count; ++o)
         {
@@ -1015,10 +1015,15 @@ bool build_host_trees(const asgpu_scene_desc& desc, int threads, HostTrees& out,
             std::vector<uint32_t>& mt = out.mesh_triangles[oi.mesh_index];
             if (mv.empty() && mesh.vertex_count) mv.assign(mesh.vertices, mesh.vertices + size_t(mesh.vertex_count) * 3);
             if (mt.empty() && mesh.triangle_count) mt.assign(mesh.triangles, mesh.triangles + size_t(mesh.triangle_count) * 3);
+            std::vector<float>& mp = out.mesh_poses[oi.mesh_index];
+            const bool deforming = mesh.motion_segment_count != 0 && mesh.vertex_poses != nullptr && mesh.vertex_count != 0;
+            if (mp.empty() && deforming) mp.assign(mesh.vertex_poses, mesh.vertex_poses + size_t(mesh.vertex_count) * mesh.motion_segment_count * 3);
             asgpu_source_object& so = tree.source_objects[o];
             std::memset(&so, 0, sizeof(so));
             so.vertices = mv.data();
             so.triangles = mt.data();
+            so.vertex_poses = deforming ? mp.data() : nullptr;
+            so.motion_segment_count = deforming ? mesh.motion_segment_count : 0;
             so.vertex_count = mesh.vertex_count;
             so.triangle_count = mesh.triangle_count;
             so.triangle_stride = 12;

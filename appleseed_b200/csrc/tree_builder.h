@@ -62,7 +62,8 @@ struct HostTrees
     std::vector<std::unique_ptr<HostTriangleTree>>  triangle_trees;
     std::vector<int>                                assembly_to_tree;   // -1 = assembly without geometry
     HostAssemblyTree                                assembly_tree;
-    std::vector<std::vector<float>>                 mesh_vertices;      // copies of the static meshes (source geometry)
+    std::vector<std::vector<float>>                 mesh_vertices;      // copies of the meshes (source geometry)
+    std::vector<std::vector<float>>                 mesh_poses;         // ... and of the vertex poses of deforming meshes
     std::vector<std::vector<uint32_t>>              mesh_triangles;
     double                                          build_seconds = 0.0;
     double                                          topology_seconds = 0.0;    // inside the LbvhTopologyFn calls (device build only)

@@ -37,6 +37,7 @@
 #include <cfloat>
 #include <cstring>
 #include <new>
+#include <utility>
 #include <vector>
 
 using namespace asgpu;
@@ -53,6 +54,8 @@ struct asgpu_ray_queue
     double*             dir = nullptr;
     double*             tmin = nullptr;
     double*             tmax = nullptr;
+    float*              time_absolute = nullptr;    // ShadingRay::Time of every ray (shadingray.h:68-85)
+    float*              time_normalized = nullptr;
     uint32_t*           flags = nullptr;
     uint32_t*           path = nullptr;
     unsigned long long* count = nullptr;
@@ -69,6 +72,8 @@ struct QueueView
     double*             dir;
     double*             tmin;
     double*             tmax;
+    float*              time_absolute;
+    float*              time_normalized;
     uint32_t*           flags;
     uint32_t*           path;
     unsigned long long* count;
@@ -79,6 +84,7 @@ QueueView view_of(const asgpu_ray_queue* q)
 {
     QueueView v;
     v.org = q->org; v.dir = q->dir; v.tmin = q->tmin; v.tmax = q->tmax;
+    v.time_absolute = q->time_absolute; v.time_normalized = q->time_normalized;
     v.flags = q->flags; v.path = q->path; v.count = q->count; v.capacity = q->capacity; v.parents = q->parents;
     return v;
 }
@@ -87,7 +93,7 @@ asgpu_rays rays_of(const asgpu_ray_queue* q)
 {
     asgpu_rays r;
     r.org = q->org; r.dir = q->dir; r.tmin = q->tmin; r.tmax = q->tmax;
-    r.time_absolute = nullptr; r.time_normalized = nullptr; r.flags = q->flags;
+    r.time_absolute = q->time_absolute; r.time_normalized = q->time_normalized; r.flags = q->flags;
     return r;
 }
 
@@ -99,6 +105,7 @@ struct StreamParams
     double      film_w, film_h, focal;
     double      lights[8][3];
     double      eps;
+    float       shutter_open, shutter_close;
 };
 
 enum { StatCamera = 0, StatBounce, StatProbe, StatHits, StatEscaped, StatUnoccluded, StatCount };
@@ -142,8 +149,11 @@ __device__ __forceinline__ unsigned long long enqueue_slot(const QueueView& q, c
 }
 
 __device__ __forceinline__ void write_ray(const QueueView& q, const unsigned long long slot, const double o[3], const double d[3],
-                                          const double tmin, const double tmax, const uint32_t flags, const uint32_t path)
+                                          const double tmin, const double tmax, const float time_absolute, const float time_normalized,
+                                          const uint32_t flags, const uint32_t path)
 {
+    q.time_absolute[slot] = time_absolute;
+    q.time_normalized[slot] = time_normalized;
     q.org[slot * 3] = o[0]; q.org[slot * 3 + 1] = o[1]; q.org[slot * 3 + 2] = o[2];
     q.dir[slot * 3] = d[0]; q.dir[slot * 3 + 1] = d[1]; q.dir[slot * 3 + 2] = d[2];
     q.tmin[slot] = tmin;
@@ -202,6 +212,7 @@ generate_kernel(const StreamParams p, const uint32_t* __restrict__ tiles, const 
     {
         bool emit = false;
         uint32_t path = 0;
+        float time_absolute = 0.0f, time_normalized = 0.0f;
         double o[3] = { 0.0, 0.0, 0.0 }, d[3] = { 0.0, 0.0, 0.0 };
         if (i < total)
         {
@@ -224,12 +235,19 @@ generate_kernel(const StreamParams p, const uint32_t* __restrict__ tiles, const 
                     o[k] = p.cam[k * 4 + 3];
                 }
                 normalize3(d);
+                if (p.shutter_open != p.shutter_close)
+                {
+                    // One time sample per camera path: a float in [0, 1) (24 random bits), then
+                    // ShadingRay::Time::create_with_normalized_time (shadingray.h:230-239).
+                    time_normalized = static_cast<float>(static_cast<uint32_t>(rng(p.seed, path, 0, 3) * 16777216.0)) * (1.0f / 16777216.0f);
+                    time_absolute = __fadd_rn(__fmul_rn(__fsub_rn(1.0f, time_normalized), p.shutter_open), __fmul_rn(time_normalized, p.shutter_close));
+                }
             }
         }
         const unsigned long long slot = enqueue_slot(out, emit);
         if (slot != ~0ull)
         {
-            write_ray(out, slot, o, d, 0.0, DBL_MAX, ASGPU_VIS_CAMERA, path);
+            write_ray(out, slot, o, d, 0.0, DBL_MAX, time_absolute, time_normalized, ASGPU_VIS_CAMERA, path);
             write_parent(out, slot, nullptr);
             ++local[StatCamera];
         }
@@ -257,10 +275,13 @@ shade_kernel(const StreamParams p, const SceneView s, const QueueView in, const 
     {
         bool vertex = false;
         uint32_t path = 0, pixel = 0, identity = 0;
+        float time_absolute = 0.0f, time_normalized = 0.0f;     // child rays inherit their path's time (pathtracer.h:764)
         double o[3] = { 0.0, 0.0, 0.0 }, nrm[3] = { 0.0, 1.0, 0.0 };
         if (i < n)
         {
             path = in.path[i];
+            time_absolute = in.time_absolute[i];
+            time_normalized = in.time_normalized[i];
             pixel = path / p.spp;
             const unsigned long long* hw = reinterpret_cast<const unsigned long long*>(hits + i);
             const unsigned long long w0 = hw[0], w2 = hw[2], w3 = hw[3], w4 = hw[4];
@@ -278,14 +299,24 @@ shade_kernel(const StreamParams p, const SceneView s, const QueueView in, const 
                 const uint8_t* ip = s.blob + s.items + static_cast<uint64_t>(item) * sizeof(ItemRecord);
                 const uint4 meta = load16(ip + 96);
                 const uint8_t* tp = s.blob + s.trees + static_cast<uint64_t>(meta.x) * sizeof(TreeDesc);
-                const uint2 o_tris = load8(tp + offsetof(TreeDesc, tris));
-                const uint8_t* rec = s.blob + (static_cast<uint64_t>(o_tris.x) | (static_cast<uint64_t>(o_tris.y) << 32)) + static_cast<uint64_t>(slot) * sizeof(TriRecord);
-                const uint4 a = load16(rec), b = load16(rec + 16), c = load16(rec + 32);
-                const double e0[3] = { u2f(a.w), u2f(b.x), u2f(b.y) }, e1[3] = { u2f(b.z), u2f(b.w), u2f(c.x) };
+                // The hit triangle: the leaf's, or for a moving triangle the one interpolated at the ray time.
+                TriD tri;
+                hit_triangle(s.blob + load_u64(tp + offsetof(TreeDesc, tris)) + static_cast<uint64_t>(slot) * sizeof(TriRecord),
+                             s.blob + load_u64(tp + offsetof(TreeDesc, poses)), time_normalized, tri);
+                const double* e0 = tri.e0;
+                const double* e1 = tri.e1;
                 const double nl[3] = { e0[1] * e1[2] - e0[2] * e1[1], e0[2] * e1[0] - e0[0] * e1[2], e0[0] * e1[1] - e0[1] * e1[0] };
+                // normal_to_parent = transpose of parent_to_local; an animated instance: its transform at the ray time.
+                double m[12];
+                if (meta.w >= 2) animated_item_matrix(s.blob, ip, meta.w, time_absolute, m);
+                else
+                {
+                    #pragma unroll
+                    for (int k = 0; k < 12; ++k) m[k] = load_f64(ip + k * 8);
+                }
                 #pragma unroll
                 for (int k = 0; k < 3; ++k)
-                    nrm[k] = load_f64(ip + k * 8) * nl[0] + load_f64(ip + (4 + k) * 8) * nl[1] + load_f64(ip + (8 + k) * 8) * nl[2];
+                    nrm[k] = m[k] * nl[0] + m[4 + k] * nl[1] + m[8 + k] * nl[2];
                 normalize3(nrm);
                 if (nrm[0] * dir[0] + nrm[1] * dir[1] + nrm[2] * dir[2] > 0.0) { nrm[0] = -nrm[0]; nrm[1] = -nrm[1]; nrm[2] = -nrm[2]; }
                 // Next origin: the hit point itself when the child rays carry the refined parent record,
@@ -337,7 +368,7 @@ shade_kernel(const StreamParams p, const SceneView s, const QueueView in, const 
             const unsigned long long slot = enqueue_slot(probes, vertex);
             if (slot != ~0ull)
             {
-                write_ray(probes, slot, o, d, 0.0, tmax, ASGPU_VIS_SHADOW, path);
+                write_ray(probes, slot, o, d, 0.0, tmax, time_absolute, time_normalized, ASGPU_VIS_SHADOW, path);
                 write_parent(probes, slot, refined ? refined + i : nullptr);
                 ++local[StatProbe];
             }
@@ -369,7 +400,7 @@ shade_kernel(const StreamParams p, const SceneView s, const QueueView in, const 
             const unsigned long long slot = enqueue_slot(next, vertex);
             if (slot != ~0ull)
             {
-                write_ray(next, slot, o, d, 0.0, DBL_MAX, ASGPU_VIS_DIFFUSE, path);
+                write_ray(next, slot, o, d, 0.0, DBL_MAX, time_absolute, time_normalized, ASGPU_VIS_DIFFUSE, path);
                 write_parent(next, slot, refined ? refined + i : nullptr);
                 ++local[StatBounce];
             }
@@ -415,6 +446,7 @@ struct Captured
     int                     kind = 0;
     uint32_t                depth = 0;
     std::vector<double>     org, dir, tmin, tmax;
+    std::vector<float>      time_absolute, time_normalized;
     std::vector<uint32_t>   flags, path;
     std::vector<uint8_t>    results;
     std::vector<asgpu_parent> parents;
@@ -446,12 +478,51 @@ struct asgpu_path_stream
     bool                    capture_armed = false;
     size_t                  capture_budget = 0;
     std::vector<Captured>   captured;
+    // Optional per-launch timing (asgpu_path_stream_set_profiling): event pairs recorded on the
+    // launch stream around every kernel, by kind: 0 closest-hit trace, 1 probe trace, 2 refine, 3 stage.
+    bool                    profiling = false;
+    std::vector<cudaEvent_t> event_pool;
+    size_t                  events_used = 0;
+    std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> timed;
 };
 
 namespace
 {
 
 int stage_grid(const asgpu_scene* scene) { return scene->sm_count * 8; }
+
+// Event pair around one launch when profiling is on (kind: 0 closest-hit trace, 1 probe trace,
+// 2 refine, 3 generate / shade / accumulate).  Events are pooled: no allocation in steady state.
+cudaEvent_t next_event(asgpu_path_stream* ps)
+{
+    if (ps->events_used == ps->event_pool.size())
+    {
+        cudaEvent_t e = nullptr;
+        if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+        ps->event_pool.push_back(e);
+    }
+    return ps->event_pool[ps->events_used++];
+}
+
+struct TimedLaunch
+{
+    asgpu_path_stream*  ps;
+    cudaStream_t        stream;
+    int                 kind;
+    cudaEvent_t         start = nullptr;
+    TimedLaunch(asgpu_path_stream* ps_, const int kind_, cudaStream_t stream_) : ps(ps_), stream(stream_), kind(kind_)
+    {
+        if (ps->profiling && (start = next_event(ps)) != nullptr) cudaEventRecord(start, stream);
+    }
+    ~TimedLaunch()
+    {
+        if (start == nullptr) return;
+        cudaEvent_t stop = next_event(ps);
+        if (stop == nullptr) return;
+        cudaEventRecord(stop, stream);
+        ps->timed.push_back(std::make_pair(kind, std::make_pair(start, stop)));
+    }
+};
 
 int capture_wavefront(asgpu_path_stream* ps, const asgpu_ray_queue* q, const int kind, const uint32_t depth, cudaStream_t stream)
 {
@@ -465,6 +536,7 @@ int capture_wavefront(asgpu_path_stream* ps, const asgpu_ray_queue* q, const int
     Captured& c = ps->captured.back();
     c.kind = kind; c.depth = depth;
     c.org.resize(n * 3); c.dir.resize(n * 3); c.tmin.resize(n); c.tmax.resize(n); c.flags.resize(n); c.path.resize(n);
+    c.time_absolute.resize(n); c.time_normalized.resize(n);
     c.results.resize(n * (kind == 0 ? sizeof(asgpu_hit) : 1));
     c.parents.clear();
     if (n == 0) return ASGPU_OK;
@@ -472,6 +544,8 @@ int capture_wavefront(asgpu_path_stream* ps, const asgpu_ray_queue* q, const int
     ASGPU_CUDA(cudaMemcpy(c.dir.data(), q->dir, n * 24, cudaMemcpyDeviceToHost), "capture");
     ASGPU_CUDA(cudaMemcpy(c.tmin.data(), q->tmin, n * 8, cudaMemcpyDeviceToHost), "capture");
     ASGPU_CUDA(cudaMemcpy(c.tmax.data(), q->tmax, n * 8, cudaMemcpyDeviceToHost), "capture");
+    ASGPU_CUDA(cudaMemcpy(c.time_absolute.data(), q->time_absolute, n * 4, cudaMemcpyDeviceToHost), "capture");
+    ASGPU_CUDA(cudaMemcpy(c.time_normalized.data(), q->time_normalized, n * 4, cudaMemcpyDeviceToHost), "capture");
     ASGPU_CUDA(cudaMemcpy(c.flags.data(), q->flags, n * 4, cudaMemcpyDeviceToHost), "capture");
     ASGPU_CUDA(cudaMemcpy(c.path.data(), q->path, n * 4, cudaMemcpyDeviceToHost), "capture");
     c.parents.resize(n);
@@ -493,6 +567,7 @@ int trace_queue(asgpu_scene* scene, asgpu_ray_queue* q, asgpu_hit* hits, uint8_t
                 unsigned long long* cursor, const bool raw_item, void* stream)
 {
     const bool wide = (flags & ASGPU_TRACE_EXACT) == 0;
+    if (flags & ASGPU_TRACE_SORT) return fail(ASGPU_E_UNSUPPORTED, "ASGPU_TRACE_SORT needs the ray count on the host: not available for queues");
     if (wide && !(scene->header.flags & ASGPU_SCENE_WIDE)) return fail(ASGPU_E_INVALID, "scene was created without the wide layout");
     if (!wide && !(scene->header.flags & ASGPU_SCENE_EXACT)) return fail(ASGPU_E_INVALID, "scene was created without the exact layout");
     const asgpu_rays rays = rays_of(q);
@@ -524,6 +599,8 @@ asgpu_ray_queue* asgpu_queue_create(asgpu_scene* scene, size_t capacity)
     if (e == cudaSuccess) e = cudaMalloc(&q->dir, capacity * 24);
     if (e == cudaSuccess) e = cudaMalloc(&q->tmin, capacity * 8);
     if (e == cudaSuccess) e = cudaMalloc(&q->tmax, capacity * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&q->time_absolute, capacity * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&q->time_normalized, capacity * 4);
     if (e == cudaSuccess) e = cudaMalloc(&q->flags, capacity * 4);
     if (e == cudaSuccess) e = cudaMalloc(&q->path, capacity * 4);
     if (e == cudaSuccess) e = cudaMalloc(&q->count, 8);
@@ -537,6 +614,7 @@ void asgpu_queue_destroy(asgpu_ray_queue* q)
     if (!q) return;
     cudaSetDevice(q->scene->device);
     cudaFree(q->org); cudaFree(q->dir); cudaFree(q->tmin); cudaFree(q->tmax);
+    cudaFree(q->time_absolute); cudaFree(q->time_normalized);
     cudaFree(q->flags); cudaFree(q->path); cudaFree(q->count); cudaFree(q->parents);
     delete q;
 }
@@ -576,7 +654,6 @@ int asgpu_queue_push_host(asgpu_ray_queue* q, const asgpu_rays* rays, const uint
     if (!q) return fail(ASGPU_E_INVALID, "null queue");
     if (n == 0) return ASGPU_OK;
     if (!rays || !rays->org || !rays->dir || !rays->tmin || !rays->tmax) return fail(ASGPU_E_INVALID, "ray batch misses a mandatory array");
-    if (rays->time_absolute || rays->time_normalized) return fail(ASGPU_E_UNSUPPORTED, "queues carry no ray time (static scenes)");
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     uint64_t have = 0;
     const int rc = asgpu_queue_count(q, stream_, &have);
@@ -586,6 +663,10 @@ int asgpu_queue_push_host(asgpu_ray_queue* q, const asgpu_rays* rays, const uint
     ASGPU_CUDA(cudaMemcpyAsync(q->dir + have * 3, rays->dir, n * 24, cudaMemcpyHostToDevice, stream), "H2D dir");
     ASGPU_CUDA(cudaMemcpyAsync(q->tmin + have, rays->tmin, n * 8, cudaMemcpyHostToDevice, stream), "H2D tmin");
     ASGPU_CUDA(cudaMemcpyAsync(q->tmax + have, rays->tmax, n * 8, cudaMemcpyHostToDevice, stream), "H2D tmax");
+    if (rays->time_absolute) ASGPU_CUDA(cudaMemcpyAsync(q->time_absolute + have, rays->time_absolute, n * 4, cudaMemcpyHostToDevice, stream), "H2D time");
+    else ASGPU_CUDA(cudaMemsetAsync(q->time_absolute + have, 0, n * 4, stream), "time");
+    if (rays->time_normalized) ASGPU_CUDA(cudaMemcpyAsync(q->time_normalized + have, rays->time_normalized, n * 4, cudaMemcpyHostToDevice, stream), "H2D time");
+    else ASGPU_CUDA(cudaMemsetAsync(q->time_normalized + have, 0, n * 4, stream), "time");
     if (rays->flags) ASGPU_CUDA(cudaMemcpyAsync(q->flags + have, rays->flags, n * 4, cudaMemcpyHostToDevice, stream), "H2D flags");
     else ASGPU_CUDA(cudaMemsetAsync(q->flags + have, 0xFF, n * 4, stream), "flags");
     if (path_ids) ASGPU_CUDA(cudaMemcpyAsync(q->path + have, path_ids, n * 4, cudaMemcpyHostToDevice, stream), "H2D path ids");
@@ -618,8 +699,7 @@ asgpu_path_stream* asgpu_path_stream_create(asgpu_scene* scene, const asgpu_path
     if (desc->light_count == 0 || desc->light_count > 8) { fail(ASGPU_E_INVALID, "light_count must be 1..8"); return nullptr; }
     if (desc->max_bounces > 200) { fail(ASGPU_E_INVALID, "max_bounces above 200"); return nullptr; }
     if (static_cast<uint64_t>(desc->width) * desc->height * desc->spp > 0xFFFFFFFFull) { fail(ASGPU_E_UNSUPPORTED, "more than 2^32 - 1 paths per frame"); return nullptr; }
-    if (scene->header.moving_triangle_count != 0) { fail(ASGPU_E_UNSUPPORTED, "the path stream handles static triangles only"); return nullptr; }
-    if (scene->header.flags & BlobHasAnimatedInstances) { fail(ASGPU_E_UNSUPPORTED, "the path stream handles static assembly instances only"); return nullptr; }
+    if (!(desc->shutter_open <= desc->shutter_close)) { fail(ASGPU_E_INVALID, "shutter_open must not exceed shutter_close"); return nullptr; }
     if (!(scene->header.flags & ASGPU_SCENE_EXACT)) { fail(ASGPU_E_INVALID, "the path stream needs the per-slot triangle records of the exact layout"); return nullptr; }
     const bool with_parents = (desc->stream_flags & ASGPU_STREAM_PARENTS) != 0;
     if (with_parents && !scene->has_source) { fail(ASGPU_E_INVALID, "ASGPU_STREAM_PARENTS needs a scene with source geometry (asgpu_scene_create_ex)"); return nullptr; }
@@ -643,6 +723,7 @@ asgpu_path_stream* asgpu_path_stream_create(asgpu_scene* scene, const asgpu_path
     p.film_w = desc->film_width; p.film_h = desc->film_height; p.focal = desc->focal_length;
     std::memcpy(p.lights, desc->lights, sizeof(p.lights));
     p.eps = desc->offset_eps;
+    p.shutter_open = desc->shutter_open; p.shutter_close = desc->shutter_close;
 
     cudaSetDevice(scene->device);
     ps->qa = asgpu_queue_create(scene, capacity);
@@ -686,6 +767,7 @@ void asgpu_path_stream_destroy(asgpu_path_stream* ps)
     asgpu_queue_destroy(ps->qa); asgpu_queue_destroy(ps->qb); asgpu_queue_destroy(ps->qp);
     cudaFree(ps->hits); cudaFree(ps->refined); cudaFree(ps->occluded); cudaFree(ps->image); cudaFree(ps->tiles_dev);
     cudaFree(ps->stats_dev); cudaFree(ps->cursors);
+    for (cudaEvent_t e : ps->event_pool) cudaEventDestroy(e);
     delete ps;
 }
 
@@ -717,12 +799,19 @@ int asgpu_path_stream_render(asgpu_path_stream* ps, const uint32_t* tiles, size_
         asgpu_ray_queue* qa = ps->qa;
         asgpu_ray_queue* qb = ps->qb;
         ASGPU_CUDA(cudaMemsetAsync(qa->count, 0, 8, stream), "cudaMemsetAsync");
-        generate_kernel<<<grid, StageThreads, 0, stream>>>(ps->params, ps->tiles_dev + begin, count, view_of(qa), ps->stats_dev);
+        {
+            TimedLaunch timed(ps, 3, stream);
+            generate_kernel<<<grid, StageThreads, 0, stream>>>(ps->params, ps->tiles_dev + begin, count, view_of(qa), ps->stats_dev);
+        }
         ASGPU_CUDA(cudaGetLastError(), "generate_kernel");
         ++ps->launches;
         for (uint32_t depth = 0; depth <= ps->desc.max_bounces; ++depth)
         {
-            int rc = trace_queue(scene, qa, ps->hits, nullptr, false, flags, ps->cursors + (ps->cursor_next++ % QueueRing), true, stream);
+            int rc;
+            {
+                TimedLaunch timed(ps, 0, stream);
+                rc = trace_queue(scene, qa, ps->hits, nullptr, false, flags, ps->cursors + (ps->cursor_next++ % QueueRing), true, stream);
+            }
             if (rc != ASGPU_OK) return rc;
             ++ps->launches; ++ps->wavefronts;
             if (ps->capture_armed && (rc = capture_wavefront(ps, qa, 0, depth, stream)) != ASGPU_OK) return rc;
@@ -730,18 +819,28 @@ int asgpu_path_stream_render(asgpu_path_stream* ps, const uint32_t* tiles, size_
             ASGPU_CUDA(cudaMemsetAsync(ps->qp->count, 0, 8, stream), "cudaMemsetAsync");
             if (ps->refined)
             {
+                TimedLaunch timed(ps, 2, stream);
                 const int er = launch_refine_offset(scene->view, rays_of(qa), ps->hits, qa->capacity, qa->count, true, nullptr, 0, ps->refined, scene->sm_count, stream);
                 if (er != 0) return fail_cuda(static_cast<cudaError_t>(er), "refine_offset_kernel");
                 ++ps->launches;
             }
-            shade_kernel<<<grid, StageThreads, 0, stream>>>(ps->params, scene->view, view_of(qa), ps->hits, ps->refined, vp, view_of(qb), depth, ps->image, ps->stats_dev);
+            {
+                TimedLaunch timed(ps, 3, stream);
+                shade_kernel<<<grid, StageThreads, 0, stream>>>(ps->params, scene->view, view_of(qa), ps->hits, ps->refined, vp, view_of(qb), depth, ps->image, ps->stats_dev);
+            }
             ASGPU_CUDA(cudaGetLastError(), "shade_kernel");
             ++ps->launches;
-            rc = trace_queue(scene, ps->qp, nullptr, ps->occluded, true, flags, ps->cursors + (ps->cursor_next++ % QueueRing), true, stream);
+            {
+                TimedLaunch timed(ps, 1, stream);
+                rc = trace_queue(scene, ps->qp, nullptr, ps->occluded, true, flags, ps->cursors + (ps->cursor_next++ % QueueRing), true, stream);
+            }
             if (rc != ASGPU_OK) return rc;
             ++ps->launches;
             if (ps->capture_armed && (rc = capture_wavefront(ps, ps->qp, 1, depth, stream)) != ASGPU_OK) return rc;
-            accumulate_kernel<<<grid, StageThreads, 0, stream>>>(ps->params, vp, ps->occluded, ps->image, ps->stats_dev);
+            {
+                TimedLaunch timed(ps, 3, stream);
+                accumulate_kernel<<<grid, StageThreads, 0, stream>>>(ps->params, vp, ps->occluded, ps->image, ps->stats_dev);
+            }
             ASGPU_CUDA(cudaGetLastError(), "accumulate_kernel");
             ++ps->launches;
             std::swap(qa, qb);
@@ -769,6 +868,33 @@ int asgpu_path_stream_clear(asgpu_path_stream* ps)
     ASGPU_CUDA(cudaMemset(ps->stats_dev, 0, StatCount * 8), "cudaMemset(stats)");
     ps->wavefronts = 0;
     ps->launches = 0;
+    ps->timed.clear();
+    ps->events_used = 0;
+    return ASGPU_OK;
+}
+
+int asgpu_path_stream_set_profiling(asgpu_path_stream* ps, int enabled)
+{
+    if (!ps) return fail(ASGPU_E_INVALID, "null path stream");
+    ps->profiling = enabled != 0;
+    return ASGPU_OK;
+}
+
+int asgpu_path_stream_get_profile(asgpu_path_stream* ps, asgpu_path_stream_profile* out)
+{
+    if (!ps || !out) return fail(ASGPU_E_INVALID, "null argument");
+    ASGPU_CUDA(cudaSetDevice(ps->scene->device), "cudaSetDevice");
+    ASGPU_CUDA(cudaDeviceSynchronize(), "cudaDeviceSynchronize");
+    std::memset(out, 0, sizeof(*out));
+    for (const auto& t : ps->timed)
+    {
+        float ms = 0.0f;
+        ASGPU_CUDA(cudaEventElapsedTime(&ms, t.second.first, t.second.second), "cudaEventElapsedTime");
+        if (t.first == 0) { out->closest_ms += ms; ++out->closest_launches; }
+        else if (t.first == 1) { out->probe_ms += ms; ++out->probe_launches; }
+        else if (t.first == 2) out->refine_ms += ms;
+        else out->stage_ms += ms;
+    }
     return ASGPU_OK;
 }
 
@@ -814,6 +940,16 @@ long long asgpu_path_stream_capture_get(const asgpu_path_stream* ps, int k, int*
     if (path_ids) std::memcpy(path_ids, c.path.data(), n * 4);
     if (results) std::memcpy(results, c.results.data(), c.results.size());
     if (parents && !c.parents.empty()) std::memcpy(parents, c.parents.data(), c.parents.size() * sizeof(asgpu_parent));
+    return static_cast<long long>(n);
+}
+
+long long asgpu_path_stream_capture_get_times(const asgpu_path_stream* ps, int k, float* time_absolute, float* time_normalized)
+{
+    if (!ps || k < 0 || k >= static_cast<int>(ps->captured.size())) return fail(ASGPU_E_INVALID, "no such captured wavefront");
+    const Captured& c = ps->captured[k];
+    const size_t n = c.tmin.size();
+    if (time_absolute) std::memcpy(time_absolute, c.time_absolute.data(), n * 4);
+    if (time_normalized) std::memcpy(time_normalized, c.time_normalized.data(), n * 4);
     return static_cast<long long>(n);
 }
 

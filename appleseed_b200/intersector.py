@@ -341,6 +341,27 @@ class Intersector:
         _check(self.lib.asgpu_trace_probe_with_parents(self.ctx.handle, C.byref(cr), parents.data_ptr(), len(rays), occluded.data_ptr(),
                                                        self._flags(exact, False, False), C.c_void_p(stream)), "asgpu_trace_probe_with_parents")
 
+    def support_planes_device(self, rays: DeviceRays, hits: "torch.Tensor", planes: "torch.Tensor"):
+        """``planes``: float64 CUDA tensor of n * 9 values receiving ``m_triangle_support_plane``
+        (v0, e0, e1) of every hit (``asgpu_get_support_planes``)."""
+        import torch
+        n = len(rays)
+        assert planes.dtype == torch.float64 and planes.numel() >= n * 9
+        cr = rays.to_c()
+        stream = torch.cuda.current_stream(self.ctx.device).cuda_stream
+        _check(self.lib.asgpu_get_support_planes(self.ctx.handle, C.byref(cr), hits.data_ptr(), n, planes.data_ptr(), C.c_void_p(stream)),
+               "asgpu_get_support_planes")
+
+    def support_planes(self, rays: RayBatch, hits: np.ndarray) -> np.ndarray:
+        import torch
+        dev = "cuda:%d" % self.ctx.device
+        d = DeviceRays.from_host(rays, dev)
+        h = torch.from_numpy(np.ascontiguousarray(hits).view(np.uint8)).to(dev)
+        out = torch.empty(max(1, len(rays)) * 9, dtype=torch.float64, device=dev)
+        self.support_planes_device(d, h, out)
+        torch.cuda.synchronize()
+        return out.cpu().numpy()[: len(rays) * 9].reshape(-1, 9).copy()
+
     # Host-array conveniences over the three calls above (upload, run, download).
     def refine_and_offset(self, rays: RayBatch, hits: np.ndarray) -> np.ndarray:
         import torch

@@ -83,6 +83,8 @@ class PathStreamConfig:
     exact: bool = False
     counters: bool = False                 # accumulate the scene's traversal counters (slower)
     parents: bool = False                  # child rays carry their refined parent shading point (ASGPU_STREAM_PARENTS)
+    shutter_open: float = 0.0              # ray time: one normalized time per camera path, absolute = lerp(open, close, t);
+    shutter_close: float = 0.0             # open == close: every ray at time 0
 
     def to_c(self) -> "_lib.PathStreamDesc":
         d = _lib.PathStreamDesc()
@@ -102,6 +104,7 @@ class PathStreamConfig:
             for a in range(3):
                 d.lights[k][a] = float(lights[k, a])
         d.offset_eps = self.offset_eps
+        d.shutter_open, d.shutter_close = self.shutter_open, self.shutter_close
         return d
 
 
@@ -185,6 +188,18 @@ class PathStream:
             par = np.zeros(n, dtype=PARENT_DTYPE)
             ptr = lambda a: a.ctypes.data if n else None
             self.lib.asgpu_path_stream_capture_get(self.handle, k, None, None, ptr(org), ptr(dirs), ptr(tmin), ptr(tmax), ptr(flags), ptr(ids), ptr(res), ptr(par))
+            ta, tn = np.zeros(n, dtype=np.float32), np.zeros(n, dtype=np.float32)
+            self.lib.asgpu_path_stream_capture_get_times(self.handle, k, ptr(ta), ptr(tn))
             out.append(CapturedWavefront("closest" if kind.value == 0 else "probe", int(depth.value),
-                                         RayBatch(org, dirs, tmin, tmax, flags=flags), ids, res, par))
+                                         RayBatch(org, dirs, tmin, tmax, ta, tn, flags), ids, res, par))
         return out
+
+    def set_profiling(self, enabled: bool = True):
+        """Record CUDA events around every launch of the following render calls."""
+        _check(self.lib.asgpu_path_stream_set_profiling(self.handle, 1 if enabled else 0), "asgpu_path_stream_set_profiling")
+
+    def profile(self) -> dict:
+        """Device time by kind of launch since the last clear() (needs set_profiling)."""
+        v = _lib.PathStreamProfile()
+        _check(self.lib.asgpu_path_stream_get_profile(self.handle, C.byref(v)), "asgpu_path_stream_get_profile")
+        return v.as_dict()

@@ -25,6 +25,12 @@
  *   asgpu_scene_export_blob /
  *   asgpu_scene_import_blob      (new) one contiguous device blob = the payload of the single
  *                                  NCCL broadcast that replicates the scene to every GPU
+ *   asgpu_get_support_planes     ShadingPoint::m_triangle_support_plane, written by
+ *                                  TriangleLeafVisitor::read_hit_triangle_data, triangletree.cpp:1483-1499
+ *                                  (TriangleMTSupportPlane<double>, foundation/math/intersection/raytrianglemt.h:84-108);
+ *                                  input of Intersector::make_triangle_shading_point, intersector.cpp:240-271
+ *   asgpu_refine_and_offset      ShadingPoint::refine_and_offset   shading/shadingpoint.cpp:362-425
+ *                                  with fetch_triangle_source_geometry :186-256 (static and deforming meshes)
  */
 #ifndef ASGPU_H
 #define ASGPU_H
@@ -36,7 +42,7 @@
 extern "C" {
 #endif
 
-#define ASGPU_VERSION 1
+#define ASGPU_VERSION 2
 
 /* Error codes. */
 #define ASGPU_OK              0
@@ -168,16 +174,18 @@ typedef struct asgpu_assembly_tree_view {
 
 /* Optional source geometry, one asgpu_source_geometry per triangle tree: what
  * ShadingPoint::fetch_triangle_source_geometry (renderer/kernel/shading/shadingpoint.cpp:186-256)
- * reads for a static mesh -- StaticTriangleTess::m_vertices / m_primitives and the ObjectInstance
- * transform.  Only needed for asgpu_refine_and_offset. */
+ * reads -- StaticTriangleTess::m_vertices / m_primitives, the vertex poses of a deforming mesh
+ * (get_vertex_pose, statictessellation.h) and the ObjectInstance transform.  Only needed for
+ * asgpu_refine_and_offset. */
 typedef struct asgpu_source_object {
     const float*    vertices;           /* vertex_count * 3, object space */
     const void*     triangles;          /* triangle i: three uint32_t vertex indices at triangles + i * triangle_stride */
     uint32_t        vertex_count;
     uint32_t        triangle_count;
     uint32_t        triangle_stride;    /* bytes: 12 for a packed index array, sizeof(renderer::Triangle) for m_primitives */
-    uint32_t        reserved;
+    uint32_t        motion_segment_count;   /* StaticTriangleTess::get_motion_segment_count(); 0 = static mesh */
     double          parent_to_local[16];    /* ObjectInstance::get_transform().get_parent_to_local() */
+    const float*    vertex_poses;       /* vertex_count * motion_segment_count * 3, [v * msc + m] as in asgpu_mesh; NULL for a static mesh */
 } asgpu_source_object;
 
 /* renderer::IntersectionFilter of one object instance (renderer/kernel/intersection/
@@ -330,10 +338,28 @@ int             asgpu_trace(asgpu_scene* scene, const asgpu_rays* rays, size_t n
 int             asgpu_trace_probe(asgpu_scene* scene, const asgpu_rays* rays, size_t n, uint8_t* occluded,
                                   uint32_t flags, void* stream);
 
-/* Same with HOST buffers: rays are staged through pinned memory in chunks and the copies overlap
- * the kernels; returns when the results are in `hits` / `occluded`. */
+/* Same with HOST buffers: the batch is cut into chunks (1 Mi rays) that go through device staging
+ * buffers on three streams, so that the H2D copy of one chunk, the kernel of the previous one and
+ * the D2H copy of the one before overlap; returns when the results are in `hits` / `occluded`.
+ * The copies are issued straight from / into the caller's arrays: they are asynchronous (and the
+ * overlap real) when those arrays are page-locked -- asgpu_pin_host below, or any pinned allocation
+ * of the caller's; from pageable memory the CUDA driver stages every copy synchronously. */
 int             asgpu_trace_host(asgpu_scene* scene, const asgpu_rays* rays, size_t n, asgpu_hit* hits, uint32_t flags);
 int             asgpu_trace_probe_host(asgpu_scene* scene, const asgpu_rays* rays, size_t n, uint8_t* occluded, uint32_t flags);
+
+/* Page-locks / unlocks a host range for the calls above (cudaHostRegister / cudaHostUnregister), so
+ * that a caller without CUDA headers can pin its ray and hit arenas once. */
+int             asgpu_pin_host(void* ptr, size_t bytes);
+int             asgpu_unpin_host(void* ptr);
+
+/* The support plane of every hit: planes[i * 9 ...] = v0, e0, e1 of the hit triangle as doubles,
+ * exactly what TriangleLeafVisitor::read_hit_triangle_data stores in
+ * ShadingPoint::m_triangle_support_plane (triangletree.cpp:1483-1499): the float triangle of the
+ * leaf -- for a moving triangle the one interpolated at rays->time_normalized[i] by the closest-hit
+ * visitor (:1432-1469) -- widened to double.  Zeros for a miss.  rays = the rays that produced
+ * `hits` (only the time is read).  DEVICE pointers.  Needs the exact layout. */
+int             asgpu_get_support_planes(asgpu_scene* scene, const asgpu_rays* rays, const asgpu_hit* hits, size_t n,
+                                         double* planes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Parent shading points.  Intersector::trace(ray, shading_point,
@@ -355,8 +381,10 @@ typedef struct asgpu_parent {           /* 80 bytes */
 
 /* For every hit of a closest-hit trace: the parent record its ShadingPoint would hold.  rays =
  * the rays that produced `hits`.  DEVICE pointers.  Needs source geometry (asgpu_scene_create_ex)
- * and the exact layout; static triangles only (animated assembly instances are handled: the refine
- * space is the instance transform at rays->time_absolute[i]). */
+ * and the exact layout.  Moving triangles: the support plane is the triangle interpolated at
+ * rays->time_normalized[i] and the geometric normal comes from the source vertices interpolated
+ * between the two poses around that time (shadingpoint.cpp:186-256).  Animated assembly instances:
+ * the refine space is the instance transform at rays->time_absolute[i]. */
 int             asgpu_refine_and_offset(asgpu_scene* scene, const asgpu_rays* rays, const asgpu_hit* hits, size_t n,
                                         asgpu_parent* parents, void* stream);
 
@@ -369,8 +397,8 @@ int             asgpu_trace_probe_with_parents(asgpu_scene* scene, const asgpu_r
 
 /* The coherence sort behind ASGPU_TRACE_SORT on its own: order[i] = index of the ray to process
  * at position i (a permutation of 0..n-1, device array) by ascending 24-bit origin / direction
- * Morton key; keys (optional, device) receives the sorted keys.  One sort at a time per scene
- * (the scratch memory belongs to the scene handle). */
+ * Morton key; keys (optional, device) receives the sorted keys.  The workspace is a stream-ordered
+ * allocation of the call (as for ASGPU_TRACE_SORT): any number of sorts may be in flight. */
 int             asgpu_sort_rays(asgpu_scene* scene, const asgpu_rays* rays, size_t n, uint32_t* order, uint32_t* keys, void* stream);
 
 typedef struct asgpu_counters {
@@ -406,14 +434,17 @@ asgpu_ray_queue* asgpu_queue_create(asgpu_scene* scene, size_t capacity);
 void            asgpu_queue_destroy(asgpu_ray_queue* queue);
 size_t          asgpu_queue_capacity(const asgpu_ray_queue* queue);
 /* Device pointers of the queue's arrays (for a caller's own generate / shade kernels):
- * rays->org ... flags as in asgpu_rays; path_ids = uint32_t[capacity]; count = uint64_t in device memory. */
+ * rays->org ... flags as in asgpu_rays, the two time arrays included; path_ids =
+ * uint32_t[capacity]; count = uint64_t in device memory.  A producer that counts past `capacity`
+ * only loses the rays beyond it: every consumer clamps the count. */
 int             asgpu_queue_device_arrays(asgpu_ray_queue* queue, asgpu_rays* rays, uint32_t** path_ids, uint64_t** count);
 int             asgpu_queue_reset(asgpu_ray_queue* queue, void* stream);                    /* count = 0 */
 int             asgpu_queue_count(asgpu_ray_queue* queue, void* stream, uint64_t* count);   /* synchronises `stream` */
-/* Appends n rays from HOST arrays (path_ids may be NULL: ids = position). */
+/* Appends n rays from HOST arrays (path_ids may be NULL: ids = position; NULL time arrays: time 0). */
 int             asgpu_queue_push_host(asgpu_ray_queue* queue, const asgpu_rays* rays, const uint32_t* path_ids, size_t n, void* stream);
 /* Trace everything in the queue (the ray count is read on the device).  hits / occluded: DEVICE
- * arrays of at least `capacity` entries. */
+ * arrays of at least `capacity` entries.  ASGPU_TRACE_SORT is refused (ASGPU_E_UNSUPPORTED): the
+ * sort needs the ray count on the host. */
 int             asgpu_trace_queue(asgpu_scene* scene, asgpu_ray_queue* queue, asgpu_hit* hits, uint32_t flags, void* stream);
 int             asgpu_trace_probe_queue(asgpu_scene* scene, asgpu_ray_queue* queue, uint8_t* occluded, uint32_t flags, void* stream);
 
@@ -444,6 +475,11 @@ typedef struct asgpu_path_stream_desc {
     double          film_width, film_height, focal_length;
     double          lights[8][3];           /* point light positions, world space */
     double          offset_eps;             /* next-ray origin offset along the geometric normal (parent == nullptr convention) */
+    /* Ray time: every camera path draws one normalized time in [0, 1) (a float) and gets
+     * ShadingRay::Time::create_with_normalized_time(t, shutter_open, shutter_close)
+     * (shading/shadingray.h:230-239: absolute = lerp(open, close, t)); bounce and shadow rays inherit
+     * their path's time (pathtracer.h:764).  open == close == 0: time 0 for every ray. */
+    float           shutter_open, shutter_close;
 } asgpu_path_stream_desc;
 
 typedef struct asgpu_path_stream_stats {
@@ -477,6 +513,22 @@ int             asgpu_path_stream_capture_count(const asgpu_path_stream* stream)
 long long       asgpu_path_stream_capture_get(const asgpu_path_stream* stream, int k, int* kind, uint32_t* depth,
                                               double* org, double* dir, double* tmin, double* tmax, uint32_t* flags,
                                               uint32_t* path_ids, void* results, asgpu_parent* parents);
+/* The ray times of captured wavefront k (either array may be NULL). */
+long long       asgpu_path_stream_capture_get_times(const asgpu_path_stream* stream, int k, float* time_absolute, float* time_normalized);
+/* Device time of the trace launches of the render calls since the last clear, measured with CUDA
+ * events on the stream's own launch stream when profiling is switched on (events are recorded
+ * around every trace launch; off by default).  closest_ms / probe_ms: sums over the launches;
+ * closest_rays / probe_rays: rays those launches traced (read back after the frame). */
+typedef struct asgpu_path_stream_profile {
+    double          closest_ms, probe_ms, refine_ms, stage_ms;  /* stage = generate + shade + accumulate */
+    uint64_t        closest_launches, probe_launches;
+} asgpu_path_stream_profile;
+int             asgpu_path_stream_set_profiling(asgpu_path_stream* stream, int enabled);
+int             asgpu_path_stream_get_profile(asgpu_path_stream* stream, asgpu_path_stream_profile* out);     /* synchronises */
+
+/* Forgets the cached ASGPU_* scheduling knobs (environment variables read once per process):
+ * the next launch reads the environment again.  Tuning experiments only. */
+void            asgpu_reload_tuning(void);
 
 const char*     asgpu_last_error(void);
 int             asgpu_version(void);

@@ -498,6 +498,9 @@ struct TriTree
     std::vector<uint8_t>    leaf_data;
     std::vector<Key>        keys;
     std::vector<float>      slot_tri;           // 9 floats per leaf slot: TriangleMT<float> of a static triangle (zeros if moving)
+    std::vector<uint32_t>   slot_msc;           // per leaf slot: motion segment count of the triangle
+    std::vector<size_t>     slot_pose;          // per leaf slot: index of the first vertex of pose 0 in slot_poses (moving triangles)
+    std::vector<V3f>        slot_poses;         // (msc + 1) * 3 assembly-space vertices per moving triangle, as the leaf stores them
     size_t                  static_count = 0;
     size_t                  moving_count = 0;
     size_t                  undecided = 0;
@@ -748,6 +751,10 @@ void store_triangles(TriTree& tree, const std::vector<size_t>& order, const TriC
                 std::memcpy(t, u, 36);
             }
             tree.slot_tri.insert(tree.slot_tri.end(), t, t + 9);
+            tree.slot_msc.push_back(static_cast<uint32_t>(info.msc));
+            tree.slot_pose.push_back(tree.slot_poses.size());
+            if (info.msc != 0)
+                tree.slot_poses.insert(tree.slot_poses.end(), c.vertices.begin() + info.vertex_index, c.vertices.begin() + info.vertex_index + (info.msc + 1) * 3);
         }
         const size_t s = encoded_size(c, order, begin, count);
         uint8_t* user = reinterpret_cast<uint8_t*>(node.bbox);
@@ -1589,6 +1596,59 @@ inline void offset_point(const MTd& tri, const double p[3], const double n[3], d
     out[0] = result[0]; out[1] = result[1]; out[2] = result[2];
 }
 
+// The triangle the closest-hit leaf visitor leaves behind for a hit (m_hit_triangle,
+// triangletree.cpp:1413, 1468-1469), from which read_hit_triangle_data (:1483-1499) makes the
+// ShadingPoint's support plane: the stored triangle, or for a moving triangle the one interpolated at
+// the ray's normalized time (float product time * msc, float lerp), widened to double.
+void hit_triangle(const TriTree& tree, const uint32_t slot, const float time_normalized, MTd& tri)
+{
+    const uint32_t msc = tree.slot_msc[slot];
+    if (msc == 0)
+    {
+        const float* f = tree.slot_tri.data() + size_t(slot) * 9;
+        for (int i = 0; i < 3; ++i) { tri.v0[i] = f[i]; tri.e0[i] = f[3 + i]; tri.e1[i] = f[6 + i]; }
+        return;
+    }
+    const double base_time = time_normalized * msc;         // float * uint32 -> float product, widened
+    const size_t base_index = static_cast<size_t>(base_time);
+    const float frac = static_cast<float>(base_time - base_index);
+    const float omf = 1.0f - frac;
+    const V3f* p = tree.slot_poses.data() + tree.slot_pose[slot] + base_index * 3;
+    float v[3][3];
+    for (int c = 0; c < 3; ++c)
+    {
+        v[c][0] = p[c].x * omf + p[3 + c].x * frac;
+        v[c][1] = p[c].y * omf + p[3 + c].y * frac;
+        v[c][2] = p[c].z * omf + p[3 + c].z * frac;
+    }
+    // TriangleMT<float>(v0, v1, v2): edges in float (raytrianglemt.h:128-137).
+    for (int i = 0; i < 3; ++i)
+    {
+        tri.v0[i] = v[0][i];
+        tri.e0[i] = v[1][i] - v[0][i];
+        tri.e1[i] = v[2][i] - v[0][i];
+    }
+}
+
+// Source vertex `index` of a mesh at the ray time (fetch_triangle_source_geometry,
+// shadingpoint.cpp:186-256): previous pose * (1 - frac) + next pose * frac in float.
+V3f source_vertex(const orc_mesh& mesh, const uint32_t index, const float time_normalized)
+{
+    if (mesh.motion_segment_count == 0 || mesh.vertex_poses == nullptr) return mesh_vertex(mesh, index);
+    const size_t msc = mesh.motion_segment_count;
+    const double base_time = time_normalized * msc;         // float * size_t -> float product, widened
+    const size_t base_index = static_cast<size_t>(base_time);
+    const float frac = static_cast<float>(base_time - base_index);
+    const float omf = 1.0f - frac;
+    const V3f prev = base_index == 0 ? mesh_vertex(mesh, index) : mesh_pose(mesh, index, base_index - 1);
+    const V3f next = mesh_pose(mesh, index, base_index);
+    V3f r;
+    r.x = prev.x * omf + next.x * frac;
+    r.y = prev.y * omf + next.y * frac;
+    r.z = prev.z * omf + next.z * frac;
+    return r;
+}
+
 void refine_offset_one(const Scene& s, const Ray& ray, const orc_hit& h, orc_parent& out)
 {
     std::memset(&out, 0, sizeof(out));
@@ -1605,8 +1665,7 @@ void refine_offset_one(const Scene& s, const Ray& ray, const orc_hit& h, orc_par
     double p[3] = { lo.x + dir[0] * h.t, lo.y + dir[1] * h.t, lo.z + dir[2] * h.t };
 
     MTd tri;
-    const float* f = tree.slot_tri.data() + size_t(h.tri_slot) * 9;
-    for (int i = 0; i < 3; ++i) { tri.v0[i] = f[i]; tri.e0[i] = f[3 + i]; tri.e1[i] = f[6 + i]; }
+    hit_triangle(tree, h.tri_slot, ray.time_normalized, tri);
 
     for (int step = 0; step < 2; ++step)
     {
@@ -1618,7 +1677,7 @@ void refine_offset_one(const Scene& s, const Ray& ray, const orc_hit& h, orc_par
     const orc_object_instance& oi = assembly.object_instances[h.object_instance_index];
     const orc_mesh& mesh = s.desc.meshes[oi.mesh_index];
     const uint32_t* t3 = mesh.triangles + size_t(h.primitive_index) * 3;
-    const V3f v0 = mesh_vertex(mesh, t3[0]), v1 = mesh_vertex(mesh, t3[1]), v2 = mesh_vertex(mesh, t3[2]);
+    const V3f v0 = source_vertex(mesh, t3[0], ray.time_normalized), v1 = source_vertex(mesh, t3[1], ray.time_normalized), v2 = source_vertex(mesh, t3[2], ray.time_normalized);
     const float a[3] = { v1.x - v0.x, v1.y - v0.y, v1.z - v0.z }, b[3] = { v2.x - v0.x, v2.y - v0.y, v2.z - v0.z };
     const float nf[3] = { a[1] * b[2] - b[1] * a[2], a[2] * b[0] - b[2] * a[0], a[0] * b[1] - b[0] * a[1] };
     const double nd[3] = { nf[0], nf[1], nf[2] };
@@ -1647,6 +1706,27 @@ void orc_refine_offset(const void* scene, const orc_rays* rays, const orc_hit* h
         {
             Ray ray; load_ray(*rays, i, ray);
             refine_offset_one(s, ray, hits[i], out[i]);
+        }
+    });
+}
+
+// ShadingPoint::m_triangle_support_plane of every hit: v0, e0, e1 as doubles (zeros for a miss).
+void orc_support_planes(const void* scene, const orc_rays* rays, const orc_hit* hits, size_t n, double* planes, int threads)
+{
+    const Scene& s = *static_cast<const Scene*>(scene);
+    parallel_ranges(n, threads, [&](int, size_t begin, size_t end)
+    {
+        for (size_t i = begin; i < end; ++i)
+        {
+            double* dst = planes + i * 9;
+            for (int k = 0; k < 9; ++k) dst[k] = 0.0;
+            const orc_hit& h = hits[i];
+            if (h.prim_type != 2) continue;
+            const orc_assembly_instance& ai = s.desc.assembly_instances[h.assembly_instance];
+            const TriTree& tree = *s.trees[s.assembly_tree[ai.assembly_index]];
+            MTd tri;
+            hit_triangle(tree, h.tri_slot, rays->time_normalized ? rays->time_normalized[i] : 0.0f, tri);
+            for (int k = 0; k < 3; ++k) { dst[k] = tri.v0[k]; dst[3 + k] = tri.e0[k]; dst[6 + k] = tri.e1[k]; }
         }
     });
 }

@@ -112,6 +112,8 @@ class Oracle:
         self._probe.argtypes = [C.c_void_p, C.POINTER(CRays), C.c_size_t, C.c_void_p, C.c_int, C.POINTER(Counters)]
         self._refine = getattr(L, p + "_refine_offset")
         self._refine.argtypes = [C.c_void_p, C.POINTER(CRays), C.c_void_p, C.c_size_t, C.c_void_p, C.c_int]
+        self._planes = getattr(L, p + "_support_planes")
+        self._planes.argtypes = [C.c_void_p, C.POINTER(CRays), C.c_void_p, C.c_size_t, C.c_void_p, C.c_int]
         self._trace_par = getattr(L, p + "_trace_parents")
         self._trace_par.argtypes = [C.c_void_p, C.POINTER(CRays), C.c_void_p, C.c_size_t, C.c_void_p, C.c_int]
         self._probe_par = getattr(L, p + "_trace_probe_parents")
@@ -126,6 +128,8 @@ class Oracle:
             self._item_motion.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(CItemMotion)]
             self._item_p2l = L.asref_get_item_parent_to_local
             self._item_p2l.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
+            self._trace_planes = L.asref_trace_planes
+            self._trace_planes.argtypes = [C.c_void_p, C.POINTER(CRays), C.c_size_t, C.c_void_p, C.c_void_p, C.c_int]
         if prefix == "orc":
             self._two = L.orc_two_nearest
             self._two.argtypes = [C.c_void_p, C.POINTER(CRays), C.c_size_t, C.c_void_p, C.c_void_p, C.c_int]
@@ -273,6 +277,23 @@ class OracleScene:
         hits = np.ascontiguousarray(hits)
         self.oracle._refine(self.handle, C.byref(cr), hits.ctypes.data, n, out.ctypes.data, threads)
         return out
+
+    def support_planes(self, rays: RayBatch, hits: np.ndarray, threads: int = 1) -> np.ndarray:
+        """m_triangle_support_plane (v0, e0, e1) of every hit, recomputed from leaf slot + ray time."""
+        out = np.zeros((len(rays), 9), dtype=np.float64)
+        cr = rays.to_c()
+        hits = np.ascontiguousarray(hits)
+        self.oracle._planes(self.handle, C.byref(cr), hits.ctypes.data, len(rays), out.ctypes.data, threads)
+        return out
+
+    def trace_planes(self, rays: RayBatch, threads: int = 1):
+        """(hits, planes): Intersector::trace with the support plane the traversal itself stored in the
+        ShadingPoint (oracle/_ref only)."""
+        hits = np.zeros(len(rays), dtype=HIT_DTYPE)
+        planes = np.zeros((len(rays), 9), dtype=np.float64)
+        cr = rays.to_c()
+        self.oracle._trace_planes(self.handle, C.byref(cr), len(rays), hits.ctypes.data, planes.ctypes.data, threads)
+        return hits, planes
 
     def trace_parents(self, rays: RayBatch, parents: np.ndarray, threads: int = 1) -> np.ndarray:
         n = len(rays)

@@ -192,6 +192,9 @@ void    asref_kat_bitmask(uint32_t width, uint32_t height, const uint32_t* xs, c
 void*   asref_scene_create_animated(const orc_scene_desc* desc, const orc_instance_keys* keys /* per assembly instance */);
 void    asref_get_item_motion(const void* scene, uint32_t item /* tree order */, orc_item_motion* out);
 void    asref_get_item_parent_to_local(const void* scene, uint32_t item, double out[16]);
+/* Intersector::trace returning, next to the hit records, ShadingPoint::m_triangle_support_plane as
+ * the traversal stored it (triangletree.cpp:1483-1499; nine doubles v0, e0, e1; zeros for a miss). */
+void    asref_trace_planes(const void* scene, const orc_rays* rays, size_t n, orc_hit* out, double* planes, int threads);
 
 #define ORC_DECLARE(prefix)                                                                         \
     void*   prefix##_scene_create(const orc_scene_desc* desc);                                      \
@@ -208,6 +211,8 @@ void    asref_get_item_parent_to_local(const void* scene, uint32_t item, double 
     void    prefix##_refine_offset(const void* scene, const orc_rays* rays, const orc_hit* hits,    \
                                    size_t n, orc_parent* out, int threads);                         \
     /* trace / trace_probe with a parent shading point per ray. */                                  \
+    void    prefix##_support_planes(const void* scene, const orc_rays* rays, const orc_hit* hits,   \
+                                    size_t n, double* planes, int threads);                         \
     void    prefix##_trace_parents(const void* scene, const orc_rays* rays,                         \
                                    const orc_parent* parents, size_t n, orc_hit* out, int threads); \
     void    prefix##_trace_probe_parents(const void* scene, const orc_rays* rays,                   \

@@ -190,6 +190,9 @@ class RefTriangleTree
     std::vector<TriangleKey>    m_triangle_keys;
     std::vector<std::uint8_t>   m_leaf_data;
     std::vector<GTriangleType>  m_slot_triangles;       // per leaf slot: the static triangle the leaf stores (checker convenience)
+    std::vector<std::uint32_t>  m_slot_msc;             // per leaf slot: the triangle's motion segment count
+    std::vector<size_t>         m_slot_pose;            // per leaf slot: first vertex of pose 0 in m_slot_poses (moving triangles)
+    std::vector<GVector3>       m_slot_poses;           // (msc + 1) * 3 vertices per moving triangle, as encoded in the leaf
     std::vector<std::unique_ptr<RefIntersectionFilter>> m_intersection_filters;    // per object instance, or empty
     size_t                      m_static_triangle_count = 0;
     size_t                      m_moving_triangle_count = 0;
@@ -683,6 +686,11 @@ class RefTriangleTree
                     if (info.m_motion_segment_count == 0)
                         triangle = GTriangleType(triangle_vertices[info.m_vertex_index], triangle_vertices[info.m_vertex_index + 1], triangle_vertices[info.m_vertex_index + 2]);
                     m_slot_triangles.push_back(triangle);
+                    m_slot_msc.push_back(static_cast<std::uint32_t>(info.m_motion_segment_count));
+                    m_slot_pose.push_back(m_slot_poses.size());
+                    if (info.m_motion_segment_count != 0)
+                        m_slot_poses.insert(m_slot_poses.end(), triangle_vertices.begin() + info.m_vertex_index,
+                                            triangle_vertices.begin() + info.m_vertex_index + (info.m_motion_segment_count + 1) * 3);
                 }
 
                 const size_t leaf_size =
@@ -730,6 +738,7 @@ struct RefShadingPoint
     std::uint32_t   m_primitive_index = 0;
     std::uint32_t   m_tri_slot = 0;
     std::uint32_t   m_motion_segment = 0;
+    TriangleMTSupportPlane<double> m_triangle_support_plane;    // shadingpoint.h:300, written at triangletree.cpp:1496-1497
 };
 
 //
@@ -743,6 +752,10 @@ struct TriLeafVisitor
     bool                    m_has_hit = false;
     size_t                  m_hit_triangle_index = 0;
     std::uint32_t           m_hit_motion_segment = 0;
+    // m_hit_triangle (triangletree.h:233) points into the leaf data for a static triangle and at the
+    // member m_interpolated_triangle (triangletree.h:232, assigned at triangletree.cpp:1468-1469) for
+    // a moving one; this driver copies leaf triangles out of unaligned storage, so both cases keep a copy.
+    GTriangleType           m_interpolated_triangle;
     orc_counters*           m_counters;
 
     TriLeafVisitor(const RefTriangleTree& tree, RefShadingPoint& sp, orc_counters* counters)
@@ -797,6 +810,7 @@ struct TriLeafVisitor
                             continue;
                     }
                     m_has_hit = true;
+                    m_interpolated_triangle = gtriangle;
                     m_hit_triangle_index = triangle_index;
                     m_hit_motion_segment = 0;
                     m_shading_point.m_ray.m_tmax = t;
@@ -847,6 +861,7 @@ struct TriLeafVisitor
                             continue;
                     }
                     m_has_hit = true;
+                    m_interpolated_triangle = gtriangle;
                     m_hit_triangle_index = triangle_index;
                     m_hit_motion_segment = static_cast<std::uint32_t>(base_index);
                     m_shading_point.m_ray.m_tmax = t;
@@ -871,6 +886,8 @@ struct TriLeafVisitor
             m_shading_point.m_primitive_index = key.m_triangle_index;
             m_shading_point.m_tri_slot = static_cast<std::uint32_t>(m_hit_triangle_index);
             m_shading_point.m_motion_segment = m_hit_motion_segment;
+            // Compute and store the support plane of the hit triangle (triangletree.cpp:1495-1497).
+            m_shading_point.m_triangle_support_plane.initialize(TriangleType(m_interpolated_triangle));
         }
     }
 };
@@ -1232,6 +1249,7 @@ struct AsmLeafVisitor
                 m_shading_point.m_primitive_index = asm_inst_shading_point.m_primitive_index;
                 m_shading_point.m_tri_slot = asm_inst_shading_point.m_tri_slot;
                 m_shading_point.m_motion_segment = asm_inst_shading_point.m_motion_segment;
+                m_shading_point.m_triangle_support_plane = asm_inst_shading_point.m_triangle_support_plane;     // assemblytree.cpp:743
             }
         }
 
@@ -1364,6 +1382,70 @@ void accumulate(orc_counters* total, const std::vector<orc_counters>& parts)
 
 }   // anonymous namespace
 
+// The hit triangle of a leaf slot at a ray time, recomputed the way TriangleLeafVisitor::visit makes
+// it (triangletree.cpp:1432-1451); asref_trace_planes returns the one the traversal itself left in
+// the ShadingPoint, and the tests demand that the two agree.
+static GTriangleType hit_triangle_of_slot(const RefTriangleTree& tree, const std::uint32_t slot, const float time_normalized)
+{
+    const std::uint32_t motion_segment_count = tree.m_slot_msc[slot];
+    if (motion_segment_count == 0) return tree.m_slot_triangles[slot];
+    const double base_time = time_normalized * motion_segment_count;
+    const size_t base_index = truncate<size_t>(base_time);
+    const GVector3* p = tree.m_slot_poses.data() + tree.m_slot_pose[slot] + base_index * 3;
+    const GScalar frac = static_cast<GScalar>(base_time - base_index);
+    const GScalar one_minus_frac = GScalar(1.0) - frac;
+    GVector3 v0 = p[0] * one_minus_frac;
+    GVector3 v1 = p[1] * one_minus_frac;
+    GVector3 v2 = p[2] * one_minus_frac;
+    v0 += p[3] * frac;
+    v1 += p[4] * frac;
+    v2 += p[5] * frac;
+    return GTriangleType(v0, v1, v2);
+}
+
+// ShadingPoint::fetch_triangle_source_geometry (shadingpoint.cpp:186-256), vertices only.
+static void fetch_source_vertices(const orc_mesh& mesh, const std::uint32_t* t3, const float time_normalized, GVector3& m_v0, GVector3& m_v1, GVector3& m_v2)
+{
+    const auto vertex = [&mesh](const std::uint32_t i) { return GVector3(mesh.vertices[i * 3], mesh.vertices[i * 3 + 1], mesh.vertices[i * 3 + 2]); };
+    const auto get_vertex_pose = [&mesh](const std::uint32_t i, const size_t m)
+    {
+        const float* p = mesh.vertex_poses + (size_t(i) * mesh.motion_segment_count + m) * 3;
+        return GVector3(p[0], p[1], p[2]);
+    };
+    const size_t motion_segment_count = mesh.vertex_poses ? mesh.motion_segment_count : 0;
+    const double base_time = time_normalized * motion_segment_count;
+    const size_t base_index = truncate<size_t>(base_time);
+    const GScalar frac = static_cast<GScalar>(base_time - base_index);
+    const GScalar one_minus_frac = GScalar(1.0) - frac;
+    if (motion_segment_count > 0)
+    {
+        if (base_index == 0)
+        {
+            m_v0 = vertex(t3[0]);
+            m_v1 = vertex(t3[1]);
+            m_v2 = vertex(t3[2]);
+        }
+        else
+        {
+            m_v0 = get_vertex_pose(t3[0], base_index - 1);
+            m_v1 = get_vertex_pose(t3[1], base_index - 1);
+            m_v2 = get_vertex_pose(t3[2], base_index - 1);
+        }
+        m_v0 *= one_minus_frac;
+        m_v1 *= one_minus_frac;
+        m_v2 *= one_minus_frac;
+        m_v0 += get_vertex_pose(t3[0], base_index) * frac;
+        m_v1 += get_vertex_pose(t3[1], base_index) * frac;
+        m_v2 += get_vertex_pose(t3[2], base_index) * frac;
+    }
+    else
+    {
+        m_v0 = vertex(t3[0]);
+        m_v1 = vertex(t3[1]);
+        m_v2 = vertex(t3[2]);
+    }
+}
+
 extern "C" {
 
 void* asref_scene_create(const orc_scene_desc* desc)
@@ -1455,6 +1537,66 @@ void asref_trace(const void* scene_, const orc_rays* rays, size_t n, orc_hit* ou
     accumulate(counters, parts);
 }
 
+// Intersector::trace with the support plane the traversal stored in the ShadingPoint
+// (m_triangle_support_plane: v0, e0, e1 as doubles; zeros for a miss).
+void asref_trace_planes(const void* scene_, const orc_rays* rays, size_t n, orc_hit* out, double* planes, int threads)
+{
+    const RefScene& scene = *static_cast<const RefScene*>(scene_);
+    parallel_ranges(n, threads, [&](int, size_t begin, size_t end)
+    {
+        orc_counters local;
+        std::memset(&local, 0, sizeof(local));
+        for (size_t i = begin; i < end; ++i)
+        {
+            RefShadingPoint shading_point;
+            load_ray(*rays, i, shading_point.m_ray);
+            const RayInfo3d ray_info(shading_point.m_ray);
+            AssemblyTreeIntersector intersector;
+            AsmLeafVisitor visitor{shading_point, scene.m_assembly_tree, &local};
+            intersector.intersect_no_motion(scene.m_assembly_tree, shading_point.m_ray, ray_info, visitor);
+            orc_hit& hit = out[i];
+            hit.t = shading_point.m_ray.m_tmax;
+            hit.u = shading_point.m_hit ? shading_point.m_bary[0] : 0.0f;
+            hit.v = shading_point.m_hit ? shading_point.m_bary[1] : 0.0f;
+            hit.assembly_instance = shading_point.m_hit ? shading_point.m_assembly_instance : ~std::uint32_t(0);
+            hit.object_instance_index = shading_point.m_hit ? shading_point.m_object_instance_index : 0;
+            hit.primitive_index = shading_point.m_hit ? shading_point.m_primitive_index : 0;
+            hit.tri_slot = shading_point.m_hit ? shading_point.m_tri_slot : 0;
+            hit.motion_segment = shading_point.m_hit ? shading_point.m_motion_segment : 0;
+            hit.prim_type = shading_point.m_hit ? 2 : 0;
+            double* dst = planes + i * 9;
+            for (int k = 0; k < 9; ++k) dst[k] = 0.0;
+            if (shading_point.m_hit)
+            {
+                const TriangleMTSupportPlane<double>& sp = shading_point.m_triangle_support_plane;
+                for (int k = 0; k < 3; ++k) { dst[k] = sp.m_v0[k]; dst[3 + k] = sp.m_e0[k]; dst[6 + k] = sp.m_e1[k]; }
+            }
+        }
+    });
+}
+
+// The same planes recomputed from the hit records (leaf slot + ray time), as the GPU ABI call
+// asgpu_get_support_planes does.
+void asref_support_planes(const void* scene_, const orc_rays* rays, const orc_hit* hits, size_t n, double* planes, int threads)
+{
+    const RefScene& scene = *static_cast<const RefScene*>(scene_);
+    const orc_scene_desc& desc = scene.m_desc;
+    parallel_ranges(n, threads, [&](int, size_t begin, size_t end)
+    {
+        for (size_t i = begin; i < end; ++i)
+        {
+            double* dst = planes + i * 9;
+            for (int k = 0; k < 9; ++k) dst[k] = 0.0;
+            const orc_hit& hit = hits[i];
+            if (hit.prim_type != 2) continue;
+            const orc_assembly_instance& inst = desc.assembly_instances[hit.assembly_instance];
+            const RefTriangleTree& tree = *scene.m_assembly_tree.m_triangle_trees[scene.m_assembly_tree.m_assembly_tree_index[inst.assembly_index]];
+            const TriangleMTSupportPlane<double> sp{TriangleType(hit_triangle_of_slot(tree, hit.tri_slot, rays->time_normalized ? rays->time_normalized[i] : 0.0f))};
+            for (int k = 0; k < 3; ++k) { dst[k] = sp.m_v0[k]; dst[3 + k] = sp.m_e0[k]; dst[6 + k] = sp.m_e1[k]; }
+        }
+    });
+}
+
 // Intersector::trace_probe (intersector.cpp:191-238), parent_shading_point == nullptr.
 void asref_trace_probe(const void* scene_, const orc_rays* rays, size_t n, uint8_t* out, int threads, orc_counters* counters)
 {
@@ -1524,16 +1666,15 @@ void asref_refine_offset(const void* scene_, const orc_rays* rays, const orc_hit
             }
             const RefTriangleTree& tree = *scene.m_assembly_tree.m_triangle_trees[scene.m_assembly_tree.m_assembly_tree_index[inst.assembly_index]];
 
-            // m_triangle_support_plane.initialize(TriangleType(triangle)) (triangletree.cpp:1483-1499).
-            const TriangleMTSupportPlane<double> support_plane{TriangleType(tree.m_slot_triangles[hit.tri_slot])};
+            // m_triangle_support_plane.initialize(TriangleType(*m_hit_triangle)) (triangletree.cpp:1483-1499).
+            const TriangleMTSupportPlane<double> support_plane{TriangleType(hit_triangle_of_slot(tree, hit.tri_slot, m_ray.m_time_normalized))};
 
-            // Source geometry (fetch_triangle_source_geometry, shadingpoint.cpp:186-256, static mesh).
+            // Source geometry (fetch_triangle_source_geometry, shadingpoint.cpp:186-256).
             const orc_object_instance& oi = assembly.object_instances[hit.object_instance_index];
             const orc_mesh& mesh = desc.meshes[oi.mesh_index];
             const std::uint32_t* t3 = mesh.triangles + size_t(hit.primitive_index) * 3;
-            const GVector3 v0(mesh.vertices[t3[0] * 3], mesh.vertices[t3[0] * 3 + 1], mesh.vertices[t3[0] * 3 + 2]);
-            const GVector3 v1(mesh.vertices[t3[1] * 3], mesh.vertices[t3[1] * 3 + 1], mesh.vertices[t3[1] * 3 + 2]);
-            const GVector3 v2(mesh.vertices[t3[2] * 3], mesh.vertices[t3[2] * 3 + 1], mesh.vertices[t3[2] * 3 + 2]);
+            GVector3 v0, v1, v2;
+            fetch_source_vertices(mesh, t3, m_ray.m_time_normalized, v0, v1, v2);
             const Transformd object_instance_transform = make_transform(oi.local_to_parent, oi.parent_to_local);
 
             Ray3d refine_space_ray = assembly_instance_transform.to_local(static_cast<const Ray3d&>(m_ray));

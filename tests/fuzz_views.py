@@ -22,7 +22,8 @@ from hostsim import hostsim  # noqa: E402
 
 class SourceObject(C.Structure):       # asgpu_source_object
     _fields_ = [("vertices", C.c_void_p), ("triangles", C.c_void_p), ("vertex_count", C.c_uint32), ("triangle_count", C.c_uint32),
-                ("triangle_stride", C.c_uint32), ("reserved", C.c_uint32), ("parent_to_local", C.c_double * 16)]
+                ("triangle_stride", C.c_uint32), ("motion_segment_count", C.c_uint32), ("parent_to_local", C.c_double * 16),
+                ("vertex_poses", C.c_void_p)]
 
 
 NODE_U32 = 32       # 128-byte node = 32 words: item_count, index, 4 motion box words, 2 pad, 24 words of boxes / user data

@@ -269,7 +269,29 @@ void hostsim_refine_offset(void* scene, const asgpu_rays* rays, const asgpu_hit*
         const double org[3] = { rays->org[i * 3], rays->org[i * 3 + 1], rays->org[i * 3 + 2] };
         const double dir[3] = { rays->dir[i * 3], rays->dir[i * 3 + 1], rays->dir[i * 3 + 2] };
         const float time_absolute = rays->time_absolute ? rays->time_absolute[i] : 0.0f;
-        refine_offset_one(s.view, org, dir, time_absolute, hits[i].t, item, hits[i].object_instance_index, hits[i].primitive_index, hits[i].tri_slot, dst);
+        const float time_normalized = rays->time_normalized ? rays->time_normalized[i] : 0.0f;
+        refine_offset_one(s.view, org, dir, time_absolute, time_normalized, hits[i].t, item, hits[i].object_instance_index, hits[i].primitive_index, hits[i].tri_slot, dst);
+    }
+}
+
+// asgpu_get_support_planes on the host build (hit_triangle of traverse_core.h).
+void hostsim_support_planes(void* scene, const asgpu_rays* rays, const asgpu_hit* hits, size_t n, double* planes)
+{
+    const SimScene& s = *static_cast<SimScene*>(scene);
+    const ItemRecord* items = reinterpret_cast<const ItemRecord*>(s.blob.data() + s.view.items);
+    for (size_t i = 0; i < n; ++i)
+    {
+        double* dst = planes + i * 9;
+        for (int k = 0; k < 9; ++k) dst[k] = 0.0;
+        if (hits[i].prim_type != 2) continue;
+        uint32_t item = ASGPU_MISS;
+        for (uint32_t k = 0; k < s.view.item_count; ++k) if (items[k].assembly_instance == hits[i].assembly_instance) { item = k; break; }
+        if (item == ASGPU_MISS) continue;
+        TreeDesc td; load_tree_desc(s.view, items[item].tree, td);
+        TriD tri;
+        hit_triangle(s.blob.data() + td.tris + static_cast<uint64_t>(hits[i].tri_slot) * sizeof(TriRecord), s.blob.data() + td.poses,
+                     rays->time_normalized ? rays->time_normalized[i] : 0.0f, tri);
+        for (int k = 0; k < 3; ++k) { dst[k] = tri.v0[k]; dst[3 + k] = tri.e0[k]; dst[6 + k] = tri.e1[k]; }
     }
 }
 

@@ -33,6 +33,7 @@ def load():
     lib.hostsim_trace_parents.argtypes = [C.c_void_p, C.POINTER(CRays), C.c_void_p, C.c_size_t, C.c_void_p, C.c_int]
     lib.hostsim_trace_probe_parents.argtypes = [C.c_void_p, C.POINTER(CRays), C.c_void_p, C.c_size_t, C.c_void_p, C.c_int]
     lib.hostsim_refine_offset.argtypes = [C.c_void_p, C.POINTER(CRays), C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.hostsim_support_planes.argtypes = [C.c_void_p, C.POINTER(CRays), C.c_void_p, C.c_size_t, C.c_void_p]
     return lib
 
 
@@ -101,6 +102,13 @@ class SimScene:
         cr = rays.to_c()
         hits = np.ascontiguousarray(hits)
         self.lib.hostsim_refine_offset(self.handle, C.byref(cr), hits.ctypes.data, len(rays), out.ctypes.data)
+        return out
+
+    def support_planes(self, rays: RayBatch, hits: np.ndarray) -> np.ndarray:
+        out = np.zeros((len(rays), 9), dtype=np.float64)
+        cr = rays.to_c()
+        hits = np.ascontiguousarray(hits)
+        self.lib.hostsim_support_planes(self.handle, C.byref(cr), hits.ctypes.data, len(rays), out.ctypes.data)
         return out
 
     def trace_parents(self, rays: RayBatch, parents: np.ndarray, wide: bool) -> np.ndarray:

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     for name in names:
         assert hasattr(lib, name), name
     assert sorted(_lib.EXPORTS) == names
-    assert lib.asgpu_version() == 1
+    assert lib.asgpu_version() == 2
 
 
 def test_struct_sizes_match_header():
@@ -34,7 +34,10 @@ def test_struct_sizes_match_header():
     assert C.sizeof(CMesh) == 48 and C.sizeof(CObjectInstance) == 264 and C.sizeof(CAssemblyInstance) == 264
     assert C.sizeof(CRays) == 56
     assert C.sizeof(_lib.AssemblyItem) == 144 and C.sizeof(_lib.TriangleTreeView) == 80
-    assert C.sizeof(_lib.PathStreamDesc) == 360 and C.sizeof(_lib.PathStreamStats) == 64      # gcc sizeof of the header's structs
+    assert C.sizeof(_lib.PathStreamDesc) == 368 and C.sizeof(_lib.PathStreamStats) == 64      # gcc sizeof of the header's structs
+    assert C.sizeof(_lib.PathStreamProfile) == 48
+    import fuzz_views
+    assert C.sizeof(fuzz_views.SourceObject) == 168
 
 
 def test_null_arguments_are_rejected_with_a_message():

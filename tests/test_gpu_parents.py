@@ -71,9 +71,43 @@ def test_refine_needs_source_geometry(engine):
         isect.refine_and_offset(rays, hits)
 
 
-def test_refine_rejects_moving_triangles(engine):
-    desc, rays, _ = cases.case_mixed()
+@pytest.mark.parametrize("name", ["c4_msc1", "c4_msc2", "c4_msc3", "mixed"])
+def test_moving_triangles_support_planes_and_parents(engine, asref, name):
+    """Moving hits: the support plane is the triangle interpolated at the ray time (a member of the
+    leaf visitor, triangletree.h:232, triangletree.cpp:1468-1469, 1496-1497) and the geometric normal
+    comes from the source vertices interpolated between the poses around that time
+    (shadingpoint.cpp:186-256).  Checked against oracle/_ref, byte for byte."""
+    desc, rays, _ = cases.CASES[name]()
+    r = asref.scene(desc)
     ctx = engine.TraceContext(desc, device=0)
     isect = engine.Intersector(ctx)
-    with pytest.raises(engine.AsgpuError, match="static triangles"):
-        isect.refine_and_offset(rays, isect.trace(rays))
+    ref_hits, ref_planes = r.trace_planes(rays, threads=4)
+    hits = isect.trace(rays, exact=True)
+    assert hits.tobytes() == ref_hits.tobytes()
+    assert isect.support_planes(rays, hits).tobytes() == ref_planes.tobytes()
+    par = isect.refine_and_offset(rays, hits)
+    assert par.tobytes() == r.refine_offset(rays, ref_hits, threads=4).tobytes()
+
+    h = hits["prim_type"] == 2
+    pts = rays.org[h] + hits["t"][h][:, None] * rays.dir[h]
+    nrm = par["geo_normal"][h] / np.linalg.norm(par["geo_normal"][h], axis=1, keepdims=True)
+    bounce = scenes.bounce_rays(pts, nrm, 5, offset=0.0)
+    bounce.time_absolute, bounce.time_normalized = rays.time_absolute[h], rays.time_normalized[h]
+    p = par[h]
+    ref = r.trace_parents(bounce, p, threads=4)
+    assert isect.trace_with_parents(bounce, p, exact=True).tobytes() == ref.tobytes()
+    wide = isect.trace_with_parents(bounce, p)
+    same = wide["tri_slot"] == ref["tri_slot"]
+    assert same.mean() > 0.999 and np.allclose(wide["t"][same], ref["t"][same], rtol=1e-5, atol=0)
+
+
+def test_support_planes_of_static_scenes(engine, asref):
+    desc, rays, _ = cases.case_c3()
+    r = asref.scene(desc)
+    isect = engine.Intersector(engine.TraceContext(desc, device=0))
+    ref_hits, ref_planes = r.trace_planes(rays, threads=4)
+    hits = isect.trace(rays)
+    assert hits.tobytes() == ref_hits.tobytes()
+    planes = isect.support_planes(rays, hits)
+    assert planes.tobytes() == ref_planes.tobytes()
+    assert np.all(planes[hits["prim_type"] != 2] == 0.0)

@@ -182,6 +182,29 @@ def test_blob_export_import_round_trip(engine, orc):
     assert ctx2.info() == ctx.info()
 
 
+def test_corrupted_blob_is_refused_on_import(engine):
+    """The import path runs the flattener's structural checks on the header and the small tables (a
+    truncated or corrupted broadcast payload must not reach the kernels)."""
+    import torch
+    desc, rays, _ = cases.case_c4(1)
+    ctx, isect = make(engine, desc)
+    good = ctx.blob_tensor()
+    torch.cuda.synchronize()
+    header = good[:256].cpu().numpy().copy()
+    trees_off = int(header.view(np.uint64)[5])              # BlobHeader::trees (after 8 uint32 + total_bytes)
+    assert 0 < trees_off < good.numel()
+    for field_offset in (0, 24, 40, 48, 56):                # TreeDesc::bnodes, tris, keys, wnodes, wtris
+        bad = good.clone()
+        huge = torch.tensor(np.array([good.numel() - 8], dtype=np.uint64).view(np.uint8), device=bad.device)
+        bad[trees_off + field_offset: trees_off + field_offset + 8] = huge
+        with pytest.raises(engine.AsgpuError, match="validation"):
+            engine.TraceContext.from_blob(bad, adopt=True)
+    with pytest.raises(engine.AsgpuError):
+        engine.TraceContext.from_blob(good[: good.numel() // 2].clone(), adopt=True)      # truncated
+    ok = engine.TraceContext.from_blob(good, adopt=True)
+    assert engine.Intersector(ok).trace(rays).tobytes() == isect.trace(rays).tobytes()
+
+
 def test_wide_only_and_exact_only_scenes(engine, orc):
     from appleseed_b200 import _lib
     desc, rays, _ = cases.case_c3()

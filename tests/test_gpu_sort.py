@@ -53,3 +53,29 @@ def test_sort_is_a_stable_permutation_by_key(engine, n):
         near = np.linalg.norm(np.diff(o[ok], axis=0), axis=1).mean()
         far = np.linalg.norm(np.diff(rays.org[np.isfinite(rays.org).all(axis=1)], axis=0), axis=1).mean()
         assert near < 0.5 * far
+
+
+def test_sorted_traces_in_flight_on_several_streams(engine):
+    """Two sorted traces on two streams at once: the sort scratch is a stream-ordered allocation of
+    each call, never shared through the scene handle."""
+    import torch
+    desc, rays, _ = cases.case_c3(n=200000)
+    ctx = engine.TraceContext(desc, device=0)
+    isect = engine.Intersector(ctx)
+    a, b = rays.slice(0, 100000), rays.slice(100000, 200000)
+    want_a, want_b = isect.trace(a), isect.trace(b)
+    da, db = engine.DeviceRays.from_host(a, "cuda:0"), engine.DeviceRays.from_host(b, "cuda:0")
+    ha = torch.empty(len(a) * engine.HIT_BYTES, dtype=torch.uint8, device="cuda:0")
+    hb = torch.empty(len(b) * engine.HIT_BYTES, dtype=torch.uint8, device="cuda:0")
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    torch.cuda.synchronize()
+    for _ in range(4):
+        ha.zero_(); hb.zero_()
+        torch.cuda.synchronize()
+        with torch.cuda.stream(s1):
+            isect.trace_device(da, ha, sort=True)
+        with torch.cuda.stream(s2):
+            isect.trace_device(db, hb, sort=True)
+        torch.cuda.synchronize()
+        assert engine.hits_from_tensor(ha, len(a)).tobytes() == want_a.tobytes()
+        assert engine.hits_from_tensor(hb, len(b)).tobytes() == want_b.tobytes()

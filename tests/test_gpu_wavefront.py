@@ -141,7 +141,6 @@ def test_queue_api_round_trip(setup, orc):
     from appleseed_b200.intersector import HIT_BYTES, hits_from_tensor
     _, rays, probes = cases.case_c3()
     rays = rays.slice(0, 5000)
-    rays = type(rays)(rays.org, rays.dir, rays.tmin, rays.tmax, flags=rays.flags)       # queues carry no time
     q = wavefront.RayQueue(ctx, 8192)
     assert len(q) == 0
     q.push(rays.slice(0, 2000))
@@ -202,3 +201,117 @@ def test_stream_with_parent_shading_points(setup, orc):
     # Same image from the exact kernels.
     exact, _, _ = render(wavefront, ctx, cfg, 1 << 20, parents=True, exact=True)
     assert np.array_equal(img, exact)
+
+
+def test_queue_count_beyond_capacity_is_clamped(setup):
+    """A producer that counts past the capacity (enqueue_slot keeps adding on overflow) must not make
+    the trace kernels read or write beyond the queue's arrays: every consumer clamps the count."""
+    import ctypes as C
+    import torch
+    desc, ctx, wavefront, cfg = setup
+    from appleseed_b200 import _lib
+    from appleseed_b200.intersector import HIT_BYTES, Intersector, hits_from_tensor
+    from appleseed_b200.scene import CRays
+    _, rays, probes = cases.case_c3()
+    cap = 4096
+    rays, probes = rays.slice(0, cap), probes.slice(0, cap)
+    for exact in (False, True):
+        q = wavefront.RayQueue(ctx, cap)
+        q.push(rays)
+        cr, ids, count = CRays(), C.c_void_p(), C.c_void_p()
+        assert q.lib.asgpu_queue_device_arrays(q.handle, C.byref(cr), C.byref(ids), C.byref(count)) == 0
+        # Overwrite the device-side count with capacity + 100000.
+        from cuda.bindings import runtime as cudart
+        big = np.array([cap + 100000], dtype=np.uint64)
+        err, = cudart.cudaMemcpy(count.value, big.ctypes.data, 8, cudart.cudaMemcpyKind.cudaMemcpyHostToDevice)
+        assert int(err) == 0
+        guard = 64 * HIT_BYTES
+        hits = torch.full((cap * HIT_BYTES + guard,), 0xAB, dtype=torch.uint8, device="cuda:0")
+        q.trace(hits, exact=exact)
+        torch.cuda.synchronize()
+        assert bool((hits[cap * HIT_BYTES:] == 0xAB).all()), "the trace wrote past the queue capacity"
+        assert hits_from_tensor(hits, cap).tobytes() == Intersector(ctx).trace(rays, exact=exact).tobytes()
+        assert len(q) == cap            # asgpu_queue_count clamps too
+        occ = torch.full((cap + 64,), 0xAB, dtype=torch.uint8, device="cuda:0")
+        q.trace_probe(occ, exact=exact)
+        torch.cuda.synchronize()
+        assert bool((occ[cap:] == 0xAB).all())
+        q.close()
+
+
+def test_queue_rejects_sort_flag(setup):
+    import torch
+    desc, ctx, wavefront, cfg = setup
+    from appleseed_b200 import _lib
+    from appleseed_b200.intersector import HIT_BYTES
+    q = wavefront.RayQueue(ctx, 1024)
+    hits = torch.empty(1024 * HIT_BYTES, dtype=torch.uint8, device="cuda:0")
+    rc = q.lib.asgpu_trace_queue(ctx.handle, q.handle, hits.data_ptr(), _lib.TRACE_SORT, None)
+    assert rc == -3 and "SORT" in _lib.last_error()
+    q.close()
+
+
+@pytest.fixture(scope="module")
+def moving_setup():
+    """The path stream over a DEFORMING mesh (C4-style, msc = 3) under two assembly instances, with a
+    shutter interval: every ray of a path carries the path's time."""
+    from appleseed_b200 import scenes, wavefront
+    from appleseed_b200.intersector import TraceContext
+    desc = scenes.scene_c4(40, 3)
+    lo, hi = scenes.scene_bbox(desc)
+    centre = 0.5 * (lo + hi)
+    diag = float(np.linalg.norm(hi - lo))
+    eye = centre + np.array([0.25, 1.3, 0.9]) * diag * 0.6
+    lights = np.array([[lo[0], hi[1] + 2.0, lo[2]], [hi[0], hi[1] + 2.0, hi[2]]])
+    cfg = dict(width=64, height=48, spp=4, camera_to_world=wavefront.look_at(eye, centre), lights=lights, max_bounces=2,
+               tile_size=16, seed=3, offset_eps=1.0e-6 * diag, shutter_open=0.25, shutter_close=1.5, parents=True)
+    return desc, TraceContext(desc, device=0), wavefront, cfg
+
+
+def test_stream_over_moving_triangles_carries_ray_time(moving_setup, asref):
+    desc, ctx, wavefront, cfg = moving_setup
+    r = asref.scene(desc)
+    img, stats, caps = render(wavefront, ctx, cfg, 1 << 20, capture=1 << 22)
+    closest = [c for c in caps if c.kind == "closest"]
+    probes = [c for c in caps if c.kind == "probe"]
+    assert len(closest) == cfg["max_bounces"] + 1 and stats["surface_hits"] > 1000
+    cam = closest[0]
+    tn, ta = cam.rays.time_normalized, cam.rays.time_absolute
+    assert tn.min() >= 0.0 and tn.max() < 1.0 and len(np.unique(tn)) > 0.9 * len(tn)
+    one = np.float32(1.0)
+    expect = (one - tn) * np.float32(cfg["shutter_open"]) + tn * np.float32(cfg["shutter_close"])     # foundation::lerp in float
+    assert np.array_equal(ta, expect.astype(np.float32))
+    time_of_path = dict(zip(cam.path_ids.tolist(), tn.tolist()))
+    for d, (parent, probe) in enumerate(zip(closest, probes)):
+        # Children inherit their path's time (pathtracer.h:764).
+        for c in (parent, probe):
+            assert np.array_equal(c.rays.time_normalized, np.array([time_of_path[p] for p in c.path_ids.tolist()], dtype=np.float32))
+        ref = r.trace_parents(parent.rays, parent.parents, threads=4)
+        same = parent.results["tri_slot"] == ref["tri_slot"]
+        assert np.array_equal(parent.results["prim_type"], ref["prim_type"]) and same.mean() > 0.999
+        assert parent.results[same].tobytes() == ref[same].tobytes()
+        assert int(((parent.results["prim_type"] == 2) & (parent.results["t"] < 1e-9)).sum()) == 0     # no self-intersection
+        refined = r.refine_offset(parent.rays, parent.results, threads=4)
+        by_path = dict(zip(parent.path_ids.tolist(), range(len(parent.path_ids))))
+        idx = np.array([by_path[p] for p in probe.path_ids.tolist()])
+        assert probe.parents.tobytes() == refined[idx].tobytes()
+        pref = r.trace_probe_parents(probe.rays, probe.parents, threads=4)
+        assert (probe.results == pref).mean() > 0.999
+    # A closed shutter freezes the mesh at time 0: a different image.
+    still, _, _ = render(wavefront, ctx, cfg, 1 << 20, shutter_open=0.0, shutter_close=0.0)
+    assert not np.array_equal(still, img)
+    exact, _, _ = render(wavefront, ctx, cfg, 1 << 20, exact=True)
+    assert np.array_equal(img, exact)
+
+
+def test_stream_profile_times_every_trace_launch(setup):
+    desc, ctx, wavefront, cfg = setup
+    ps = wavefront.PathStream(ctx, wavefront.PathStreamConfig(**cfg), queue_capacity=1 << 20)
+    ps.set_profiling(True)
+    ps.render()
+    prof = ps.profile()
+    assert prof["closest_launches"] == cfg["max_bounces"] + 1 == prof["probe_launches"]
+    assert prof["closest_ms"] > 0 and prof["probe_ms"] > 0 and prof["stage_ms"] > 0
+    ps.clear()
+    assert ps.profile()["closest_launches"] == 0
+    ps.close()
