@@ -84,8 +84,8 @@ int init_device_side(asgpu_scene* s)
     ASGPU_CUDA(cudaGetDeviceProperties(&prop, s->device), "cudaGetDeviceProperties");
     s->sm_count = prop.multiProcessorCount;
     ASGPU_CUDA(cudaMalloc(&s->queue, QueueRing * sizeof(unsigned long long)), "cudaMalloc(queue)");
-    ASGPU_CUDA(cudaMalloc(&s->counters, sizeof(asgpu_counters)), "cudaMalloc(counters)");
-    ASGPU_CUDA(cudaMemset(s->counters, 0, sizeof(asgpu_counters)), "cudaMemset(counters)");
+    ASGPU_CUDA(cudaMalloc(&s->counters, 2 * sizeof(asgpu_counters)), "cudaMalloc(counters)");      // closest-hit bank, any-hit bank
+    ASGPU_CUDA(cudaMemset(s->counters, 0, 2 * sizeof(asgpu_counters)), "cudaMemset(counters)");
     return ASGPU_OK;
 }
 
@@ -643,19 +643,38 @@ int asgpu_sort_rays(asgpu_scene* scene, const asgpu_rays* rays, size_t n, uint32
     return ASGPU_OK;
 }
 
+int asgpu_get_counters_by_kind(asgpu_scene* scene, asgpu_counters* closest, asgpu_counters* probe, int reset)
+{
+    if (!scene) return fail(ASGPU_E_INVALID, "null argument");
+    ASGPU_CUDA(cudaSetDevice(scene->device), "cudaSetDevice");
+    ASGPU_CUDA(cudaDeviceSynchronize(), "cudaDeviceSynchronize");
+    asgpu_counters banks[2];
+    ASGPU_CUDA(cudaMemcpy(banks, scene->counters, sizeof(banks), cudaMemcpyDeviceToHost), "cudaMemcpy(counters)");
+    for (asgpu_counters& b : banks) { b.kernel_launches = scene->launches; b.reserved = 0; }
+    if (closest) *closest = banks[0];
+    if (probe) *probe = banks[1];
+    if (reset)
+    {
+        ASGPU_CUDA(cudaMemset(scene->counters, 0, sizeof(banks)), "cudaMemset(counters)");
+        scene->launches = 0;
+    }
+    return ASGPU_OK;
+}
+
 int asgpu_get_counters(asgpu_scene* scene, asgpu_counters* out, int reset)
 {
     if (!scene || !out) return fail(ASGPU_E_INVALID, "null argument");
-    ASGPU_CUDA(cudaSetDevice(scene->device), "cudaSetDevice");
-    ASGPU_CUDA(cudaDeviceSynchronize(), "cudaDeviceSynchronize");
-    std::memset(out, 0, sizeof(*out));
-    ASGPU_CUDA(cudaMemcpy(out, scene->counters, 6 * sizeof(uint64_t), cudaMemcpyDeviceToHost), "cudaMemcpy(counters)");
-    out->kernel_launches = scene->launches;
-    if (reset)
-    {
-        ASGPU_CUDA(cudaMemset(scene->counters, 0, sizeof(asgpu_counters)), "cudaMemset(counters)");
-        scene->launches = 0;
-    }
+    asgpu_counters closest, probe;
+    const int rc = asgpu_get_counters_by_kind(scene, &closest, &probe, reset);
+    if (rc != ASGPU_OK) return rc;
+    out->rays = closest.rays + probe.rays;
+    out->assembly_nodes_visited = closest.assembly_nodes_visited + probe.assembly_nodes_visited;
+    out->instances_visited = closest.instances_visited + probe.instances_visited;
+    out->triangle_nodes_visited = closest.triangle_nodes_visited + probe.triangle_nodes_visited;
+    out->triangles_tested = closest.triangles_tested + probe.triangles_tested;
+    out->hits = closest.hits + probe.hits;
+    out->kernel_launches = closest.kernel_launches;
+    out->reserved = 0;
     return ASGPU_OK;
 }
 

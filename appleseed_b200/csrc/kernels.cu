@@ -40,6 +40,7 @@ namespace
 {
 
 const int BlockThreads = 128;
+const int CounterBankWords = 8;       // counters: one asgpu_counters-shaped bank for closest-hit launches, one for any-hit launches
 
 struct KernelArgs
 {
@@ -147,7 +148,7 @@ trace_kernel(const KernelArgs args)
         }
     }
 
-    if (COUNT) flush_counters(args.counters, lane, rays_done, stats, hits_found);
+    if (COUNT) flush_counters(args.counters + (ANY ? CounterBankWords : 0), lane, rays_done, stats, hits_found);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -663,7 +664,7 @@ wide_kernel(const KernelArgs args)
         }
     }
 
-    if (COUNT) flush_counters(args.counters, lane, rays_done, stats, hits_found);
+    if (COUNT) flush_counters(args.counters + (ANY ? CounterBankWords : 0), lane, rays_done, stats, hits_found);
 }
 
 // Scheduling knobs of the wide kernel.  Defaults are the measured optima (profiles/README.md, sweeps

@@ -263,6 +263,12 @@ class TraceContext:
         _check(self.lib.asgpu_get_counters(self.handle, C.byref(v), 1 if reset else 0), "asgpu_get_counters")
         return v.as_dict()
 
+    def counters_by_kind(self, reset: bool = False):
+        """(closest-hit counters, any-hit counters) -- the same traversal statistics kept apart."""
+        a, b = _lib.Counters(), _lib.Counters()
+        _check(self.lib.asgpu_get_counters_by_kind(self.handle, C.byref(a), C.byref(b), 1 if reset else 0), "asgpu_get_counters_by_kind")
+        return a.as_dict(), b.as_dict()
+
 
 class Intersector:
     """Batched ``trace`` / ``trace_probe`` on a ``TraceContext``."""

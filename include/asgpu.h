@@ -413,6 +413,9 @@ typedef struct asgpu_counters {
 } asgpu_counters;
 
 int             asgpu_get_counters(asgpu_scene* scene, asgpu_counters* out, int reset);
+/* The same counters kept apart for closest-hit (asgpu_trace*) and any-hit (asgpu_trace_probe*)
+ * launches; either pointer may be NULL.  asgpu_get_counters returns their sum. */
+int             asgpu_get_counters_by_kind(asgpu_scene* scene, asgpu_counters* closest, asgpu_counters* probe, int reset);
 
 /* ------------------------------------------------------------------------------------------
  * Wavefront ray queues: the renderer's recursive per-sample trace

@@ -12,6 +12,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 import subprocess
+import sys
 
 import numpy as np
 
@@ -67,7 +68,7 @@ def build(which: str = "all") -> None:
     """Compile the checkers (``make -C oracle``).  ``_ref`` is only rebuilt where the
     reference tree exists; elsewhere the prebuilt library that travelled is used."""
     target = {"all": "all", "orc": "liboracle.so", "asref": "ref"}[which]
-    subprocess.run(["make", "-s", "-C", _HERE, target], check=True)
+    subprocess.run(["make", "-s", "-C", _HERE, target], check=True, stdout=sys.stderr)      # keep stdout for bench.py's JSON line
 
 
 def available(prefix: str) -> bool:

@@ -30,7 +30,7 @@ def main():
     ap.add_argument("--repeat", type=int, default=2)
     ap.add_argument("--exact", action="store_true")
     args = ap.parse_args()
-    desc = bench.make_scene(args)
+    desc = bench.make_scene(args.workload, args.res)
     ctx = TraceContext(desc, device=0)
     isect = Intersector(ctx)
     dev = "cuda:0"

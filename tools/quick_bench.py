@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--rays", type=int, default=8 << 20)
     ap.add_argument("--res", type=int, default=0)
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--msc", type=int, default=1, help="c4: motion segment count")
     ap.add_argument("--sort", action="store_true", help="also time every wavefront with ASGPU_TRACE_SORT (sort + trace) and the sort alone")
     ap.add_argument("--sweep", action="append", default=[], help="ENV=v1,v2,... (cartesian product of all sweeps)")
     ap.add_argument("--tree-build", default="sah", choices=["sah", "device"], help="device: triangle trees from asgpu_trees_build_on_device (linear BVH)")
@@ -38,7 +39,7 @@ def main():
     settings = [dict(zip([k for k, _ in sweeps], combo)) for combo in itertools.product(*[v for _, v in sweeps])] or [{}]
     for wl in args.workloads.split(","):
         a = argparse.Namespace(workload=wl, res=args.res, rays=args.rays)
-        desc = bench.make_scene(a)
+        desc = bench.make_scene(wl, args.res, args.msc)
         if args.tree_build == "device":
             from appleseed_b200.intersector import HostTrees
             ctx = TraceContext(trees=HostTrees(desc, build_device=0), device=0)
@@ -81,6 +82,7 @@ def main():
         for setting in settings:
             for k, v in setting.items():
                 os.environ[k] = v
+            ctx.lib.asgpu_reload_tuning()       # the knobs are cached per process
             res = {}
             for name, rays, probe in waves:
                 run = (lambda: isect.trace_probe_device(rays, occ)) if probe else (lambda: isect.trace_device(rays, out))
