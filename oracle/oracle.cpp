@@ -1824,6 +1824,32 @@ int orc_kat_ray_aabb(const double bmin[3], const double bmax[3], const double or
     return hit ? 1 : 0;
 }
 
+// The other entry points of rayaabb.h the reference tests: the 3-argument intersect (the SSE2
+// specialisation :192-228 computes the same products and comparisons as the generic code, two lanes
+// at a time), the 4-argument one with its "distance unchanged on a miss" contract (:230-252) and
+// clip (:310-336).  mode 0: io untouched; mode 1: io[0] = distance in / out; mode 2: io[0], io[1] =
+// ray tmin, tmax in / out.
+int orc_kat_ray_aabb_ex(int mode, const double bmin[3], const double bmax[3], const double org[3], const double dir[3], double tmin, double tmax, double* io)
+{
+    Ray r; make_ray(org, dir, tmin, tmax, r);
+    const RayInfo info(r);
+    const double o[3] = { r.org.x, r.org.y, r.org.z };
+    double l1[3], l2[3];
+    for (int a = 0; a < 3; ++a)
+    {
+        const double near_plane = info.sgn[a] ? bmin[a] : bmax[a];      // bbox[1 - sgn]
+        const double far_plane = info.sgn[a] ? bmax[a] : bmin[a];       // bbox[sgn]
+        l1[a] = info.rcp[a] * (near_plane - o[a]);
+        l2[a] = info.rcp[a] * (far_plane - o[a]);
+    }
+    const double t0 = ssemax(l1[2], ssemax(l1[1], ssemax(l1[0], r.tmin)));
+    const double t1 = ssemin(l2[2], ssemin(l2[1], ssemin(l2[0], r.tmax)));
+    if (t0 > t1 || t1 < r.tmin || t0 >= r.tmax) return 0;
+    if (mode == 1) io[0] = ssemax(r.tmin, t0);
+    if (mode == 2) { io[0] = ssemax(r.tmin, t0); io[1] = ssemin(r.tmax, t1); }
+    return 1;
+}
+
 void orc_kat_ray_info(const double dir[3], double rcp[3], uint32_t sgn[3])
 {
     Ray r; const double o[3] = { 0.0, 0.0, 0.0 };

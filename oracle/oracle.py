@@ -138,6 +138,7 @@ class Oracle:
             ("_kat_ray_triangle", [C.c_void_p] * 5 + [C.c_double, C.c_double, C.c_void_p], C.c_int),
             ("_kat_ray_triangle_bool", [C.c_void_p] * 5 + [C.c_double, C.c_double], C.c_int),
             ("_kat_ray_aabb", [C.c_void_p] * 4 + [C.c_double, C.c_double, C.c_void_p], C.c_int),
+            ("_kat_ray_aabb_ex", [C.c_int] + [C.c_void_p] * 4 + [C.c_double, C.c_double, C.c_void_p], C.c_int),
             ("_kat_ray_info", [C.c_void_p] * 3, None),
         ):
             f = getattr(L, p + name)
@@ -174,6 +175,14 @@ class Oracle:
         t = np.zeros(1)
         hit = getattr(self.lib, self.prefix + "_kat_ray_aabb")(*[x.ctypes.data for x in a], tmin, tmax, t.ctypes.data)
         return bool(hit), float(t[0])
+
+    def kat_ray_aabb_ex(self, mode, bmin, bmax, org, dir, tmin, tmax, io):
+        """rayaabb.h: mode 0 = intersect(ray, info, bbox), 1 = intersect(..., distance) with io = [distance],
+        2 = clip(ray, ...) with io = [ray tmin, ray tmax]; io is updated in place; returns the bool."""
+        a = [self._v(x) for x in (bmin, bmax, org, dir)]
+        buf = np.array(io, dtype=np.float64)
+        hit = getattr(self.lib, self.prefix + "_kat_ray_aabb_ex")(mode, *[x.ctypes.data for x in a], tmin, tmax, buf.ctypes.data)
+        return bool(hit), buf
 
     def kat_ray_info(self, dir):
         d = self._v(dir)

@@ -238,6 +238,9 @@ void orc_two_nearest(const void* scene, const orc_rays* rays, size_t n, double* 
     int     prefix##_kat_ray_triangle_bool(const double v0[3], const double v1[3],                  \
                                       const double v2[3], const double org[3],                      \
                                       const double dir[3], double tmin, double tmax);               \
+    int     prefix##_kat_ray_aabb_ex(int mode, const double bmin[3], const double bmax[3],          \
+                                     const double org[3], const double dir[3], double tmin,         \
+                                     double tmax, double* io);                                      \
     int     prefix##_kat_ray_aabb(const double bmin[3], const double bmax[3], const double org[3],  \
                                   const double dir[3], double tmin, double tmax, double* tmin_out); \
     void    prefix##_kat_ray_info(const double dir[3], double rcp[3], uint32_t sgn[3]);

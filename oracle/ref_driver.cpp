@@ -1832,6 +1832,21 @@ int asref_kat_ray_aabb(
     return hit ? 1 : 0;
 }
 
+// The reference's own 3-argument intersect (SSE2 specialisation), 4-argument intersect and clip
+// (rayaabb.h), as test_intersection_rayaabb.cpp calls them.  mode / io: see oracle.cpp.
+int asref_kat_ray_aabb_ex(int mode, const double bmin[3], const double bmax[3], const double org[3], const double dir[3], double tmin, double tmax, double* io)
+{
+    const AABB3d bbox(Vector3d(bmin[0], bmin[1], bmin[2]), Vector3d(bmax[0], bmax[1], bmax[2]));
+    Ray3d ray(Vector3d(org[0], org[1], org[2]), Vector3d(dir[0], dir[1], dir[2]), tmin, tmax);
+    const RayInfo3d ray_info(ray);
+    if (mode == 0) return intersect(ray, ray_info, bbox) ? 1 : 0;
+    if (mode == 1) return intersect(ray, ray_info, bbox, io[0]) ? 1 : 0;
+    ray.m_tmin = io[0]; ray.m_tmax = io[1];
+    const bool hit = clip(ray, ray_info, bbox);
+    io[0] = ray.m_tmin; io[1] = ray.m_tmax;
+    return hit ? 1 : 0;
+}
+
 void asref_kat_ray_info(const double dir[3], double rcp[3], uint32_t sgn[3])
 {
     const Ray3d ray(Vector3d(0.0), Vector3d(dir[0], dir[1], dir[2]));

@@ -19,8 +19,9 @@ RAY_TRIANGLE = [
     ("quad_diagonal",                 [0.0, 1.0, 0.0],  [0.0, -1.0, 0.0], 0.0, DBL_MAX, True,  (1.0, 0.0, 0.5)),
 ]
 
-# foundation/meta/tests/test_intersection_rayaabb.cpp:47-346 (3- and 4-argument intersect; the
-# clip() cases :349-419 are not on the path).  (name, bmin, bmax, org, dir, tmin, tmax, hit, distance)
+# foundation/meta/tests/test_intersection_rayaabb.cpp: all 34 cases.  First the 17 three-argument
+# cases (:47-214; the distance column is what the 4-argument overload returns on the same input).
+# (name, bmin, bmax, org, dir, tmin, tmax, hit, distance)
 _U = ([-1.0] * 3, [1.0] * 3)
 _P = ([0.0] * 3, [1.0] * 3)
 RAY_AABB = [
@@ -41,6 +42,32 @@ RAY_AABB = [
     ("tmax_equal_hit",      *_U, [0, 0, 2],  [0, 0, -1], 0.0, 1.0,     False, None),
     ("tmin_larger_than_hit", *_U, [0, 0, 2], [0, 0, -1], 3.1, 10.0,    False, None),
     ("tmax_smaller_than_hit", *_U, [0, 0, 2], [0, 0, -1], 0.0, 0.9,    False, None),
+]
+
+# The 11 four-argument cases (:217-346: the distance argument starts at 42 and must be left alone on
+# a miss) and the 6 clip cases (:349-419: ray.m_tmin / m_tmax updated on a hit, untouched on a miss).
+# (name, bmin, bmax, org, dir, tmin, tmax, hit, distance after the call)
+RAY_AABB_DISTANCE = [
+    ("not_piercing_distance_unchanged", *_U, [2, 0, 2], [0, 0, -1], 0.0, DBL_MAX, False, 42.0),
+    ("embedded_pos_x_face_distance", *_P, [1, 0, 2], [0, 0, -1], 0.0, DBL_MAX, True, 1.0),
+    ("embedded_neg_x_face_distance", *_P, [0, 0, 2], [0, 0, -1], 0.0, DBL_MAX, True, 1.0),
+    ("embedded_pos_y_face_distance", *_P, [2, 1, 0], [-1, 0, 0], 0.0, DBL_MAX, True, 1.0),
+    ("embedded_neg_y_face_distance", *_P, [2, 0, 0], [-1, 0, 0], 0.0, DBL_MAX, True, 1.0),
+    ("embedded_pos_z_face_distance", *_P, [0, 2, 1], [0, -1, 0], 0.0, DBL_MAX, True, 1.0),
+    ("embedded_neg_z_face_distance", *_P, [0, 2, 0], [0, -1, 0], 0.0, DBL_MAX, True, 1.0),
+    ("tmin_equal_hit_distance", *_U, [0, 0, 2], [0, 0, -1], 3.0, 10.0, True, 3.0),
+    ("tmax_equal_hit_distance_unchanged", *_U, [0, 0, 2], [0, 0, -1], 0.0, 1.0, False, 42.0),
+    ("tmin_larger_than_hit_distance_unchanged", *_U, [0, 0, 2], [0, 0, -1], 3.1, 10.0, False, 42.0),
+    ("tmax_smaller_than_hit_distance_unchanged", *_U, [0, 0, 2], [0, 0, -1], 0.0, 0.9, False, 42.0),
+]
+# (name, bmin, bmax, org, dir, tmin, tmax, hit, ray tmin after, ray tmax after)
+RAY_AABB_CLIP = [
+    ("clip_not_piercing", *_U, [2, 0, 2], [0, 0, -1], 0.0, DBL_MAX, False, 0.0, DBL_MAX),
+    ("clip_pos_z_face_middle", *_U, [0, 0, 2], [0, 0, -1], 0.0, DBL_MAX, True, 1.0, 3.0),
+    ("clip_tmin_equal_hit", *_U, [0, 0, 2], [0, 0, -1], 3.0, 10.0, True, 3.0, 3.0),
+    ("clip_tmax_equal_hit", *_U, [0, 0, 2], [0, 0, -1], 0.0, 1.0, False, 0.0, 1.0),
+    ("clip_tmin_larger_than_hit", *_U, [0, 0, 2], [0, 0, -1], 3.1, 10.0, False, 3.1, 10.0),
+    ("clip_tmax_smaller_than_hit", *_U, [0, 0, 2], [0, 0, -1], 0.0, 0.9, False, 0.0, 0.9),
 ]
 
 # foundation/meta/tests/test_ray.cpp:59-83.

@@ -267,7 +267,7 @@ def test_full_size_c2_properties(engine, orc):
     short.tmax = exact["t"][hit][:500_000] * (1.0 - 1e-9)
     assert isect.trace_probe(short).sum() == 0
     # (5) oracle on a sample
-    idx = np.arange(0, len(rays), 40)
+    idx = np.arange(0, len(rays), 16)            # 250 000 rays
     o = orc.scene(desc)
     sub = rays.take(idx)
     ref = o.trace(sub, threads=8)
@@ -343,13 +343,79 @@ def test_full_size_c3_properties(engine, orc):
     # Parent shading points at scale: refined points sit within a few ulps of the hit point.
     par = isect.refine_and_offset(rays, exact)
     assert np.all(par["assembly_instance"][hit] == exact["assembly_instance"][hit]) and np.all(par["assembly_instance"][~hit] == 0xFFFFFFFF)
-    idx = np.arange(0, len(rays), 100)
+    # Oracle on every 8th ray: 250 000 closest-hit rays, as many shadow probes from their hit points
+    # (Tracer::trace_between's tmax), and the parent records of the hits.
+    idx = np.arange(0, len(rays), 8)
     o = orc.scene(desc)
     sub = rays.take(idx)
-    ref = o.trace(sub, threads=8)
+    ref = o.trace(sub, threads=16)
+    assert exact[idx].tobytes() == ref.tobytes()
+    stats = parity.compare_hits(o, sub, wide[idx], ref)
+    assert stats["rays"] == 250_000
+    assert par[idx].tobytes() == o.refine_offset(sub, ref, threads=16).tobytes()
+    import bench
+    probes = bench.shadow_rays_from(desc, sub, ref, 3)
+    pref = o.trace_probe(probes, threads=16)
+    assert 0.05 < pref.mean() < 0.95
+    assert np.array_equal(isect.trace_probe(probes, exact=True), pref)
+    parity.compare_probes(o, probes, isect.trace_probe(probes), pref)
+
+    # A C5 frame on the same scene (480 x 270 x 1 spp, parents carried): every wavefront of the path
+    # stream against the oracle's trace_parents / trace_probe_parents on the identical rays.
+    from appleseed_b200 import wavefront
+    args = type("A", (), {"width": 480, "height": 270, "spp": 1, "no_parents": False})()
+    cfg = bench.c5_config(args, desc)
+    ps = wavefront.PathStream(ctx, wavefront.PathStreamConfig(**cfg), queue_capacity=1 << 20)
+    ps.capture(1 << 23)
+    ps.render()
+    caps, st = ps.captured(), ps.stats()
+    ps.close()
+    assert st["camera_rays"] == 480 * 270 and st["surface_hits"] > 50_000 and len(caps) == 8
+    for c in caps:
+        if c.kind == "closest":
+            cref = o.trace_parents(c.rays, c.parents, threads=16)
+            s5 = parity.compare_hits(o, c.rays, c.results, cref)
+            assert s5["identity_equal"] >= s5["rays"] - s5["tie_exempt"]
+            assert int(((c.results["prim_type"] == 2) & (c.results["t"] < 1e-9)).sum()) == 0
+        else:
+            parity.compare_probes(o, c.rays, c.results, o.trace_probe_parents(c.rays, c.parents, threads=16))
+
+
+@pytest.mark.parametrize("msc", [1, 3])
+def test_full_size_c4_properties(engine, orc, msc):
+    """BASELINE config C4 at full size (2 000 000 moving triangles, 2 and 4 poses): the two
+    independent kernels agree everywhere, probes agree with closest hit, oracle on a sample."""
+    from appleseed_b200 import scenes
+    desc = scenes.scene_c4(1000, msc)
+    ctx, isect = make(engine, desc)
+    info = ctx.info()
+    assert info["triangle_count"] == 2_000_000 == info["moving_triangle_count"]
+    lo, hi = scenes.scene_bbox(desc)
+    ext = hi - lo
+    rays = scenes.uniform_sphere_rays(2_000_000, lo - 0.02 * ext, hi + 0.02 * ext, 31 + msc, time=True)
+    wide = isect.trace(rays)
+    exact = isect.trace(rays, exact=True)
+    assert np.array_equal(wide["prim_type"], exact["prim_type"])
+    hit = exact["prim_type"] == 2
+    assert 0.1 < hit.mean() < 0.9
+    assert np.allclose(wide["t"][hit], exact["t"][hit], rtol=1e-5, atol=0.0)
+    assert (wide["tri_slot"] == exact["tri_slot"]).mean() > 0.9999
+    assert set(np.unique(exact["motion_segment"][hit])) == set(range(msc))        # every pose interval is used
+    occ = isect.trace_probe(rays)
+    assert np.array_equal(occ.astype(bool), hit)
+    assert np.array_equal(isect.trace_probe(rays, exact=True), occ)
+    idx = np.arange(0, len(rays), 10)
+    o = orc.scene(desc)
+    sub = rays.take(idx)
+    ref = o.trace(sub, threads=16)
     assert exact[idx].tobytes() == ref.tobytes()
     parity.compare_hits(o, sub, wide[idx], ref)
-    assert par[idx].tobytes() == o.refine_offset(sub, ref, threads=8).tobytes()
+    parity.compare_probes(o, sub, occ[idx], o.trace_probe(sub, threads=16))
+    # Parent records and support planes of moving hits at scale.
+    par = isect.refine_and_offset(sub, ref)
+    assert par.tobytes() == o.refine_offset(sub, ref, threads=16).tobytes()
+    assert isect.support_planes(sub, ref).tobytes() == o.support_planes(sub, ref, threads=16).tobytes()
+    ctx.close()
 
 
 @pytest.mark.parametrize("name", ["c3", "mixed"])

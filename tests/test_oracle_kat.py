@@ -31,6 +31,35 @@ def test_ray_aabb(oracle, case):
         assert abs(t - dist) <= 1e-14
 
 
+@pytest.mark.parametrize("case", kat.RAY_AABB, ids=[c[0] for c in kat.RAY_AABB])
+def test_ray_aabb_three_argument_overload(oracle, case):
+    _, bmin, bmax, org, d, tmin, tmax, expect_hit, _ = case
+    hit, _ = oracle.kat_ray_aabb_ex(0, bmin, bmax, org, d, tmin, tmax, [0.0])
+    assert hit == expect_hit
+
+
+@pytest.mark.parametrize("case", kat.RAY_AABB_DISTANCE, ids=[c[0] for c in kat.RAY_AABB_DISTANCE])
+def test_ray_aabb_distance_contract(oracle, case):
+    _, bmin, bmax, org, d, tmin, tmax, expect_hit, dist = case
+    hit, io = oracle.kat_ray_aabb_ex(1, bmin, bmax, org, d, tmin, tmax, [42.0])
+    assert hit == expect_hit
+    if hit:
+        assert abs(io[0] - dist) <= 1e-14
+    else:
+        assert io[0] == 42.0                 # EXPECT_EQ(42.0, distance)
+
+
+@pytest.mark.parametrize("case", kat.RAY_AABB_CLIP, ids=[c[0] for c in kat.RAY_AABB_CLIP])
+def test_ray_aabb_clip(oracle, case):
+    _, bmin, bmax, org, d, tmin, tmax, expect_hit, tmin_after, tmax_after = case
+    hit, io = oracle.kat_ray_aabb_ex(2, bmin, bmax, org, d, tmin, tmax, [tmin, tmax])
+    assert hit == expect_hit
+    if hit:
+        assert abs(io[0] - tmin_after) <= 1e-14 and abs(io[1] - tmax_after) <= 1e-14
+    else:
+        assert io[0] == tmin_after and io[1] == tmax_after
+
+
 def test_ray_info(oracle):
     d, rcp, sgn = kat.RAY_INFO
     got_rcp, got_sgn = oracle.kat_ray_info(d)
