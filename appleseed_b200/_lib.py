@@ -31,7 +31,7 @@ EXPORTS = [
     "asgpu_path_stream_read_image", "asgpu_path_stream_clear", "asgpu_path_stream_get_stats",
     "asgpu_path_stream_capture", "asgpu_path_stream_capture_count", "asgpu_path_stream_capture_get",
     "asgpu_trees_build_on_device", "asgpu_trees_device_seconds",
-    "asgpu_get_counters_by_kind", "asgpu_get_support_planes", "asgpu_pin_host", "asgpu_unpin_host", "asgpu_reload_tuning",
+    "asgpu_get_counters_by_kind", "asgpu_get_lane_profile", "asgpu_get_support_planes", "asgpu_pin_host", "asgpu_unpin_host", "asgpu_reload_tuning",
     "asgpu_path_stream_capture_get_times", "asgpu_path_stream_set_profiling", "asgpu_path_stream_get_profile",
 ]
 
@@ -86,6 +86,14 @@ class Counters(C.Structure):
         ("triangle_nodes_visited", C.c_uint64), ("triangles_tested", C.c_uint64), ("hits", C.c_uint64),
         ("kernel_launches", C.c_uint64), ("reserved", C.c_uint64),
     ]
+
+    def as_dict(self):
+        return {k: int(getattr(self, k)) for k, _ in self._fields_ if k != "reserved"}
+
+
+class LaneProfile(C.Structure):
+    _fields_ = [(k, C.c_uint64) for k in ("rounds", "testing", "no_ray", "traversed", "held", "want_enter", "found_leaf", "nothing_to_fetch",
+                                          "iterations", "batched_entries", "lanes_entered", "refills", "lanes_refilled")] + [("reserved", C.c_uint64 * 3)]
 
     def as_dict(self):
         return {k: int(getattr(self, k)) for k, _ in self._fields_ if k != "reserved"}
@@ -170,6 +178,7 @@ def load() -> C.CDLL:
     lib.asgpu_trace_probe_host.argtypes = [C.c_void_p, P(CRays), C.c_size_t, C.c_void_p, C.c_uint32]
     lib.asgpu_get_counters.argtypes = [C.c_void_p, P(Counters), C.c_int]
     lib.asgpu_get_counters_by_kind.argtypes = [C.c_void_p, P(Counters), P(Counters), C.c_int]
+    lib.asgpu_get_lane_profile.argtypes = [C.c_void_p, P(LaneProfile), P(LaneProfile)]
     lib.asgpu_trees_get_source_geometry.argtypes = [C.c_void_p, C.c_int, P(SourceGeometry)]
     lib.asgpu_scene_create_ex.restype = C.c_void_p
     lib.asgpu_scene_create_ex.argtypes = [P(TriangleTreeView), C.c_uint32, P(AssemblyTreeView), P(SourceGeometry), C.c_uint32, C.c_int]

@@ -53,6 +53,9 @@ struct asgpu_trees
 namespace
 {
 
+// Device counters: a closest-hit and an any-hit bank of traversal counters, then the two lane profiles.
+const size_t CounterBytes = 2 * sizeof(asgpu_counters) + 2 * sizeof(asgpu_lane_profile);
+
 void make_view(asgpu_scene* s)
 {
     s->view.blob = s->blob;
@@ -84,8 +87,8 @@ int init_device_side(asgpu_scene* s)
     ASGPU_CUDA(cudaGetDeviceProperties(&prop, s->device), "cudaGetDeviceProperties");
     s->sm_count = prop.multiProcessorCount;
     ASGPU_CUDA(cudaMalloc(&s->queue, QueueRing * sizeof(unsigned long long)), "cudaMalloc(queue)");
-    ASGPU_CUDA(cudaMalloc(&s->counters, 2 * sizeof(asgpu_counters)), "cudaMalloc(counters)");      // closest-hit bank, any-hit bank
-    ASGPU_CUDA(cudaMemset(s->counters, 0, 2 * sizeof(asgpu_counters)), "cudaMemset(counters)");
+    ASGPU_CUDA(cudaMalloc(&s->counters, CounterBytes), "cudaMalloc(counters)");
+    ASGPU_CUDA(cudaMemset(s->counters, 0, CounterBytes), "cudaMemset(counters)");
     return ASGPU_OK;
 }
 
@@ -655,9 +658,22 @@ int asgpu_get_counters_by_kind(asgpu_scene* scene, asgpu_counters* closest, asgp
     if (probe) *probe = banks[1];
     if (reset)
     {
-        ASGPU_CUDA(cudaMemset(scene->counters, 0, sizeof(banks)), "cudaMemset(counters)");
+        ASGPU_CUDA(cudaMemset(scene->counters, 0, CounterBytes), "cudaMemset(counters)");
         scene->launches = 0;
     }
+    return ASGPU_OK;
+}
+
+int asgpu_get_lane_profile(asgpu_scene* scene, asgpu_lane_profile* closest, asgpu_lane_profile* probe)
+{
+    if (!scene) return fail(ASGPU_E_INVALID, "null argument");
+    ASGPU_CUDA(cudaSetDevice(scene->device), "cudaSetDevice");
+    ASGPU_CUDA(cudaDeviceSynchronize(), "cudaDeviceSynchronize");
+    asgpu_lane_profile banks[2];
+    static_assert(sizeof(banks) == CounterBytes - 2 * sizeof(asgpu_counters), "lane profile banks");
+    ASGPU_CUDA(cudaMemcpy(banks, reinterpret_cast<const uint8_t*>(scene->counters) + 2 * sizeof(asgpu_counters), sizeof(banks), cudaMemcpyDeviceToHost), "cudaMemcpy(lane profile)");
+    if (closest) *closest = banks[0];
+    if (probe) *probe = banks[1];
     return ASGPU_OK;
 }
 

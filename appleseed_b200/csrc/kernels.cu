@@ -40,6 +40,7 @@ namespace
 {
 
 const int BlockThreads = 128;
+const int LaneProfileWords = 16;      // ... followed by two lane-profile banks (closest, any hit) of the wide kernels' COUNT instantiations
 const int CounterBankWords = 8;       // counters: one asgpu_counters-shaped bank for closest-hit launches, one for any-hit launches
 
 struct KernelArgs
@@ -65,7 +66,6 @@ struct KernelArgs
     int                 enter_late;         // enter assembly instances once per iteration, all lanes together
     int                 enter_threshold;    // ... once this many lanes want to
     int                 enter_min_busy;     // ... or fewer lanes than this can advance without entering
-    int                 push_early;         // closest hit: queue leaf triangles at once and keep walking (see wide_kernel)
 };
 
 __device__ __forceinline__ void store_hit(asgpu_hit* out, const SceneView& s, const double t, const Hit& hit, const bool found, const bool raw_item)
@@ -171,7 +171,6 @@ struct WideShared
     unsigned long long  pose_base[BlockThreads];        // blob offset of its pose pool
     unsigned long long  best[BlockThreads];             // ordered key of the nearest hit of the running batch
     unsigned long long  queue[BlockThreads / 32][QueueSlots];
-    unsigned            queue_tail[BlockThreads / 32];  // candidates waiting in each warp's queue (shared so that lanes can claim slots on their own)
     uint32_t            flags[BlockThreads];
     float               time_n[BlockThreads];
     float               hit_u[BlockThreads], hit_v[BlockThreads];
@@ -325,9 +324,6 @@ wide_kernel(const KernelArgs args)
     const unsigned warp_thread0 = tid - lane;
     const unsigned lanes_below = (1u << lane) - 1u;
     unsigned long long* queue = sm.queue[tid >> 5];
-    unsigned* queue_tail = &sm.queue_tail[tid >> 5];
-    if (lane == 0) *queue_tail = 0;
-    __syncwarp();
     const SceneView& s = args.scene;
     const uint8_t* blob = s.blob;
     const unsigned long long n = args.n_dev ? min(*args.n_dev, args.n) : args.n;     // clamped: see trace_kernel
@@ -336,6 +332,10 @@ wide_kernel(const KernelArgs args)
 
     Stats stats; stats.top_nodes = stats.instances = stats.nodes = stats.triangles = 0;
     unsigned rays_done = 0, hits_found = 0;
+    // COUNT only: where the lane slots of the node-test rounds go (asgpu_get_lane_profile).
+    unsigned prof[LaneProfileWords];
+    #pragma unroll
+    for (int k = 0; k < LaneProfileWords; ++k) prof[k] = 0;
 
     // Per-lane traversal cursor.
     WideRay w;
@@ -437,6 +437,7 @@ wide_kernel(const KernelArgs args)
         if (idle != 0 && !exhausted && (__popc(idle) >= args.refill_threshold || idle == 0xFFFFFFFFu))
         {
             const int leader = __ffs(idle) - 1;
+            if (COUNT) { prof[11] += 1; prof[12] += __popc(idle); }
             unsigned long long base = 0;
             if (lane == leader) base = atomicAdd(args.queue, static_cast<unsigned long long>(__popc(idle)));
             base = __shfl_sync(0xFFFFFFFFu, base, leader);
@@ -476,11 +477,25 @@ wide_kernel(const KernelArgs args)
         // triangles (most node tests find none), so the warp-level bookkeeping below (refill,
         // gather, flush, pick-up) is paid once per `max_steps` node tests instead of once per test.
         // The extra rounds only run while enough lanes can still advance.
+        if (COUNT) prof[8] += 1;                        // loop iterations
         uint32_t pending = 0, tri_first = 0;            // leaf triangles found by this iteration's node tests
         bool held = false;                              // this lane cannot advance before the queue drains
         bool want_enter = false;                        // this lane's next move is to enter an assembly instance
         for (int round = 0; ; ++round)
         {
+        if (COUNT)
+        {
+            // One round = 32 lane slots: how many test a node, and why the others do not.
+            const bool can = active && !traversed && !held && !want_enter && pending == 0;
+            prof[0] += 1;
+            prof[1] += __popc(__ballot_sync(0xFFFFFFFFu, can && fetch != None));
+            prof[2] += __popc(__ballot_sync(0xFFFFFFFFu, !active));
+            prof[3] += __popc(__ballot_sync(0xFFFFFFFFu, active && traversed));
+            prof[4] += __popc(__ballot_sync(0xFFFFFFFFu, active && !traversed && held));
+            prof[5] += __popc(__ballot_sync(0xFFFFFFFFu, active && !traversed && !held && want_enter));
+            prof[6] += __popc(__ballot_sync(0xFFFFFFFFu, active && !traversed && !held && !want_enter && pending != 0));
+            prof[7] += __popc(__ballot_sync(0xFFFFFFFFu, can && fetch == None));
+        }
         if (active && !traversed && !held && !want_enter && pending == 0)
         {
             if (fetch != None)
@@ -491,38 +506,7 @@ wide_kernel(const KernelArgs args)
                 const uint8_t* np = wnodes + static_cast<uint64_t>(fetch) * sizeof(WNode);
                 wide_node_test(np, LEAN ? np + 32 : qbase + static_cast<uint64_t>(fetch) * qstride, w, args.unit_bits, child_base, tri_base, nmask, tmask);
                 ngroup.x = child_base; ngroup.y = nmask;
-                if (cur_item != None)
-                {
-                    if (!ANY && args.push_early && tmask != 0)
-                    {
-                        // Closest hit: claim queue slots for the leaf triangles right away and keep
-                        // walking; the ray's tmax shrinks a little later (at the next batch test), which
-                        // costs a few node visits and saves the lane from idling until the gather.
-                        const unsigned count = __popc(tmask);
-                        const unsigned pos = atomicAdd(queue_tail, count);
-                        if (pos + count <= QueueSlots)
-                        {
-                            const unsigned long long base = (static_cast<unsigned long long>(tri_base) << 5) | lane;
-                            unsigned at = pos;
-                            uint32_t bits = tmask;
-                            while (bits != 0)
-                            {
-                                const int bit = high_bit(bits);
-                                bits &= ~(1u << bit);
-                                queue[at++] = base + (static_cast<unsigned long long>(bit) << 5);
-                            }
-                            waiting = true;
-                        }
-                        else
-                        {
-                            // No room (all claims of one instruction are handed out before any is returned:
-                            // the overflowing ones are the last): through the gather below.
-                            atomicSub(queue_tail, count);
-                            pending = tmask; tri_first = tri_base;
-                        }
-                    }
-                    else { pending = tmask; tri_first = tri_base; }
-                }
+                if (cur_item != None) { pending = tmask; tri_first = tri_base; }
                 else { tgroup.x = tri_base; tgroup.y = tmask; }
                 fetch = None;
             }
@@ -585,12 +569,6 @@ wide_kernel(const KernelArgs args)
         if (__popc(__ballot_sync(0xFFFFFFFFu, active && !traversed && !held && !want_enter && pending == 0)) < args.step_threshold) break;
         }
 
-        if (!ANY && args.push_early)
-        {
-            __syncwarp();                               // claims and entries of this iteration's rounds are visible
-            queued = *queue_tail;
-        }
-
         // ---- enter assembly instances: every lane that reached one in this iteration, together ------
         if (!LEAN)
         {
@@ -600,6 +578,7 @@ wide_kernel(const KernelArgs args)
                 // Enter when enough lanes wait for it, or when too few lanes could go on without.
                 bool go = __popc(want) >= args.enter_threshold;
                 if (!go) go = __popc(__ballot_sync(0xFFFFFFFFu, active && !traversed && !held && !want_enter)) < args.enter_min_busy;
+                if (COUNT && go) { prof[9] += 1; prof[10] += __popc(want); }
                 if (go && want_enter) enter_instance();
             }
         }
@@ -676,12 +655,6 @@ wide_kernel(const KernelArgs args)
             }
         }
         if (queued == 0) waiting = false;
-        if (!ANY && args.push_early)
-        {
-            if (lane == 0) *queue_tail = queued;
-            __syncwarp();
-        }
-
         // ---- pick up the results, retire finished rays ---------------------------------------------
         if (active)
         {
@@ -711,7 +684,16 @@ wide_kernel(const KernelArgs args)
         }
     }
 
-    if (COUNT) flush_counters(args.counters + (ANY ? CounterBankWords : 0), lane, rays_done, stats, hits_found);
+    if (COUNT)
+    {
+        flush_counters(args.counters + (ANY ? CounterBankWords : 0), lane, rays_done, stats, hits_found);
+        if (lane == 0)
+        {
+            #pragma unroll
+            for (int k = 0; k < LaneProfileWords; ++k)
+                if (prof[k]) atomicAdd(args.counters + 2 * CounterBankWords + (ANY ? LaneProfileWords : 0) + k, static_cast<unsigned long long>(prof[k]));
+        }
+    }
 }
 
 // Scheduling knobs of the wide kernel.  Defaults are the measured optima (profiles/README.md, sweeps
@@ -719,11 +701,11 @@ wide_kernel(const KernelArgs args)
 // prefer fuller refills and more steps per iteration; instanced scenes re-do the set-up on every
 // instance entry and prefer to refill earlier.  ASGPU_REFILL / ASGPU_FLUSH / ASGPU_STALL /
 // ASGPU_STEPS / ASGPU_STEPTHR / ASGPU_PREFETCH override them for experiments.
-struct Tuning { int refill, flush, stall, prefetch, steps, step_threshold, enter_late, enter_threshold, enter_min_busy, push_early; };
+struct Tuning { int refill, flush, stall, prefetch, steps, step_threshold, enter_late, enter_threshold, enter_min_busy; };
 
 Tuning read_tuning(const bool single_instance)
 {
-    Tuning v = { 8, 16, 16, 0, 3, 8, 1, 6, 8, 0 };           // prefetch: measured neutral (C2) to -5 % (C3 probes), off
+    Tuning v = { 8, 16, 16, 0, 3, 8, 1, 6, 8 };              // prefetch: measured neutral (C2) to -5 % (C3 probes), off
     if (single_instance) { v.refill = 22; v.flush = 24; v.stall = 24; v.steps = 4; v.enter_late = 0; }
     if (const char* e = getenv("ASGPU_REFILL")) v.refill = atoi(e);
     if (const char* e = getenv("ASGPU_FLUSH")) v.flush = atoi(e);
@@ -734,7 +716,6 @@ Tuning read_tuning(const bool single_instance)
     if (const char* e = getenv("ASGPU_ENTERLATE")) v.enter_late = atoi(e);
     if (const char* e = getenv("ASGPU_ENTERTHR")) v.enter_threshold = atoi(e);
     if (const char* e = getenv("ASGPU_ENTERBUSY")) v.enter_min_busy = atoi(e);
-    if (const char* e = getenv("ASGPU_PUSHEARLY")) v.push_early = atoi(e);
     if (v.refill < 1) v.refill = 1;
     if (v.flush < 1) v.flush = 1;
     if (v.stall < 1) v.stall = 1;
@@ -872,7 +853,6 @@ int launch_trace(
     args.enter_late = knobs.enter_late;
     args.enter_threshold = knobs.enter_threshold;
     args.enter_min_busy = knobs.enter_min_busy;
-    args.push_early = knobs.push_early;
 
     cudaError_t err = cudaMemsetAsync(queue, 0, sizeof(unsigned long long), stream);
     if (err != cudaSuccess) return static_cast<int>(err);

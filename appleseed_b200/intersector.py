@@ -263,6 +263,12 @@ class TraceContext:
         _check(self.lib.asgpu_get_counters(self.handle, C.byref(v), 1 if reset else 0), "asgpu_get_counters")
         return v.as_dict()
 
+    def lane_profile(self):
+        """(closest-hit, any-hit) ``asgpu_lane_profile`` dicts of the counters launches so far."""
+        a, b = _lib.LaneProfile(), _lib.LaneProfile()
+        _check(self.lib.asgpu_get_lane_profile(self.handle, C.byref(a), C.byref(b)), "asgpu_get_lane_profile")
+        return a.as_dict(), b.as_dict()
+
     def counters_by_kind(self, reset: bool = False):
         """(closest-hit counters, any-hit counters) -- the same traversal statistics kept apart."""
         a, b = _lib.Counters(), _lib.Counters()

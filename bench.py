@@ -298,6 +298,16 @@ def bytes_per_ray(per_ray: dict, ray_in: float, out_bytes: float, moving: bool) 
     return b
 
 
+def lane_shares(lp: dict) -> dict:
+    """asgpu_lane_profile as percentages of the lane slots of the node-test rounds."""
+    slots = max(1, 32 * lp["rounds"])
+    out = {k: round(100.0 * lp[k] / slots, 1) for k in ("testing", "no_ray", "traversed", "held", "want_enter", "found_leaf", "nothing_to_fetch")}
+    out.update({"rounds_per_iteration": round(lp["rounds"] / max(1, lp["iterations"]), 2),
+                "lanes_per_batched_entry": round(lp["lanes_entered"] / max(1, lp["batched_entries"]), 1),
+                "lanes_per_refill": round(lp["lanes_refilled"] / max(1, lp["refills"]), 1)})
+    return out
+
+
 def per_ray_of(c: dict) -> dict:
     r = max(1, c["rays"])
     return {"top_nodes": c["assembly_nodes_visited"] / r, "instances": c["instances_visited"] / r, "nodes": c["triangle_nodes_visited"] / r,
@@ -526,6 +536,7 @@ def batch_figures(D: Dist, workload: str, args, desc, ctx, isect, timing, steps:
     ctx.counters(reset=True)
     for (_, b), o in zip(batches, outs):
         isect.trace_device(b.dev, o, counters=True)
+    lanes = lane_shares(ctx.lane_profile()[0])
     per_ray = per_ray_of(ctx.counters(reset=True))
     probe_per_ray = None
     if probe_batch is not None:
@@ -542,7 +553,7 @@ def batch_figures(D: Dist, workload: str, args, desc, ctx, isect, timing, steps:
         "workload": workload_name(workload, args, msc), "value": total_rays / ms_step / 1e3, "unit": UNIT, "ms_per_step": ms_step,
         "rays_per_step": total_rays, "rays_per_step_per_gpu": rays_step,
         "batches": {label: {"rays": b.n, "ms": round(m, 4), "mrays_s": round(b.n / m / 1e3, 1)} for (label, b), m in zip(batches, ms)},
-        "per_ray": {k: round(v, 3) for k, v in per_ray.items()},
+        "per_ray": {k: round(v, 3) for k, v in per_ray.items()}, "lane_slots_pct": lanes,
         "scene": {k: info[k] for k in ("triangle_count", "moving_triangle_count", "instance_count", "wide_node_count", "binary_node_count", "blob_bytes")},
         "timing": timing, "launches": steps * len(batches), "clocks": clocks,
         "l2": "inputs larger than L2 (%.0f MB of rays + %.0f MB scene blob per step vs 126 MB L2)" % (h2d / 1e6, info["blob_bytes"] / 1e6),
@@ -752,6 +763,7 @@ def run_gpu_c5(args):
     psc = PathStream(ctx, PathStreamConfig(**{**cfg, "counters": True}), queue_capacity=capacity)
     ctx.counters(reset=True)
     psc.render(tiles[: max(1, len(tiles) // 8)])
+    lp_closest, lp_probe = ctx.lane_profile()
     c_closest, c_probe = ctx.counters_by_kind(reset=True)
     psc.close()
     pr_closest, pr_probe = per_ray_of(c_closest), per_ray_of(c_probe)
@@ -787,6 +799,7 @@ def run_gpu_c5(args):
                 "scene": {k: info[k] for k in ("triangle_count", "instance_count", "wide_node_count", "binary_node_count", "blob_bytes")},
                 "timing": timing,
                 "per_ray_closest": {k: round(v, 3) for k, v in pr_closest.items()}, "per_ray_probe": {k: round(v, 3) for k, v in pr_probe.items()},
+                "lane_slots_closest_pct": lane_shares(lp_closest), "lane_slots_probe_pct": lane_shares(lp_probe),
                 "rank0_device_ms_per_frame": {"closest_trace": round(prof["closest_ms"] / args.steps, 3), "probe_trace": round(prof["probe_ms"] / args.steps, 3),
                                               "refine_and_offset": round(prof["refine_ms"] / args.steps, 3),
                                               "generate_shade_accumulate": round(prof["stage_ms"] / args.steps, 3)},

@@ -417,6 +417,26 @@ int             asgpu_get_counters(asgpu_scene* scene, asgpu_counters* out, int 
  * launches; either pointer may be NULL.  asgpu_get_counters returns their sum. */
 int             asgpu_get_counters_by_kind(asgpu_scene* scene, asgpu_counters* closest, asgpu_counters* probe, int reset);
 
+/* Diagnostic next to the counters (accumulated by ASGPU_TRACE_COUNTERS launches of the throughput
+ * kernels, cleared with them): where the lane slots of the warps' node-test rounds go -- one round
+ * offers 32 slots; `testing` of them run a node test, the others idle for the reason named.  This
+ * is the kernel's SIMD efficiency seen from inside (ncu reports the same thing per instruction). */
+typedef struct asgpu_lane_profile {
+    uint64_t        rounds;             /* node-test rounds executed by all warps */
+    uint64_t        testing;            /* lane slots that tested a node */
+    uint64_t        no_ray;             /* lane had no ray (waiting for the next refill) */
+    uint64_t        traversed;          /* ray done walking, waits for queued triangle candidates */
+    uint64_t        held;               /* must not enter the next instance before its candidates are tested */
+    uint64_t        want_enter;         /* waits for the warp's batched instance entry */
+    uint64_t        found_leaf;         /* found leaf triangles earlier in this iteration */
+    uint64_t        nothing_to_fetch;   /* choosing (pop / back to world space) took this round */
+    uint64_t        iterations;         /* passes of the warps' outer loops */
+    uint64_t        batched_entries, lanes_entered;
+    uint64_t        refills, lanes_refilled;
+    uint64_t        reserved[3];
+} asgpu_lane_profile;
+int             asgpu_get_lane_profile(asgpu_scene* scene, asgpu_lane_profile* closest, asgpu_lane_profile* probe);
+
 /* ------------------------------------------------------------------------------------------
  * Wavefront ray queues: the renderer's recursive per-sample trace
  * loop -- GenericSampleRenderer::render_sample (generic/genericsamplerenderer.cpp:164-299) ->

@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--res", type=int, default=0)
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--msc", type=int, default=1, help="c4: motion segment count")
+    ap.add_argument("--spp", type=int, default=4, help="c5: camera paths per pixel")
     ap.add_argument("--sort", action="store_true", help="also time every wavefront with ASGPU_TRACE_SORT (sort + trace) and the sort alone")
     ap.add_argument("--sweep", action="append", default=[], help="ENV=v1,v2,... (cartesian product of all sweeps)")
     ap.add_argument("--tree-build", default="sah", choices=["sah", "device"], help="device: triangle trees from asgpu_trees_build_on_device (linear BVH)")
@@ -50,6 +51,41 @@ def main():
         print(json.dumps({"workload": wl, "wide_nodes": info["wide_node_count"], "wide_stack_depth": info["wide_stack_depth"], "blob_MB": round(info["blob_bytes"] / 1e6, 1)}), flush=True)
         n = args.rays
         waves = []
+        if wl == "c5":
+            # The path stream (a few spp of the 1920 x 1080 frame) under every setting: Mrays/s of the
+            # whole frame and of its closest-hit / probe launches (CUDA events around every launch).
+            from appleseed_b200.wavefront import PathStream, PathStreamConfig
+            a5 = argparse.Namespace(width=1920, height=1080, spp=args.spp, no_parents=False)
+            ps = PathStream(ctx, PathStreamConfig(**bench.c5_config(a5, desc)), queue_capacity=16 << 20)
+            first = None
+            for setting in settings:
+                for k, v in setting.items():
+                    os.environ[k] = v
+                ctx.lib.asgpu_reload_tuning()
+                ps.render()
+                torch.cuda.synchronize()
+                ps.clear()
+                ps.set_profiling(True)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(args.reps):
+                    ps.render()
+                e1.record()
+                torch.cuda.synchronize()
+                st, prof = ps.stats(), ps.profile()
+                img = ps.image()
+                if first is None:
+                    first = img
+                rays = st["camera_rays"] + st["bounce_rays"] + st["probe_rays"]
+                print(json.dumps({"workload": wl, "spp": args.spp, "setting": setting, "frame": round(rays / e0.elapsed_time(e1) / 1e3, 1),
+                                  "closest": round((st["camera_rays"] + st["bounce_rays"]) / prof["closest_ms"] / 1e3, 1),
+                                  "probe": round(st["probe_rays"] / prof["probe_ms"] / 1e3, 1),
+                                  "refine_ms": round(prof["refine_ms"] / args.reps, 2), "stage_ms": round(prof["stage_ms"] / args.reps, 2),
+                                  "image_unchanged": bool((img == first).all())}), flush=True)
+                ps.set_profiling(False)
+            ps.close()
+            del ctx, isect
+            continue
         if wl == "c2":
             prim = bench.primary_rays_c2(n, 0)
             n = len(prim)
@@ -124,8 +160,15 @@ def main():
                                              "trace_only_mrays_s": round(n / max(1e-6, ms_sorted - ms_sort) / 1e3, 1), "identical": bool(same)}
                 ctx.counters(reset=True)
                 (isect.trace_probe_device(rays, occ, counters=True) if probe else isect.trace_device(rays, out, counters=True))
+                lp = ctx.lane_profile()[1 if probe else 0]
                 c = ctx.counters(reset=True)
                 r = max(1, c["rays"])
+                slots = max(1, 32 * lp["rounds"])
+                res[name + "_lanes"] = {k: round(100.0 * lp[k] / slots, 1) for k in ("testing", "no_ray", "traversed", "held", "want_enter", "found_leaf", "nothing_to_fetch")}
+                res[name + "_lanes"].update({"rounds_per_iter": round(lp["rounds"] / max(1, lp["iterations"]), 2),
+                                             "lanes_per_entry": round(lp["lanes_entered"] / max(1, lp["batched_entries"]), 1),
+                                             "lanes_per_refill": round(lp["lanes_refilled"] / max(1, lp["refills"]), 1),
+                                             "rounds_per_ray": round(lp["rounds"] * 32 / r, 2)})
                 res[name + "_visits"] = "n%.2f t%.2f" % ((c["triangle_nodes_visited"] + c["assembly_nodes_visited"]) / r, c["triangles_tested"] / r)
             print(json.dumps({"workload": wl, "rays": n, "setting": setting, **res}), flush=True)
         del ctx, isect
