@@ -83,10 +83,11 @@ def _view_bytes(ptr, nbytes):
 
 
 class Oracle:
-    def __init__(self, prefix: str = "orc"):
+    def __init__(self, prefix: str = "orc", path: str = None):
+        """``path``: another library exporting the same interface (tests/adaptor's build of ref_driver.cpp)."""
         if prefix not in _PATHS:
             raise ValueError(prefix)
-        path = _PATHS[prefix]
+        path = path or _PATHS[prefix]
         if not os.path.exists(path):
             if prefix == "orc":
                 build("orc")

@@ -47,6 +47,11 @@
 #include <thread>
 #include <vector>
 
+// The product's C++ adaptor (include/asgpu_adaptor.hpp) reads the trees through one friend
+// declaration per class, exactly as an in-tree integration would add to renderer::TriangleTree and
+// renderer::AssemblyTree; tests/adaptor compiles it against these types.
+namespace asgpu_adaptor { class GpuSceneFlattener; }
+
 using namespace foundation;
 
 // Allocation logging hooks declared in main/allocator.h; foundation/memory/memory.cpp calls them.
@@ -186,6 +191,8 @@ class RefTriangleTree
     {
         build_bvh();
     }
+
+    friend class asgpu_adaptor::GpuSceneFlattener;
 
     std::vector<TriangleKey>    m_triangle_keys;
     std::vector<std::uint8_t>   m_leaf_data;
@@ -739,6 +746,7 @@ struct RefShadingPoint
     std::uint32_t   m_tri_slot = 0;
     std::uint32_t   m_motion_segment = 0;
     TriangleMTSupportPlane<double> m_triangle_support_plane;    // shadingpoint.h:300, written at triangletree.cpp:1496-1497
+    Transformd      m_assembly_instance_transform;              // shadingpoint.h:297, written at assemblytree.cpp:738
 };
 
 //
@@ -1017,6 +1025,8 @@ class RefAssemblyTree
     RefAssemblyTree()
       : bvh::Tree<NodeVector>(AlignedAllocator<void>(64)) {}
 
+    friend class asgpu_adaptor::GpuSceneFlattener;
+
     std::vector<RefItem>                            m_items;
     std::vector<std::unique_ptr<RefTriangleTree>>   m_triangle_trees;       // one per assembly with geometry
     std::vector<int>                                m_assembly_tree_index;  // assembly -> tree or -1
@@ -1250,6 +1260,7 @@ struct AsmLeafVisitor
                 m_shading_point.m_tri_slot = asm_inst_shading_point.m_tri_slot;
                 m_shading_point.m_motion_segment = asm_inst_shading_point.m_motion_segment;
                 m_shading_point.m_triangle_support_plane = asm_inst_shading_point.m_triangle_support_plane;     // assemblytree.cpp:743
+                m_shading_point.m_assembly_instance_transform = assembly_instance_transform;                     // assemblytree.cpp:738
             }
         }
 
