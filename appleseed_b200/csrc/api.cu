@@ -12,6 +12,7 @@
 #include "api_internal.h"
 #include "kernels.h"
 #include "tree_builder.h"
+#include "parallel.h"
 
 #include <cuda_runtime.h>
 
@@ -298,7 +299,40 @@ int asgpu::ensure_id_table(asgpu_scene* scene)
 namespace
 {
 
-asgpu_scene* adopt_blob_image(const std::vector<uint8_t>& image, const int device)
+// Host image -> device through two page-locked staging buffers: a pageable cudaMemcpy of a
+// multi-gigabyte blob runs at a fraction of the link rate; here several threads fill one buffer
+// while the other one is on its way.
+cudaError_t upload_blob(uint8_t* device_dst, const uint8_t* host_src, const size_t bytes)
+{
+    const size_t Chunk = size_t(64) << 20;
+    if (bytes <= Chunk) return cudaMemcpy(device_dst, host_src, bytes, cudaMemcpyHostToDevice);
+    uint8_t* staging[2] = { nullptr, nullptr };
+    cudaEvent_t done[2] = { nullptr, nullptr };
+    cudaStream_t stream = nullptr;
+    cudaError_t e = cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking);
+    for (int k = 0; k < 2 && e == cudaSuccess; ++k)
+    {
+        e = cudaMallocHost(reinterpret_cast<void**>(&staging[k]), Chunk);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&done[k], cudaEventDisableTiming);
+    }
+    size_t index = 0;
+    for (size_t begin = 0; begin < bytes && e == cudaSuccess; begin += Chunk, ++index)
+    {
+        const int k = static_cast<int>(index & 1);
+        const size_t n = std::min(Chunk, bytes - begin);
+        if (index >= 2) e = cudaEventSynchronize(done[k]);          // the previous copy out of this buffer has finished
+        if (e != cudaSuccess) break;
+        parallel_memcpy(staging[k], host_src + begin, n, host_threads());
+        e = cudaMemcpyAsync(device_dst + begin, staging[k], n, cudaMemcpyHostToDevice, stream);
+        if (e == cudaSuccess) e = cudaEventRecord(done[k], stream);
+    }
+    if (stream) { const cudaError_t s = cudaStreamSynchronize(stream); if (e == cudaSuccess) e = s; }
+    for (int k = 0; k < 2; ++k) { if (staging[k]) cudaFreeHost(staging[k]); if (done[k]) cudaEventDestroy(done[k]); }
+    if (stream) cudaStreamDestroy(stream);
+    return e;
+}
+
+asgpu_scene* adopt_blob_image(const HostBlob& image, const int device)
 {
     {
         // Structural check of what the flattener produced (offsets and counts of every table).
@@ -314,7 +348,7 @@ asgpu_scene* adopt_blob_image(const std::vector<uint8_t>& image, const int devic
     if (init_device_side(s) != ASGPU_OK) { asgpu_scene_destroy(s); return nullptr; }
     cudaError_t e = cudaMalloc(&s->blob, s->blob_bytes);
     if (e != cudaSuccess) { fail_cuda(e, "cudaMalloc(blob)"); asgpu_scene_destroy(s); return nullptr; }
-    e = cudaMemcpy(s->blob, image.data(), s->blob_bytes, cudaMemcpyHostToDevice);
+    e = upload_blob(s->blob, image.data(), s->blob_bytes);
     if (e != cudaSuccess) { fail_cuda(e, "cudaMemcpy(blob)"); asgpu_scene_destroy(s); return nullptr; }
     make_view(s);
     return s;
@@ -431,7 +465,7 @@ asgpu_scene* asgpu_scene_create_ex(
     int                             device)
 {
     if (!assembly_tree) { fail(ASGPU_E_INVALID, "null assembly tree"); return nullptr; }
-    std::vector<uint8_t> image;
+    HostBlob image;
     std::string error;
     int rc;
     try { rc = flatten_scene(triangle_trees, triangle_tree_count, *assembly_tree, sources, flags ? flags : ASGPU_SCENE_DEFAULT, image, error); }

@@ -18,13 +18,18 @@
 
 #include "flatten.h"
 #include "as_format.h"
+#include "parallel.h"
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <limits>
+#include <mutex>
 
 namespace asgpu
 {
@@ -64,14 +69,24 @@ inline float float_above(const double v)    // smallest float >= v
 class BlobWriter
 {
   public:
-    explicit BlobWriter(std::vector<uint8_t>& bytes) : m_bytes(bytes) { m_bytes.clear(); }
+    explicit BlobWriter(HostBlob& bytes) : m_bytes(bytes) { m_bytes.clear(); }
+
+    // Room for `size` bytes at the next SectionAlign boundary (the gap is zeroed, the room is not);
+    // returns the offset.
+    uint64_t reserve(const size_t size)
+    {
+        const size_t old = m_bytes.size();
+        const uint64_t offset = (old + SectionAlign - 1) / SectionAlign * SectionAlign;
+        m_bytes.grow_to(offset + size);
+        if (offset > old) std::memset(m_bytes.data() + old, 0, offset - old);
+        return offset;
+    }
 
     // Appends `size` bytes at the next SectionAlign boundary; returns the offset.
     uint64_t append(const void* data, const size_t size)
     {
-        const uint64_t offset = (m_bytes.size() + SectionAlign - 1) / SectionAlign * SectionAlign;
-        m_bytes.resize(offset + size, 0);
-        if (size) std::memcpy(m_bytes.data() + offset, data, size);
+        const uint64_t offset = reserve(size);
+        parallel_memcpy(m_bytes.data() + offset, data, size, host_threads());
         return offset;
     }
 
@@ -80,13 +95,17 @@ class BlobWriter
         return append(v.empty() ? nullptr : v.data(), v.size() * sizeof(T));
     }
 
-    void finish()
+    template <typename T> uint64_t append(const RawVector<T>& v)
     {
-        m_bytes.resize((m_bytes.size() + SectionAlign - 1) / SectionAlign * SectionAlign, 0);
+        return append(v.empty() ? nullptr : v.data(), v.size() * sizeof(T));
     }
 
+    uint8_t* at(const uint64_t offset) { return m_bytes.data() + offset; }
+
+    void finish() { reserve(0); }
+
   private:
-    std::vector<uint8_t>& m_bytes;
+    HostBlob& m_bytes;
 };
 
 //
@@ -95,12 +114,12 @@ class BlobWriter
 
 struct ExactTree
 {
-    std::vector<BNodeF>     bnodes;
-    std::vector<MNode>      mnodes;
-    std::vector<MBox>       mboxes;
-    std::vector<TriRecord>  tris;
-    std::vector<float>      poses;
-    std::vector<HitKey>     keys;
+    RawVector<BNodeF>       bnodes;
+    RawVector<MNode>        mnodes;
+    RawVector<MBox>         mboxes;
+    RawVector<TriRecord>    tris;
+    RawVector<float>        poses;
+    RawVector<HitKey>       keys;
     uint64_t                moving = 0;
 };
 
@@ -126,6 +145,57 @@ int check_hierarchy(const AsNode* nodes, const uint64_t count, const char* what,
     return ASGPU_OK;
 }
 
+// ASGPU_BUILD_TIMING=1: seconds since the previous mark, on stderr.
+struct PhaseTimer
+{
+    const bool enabled = std::getenv("ASGPU_BUILD_TIMING") != nullptr;
+    std::chrono::steady_clock::time_point last = std::chrono::steady_clock::now();
+    void mark(const char* what)
+    {
+        if (!enabled) return;
+        const auto now = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "asgpu flatten:   %-20s %.3f s\n", what, std::chrono::duration<double>(now - last).count());
+        last = now;
+    }
+};
+
+// First error of a parallel section (later ones are dropped).
+class ErrorSink
+{
+  public:
+    bool failed() const { return m_failed.load(std::memory_order_relaxed); }
+    void fail(const int code, const char* message)
+    {
+        std::lock_guard<std::mutex> lock(m_mutex);
+        if (!m_failed.load()) { m_code = code; m_message = message; m_failed.store(true); }
+    }
+    int finish(std::string& error) const { if (failed()) error = m_message; return failed() ? m_code : ASGPU_OK; }
+
+  private:
+    std::atomic<bool>   m_failed{false};
+    std::mutex          m_mutex;
+    int                 m_code = ASGPU_OK;
+    std::string         m_message;
+};
+
+// Where the payload of a leaf lives: in the node when its first u32 is ~0, else at m_leaf_data[offset].
+inline bool leaf_payload(const asgpu_triangle_tree_view& v, const AsNode& src, const uint8_t*& p, const uint8_t*& limit)
+{
+    const uint8_t* user = src.user_data();
+    uint32_t offset;
+    std::memcpy(&offset, user, 4);
+    if (src.item_count == 0) { p = limit = user; }
+    else if (offset == 0xFFFFFFFFu) { p = user + 4; limit = user + AsNodeUserDataSize; }
+    else
+    {
+        if (offset >= v.leaf_data_size) return false;
+        p = v.leaf_data + offset; limit = v.leaf_data + v.leaf_data_size;
+    }
+    return true;
+}
+
+// Nodes are decoded in parallel over contiguous node ranges; the pose pool keeps the reference's leaf
+// order because every range knows where its poses start (prefix sum of a first, counting pass).
 int decode_tree(const asgpu_triangle_tree_view& v, ExactTree& out, std::string& error)
 {
     if (v.node_count == 0 || !v.nodes) { error = "triangle tree without nodes"; return ASGPU_E_INVALID; }
@@ -135,118 +205,158 @@ int decode_tree(const asgpu_triangle_tree_view& v, ExactTree& out, std::string& 
     const bool motion = v.moving_triangle_count > 0;
     const int shape = check_hierarchy(nodes, v.node_count, "triangle tree", error);
     if (shape != ASGPU_OK) return shape;
+    const int threads = host_threads();
+    const size_t grain = 1 << 15;
+    PhaseTimer phase;
+    phase.mark("hierarchy check");
 
     out.bnodes.resize(v.node_count);
     if (motion) out.mnodes.resize(v.node_count);
     out.tris.resize(v.triangle_key_count);
     out.keys.resize(v.triangle_key_count);
-    for (uint64_t i = 0; i < v.triangle_key_count; ++i)
+    parallel_chunks(v.triangle_key_count, threads, grain, [&](int, size_t begin, size_t end)
     {
-        out.keys[i].object_instance_index = keys[i].object_instance_index;
-        out.keys[i].triangle_index = keys[i].triangle_index;
-    }
+        for (size_t i = begin; i < end; ++i)
+        {
+            out.keys[i].object_instance_index = keys[i].object_instance_index;
+            out.keys[i].triangle_index = keys[i].triangle_index;
+        }
+    });
 
+    ErrorSink sink;
     if (motion)
     {
         out.mboxes.resize(v.node_bbox_count);
-        for (uint64_t i = 0; i < v.node_bbox_count; ++i)
-            for (int k = 0; k < 6; ++k)
-            {
-                const double d = v.node_bboxes[i * 6 + k];
-                const float f = static_cast<float>(d);
-                if (static_cast<double>(f) != d) { error = "motion box is not float-representable"; return ASGPU_E_UNSUPPORTED; }
-                out.mboxes[i].v[k] = f;
-            }
+        parallel_chunks(v.node_bbox_count, threads, grain, [&](int, size_t begin, size_t end)
+        {
+            for (size_t i = begin; i < end; ++i)
+                for (int k = 0; k < 6; ++k)
+                {
+                    const double d = v.node_bboxes[i * 6 + k];
+                    const float f = static_cast<float>(d);
+                    if (static_cast<double>(f) != d) { sink.fail(ASGPU_E_UNSUPPORTED, "motion box is not float-representable"); return; }
+                    out.mboxes[i].v[k] = f;
+                }
+        });
+        if (sink.failed()) return sink.finish(error);
     }
 
-    std::vector<uint8_t> seen(v.triangle_key_count, 0);
-    for (uint64_t n = 0; n < v.node_count; ++n)
+    phase.mark("alloc + keys");
+    // Pass 1: pose floats of every node range (walks the leaf payload headers only).
+    const int chunks = chunk_count(v.node_count, threads, grain);
+    std::vector<uint64_t> pose_floats(chunks + 1, 0);
+    parallel_chunks(v.node_count, threads, grain, [&](int chunk, size_t begin, size_t end)
     {
-        const AsNode& src = nodes[n];
-        BNodeF& dst = out.bnodes[n];
-        std::memset(&dst, 0, sizeof(dst));
-        dst.index = src.index;
-        dst.item_count = src.item_count;
-
-        if (src.interior())
+        uint64_t total = 0;
+        for (size_t n = begin; n < end && !sink.failed(); ++n)
         {
-            if (uint64_t(src.index) + 1 >= v.node_count) { error = "child node index out of range"; return ASGPU_E_INVALID; }
-            for (int k = 0; k < 12; ++k)
+            const AsNode& src = nodes[n];
+            if (src.interior()) continue;
+            const uint8_t* p; const uint8_t* limit;
+            if (!leaf_payload(v, src, p, limit)) { sink.fail(ASGPU_E_INVALID, "leaf data offset out of range"); return; }
+            for (uint32_t j = 0; j < src.item_count; ++j)
             {
-                const float f = static_cast<float>(src.bbox[k]);
-                // The reference builds triangle-tree boxes in float and widens them
-                // (triangletree.cpp:543, bvh_builder.h:193-204).
-                if (static_cast<double>(f) != src.bbox[k]) { error = "triangle tree box is not float-representable"; return ASGPU_E_UNSUPPORTED; }
-                dst.box[k] = f;
-            }
-            if (motion)
-            {
-                MNode& m = out.mnodes[n];
-                m.left_index = src.left_bbox_index; m.left_count = src.left_bbox_count;
-                m.right_index = src.right_bbox_index; m.right_count = src.right_bbox_count;
-                if ((m.left_count > 1 && uint64_t(m.left_index) + m.left_count > v.node_bbox_count) ||
-                    (m.right_count > 1 && uint64_t(m.right_index) + m.right_count > v.node_bbox_count) ||
-                    m.left_count == 0 || m.right_count == 0)
-                { error = "motion box range out of range"; return ASGPU_E_INVALID; }
-            }
-            continue;
-        }
-
-        if (uint64_t(src.index) + src.item_count > v.triangle_key_count) { error = "leaf item range out of range"; return ASGPU_E_INVALID; }
-
-        // Leaf payload: in the node when its first u32 is ~0, else at m_leaf_data[offset].
-        const uint8_t* user = src.user_data();
-        uint32_t offset;
-        std::memcpy(&offset, user, 4);
-        const uint8_t* p;
-        const uint8_t* limit;
-        if (src.item_count == 0) { p = limit = user; }
-        else if (offset == 0xFFFFFFFFu) { p = user + 4; limit = user + AsNodeUserDataSize; }
-        else
-        {
-            if (offset >= v.leaf_data_size) { error = "leaf data offset out of range"; return ASGPU_E_INVALID; }
-            p = v.leaf_data + offset; limit = v.leaf_data + v.leaf_data_size;
-        }
-
-        for (uint32_t j = 0; j < src.item_count; ++j)
-        {
-            const uint32_t slot = src.index + j;
-            if (seen[slot]) { error = "triangle slot referenced twice"; return ASGPU_E_INVALID; }
-            seen[slot] = 1;
-            if (p + 8 > limit) { error = "truncated leaf payload"; return ASGPU_E_INVALID; }
-            uint32_t vis, msc;
-            std::memcpy(&vis, p, 4); std::memcpy(&msc, p + 4, 4); p += 8;
-            TriRecord& tri = out.tris[slot];
-            std::memset(&tri, 0, sizeof(tri));
-            tri.vis_flags = vis;
-            tri.ref_slot = slot;
-            if (msc == 0)
-            {
-                if (p + AsTriangleBytes > limit) { error = "truncated leaf payload"; return ASGPU_E_INVALID; }
-                std::memcpy(tri.v0, p, AsTriangleBytes); p += AsTriangleBytes;
-                tri.motion = 0;
-            }
-            else
-            {
-                const size_t bytes = (size_t(msc) + 1) * AsPoseBytes;
-                if (p + bytes > limit) { error = "truncated leaf payload"; return ASGPU_E_INVALID; }
-                if (out.poses.size() + bytes / 4 >= 0xFFFFFFFEull) { error = "pose pool too large"; return ASGPU_E_UNSUPPORTED; }
-                tri.motion = static_cast<uint32_t>(out.poses.size()) + 1;
-                std::memcpy(&tri.v0[0], &msc, 4);
-                const size_t base = out.poses.size();
-                out.poses.resize(base + bytes / 4);
-                std::memcpy(out.poses.data() + base, p, bytes); p += bytes;
-                ++out.moving;
+                if (p + 8 > limit) { sink.fail(ASGPU_E_INVALID, "truncated leaf payload"); return; }
+                uint32_t msc;
+                std::memcpy(&msc, p + 4, 4); p += 8;
+                const size_t bytes = msc == 0 ? size_t(AsTriangleBytes) : (size_t(msc) + 1) * AsPoseBytes;
+                if (p + bytes > limit) { sink.fail(ASGPU_E_INVALID, "truncated leaf payload"); return; }
+                p += bytes;
+                if (msc != 0) total += bytes / 4;
             }
         }
-    }
-    for (uint64_t i = 0; i < v.triangle_key_count; ++i)
-        if (!seen[i]) { error = "triangle slot not referenced by any leaf"; return ASGPU_E_INVALID; }
+        pose_floats[chunk + 1] = total;
+    });
+    if (sink.failed()) return sink.finish(error);
+    for (int c = 0; c < chunks; ++c) pose_floats[c + 1] += pose_floats[c];
+    if (pose_floats[chunks] >= 0xFFFFFFFEull) { error = "pose pool too large"; return ASGPU_E_UNSUPPORTED; }
+    out.poses.resize(pose_floats[chunks]);
+
+    phase.mark("pass 1");
+    // Pass 2: the records.
+    RawVector<uint8_t> seen;
+    seen.assign(v.triangle_key_count, uint8_t(0), threads);
+    std::vector<uint64_t> moving(chunks, 0);
+    parallel_chunks(v.node_count, threads, grain, [&](int chunk, size_t begin, size_t end)
+    {
+        uint64_t pose_cursor = pose_floats[chunk];
+        for (size_t n = begin; n < end && !sink.failed(); ++n)
+        {
+            const AsNode& src = nodes[n];
+            BNodeF& dst = out.bnodes[n];
+            std::memset(&dst, 0, sizeof(dst));
+            dst.index = src.index;
+            dst.item_count = src.item_count;
+
+            if (src.interior())
+            {
+                if (uint64_t(src.index) + 1 >= v.node_count) { sink.fail(ASGPU_E_INVALID, "child node index out of range"); return; }
+                for (int k = 0; k < 12; ++k)
+                {
+                    const float f = static_cast<float>(src.bbox[k]);
+                    // The reference builds triangle-tree boxes in float and widens them
+                    // (triangletree.cpp:543, bvh_builder.h:193-204).
+                    if (static_cast<double>(f) != src.bbox[k]) { sink.fail(ASGPU_E_UNSUPPORTED, "triangle tree box is not float-representable"); return; }
+                    dst.box[k] = f;
+                }
+                if (motion)
+                {
+                    MNode& m = out.mnodes[n];
+                    m.left_index = src.left_bbox_index; m.left_count = src.left_bbox_count;
+                    m.right_index = src.right_bbox_index; m.right_count = src.right_bbox_count;
+                    if ((m.left_count > 1 && uint64_t(m.left_index) + m.left_count > v.node_bbox_count) ||
+                        (m.right_count > 1 && uint64_t(m.right_index) + m.right_count > v.node_bbox_count) ||
+                        m.left_count == 0 || m.right_count == 0)
+                    { sink.fail(ASGPU_E_INVALID, "motion box range out of range"); return; }
+                }
+                continue;
+            }
+
+            if (uint64_t(src.index) + src.item_count > v.triangle_key_count) { sink.fail(ASGPU_E_INVALID, "leaf item range out of range"); return; }
+            if (motion) std::memset(&out.mnodes[n], 0, sizeof(MNode));
+            const uint8_t* p = nullptr; const uint8_t* limit = nullptr;
+            leaf_payload(v, src, p, limit);
+            for (uint32_t j = 0; j < src.item_count; ++j)
+            {
+                const uint32_t slot = src.index + j;
+                if (__atomic_exchange_n(&seen[slot], uint8_t(1), __ATOMIC_RELAXED)) { sink.fail(ASGPU_E_INVALID, "triangle slot referenced twice"); return; }
+                uint32_t vis, msc;
+                std::memcpy(&vis, p, 4); std::memcpy(&msc, p + 4, 4); p += 8;
+                TriRecord& tri = out.tris[slot];
+                std::memset(&tri, 0, sizeof(tri));
+                tri.vis_flags = vis;
+                tri.ref_slot = slot;
+                if (msc == 0)
+                {
+                    std::memcpy(tri.v0, p, AsTriangleBytes); p += AsTriangleBytes;
+                    tri.motion = 0;
+                }
+                else
+                {
+                    const size_t bytes = (size_t(msc) + 1) * AsPoseBytes;
+                    tri.motion = static_cast<uint32_t>(pose_cursor) + 1;
+                    std::memcpy(&tri.v0[0], &msc, 4);
+                    std::memcpy(out.poses.data() + pose_cursor, p, bytes); p += bytes;
+                    pose_cursor += bytes / 4;
+                    ++moving[chunk];
+                }
+            }
+        }
+    });
+    if (sink.failed()) return sink.finish(error);
+    phase.mark("pass 2");
+    out.moving = 0;
+    for (const uint64_t m : moving) out.moving += m;
+    parallel_chunks(v.triangle_key_count, threads, grain, [&](int, size_t begin, size_t end)
+    {
+        for (size_t i = begin; i < end; ++i)
+            if (!seen[i]) { sink.fail(ASGPU_E_INVALID, "triangle slot not referenced by any leaf"); return; }
+    });
+    if (sink.failed()) return sink.finish(error);
     if ((out.moving > 0) != motion) { error = "moving_triangle_count does not match the leaf payloads"; return ASGPU_E_INVALID; }
     return ASGPU_OK;
 }
 
-// Conservative all-time float box of a moving triangle: union of its poses.
 FBox triangle_box(const ExactTree& t, const uint32_t slot)
 {
     FBox b; b.reset();
@@ -285,9 +395,9 @@ FBox triangle_box(const ExactTree& t, const uint32_t slot)
 struct BinaryView
 {
     uint64_t                    node_count;
-    std::vector<uint32_t>       child;          // first child or InteriorMark^... (leaf: InteriorMark)
-    std::vector<uint32_t>       first, count;   // leaf item range
-    std::vector<FBox>           box;            // conservative all-time box of each node
+    RawVector<uint32_t>         child;          // first child or InteriorMark^... (leaf: InteriorMark)
+    RawVector<uint32_t>         first, count;   // leaf item range
+    RawVector<FBox>             box;            // conservative all-time box of each node
     // Trees with motion: box of node x over the ray-time interval [t0, t1] (empty = use `box`).
     std::function<FBox(uint32_t x, float t0, float t1)> timed_box;
 };
@@ -308,6 +418,8 @@ struct Element
     uint32_t    first, count;   // item range (!is_node)
     FBox        box;
 };
+
+struct Work { uint32_t node; int budget; };
 
 int quantise_node(WNode& w, const Element* kids, const int n, const int* slot_of, std::string& error)
 {
@@ -412,13 +524,19 @@ int collapse(const BinaryView& bv, const uint32_t leaf_cap, const CollapseCosts 
 
     // ---- augmented binary tree: leaves larger than leaf_cap are halved into virtual nodes --------
     const uint32_t Leaf = InteriorMark;
-    std::vector<uint32_t> lc(bv.child.begin(), bv.child.end());     // left child (right = left + 1 for real nodes)
-    std::vector<uint32_t> rc(bv.node_count);
-    std::vector<uint32_t> first(bv.first.begin(), bv.first.end()), count(bv.count.begin(), bv.count.end());
-    std::vector<FBox> box(bv.box.begin(), bv.box.end());
-    std::vector<uint32_t> src(bv.node_count);
-    for (uint64_t i = 0; i < bv.node_count; ++i) src[i] = static_cast<uint32_t>(i);
-    for (uint64_t i = 0; i < bv.node_count; ++i) rc[i] = lc[i] == Leaf ? Leaf : lc[i] + 1;
+    const int threads = host_threads();
+    PhaseTimer phase;
+    RawVector<uint32_t> lc, rc, first, count, src;                  // lc: left child (right = left + 1 for real nodes)
+    RawVector<FBox> box;
+    lc.copy_from(bv.child.data(), bv.node_count, threads);
+    first.copy_from(bv.first.data(), bv.node_count, threads);
+    count.copy_from(bv.count.data(), bv.node_count, threads);
+    box.copy_from(bv.box.data(), bv.node_count, threads);
+    rc.resize(bv.node_count); src.resize(bv.node_count);
+    parallel_chunks(bv.node_count, threads, 1 << 16, [&](int, size_t begin, size_t end)
+    {
+        for (size_t i = begin; i < end; ++i) { src[i] = static_cast<uint32_t>(i); rc[i] = lc[i] == Leaf ? Leaf : lc[i] + 1; }
+    });
     for (uint64_t i = 0; i < lc.size(); ++i)
     {
         if (lc[i] != Leaf || count[i] <= leaf_cap) continue;
@@ -434,22 +552,50 @@ int collapse(const BinaryView& bv, const uint32_t leaf_cap, const CollapseCosts 
 
     // ---- bottom-up: item range of every subtree, cost tables --------------------------------------
     // Children have larger indices than their parent (bvh_builder.h:197-205; virtual nodes are
-    // appended), so a descending sweep sees children first.
+    // appended), so one ascending sweep gives every node its depth; the dynamic programme then runs
+    // level by level from the deepest one, the nodes of a level in parallel.
+    phase.mark("augment");
     const double Inf = std::numeric_limits<double>::infinity();
-    std::vector<uint32_t> sub_first(n), sub_count(n);
-    std::vector<uint8_t> contiguous(n);
-    std::vector<float> cost(n * 8);         // cost[x * 8 + i], i = 1..7
-    std::vector<uint8_t> choice(n * 8);     // i = 1: 0 leaf child, 1 wide node;  i > 1: 0 = same as i - 1, else children given to the left subtree
-    std::vector<uint8_t> split8(n);         // children given to the left subtree when x becomes a wide node
+    RawVector<uint32_t> level_of;
+    level_of.assign(n, 0u, threads);
+    uint32_t max_level = 0;
+    for (uint64_t x = 0; x < n; ++x)
+    {
+        if (lc[x] == Leaf) continue;
+        const uint64_t l = lc[x], r = rc[x];
+        if (l <= x || r <= x || l >= n || r >= n) { error = "binary tree is not in parent-before-child order"; return ASGPU_E_INVALID; }
+        // (max: in a tree every node has one parent, but a malformed input that slipped a shared child
+        // past check_hierarchy through an unreachable node must still be processed children first.)
+        level_of[l] = std::max(level_of[l], level_of[x] + 1);
+        level_of[r] = std::max(level_of[r], level_of[x] + 1);
+        max_level = std::max(max_level, level_of[x] + 1);
+    }
+    std::vector<uint64_t> level_begin(size_t(max_level) + 2, 0);
+    for (uint64_t x = 0; x < n; ++x) ++level_begin[level_of[x] + 1];
+    for (size_t d = 0; d <= max_level; ++d) level_begin[d + 1] += level_begin[d];
+    RawVector<uint32_t> by_level(n);
+    {
+        std::vector<uint64_t> cursor(level_begin.begin(), level_begin.end() - 1);
+        for (uint64_t x = 0; x < n; ++x) by_level[cursor[level_of[x]]++] = static_cast<uint32_t>(x);
+    }
+    level_of.release();
+    phase.mark("levels");
+
+    // (Uninitialised: every entry that is read was written by cost_tables -- entry 0 of a row never is.)
+    RawVector<uint32_t> sub_first(n), sub_count(n);
+    RawVector<uint8_t> contiguous(n);
+    RawVector<float> cost(n * 8);           // cost[x * 8 + i], i = 1..7
+    RawVector<uint8_t> choice;              // i = 1: 0 leaf child, 1 wide node;  i > 1: 0 = same as i - 1, else children given to the left subtree
+    choice.assign(n * 8, uint8_t(0), threads);
+    RawVector<uint8_t> split8(n);           // children given to the left subtree when x becomes a wide node
     auto area_of = [&](const uint64_t x) -> double
     {
         if (!box[x].valid()) return 0.0;
         const double a = box[x].half_area();
         return a < 1.0e30 ? a : 1.0e30;
     };
-    for (uint64_t xi = n; xi-- > 0; )
+    auto cost_tables = [&](const uint64_t x)
     {
-        const uint64_t x = xi;
         float* cx = &cost[x * 8];
         uint8_t* hx = &choice[x * 8];
         const double area = area_of(x);
@@ -457,10 +603,9 @@ int collapse(const BinaryView& bv, const uint32_t leaf_cap, const CollapseCosts 
         {
             sub_first[x] = first[x]; sub_count[x] = count[x]; contiguous[x] = 1;
             for (int i = 1; i < 8; ++i) { cx[i] = static_cast<float>(area * count[x] * costs.item); hx[i] = 0; }
-            continue;
+            return;
         }
         const uint64_t l = lc[x], r = rc[x];
-        if (l <= x || r <= x || l >= n || r >= n) { error = "binary tree is not in parent-before-child order"; return ASGPU_E_INVALID; }
         contiguous[x] = contiguous[l] && contiguous[r] && (sub_count[l] == 0 || sub_count[r] == 0 || sub_first[l] + sub_count[l] == sub_first[r]);
         sub_first[x] = sub_count[l] ? sub_first[l] : sub_first[r];
         sub_count[x] = sub_count[l] + sub_count[r];
@@ -487,159 +632,235 @@ int collapse(const BinaryView& bv, const uint32_t leaf_cap, const CollapseCosts 
             if (dist[i] < cx[i - 1]) { cx[i] = static_cast<float>(dist[i]); hx[i] = static_cast<uint8_t>(dist_k[i]); }
             else { cx[i] = cx[i - 1]; hx[i] = 0; }
         }
+    };
+    phase.mark("tables alloc");
+    for (size_t d = size_t(max_level) + 1; d-- > 0; )
+    {
+        const uint32_t* level = by_level.data() + level_begin[d];
+        parallel_chunks(level_begin[d + 1] - level_begin[d], threads, 1 << 13, [&](int, size_t begin, size_t end)
+        {
+            for (size_t i = begin; i < end; ++i) cost_tables(level[i]);
+        });
     }
+    by_level.release();
+    cost.release();
+    phase.mark("cost tables");
 
-    // ---- top-down: emit wide nodes breadth first ---------------------------------------------------
-    struct Pending { uint32_t wide_index; uint32_t depth; uint32_t node; };
-    std::vector<Pending> queue;
+    // ---- top-down: emit wide nodes breadth first, one level at a time --------------------------------
+    // The nodes of a level choose their children, slots and quantised planes in parallel (pass A);
+    // prefix sums over the level give every node the index of its first internal child and of its first
+    // leaf item -- the positions a sequential breadth-first walk would hand out -- and pass B writes.
+    struct Pending { uint32_t wide_index; uint32_t node; };
+    struct Kid { uint32_t is_node, node, src, first, count; };
+    struct Temp
+    {
+        WNode       w;
+        Kid         kids[8];
+        int8_t      kid_in_slot[8];
+        int8_t      slot_of[8];
+        uint32_t    n_children, internal, items;
+    };
+    std::vector<Pending> level, next_level;
     {
         WNode blank; std::memset(&blank, 0, sizeof(blank));
         out.nodes.push_back(blank);
-        Pending p; p.wide_index = 0; p.depth = 1; p.node = 0;
-        queue.push_back(p);
+        Pending p; p.wide_index = 0; p.node = 0;
+        level.push_back(p);
     }
-    struct Work { uint32_t node; int budget; };
-    std::vector<Work> work;
+    RawVector<Temp> temp;
+    std::vector<uint64_t> node_offset, item_offset;
+    ErrorSink sink;
 
-    for (size_t qi = 0; qi < queue.size(); ++qi)
+    while (!level.empty())
     {
-        const Pending cur = queue[qi];
-        if (cur.depth > out.depth) out.depth = cur.depth;
-        Element kids[8];
-        int n_kids = 0;
-        bool overflow = false;
+        ++out.depth;
+        const size_t m = level.size();
+        temp.resize(m);
 
-        auto emit_leaf = [&](const uint32_t x)
+        // Pass A.
+        parallel_chunks(m, threads, 256, [&](int, size_t begin, size_t end)
         {
-            Element e; e.is_node = false; e.node = 0; e.src = src[x]; e.first = sub_first[x]; e.count = sub_count[x]; e.box = box[x];
-            if (n_kids < 8) kids[n_kids++] = e; else overflow = true;
-        };
-        auto emit_node = [&](const uint32_t x)
-        {
-            Element e; e.is_node = true; e.node = x; e.src = src[x]; e.first = e.count = 0; e.box = box[x];
-            if (n_kids < 8) kids[n_kids++] = e; else overflow = true;
-        };
-
-        if (lc[cur.node] == Leaf) { if (count[cur.node] > 0) emit_leaf(cur.node); }    // the whole tree is one small leaf
-        else
-        {
-            work.clear();
-            const int k8 = split8[cur.node];
-            Work wr; wr.node = rc[cur.node]; wr.budget = 8 - k8; work.push_back(wr);
-            Work wl; wl.node = lc[cur.node]; wl.budget = k8; work.push_back(wl);
-            while (!work.empty())
+            std::vector<Work> work;
+            for (size_t qi = begin; qi < end && !sink.failed(); ++qi)
             {
-                Work wk = work.back(); work.pop_back();
-                const uint32_t x = wk.node;
-                int i = wk.budget > 7 ? 7 : wk.budget;
-                if (lc[x] == Leaf) { if (count[x] > 0) emit_leaf(x); continue; }
-                while (i > 1 && choice[x * 8 + i] == 0) --i;
-                if (i == 1)
+                const Pending cur = level[qi];
+                Temp& t = temp[qi];
+                Element kids[8];
+                int n_kids = 0;
+                bool overflow = false;
+
+                auto emit_leaf = [&](const uint32_t x)
                 {
-                    if (choice[x * 8 + 1] == 0) emit_leaf(x); else emit_node(x);
-                    continue;
+                    Element e; e.is_node = false; e.node = 0; e.src = src[x]; e.first = sub_first[x]; e.count = sub_count[x]; e.box = box[x];
+                    if (n_kids < 8) kids[n_kids++] = e; else overflow = true;
+                };
+                auto emit_node = [&](const uint32_t x)
+                {
+                    Element e; e.is_node = true; e.node = x; e.src = src[x]; e.first = e.count = 0; e.box = box[x];
+                    if (n_kids < 8) kids[n_kids++] = e; else overflow = true;
+                };
+
+                if (lc[cur.node] == Leaf) { if (count[cur.node] > 0) emit_leaf(cur.node); }    // the whole tree is one small leaf
+                else
+                {
+                    work.clear();
+                    const int k8 = split8[cur.node];
+                    Work wr; wr.node = rc[cur.node]; wr.budget = 8 - k8; work.push_back(wr);
+                    Work wl; wl.node = lc[cur.node]; wl.budget = k8; work.push_back(wl);
+                    while (!work.empty())
+                    {
+                        Work wk = work.back(); work.pop_back();
+                        const uint32_t x = wk.node;
+                        int i = wk.budget > 7 ? 7 : wk.budget;
+                        if (lc[x] == Leaf) { if (count[x] > 0) emit_leaf(x); continue; }
+                        while (i > 1 && choice[size_t(x) * 8 + i] == 0) --i;
+                        if (i == 1)
+                        {
+                            if (choice[size_t(x) * 8 + 1] == 0) emit_leaf(x); else emit_node(x);
+                            continue;
+                        }
+                        const int k = choice[size_t(x) * 8 + i];
+                        Work b; b.node = rc[x]; b.budget = i - k; work.push_back(b);
+                        Work a; a.node = lc[x]; a.budget = k; work.push_back(a);
+                    }
                 }
-                const int k = choice[x * 8 + i];
-                Work b; b.node = rc[x]; b.budget = i - k; work.push_back(b);
-                Work a; a.node = lc[x]; a.budget = k; work.push_back(a);
+                if (overflow) { sink.fail(ASGPU_E_INVALID, "internal error: wide collapse produced more than 8 children"); return; }
+                const int n_children = n_kids;
+
+                // Octant slot assignment: slot s should hold the child that comes first for rays whose
+                // direction signs are those of octant s (bit a set = negative along axis a).
+                FBox nb; nb.reset();
+                for (int i = 0; i < n_children; ++i) nb.grow(kids[i].box);
+                int slot_of[8];
+                bool slot_used[8] = { false, false, false, false, false, false, false, false };
+                bool kid_done[8] = { false, false, false, false, false, false, false, false };
+                float slot_cost[8][8];
+                for (int i = 0; i < n_children; ++i)
+                    for (int sl = 0; sl < 8; ++sl)
+                    {
+                        float c = 0.0f;
+                        for (int a = 0; a < 3; ++a)
+                        {
+                            const float centre = kids[i].box.valid() ? 0.5f * (kids[i].box.lo[a] + kids[i].box.hi[a]) - 0.5f * (nb.lo[a] + nb.hi[a]) : 0.0f;
+                            c += ((sl >> a) & 1) ? -centre : centre;
+                        }
+                        slot_cost[i][sl] = c;
+                    }
+                for (int round = 0; round < n_children; ++round)
+                {
+                    int bi = -1, bs = -1; float bc = std::numeric_limits<float>::max();
+                    for (int i = 0; i < n_children; ++i)
+                    {
+                        if (kid_done[i]) continue;
+                        for (int sl = 0; sl < 8; ++sl)
+                            if (!slot_used[sl] && slot_cost[i][sl] < bc) { bc = slot_cost[i][sl]; bi = i; bs = sl; }
+                    }
+                    if (bi < 0)         // all remaining costs are +max/NaN: take any free pair
+                    {
+                        for (int i = 0; i < n_children && bi < 0; ++i) if (!kid_done[i]) bi = i;
+                        for (int sl = 0; sl < 8 && bs < 0; ++sl) if (!slot_used[sl]) bs = sl;
+                    }
+                    slot_of[bi] = bs; slot_used[bs] = true; kid_done[bi] = true;
+                }
+
+                WNode& w = t.w;
+                std::memset(&w, 0, sizeof(w));
+                for (int a = 0; a < 3; ++a) for (int sl = 0; sl < 8; ++sl) { w.qlo[a][sl] = 255; w.qhi[a][sl] = 0; }
+                std::string local_error;
+                const int rc_q = quantise_node(w, kids, n_children, slot_of, local_error);
+                if (rc_q != ASGPU_OK) { sink.fail(rc_q, local_error.c_str()); return; }
+
+                t.n_children = static_cast<uint32_t>(n_children);
+                t.internal = t.items = 0;
+                for (int sl = 0; sl < 8; ++sl) t.kid_in_slot[sl] = -1;
+                for (int i = 0; i < n_children; ++i)
+                {
+                    t.kid_in_slot[slot_of[i]] = static_cast<int8_t>(i);
+                    t.slot_of[i] = static_cast<int8_t>(slot_of[i]);
+                    Kid& k = t.kids[i];
+                    k.is_node = kids[i].is_node ? 1u : 0u; k.node = kids[i].node; k.src = kids[i].src; k.first = kids[i].first; k.count = kids[i].count;
+                    if (kids[i].is_node) ++t.internal; else t.items += kids[i].count;
+                }
             }
+        });
+        if (sink.failed()) return sink.finish(error);
+
+        // Positions: what a sequential breadth-first walk would hand out.
+        node_offset.resize(m + 1); item_offset.resize(m + 1);
+        node_offset[0] = out.nodes.size(); item_offset[0] = out.leaf_order.size();
+        for (size_t qi = 0; qi < m; ++qi)
+        {
+            node_offset[qi + 1] = node_offset[qi] + temp[qi].internal;
+            item_offset[qi + 1] = item_offset[qi] + temp[qi].items;
         }
-        if (overflow) { error = "internal error: wide collapse produced more than 8 children"; return ASGPU_E_INVALID; }
-        const int n_children = n_kids;
+        if (node_offset[m] >= 0xFFFFFFFFull) { error = "wide tree too large"; return ASGPU_E_UNSUPPORTED; }
+        out.nodes.resize(node_offset[m]);
+        out.leaf_order.resize(item_offset[m]);
+        next_level.resize(node_offset[m] - node_offset[0]);
+        const bool sliced = slice_count != 0 && static_cast<bool>(bv.timed_box);
+        if (sliced) out.slices.resize(out.nodes.size() * slice_count);
 
-        // Octant slot assignment: slot s should hold the child that comes first for rays whose
-        // direction signs are those of octant s (bit a set = negative along axis a).
-        FBox nb; nb.reset();
-        for (int i = 0; i < n_children; ++i) nb.grow(kids[i].box);
-        int slot_of[8];
-        bool slot_used[8] = { false, false, false, false, false, false, false, false };
-        bool kid_done[8] = { false, false, false, false, false, false, false, false };
-        float slot_cost[8][8];
-        for (int i = 0; i < n_children; ++i)
-            for (int sl = 0; sl < 8; ++sl)
-            {
-                float c = 0.0f;
-                for (int a = 0; a < 3; ++a)
-                {
-                    const float centre = kids[i].box.valid() ? 0.5f * (kids[i].box.lo[a] + kids[i].box.hi[a]) - 0.5f * (nb.lo[a] + nb.hi[a]) : 0.0f;
-                    c += ((sl >> a) & 1) ? -centre : centre;
-                }
-                slot_cost[i][sl] = c;
-            }
-        for (int round = 0; round < n_children; ++round)
+        // Pass B.
+        parallel_chunks(m, threads, 256, [&](int, size_t begin, size_t end)
         {
-            int bi = -1, bs = -1; float bc = std::numeric_limits<float>::max();
-            for (int i = 0; i < n_children; ++i)
+            for (size_t qi = begin; qi < end && !sink.failed(); ++qi)
             {
-                if (kid_done[i]) continue;
+                const Pending cur = level[qi];
+                Temp& t = temp[qi];
+                WNode& w = t.w;
+                // Internal children are allocated contiguously in slot order; leaves append their items
+                // to the wide item order in slot order.
+                w.child_base = static_cast<uint32_t>(node_offset[qi]);
+                w.tri_base = static_cast<uint32_t>(item_offset[qi]);
+                uint32_t leaf_offset = 0, child_cursor = 0;
                 for (int sl = 0; sl < 8; ++sl)
-                    if (!slot_used[sl] && slot_cost[i][sl] < bc) { bc = slot_cost[i][sl]; bi = i; bs = sl; }
-            }
-            if (bi < 0)         // all remaining costs are +max/NaN: take any free pair
-            {
-                for (int i = 0; i < n_children && bi < 0; ++i) if (!kid_done[i]) bi = i;
-                for (int sl = 0; sl < 8 && bs < 0; ++sl) if (!slot_used[sl]) bs = sl;
-            }
-            slot_of[bi] = bs; slot_used[bs] = true; kid_done[bi] = true;
-        }
+                {
+                    const int i = t.kid_in_slot[sl];
+                    if (i < 0) continue;
+                    const Kid& k = t.kids[i];
+                    if (k.is_node)
+                    {
+                        w.imask |= uint8_t(1u << sl);
+                        w.meta[sl] = uint8_t(0x20 | (24 + sl));
+                        Pending p; p.wide_index = w.child_base + child_cursor; p.node = k.node;
+                        next_level[node_offset[qi] - node_offset[0] + child_cursor] = p;
+                        ++child_cursor;
+                    }
+                    else
+                    {
+                        if (k.count == 0) { w.meta[sl] = 0; continue; }
+                        if (k.count > 3 || leaf_offset + k.count > 24) { sink.fail(ASGPU_E_INVALID, "internal error: wide leaf does not fit its node"); return; }
+                        const uint32_t unary = (1u << k.count) - 1;     // 1 -> 001, 2 -> 011, 3 -> 111
+                        w.meta[sl] = uint8_t((unary << 5) | leaf_offset);
+                        for (uint32_t j = 0; j < k.count; ++j) out.leaf_order[item_offset[qi] + leaf_offset + j] = k.first + j;
+                        leaf_offset += k.count;
+                    }
+                }
+                out.nodes[cur.wide_index] = w;
 
-        WNode w; std::memset(&w, 0, sizeof(w));
-        for (int a = 0; a < 3; ++a) for (int sl = 0; sl < 8; ++sl) { w.qlo[a][sl] = 255; w.qhi[a][sl] = 0; }
-        const int rc_q = quantise_node(w, kids, n_children, slot_of, error);
-        if (rc_q != ASGPU_OK) return rc_q;
-
-        // Internal children are allocated contiguously in slot order; leaves append their items
-        // to the wide item order in slot order.
-        int kid_in_slot[8];
-        for (int sl = 0; sl < 8; ++sl) kid_in_slot[sl] = -1;
-        for (int i = 0; i < n_children; ++i) kid_in_slot[slot_of[i]] = i;
-
-        w.child_base = static_cast<uint32_t>(out.nodes.size());
-        w.tri_base = static_cast<uint32_t>(out.leaf_order.size());
-        uint32_t leaf_offset = 0;
-        for (int sl = 0; sl < 8; ++sl)
-        {
-            const int i = kid_in_slot[sl];
-            if (i < 0) continue;
-            if (kids[i].is_node)
-            {
-                w.imask |= uint8_t(1u << sl);
-                w.meta[sl] = uint8_t(0x20 | (24 + sl));
-                WNode blank; std::memset(&blank, 0, sizeof(blank));
-                Pending p; p.wide_index = static_cast<uint32_t>(out.nodes.size()); p.depth = cur.depth + 1; p.node = kids[i].node;
-                out.nodes.push_back(blank);
-                queue.push_back(p);
+                if (sliced)
+                {
+                    // Time slices: the same children in the same frame, bounded over 1 / T of the time axis
+                    // each (a small overlap absorbs the rounding of the ray's slice index).
+                    int slot_of[8];
+                    for (uint32_t i = 0; i < t.n_children; ++i) slot_of[i] = t.slot_of[i];
+                    for (uint32_t j = 0; j < slice_count; ++j)
+                    {
+                        const float t0 = std::max(0.0f, (float(j) - 1.0e-3f) / float(slice_count));
+                        const float t1 = std::min(1.0f, (float(j) + 1.0f + 1.0e-3f) / float(slice_count));
+                        FBox boxes[8];
+                        for (uint32_t i = 0; i < t.n_children; ++i) boxes[i] = bv.timed_box(t.kids[i].src, t0, t1);
+                        std::string local_error;
+                        const int rs = quantise_slice(w, out.slices[size_t(cur.wide_index) * slice_count + j], boxes, static_cast<int>(t.n_children), slot_of, local_error);
+                        if (rs != ASGPU_OK) { sink.fail(rs, local_error.c_str()); return; }
+                    }
+                }
             }
-            else
-            {
-                if (kids[i].count == 0) { w.meta[sl] = 0; continue; }
-                if (kids[i].count > 3 || leaf_offset + kids[i].count > 24) { error = "internal error: wide leaf does not fit its node"; return ASGPU_E_INVALID; }
-                const uint32_t unary = (1u << kids[i].count) - 1;       // 1 -> 001, 2 -> 011, 3 -> 111
-                w.meta[sl] = uint8_t((unary << 5) | leaf_offset);
-                for (uint32_t k = 0; k < kids[i].count; ++k) out.leaf_order.push_back(kids[i].first + k);
-                leaf_offset += kids[i].count;
-            }
-        }
-        if (out.nodes.size() >= 0xFFFFFFFFull) { error = "wide tree too large"; return ASGPU_E_UNSUPPORTED; }
-        out.nodes[cur.wide_index] = w;
-
-        if (slice_count != 0 && bv.timed_box)
-        {
-            // Time slices: the same children in the same frame, bounded over 1 / T of the time axis
-            // each (a small overlap absorbs the rounding of the ray's slice index).
-            if (out.slices.size() < out.nodes.size() * slice_count) out.slices.resize(out.nodes.size() * slice_count);
-            for (uint32_t j = 0; j < slice_count; ++j)
-            {
-                const float t0 = std::max(0.0f, (float(j) - 1.0e-3f) / float(slice_count));
-                const float t1 = std::min(1.0f, (float(j) + 1.0f + 1.0e-3f) / float(slice_count));
-                FBox boxes[8];
-                for (int i = 0; i < n_children; ++i) boxes[i] = bv.timed_box(kids[i].src, t0, t1);
-                const int rs = quantise_slice(w, out.slices[size_t(cur.wide_index) * slice_count + j], boxes, n_children, slot_of, error);
-                if (rs != ASGPU_OK) return rs;
-            }
-        }
+        });
+        if (sink.failed()) return sink.finish(error);
+        level.swap(next_level);
     }
-    if (slice_count != 0 && bv.timed_box) out.slices.resize(out.nodes.size() * slice_count);
+    phase.mark("emit");
     return ASGPU_OK;
 }
 
@@ -649,9 +870,9 @@ void triangle_tree_boxes(const asgpu_triangle_tree_view& v, const ExactTree& t, 
     const AsNode* nodes = static_cast<const AsNode*>(v.nodes);
     const uint64_t n = v.node_count;
     bv.node_count = n;
-    bv.child.assign(n, InteriorMark);
-    bv.first.assign(n, 0);
-    bv.count.assign(n, 0);
+    bv.child.assign(n, InteriorMark, host_threads());
+    bv.first.assign(n, 0u, host_threads());
+    bv.count.assign(n, 0u, host_threads());
     bv.box.resize(n);
     const bool motion = t.moving > 0;
 
@@ -703,26 +924,30 @@ void triangle_tree_boxes(const asgpu_triangle_tree_view& v, const ExactTree& t, 
         bv.box[0].reset();
         for (uint32_t j = 0; j < nodes[0].item_count; ++j) bv.box[0].grow(triangle_box(t, nodes[0].index + j));
     }
-    for (uint64_t i = 0; i < n; ++i)
+    // (Every node has one parent -- check_hierarchy -- so the writes of different nodes never meet.)
+    parallel_chunks(n, host_threads(), 1 << 15, [&](int, size_t begin, size_t end)
     {
-        const AsNode& node = nodes[i];
-        if (node.interior())
+        for (size_t i = begin; i < end; ++i)
         {
-            bv.child[i] = node.index;
-            bv.box[node.index] = child_box(node, 0);
-            bv.box[node.index + 1] = child_box(node, 1);
-            if (motion)
+            const AsNode& node = nodes[i];
+            if (node.interior())
             {
-                mindex[node.index] = node.left_bbox_index; mcount[node.index] = node.left_bbox_count;
-                mindex[node.index + 1] = node.right_bbox_index; mcount[node.index + 1] = node.right_bbox_count;
+                bv.child[i] = node.index;
+                bv.box[node.index] = child_box(node, 0);
+                bv.box[node.index + 1] = child_box(node, 1);
+                if (motion)
+                {
+                    mindex[node.index] = node.left_bbox_index; mcount[node.index] = node.left_bbox_count;
+                    mindex[node.index + 1] = node.right_bbox_index; mcount[node.index + 1] = node.right_bbox_count;
+                }
+            }
+            else
+            {
+                bv.first[i] = node.index;
+                bv.count[i] = node.item_count;
             }
         }
-        else
-        {
-            bv.first[i] = node.index;
-            bv.count[i] = node.item_count;
-        }
-    }
+    });
 
     if (motion)
     {
@@ -730,13 +955,14 @@ void triangle_tree_boxes(const asgpu_triangle_tree_view& v, const ExactTree& t, 
         // boxes linearly in the ray time (bvh_intersector.h:680-722), so the union over an interval
         // is the union of the interpolants at its ends and at the knots inside it.  Padded for the
         // float rounding of the interpolation and of the time products.
-        const std::vector<FBox> all = bv.box;
-        const std::vector<MBox>* mboxes = &t.mboxes;
+        // (bv.box and t.mboxes outlive the closure: both belong to the caller of collapse().)
+        const FBox* all = bv.box.data();
+        const MBox* mboxes = t.mboxes.data();
         bv.timed_box = [all, mindex, mcount, mboxes](const uint32_t x, const float t0, const float t1) -> FBox
         {
             if (x == 0 || mcount[x] <= 1) return all[x];
             const uint32_t segments = mcount[x] - 1;
-            const MBox* mb = mboxes->data() + mindex[x];
+            const MBox* mb = mboxes + mindex[x];
             FBox b; b.reset();
             double span[3] = { 0.0, 0.0, 0.0 };
             auto add_at = [&](const double time)
@@ -778,9 +1004,9 @@ int assembly_tree_boxes(const asgpu_assembly_tree_view& top, BinaryView& bv, std
     const AsNode* nodes = static_cast<const AsNode*>(top.nodes);
     const uint64_t n = top.node_count;
     bv.node_count = n;
-    bv.child.assign(n, InteriorMark);
-    bv.first.assign(n, 0);
-    bv.count.assign(n, 0);
+    bv.child.assign(n, InteriorMark, 1);
+    bv.first.assign(n, 0u, 1);
+    bv.count.assign(n, 0u, 1);
     bv.box.resize(n);
     auto child_box = [&](const AsNode& node, const int side) -> FBox
     {
@@ -831,7 +1057,7 @@ int flatten_scene(
     const asgpu_assembly_tree_view& top,
     const asgpu_source_geometry*    sources,
     uint32_t                        flags,
-    std::vector<uint8_t>&           blob,
+    HostBlob&                       blob,
     std::string&                    error)
 {
     if ((flags & (ASGPU_SCENE_EXACT | ASGPU_SCENE_WIDE)) == 0) { error = "scene flags select no layout"; return ASGPU_E_INVALID; }
@@ -862,6 +1088,15 @@ int flatten_scene(
     BlobWriter writer(blob);
     writer.append(&header, sizeof(header));     // rewritten at the end
 
+    const bool timing = std::getenv("ASGPU_BUILD_TIMING") != nullptr;
+    auto stamp = [timing, last = std::chrono::steady_clock::now()](const char* what) mutable
+    {
+        if (!timing) return;
+        const auto now = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "asgpu flatten: %-22s %.3f s\n", what, std::chrono::duration<double>(now - last).count());
+        last = now;
+    };
+
     uint32_t max_bottom_depth = 0;
     std::vector<TreeDesc> descs(tree_count);
     for (uint32_t ti = 0; ti < tree_count; ++ti)
@@ -869,6 +1104,7 @@ int flatten_scene(
         ExactTree et;
         int rc = decode_tree(trees[ti], et, error);
         if (rc != ASGPU_OK) return rc;
+        stamp("decode tree");
 
         TreeDesc& d = descs[ti];
         std::memset(&d, 0, sizeof(d));
@@ -896,6 +1132,7 @@ int flatten_scene(
             header.triangle_bytes += et.tris.size() * sizeof(TriRecord);
         }
 
+        stamp("exact layout");
         if (sources && sources[ti].object_count != 0)
         {
             // Source geometry for the device-side refine_and_offset: packed copies of every object
@@ -921,19 +1158,37 @@ int flatten_scene(
                     dst.poses = writer.append(so.vertex_poses, size_t(so.vertex_count) * so.motion_segment_count * 12);
                     dst.motion_segment_count = so.motion_segment_count;
                 }
-                std::vector<uint32_t> packed(size_t(so.triangle_count) * 3);
-                const uint8_t* src = static_cast<const uint8_t*>(so.triangles);
-                for (size_t t = 0; t < so.triangle_count; ++t)
+                // Vertex indices packed straight into the blob (and checked), several threads.
+                dst.triangles = writer.reserve(size_t(so.triangle_count) * 12);
                 {
-                    std::memcpy(&packed[t * 3], src + t * so.triangle_stride, 12);
-                    for (int k = 0; k < 3; ++k)
-                        if (packed[t * 3 + k] >= so.vertex_count) { error = "source triangle references a missing vertex"; return ASGPU_E_INVALID; }
+                    uint32_t* packed = reinterpret_cast<uint32_t*>(writer.at(dst.triangles));
+                    const uint8_t* src = static_cast<const uint8_t*>(so.triangles);
+                    std::atomic<bool> bad(false);
+                    parallel_chunks(so.triangle_count, host_threads(), 1 << 16, [&](int, size_t begin, size_t end)
+                    {
+                        for (size_t t = begin; t < end; ++t)
+                        {
+                            std::memcpy(&packed[t * 3], src + t * so.triangle_stride, 12);
+                            for (int k = 0; k < 3; ++k)
+                                if (packed[t * 3 + k] >= so.vertex_count) bad.store(true, std::memory_order_relaxed);
+                        }
+                    });
+                    if (bad.load()) { error = "source triangle references a missing vertex"; return ASGPU_E_INVALID; }
                 }
-                dst.triangles = writer.append(packed);
             }
-            for (const HitKey& key : et.keys)
-                if (key.object_instance_index >= sg.object_count || key.triangle_index >= objs[key.object_instance_index].triangle_count)
-                { error = "triangle key outside the source geometry"; return ASGPU_E_INVALID; }
+            {
+                std::atomic<bool> bad(false);
+                parallel_chunks(et.keys.size(), host_threads(), 1 << 16, [&](int, size_t begin, size_t end)
+                {
+                    for (size_t i = begin; i < end; ++i)
+                    {
+                        const HitKey& key = et.keys[i];
+                        if (key.object_instance_index >= sg.object_count || key.triangle_index >= objs[key.object_instance_index].triangle_count)
+                            bad.store(true, std::memory_order_relaxed);
+                    }
+                });
+                if (bad.load()) { error = "triangle key outside the source geometry"; return ASGPU_E_INVALID; }
+            }
             d.src_objects = writer.append(objs);
             d.src_object_count = sg.object_count;
 
@@ -978,21 +1233,31 @@ int flatten_scene(
             }
         }
 
+        stamp("source geometry");
         if (want_wide)
         {
             BinaryView bv;
             triangle_tree_boxes(trees[ti], et, bv);
+            stamp("binary boxes");
             WideOut wo;
             const uint32_t slice_count = et.moving > 0 ? time_slices() : 0;
             rc = collapse(bv, 3, collapse_costs(), wo, error, slice_count);
             if (rc != ASGPU_OK) return rc;
+            stamp("wide collapse");
             if (wo.leaf_order.size() != et.tris.size()) { error = "internal error: wide collapse lost triangles"; return ASGPU_E_INVALID; }
             max_bottom_depth = std::max(max_bottom_depth, wo.depth);
-            std::vector<TriRecord> wtris(wo.leaf_order.size());
-            for (size_t i = 0; i < wtris.size(); ++i) wtris[i] = et.tris[wo.leaf_order[i]];
             d.wnodes = writer.append(wo.nodes);
             d.wnode_count = static_cast<uint32_t>(wo.nodes.size());
-            d.wtris = writer.append(wtris);
+            // The triangle records in wide-node order, gathered straight into the blob.
+            const size_t wtri_count = wo.leaf_order.size();
+            d.wtris = writer.reserve(wtri_count * sizeof(TriRecord));
+            {
+                TriRecord* wtris = reinterpret_cast<TriRecord*>(writer.at(d.wtris));
+                parallel_chunks(wtri_count, host_threads(), 1 << 15, [&](int, size_t begin, size_t end)
+                {
+                    for (size_t i = begin; i < end; ++i) wtris[i] = et.tris[wo.leaf_order[i]];
+                });
+            }
             if (slice_count != 0 && !wo.slices.empty())
             {
                 d.wslices = writer.append(wo.slices);
@@ -1000,7 +1265,8 @@ int flatten_scene(
             }
             header.wide_node_count += wo.nodes.size();
             header.wide_node_bytes += wo.nodes.size() * sizeof(WNode) + wo.slices.size() * sizeof(WSlice);
-            if (!want_exact) header.triangle_bytes += wtris.size() * sizeof(TriRecord);
+            if (!want_exact) header.triangle_bytes += wtri_count * sizeof(TriRecord);
+            stamp("wide triangles");
         }
     }
     header.trees = writer.append(descs);
@@ -1075,6 +1341,7 @@ int flatten_scene(
         header.wide_node_bytes += wo.nodes.size() * sizeof(WNode);
     }
 
+    stamp("items + top level");
     writer.finish();
     header.total_bytes = blob.size();
     std::memcpy(blob.data(), &header, sizeof(header));

@@ -24,6 +24,7 @@
 
 #include "tree_builder.h"
 #include "lbvh_core.h"
+#include "parallel.h"
 
 #include <algorithm>
 #include <atomic>
@@ -555,13 +556,14 @@ inline bool touches(const BoundsF& b, const P3& v0, const P3& v1, const P3& v2)
     return all == 0x3F;
 }
 
-void collect(const asgpu_scene_desc& desc, const asgpu_assembly& assembly, const BoundsF& tree_box, Collected& out)
+// Triangles [tri_begin, tri_end) of object instance `oi`, appended to `out` (first_vertex counts from
+// the start of out.vertices).
+void collect_range(const asgpu_scene_desc& desc, const asgpu_assembly& assembly, const BoundsF& tree_box, const uint32_t oi,
+                   const uint32_t tri_begin, const uint32_t tri_end, Collected& out)
 {
     const double time = assembly.time;
-    uint64_t vertex_cursor = 0;
+    uint64_t vertex_cursor = out.vertices.size();
     std::vector<BoundsF> pose_box;
-
-    for (uint32_t oi = 0; oi < assembly.object_instance_count; ++oi)
     {
         const asgpu_object_instance& inst = assembly.object_instances[oi];
         const asgpu_mesh& mesh = desc.meshes[inst.mesh_index];
@@ -569,7 +571,7 @@ void collect(const asgpu_scene_desc& desc, const asgpu_assembly& assembly, const
         const uint32_t msc = mesh.motion_segment_count;
         pose_box.resize(msc + 1);
 
-        for (uint32_t ti = 0; ti < mesh.triangle_count; ++ti)
+        for (uint32_t ti = tri_begin; ti < tri_end; ++ti)
         {
             const uint32_t* tv = mesh.triangles + size_t(ti) * 3;
             BoundsF build_box;
@@ -631,6 +633,46 @@ void collect(const asgpu_scene_desc& desc, const asgpu_assembly& assembly, const
             out.boxes.push_back(build_box);
             vertex_cursor += uint64_t(msc + 1) * 3;
         }
+    }
+}
+
+// Every triangle of the assembly, in the reference's order (object instances, then triangles:
+// triangletree.cpp:105-383).  The triangles of an instance are collected by several threads over
+// contiguous ranges and stitched in order, so the result does not depend on the number of threads.
+void collect(const asgpu_scene_desc& desc, const asgpu_assembly& assembly, const BoundsF& tree_box, Collected& out, const int threads)
+{
+    for (uint32_t oi = 0; oi < assembly.object_instance_count; ++oi)
+    {
+        const asgpu_mesh& mesh = desc.meshes[assembly.object_instances[oi].mesh_index];
+        const int chunks = chunk_count(mesh.triangle_count, threads, 1 << 14);
+        if (chunks <= 1) { collect_range(desc, assembly, tree_box, oi, 0, mesh.triangle_count, out); continue; }
+        std::vector<Collected> parts(chunks);
+        parallel_chunks(mesh.triangle_count, threads, 1 << 14, [&](int c, size_t begin, size_t end)
+        {
+            collect_range(desc, assembly, tree_box, oi, static_cast<uint32_t>(begin), static_cast<uint32_t>(end), parts[c]);
+        });
+        std::vector<size_t> tri_at(chunks + 1), vertex_begin(chunks + 1);
+        tri_at[0] = out.keys.size(); vertex_begin[0] = out.vertices.size();
+        for (int c = 0; c < chunks; ++c) { tri_at[c + 1] = tri_at[c] + parts[c].keys.size(); vertex_begin[c + 1] = vertex_begin[c] + parts[c].vertices.size(); }
+        out.keys.resize(tri_at[chunks]); out.infos.resize(tri_at[chunks]); out.boxes.resize(tri_at[chunks]);
+        out.vertices.resize(vertex_begin[chunks]);
+        parallel_chunks(static_cast<size_t>(chunks), threads, 1, [&](int, size_t begin, size_t end)
+        {
+            for (size_t c = begin; c < end; ++c)
+            {
+                const Collected& p = parts[c];
+                if (p.keys.empty()) continue;
+                std::memcpy(&out.keys[tri_at[c]], p.keys.data(), p.keys.size() * sizeof(p.keys[0]));
+                std::memcpy(&out.boxes[tri_at[c]], p.boxes.data(), p.boxes.size() * sizeof(p.boxes[0]));
+                std::memcpy(&out.vertices[vertex_begin[c]], p.vertices.data(), p.vertices.size() * sizeof(p.vertices[0]));
+                for (size_t i = 0; i < p.infos.size(); ++i)
+                {
+                    TriInfo info = p.infos[i];
+                    info.first_vertex += vertex_begin[c];
+                    out.infos[tri_at[c] + i] = info;
+                }
+            }
+        });
     }
 }
 
@@ -803,41 +845,60 @@ uint8_t* write_payload(uint8_t* out, const uint32_t first, const uint32_t count,
     return out;
 }
 
-void store_leaves(HostTriangleTree& tree, const std::vector<uint32_t>& order, const Collected& c)
+// Leaf payloads (triangletree.cpp:878-978).  Keys and spilled payloads land where a sequential walk
+// over the nodes would put them: every node range knows its first key and its first spill byte from a
+// counting pass, then the ranges are written by several threads.
+void store_leaves(HostTriangleTree& tree, const std::vector<uint32_t>& order, const Collected& c, const int threads)
 {
     const size_t in_node_limit = AsNodeUserDataSize - sizeof(uint32_t);     // 92 bytes
-    size_t spill = 0;
-    for (const AsNode& node : tree.nodes)
-        if (!node.interior())
+    const size_t node_count = tree.nodes.size();
+    const size_t grain = 1 << 14;
+    const int chunks = chunk_count(node_count, threads, grain);
+    std::vector<size_t> key_at(chunks + 1, 0), spill_at(chunks + 1, 0);
+    parallel_chunks(node_count, threads, grain, [&](int chunk, size_t begin, size_t end)
+    {
+        size_t keys = 0, spill = 0;
+        for (size_t n = begin; n < end; ++n)
         {
+            const AsNode& node = tree.nodes[n];
+            if (node.interior()) continue;
+            keys += node.item_count;
             const size_t s = payload_size(node, order, c);
             if (s > in_node_limit) spill += s;
         }
-    tree.leaf_data.resize(spill);
-    tree.keys.reserve(order.size());
-    uint8_t* spill_writer = tree.leaf_data.data();
+        key_at[chunk + 1] = keys; spill_at[chunk + 1] = spill;
+    });
+    for (int k = 0; k < chunks; ++k) { key_at[k + 1] += key_at[k]; spill_at[k + 1] += spill_at[k]; }
+    tree.leaf_data.resize(spill_at[chunks]);
+    tree.keys.resize(key_at[chunks]);
 
-    for (AsNode& node : tree.nodes)
+    parallel_chunks(node_count, threads, grain, [&](int chunk, size_t begin, size_t end)
     {
-        if (node.interior()) continue;
-        const uint32_t first = node.index, count = node.item_count;
-        const size_t s = payload_size(node, order, c);
-        node.index = static_cast<uint32_t>(tree.keys.size());
-        for (uint32_t j = 0; j < count; ++j) tree.keys.push_back(c.keys[order[first + j]]);
-        uint8_t* user = node.user_data();
-        if (s <= in_node_limit)
+        size_t key_cursor = key_at[chunk];
+        uint8_t* spill_writer = tree.leaf_data.data() + spill_at[chunk];
+        for (size_t n = begin; n < end; ++n)
         {
-            const uint32_t in_node = 0xFFFFFFFFu;
-            std::memcpy(user, &in_node, 4);
-            write_payload(user + 4, first, count, order, c);
+            AsNode& node = tree.nodes[n];
+            if (node.interior()) continue;
+            const uint32_t first = node.index, count = node.item_count;
+            const size_t s = payload_size(node, order, c);
+            node.index = static_cast<uint32_t>(key_cursor);
+            for (uint32_t j = 0; j < count; ++j) tree.keys[key_cursor++] = c.keys[order[first + j]];
+            uint8_t* user = node.user_data();
+            if (s <= in_node_limit)
+            {
+                const uint32_t in_node = 0xFFFFFFFFu;
+                std::memcpy(user, &in_node, 4);
+                write_payload(user + 4, first, count, order, c);
+            }
+            else
+            {
+                const uint32_t offset = static_cast<uint32_t>(spill_writer - tree.leaf_data.data());
+                std::memcpy(user, &offset, 4);
+                spill_writer = write_payload(spill_writer, first, count, order, c);
+            }
         }
-        else
-        {
-            const uint32_t offset = static_cast<uint32_t>(spill_writer - tree.leaf_data.data());
-            std::memcpy(user, &offset, 4);
-            spill_writer = write_payload(spill_writer, first, count, order, c);
-        }
-    }
+    });
 }
 
 bool check_desc(const asgpu_scene_desc& d, std::string& error)
@@ -1040,7 +1101,7 @@ bool build_host_trees(const asgpu_scene_desc& desc, int threads, HostTrees& out,
         };
         stamp("source geometry");
         Collected c;
-        collect(desc, assembly, ab, c);
+        collect(desc, assembly, ab, c, threads);
         stamp("collect");
         if (c.keys.size() >= 0xFFFFFFFFull) { error = "too many triangles in one assembly"; return false; }
         for (const TriInfo& info : c.infos) (info.msc == 0 ? tree.static_triangle_count : tree.moving_triangle_count) += 1;
@@ -1060,7 +1121,7 @@ bool build_host_trees(const asgpu_scene_desc& desc, int threads, HostTrees& out,
             stamp("emit nodes");
             propagate_motion_boxes(tree, topology.order, c);
             stamp("motion boxes");
-            store_leaves(tree, topology.order, c);
+            store_leaves(tree, topology.order, c, threads);
             stamp("store leaves");
             continue;
         }
@@ -1071,7 +1132,7 @@ bool build_host_trees(const asgpu_scene_desc& desc, int threads, HostTrees& out,
         stamp("sweep SAH");
         propagate_motion_boxes(tree, builder.ordering(), c);
         stamp("motion boxes");
-        store_leaves(tree, builder.ordering(), c);
+        store_leaves(tree, builder.ordering(), c, threads);
         stamp("store leaves");
     }
 

@@ -158,8 +158,12 @@ class PathStream:
         stream = C.c_void_p(torch.cuda.current_stream(self.ctx.device).cuda_stream)
         _check(self.lib.asgpu_path_stream_render(self.handle, t.ctypes.data if len(t) else None, len(t), stream), "asgpu_path_stream_render")
 
-    def image(self) -> np.ndarray:
-        out = np.empty((self.config.height, self.config.width, 4), dtype=np.uint32)
+    def image(self, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """Per-pixel accumulators (height x width x 4 uint32).  ``out``: a caller-owned array to fill
+        (page-locked memory makes the device-to-host copy several times faster)."""
+        if out is None:
+            out = np.empty((self.config.height, self.config.width, 4), dtype=np.uint32)
+        assert out.dtype == np.uint32 and out.size == self.config.height * self.config.width * 4 and out.flags.c_contiguous
         _check(self.lib.asgpu_path_stream_read_image(self.handle, out.ctypes.data), "asgpu_path_stream_read_image")
         return out
 

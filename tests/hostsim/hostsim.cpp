@@ -24,7 +24,7 @@ namespace
 {
     struct SimScene
     {
-        std::vector<uint8_t>    blob;
+        HostBlob                blob;
         SceneView               view;
     };
 
@@ -232,6 +232,7 @@ void* hostsim_scene_create_views(const asgpu_triangle_tree_view* views, uint32_t
 void hostsim_scene_destroy(void* scene) { delete static_cast<SimScene*>(scene); }
 
 size_t hostsim_blob_size(void* scene) { return static_cast<SimScene*>(scene)->blob.size(); }
+const uint8_t* hostsim_blob_data(void* scene) { return static_cast<SimScene*>(scene)->blob.data(); }
 
 void hostsim_trace(void* scene, const asgpu_rays* rays, size_t n, asgpu_hit* hits, int wide, uint64_t* counters)
 {

@@ -28,6 +28,8 @@ def load():
     lib.hostsim_last_error.restype = C.c_char_p
     lib.hostsim_blob_size.restype = C.c_size_t
     lib.hostsim_blob_size.argtypes = [C.c_void_p]
+    lib.hostsim_blob_data.restype = C.c_void_p
+    lib.hostsim_blob_data.argtypes = [C.c_void_p]
     lib.hostsim_trace.argtypes = [C.c_void_p, C.POINTER(CRays), C.c_size_t, C.c_void_p, C.c_int, C.c_void_p]
     lib.hostsim_trace_probe.argtypes = [C.c_void_p, C.POINTER(CRays), C.c_size_t, C.c_void_p, C.c_int, C.c_void_p]
     lib.hostsim_trace_parents.argtypes = [C.c_void_p, C.POINTER(CRays), C.c_void_p, C.c_size_t, C.c_void_p, C.c_int]
@@ -88,6 +90,11 @@ class SimScene:
         if getattr(self, "handle", None):
             self.lib.hostsim_scene_destroy(self.handle)
             self.handle = None
+
+    def blob(self) -> np.ndarray:
+        """A copy of the flattened scene image."""
+        n = int(self.lib.hostsim_blob_size(self.handle))
+        return np.frombuffer((C.c_uint8 * n).from_address(self.lib.hostsim_blob_data(self.handle)), dtype=np.uint8).copy()
 
     def trace(self, rays: RayBatch, wide: bool):
         out = np.zeros(len(rays), dtype=HIT_DTYPE)

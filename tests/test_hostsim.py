@@ -107,3 +107,18 @@ def test_extreme_and_non_finite_rays(sim, orc, name):
     assert s.trace(bad, wide=False)[0].tobytes() == o.trace(bad, threads=4).tobytes()
     assert np.array_equal(s.trace_probe(bad, wide=False)[0], o.trace_probe(bad, threads=4))
     assert len(s.trace(bad, wide=True)[0]) == len(bad) and len(s.trace_probe(bad, wide=True)[0]) == len(bad)
+
+
+@pytest.mark.parametrize("name", ["c3", "c4_msc2", "mixed"])
+def test_flattened_scene_does_not_depend_on_the_thread_count(sim, name, monkeypatch):
+    """The host builder and the flattener run on several threads (triangle collection, leaf payloads,
+    node decoding, the wide collapse level by level): chunks land at positions fixed by prefix sums, so
+    the blob is the same byte for byte whatever ASGPU_HOST_THREADS says."""
+    from appleseed_b200 import scenes
+    desc = {"c3": lambda: scenes.scene_c3(120, 3), "c4_msc2": lambda: scenes.scene_c4(160, 2), "mixed": lambda: cases.case_mixed()[0]}[name]()
+    blobs = []
+    for threads in ("1", "3", "8"):
+        monkeypatch.setenv("ASGPU_HOST_THREADS", threads)
+        blobs.append(hostsim.SimScene(sim, desc, threads=int(threads)).blob())
+    assert blobs[0].tobytes() == blobs[1].tobytes() == blobs[2].tobytes()
+    assert len(blobs[0]) > 100000
