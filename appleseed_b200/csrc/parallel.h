@@ -62,6 +62,7 @@ inline void parallel_chunks(const size_t n, const int threads, const size_t grai
 #if defined(__GNUC__) && !defined(__clang__)
 #pragma GCC diagnostic push
 #pragma GCC diagnostic ignored "-Wstringop-overflow"     // gcc 13 mis-sizes the chunk of the single-chunk path
+#pragma GCC diagnostic ignored "-Wrestrict"
 #endif
 inline void parallel_memcpy(void* dst, const void* src, const size_t bytes, const int threads)
 {
