@@ -21,7 +21,9 @@ namespace
 
 const int RefineThreads = 128;
 
-__global__ void __launch_bounds__(RefineThreads)
+// 8 resident CTAs (64 registers, a few spills): the kernel waits on dependent loads, more warps in
+// flight beat fewer spills (2.19 -> 1.86 ms per 8-spp C5 frame, profiles/README.md).
+__global__ void __launch_bounds__(RefineThreads, 8)
 refine_offset_kernel(const SceneView s, const asgpu_rays rays, const asgpu_hit* __restrict__ hits, const unsigned long long n_host,
                      const unsigned long long* n_dev, const bool raw_item, const uint32_t* __restrict__ id_to_item, const uint32_t id_count,
                      asgpu_parent* out)
@@ -112,7 +114,7 @@ int launch_refine_offset(const SceneView& scene, const asgpu_rays& rays, const a
                          const int sm_count, void* stream)
 {
     if (n == 0) return 0;
-    long long grid = static_cast<long long>(sm_count) * 8;
+    long long grid = static_cast<long long>(sm_count) * 16;
     const long long needed = static_cast<long long>((n + RefineThreads - 1) / RefineThreads);
     if (grid > needed) grid = needed;
     refine_offset_kernel<<<static_cast<unsigned>(grid), RefineThreads, 0, static_cast<cudaStream_t>(stream)>>>(

@@ -35,6 +35,7 @@
 
 #include <algorithm>
 #include <cfloat>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <utility>
@@ -262,7 +263,7 @@ generate_kernel(const StreamParams p, const uint32_t* __restrict__ tiles, const 
 //     (Tracer::trace_between, tracer.h:252-259), flags ShadowRay;
 //   * when depth < max_bounces, one cosine-weighted bounce (mappings.h:299-314), flags DiffuseRay.
 // hit.assembly_instance holds the ItemRecord index here (raw_item launches).
-__global__ void __launch_bounds__(StageThreads)
+__global__ void __launch_bounds__(StageThreads, 3)
 shade_kernel(const StreamParams p, const SceneView s, const QueueView in, const asgpu_hit* __restrict__ hits, const asgpu_parent* refined,
              const QueueView probes, const QueueView next, const uint32_t depth, uint32_t* image, unsigned long long* stats)
 {
