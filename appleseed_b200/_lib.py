@@ -12,7 +12,8 @@ import os
 from .scene import CIntersectionFilter, CRays, CSceneDesc
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libasgpu.so")
+# ASGPU_LIB: another build of the same library (kernel experiments: tools/build_variant.sh).
+LIB_PATH = os.environ.get("ASGPU_LIB") or os.path.join(_HERE, "libasgpu.so")
 
 # Every symbol include/asgpu.h declares.
 EXPORTS = [
@@ -33,6 +34,7 @@ EXPORTS = [
     "asgpu_trees_build_on_device", "asgpu_trees_device_seconds",
     "asgpu_get_counters_by_kind", "asgpu_get_lane_profile", "asgpu_get_support_planes", "asgpu_pin_host", "asgpu_unpin_host", "asgpu_reload_tuning",
     "asgpu_path_stream_capture_get_times", "asgpu_path_stream_set_profiling", "asgpu_path_stream_get_profile",
+    "asgpu_path_stream_read_tiles",
 ]
 
 SCENE_EXACT = 1 << 0
@@ -204,6 +206,7 @@ def load() -> C.CDLL:
     lib.asgpu_path_stream_tile_count.argtypes = [C.c_void_p]
     lib.asgpu_path_stream_render.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     lib.asgpu_path_stream_read_image.argtypes = [C.c_void_p, C.c_void_p]
+    lib.asgpu_path_stream_read_tiles.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     lib.asgpu_path_stream_clear.argtypes = [C.c_void_p]
     lib.asgpu_path_stream_get_stats.argtypes = [C.c_void_p, P(PathStreamStats)]
     lib.asgpu_path_stream_capture.argtypes = [C.c_void_p, C.c_size_t]

@@ -387,7 +387,10 @@ asgpu_trees* asgpu_trees_build_on_device(const asgpu_scene_desc* desc, int threa
     if (!t) { fail(ASGPU_E_NOMEM, "out of host memory"); return nullptr; }
     std::string error;
     bool ok = false;
-    try { ok = build_host_trees(*desc, threads, t->trees, error, lbvh_topology_device, &device); }
+    // ASGPU_DEVICE_BUILD = lbvh: the linear BVH (Morton splits); default: locally-ordered clustering.
+    const char* algorithm = getenv("ASGPU_DEVICE_BUILD");
+    const bool linear = algorithm != nullptr && std::strcmp(algorithm, "lbvh") == 0;
+    try { ok = build_host_trees(*desc, threads, t->trees, error, linear ? lbvh_topology_device : ploc_topology_device, &device); }
     catch (const std::exception& e) { error = e.what(); }
     if (!ok) { fail(error.compare(0, 18, "device tree build:") == 0 ? ASGPU_E_CUDA : ASGPU_E_INVALID, error); delete t; return nullptr; }
     return t;

@@ -161,24 +161,27 @@ trace_kernel(const KernelArgs args)
 const int QueueSlots = 128;         // per warp: < 32 left over + one step's candidates (more are pushed in rounds)
 const uint32_t None = 0xFFFFFFFFu;
 
-// Shared memory of one CTA, every per-thread array laid out [component][thread].
-template <int STACK>
+// Shared memory of one CTA, every per-thread array laid out [component][thread].  Arrays that only
+// the MOTION / EXTRAS instantiations use shrink to one element elsewhere: what the CTAs do not take
+// as shared memory is the SM's L1 cache, which the node fetches want.
+template <int STACK, bool MOTION, bool EXTRAS, bool LEAN, bool ANY>
 struct WideShared
 {
     uint2               stack[STACK][BlockThreads];
     double              ray[8][BlockThreads];           // current-space org, dir; tmin; tmax (= closest t so far)
     unsigned long long  tri_base[BlockThreads];         // blob offset of the current tree's wide triangle records
-    unsigned long long  pose_base[BlockThreads];        // blob offset of its pose pool
-    unsigned long long  best[BlockThreads];             // ordered key of the nearest hit of the running batch
+    unsigned long long  pose_base[MOTION ? BlockThreads : 1];   // blob offset of its pose pool
+    unsigned long long  best[ANY ? 1 : BlockThreads];   // ordered key of the nearest hit of the running batch
     unsigned long long  queue[BlockThreads / 32][QueueSlots];
     uint32_t            flags[BlockThreads];
-    float               time_n[BlockThreads];
-    float               hit_u[BlockThreads], hit_v[BlockThreads];
-    uint32_t            hit_slot[BlockThreads], hit_item[BlockThreads], hit_segment[BlockThreads];
+    float               time_n[MOTION ? BlockThreads : 1];
+    float               hit_u[ANY ? 1 : BlockThreads], hit_v[ANY ? 1 : BlockThreads];
+    uint32_t            hit_slot[ANY ? 1 : BlockThreads], hit_item[BlockThreads], hit_segment[MOTION && !ANY ? BlockThreads : 1];
     uint32_t            cur_item[BlockThreads];
-    float               world_rcp[6][BlockThreads];     // world-space reciprocal bounds (rn, rf), saved while inside an instance
-    uint32_t            world_oct[BlockThreads];
-    unsigned long long  filter_tree[BlockThreads];      // blob offset of the current tree's TreeDesc when it has intersection filters, else 0
+    float               world_ray[12][LEAN ? 1 : BlockThreads];    // world-space interval ray (o_lo, o_hi, rn, rf), saved while inside an instance
+    uint32_t            world_oct[LEAN ? 1 : BlockThreads];
+    uint32_t            key_base[ANY ? 1 : BlockThreads];       // blob offset / SectionAlign of the current tree's hit keys (closest hit: prefetch of the winner's key)
+    unsigned long long  filter_tree[EXTRAS ? BlockThreads : 1]; // blob offset of the current tree's TreeDesc when it has intersection filters, else 0
 };
 
 // Starts the fetch of one wide node (80 bytes, 16-byte aligned: at most two 128-byte lines) into L1.
@@ -215,16 +218,16 @@ __device__ __noinline__ bool filter_accept_call(const uint8_t* blob, const uint8
 // Tests `count` (<= 32) queued candidates, one per lane.  Entry = (index of the triangle record in
 // the source lane's current tree) << 5 | source lane.  Closest hit: the nearest accepted candidate of each source lane
 // updates that lane's tmax and hit record (ties: lowest queue position).  Any hit: marks the lane.
-template <bool ANY, bool COUNT, int STACK, bool EXTRAS>
+template <bool ANY, bool COUNT, bool EXTRAS, bool MOTION, typename Shared>
 __device__ __forceinline__ void test_candidates(
-    WideShared<STACK>& sm, const uint8_t* blob, const unsigned long long* entries, const unsigned count,
+    Shared& sm, const uint8_t* blob, const unsigned long long* entries, const unsigned count,
     const unsigned lane, const unsigned warp_thread0, Stats& stats)
 {
     bool hit = false;
     double t = 0.0, u = 0.0, v = 0.0;
     uint32_t slot = 0, segment = 0;
     unsigned st = warp_thread0;
-    if (!ANY) sm.best[warp_thread0 + lane] = ~0ull;
+    if (!ANY) sm.best[ANY ? 0 : warp_thread0 + lane] = ~0ull;
     if (lane < count)
     {
         const unsigned long long e = entries[lane];
@@ -235,14 +238,14 @@ __device__ __forceinline__ void test_candidates(
         ray.tmin = sm.ray[6][st];
         ray.tmax = sm.ray[7][st];
         ray.flags = sm.flags[st];
-        ray.time_normalized = sm.time_n[st];
+        ray.time_normalized = MOTION ? sm.time_n[MOTION ? st : 0] : 0.0f;
         ray.time_absolute = 0.0f;
         if (COUNT) ++stats.triangles;
         TriD tri;
-        if (fetch_triangle<ANY>(blob + sm.tri_base[st] + (e >> 5) * sizeof(TriRecord), blob + sm.pose_base[st], ray, tri, slot, segment))
+        if (fetch_triangle<ANY, MOTION>(blob + sm.tri_base[st] + (e >> 5) * sizeof(TriRecord), MOTION ? blob + sm.pose_base[MOTION ? st : 0] : nullptr, ray, tri, slot, segment))
             hit = mt_test<!ANY>(tri, ray, t, u, v);
         // Optionally filter intersections (triangletree.cpp:1404-1411; closest hit only).
-        if (!ANY && EXTRAS && hit && sm.filter_tree[st] != 0) hit = filter_accept_call(blob, blob + sm.filter_tree[st], slot, u, v);
+        if (!ANY && EXTRAS && hit && sm.filter_tree[EXTRAS ? st : 0] != 0) hit = filter_accept_call(blob, blob + sm.filter_tree[EXTRAS ? st : 0], slot, u, v);
     }
     if (ANY)
     {
@@ -254,9 +257,9 @@ __device__ __forceinline__ void test_candidates(
     if (hits == 0) return;
     __syncwarp();                                   // best[] initialised
     const unsigned long long key = ordered_key(t);
-    if (hit) atomicMin(&sm.best[st], key);
+    if (hit) atomicMin(&sm.best[ANY ? 0 : st], key);
     __syncwarp();
-    const bool win = hit && sm.best[st] == key;
+    const bool win = hit && sm.best[ANY ? 0 : st] == key;
     const unsigned winners = __ballot_sync(0xFFFFFFFFu, win);
     if (win)
     {
@@ -264,45 +267,36 @@ __device__ __forceinline__ void test_candidates(
         if (lane == static_cast<unsigned>(__ffs(peers) - 1))
         {
             sm.ray[7][st] = t;
-            sm.hit_u[st] = static_cast<float>(u);
-            sm.hit_v[st] = static_cast<float>(v);
-            sm.hit_slot[st] = slot;
-            sm.hit_segment[st] = segment;
+            sm.hit_u[ANY ? 0 : st] = static_cast<float>(u);
+            sm.hit_v[ANY ? 0 : st] = static_cast<float>(v);
+            sm.hit_slot[ANY ? 0 : st] = slot;
+            if (MOTION) sm.hit_segment[MOTION && !ANY ? st : 0] = segment;
             sm.hit_item[st] = sm.cur_item[st];
+            // The identity of the hit (store_hit reads its HitKey when the ray retires: one random
+            // 8-byte read at the end of a chain of dependent loads) starts its way up from DRAM now.
+            asm volatile("prefetch.global.L2 [%0];" :: "l"(blob + static_cast<uint64_t>(sm.key_base[ANY ? 0 : st]) * SectionAlign + static_cast<uint64_t>(slot) * sizeof(HitKey)));
         }
     }
     __syncwarp();
 }
 
-// Back from an instance: the world-space interval ray again.  Its reciprocal bounds and octant were
-// saved at instance entry; the origin interval is two conversions per axis.  (A negative tmin
-// shifts the origin along the direction: that rare case takes the full set-up.)
-template <int STACK>
-__device__ __forceinline__ void restore_world_ray(const asgpu_rays& rays, const unsigned long long index, const double tmin, const double tmax,
-                                                  const WideShared<STACK>& sm, const unsigned tid, WideRay& w)
+// Back from an instance: the world-space interval ray again, as it was saved at instance entry (12
+// floats and the octant in shared memory); only the parameter interval is new (tmax has shrunk).
+template <typename Shared>
+__device__ __forceinline__ void restore_world_ray(const double tmin, const double tmax, const Shared& sm, const unsigned tid, WideRay& w)
 {
-    if (tmin < 0.0)
-    {
-        Ray world;
-        load_ray_org_dir(rays, index, world);
-        make_wide_ray(world.org, world.dir, tmin, tmax, w);
-        return;
-    }
-    w.shift = 0.0;
+    w.shift = tmin < 0.0 ? tmin : 0.0;
     w.oct = sm.world_oct[tid];
     #pragma unroll
     for (int a = 0; a < 3; ++a)
     {
-        const double o = __ldg(rays.org + index * 3 + a);
-        const float lo = d2f_dn(o), hi = d2f_up(o);
-        const bool neg = (w.oct >> a) & 1;
-        w.o_lo[a] = neg ? -hi : lo;
-        w.o_hi[a] = neg ? -lo : hi;
-        w.rn[a] = sm.world_rcp[a][tid];
-        w.rf[a] = sm.world_rcp[3 + a][tid];
+        w.o_lo[a] = sm.world_ray[a][tid];
+        w.o_hi[a] = sm.world_ray[3 + a][tid];
+        w.rn[a] = sm.world_ray[6 + a][tid];
+        w.rf[a] = sm.world_ray[9 + a][tid];
     }
-    w.tmin_f = d2f_dn(tmin);
-    w.tmax_f = d2f_up(tmax);
+    w.tmin_f = d2f_dn(dsub(tmin, w.shift));
+    w.tmax_f = d2f_up(dsub(tmax, w.shift));
 }
 
 // LEAN = the scene has one assembly instance and no moving triangles (e.g. C2): nothing ever comes
@@ -312,12 +306,16 @@ __device__ __forceinline__ void restore_world_ray(const asgpu_rays& rays, const 
 // only then does the instantiation contain the alpha-mask lookup (closest hit) and the evaluation
 // of a transform sequence at the ray time (both cost registers: -3 % when compiled into the common
 // kernel).
-template <bool ANY, bool COUNT, int STACK, int MINB, bool LEAN, bool EXTRAS>
+// MOTION = some tree of the scene has moving triangles: only then do the instantiations contain the
+// pose interpolation of the triangle stage and the time slices of the child planes (their registers
+// cost the static scenes nothing: C3 +2 % closest hit, +4 % probes).
+template <bool ANY, bool COUNT, int STACK, int MINB, bool LEAN, bool EXTRAS, bool MOTION>
 __global__ void __launch_bounds__(BlockThreads, MINB)
 wide_kernel(const KernelArgs args)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    WideShared<STACK>& sm = *reinterpret_cast<WideShared<STACK>*>(smem_raw);
+    typedef WideShared<STACK, MOTION, EXTRAS, LEAN, ANY> Shared;
+    Shared& sm = *reinterpret_cast<Shared*>(smem_raw);
 
     const unsigned tid = threadIdx.x;
     const unsigned lane = tid & 31;
@@ -346,6 +344,8 @@ wide_kernel(const KernelArgs args)
     ngroup.x = ngroup.y = tgroup.x = tgroup.y = 0;
     uint32_t fetch = None;              // wide node to test next
     uint32_t sp = 0;
+    auto push = [&](const uint2 v) { stack[sp * stride] = v; ++sp; };
+    auto pop = [&]() -> uint2 { --sp; return stack[sp * stride]; };
     uint32_t cur_item = None;           // None while in world space
     unsigned long long index = 0;
     bool active = false;                // this lane owns a ray
@@ -372,12 +372,12 @@ wide_kernel(const KernelArgs args)
             // Save the world-space cursor, then descend.  When nothing is left to do in
             // world space there is nothing to come back to: no sentinel, the ray ends
             // with the instance.
-            if (ngroup.y & 0xFF000000u) { stack[sp * stride] = ngroup; ++sp; }
-            if (tgroup.y) { stack[sp * stride] = tgroup; ++sp; }
+            if (ngroup.y & 0xFF000000u) push(ngroup);
+            if (tgroup.y) push(tgroup);
             if (sp != 0)
             {
                 uint2 sentinel; sentinel.x = None; sentinel.y = 0;
-                stack[sp * stride] = sentinel; ++sp;
+                push(sentinel);
             }
             Ray world;
             load_ray_org_dir(args.rays, index, world);
@@ -399,7 +399,11 @@ wide_kernel(const KernelArgs args)
             {
                 // Something is left to do in world space: keep the expensive part of the world ray.
                 #pragma unroll
-                for (int k = 0; k < 3; ++k) { sm.world_rcp[k][tid] = w.rn[k]; sm.world_rcp[3 + k][tid] = w.rf[k]; }
+                for (int k = 0; k < 3; ++k)
+                {
+                    sm.world_ray[k][tid] = w.o_lo[k]; sm.world_ray[3 + k][tid] = w.o_hi[k];
+                    sm.world_ray[6 + k][tid] = w.rn[k]; sm.world_ray[9 + k][tid] = w.rf[k];
+                }
                 sm.world_oct[tid] = w.oct;
             }
             make_wide_ray(lorg, ldir, sm.ray[6][tid], sm.ray[7][tid], w);
@@ -410,20 +414,25 @@ wide_kernel(const KernelArgs args)
             const uint32_t wnode_count = load4(tp + offsetof(TreeDesc, wnode_count));
             const uint32_t wslice_count = load4(tp + offsetof(TreeDesc, wslice_count));
             wnodes = blob + (static_cast<uint64_t>(o_nodes.x) | (static_cast<uint64_t>(o_nodes.y) << 32));
-            if (!LEAN && wslice_count != 0)
+            if (MOTION && wslice_count != 0)
             {
                 // Tree with moving triangles: child planes of this ray's time slice.
                 const uint2 o_slices = load8(tp + offsetof(TreeDesc, wslices));
                 qbase = blob + (static_cast<uint64_t>(o_slices.x) | (static_cast<uint64_t>(o_slices.y) << 32))
-                      + static_cast<uint64_t>(time_slice(sm.time_n[tid], wslice_count)) * sizeof(WSlice);
+                      + static_cast<uint64_t>(time_slice(sm.time_n[MOTION ? tid : 0], wslice_count)) * sizeof(WSlice);
                 qstride = wslice_count * static_cast<uint32_t>(sizeof(WSlice));
             }
             else { qbase = wnodes + 32; qstride = sizeof(WNode); }
             sm.tri_base[tid] = static_cast<uint64_t>(o_tris.x) | (static_cast<uint64_t>(o_tris.y) << 32);
-            sm.pose_base[tid] = static_cast<uint64_t>(o_poses.x) | (static_cast<uint64_t>(o_poses.y) << 32);
+            if (!ANY)
+            {
+                const uint2 o_keys = load8(tp + offsetof(TreeDesc, keys));
+                sm.key_base[ANY ? 0 : tid] = static_cast<uint32_t>((static_cast<uint64_t>(o_keys.x) | (static_cast<uint64_t>(o_keys.y) << 32)) / SectionAlign);   // sections are SectionAlign-aligned, blobs < 1 TB
+            }
+            if (MOTION) sm.pose_base[MOTION ? tid : 0] = static_cast<uint64_t>(o_poses.x) | (static_cast<uint64_t>(o_poses.y) << 32);
             sm.cur_item[tid] = item;
             if (EXTRAS)
-                sm.filter_tree[tid] = load4(tp + offsetof(TreeDesc, filter_count)) != 0 ? s.trees + static_cast<uint64_t>(meta.x) * sizeof(TreeDesc) : 0ull;
+                sm.filter_tree[EXTRAS ? tid : 0] = load4(tp + offsetof(TreeDesc, filter_count)) != 0 ? s.trees + static_cast<uint64_t>(meta.x) * sizeof(TreeDesc) : 0ull;
             cur_item = item;
             ngroup.y = 0; tgroup.y = 0;
             if (wnode_count != 0) fetch = 0;
@@ -452,10 +461,13 @@ wide_kernel(const KernelArgs args)
                     sm.ray[6][tid] = ray.tmin;
                     sm.ray[7][tid] = ray.tmax;
                     sm.flags[tid] = ray.flags;
-                    sm.time_n[tid] = ray.time_normalized;
+                    if (MOTION) sm.time_n[MOTION ? tid : 0] = ray.time_normalized;
                     sm.hit_item[tid] = None;
-                    sm.hit_slot[tid] = 0; sm.hit_segment[tid] = 0;
-                    sm.hit_u[tid] = 0.0f; sm.hit_v[tid] = 0.0f;
+                    if (!ANY)
+                    {
+                        sm.hit_slot[ANY ? 0 : tid] = 0; if (MOTION) sm.hit_segment[MOTION && !ANY ? tid : 0] = 0;
+                        sm.hit_u[ANY ? 0 : tid] = 0.0f; sm.hit_v[ANY ? 0 : tid] = 0.0f;
+                    }
                     sm.cur_item[tid] = None;
                     make_wide_ray(ray.org, ray.dir, ray.tmin, ray.tmax, w);
                     wnodes = blob + s.top_wnodes;
@@ -501,10 +513,10 @@ wide_kernel(const KernelArgs args)
             if (fetch != None)
             {
                 if (COUNT) { if (cur_item != None) ++stats.nodes; else ++stats.top_nodes; }
-                if (ngroup.y & 0xFF000000u) { stack[sp * stride] = ngroup; ++sp; }
+                if (ngroup.y & 0xFF000000u) push(ngroup);
                 uint32_t child_base, tri_base, nmask, tmask;
                 const uint8_t* np = wnodes + static_cast<uint64_t>(fetch) * sizeof(WNode);
-                wide_node_test(np, LEAN ? np + 32 : qbase + static_cast<uint64_t>(fetch) * qstride, w, args.unit_bits, child_base, tri_base, nmask, tmask);
+                wide_node_test(np, !MOTION ? np + 32 : qbase + static_cast<uint64_t>(fetch) * qstride, w, args.unit_bits, child_base, tri_base, nmask, tmask);
                 ngroup.x = child_base; ngroup.y = nmask;
                 if (cur_item != None) { pending = tmask; tri_first = tri_base; }
                 else { tgroup.x = tri_base; tgroup.y = tmask; }
@@ -532,8 +544,7 @@ wide_kernel(const KernelArgs args)
                         if (sp == 0) traversed = true;
                         else
                         {
-                            --sp;
-                            const uint2 top = stack[sp * stride];
+                            const uint2 top = pop();
                             if (top.x == None && top.y == 0)
                             {
                                 // Back to world space: the world ray comes from the ray arrays again.
@@ -544,7 +555,7 @@ wide_kernel(const KernelArgs args)
                                     load_ray_org_dir(args.rays, index, world);
                                     make_wide_ray(world.org, world.dir, sm.ray[6][tid], sm.ray[7][tid], w);
                                 }
-                                else restore_world_ray(args.rays, index, sm.ray[6][tid], sm.ray[7][tid], sm, tid, w);
+                                else restore_world_ray(sm.ray[6][tid], sm.ray[7][tid], sm, tid, w);
                                 wnodes = blob + s.top_wnodes;
                                 qbase = wnodes + 32; qstride = sizeof(WNode);
                                 cur_item = None;
@@ -614,7 +625,7 @@ wide_kernel(const KernelArgs args)
                 while (queued >= 32)
                 {
                     queued -= 32;
-                    test_candidates<ANY, COUNT, STACK, EXTRAS>(sm, blob, queue + queued, 32, lane, warp_thread0, stats);
+                    test_candidates<ANY, COUNT, EXTRAS, MOTION>(sm, blob, queue + queued, 32, lane, warp_thread0, stats);
                     tested = true;
                 }
             }
@@ -635,7 +646,7 @@ wide_kernel(const KernelArgs args)
                     if (queued >= 32)
                     {
                         queued -= 32;
-                        test_candidates<ANY, COUNT, STACK, EXTRAS>(sm, blob, queue + queued, 32, lane, warp_thread0, stats);
+                        test_candidates<ANY, COUNT, EXTRAS, MOTION>(sm, blob, queue + queued, 32, lane, warp_thread0, stats);
                         tested = true;
                     }
                     pushers = __ballot_sync(0xFFFFFFFFu, pending != 0);
@@ -649,7 +660,7 @@ wide_kernel(const KernelArgs args)
             const unsigned stalled = __ballot_sync(0xFFFFFFFFu, !active || held || (traversed && waiting));
             if (queued >= args.flush_threshold || __popc(stalled) >= args.stall_threshold)
             {
-                test_candidates<ANY, COUNT, STACK, EXTRAS>(sm, blob, queue, queued, lane, warp_thread0, stats);
+                test_candidates<ANY, COUNT, EXTRAS, MOTION>(sm, blob, queue, queued, lane, warp_thread0, stats);
                 queued = 0;
                 tested = true;
             }
@@ -674,8 +685,8 @@ wide_kernel(const KernelArgs args)
                 else
                 {
                     Hit hit;
-                    hit.u = sm.hit_u[tid]; hit.v = sm.hit_v[tid];
-                    hit.item = sm.hit_item[tid]; hit.slot = sm.hit_slot[tid]; hit.segment = sm.hit_segment[tid];
+                    hit.u = sm.hit_u[ANY ? 0 : tid]; hit.v = sm.hit_v[ANY ? 0 : tid];
+                    hit.item = sm.hit_item[tid]; hit.slot = sm.hit_slot[ANY ? 0 : tid]; hit.segment = MOTION ? sm.hit_segment[MOTION && !ANY ? tid : 0] : 0u;
                     store_hit(args.hits + index, s, sm.ray[7][tid], hit, found, args.raw_item != 0);
                 }
                 if (COUNT) { ++rays_done; hits_found += found ? 1 : 0; }
@@ -782,25 +793,25 @@ cudaError_t launch_persistent(Kernel kernel, const KernelArgs& args, const size_
 // and run ~10 % slower (profiles/README.md).
 const int WideMinBlocks = 5;
 
-template <int STACK, bool LEAN, bool EXTRAS>
+template <int STACK, bool LEAN, bool EXTRAS, bool MOTION>
 cudaError_t launch_wide(const KernelArgs& args, const bool any_hit, const bool count, const int sm_count, cudaStream_t stream)
 {
-    const size_t smem = sizeof(WideShared<STACK>);
+    const size_t smem = any_hit ? sizeof(WideShared<STACK, MOTION, EXTRAS, LEAN, true>) : sizeof(WideShared<STACK, MOTION, EXTRAS, LEAN, false>);
     // (Shadow probes ignore intersection filters -- TriangleLeafProbeVisitor has none -- but do see animated instances.)
-    if (any_hit) return count ? launch_persistent(wide_kernel<true, true, STACK, WideMinBlocks, LEAN, EXTRAS>, args, smem, sm_count, stream)
-                              : launch_persistent(wide_kernel<true, false, STACK, WideMinBlocks, LEAN, EXTRAS>, args, smem, sm_count, stream);
-    return count ? launch_persistent(wide_kernel<false, true, STACK, WideMinBlocks, LEAN, EXTRAS>, args, smem, sm_count, stream)
-                 : launch_persistent(wide_kernel<false, false, STACK, WideMinBlocks, LEAN, EXTRAS>, args, smem, sm_count, stream);
+    if (any_hit) return count ? launch_persistent(wide_kernel<true, true, STACK, WideMinBlocks, LEAN, EXTRAS, MOTION>, args, smem, sm_count, stream)
+                              : launch_persistent(wide_kernel<true, false, STACK, WideMinBlocks, LEAN, EXTRAS, MOTION>, args, smem, sm_count, stream);
+    return count ? launch_persistent(wide_kernel<false, true, STACK, WideMinBlocks, LEAN, EXTRAS, MOTION>, args, smem, sm_count, stream)
+                 : launch_persistent(wide_kernel<false, false, STACK, WideMinBlocks, LEAN, EXTRAS, MOTION>, args, smem, sm_count, stream);
 }
 
-template <bool LEAN, bool EXTRAS>
+template <bool LEAN, bool EXTRAS, bool MOTION>
 cudaError_t launch_wide_depth(const KernelArgs& args, const uint32_t stack_need, const bool any_hit, const bool count, const int sm_count, cudaStream_t stream)
 {
     // The traversal stack lives in shared memory; its depth is the scene's (flatten.cpp computes
     // the bound), rounded up to one of the compiled variants.
-    if (stack_need <= 16) return launch_wide<16, LEAN, EXTRAS>(args, any_hit, count, sm_count, stream);
-    if (stack_need <= 24) return launch_wide<24, LEAN, EXTRAS>(args, any_hit, count, sm_count, stream);
-    return launch_wide<WideStackMax, LEAN, EXTRAS>(args, any_hit, count, sm_count, stream);
+    if (stack_need <= 16) return launch_wide<16, LEAN, EXTRAS, MOTION>(args, any_hit, count, sm_count, stream);
+    if (stack_need <= 24) return launch_wide<24, LEAN, EXTRAS, MOTION>(args, any_hit, count, sm_count, stream);
+    return launch_wide<WideStackMax, LEAN, EXTRAS, MOTION>(args, any_hit, count, sm_count, stream);
 }
 
 }   // anonymous namespace
@@ -862,9 +873,10 @@ int launch_trace(
     {
         const bool extras = scene.has_filters || scene.has_animated;
         const bool lean = scene.item_count <= 1 && !scene.has_motion && !extras && lean_allowed;
-        if (lean) err = launch_wide_depth<true, false>(args, scene.wide_stack_need, any_hit, count, sm_count, stream);
-        else if (extras) err = launch_wide_depth<false, true>(args, scene.wide_stack_need, any_hit, count, sm_count, stream);
-        else err = launch_wide_depth<false, false>(args, scene.wide_stack_need, any_hit, count, sm_count, stream);
+        if (lean) err = launch_wide_depth<true, false, false>(args, scene.wide_stack_need, any_hit, count, sm_count, stream);
+        else if (extras) err = launch_wide_depth<false, true, true>(args, scene.wide_stack_need, any_hit, count, sm_count, stream);
+        else if (scene.has_motion) err = launch_wide_depth<false, false, true>(args, scene.wide_stack_need, any_hit, count, sm_count, stream);
+        else err = launch_wide_depth<false, false, false>(args, scene.wide_stack_need, any_hit, count, sm_count, stream);
     }
     else if (any_hit) err = count ? launch_persistent(trace_kernel<true, true>, args, 0, sm_count, stream)
                                   : launch_persistent(trace_kernel<true, false>, args, 0, sm_count, stream);

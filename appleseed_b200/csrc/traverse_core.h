@@ -416,7 +416,8 @@ ASGPU_HD bool mt_test(const TriD& tri, const Ray& ray, double& t, double& u, dou
 // Loads the triangle of one record for this ray's time.  Returns false when the triangle is
 // invisible to the ray (triangletree.cpp:1389-1393, 1426-1430).  Moving triangles follow
 // triangletree.cpp:1432-1451 (closest hit: float product) / :1570-1585 (probe: double product).
-template <bool ANY>
+// MOTION = false: the caller knows the scene has no moving triangle (the pose code is compiled out).
+template <bool ANY, bool MOTION = true>
 ASGPU_HD bool fetch_triangle(const uint8_t* record, const uint8_t* poses, const Ray& ray, TriD& tri, uint32_t& slot, uint32_t& segment)
 {
     const uint4 a = load16(record);
@@ -427,7 +428,7 @@ ASGPU_HD bool fetch_triangle(const uint8_t* record, const uint8_t* poses, const 
     segment = 0;
     if (!(vis & ray.flags)) return false;
     float f[9];
-    if (c.w == 0)
+    if (!MOTION || c.w == 0)
     {
         f[0] = u2f(a.x); f[1] = u2f(a.y); f[2] = u2f(a.z); f[3] = u2f(a.w);
         f[4] = u2f(b.x); f[5] = u2f(b.y); f[6] = u2f(b.z); f[7] = u2f(b.w);

@@ -87,6 +87,13 @@ typedef bool (*LbvhTopologyFn)(const float* boxes, size_t n, const float root_lo
 bool lbvh_topology_device(const float* boxes, size_t n, const float root_lo[3], const float root_hi[3], void* context,
                           LbvhTopology& out, std::string& error);
 
+// The product's default LbvhTopologyFn (ploc.cu): parallel locally-ordered clustering over the same
+// Morton order -- surface-area driven topology, same output arrays.  ASGPU_PLOC_RADIUS (1..32,
+// default 16) sets the search radius.
+bool ploc_topology_device(const float* boxes, size_t n, const float root_lo[3], const float root_hi[3], void* context,
+                          LbvhTopology& out, std::string& error);
+int ploc_radius();
+
 // Returns false and fills `error` on malformed input.  `lbvh` = null: the reference's sweep SAH for
 // every tree (result-identical to the reference); else the triangle trees take their topology from
 // `lbvh(..., lbvh_context, ...)` (the small assembly tree always uses the sweep).

@@ -470,6 +470,8 @@ struct asgpu_path_stream
     uint8_t*                occluded = nullptr;
     uint32_t*               image = nullptr;
     uint32_t*               tiles_dev = nullptr;
+    uint32_t*               tile_pixels = nullptr;  // staging of asgpu_path_stream_read_tiles
+    size_t                  tile_pixels_bytes = 0;
     unsigned long long*     stats_dev = nullptr;
     unsigned long long*     cursors = nullptr;      // ray-queue cursors of the trace launches (ring)
     uint64_t                cursor_next = 0;
@@ -766,7 +768,7 @@ void asgpu_path_stream_destroy(asgpu_path_stream* ps)
     if (!ps) return;
     cudaSetDevice(ps->scene->device);
     asgpu_queue_destroy(ps->qa); asgpu_queue_destroy(ps->qb); asgpu_queue_destroy(ps->qp);
-    cudaFree(ps->hits); cudaFree(ps->refined); cudaFree(ps->occluded); cudaFree(ps->image); cudaFree(ps->tiles_dev);
+    cudaFree(ps->hits); cudaFree(ps->refined); cudaFree(ps->occluded); cudaFree(ps->image); cudaFree(ps->tiles_dev); cudaFree(ps->tile_pixels);
     cudaFree(ps->stats_dev); cudaFree(ps->cursors);
     for (cudaEvent_t e : ps->event_pool) cudaEventDestroy(e);
     delete ps;
@@ -857,6 +859,58 @@ int asgpu_path_stream_read_image(asgpu_path_stream* ps, uint32_t* accum)
     ASGPU_CUDA(cudaSetDevice(ps->scene->device), "cudaSetDevice");
     ASGPU_CUDA(cudaDeviceSynchronize(), "cudaDeviceSynchronize");
     ASGPU_CUDA(cudaMemcpy(accum, ps->image, static_cast<size_t>(ps->desc.width) * ps->desc.height * 16, cudaMemcpyDeviceToHost), "cudaMemcpy(image)");
+    return ASGPU_OK;
+}
+
+namespace
+{
+
+// Pixels of the listed tiles, tile after tile (tile_size x tile_size x 4 words each, row-major inside
+// the tile; pixels of an edge tile that fall outside the image are zero).
+__global__ void gather_tiles_kernel(const uint32_t* image, const uint32_t* tiles, const size_t tile_count, const uint32_t width, const uint32_t height,
+                                    const uint32_t tile_size, const uint32_t tiles_x, uint4* out)
+{
+    const size_t per_tile = static_cast<size_t>(tile_size) * tile_size;
+    const size_t total = tile_count * per_tile;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    {
+        const uint32_t tile = tiles[i / per_tile];
+        const uint32_t in_tile = static_cast<uint32_t>(i % per_tile);
+        const uint32_t x = (tile % tiles_x) * tile_size + in_tile % tile_size;
+        const uint32_t y = (tile / tiles_x) * tile_size + in_tile / tile_size;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (x < width && y < height) v = reinterpret_cast<const uint4*>(image)[static_cast<size_t>(y) * width + x];
+        out[i] = v;
+    }
+}
+
+}   // anonymous namespace
+
+int asgpu_path_stream_read_tiles(asgpu_path_stream* ps, const uint32_t* tiles, size_t tile_count, uint32_t* accum)
+{
+    if (!ps || !accum || (!tiles && tile_count != 0)) return fail(ASGPU_E_INVALID, "null argument");
+    const uint32_t all_tiles = ps->tiles_x * ps->tiles_y;
+    if (tile_count > all_tiles) return fail(ASGPU_E_INVALID, "more tiles than the image has");
+    for (size_t i = 0; i < tile_count; ++i)
+        if (tiles[i] >= all_tiles) return fail(ASGPU_E_INVALID, "tile index out of range");
+    if (tile_count == 0) return ASGPU_OK;
+    ASGPU_CUDA(cudaSetDevice(ps->scene->device), "cudaSetDevice");
+    const size_t bytes = tile_count * ps->desc.tile_size * ps->desc.tile_size * 16;
+    if (bytes > ps->tile_pixels_bytes)
+    {
+        cudaFree(ps->tile_pixels);
+        ps->tile_pixels = nullptr; ps->tile_pixels_bytes = 0;
+        ASGPU_CUDA(cudaMalloc(&ps->tile_pixels, bytes), "cudaMalloc(tile pixels)");
+        ps->tile_pixels_bytes = bytes;
+    }
+    // Legacy default stream: ordered after the render calls whatever (blocking) stream they used,
+    // like the cudaDeviceSynchronize of asgpu_path_stream_read_image.
+    ASGPU_CUDA(cudaDeviceSynchronize(), "cudaDeviceSynchronize");
+    ASGPU_CUDA(cudaMemcpy(ps->tiles_dev, tiles, tile_count * 4, cudaMemcpyHostToDevice), "cudaMemcpy(tiles)");
+    gather_tiles_kernel<<<stage_grid(ps->scene), StageThreads>>>(ps->image, ps->tiles_dev, tile_count, ps->desc.width, ps->desc.height,
+                                                                ps->desc.tile_size, ps->tiles_x, reinterpret_cast<uint4*>(ps->tile_pixels));
+    ASGPU_CUDA(cudaGetLastError(), "gather_tiles_kernel");
+    ASGPU_CUDA(cudaMemcpy(accum, ps->tile_pixels, bytes, cudaMemcpyDeviceToHost), "cudaMemcpy(tile pixels)");
     return ASGPU_OK;
 }
 

@@ -167,6 +167,29 @@ class PathStream:
         _check(self.lib.asgpu_path_stream_read_image(self.handle, out.ctypes.data), "asgpu_path_stream_read_image")
         return out
 
+    def image_tiles(self, tiles: Sequence[int], out: Optional[np.ndarray] = None) -> np.ndarray:
+        """Accumulators of the listed tiles only (len(tiles) x tile_size x tile_size x 4 uint32, zero
+        outside the image): what a process that rendered a share of the frame reads back."""
+        t = np.ascontiguousarray(tiles, dtype=np.uint32)
+        ts = self.config.tile_size
+        if out is None:
+            out = np.empty((len(t), ts, ts, 4), dtype=np.uint32)
+        assert out.dtype == np.uint32 and out.size == len(t) * ts * ts * 4 and out.flags.c_contiguous
+        _check(self.lib.asgpu_path_stream_read_tiles(self.handle, t.ctypes.data if len(t) else None, len(t), out.ctypes.data), "asgpu_path_stream_read_tiles")
+        return out.reshape(len(t), ts, ts, 4)
+
+    def scatter_tiles(self, tiles: Sequence[int], pixels: np.ndarray, image: Optional[np.ndarray] = None) -> np.ndarray:
+        """Writes tile pixels (image_tiles) into a height x width x 4 image (host side)."""
+        h, w, ts = self.config.height, self.config.width, self.config.tile_size
+        if image is None:
+            image = np.zeros((h, w, 4), dtype=np.uint32)
+        tiles_x = (w + ts - 1) // ts
+        for k, tile in enumerate(np.asarray(tiles, dtype=np.int64)):
+            x0, y0 = int(tile % tiles_x) * ts, int(tile // tiles_x) * ts
+            x1, y1 = min(x0 + ts, w), min(y0 + ts, h)
+            image[y0:y1, x0:x1] = pixels[k, : y1 - y0, : x1 - x0]
+        return image
+
     def clear(self):
         _check(self.lib.asgpu_path_stream_clear(self.handle), "asgpu_path_stream_clear")
 

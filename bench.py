@@ -746,16 +746,19 @@ def run_gpu_c5(args):
     launches = st["kernel_launches"]
 
     # ---- end to end: clear, tile list in, image out, through the public API (host buffers) ----
-    image_host = torch.empty((args.height, args.width, 4), dtype=torch.int32).pin_memory().numpy().view(np.uint32)
+    # Every rank reads back the pixels of ITS tiles (asgpu_path_stream_read_tiles): 1 / N of the frame.
+    ts = cfg["tile_size"]
+    image_host = torch.empty((len(tiles), ts, ts, 4), dtype=torch.int32).pin_memory().numpy().view(np.uint32)
     D.barrier()
     t0 = time.perf_counter()
     e2e_steps = max(1, min(args.steps, 3))
     for _ in range(e2e_steps):
         ps.clear()
         ps.render(tiles)
-        image = ps.image(out=image_host)
+        image = ps.image_tiles(tiles, out=image_host)
     e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
     D.barrier()
+    assert int(ps.image().astype(np.uint64).sum()) == int(image.astype(np.uint64).sum()), "tile read-back differs from the frame"
     # One frame's accumulators of this rank's pixels; summed over ranks it does not depend on N.
     checksum = int(image.astype(np.uint64).sum())
 
@@ -774,7 +777,7 @@ def run_gpu_c5(args):
     bpr_probe = bytes_per_ray(pr_probe, ray_in + parent_bytes, 1.0, False)
 
     ms_step, e2e_ms = D.max([ms_step, e2e_ms])
-    total_rays, total_closest, total_probe, checksum, launches = D.sum([rays_step, closest_step, probe_step, checksum, launches])
+    total_rays, total_closest, total_probe, checksum, launches, tiles_total = D.sum([rays_step, closest_step, probe_step, checksum, launches, len(tiles)])
     value = total_rays / (ms_step * 1e-3) / 1e6
     line = None
     if D.rank == 0:
@@ -808,8 +811,8 @@ def run_gpu_c5(args):
                 "rank0_probe_mrays_s": round(probe_step / (prof["probe_ms"] / args.steps) / 1e3, 1) if prof["probe_ms"] else None,
             },
             "e2e": {"value": total_rays / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(len(tiles)) * 4 * D.world,
-                    "d2h_bytes_per_step": args.width * args.height * 16 * D.world, "ms_per_step": e2e_ms,
-                    "note": "tile list in, image out through asgpu_path_stream_render + _read_image; the rays are generated, traced and shaded on the device"},
+                    "d2h_bytes_per_step": int(tiles_total) * ts * ts * 16, "ms_per_step": e2e_ms,
+                    "note": "tile list in, this rank's tiles of the image out through asgpu_path_stream_render + _read_tiles; the rays are generated, traced and shaded on the device"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic_per_ray * closest_rays_per_launch if traffic_per_ray is not None else None,

@@ -524,6 +524,11 @@ int             asgpu_path_stream_render(asgpu_path_stream* stream, const uint32
 /* Per pixel accumulators, HOST array of width * height * 4 uint32_t:
  * [0] surface hits, [1] unoccluded shadow probes, [2] escaped rays, [3] sum of hit-identity hashes.  Synchronises. */
 int             asgpu_path_stream_read_image(asgpu_path_stream* stream, uint32_t* accum);
+/* The same accumulators for the listed tiles only, HOST array of tile_count * tile_size * tile_size * 4
+ * uint32_t: tile after tile in list order, row-major inside a tile, zero where an edge tile sticks
+ * out of the image.  With the tiles of a frame dealt to several GPUs every process reads back its
+ * own tiles (1 / N of the image) instead of the whole frame.  Synchronises. */
+int             asgpu_path_stream_read_tiles(asgpu_path_stream* stream, const uint32_t* tiles, size_t tile_count, uint32_t* accum);
 int             asgpu_path_stream_clear(asgpu_path_stream* stream);
 int             asgpu_path_stream_get_stats(asgpu_path_stream* stream, asgpu_path_stream_stats* out);
 /* Test hook: keep a copy of every wavefront's rays and results of the NEXT render call (HOST side,

@@ -10,6 +10,7 @@
 #include "../../appleseed_b200/csrc/flatten.h"
 #include "../../appleseed_b200/csrc/refine_core.h"
 #include "../../appleseed_b200/csrc/lbvh_core.h"
+#include "../../appleseed_b200/csrc/ploc_core.h"
 #include "../../appleseed_b200/csrc/traverse_core.h"
 #include "../../appleseed_b200/csrc/tree_builder.h"
 
@@ -120,7 +121,92 @@ static bool lbvh_topology_host(const float* boxes, size_t n, const float root_lo
     return true;
 }
 
+// Sequential host run of ploc_core.h -- what ploc.cu computes with one thread per cluster: the same
+// rounds (nearest / fate / prefix sum / merge), the same node numbering (n - 2 downwards, in cluster
+// order within a round), the same hand-down of the leaf ranges.
+static int g_ploc_radius = 16;
+
+static bool ploc_topology_host(const float* boxes, size_t n, const float root_lo[3], const float root_hi[3], void*, LbvhTopology& out, std::string& error)
+{
+    float origin[3], scale[3];
+    for (int a = 0; a < 3; ++a)
+    {
+        const float extent = 2.0f * (root_hi[a] - root_lo[a]);
+        origin[a] = 2.0f * root_lo[a];
+        scale[a] = extent > 0.0f ? 2097152.0f / extent : 0.0f;
+    }
+    std::vector<uint64_t> keys(n);
+    std::vector<uint32_t> sorted_ids(n);
+    for (size_t i = 0; i < n; ++i) { keys[i] = lbvh_morton(boxes + i * 6, origin, scale); sorted_ids[i] = static_cast<uint32_t>(i); }
+    std::stable_sort(sorted_ids.begin(), sorted_ids.end(), [&keys](uint32_t a, uint32_t b) { return keys[a] < keys[b]; });
+
+    out.order.assign(n, 0); out.left.assign(n - 1, 0); out.right.assign(n - 1, 0); out.first.assign(n - 1, 0); out.last.assign(n - 1, 0);
+    out.node_boxes.assign((n - 1) * 6, 0.0f);
+    std::vector<uint32_t> leaves(n - 1, 0);
+    std::vector<float> cbox(n * 6), obox;
+    std::vector<uint32_t> cref(n), ccount(n, 1), oref, ocount, nearest;
+    for (size_t i = 0; i < n; ++i)
+    {
+        for (int k = 0; k < 6; ++k) cbox[i * 6 + k] = boxes[size_t(sorted_ids[i]) * 6 + k];
+        cref[i] = static_cast<uint32_t>(i) | LbvhLeafFlag;
+    }
+    std::vector<std::pair<uint32_t, uint32_t>> rounds;
+    uint32_t clusters = static_cast<uint32_t>(n), next_node = static_cast<uint32_t>(n) - 2;
+    while (clusters > 1)
+    {
+        nearest.resize(clusters);
+        const float* base = cbox.data();
+        auto box_at = [base](const uint32_t k) -> const float* { return base + size_t(k) * 6; };
+        for (uint32_t i = 0; i < clusters; ++i) nearest[i] = ploc_nearest(box_at, clusters, i, g_ploc_radius);
+        obox.clear(); oref.clear(); ocount.clear();
+        uint32_t created = 0;
+        for (uint32_t i = 0; i < clusters; ++i)
+        {
+            const uint64_t f = ploc_fate(nearest.data(), i);
+            if (!(f & 1ull)) continue;
+            float box[6];
+            for (int k = 0; k < 6; ++k) box[k] = cbox[size_t(i) * 6 + k];
+            uint32_t ref = cref[i], count = ccount[i];
+            if (f >> 32)
+            {
+                const uint32_t j = nearest[i], node = next_node - created;
+                ++created;
+                for (int k = 0; k < 3; ++k)
+                {
+                    box[k] = ploc_min(box[k], cbox[size_t(j) * 6 + k]);
+                    box[3 + k] = ploc_max(box[3 + k], cbox[size_t(j) * 6 + 3 + k]);
+                }
+                out.left[node] = ref; out.right[node] = cref[j];
+                count += ccount[j];
+                leaves[node] = count;
+                for (int k = 0; k < 6; ++k) out.node_boxes[size_t(node) * 6 + k] = box[k];
+                ref = node;
+            }
+            for (int k = 0; k < 6; ++k) obox.push_back(box[k]);
+            oref.push_back(ref); ocount.push_back(count);
+        }
+        if (created == 0) { error = "a clustering round made no progress"; return false; }
+        rounds.push_back(std::make_pair(next_node - (created - 1), next_node + 1));
+        next_node -= created;
+        clusters = static_cast<uint32_t>(oref.size());
+        cbox.swap(obox); cref.swap(oref); ccount.swap(ocount);
+    }
+    out.first[0] = 0; out.last[0] = static_cast<uint32_t>(n) - 1;
+    for (size_t k = rounds.size(); k-- > 0; )
+        for (uint32_t node = rounds[k].first; node < rounds[k].second; ++node)
+        {
+            const uint32_t f = out.first[node], e = out.last[node], l = out.left[node], r = out.right[node];
+            const uint32_t left_leaves = (l & LbvhLeafFlag) ? 1u : leaves[l];
+            if (l & LbvhLeafFlag) { out.order[f] = sorted_ids[l & ~LbvhLeafFlag]; out.left[node] = f | LbvhLeafFlag; }
+            else { out.first[l] = f; out.last[l] = f + left_leaves - 1; }
+            if (r & LbvhLeafFlag) { out.order[e] = sorted_ids[r & ~LbvhLeafFlag]; out.right[node] = e | LbvhLeafFlag; }
+            else { out.first[r] = f + left_leaves; out.last[r] = e; }
+        }
+    return true;
+}
+
 static bool g_use_lbvh = false;
+static bool g_use_ploc = false;
 
 extern "C" {
 
@@ -139,7 +225,7 @@ void* hostsim_scene_create_filtered(const asgpu_scene_desc* desc, uint32_t flags
                                     const uint32_t* filter_tree, const uint32_t* filter_object, const asgpu_intersection_filter* filters)
 {
     HostTrees trees;
-    if (!build_host_trees(*desc, threads, trees, g_error, g_use_lbvh ? lbvh_topology_host : nullptr)) return nullptr;
+    if (!build_host_trees(*desc, threads, trees, g_error, g_use_ploc ? ploc_topology_host : (g_use_lbvh ? lbvh_topology_host : nullptr))) return nullptr;
     std::vector<asgpu_triangle_tree_view> views(trees.triangle_trees.size());
     for (size_t i = 0; i < views.size(); ++i)
     {
@@ -207,6 +293,16 @@ void* hostsim_scene_create_lbvh(const asgpu_scene_desc* desc, uint32_t flags, in
     g_use_lbvh = true;
     void* s = hostsim_scene_create_filtered(desc, flags, threads, 0, nullptr, nullptr, nullptr);
     g_use_lbvh = false;
+    return s;
+}
+
+// Same with the topology of ploc.cu (search radius as ASGPU_PLOC_RADIUS sets it for the product).
+void* hostsim_scene_create_ploc(const asgpu_scene_desc* desc, uint32_t flags, int threads, int radius)
+{
+    g_use_ploc = true;
+    g_ploc_radius = radius < 1 ? 1 : (radius > PlocMaxRadius ? PlocMaxRadius : radius);
+    void* s = hostsim_scene_create_filtered(desc, flags, threads, 0, nullptr, nullptr, nullptr);
+    g_use_ploc = false;
     return s;
 }
 

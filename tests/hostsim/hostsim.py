@@ -22,6 +22,8 @@ def load():
     lib.hostsim_scene_create_filtered.argtypes = [C.POINTER(CSceneDesc), C.c_uint32, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.hostsim_scene_create_lbvh.restype = C.c_void_p
     lib.hostsim_scene_create_lbvh.argtypes = [C.POINTER(CSceneDesc), C.c_uint32, C.c_int]
+    lib.hostsim_scene_create_ploc.restype = C.c_void_p
+    lib.hostsim_scene_create_ploc.argtypes = [C.POINTER(CSceneDesc), C.c_uint32, C.c_int, C.c_int]
     lib.hostsim_scene_create_views.restype = C.c_void_p
     lib.hostsim_scene_create_views.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32]
     lib.hostsim_scene_destroy.argtypes = [C.c_void_p]
@@ -40,16 +42,19 @@ def load():
 
 
 class SimScene:
-    def __init__(self, lib, desc: SceneDesc, flags=SCENE_EXACT | SCENE_WIDE, threads=4, filters=None, lbvh=False):
+    def __init__(self, lib, desc: SceneDesc, flags=SCENE_EXACT | SCENE_WIDE, threads=4, filters=None, lbvh=False, ploc=0):
         """``filters``: {(triangle tree index, object instance index): scene.IntersectionFilter};
-        ``lbvh``: triangle trees as asgpu_trees_build_on_device makes them (topology from a sequential
-        host run of lbvh_core.h)."""
+        ``lbvh`` / ``ploc`` (= search radius): triangle trees as asgpu_trees_build_on_device makes them
+        (topology from a sequential host run of lbvh_core.h / ploc_core.h)."""
         from appleseed_b200.scene import CIntersectionFilter
         self.lib = lib
         self._cdesc, self._keep = desc.to_c()
-        if lbvh:
+        if lbvh or ploc:
             assert not filters
-            self.handle = lib.hostsim_scene_create_lbvh(C.byref(self._cdesc), flags, threads)
+            if ploc:
+                self.handle = lib.hostsim_scene_create_ploc(C.byref(self._cdesc), flags, threads, int(ploc))
+            else:
+                self.handle = lib.hostsim_scene_create_lbvh(C.byref(self._cdesc), flags, threads)
             if not self.handle:
                 raise RuntimeError(lib.hostsim_last_error().decode())
             return

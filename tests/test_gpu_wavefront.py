@@ -315,3 +315,25 @@ def test_stream_profile_times_every_trace_launch(setup):
     ps.clear()
     assert ps.profile()["closest_launches"] == 0
     ps.close()
+
+
+def test_tile_read_back_equals_the_frame(setup):
+    """asgpu_path_stream_read_tiles: the pixels of a rank's own tiles (what a tile-sharded renderer
+    reads back) scatter into exactly the frame asgpu_path_stream_read_image returns; edge tiles
+    that stick out of the image (height 56 = 3.5 tiles of 16) are zero-padded; bad lists are refused."""
+    desc, ctx, wavefront, cfg = setup
+    ps = wavefront.PathStream(ctx, wavefront.PathStreamConfig(**cfg), queue_capacity=1 << 18)
+    n_tiles = ps.tile_count
+    mine = np.arange(n_tiles, dtype=np.uint32)[1::2][::-1].copy()          # a shard, in an order of its own
+    ps.render(mine)
+    frame = ps.image()
+    px = ps.image_tiles(mine)
+    assert px.shape == (len(mine), cfg["tile_size"], cfg["tile_size"], 4)
+    assert np.array_equal(ps.scatter_tiles(mine, px), frame)
+    assert int(px.astype(np.uint64).sum()) == int(frame.astype(np.uint64).sum()) > 0
+    others = np.arange(n_tiles, dtype=np.uint32)[0::2]
+    assert not ps.image_tiles(others).any()                                # tiles nobody rendered
+    assert ps.image_tiles(np.zeros(0, dtype=np.uint32)).shape[0] == 0
+    with pytest.raises(Exception):
+        ps.image_tiles(np.array([n_tiles], dtype=np.uint32))
+    ps.close()

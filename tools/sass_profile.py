@@ -18,14 +18,14 @@ import subprocess
 import tempfile
 
 
-def disasm_lines(lib, func):
+def disasm_lines(lib, func, outer=False):
     tmp = tempfile.mkdtemp()
     subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=tmp, check=True, stdout=subprocess.DEVNULL)
     out = []
     for name in sorted(os.listdir(tmp)):
         if not name.endswith(".cubin"):
             continue
-        text = subprocess.run(["nvdisasm", "--print-line-info", os.path.join(tmp, name)], capture_output=True, text=True).stdout
+        text = subprocess.run(["nvdisasm", "--print-line-info-inline" if outer else "--print-line-info", os.path.join(tmp, name)], capture_output=True, text=True).stdout
         cur, inside, line = None, False, ("?", 0)
         for l in text.splitlines():
             if l.startswith(".text."):
@@ -38,6 +38,8 @@ def disasm_lines(lib, func):
                 continue
             m = re.search(r'//## File "([^"]+)", line (\d+)', l)
             if m:
+                # With inline info the chain runs innermost first; the last entry before the
+                # instruction is the outermost call site (a line of the kernel itself).
                 line = (os.path.basename(m.group(1)), int(m.group(2)))
                 continue
             m = re.match(r"\s+/\*([0-9a-f]{4,})\*/\s+(.*?);", l)
@@ -54,6 +56,8 @@ def main():
     ap.add_argument("--lib", default="appleseed_b200/libasgpu.so")
     ap.add_argument("--top", type=int, default=40)
     ap.add_argument("--sass", action="store_true", help="also list the hottest SASS instructions")
+    ap.add_argument("--outer", action="store_true", help="attribute inlined code to the outermost call site (a line of the kernel)")
+    ap.add_argument("--regions", default="", help="with --outer: 'name=first-last,...' kernel line ranges summed into named regions")
     args = ap.parse_args()
 
     raw = subprocess.run(["ncu", "-i", args.report, "--page", "source", "--csv"], capture_output=True, text=True).stdout
@@ -68,7 +72,7 @@ def main():
     name, hdr, body = blocks[args.block]
     print("launch %d of %d: %s" % (args.block, len(blocks), name[:100]))
     col = {n: hdr.index(n) for n in hdr}
-    sass = disasm_lines(args.lib, args.func)
+    sass = disasm_lines(args.lib, args.func, args.outer)
     if len(sass) != len(body):
         print("warning: %d profiled instructions vs %d disassembled (library differs from the profiled one?)" % (len(body), len(sass)))
     n = min(len(sass), len(body))
@@ -89,6 +93,22 @@ def main():
     for key, v in sorted(per_line.items(), key=lambda kv: -kv[1][0])[: args.top]:
         print("%-28s %6d %7.2f %7.1f %7.2f %8.2f" % ("%s:%d" % key, v[4], 100 * v[0] / tot[0], v[1] / max(v[0], 1),
                                                      100 * v[2] / max(tot[2], 1), 100 * v[3] / max(tot[2], 1)))
+    if args.regions:
+        regions = []
+        for part in args.regions.split(","):
+            nm, rng = part.split("=")
+            lo, hi = rng.split("-")
+            regions.append((nm, int(lo), int(hi)))
+        agg = collections.OrderedDict((nm, [0.0, 0.0, 0.0, 0.0, 0]) for nm, _, _ in regions)
+        agg["(other)"] = [0.0, 0.0, 0.0, 0.0, 0]
+        for key, v in per_line.items():
+            nm = next((nm for nm, lo, hi in regions if key[0].endswith(".cu") and lo <= key[1] <= hi), "(other)")
+            for k in range(5):
+                agg[nm][k] += v[k]
+        print("\n%-28s %6s %7s %7s %7s %8s %9s" % ("region", "#sass", "%instr", "thr/in", "%sampl", "%long_sb", "%laneslot"))
+        for nm, v in agg.items():
+            print("%-28s %6d %7.2f %7.1f %7.2f %8.2f %9.2f" % (nm, v[4], 100 * v[0] / tot[0], v[1] / max(v[0], 1), 100 * v[2] / max(tot[2], 1),
+                                                            100 * v[3] / max(tot[2], 1), 100 * v[1] / tot[1]))
     if args.sass:
         print("\nhottest SASS by samples")
         order = sorted(range(n), key=lambda i: -f(body[i], "# Samples"))[: args.top]
