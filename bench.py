@@ -29,7 +29,7 @@ ABI call, with the H2D / D2H rates each GPU saw and the raw pinned-copy ceiling 
 
 `value`  = rays / device time (CUDA events on the launch stream), max over ranks.
 `e2e`    = the same step through the public API with host buffers inside the timed region: for c5
-           tile list in -> image out (asgpu_path_stream_render + _read_image); for c1-c4 rays in ->
+           tile list in -> this rank's tiles of the image out (asgpu_path_stream_render + _read_tiles); for c1-c4 rays in ->
            hit records out (asgpu_trace_host) from pinned host memory.
 `roofline` = algorithmic bytes (measured node / triangle / instance visits per ray x record sizes
            + ray in + hit out) of the dominant kernel's launches / its launch durations, measured live
