@@ -34,7 +34,7 @@ EXPORTS = [
     "asgpu_trees_build_on_device", "asgpu_trees_device_seconds",
     "asgpu_get_counters_by_kind", "asgpu_get_lane_profile", "asgpu_get_support_planes", "asgpu_pin_host", "asgpu_unpin_host", "asgpu_reload_tuning",
     "asgpu_path_stream_capture_get_times", "asgpu_path_stream_set_profiling", "asgpu_path_stream_get_profile",
-    "asgpu_path_stream_read_tiles",
+    "asgpu_path_stream_read_tiles", "asgpu_trees_build_animated",
 ]
 
 SCENE_EXACT = 1 << 0
@@ -151,6 +151,8 @@ def load() -> C.CDLL:
     lib.asgpu_version.restype = C.c_int
     lib.asgpu_trees_build.restype = C.c_void_p
     lib.asgpu_trees_build.argtypes = [P(CSceneDesc), C.c_int]
+    lib.asgpu_trees_build_animated.restype = C.c_void_p
+    lib.asgpu_trees_build_animated.argtypes = [P(CSceneDesc), C.c_void_p, C.c_int]
     lib.asgpu_trees_build_on_device.restype = C.c_void_p
     lib.asgpu_trees_build_on_device.argtypes = [P(CSceneDesc), C.c_int, C.c_int]
     lib.asgpu_trees_destroy.argtypes = [C.c_void_p]

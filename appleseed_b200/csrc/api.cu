@@ -377,6 +377,19 @@ asgpu_trees* asgpu_trees_build(const asgpu_scene_desc* desc, int threads)
     return t;
 }
 
+asgpu_trees* asgpu_trees_build_animated(const asgpu_scene_desc* desc, const asgpu_instance_keys* keys, int threads)
+{
+    if (!desc) { fail(ASGPU_E_INVALID, "null scene description"); return nullptr; }
+    asgpu_trees* t = new (std::nothrow) asgpu_trees();
+    if (!t) { fail(ASGPU_E_NOMEM, "out of host memory"); return nullptr; }
+    std::string error;
+    bool ok = false;
+    try { ok = build_host_trees(*desc, threads, t->trees, error, nullptr, nullptr, keys); }
+    catch (const std::exception& e) { error = e.what(); }
+    if (!ok) { fail(ASGPU_E_INVALID, error); delete t; return nullptr; }
+    return t;
+}
+
 asgpu_trees* asgpu_trees_build_on_device(const asgpu_scene_desc* desc, int threads, int device)
 {
     if (!desc) { fail(ASGPU_E_INVALID, "null scene description"); return nullptr; }
@@ -429,7 +442,7 @@ int asgpu_trees_get_assembly_tree(const asgpu_trees* trees, asgpu_assembly_tree_
     out->items = t.items.empty() ? nullptr : t.items.data();
     out->node_count = t.nodes.size();
     out->item_count = t.items.size();
-    out->item_motion = nullptr;         // the host builder handles single-key transform sequences
+    out->item_motion = t.item_motion.empty() ? nullptr : t.item_motion.data();      // asgpu_trees_build_animated
     return ASGPU_OK;
 }
 

@@ -24,11 +24,13 @@
 
 #include "tree_builder.h"
 #include "lbvh_core.h"
+#include "motion_bounds.h"
 #include "parallel.h"
 
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -1019,9 +1021,24 @@ static bool emit_lbvh(const LbvhTopology& t, const std::vector<BoundsF>& boxes, 
     return true;
 }
 
-bool build_host_trees(const asgpu_scene_desc& desc, int threads, HostTrees& out, std::string& error, LbvhTopologyFn lbvh, void* lbvh_context)
+bool build_host_trees(const asgpu_scene_desc& desc, int threads, HostTrees& out, std::string& error, LbvhTopologyFn lbvh, void* lbvh_context,
+                      const asgpu_instance_keys* keys)
 {
     if (!check_desc(desc, error)) return false;
+    if (keys)
+        for (uint32_t i = 0; i < desc.assembly_instance_count; ++i)
+        {
+            const asgpu_instance_keys& k = keys[i];
+            if (k.key_count < 2) continue;
+            if (!k.times || !k.local_to_parent || !k.parent_to_local) { error = "animated assembly instance without key arrays"; return false; }
+            for (uint32_t j = 0; j < k.key_count; ++j)
+            {
+                if (!(k.times[j] == k.times[j]) || (j > 0 && !(k.times[j - 1] < k.times[j]))) { error = "key times of an animated assembly instance must ascend strictly"; return false; }
+                for (int e = 0; e < 16; ++e)
+                    if (!std::isfinite(k.local_to_parent[size_t(j) * 16 + e]) || !std::isfinite(k.parent_to_local[size_t(j) * 16 + e]))
+                    { error = "non-finite key transform"; return false; }
+            }
+        }
     if (threads < 1) threads = std::max(1u, std::thread::hardware_concurrency());
     const auto t0 = std::chrono::steady_clock::now();
 
@@ -1141,18 +1158,31 @@ bool build_host_trees(const asgpu_scene_desc& desc, int threads, HostTrees& out,
     // (aabb.h:621-641); SAH with leaf size 1 and costs (1, 10) (intersectionsettings.h:51-53).
     std::vector<asgpu_assembly_item> items;
     std::vector<BoundsD> item_box;
+    std::vector<uint32_t> item_instance;        // assembly instance behind every item (for its keys)
+    bool any_animated = false;
     for (uint32_t i = 0; i < desc.assembly_instance_count; ++i)
     {
         const asgpu_assembly_instance& inst = desc.assembly_instances[i];
         if (desc.assemblies[inst.assembly_index].object_instance_count == 0) continue;
+        const bool animated = keys != nullptr && keys[i].key_count >= 2;
+        any_animated = any_animated || animated;
         asgpu_assembly_item item; std::memset(&item, 0, sizeof(item));
-        std::memcpy(item.parent_to_local, inst.parent_to_local, sizeof(item.parent_to_local));
+        std::memcpy(item.parent_to_local, animated ? keys[i].parent_to_local : inst.parent_to_local, sizeof(item.parent_to_local));
         item.assembly_instance = i;
         item.triangle_tree = static_cast<uint32_t>(out.assembly_to_tree[inst.assembly_index]);
         item.vis_flags = inst.vis_flags;
         items.push_back(item);
+        item_instance.push_back(i);
 
-        const BoundsF wb = box_to_parent(inst.local_to_parent, assembly_box[inst.assembly_index]);
+        // cumulated_transform_seq.to_parent(assembly box) (assemblytree.cpp:146-149): one key = the
+        // box through that transform; several = the box over the whole motion (motion_bounds.cpp).
+        BoundsF wb;
+        if (animated)
+        {
+            const BoundsF& ab = assembly_box[inst.assembly_index];
+            motion_bounds(keys[i].local_to_parent, keys[i].parent_to_local, keys[i].key_count, ab.lo, ab.hi, wb.lo, wb.hi);
+        }
+        else wb = box_to_parent(inst.local_to_parent, assembly_box[inst.assembly_index]);
         BoundsD b;
         for (int a = 0; a < 3; ++a)
         {
@@ -1178,6 +1208,31 @@ bool build_host_trees(const asgpu_scene_desc& desc, int threads, HostTrees& out,
     out.assembly_tree.items.resize(items.size());
     for (size_t i = 0; i < items.size(); ++i)
         out.assembly_tree.items[i] = items[top_builder.ordering()[i]];
+
+    // Animated instances: keys and interpolator segments per item, in tree order.
+    HostAssemblyTree& top = out.assembly_tree;
+    top.item_motion.clear(); top.key_times.clear(); top.key_parent_to_local.clear(); top.segments.clear();
+    if (any_animated)
+    {
+        top.item_motion.resize(items.size());
+        top.key_times.resize(items.size()); top.key_parent_to_local.resize(items.size()); top.segments.resize(items.size());
+        for (size_t i = 0; i < items.size(); ++i)
+        {
+            asgpu_item_motion& m = top.item_motion[i];
+            std::memset(&m, 0, sizeof(m));
+            const asgpu_instance_keys& k = keys[item_instance[top_builder.ordering()[i]]];
+            if (k.key_count < 2) continue;
+            top.key_times[i].assign(k.times, k.times + k.key_count);
+            top.key_parent_to_local[i].assign(k.parent_to_local, k.parent_to_local + size_t(k.key_count) * 16);
+            top.segments[i].resize(k.key_count - 1);
+            for (uint32_t j = 0; j + 1 < k.key_count; ++j)
+                make_transform_segment(k.local_to_parent + size_t(j) * 16, k.local_to_parent + size_t(j + 1) * 16, top.segments[i][j]);
+            m.key_times = top.key_times[i].data();
+            m.key_parent_to_local = top.key_parent_to_local[i].data();
+            m.segments = top.segments[i].data();
+            m.key_count = k.key_count;
+        }
+    }
 
     out.build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     return true;

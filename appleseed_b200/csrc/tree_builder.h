@@ -55,6 +55,13 @@ struct HostAssemblyTree
 {
     AsNodeVector                        nodes;
     std::vector<asgpu_assembly_item>    items;      // tree order
+    // Animated instances (asgpu_trees_build_animated): per item, in tree order, what the flattener
+    // takes as asgpu_item_motion; the pointers of `item_motion` look into the three pools.  Empty
+    // when no instance is animated.
+    std::vector<asgpu_item_motion>          item_motion;
+    std::vector<std::vector<float>>         key_times;
+    std::vector<std::vector<double>>        key_parent_to_local;
+    std::vector<std::vector<asgpu_transform_segment>> segments;
 };
 
 struct HostTrees
@@ -97,7 +104,8 @@ int ploc_radius();
 // Returns false and fills `error` on malformed input.  `lbvh` = null: the reference's sweep SAH for
 // every tree (result-identical to the reference); else the triangle trees take their topology from
 // `lbvh(..., lbvh_context, ...)` (the small assembly tree always uses the sweep).
+// `keys`: null, or one entry per assembly instance (animated instances: motion boxes + segments).
 bool build_host_trees(const asgpu_scene_desc& desc, int threads, HostTrees& out, std::string& error,
-                      LbvhTopologyFn lbvh = nullptr, void* lbvh_context = nullptr);
+                      LbvhTopologyFn lbvh = nullptr, void* lbvh_context = nullptr, const asgpu_instance_keys* keys = nullptr);
 
 }   // namespace asgpu

@@ -41,10 +41,22 @@ class HostTrees:
     with ``build_device`` = a CUDA device ordinal, triangle-tree topology built on that device as a
     linear BVH (``asgpu_trees_build_on_device``)."""
 
-    def __init__(self, desc: SceneDesc, threads: int = 0, build_device: Optional[int] = None):
+    def __init__(self, desc: SceneDesc, threads: int = 0, build_device: Optional[int] = None, keys=None):
+        """``keys``: {assembly instance index: scene.InstanceKeys} -- animated assembly instances
+        (``asgpu_trees_build_animated``: motion bounding boxes and interpolator segments as the
+        reference's TransformSequence computes them)."""
         self.lib = _lib.load()
         self._cdesc, self._keep = desc.to_c()
-        if build_device is None:
+        if keys:
+            assert build_device is None, "animated instances are built by the host builder"
+            from .scene import CInstanceKeys
+            arr = (CInstanceKeys * len(desc.assembly_instances))()
+            for i, k in keys.items():
+                arr[i].times, arr[i].local_to_parent, arr[i].parent_to_local = k.times.ctypes.data, k.local_to_parent.ctypes.data, k.parent_to_local.ctypes.data
+                arr[i].key_count = len(k.times)
+            self._keep += [arr, keys]
+            self.handle = self.lib.asgpu_trees_build_animated(C.byref(self._cdesc), C.cast(arr, C.c_void_p), threads)
+        elif build_device is None:
             self.handle = self.lib.asgpu_trees_build(C.byref(self._cdesc), threads)
         else:
             self.handle = self.lib.asgpu_trees_build_on_device(C.byref(self._cdesc), threads, int(build_device))

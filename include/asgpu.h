@@ -222,6 +222,23 @@ typedef struct asgpu_trees asgpu_trees;
 
 asgpu_trees*    asgpu_trees_build(const asgpu_scene_desc* desc, int threads);
 
+/* The keys of an ANIMATED assembly instance: its cumulated TransformSequence
+ * (assemblytree.cpp:124-127), times strictly ascending as TransformSequence::prepare() leaves them. */
+typedef struct asgpu_instance_keys {
+    const float*    times;              /* key_count (TransformSequence::m_keys[k].m_time) */
+    const double*   local_to_parent;    /* key_count * 16 (m_keys[k].m_transform) */
+    const double*   parent_to_local;    /* key_count * 16 */
+    uint32_t        key_count;          /* < 2: the instance is not animated, asgpu_assembly_instance's matrices are used */
+    uint32_t        reserved;
+} asgpu_instance_keys;
+
+/* asgpu_trees_build for scenes with animated assembly instances: `keys` has one entry per
+ * assembly instance of the description (NULL = asgpu_trees_build).  The assembly tree is built
+ * over the reference's motion bounding boxes (TransformSequence::to_parent,
+ * renderer/utility/transformsequence.h:212-236, transformsequence.cpp:509-616) and the items come
+ * with the interpolator segments the traversal evaluates (asgpu_assembly_tree_view::item_motion). */
+asgpu_trees*    asgpu_trees_build_animated(const asgpu_scene_desc* desc, const asgpu_instance_keys* keys, int threads);
+
 /* Same trees-from-description entry point with the triangle-tree topology built on CUDA device
  * `device`: a linear BVH in Morton order of the triangle centroids
  * (Karras 2012), every node in parallel, instead of the reference's single-threaded sweep SAH

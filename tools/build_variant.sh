@@ -6,7 +6,7 @@ name=$1; shift
 cd "$(dirname "$0")/../appleseed_b200/csrc"
 mkdir -p build_$name
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 --expt-relaxed-constexpr -Xcompiler -fPIC,-ffp-contract=off,-pthread,-Wall,-Wno-unused-function"
-for f in api.cu kernels.cu wavefront.cu sort.cu refine.cu lbvh.cu ploc.cu flatten.cpp tree_builder.cpp; do
+for f in api.cu kernels.cu wavefront.cu sort.cu refine.cu lbvh.cu ploc.cu flatten.cpp tree_builder.cpp motion_bounds.cpp; do
   o=build_$name/${f%.*}.o
   case $f in
     kernels.cu|wavefront.cu) /usr/local/cuda/bin/nvcc $FLAGS "$@" -Xptxas -v -c -o $o $f 2> build_$name/${f%.*}.log & ;;
