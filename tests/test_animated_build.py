@@ -127,3 +127,19 @@ def test_bad_keys_are_refused():
     k.local_to_parent[1, 0, 0] = np.nan
     with pytest.raises(AsgpuError, match="finite"):
         HostTrees(desc, keys={0: k})
+
+
+@pytest.mark.gpu
+def test_kernels_on_product_built_animated_trees(asref):
+    """Description + keys -> asgpu_trees_build_animated -> asgpu_scene_create_ex -> both kernels,
+    refine_and_offset included (the trees carry their source geometry), against the reference."""
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from appleseed_b200.intersector import Intersector, TraceContext
+    desc, rays, probes, keys = animated_case()
+    o = asref.scene(desc, keys=keys)
+    isect = Intersector(TraceContext(trees=HostTrees(desc, keys=keys), device=0))
+    ref = o.trace(rays, threads=4)
+    check(ref, isect.trace(rays, exact=True), isect.trace(rays), o.trace_probe(probes, threads=4),
+          isect.trace_probe(probes, exact=True), isect.trace_probe(probes))
+    assert isect.refine_and_offset(rays, ref).tobytes() == o.refine_offset(rays, ref, threads=4).tobytes()
