@@ -100,40 +100,6 @@ ASGPU_HD uint2  load8(const void* p) { return __ldg(reinterpret_cast<const uint2
 ASGPU_HD uint32_t load4(const void* p) { return __ldg(reinterpret_cast<const uint32_t*>(p)); }
 ASGPU_HD double load_f64(const void* p) { return __ldg(reinterpret_cast<const double*>(p)); }
 
-// L2 placement of the wide kernels' two big random streams: the wide nodes (80 MB on C3, every ray
-// walks them) load with an evict_last policy, the triangle records (480 MB touched at random, 1-7
-// per ray) with evict_first.  Measured together: C3 +1.0 % / +1.6 %, C5 frame +1.5 % (probes +2.8 %);
-// evict_last on the nodes alone: 0; L1-level hints on any stream: negative
-// (profiles/r2/negative_results.txt sections 6 and 8).  evict_first on the ray loads and the hit
-// stores as well: -0.7 % (r2_l2hint2.log).  ASGPU_L2HINT=0 compiles the hints out.
-#ifndef ASGPU_L2HINT
-#define ASGPU_L2HINT 3
-#endif
-ASGPU_HD uint4 load16_node(const void* p)
-{
-#if ASGPU_L2HINT & 1
-    unsigned long long policy;
-    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy));
-    uint4 r;
-    asm("ld.global.nc.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p), "l"(policy));
-    return r;
-#else
-    return load16(p);
-#endif
-}
-ASGPU_HD uint4 load16_tri(const void* p)
-{
-#if ASGPU_L2HINT & 2
-    unsigned long long policy;
-    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
-    uint4 r;
-    asm("ld.global.nc.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p), "l"(policy));
-    return r;
-#else
-    return load16(p);
-#endif
-}
-
 #else
 
 struct uint4_h { uint32_t x, y, z, w; };
@@ -178,8 +144,6 @@ inline uint4  load16(const void* p) { uint4 r; std::memcpy(&r, p, 16); return r;
 inline uint2  load8(const void* p) { uint2 r; std::memcpy(&r, p, 8); return r; }
 inline uint32_t load4(const void* p) { uint32_t r; std::memcpy(&r, p, 4); return r; }
 inline double load_f64(const void* p) { double r; std::memcpy(&r, p, 8); return r; }
-inline uint4  load16_node(const void* p) { return load16(p); }
-inline uint4  load16_tri(const void* p) { return load16(p); }
 
 #endif
 
@@ -456,9 +420,9 @@ ASGPU_HD bool mt_test(const TriD& tri, const Ray& ray, double& t, double& u, dou
 template <bool ANY, bool MOTION = true>
 ASGPU_HD bool fetch_triangle(const uint8_t* record, const uint8_t* poses, const Ray& ray, TriD& tri, uint32_t& slot, uint32_t& segment)
 {
-    const uint4 a = load16_tri(record);
-    const uint4 b = load16_tri(record + 16);
-    const uint4 c = load16_tri(record + 32);
+    const uint4 a = load16(record);
+    const uint4 b = load16(record + 16);
+    const uint4 c = load16(record + 32);
     const uint32_t vis = c.y;
     slot = c.z;
     segment = 0;
@@ -952,7 +916,7 @@ ASGPU_HD float byte_to_unit(const uint32_t word, const int k, const uint32_t one
 template <bool EXPANDED>
 ASGPU_HD void wide_node_test_form(const uint8_t* np, const uint8_t* qp, const WideRay& w, const uint32_t one, uint32_t& child_base, uint32_t& tri_base, uint32_t& nmask, uint32_t& tmask)
 {
-    const uint4 n0 = load16_node(np), n1 = load16_node(np + 16), n2 = load16_node(qp), n3 = load16_node(qp + 16), n4 = load16_node(qp + 32);
+    const uint4 n0 = load16(np), n1 = load16(np + 16), n2 = load16(qp), n3 = load16(qp + 16), n4 = load16(qp + 32);
     child_base = n1.x;
     tri_base = n1.y;
     const uint32_t imask = n0.w >> 24;
