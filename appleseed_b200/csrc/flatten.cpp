@@ -9,7 +9,7 @@
 // layout written by triangleencoder.cpp:72-103).
 //
 // Output: see gpu_layout.h.  The EXACT layout is a lossless re-packing.  The WIDE layout
-// collapses each binary tree into 8-wide nodes (greedy largest-area expansion), orders children
+// collapses each binary tree into 8-wide nodes (SAH-optimal: the dynamic programme of Ylitie, Karras, Laine 2017, section 4.1), orders children
 // into octant slots, stores child boxes quantised to 8 bits per plane ROUNDED OUTWARD, and
 // re-orders triangle records so that one node's leaves are contiguous.  Because every wide box
 // contains the binary boxes it replaces, a traversal that tests wide boxes conservatively can only
