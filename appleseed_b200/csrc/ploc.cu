@@ -274,16 +274,14 @@ bool ploc_topology_device(const float* boxes, size_t n, const float root_lo[3], 
         cur ^= 1;
     }
 
-    // Leaf ranges, root first.
-    {
-        const uint32_t root_range[2] = { 0u, count - 1 };
-        if (cuda_failed(cudaMemcpyAsync(d_first, &root_range[0], 4, cudaMemcpyHostToDevice, stream), "H2D root range") ||
-            cuda_failed(cudaMemcpyAsync(d_last, &root_range[1], 4, cudaMemcpyHostToDevice, stream), "H2D root range"))
-            return false;
-        for (size_t k = round_begin.size(); k-- > 0; )
-            ploc_ranges_kernel<<<grid_for(round_end[k] - round_begin[k]), PlocThreads, 0, stream>>>(round_begin[k], round_end[k], d_left, d_right, d_leaves,
-                                                                                                    d_first, d_last, d_sorted_ids, d_order);
-    }
+    // Leaf ranges, root first (the two words stay alive until the final synchronisation below).
+    const uint32_t root_range[2] = { 0u, count - 1 };
+    if (cuda_failed(cudaMemcpyAsync(d_first, &root_range[0], 4, cudaMemcpyHostToDevice, stream), "H2D root range") ||
+        cuda_failed(cudaMemcpyAsync(d_last, &root_range[1], 4, cudaMemcpyHostToDevice, stream), "H2D root range"))
+        return false;
+    for (size_t k = round_begin.size(); k-- > 0; )
+        ploc_ranges_kernel<<<grid_for(round_end[k] - round_begin[k]), PlocThreads, 0, stream>>>(round_begin[k], round_end[k], d_left, d_right, d_leaves,
+                                                                                                d_first, d_last, d_sorted_ids, d_order);
     if (cuda_failed(cudaGetLastError(), "kernel launch")) return false;
 
     out.order.resize(n); out.left.resize(n - 1); out.right.resize(n - 1); out.first.resize(n - 1); out.last.resize(n - 1);
