@@ -30,6 +30,7 @@
 
 #include "api_internal.h"
 #include "kernels.h"
+#include "refine_core.h"
 
 #include <cuda_runtime.h>
 
@@ -263,6 +264,17 @@ generate_kernel(const StreamParams p, const uint32_t* __restrict__ tiles, const 
 //     (Tracer::trace_between, tracer.h:252-259), flags ShadowRay;
 //   * when depth < max_bounces, one cosine-weighted bounce (mappings.h:299-314), flags DiffuseRay.
 // hit.assembly_instance holds the ItemRecord index here (raw_item launches).
+// FUSED: ShadingPoint::refine_and_offset of the hit runs here (refine_core.h, the very function of
+// refine_offset_kernel) instead of in a kernel of its own: the 80-byte parent record goes straight
+// into the two child queues, hits and rays are read once.
+__device__ __noinline__ void refine_offset_call(const SceneView* s, const double* org_dir, const float time_absolute, const float time_normalized,
+                                                const double t, const uint32_t item, const uint32_t object_instance, const uint32_t primitive,
+                                                const uint32_t slot, double* dst)
+{
+    refine_offset_one(*s, org_dir, org_dir + 3, time_absolute, time_normalized, t, item, object_instance, primitive, slot, dst);
+}
+
+template <bool FUSED>
 __global__ void __launch_bounds__(StageThreads, 3)
 shade_kernel(const StreamParams p, const SceneView s, const QueueView in, const asgpu_hit* __restrict__ hits, const asgpu_parent* refined,
              const QueueView probes, const QueueView next, const uint32_t depth, uint32_t* image, unsigned long long* stats)
@@ -278,6 +290,8 @@ shade_kernel(const StreamParams p, const SceneView s, const QueueView in, const 
         uint32_t path = 0, pixel = 0, identity = 0;
         float time_absolute = 0.0f, time_normalized = 0.0f;     // child rays inherit their path's time (pathtracer.h:764)
         double o[3] = { 0.0, 0.0, 0.0 }, nrm[3] = { 0.0, 1.0, 0.0 };
+        double parent_words[10];                                 // FUSED: this vertex's asgpu_parent record
+        const bool with_parents = FUSED || refined != nullptr;
         if (i < n)
         {
             path = in.path[i];
@@ -294,8 +308,20 @@ shade_kernel(const StreamParams p, const SceneView s, const QueueView in, const 
                 const uint32_t item = static_cast<uint32_t>(w2), object_instance = static_cast<uint32_t>(w2 >> 32);
                 const uint32_t primitive = static_cast<uint32_t>(w3), slot = static_cast<uint32_t>(w3 >> 32);
                 double dir[3];
-                #pragma unroll
-                for (int k = 0; k < 3; ++k) { dir[k] = in.dir[i * 3 + k]; o[k] = in.org[i * 3 + k] + t * dir[k]; }
+                if (FUSED)
+                {
+                    double org_dir[6];
+                    #pragma unroll
+                    for (int k = 0; k < 3; ++k) { org_dir[k] = in.org[i * 3 + k]; org_dir[3 + k] = in.dir[i * 3 + k]; }
+                    refine_offset_call(&s, org_dir, time_absolute, time_normalized, t, item, object_instance, primitive, slot, parent_words);
+                    #pragma unroll
+                    for (int k = 0; k < 3; ++k) { dir[k] = org_dir[3 + k]; o[k] = org_dir[k] + t * dir[k]; }
+                }
+                else
+                {
+                    #pragma unroll
+                    for (int k = 0; k < 3; ++k) { dir[k] = in.dir[i * 3 + k]; o[k] = in.org[i * 3 + k] + t * dir[k]; }
+                }
                 // Geometric normal.
                 const uint8_t* ip = s.blob + s.items + static_cast<uint64_t>(item) * sizeof(ItemRecord);
                 const uint4 meta = load16(ip + 96);
@@ -322,7 +348,7 @@ shade_kernel(const StreamParams p, const SceneView s, const QueueView in, const 
                 if (nrm[0] * dir[0] + nrm[1] * dir[1] + nrm[2] * dir[2] > 0.0) { nrm[0] = -nrm[0]; nrm[1] = -nrm[1]; nrm[2] = -nrm[2]; }
                 // Next origin: the hit point itself when the child rays carry the refined parent record,
                 // else offset along the normal.
-                if (refined == nullptr)
+                if (!with_parents)
                 {
                     #pragma unroll
                     for (int k = 0; k < 3; ++k) o[k] += p.eps * nrm[k];
@@ -370,7 +396,7 @@ shade_kernel(const StreamParams p, const SceneView s, const QueueView in, const 
             if (slot != ~0ull)
             {
                 write_ray(probes, slot, o, d, 0.0, tmax, time_absolute, time_normalized, ASGPU_VIS_SHADOW, path);
-                write_parent(probes, slot, refined ? refined + i : nullptr);
+                write_parent(probes, slot, FUSED ? reinterpret_cast<const asgpu_parent*>(parent_words) : (refined ? refined + i : nullptr));
                 ++local[StatProbe];
             }
         }
@@ -402,7 +428,7 @@ shade_kernel(const StreamParams p, const SceneView s, const QueueView in, const 
             if (slot != ~0ull)
             {
                 write_ray(next, slot, o, d, 0.0, DBL_MAX, time_absolute, time_normalized, ASGPU_VIS_DIFFUSE, path);
-                write_parent(next, slot, refined ? refined + i : nullptr);
+                write_parent(next, slot, FUSED ? reinterpret_cast<const asgpu_parent*>(parent_words) : (refined ? refined + i : nullptr));
                 ++local[StatBounce];
             }
         }
@@ -467,6 +493,7 @@ struct asgpu_path_stream
     asgpu_ray_queue*        qp = nullptr;
     asgpu_hit*              hits = nullptr;
     asgpu_parent*           refined = nullptr;      // refine_and_offset of the current wavefront's hits (ASGPU_STREAM_PARENTS)
+    bool                    fuse_refine = false;    // ... computed inside shade_kernel instead (ASGPU_FUSE_REFINE=1)
     uint8_t*                occluded = nullptr;
     uint32_t*               image = nullptr;
     uint32_t*               tiles_dev = nullptr;
@@ -567,7 +594,7 @@ int capture_wavefront(asgpu_path_stream* ps, const asgpu_ray_queue* q, const int
 }
 
 int trace_queue(asgpu_scene* scene, asgpu_ray_queue* q, asgpu_hit* hits, uint8_t* occluded, const bool any_hit, const uint32_t flags,
-                unsigned long long* cursor, const bool raw_item, void* stream)
+                unsigned long long* cursor, const bool raw_item, void* stream, const bool use_parents = true)
 {
     const bool wide = (flags & ASGPU_TRACE_EXACT) == 0;
     if (flags & ASGPU_TRACE_SORT) return fail(ASGPU_E_UNSUPPORTED, "ASGPU_TRACE_SORT needs the ray count on the host: not available for queues");
@@ -576,7 +603,7 @@ int trace_queue(asgpu_scene* scene, asgpu_ray_queue* q, asgpu_hit* hits, uint8_t
     const asgpu_rays rays = rays_of(q);
     const int err = launch_trace(scene->view, rays, q->capacity, hits, occluded, any_hit, wide, cursor,
                                  (flags & ASGPU_TRACE_COUNTERS) ? scene->counters : nullptr, nullptr, scene->sm_count, stream, q->count, raw_item,
-                                 q->parents);
+                                 use_parents ? q->parents : nullptr);
     if (err != 0) return fail_cuda(static_cast<cudaError_t>(err), "kernel launch");
     ++scene->launches;
     return ASGPU_OK;
@@ -740,6 +767,10 @@ asgpu_path_stream* asgpu_path_stream_create(asgpu_scene* scene, const asgpu_path
         if (e == cudaSuccess) e = cudaMalloc(&ps->qb->parents, capacity * sizeof(asgpu_parent));
         if (e == cudaSuccess) e = cudaMalloc(&ps->qp->parents, capacity * sizeof(asgpu_parent));
         if (e == cudaSuccess) e = cudaMalloc(&ps->refined, capacity * sizeof(asgpu_parent));
+        // refine_and_offset inside shade_kernel (the default: -10 % on refine + shade together, +3 % on
+        // a C5 frame, profiles/r2/r2_fuse.log); ASGPU_FUSE_REFINE=0 keeps the kernel of its own.
+        ps->fuse_refine = true;
+        if (const char* fuse = getenv("ASGPU_FUSE_REFINE")) ps->fuse_refine = atoi(fuse) != 0;
     }
     if (e == cudaSuccess) e = cudaMalloc(&ps->hits, capacity * sizeof(asgpu_hit));
     if (e == cudaSuccess) e = cudaMalloc(&ps->occluded, capacity);
@@ -813,14 +844,15 @@ int asgpu_path_stream_render(asgpu_path_stream* ps, const uint32_t* tiles, size_
             int rc;
             {
                 TimedLaunch timed(ps, 0, stream);
-                rc = trace_queue(scene, qa, ps->hits, nullptr, false, flags, ps->cursors + (ps->cursor_next++ % QueueRing), true, stream);
+                // Camera rays have no parent shading point: their launch does not look at the (all "none") records.
+                rc = trace_queue(scene, qa, ps->hits, nullptr, false, flags, ps->cursors + (ps->cursor_next++ % QueueRing), true, stream, depth != 0);
             }
             if (rc != ASGPU_OK) return rc;
             ++ps->launches; ++ps->wavefronts;
             if (ps->capture_armed && (rc = capture_wavefront(ps, qa, 0, depth, stream)) != ASGPU_OK) return rc;
             ASGPU_CUDA(cudaMemsetAsync(qb->count, 0, 8, stream), "cudaMemsetAsync");
             ASGPU_CUDA(cudaMemsetAsync(ps->qp->count, 0, 8, stream), "cudaMemsetAsync");
-            if (ps->refined)
+            if (ps->refined && !ps->fuse_refine)
             {
                 TimedLaunch timed(ps, 2, stream);
                 const int er = launch_refine_offset(scene->view, rays_of(qa), ps->hits, qa->capacity, qa->count, true, nullptr, 0, ps->refined, scene->sm_count, stream);
@@ -829,7 +861,10 @@ int asgpu_path_stream_render(asgpu_path_stream* ps, const uint32_t* tiles, size_
             }
             {
                 TimedLaunch timed(ps, 3, stream);
-                shade_kernel<<<grid, StageThreads, 0, stream>>>(ps->params, scene->view, view_of(qa), ps->hits, ps->refined, vp, view_of(qb), depth, ps->image, ps->stats_dev);
+                if (ps->refined && ps->fuse_refine)
+                    shade_kernel<true><<<grid, StageThreads, 0, stream>>>(ps->params, scene->view, view_of(qa), ps->hits, nullptr, vp, view_of(qb), depth, ps->image, ps->stats_dev);
+                else
+                    shade_kernel<false><<<grid, StageThreads, 0, stream>>>(ps->params, scene->view, view_of(qa), ps->hits, ps->refined, vp, view_of(qb), depth, ps->image, ps->stats_dev);
             }
             ASGPU_CUDA(cudaGetLastError(), "shade_kernel");
             ++ps->launches;

@@ -806,7 +806,8 @@ def run_gpu_c5(args):
                 "lane_slots_closest_pct": lane_shares(lp_closest), "lane_slots_probe_pct": lane_shares(lp_probe),
                 "rank0_device_ms_per_frame": {"closest_trace": round(prof["closest_ms"] / args.steps, 3), "probe_trace": round(prof["probe_ms"] / args.steps, 3),
                                               "refine_and_offset": round(prof["refine_ms"] / args.steps, 3),
-                                              "generate_shade_accumulate": round(prof["stage_ms"] / args.steps, 3)},
+                                              "generate_shade_accumulate": round(prof["stage_ms"] / args.steps, 3),
+                                              "note": "refine_and_offset runs inside shade_kernel (0 = no kernel of its own; ASGPU_FUSE_REFINE=0 splits it out)"},
                 "rank0_closest_mrays_s": round(closest_step / (prof["closest_ms"] / args.steps) / 1e3, 1) if prof["closest_ms"] else None,
                 "rank0_probe_mrays_s": round(probe_step / (prof["probe_ms"] / args.steps) / 1e3, 1) if prof["probe_ms"] else None,
             },

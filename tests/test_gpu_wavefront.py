@@ -197,10 +197,28 @@ def test_stream_with_parent_shading_points(setup, orc):
             assert np.allclose(child.rays.org, pts, rtol=0, atol=1e-12)                                # no epsilon offset
         pref = o.trace_probe_parents(probe.rays, probe.parents, threads=4)
         parity.compare_probes(o, probe.rays, probe.results, pref)
-    assert stats["kernel_launches"] == 1 + 5 * (cfg["max_bounces"] + 1)
+    # generate + per depth: closest trace, shade (refine_and_offset inside), probe trace, accumulate.
+    assert stats["kernel_launches"] == 1 + 4 * (cfg["max_bounces"] + 1)
     # Same image from the exact kernels.
     exact, _, _ = render(wavefront, ctx, cfg, 1 << 20, parents=True, exact=True)
     assert np.array_equal(img, exact)
+
+
+def test_refine_in_a_kernel_of_its_own_gives_the_same_stream(setup, monkeypatch):
+    """ASGPU_FUSE_REFINE=0: refine_offset_kernel + shade_kernel instead of the fused shade kernel --
+    same image, same captured parent records, one more launch per depth."""
+    desc, ctx, wavefront, cfg = setup
+    img, stats, caps = render(wavefront, ctx, cfg, 1 << 20, capture=1 << 22, parents=True)
+    monkeypatch.setenv("ASGPU_FUSE_REFINE", "0")
+    img2, stats2, caps2 = render(wavefront, ctx, cfg, 1 << 20, capture=1 << 22, parents=True)
+    assert np.array_equal(img, img2)
+    assert stats2["kernel_launches"] == stats["kernel_launches"] + cfg["max_bounces"] + 1
+    assert len(caps) == len(caps2)
+    for a, b in zip(caps, caps2):
+        # Queue order is decided by atomics: compare ray by ray through the path ids.
+        ia, ib = np.argsort(a.path_ids, kind="stable"), np.argsort(b.path_ids, kind="stable")
+        assert a.kind == b.kind and np.array_equal(a.path_ids[ia], b.path_ids[ib])
+        assert a.parents[ia].tobytes() == b.parents[ib].tobytes() and a.results[ia].tobytes() == b.results[ib].tobytes()
 
 
 def test_queue_count_beyond_capacity_is_clamped(setup):
