@@ -74,7 +74,7 @@ INSTANCE_BYTES = 112 + 32 + 4
 NODE_BYTES, TRI_BYTES, POSE_BYTES, HIT_OUT_BYTES = 80, 48, 72, 40
 UNIT = "Mrays/s"
 MI = 1 << 20
-DEFAULT_RAYS = {"c1": 512 * 512, "c2": 16 * MI, "c3": 32 * MI, "c4": 16 * MI, "c5": 16 * MI}
+DEFAULT_RAYS = {"c1": 512 * 512, "c2": 16 * MI, "c3": 32 * MI, "c4": 16 * MI, "c5": 32 * MI}   # c5: queue capacity (rays per wavefront batch)
 
 
 # ---------------------------------------------------------------------------------------------
