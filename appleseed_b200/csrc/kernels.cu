@@ -544,7 +544,7 @@ wide_kernel(const KernelArgs args)
                         if (sp == 0) traversed = true;
                         else
                         {
-                            const uint2 top = pop();
+                            uint2 top = pop();
                             if (top.x == None && top.y == 0)
                             {
                                 // Back to world space: the world ray comes from the ray arrays again.
@@ -559,8 +559,9 @@ wide_kernel(const KernelArgs args)
                                 wnodes = blob + s.top_wnodes;
                                 qbase = wnodes + 32; qstride = sizeof(WNode);
                                 cur_item = None;
+                                top = pop();    // what was left to do in world space (there is no sentinel without it)
                             }
-                            else if (top.y & 0xFF000000u) ngroup = top;
+                            if (top.y & 0xFF000000u) ngroup = top;
                             else tgroup = top;
                         }
                     }
@@ -571,6 +572,15 @@ wide_kernel(const KernelArgs args)
                         ngroup.y &= ~(1u << bit);
                         const uint32_t k = static_cast<uint32_t>(bit - 24) ^ (7 - (w.oct & 7));
                         fetch = ngroup.x + popc(ngroup.y & 0xFFu & ((1u << k) - 1u));
+                    }
+                    else if (!LEAN && tgroup.y)
+                    {
+                        // An instance group came off the stack: decided now, not one idle round later
+                        // (the entry itself always goes through the batched path below).  Leaf triangles
+                        // found by this very round's node test are not in the queue yet but refer to the
+                        // instance the lane is leaving, just like queued ones: the entry must wait for both.
+                        if (waiting || pending != 0) held = true;
+                        else want_enter = true;
                     }
                 }
             }
