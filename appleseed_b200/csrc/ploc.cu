@@ -10,7 +10,9 @@
 //   scan      one exclusive 64-bit prefix sum gives every survivor its place in the next round and
 //             every new node its index (cub::DeviceScan: library code off the trace path),
 //   merge     survivors move to their place; the left partner of a pair writes the new node,
-// until one cluster is left, then one pass per round, last round first, hands the leaf ranges down
+// until n / 8 clusters are left; the top of the tree over those is built on the host by the product's
+// sweep SAH (build_cluster_top: agglomeration is good at the bottom of a tree and poor at its top);
+// then one pass per level of the top and per round, last round first, hands the leaf ranges down
 // so that every node covers a contiguous range of the final order (what emit_lbvh lays out in the
 // reference's node format).  Node indices are given out from n - 2 downwards, in cluster order
 // within a round: the root is node 0, parents have lower indices than their children, and the tree
@@ -28,8 +30,12 @@
 #include <cub/device/device_scan.cuh>
 #include <cuda_runtime.h>
 
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace asgpu
@@ -165,17 +171,25 @@ ploc_ranges_kernel(const uint32_t begin, const uint32_t end, uint32_t* __restric
     }
 }
 
-struct DeviceBuffers
+// All device arrays of one build in ONE allocation (22 cudaMalloc / cudaFree pairs cost 0.03 - 0.2 s
+// of driver time per build, more than the kernels): sizes are collected first, then carved out.
+struct DeviceArena
 {
-    void* ptrs[32];
-    int count = 0;
-    ~DeviceBuffers() { for (int i = 0; i < count; ++i) cudaFree(ptrs[i]); }
-    template <typename T> bool alloc(T*& p, const size_t elements)
+    struct Want { void** where; size_t bytes; };
+    std::vector<Want> wants;
+    void* base = nullptr;
+    ~DeviceArena() { cudaFree(base); }
+    template <typename T> void want(T*& p, const size_t elements)
     {
-        void* q = nullptr;
-        if (cudaMalloc(&q, (elements ? elements : 1) * sizeof(T)) != cudaSuccess) return false;
-        ptrs[count++] = q;
-        p = static_cast<T*>(q);
+        wants.push_back(Want{ reinterpret_cast<void**>(&p), ((elements ? elements : 1) * sizeof(T) + 255) / 256 * 256 });
+    }
+    bool commit()
+    {
+        size_t total = 0;
+        for (const Want& w : wants) total += w.bytes;
+        if (cudaMalloc(&base, total) != cudaSuccess) { base = nullptr; return false; }
+        size_t at = 0;
+        for (const Want& w : wants) { *w.where = static_cast<uint8_t*>(base) + at; at += w.bytes; }
         return true;
     }
 };
@@ -216,7 +230,8 @@ bool ploc_topology_device(const float* boxes, size_t n, const float root_lo[3], 
     }
 
     const uint32_t count = static_cast<uint32_t>(n);
-    DeviceBuffers mem;
+    const auto t_begin = std::chrono::steady_clock::now();
+    DeviceArena mem;
     float *d_boxes, *d_node_boxes, *d_cbox[2];
     uint64_t *d_keys, *d_keys_sorted;
     unsigned long long *d_fate, *d_offsets;
@@ -230,11 +245,12 @@ bool ploc_topology_device(const float* boxes, size_t n, const float root_lo[3], 
                                                   static_cast<int>(count)), "scan sizing"))
         return false;
     const size_t temp_bytes = sort_bytes > scan_bytes ? sort_bytes : scan_bytes;
-    if (!mem.alloc(d_boxes, n * 6) || !mem.alloc(d_node_boxes, (n - 1) * 6) || !mem.alloc(d_cbox[0], n * 6) || !mem.alloc(d_cbox[1], n * 6) ||
-        !mem.alloc(d_keys, n) || !mem.alloc(d_keys_sorted, n) || !mem.alloc(d_fate, n) || !mem.alloc(d_offsets, n) ||
-        !mem.alloc(d_ids, n) || !mem.alloc(d_sorted_ids, n) || !mem.alloc(d_order, n) || !mem.alloc(d_left, n - 1) || !mem.alloc(d_right, n - 1) ||
-        !mem.alloc(d_leaves, n - 1) || !mem.alloc(d_first, n - 1) || !mem.alloc(d_last, n - 1) || !mem.alloc(d_nearest, n) ||
-        !mem.alloc(d_cref[0], n) || !mem.alloc(d_cref[1], n) || !mem.alloc(d_ccount[0], n) || !mem.alloc(d_ccount[1], n) || !mem.alloc(d_temp, temp_bytes))
+    mem.want(d_boxes, n * 6); mem.want(d_node_boxes, (n - 1) * 6); mem.want(d_cbox[0], n * 6); mem.want(d_cbox[1], n * 6);
+    mem.want(d_keys, n); mem.want(d_keys_sorted, n); mem.want(d_fate, n); mem.want(d_offsets, n);
+    mem.want(d_ids, n); mem.want(d_sorted_ids, n); mem.want(d_order, n); mem.want(d_left, n - 1); mem.want(d_right, n - 1);
+    mem.want(d_leaves, n - 1); mem.want(d_first, n - 1); mem.want(d_last, n - 1); mem.want(d_nearest, n);
+    mem.want(d_cref[0], n); mem.want(d_cref[1], n); mem.want(d_ccount[0], n); mem.want(d_ccount[1], n); mem.want(d_temp, temp_bytes);
+    if (!mem.commit())
     { error = "device tree build: out of device memory"; return false; }
 
     cudaStream_t stream = nullptr;      // the build is synchronous: the legacy stream orders everything
@@ -251,7 +267,10 @@ bool ploc_topology_device(const float* boxes, size_t n, const float root_lo[3], 
     std::vector<uint32_t> round_begin, round_end;
     uint32_t clusters = count, next_node = count - 2;
     int cur = 0;
-    while (clusters > 1)
+    // The rounds stop at n / PlocTopRatio clusters: the top of the tree over them is the sweep SAH's
+    // (build_cluster_top, tree_builder.cpp), which is good exactly where agglomeration is poor.
+    const uint32_t stop_at = std::max<uint32_t>(2u, count / PlocTopRatio);
+    while (clusters > stop_at)
     {
         const int grid = grid_for(clusters);
         ploc_nearest_kernel<<<grid, PlocThreads, 0, stream>>>(d_cbox[cur], clusters, radius, d_nearest);
@@ -269,9 +288,34 @@ bool ploc_topology_device(const float* boxes, size_t n, const float root_lo[3], 
         if (created == 0 || survivors + created != clusters) { error = "device tree build: a clustering round made no progress"; return false; }
         round_begin.push_back(next_node - (created - 1));
         round_end.push_back(next_node + 1);
-        next_node -= created;           // wraps to 0xFFFFFFFF after the root (node 0): not used again
+        next_node -= created;
         clusters = survivors;
         cur ^= 1;
+    }
+
+    const bool timing = getenv("ASGPU_BUILD_TIMING") != nullptr;
+    const auto t_rounds = std::chrono::steady_clock::now();
+    if (timing) fprintf(stderr, "asgpu build:   clustering rounds %zu, %u clusters left   %.3f s\n", round_begin.size(), clusters,
+                        std::chrono::duration<double>(t_rounds - t_begin).count());
+
+    // Top of the tree on the host: nodes 0 .. clusters - 2, breadth first.
+    ClusterTop top;
+    {
+        std::vector<float> h_cbox(size_t(clusters) * 6);
+        std::vector<uint32_t> h_cref(clusters), h_ccount(clusters);
+        if (cuda_failed(cudaMemcpyAsync(h_cbox.data(), d_cbox[cur], size_t(clusters) * 24, cudaMemcpyDeviceToHost, stream), "D2H clusters") ||
+            cuda_failed(cudaMemcpyAsync(h_cref.data(), d_cref[cur], size_t(clusters) * 4, cudaMemcpyDeviceToHost, stream), "D2H clusters") ||
+            cuda_failed(cudaMemcpyAsync(h_ccount.data(), d_ccount[cur], size_t(clusters) * 4, cudaMemcpyDeviceToHost, stream), "D2H clusters") ||
+            cuda_failed(cudaStreamSynchronize(stream), "clusters"))
+            return false;
+        if (!build_cluster_top(h_cbox.data(), h_cref.data(), h_ccount.data(), clusters, static_cast<int>(std::max(1u, std::thread::hardware_concurrency())), top, error)) return false;
+        const uint32_t top_nodes = clusters - 1;
+        if (next_node != top_nodes - 1) { error = "device tree build: node numbering of the rounds and of the top do not meet"; return false; }
+        if (cuda_failed(cudaMemcpyAsync(d_left, top.left.data(), size_t(top_nodes) * 4, cudaMemcpyHostToDevice, stream), "H2D top") ||
+            cuda_failed(cudaMemcpyAsync(d_right, top.right.data(), size_t(top_nodes) * 4, cudaMemcpyHostToDevice, stream), "H2D top") ||
+            cuda_failed(cudaMemcpyAsync(d_leaves, top.leaves.data(), size_t(top_nodes) * 4, cudaMemcpyHostToDevice, stream), "H2D top") ||
+            cuda_failed(cudaMemcpyAsync(d_node_boxes, top.boxes.data(), size_t(top_nodes) * 24, cudaMemcpyHostToDevice, stream), "H2D top"))
+            return false;
     }
 
     // Leaf ranges, root first (the two words stay alive until the final synchronisation below).
@@ -279,7 +323,12 @@ bool ploc_topology_device(const float* boxes, size_t n, const float root_lo[3], 
     if (cuda_failed(cudaMemcpyAsync(d_first, &root_range[0], 4, cudaMemcpyHostToDevice, stream), "H2D root range") ||
         cuda_failed(cudaMemcpyAsync(d_last, &root_range[1], 4, cudaMemcpyHostToDevice, stream), "H2D root range"))
         return false;
-    for (size_t k = round_begin.size(); k-- > 0; )
+    if (timing) fprintf(stderr, "asgpu build:   sweep SAH over the clusters (host)          %.3f s\n",
+                        std::chrono::duration<double>(std::chrono::steady_clock::now() - t_rounds).count());
+    for (size_t l = 0; l + 1 < top.level_begin.size(); ++l)     // the top, level by level (parents first)
+        ploc_ranges_kernel<<<grid_for(top.level_begin[l + 1] - top.level_begin[l]), PlocThreads, 0, stream>>>(top.level_begin[l], top.level_begin[l + 1], d_left, d_right,
+                                                                                                              d_leaves, d_first, d_last, d_sorted_ids, d_order);
+    for (size_t k = round_begin.size(); k-- > 0; )              // then the rounds, last round first
         ploc_ranges_kernel<<<grid_for(round_end[k] - round_begin[k]), PlocThreads, 0, stream>>>(round_begin[k], round_end[k], d_left, d_right, d_leaves,
                                                                                                 d_first, d_last, d_sorted_ids, d_order);
     if (cuda_failed(cudaGetLastError(), "kernel launch")) return false;

@@ -932,6 +932,115 @@ bool check_desc(const asgpu_scene_desc& d, std::string& error)
 }   // anonymous namespace
 
 //
+// Top of a clustered device build (ploc.cu): sweep SAH over the clusters the rounds left.
+//
+// Agglomeration is good at the bottom of a tree and poor at its top (greedy merges of ever larger
+// clusters: +19 % / +32 % wide-node visits against the sweep tree on the C2 grid, incoherent /
+// coherent rays), the sweep SAH is the other way round (its cost is in the many small nodes).  So
+// the device rounds stop when n / PlocTopRatio clusters are left and this builder -- the product's
+// own sweep SAH, the reference's partitioner (bvh_sahpartitioner.h:99-170) -- builds the top over
+// their boxes.  Nodes are numbered breadth first (root 0, parents before children, every level a
+// contiguous index range): the numbering the clustering rounds continue downwards from.
+//
+
+bool build_cluster_top(const float* cbox, const uint32_t* cref, const uint32_t* ccount, const size_t count, const int threads,
+                       ClusterTop& out, std::string& error)
+{
+    out.left.clear(); out.right.clear(); out.leaves.clear(); out.boxes.clear(); out.level_begin.clear();
+    if (count < 2) { error = "cluster top: fewer than two clusters"; return false; }
+    std::vector<BoundsF> boxes(count);
+    for (size_t i = 0; i < count; ++i)
+        for (int a = 0; a < 3; ++a) { boxes[i].lo[a] = cbox[i * 6 + a]; boxes[i].hi[a] = cbox[i * 6 + 3 + a]; }
+    AsNodeVector tree;
+    SweepBuilder<float> builder(boxes, 1, 0.0f, 1.0f, threads);
+    builder.build(tree);
+    const std::vector<uint32_t>& order = builder.ordering();
+
+    // A subtree of the top is a node of the sweep tree, or (where the sweep made a leaf of several
+    // clusters: degenerate boxes) a range of its ordering that is halved until single clusters remain.
+    struct Task { uint32_t node; uint32_t begin, end; };        // node != None: sweep node; else the range [begin, end)
+    const uint32_t NoNode = 0xFFFFFFFFu;
+    auto task_of = [&tree, NoNode](const uint32_t node) -> Task
+    {
+        const AsNode& nd = tree[node];
+        if (nd.item_count == 0xFFFFFFFFu) return Task{ node, 0u, 0u };
+        return Task{ NoNode, nd.index, nd.index + nd.item_count };
+    };
+    auto is_cluster = [NoNode](const Task& t) { return t.node == NoNode && t.end - t.begin == 1; };
+
+    // Pass 1, breadth first: indices and children.
+    std::vector<Task> tasks;                    // interior nodes of the top, in index order
+    std::vector<Task> kids;                     // two per interior node
+    const Task root = task_of(0);
+    if (is_cluster(root)) { error = "cluster top: the sweep left one cluster"; return false; }
+    tasks.push_back(root);
+    out.level_begin.push_back(0);
+    size_t level_end = 1;
+    for (size_t i = 0; i < tasks.size(); ++i)
+    {
+        if (i == level_end) { out.level_begin.push_back(static_cast<uint32_t>(i)); level_end = tasks.size(); }
+        const Task t = tasks[i];
+        Task child[2];
+        if (t.node != NoNode)
+        {
+            child[0] = task_of(tree[t.node].index);
+            child[1] = task_of(tree[t.node].index + 1);
+        }
+        else
+        {
+            const uint32_t mid = t.begin + (t.end - t.begin) / 2;
+            child[0] = Task{ NoNode, t.begin, mid };
+            child[1] = Task{ NoNode, mid, t.end };
+        }
+        for (int side = 0; side < 2; ++side)
+        {
+            kids.push_back(child[side]);
+            if (!is_cluster(child[side])) tasks.push_back(child[side]);
+        }
+    }
+    out.level_begin.push_back(static_cast<uint32_t>(tasks.size()));
+    if (tasks.size() != count - 1) { error = "cluster top: node count does not match the cluster count"; return false; }
+
+    // Child references: interior children were appended in the order they were met.
+    const size_t nodes = tasks.size();
+    out.left.resize(nodes); out.right.resize(nodes); out.leaves.assign(nodes, 0); out.boxes.assign(nodes * 6, 0.0f);
+    uint32_t next_interior = 1;
+    for (size_t i = 0; i < nodes; ++i)
+        for (int side = 0; side < 2; ++side)
+        {
+            const Task& c = kids[i * 2 + side];
+            const uint32_t ref = is_cluster(c) ? cref[order[c.begin]] : next_interior++;
+            (side == 0 ? out.left : out.right)[i] = ref;
+        }
+
+    // Pass 2, children before parents (children have higher indices): leaf counts and boxes.
+    for (size_t i = nodes; i-- > 0; )
+    {
+        float* box = &out.boxes[i * 6];
+        uint32_t leaves = 0;
+        for (int side = 0; side < 2; ++side)
+        {
+            const Task& c = kids[i * 2 + side];
+            const float* src;
+            if (is_cluster(c)) { const uint32_t k = order[c.begin]; src = cbox + size_t(k) * 6; leaves += ccount[k]; }
+            else
+            {
+                const uint32_t child = side == 0 ? out.left[i] : out.right[i];
+                src = &out.boxes[size_t(child) * 6];
+                leaves += out.leaves[child];
+            }
+            for (int a = 0; a < 3; ++a)
+            {
+                box[a] = side == 0 ? src[a] : std::min(box[a], src[a]);
+                box[3 + a] = side == 0 ? src[3 + a] : std::max(box[3 + a], src[3 + a]);
+            }
+        }
+        out.leaves[i] = leaves;
+    }
+    return true;
+}
+
+//
 // Linear BVH -> reference node format.
 //
 // The topology arrives from lbvh.cu (or its host simulation); this lays it out exactly like

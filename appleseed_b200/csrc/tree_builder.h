@@ -94,6 +94,19 @@ typedef bool (*LbvhTopologyFn)(const float* boxes, size_t n, const float root_lo
 bool lbvh_topology_device(const float* boxes, size_t n, const float root_lo[3], const float root_hi[3], void* context,
                           LbvhTopology& out, std::string& error);
 
+// Top of a clustered build: a sweep-SAH tree over the `count` clusters the clustering rounds left
+// (boxes lo[3] hi[3], the reference each cluster's subtree is known by, its leaf count).  Nodes are
+// numbered breadth first: node i of count - 1, root 0, level l = [level_begin[l], level_begin[l + 1]);
+// a child reference is a node of the top (an index below count - 1) or a cluster's own reference.
+struct ClusterTop
+{
+    std::vector<uint32_t>   left, right, leaves, level_begin;
+    std::vector<float>      boxes;
+};
+const uint32_t PlocTopRatio = 8;       // the rounds stop at n / PlocTopRatio clusters (at least 2)
+bool build_cluster_top(const float* cbox, const uint32_t* cref, const uint32_t* ccount, size_t count, int threads,
+                       ClusterTop& out, std::string& error);
+
 // The product's default LbvhTopologyFn (ploc.cu): parallel locally-ordered clustering over the same
 // Morton order -- surface-area driven topology, same output arrays.  ASGPU_PLOC_RADIUS (1..32,
 // default 16) sets the search radius.

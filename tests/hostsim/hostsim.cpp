@@ -122,8 +122,9 @@ static bool lbvh_topology_host(const float* boxes, size_t n, const float root_lo
 }
 
 // Sequential host run of ploc_core.h -- what ploc.cu computes with one thread per cluster: the same
-// rounds (nearest / fate / prefix sum / merge), the same node numbering (n - 2 downwards, in cluster
-// order within a round), the same hand-down of the leaf ranges.
+// rounds (nearest / fate / prefix sum / merge) down to n / PlocTopRatio clusters, the same sweep-SAH top over
+// them (build_cluster_top, the product's own function), the same node numbering (the rounds from n - 2
+// downwards in cluster order, the top breadth first from 0), the same hand-down of the leaf ranges.
 static int g_ploc_radius = 16;
 
 static bool ploc_topology_host(const float* boxes, size_t n, const float root_lo[3], const float root_hi[3], void*, LbvhTopology& out, std::string& error)
@@ -152,7 +153,9 @@ static bool ploc_topology_host(const float* boxes, size_t n, const float root_lo
     }
     std::vector<std::pair<uint32_t, uint32_t>> rounds;
     uint32_t clusters = static_cast<uint32_t>(n), next_node = static_cast<uint32_t>(n) - 2;
-    while (clusters > 1)
+    // The rounds stop at n / PlocTopRatio clusters; the top over them is the sweep SAH's (build_cluster_top).
+    const uint32_t stop_at = std::max<uint32_t>(2u, static_cast<uint32_t>(n / PlocTopRatio));
+    while (clusters > stop_at)
     {
         nearest.resize(clusters);
         const float* base = cbox.data();
@@ -191,7 +194,30 @@ static bool ploc_topology_host(const float* boxes, size_t n, const float root_lo
         clusters = static_cast<uint32_t>(oref.size());
         cbox.swap(obox); cref.swap(oref); ccount.swap(ocount);
     }
+    // Top of the tree: nodes 0 .. clusters - 2 (the rounds used n - 2 down to clusters - 1).
+    uint32_t top_nodes = 0;
+    if (clusters > 1)
+    {
+        ClusterTop top;
+        if (!build_cluster_top(cbox.data(), cref.data(), ccount.data(), clusters, 2, top, error)) return false;
+        top_nodes = clusters - 1;
+        if (next_node != top_nodes - 1) { error = "node numbering of the rounds and of the top do not meet"; return false; }
+        for (uint32_t i = 0; i < top_nodes; ++i)
+        {
+            out.left[i] = top.left[i]; out.right[i] = top.right[i]; leaves[i] = top.leaves[i];
+            for (int k = 0; k < 6; ++k) out.node_boxes[size_t(i) * 6 + k] = top.boxes[size_t(i) * 6 + k];
+        }
+    }
     out.first[0] = 0; out.last[0] = static_cast<uint32_t>(n) - 1;
+    for (uint32_t node = 0; node < top_nodes; ++node)
+    {
+        const uint32_t f = out.first[node], e = out.last[node], l = out.left[node], r = out.right[node];
+        const uint32_t left_leaves = (l & LbvhLeafFlag) ? 1u : leaves[l];
+        if (l & LbvhLeafFlag) { out.order[f] = sorted_ids[l & ~LbvhLeafFlag]; out.left[node] = f | LbvhLeafFlag; }
+        else { out.first[l] = f; out.last[l] = f + left_leaves - 1; }
+        if (r & LbvhLeafFlag) { out.order[e] = sorted_ids[r & ~LbvhLeafFlag]; out.right[node] = e | LbvhLeafFlag; }
+        else { out.first[r] = f + left_leaves; out.last[r] = e; }
+    }
     for (size_t k = rounds.size(); k-- > 0; )
         for (uint32_t node = rounds[k].first; node < rounds[k].second; ++node)
         {

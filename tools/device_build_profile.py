@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""Times asgpu_trees_build (sweep SAH, host) against asgpu_trees_build_on_device (lbvh.cu) on the
-C2 mesh (and, with --c4, the 2 M moving-triangle mesh).  Run it under
+"""Times asgpu_trees_build (sweep SAH, host) against asgpu_trees_build_on_device (ploc.cu / lbvh.cu) on the
+C2 mesh (and, with --c3 / --c4, the 10 M-triangle terrain / the 2 M moving-triangle mesh).  Run it under
 `ncu --metrics gpu__time_duration.sum` for the launch list of the device build."""
 import os
 import sys
@@ -17,6 +17,8 @@ def main():
     torch.cuda.init()
     torch.zeros(1, device="cuda")
     which = [("c2", scenes.scene_c2())]
+    if "--c3" in sys.argv:
+        which.append(("c3", scenes.scene_c3()))
     if "--c4" in sys.argv:
         which.append(("c4", scenes.scene_c4()))
     reps = 1 if "--once" in sys.argv else 3
