@@ -12,6 +12,7 @@
 #include <memory>
 #include <new>
 #include <string>
+#include <utility>
 #include <vector>
 
 namespace asgpu
@@ -33,6 +34,13 @@ struct Aligned64Allocator
         return static_cast<T*>(p);
     }
     void deallocate(T* p, size_t) { free(p); }
+    // resize(n) default-initialises (no zero fill, no first touch of the pages by one thread): the
+    // builder writes every node itself, from several threads.  Construction from arguments is the usual one.
+    template <typename U> void construct(U* p) { ::new (static_cast<void*>(p)) U; }
+    template <typename U, typename A, typename... Args> void construct(U* p, A&& a, Args&&... args)
+    {
+        ::new (static_cast<void*>(p)) U(std::forward<A>(a), std::forward<Args>(args)...);
+    }
     template <typename U> bool operator==(const Aligned64Allocator<U>&) const { return true; }
     template <typename U> bool operator!=(const Aligned64Allocator<U>&) const { return false; }
 };

@@ -41,6 +41,23 @@ def test_parallel_subtree_stitching_matches_serial_order(orc):
     check_against(orc, desc, 1)
 
 
+@pytest.mark.parametrize("threads", [6, 16, 48])
+def test_chunked_sweeps_of_big_ranges_match_the_serial_ones(orc, asref, threads, monkeypatch):
+    """Ranges above ASGPU_PARALLEL_SWEEP_MIN items (262 144 by default: the first levels of a
+    multi-million-triangle tree) are swept, repartitioned and bounded in chunks by several threads
+    per axis, and the two halves of a top node are expanded concurrently.  With the threshold
+    lowered the same code runs over several levels of a 135 k-triangle mesh: the tree must stay the
+    reference's byte for byte, whatever the thread count (= chunk boundaries)."""
+    monkeypatch.setenv("ASGPU_PARALLEL_SWEEP_MIN", "3000")
+    desc = scenes.scene_c2(260)
+    check_against(orc, desc, threads)
+    check_against(asref, scenes.scene_c4(120, msc=2), threads)
+
+
+def test_chunked_sweeps_at_the_default_threshold(orc):
+    check_against(orc, scenes.scene_c2(380), 12)        # 288 800 triangles: the root range is above the default threshold
+
+
 def test_many_instances_top_level_tree(orc):
     check_against(orc, scenes.scene_c3(8, 12), 2)
 
