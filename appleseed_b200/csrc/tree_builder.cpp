@@ -1240,7 +1240,7 @@ bool build_cluster_top(const float* cbox, const uint32_t* cref, const uint32_t* 
 // so that motion boxes, leaf payloads and the flattener see a tree of the usual shape.
 //
 
-static bool emit_lbvh(const LbvhTopology& t, const std::vector<BoundsF>& boxes, const size_t max_leaf_size, AsNodeVector& nodes, std::string& error)
+static bool emit_lbvh(const LbvhTopology& t, const std::vector<BoundsF>& boxes, const size_t max_leaf_size, AsNodeVector& nodes, std::string& error, const int threads)
 {
     const size_t n = boxes.size();
     if (t.order.size() != n || t.left.size() != n - 1 || t.right.size() != n - 1 || t.first.size() != n - 1 || t.last.size() != n - 1 ||
@@ -1269,54 +1269,91 @@ static bool emit_lbvh(const LbvhTopology& t, const std::vector<BoundsF>& boxes, 
         return b;
     };
 
-    struct Task { size_t slot; uint32_t ref; uint32_t first, last; uint32_t depth; };
-    AsNode blank; std::memset(&blank, 0, sizeof(blank));
-    nodes.clear();
-    nodes.reserve(2 * n / (max_leaf_size ? max_leaf_size : 1) + 2);
-    nodes.push_back(blank);
+    // Pass 1, one thread: the depth-first walk that gives every node its place (a node's children
+    // follow it as a pair, then the whole left subtree, then the right one) and checks the hierarchy.
+    // Pass 2, all threads: the nodes themselves (child boxes widened to double, 128 bytes written
+    // each) into an array that is not zero-filled first.
+    struct Task { uint32_t slot; uint32_t ref; uint32_t first, last; uint32_t depth; };
+    struct Rec { uint32_t slot, ref, first, last, pair; };         // pair = 0xFFFFFFFF: a leaf
+    const uint32_t NoPair = 0xFFFFFFFFu;
+    if (2 * n + 2 >= NoPair) { error = "device tree build: too many nodes"; return false; }
+    // The walk reads four fields of every node it meets, in no memory order: one 16-byte record per
+    // node (gathered by all threads) costs it one cache miss instead of four.
+    struct Packed { uint32_t left, right, first, last; };
+    std::vector<Packed> packed(n - 1);
+    {
+        Packed* dst = packed.data();
+        parallel_chunks(n - 1, threads, size_t(1) << 16, [&](int, size_t begin, size_t end)
+        {
+            for (size_t i = begin; i < end; ++i) dst[i] = Packed{ t.left[i], t.right[i], t.first[i], t.last[i] };
+        });
+    }
+    std::vector<Rec> recs;
+    recs.reserve(2 * n / (max_leaf_size ? max_leaf_size : 1) + 2);
     std::vector<Task> stack;
-    stack.push_back(Task{ 0, 0u, 0u, static_cast<uint32_t>(n - 1), 1u });
+    stack.push_back(Task{ 0u, 0u, 0u, static_cast<uint32_t>(n - 1), 1u });
     size_t placed = 0;
+    uint32_t total = 1;
     while (!stack.empty())
     {
         const Task k = stack.back();
         stack.pop_back();
-        uint32_t first = k.first, last = k.last;
+        const uint32_t first = k.first, last = k.last;
         if (!(k.ref & LbvhLeafFlag))
         {
             // The range an interior node reports must be the one its parent handed down.
-            if (k.ref >= n - 1 || t.first[k.ref] != first || t.last[k.ref] != last) { error = "device tree build returned an inconsistent hierarchy"; return false; }
+            if (k.ref >= n - 1 || packed[k.ref].first != first || packed[k.ref].last != last) { error = "device tree build returned an inconsistent hierarchy"; return false; }
         }
         const size_t count = size_t(last) - first + 1;
         if ((k.ref & LbvhLeafFlag) || count <= max_leaf_size)
         {
-            nodes[k.slot].item_count = static_cast<uint32_t>(count);
-            nodes[k.slot].index = first;
+            recs.push_back(Rec{ k.slot, k.ref, first, last, NoPair });
             placed += count;
             continue;
         }
         // The exact traversal keeps the reference's 64-entry stack (intersectionsettings.h:95).
         if (k.depth >= 64) { error = "linear BVH deeper than the 64-entry traversal stack (too many coincident centroids)"; return false; }
-        const uint32_t l = t.left[k.ref], r = t.right[k.ref];
-        const uint32_t split = (l & LbvhLeafFlag) ? (l & ~LbvhLeafFlag) : t.last[l < n - 1 ? l : 0];
+        const uint32_t l = packed[k.ref].left;
+        const uint32_t split = (l & LbvhLeafFlag) ? (l & ~LbvhLeafFlag) : packed[l < n - 1 ? l : 0].last;
         if ((!(l & LbvhLeafFlag) && l >= n - 1) || split < first || split >= last) { error = "device tree build returned an inconsistent split"; return false; }
-        const size_t pair = nodes.size();
-        nodes.push_back(blank);
-        nodes.push_back(blank);
-        AsNode& node = nodes[k.slot];
-        node.item_count = 0xFFFFFFFFu;
-        node.index = static_cast<uint32_t>(pair);
-        const BoundsD lb = child_box(l), rb = child_box(r);
-        for (int a = 0; a < 3; ++a)
-        {
-            node.bbox[a * 4 + 0] = lb.lo[a]; node.bbox[a * 4 + 2] = lb.hi[a];
-            node.bbox[a * 4 + 1] = rb.lo[a]; node.bbox[a * 4 + 3] = rb.hi[a];
-        }
+        const uint32_t pair = total;
+        total += 2;
+        recs.push_back(Rec{ k.slot, k.ref, first, last, pair });
         // Left subtree first: push right, then left.
-        stack.push_back(Task{ pair + 1, r, split + 1, last, k.depth + 1 });
+        stack.push_back(Task{ pair + 1, packed[k.ref].right, split + 1, last, k.depth + 1 });
         stack.push_back(Task{ pair, l, first, split, k.depth + 1 });
     }
     if (placed != n) { error = "device tree build lost triangles"; return false; }
+
+    nodes.clear();
+    nodes.resize(total);                    // default-initialised: first touched by the threads below
+    AsNode* out_nodes = nodes.data();
+    const Rec* all = recs.data();
+    parallel_chunks(recs.size(), threads, size_t(1) << 14, [&](int, size_t begin, size_t end)
+    {
+        for (size_t i = begin; i < end; ++i)
+        {
+            const Rec& k = all[i];
+            AsNode node; std::memset(&node, 0, sizeof(node));
+            if (k.pair == NoPair)
+            {
+                node.item_count = k.last - k.first + 1;
+                node.index = k.first;
+            }
+            else
+            {
+                node.item_count = 0xFFFFFFFFu;
+                node.index = k.pair;
+                const BoundsD lb = child_box(packed[k.ref].left), rb = child_box(packed[k.ref].right);
+                for (int a = 0; a < 3; ++a)
+                {
+                    node.bbox[a * 4 + 0] = lb.lo[a]; node.bbox[a * 4 + 2] = lb.hi[a];
+                    node.bbox[a * 4 + 1] = rb.lo[a]; node.bbox[a * 4 + 3] = rb.hi[a];
+                }
+            }
+            out_nodes[k.slot] = node;
+        }
+    });
     return true;
 }
 
@@ -1433,7 +1470,7 @@ bool build_host_trees(const asgpu_scene_desc& desc, int threads, HostTrees& out,
             if (!lbvh(&c.boxes[0].lo[0], c.boxes.size(), root.lo, root.hi, lbvh_context, topology, error)) return false;
             out.topology_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - l0).count();
             stamp("topology (device)");
-            if (!emit_lbvh(topology, c.boxes, assembly.max_leaf_size, tree.nodes, error)) return false;
+            if (!emit_lbvh(topology, c.boxes, assembly.max_leaf_size, tree.nodes, error, threads)) return false;
             stamp("emit nodes");
             propagate_motion_boxes(tree, topology.order, c);
             stamp("motion boxes");
