@@ -88,7 +88,8 @@ def test_device_trees_differ_from_the_sweep_tree_but_not_in_results(sim, orc):
     assert int(ca[3]) != int(cb[3]) and int(ca[3]) != int(cc[3])        # different trees: different node visits ...
     assert int(cb[3]) < 3 * int(ca[3])                                  # ... of comparable quality on a regular mesh
     assert int(cc[3]) < int(cb[3])                                      # clustering by surface area beats the Morton splits
-    print("binary node visits: sweep SAH %d, clustering %d, linear %d" % (int(ca[3]), int(cc[3]), int(cb[3])))
+    assert int(cc[3]) < 1.15 * int(ca[3])                               # ... and, with the sweep SAH on top, stays close to the sweep tree
+    print("binary node visits: sweep SAH %d, clustering + sweep top %d, linear %d" % (int(ca[3]), int(cc[3]), int(cb[3])))
     for h in (hb, hc):
         for k in ("t", "u", "v", "primitive_index", "prim_type"):
             assert np.array_equal(ha[k], h[k]), k
